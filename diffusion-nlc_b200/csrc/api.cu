@@ -1,0 +1,61 @@
+// Context lifetime and error reporting of the C ABI (include/nlc_b200.h).
+#include <string.h>
+
+#include "common.h"
+
+namespace nlc {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+}  // namespace nlc
+
+extern "C" {
+
+const char* nlc_last_error(void) { return nlc::g_err; }
+
+int nlc_abi_version(void) { return 1; }
+
+nlc_ctx* nlc_create(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        nlc::set_error(NLC_ECUDA, "nlc_create: CUDA device %d not available (%d visible)", device, ndev);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        nlc::set_error(NLC_ECUDA, "nlc_create: cudaGetDeviceProperties failed");
+        return nullptr;
+    }
+    if (prop.major != 10) {
+        nlc::set_error(NLC_ENOTSUP, "nlc_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+        nlc::set_error(NLC_ECUDA, "nlc_create: cuTensorMapEncodeTiled not found in the driver");
+        return nullptr;
+    }
+    nlc_ctx* ctx = new nlc_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->encode_tiled = reinterpret_cast<nlc::encode_tiled_fn>(fn);
+    return ctx;
+}
+
+void nlc_destroy(nlc_ctx* ctx) { delete ctx; }
+
+int nlc_sm_count(nlc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"

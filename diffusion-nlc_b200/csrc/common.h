@@ -1,0 +1,47 @@
+// Host-side plumbing shared by all translation units of libnlc_b200: error reporting, the context object
+// and the driver entry point used to encode TMA tensor maps (resolved at run time so the library links
+// against the CUDA runtime only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/nlc_b200.h"
+
+namespace nlc {
+
+int set_error(int code, const char* fmt, ...);
+
+#define NLC_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return nlc::set_error(NLC_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                                  __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define NLC_CHECK_LAUNCH()                                                                            \
+    do {                                                                                              \
+        cudaError_t _e = cudaGetLastError();                                                          \
+        if (_e != cudaSuccess)                                                                        \
+            return nlc::set_error(NLC_ECUDA, "kernel launch failed: %s (%s:%d)",                      \
+                                  cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+    } while (0)
+
+#define NLC_REQUIRE(cond, ...)                                        \
+    do {                                                              \
+        if (!(cond)) return nlc::set_error(NLC_EINVAL, __VA_ARGS__);  \
+    } while (0)
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+}  // namespace nlc
+
+struct nlc_ctx {
+    int device;
+    int sm_count;
+    nlc::encode_tiled_fn encode_tiled;
+};

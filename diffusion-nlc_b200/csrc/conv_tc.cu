@@ -1,0 +1,400 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA.  This is the kernel behind every 3x3 / 1x1 / strided convolution and every
+// q,k,v / proj GEMM of the three UNet families and the sigma-model; it replaces
+// the cuDNN / cuBLAS launches made by torch.nn.Conv2d in src/unet_ddim.py:99-211, src/unet_adm.py:143-305,
+// src/edm_networks.py:52-205.
+//
+// GEMM view:  D[M = B*Ho*Wo, N = Cout] = A[M, K] * W[N, K]^T,  K = sum over "segments" (tap, channel range).
+//   * activations are NHWC, so one output pixel's receptive-field slice for one tap is a contiguous
+//     128-byte run of channels: exactly one row of a K-major SWIZZLE_128B UMMA operand tile;
+//   * an M tile is a (BN images) x (BH rows) x (BW columns) brick with BN*BH*BW = 128 pixels; the TMA box
+//     for tap (dh,dw) is that brick shifted by (dh,dw): zero padding costs nothing (OOB fill), stride-2
+//     convolutions use the tensor map's traversal stride, and the nine taps re-read the brick from L2;
+//   * a ResNet block's 1x1 shortcut and a concat are just more K segments over another tensor map.
+//
+// One persistent CTA per SM, 6 warps:  warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
+// warps 2-5 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype stores).
+// smem ring of STAGES x (16 KB A + BLOCK_N*128 B W); two TMEM accumulators so the epilogue of tile i
+// overlaps the main loop of tile i+1.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace nlc {
+
+constexpr int kBlockM = 128;
+constexpr int kChunkBytes = 128;                      // one swizzle row = one K chunk
+constexpr int kAStageBytes = kBlockM * kChunkBytes;   // 16 KB
+constexpr int kThreads = 192;
+
+struct ConvSegDev {
+    int map, dh, dw, c0, nchunk;
+};
+
+struct ConvKParams {
+    CUtensorMap mapA[NLC_MAX_SRC];
+    CUtensorMap mapB;
+    int B, Ho, Wo, stride;
+    int BW, BH, BN;
+    int tiles_w, tiles_h, tiles_n;
+    int num_m_tiles, num_n_tiles, num_tiles;
+    int Cout, nseg, total_chunks;
+    ConvSegDev seg[NLC_MAX_SEG];
+    const float* bias;
+    const float* rowvec;
+    int ld_rowvec;
+    const float* resid;
+    int ld_resid;
+    float out_scale;
+    float* out_f32;
+    int ld_out_f32;
+    void* out_op;
+    int ld_out_op;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+    static constexpr int kBStageBytes = BLOCK_N * kChunkBytes;
+    static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
+    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
+    static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+};
+
+template <int BLOCK_N, bool TF32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kChunkElems = TF32 ? 32 : 64;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kStages;
+    uint64_t* tfull = bars + 2 * kStages;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < NLC_MAX_SRC; ++i) tma_prefetch_desc(&p.mapA[i]);
+        tma_prefetch_desc(&p.mapB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int n_tile = tile / p.num_m_tiles;
+                const int m_tile = tile - n_tile * p.num_m_tiles;
+                const int tn = m_tile / tiles_per_img;
+                const int rem = m_tile - tn * tiles_per_img;
+                const int th = rem / p.tiles_w;
+                const int tw = rem - th * p.tiles_w;
+                const int n0 = tn * p.BN, h0 = th * p.BH * p.stride, w0 = tw * p.BW * p.stride;
+                int kchunk = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const ConvSegDev sg = p.seg[s];
+                    for (int j = 0; j < sg.nchunk; ++j) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                        uint8_t* sb = sa + kAStageBytes;
+                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                        tma_load_4d(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
+                                    h0 + sg.dh, n0);
+                        tma_load_2d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N);
+                        ++kchunk;
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kc = 0; kc < p.total_chunks; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + kAStageBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // 4 x 32 B K-steps inside the 128 B swizzle row
+                        if (TF32)
+                            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                        else
+                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+        const int row = quad * 32 + lane;
+        const int brick = p.BW * p.BH;
+        const int bn = row / brick;
+        const int r2 = row - bn * brick;
+        const int bh = r2 / p.BW;
+        const int bw = r2 - bh * p.BW;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int n_tile = tile / p.num_m_tiles;
+            const int m_tile = tile - n_tile * p.num_m_tiles;
+            const int tn = m_tile / tiles_per_img;
+            const int rem = m_tile - tn * tiles_per_img;
+            const int th = rem / p.tiles_w;
+            const int tw = rem - th * p.tiles_w;
+            const int n = tn * p.BN + bn;
+            const int ho = th * p.BH + bh;
+            const int wo = tw * p.BW + bw;
+            const bool valid = n < p.B;
+            const size_t pix = (static_cast<size_t>(n) * p.Ho + ho) * p.Wo + wo;
+
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c, v);
+                tmem_ld_wait();
+                if (valid) {
+                    const int col0 = n_tile * BLOCK_N + c;
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldg(b4 + i);
+                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (p.rowvec) {
+                        const float4* b4 =
+                            reinterpret_cast<const float4*>(p.rowvec + static_cast<size_t>(n) * p.ld_rowvec + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldg(b4 + i);
+                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (p.resid) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.resid + pix * p.ld_resid + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldg(b4 + i);
+                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (p.out_scale != 1.0f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
+                    }
+                    if (p.out_f32) {
+                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_out_f32 + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    }
+                    if (p.out_op) {
+                        if (TF32) {
+                            float4* o4 =
+                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + pix * p.ld_out_op + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                o4[i] = make_float4(round_tf32(f[4 * i]), round_tf32(f[4 * i + 1]),
+                                                    round_tf32(f[4 * i + 2]), round_tf32(f[4 * i + 3]));
+                        } else {
+                            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_op) +
+                                                                 pix * p.ld_out_op + col0);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                o4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
+                                                   pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
+                                                   pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
+                                                   pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+template <int BLOCK_N, bool TF32>
+static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    static bool configured = false;
+    if (!configured) {
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            Cfg::kSmemBytes));
+        configured = true;
+    }
+    conv_tc_kernel<BLOCK_N, TF32><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && d, "nlc_conv_tc: null argument");
+    NLC_REQUIRE(d->dtype == NLC_BF16 || d->dtype == NLC_F32, "nlc_conv_tc: dtype must be NLC_BF16 or NLC_F32");
+    const bool tf32 = d->dtype == NLC_F32;
+    const int esz = tf32 ? 4 : 2;
+    const int chunk = kChunkBytes / esz;
+    NLC_REQUIRE(d->nsrc >= 1 && d->nsrc <= NLC_MAX_SRC, "nlc_conv_tc: nsrc %d out of range", d->nsrc);
+    NLC_REQUIRE(d->nseg >= 1 && d->nseg <= NLC_MAX_SEG, "nlc_conv_tc: nseg %d out of range", d->nseg);
+    NLC_REQUIRE(d->stride == 1 || d->stride == 2, "nlc_conv_tc: stride %d unsupported", d->stride);
+    NLC_REQUIRE(is_pow2(d->Ho) && is_pow2(d->Wo), "nlc_conv_tc: output %dx%d must be powers of two", d->Ho, d->Wo);
+    NLC_REQUIRE(d->B >= 1 && d->Cout % 64 == 0, "nlc_conv_tc: Cout %d must be a multiple of 64", d->Cout);
+    NLC_REQUIRE(d->out_f32 || d->out_op, "nlc_conv_tc: no output requested");
+    NLC_REQUIRE(!d->out_f32 || (d->ld_out_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out_f32) & 15) == 0),
+                "nlc_conv_tc: out_f32 must be 16-byte aligned with ld %% 4 == 0");
+    NLC_REQUIRE(!d->out_op || ((d->ld_out_op * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(d->out_op) & 15) == 0),
+                "nlc_conv_tc: out_op must be 16-byte aligned");
+    NLC_REQUIRE(!d->resid || (d->ld_resid % 4 == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0),
+                "nlc_conv_tc: resid must be 16-byte aligned with ld %% 4 == 0");
+    NLC_REQUIRE(!d->rowvec || (d->ld_rowvec % 4 == 0 && (reinterpret_cast<uintptr_t>(d->rowvec) & 15) == 0),
+                "nlc_conv_tc: rowvec must be 16-byte aligned with ld %% 4 == 0");
+    NLC_REQUIRE(!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "nlc_conv_tc: bias must be 16-byte aligned");
+
+    ConvKParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = d->B, p.Ho = d->Ho, p.Wo = d->Wo, p.stride = d->stride;
+    p.BW = d->Wo < kBlockM ? d->Wo : kBlockM;
+    p.BH = d->Ho < kBlockM / p.BW ? d->Ho : kBlockM / p.BW;
+    p.BN = kBlockM / (p.BW * p.BH);
+    p.tiles_w = d->Wo / p.BW;
+    p.tiles_h = d->Ho / p.BH;
+    p.tiles_n = (d->B + p.BN - 1) / p.BN;
+    p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    p.Cout = d->Cout;
+
+    int block_n = 64;
+    if (d->Cout % 256 == 0 && p.num_m_tiles * (d->Cout / 256) >= ctx->sm_count)
+        block_n = 256;
+    else if (d->Cout % 128 == 0 && p.num_m_tiles * (d->Cout / 128) >= ctx->sm_count)
+        block_n = 128;
+    p.num_n_tiles = d->Cout / block_n;
+    p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+    int ktot = 0;
+    p.nseg = d->nseg;
+    for (int s = 0; s < d->nseg; ++s) {
+        const nlc_kseg& sg = d->seg[s];
+        NLC_REQUIRE(sg.src >= 0 && sg.src < d->nsrc, "nlc_conv_tc: segment %d names source %d", s, sg.src);
+        NLC_REQUIRE(sg.nch > 0 && sg.nch % chunk == 0 && sg.c0 % 8 == 0 && sg.c0 + sg.nch <= d->src[sg.src].C,
+                    "nlc_conv_tc: segment %d covers channels [%d,%d) of %d; need multiples of %d", s, sg.c0,
+                    sg.c0 + sg.nch, d->src[sg.src].C, chunk);
+        p.seg[s] = ConvSegDev{sg.src, sg.dh, sg.dw, sg.c0, sg.nch / chunk};
+        ktot += sg.nch;
+    }
+    p.total_chunks = ktot / chunk;
+
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    for (int s = 0; s < d->nsrc; ++s) {
+        const nlc_operand& o = d->src[s];
+        NLC_REQUIRE(o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && (static_cast<size_t>(o.ld) * esz) % 16 == 0,
+                    "nlc_conv_tc: source %d must be 16-byte aligned (ptr and row pitch)", s);
+        NLC_REQUIRE(o.B == d->B, "nlc_conv_tc: source %d batch %d != %d", s, o.B, d->B);
+        cuuint64_t gdim[4] = {(cuuint64_t)o.C, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)o.B};
+        cuuint64_t gstr[3] = {(cuuint64_t)o.ld * esz, (cuuint64_t)o.W * o.ld * esz, (cuuint64_t)o.H * o.W * o.ld * esz};
+        cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)(p.BW * d->stride), (cuuint32_t)(p.BH * d->stride),
+                             (cuuint32_t)p.BN};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+        CUresult r = ctx->encode_tiled(&p.mapA[s], dt, 4, const_cast<void*>(o.ptr), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(A%d) failed with %d", s, (int)r);
+    }
+    for (int s = d->nsrc; s < NLC_MAX_SRC; ++s) p.mapA[s] = p.mapA[0];
+    {
+        NLC_REQUIRE(d->weight && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "nlc_conv_tc: weight unaligned");
+        cuuint64_t gdim[2] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)ktot * esz};
+        cuuint32_t box[2] = {(cuuint32_t)chunk, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = ctx->encode_tiled(&p.mapB, dt, 2, const_cast<void*>(d->weight), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    p.bias = d->bias, p.rowvec = d->rowvec, p.ld_rowvec = d->ld_rowvec;
+    p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
+    p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;
+
+    const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+    if (tf32) {
+        if (block_n == 256) return launch_conv<256, true>(p, grid, stream);
+        if (block_n == 128) return launch_conv<128, true>(p, grid, stream);
+        return launch_conv<64, true>(p, grid, stream);
+    }
+    if (block_n == 256) return launch_conv<256, false>(p, grid, stream);
+    if (block_n == 128) return launch_conv<128, false>(p, grid, stream);
+    return launch_conv<64, false>(p, grid, stream);
+}

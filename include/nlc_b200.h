@@ -1,0 +1,230 @@
+/*
+ * nlc_b200 — C ABI of the B200-native NLC sampling hot path.
+ *
+ * Every entry point below replaces a piece of PyTorch-eager work that the reference
+ * (Walleclipse/Diffusion-NLC, pure Python) performs inside its per-timestep loop; the
+ * reference has no FFI of its own, so each declaration cites the Python seam it stands
+ * behind (file:line relative to the reference tree).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; all pointers are DEVICE pointers unless a name ends in _host
+ *   - every call enqueues on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     never allocates caller-visible memory
+ *   - returns 0 on success, a negative NLC_E* code otherwise; nlc_last_error() gives the text
+ *   - activations are NHWC ("pixel rows"): element (n,h,w,c) lives at ptr[((n*H+h)*W+w)*ld + c],
+ *     ld >= C lets a tensor be a channel slice of a wider (concatenated) buffer
+ *   - one nlc_ctx per (process, device); not thread-safe (the reference is one thread per GPU)
+ */
+#ifndef NLC_B200_H
+#define NLC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NLC_OK 0
+#define NLC_EINVAL (-1)   /* bad argument / unsupported shape */
+#define NLC_ECUDA (-2)    /* CUDA runtime / driver error      */
+#define NLC_ENOTSUP (-3)  /* valid but not implemented        */
+
+#define NLC_F32 0
+#define NLC_BF16 1
+
+typedef struct nlc_ctx nlc_ctx;
+
+const char* nlc_last_error(void);
+int nlc_abi_version(void);
+nlc_ctx* nlc_create(int device);
+void nlc_destroy(nlc_ctx* ctx);
+int nlc_sm_count(nlc_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * N1/N2/N3 building blocks — replace torch.nn.Conv2d / GroupNorm / attention launches inside
+ * UNetModel.forward / encode (src/unet_ddim.py:323-393, src/unet_adm.py:636-693,
+ * src/edm_networks.py:835-909) and SigmaModel.forward (src/unet_ddim.py:521-529).
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+    const void* ptr; /* operand tensor, bf16 (dtype NLC_BF16) or fp32 holding tf32-rounded values */
+    int B, H, W, C;  /* logical NHWC extent                                                        */
+    int ld;          /* elements between consecutive pixels                                        */
+} nlc_operand;
+
+typedef struct {
+    int src;    /* index into src[]                                              */
+    int dh, dw; /* input pixel = stride * output pixel + (dh, dw); pad by OOB=0  */
+    int c0;     /* first channel of the source covered by this segment           */
+    int nch;    /* channels covered (multiple of the 128-byte K chunk)           */
+} nlc_kseg;
+
+#define NLC_MAX_SRC 3
+#define NLC_MAX_SEG 24
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores:
+ *   out[n,ho,wo,:] = scale * ( sum_seg W_seg . src[seg][n, s*ho+dh, s*wo+dw, c0:c0+nch]
+ *                              + bias + rowvec[n,:] + resid[n,ho,wo,:] )
+ * A 3x3 conv is nine segments, a 1x1 conv one, a ResNet block's 1x1 shortcut is one extra segment over a
+ * second source (torch.nn.Conv2d calls at src/unet_ddim.py:109-135,141,148-156). `weight` is
+ * [Cout][sum nch] in the operand dtype, K ordered like seg[]. */
+typedef struct {
+    int dtype; /* NLC_BF16 (kind::f16) or NLC_F32 (kind::tf32) */
+    int nsrc;
+    nlc_operand src[NLC_MAX_SRC];
+    int nseg;
+    nlc_kseg seg[NLC_MAX_SEG];
+    const void* weight;
+    int Cout;
+    int stride;
+    int B, Ho, Wo;
+    const float* bias;   /* [Cout] or NULL                          */
+    const float* rowvec; /* [B, ld_rowvec] per-sample add or NULL   */
+    int ld_rowvec;
+    const float* resid; /* NHWC fp32 [B,Ho,Wo,ld_resid] or NULL    */
+    int ld_resid;
+    float out_scale;
+    float* out_f32; /* NHWC fp32 or NULL                       */
+    int ld_out_f32;
+    void* out_op; /* NHWC operand-dtype copy (bf16 / tf32-rounded fp32) or NULL */
+    int ld_out_op;
+} nlc_conv_desc;
+
+int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);
+
+/* Direct (CUDA-core, fp32) convolution for the layers whose channel counts cannot fill a tensor-core tile:
+ * conv_in (3 -> C) reading the sampler's NCHW fp32 image with the per-sample input scale 1/sqrt(sigma^2+1)
+ * folded in (src/experiments.py:273-282,295-302), and conv_out (C -> 3|6) writing NCHW fp32.
+ * weight is the torch layout [Cout][Cin][3][3] fp32. */
+int nlc_conv_in_nchw(nlc_ctx* ctx, const float* x_nchw, const float* in_scale /*[B] or NULL*/, int B, int Cin, int H,
+                     int W, const float* weight, const float* bias, int Cout, float* out_f32, int ld_out_f32,
+                     void* out_op, int ld_out_op, int op_dtype, void* stream);
+int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int Cin, int H, int W,
+                      const float* weight, const float* bias, int Cout, float* out_nchw, void* stream);
+
+/* GroupNorm (+ optional SiLU, + optional per-sample scale/shift) producing the next conv's operand.
+ * Replaces Normalize/GroupNorm32 + nonlinearity (src/unet_ddim.py:54-55,139-146; src/nn_util.py:17-19;
+ * src/unet_adm.py:236-252).  Statistics are fp32 Welford partials per (sample, pixel chunk, group), merged by
+ * the apply pass.  x is NHWC fp32 with C channels in `groups` groups.
+ *   y = ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c]  -> SiLU (if silu) -> operand dtype */
+int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int HW, int C, int groups, float eps,
+                  const float* gamma, const float* beta, const float* scale, const float* shift, int ld_ss,
+                  int silu, void* y_op, int ld_y, int op_dtype, float* workspace /* >= nlc_groupnorm_ws floats */,
+                  void* stream);
+size_t nlc_groupnorm_ws(int B, int HW, int C, int groups);
+
+/* fp32 NHWC -> operand dtype, optionally nearest-neighbour x2 upsampled (Upsample.forward,
+ * src/unet_ddim.py:69-74) or 2x2 average pooled (src/unet_adm.py:134-140). mode: 0 copy, 1 up2, 2 avgpool2 */
+int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int mode, float* y_f32,
+                 int ld_y_f32, void* y_op, int ld_y_op, int op_dtype, void* stream);
+
+/* Fused softmax attention over NHWC tokens: qkv is [B, T, ld] with q at column q_off + h*dh, etc.
+ * Replaces bmm/softmax/bmm (src/unet_ddim.py:193-207), QKVAttention(Legacy) (src/unet_adm.py:328-389),
+ * AttentionOp (src/edm_networks.py:124-130).  softmax(scale * q k^T) v, fp32 math, output operand dtype. */
+int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld, int q_off, int k_off, int v_off,
+                  int head_stride, int B, int T, int heads, int dh, float scale, void* out_op, int ld_out,
+                  void* stream);
+
+/* Small dense layers (timestep-embedding MLP, per-block temb projections, sigma head).
+ * y[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] );  act: 0 none, 1 SiLU, 2 GELU(erf).
+ * src/unet_ddim.py:327-330,143; src/unet_adm.py:650,199-205. */
+int nlc_linear(nlc_ctx* ctx, const float* x, int ld_x, int B, int K, const float* W, const float* bias, int N,
+               int act_in, int act_out, float* y, int ld_y, void* stream);
+
+/* Sinusoidal timestep embedding. style 0: DDIM sin||cos with log(1e4)/(half-1) (src/unet_ddim.py:28-46);
+ * style 1: ADM cos||sin with log(max_period)/half (src/nn_util.py:103-121);
+ * style 2: EDM PositionalEmbedding cos||sin with endpoint option (src/edm_networks.py:212-225). */
+int nlc_timestep_embedding(nlc_ctx* ctx, const float* t, int B, int dim, int style, float max_period,
+                           int endpoint, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * D1 / S2 / S3 / S4 / S5 — the sampler arithmetic around the networks.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Per-sample L2 norm over d contiguous floats: vector_norm (src/utils.py:7-9). out[b] = ||x[b,:]||_2 */
+int nlc_row_norm(nlc_ctx* ctx, const float* x, int B, int d, float* out, void* stream);
+
+/* refine_prior_sigma + searchsorted (src/experiments.py:401-419, src/schedulers.py:185-190):
+ *   nrm = ||x_b||/sqrt(d); sigma_b = clamp(sigma_in_b, max(nrm-norm_max,0), nrm+norm_min) when refine != 0
+ *   t_b = clamp(first i with table[i] >= sigma_b  (- time_shift if min_b t > 0), 0, 1000)
+ * sigma_in / sigma_prev_in have `n_sigma_in` entries (1 = broadcast scalar, B = per sample). */
+int nlc_refine_sigma(nlc_ctx* ctx, const float* xt, int B, int d, const float* sigma_in, int n_sigma_in,
+                     float norm_min, float norm_max, int refine, const float* sigma_table, int n_table,
+                     int time_shift, float* sigma_out, float* t_out, float* in_scale_out, void* stream);
+
+/* NLC correction (src/experiments.py:424-431): sigma_hat = sigma*(1+r); sigma_prev_hat = sigma_hat*sigma_prev/sigma
+ * (style pred) or sigma_prev (pred_partial); t_hat = clamp(searchsorted(table, sigma_hat)); in_scale = 1/sqrt(s^2+1) */
+int nlc_sigma_correct(nlc_ctx* ctx, const float* r, const float* sigma, const float* sigma_prev, int n_prev, int B,
+                      int update_prev, const float* sigma_table, int n_table, float* sigma_hat,
+                      float* sigma_prev_hat, float* t_hat, float* in_scale_out, void* stream);
+
+/* eps normalisation (src/utils.py:11-16): eps_b <- sqrt(d) * eps_b / max(||eps_b||, 1e-12), in place. */
+int nlc_normalize_rows(nlc_ctx* ctx, float* x, int B, int d, void* stream);
+
+#define NLC_SCHED_DDIM 0
+#define NLC_SCHED_DDIM_SIMPLE 1
+#define NLC_SCHED_DDIM_SIMPLE_ORIG 2
+#define NLC_SCHED_DDIM_SIMPLE_DRAG 3
+#define NLC_SCHED_DDPM 4
+#define NLC_SCHED_DDPM_ORIG 5
+#define NLC_SCHED_DDIM_ORIG 6
+
+#define NLC_CLIP_NONE 0
+#define NLC_CLIP_CLAMP 1
+
+/* x0_hat = clip(x_t - sigma_b * eps)  — Scheduler.pred_xstart + clamp clip (src/schedulers.py:407-409,
+ * src/experiments.py:186-188). */
+int nlc_pred_xstart(nlc_ctx* ctx, const float* xt, const float* eps, const float* sigma, int n_sigma, int B, int d,
+                    int clip, float* x0, void* stream);
+
+/* x_{t-1} for every pred_xprev variant (src/schedulers.py:432-449,465-473,487-496,505-514,548-562,581-599,
+ * 609-627) including get_eps_logvar (:367-390).  logvar_mode: 0 none, 1 learned (v given), 2 fixedsmall,
+ * 3 fixedlarge.  noise may be NULL when eta == 0.  Also returns ||x_{t-1}|| per sample and a NaN flag. */
+int nlc_pred_xprev(nlc_ctx* ctx, int sched, float eta, const float* x0, const float* eps, const float* xt,
+                   const float* noise, const float* learned_v, int logvar_mode, float min_var_coef,
+                   const float* sigma, int n_sigma, const float* sigma_prev, int n_prev, int B, int d,
+                   float* x_prev, float* norm_out /*[B] or NULL*/, int* nan_flag /*1 int or NULL*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * P0-P6 — DDNM constraint operators (functions/svd_operators.py) and the fused projection
+ * x0 <- x0 - A^+(A x0 - y)  (image_sample.py:376-379).  x is NCHW fp32 [B,3,R,R] flattened.
+ * ---------------------------------------------------------------------------------------------- */
+#define NLC_OP_INPAINT 1   /* Inpainting          functions/svd_operators.py:324-359   */
+#define NLC_OP_COLOR 2     /* Colorization        :627-667                              */
+#define NLC_OP_SR_AVG 3    /* SuperResolution     :479-533                              */
+#define NLC_OP_WHCS 4      /* WalshHadamardCS     :211-251                              */
+#define NLC_OP_SEPARABLE 5 /* SRConv :851-931 and Deblurring :934-1014 (Kronecker SVD)  */
+
+typedef struct nlc_op nlc_op;
+
+typedef struct {
+    int task;
+    int channels, R;
+    int ratio;                /* SR_AVG / WHCS                                         */
+    const int64_t* idx_host;  /* INPAINT: missing indices (pixel*3+c); WHCS: perm[R*R] */
+    int64_t n_idx;
+    /* SEPARABLE: small-matrix SVD factors computed by the host exactly as the reference does */
+    const float* U_small_host; /* [m_small, m_small]  */
+    const float* V_small_host; /* [R, R]              */
+    const float* sing_small_host; /* [m_small]        */
+    int m_small;               /* R/f (SRConv) or R (Deblurring)                        */
+    float zero_thresh;         /* singulars below this are zero (3e-2 in the reference) */
+    const int64_t* perm_host;  /* Deblurring/SRConv singular ordering                   */
+    const float* singulars_host; /* ordered singulars                                   */
+    int64_t n_sing;
+} nlc_op_desc;
+
+int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out);
+void nlc_op_destroy(nlc_op* op);
+int64_t nlc_op_ydim(nlc_op* op);
+int nlc_op_A(nlc_op* op, const float* x, int B, float* y, void* stream);
+int nlc_op_At(nlc_op* op, const float* y, int B, float* x, void* stream);
+int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* stream);
+int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, float* l1_fwd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLC_B200_H */
