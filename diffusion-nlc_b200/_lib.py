@@ -21,7 +21,7 @@ class NlcError(RuntimeError):
 
 class Operand(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
-                ("ld", C.c_int)]
+                ("ld", C.c_int), ("sh", C.c_int64), ("sn", C.c_int64)]
 
 
 class KSeg(C.Structure):
@@ -32,11 +32,12 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("dtype", C.c_int), ("nsrc", C.c_int), ("src", Operand * MAX_SRC),
         ("nseg", C.c_int), ("seg", KSeg * MAX_SEG),
-        ("weight", C.c_void_p), ("Cout", C.c_int), ("stride", C.c_int),
+        ("weight", C.c_void_p), ("wbatched", Operand), ("Cout", C.c_int), ("stride", C.c_int),
         ("B", C.c_int), ("Ho", C.c_int), ("Wo", C.c_int),
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int),
         ("resid", C.c_void_p), ("ld_resid", C.c_int), ("out_scale", C.c_float),
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int), ("out_op", C.c_void_p), ("ld_out_op", C.c_int),
+        ("out_head_split", C.c_int),
     ]
 
 
@@ -67,15 +68,16 @@ _SIGNATURES = {
     "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _P]),
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
-    "nlc_attention": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "nlc_attention": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P]),
+    "nlc_attention_ws": (_SZ, [_I, _I, _I, _I, _I]),
     "nlc_linear": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P]),
-    "nlc_timestep_embedding": (_I, [_P, _P, _I, _I, _I, _F, _I, _P, _P]),
+    "nlc_timestep_embedding": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P]),
     "nlc_row_norm": (_I, [_P, _P, _I, _I, _P, _P]),
-    "nlc_refine_sigma": (_I, [_P, _P, _I, _I, _P, _I, _F, _F, _I, _P, _I, _I, _P, _P, _P, _P]),
+    "nlc_refine_sigma": (_I, [_P, _P, _I, _I, _P, _I, _F, _F, _I, _F, _P, _I, _I, _P, _P, _P, _P]),
     "nlc_sigma_correct": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
     "nlc_normalize_rows": (_I, [_P, _P, _I, _I, _P]),
     "nlc_pred_xstart": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "nlc_pred_xprev": (_I, [_P, _I, _F, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "nlc_pred_xprev": (_I, [_P, _I, C.c_double, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
     "nlc_op_create": (_I, [_P, C.POINTER(OpDesc), C.POINTER(_P)]),
     "nlc_op_destroy": (None, [_P]),
     "nlc_op_ydim": (_I64, [_P]),

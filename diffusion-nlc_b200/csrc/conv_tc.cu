@@ -49,6 +49,8 @@ struct ConvKParams {
     int ld_out_f32;
     void* out_op;
     int ld_out_op;
+    int out_head_split;
+    int w_batched;
 };
 
 template <int BLOCK_N>
@@ -125,7 +127,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         mbar_expect_tx(&full[stage], Cfg::kStageBytes);
                         tma_load_4d(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
                                     h0 + sg.dh, n0);
-                        tma_load_2d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N);
+                        tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
+                                    p.w_batched ? th : 0, p.w_batched ? n0 : 0);
                         ++kchunk;
                         if (++stage == kStages) {
                             stage = 0;
@@ -193,7 +196,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int ho = th * p.BH + bh;
             const int wo = tw * p.BW + bw;
             const bool valid = n < p.B;
-            const size_t pix = (static_cast<size_t>(n) * p.Ho + ho) * p.Wo + wo;
+            // dense NHWC row, or (attention head merge) row (n,wo) with a channel offset of ho*split
+            const size_t pix = p.out_head_split ? static_cast<size_t>(n) * p.Wo + wo
+                                                : (static_cast<size_t>(n) * p.Ho + ho) * p.Wo + wo;
+            const int hs_off = p.out_head_split * ho;
 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after_sync();
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 tmem_ld_wait();
                 if (valid) {
                     const int col0 = n_tile * BLOCK_N + c;
+                    const int ocol0 = col0 + hs_off;
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -238,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
                     }
                     if (p.out_f32) {
-                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_out_f32 + col0);
+                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_out_f32 + ocol0);
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
                             o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
@@ -246,14 +253,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     if (p.out_op) {
                         if (TF32) {
                             float4* o4 =
-                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + pix * p.ld_out_op + col0);
+                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + pix * p.ld_out_op + ocol0);
 #pragma unroll
                             for (int i = 0; i < 8; ++i)
                                 o4[i] = make_float4(round_tf32(f[4 * i]), round_tf32(f[4 * i + 1]),
                                                     round_tf32(f[4 * i + 2]), round_tf32(f[4 * i + 3]));
                         } else {
                             uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_op) +
-                                                                 pix * p.ld_out_op + col0);
+                                                                 pix * p.ld_out_op + ocol0);
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
                                 o4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
@@ -363,7 +370,10 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
                     "nlc_conv_tc: source %d must be 16-byte aligned (ptr and row pitch)", s);
         NLC_REQUIRE(o.B == d->B, "nlc_conv_tc: source %d batch %d != %d", s, o.B, d->B);
         cuuint64_t gdim[4] = {(cuuint64_t)o.C, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)o.B};
-        cuuint64_t gstr[3] = {(cuuint64_t)o.ld * esz, (cuuint64_t)o.W * o.ld * esz, (cuuint64_t)o.H * o.W * o.ld * esz};
+        const cuuint64_t sh = o.sh ? (cuuint64_t)o.sh : (cuuint64_t)o.W * o.ld;
+        const cuuint64_t sn = o.sn ? (cuuint64_t)o.sn : (cuuint64_t)o.H * o.W * o.ld;
+        NLC_REQUIRE((sh * esz) % 16 == 0 && (sn * esz) % 16 == 0, "nlc_conv_tc: source %d strides must be 16-byte multiples", s);
+        cuuint64_t gstr[3] = {(cuuint64_t)o.ld * esz, sh * esz, sn * esz};
         cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)(p.BW * d->stride), (cuuint32_t)(p.BH * d->stride),
                              (cuuint32_t)p.BN};
         cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
@@ -373,17 +383,39 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
         NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(A%d) failed with %d", s, (int)r);
     }
     for (int s = d->nsrc; s < NLC_MAX_SRC; ++s) p.mapA[s] = p.mapA[0];
-    {
+    p.w_batched = d->wbatched.ptr != nullptr;
+    if (p.w_batched) {
+        const nlc_operand& o = d->wbatched;
+        NLC_REQUIRE(p.BW == kBlockM && d->stride == 1, "nlc_conv_tc: batched operand needs Wo >= 128 and stride 1");
+        NLC_REQUIRE(o.C == ktot && o.W == d->Cout && o.H == d->Ho && o.B == d->B,
+                    "nlc_conv_tc: batched operand shape [%d,%d,%d,%d] does not match K=%d Cout=%d Ho=%d B=%d", o.B, o.H,
+                    o.W, o.C, ktot, d->Cout, d->Ho, d->B);
+        const cuuint64_t sh = o.sh ? (cuuint64_t)o.sh : (cuuint64_t)o.W * o.ld;
+        const cuuint64_t sn = o.sn ? (cuuint64_t)o.sn : (cuuint64_t)o.H * o.W * o.ld;
+        NLC_REQUIRE((reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && ((cuuint64_t)o.ld * esz) % 16 == 0 &&
+                        (sh * esz) % 16 == 0 && (sn * esz) % 16 == 0,
+                    "nlc_conv_tc: batched operand must be 16-byte aligned");
+        cuuint64_t gdim[4] = {(cuuint64_t)o.C, (cuuint64_t)o.W, (cuuint64_t)o.H, (cuuint64_t)o.B};
+        cuuint64_t gstr[3] = {(cuuint64_t)o.ld * esz, sh * esz, sn * esz};
+        cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)block_n, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = ctx->encode_tiled(&p.mapB, dt, 4, const_cast<void*>(o.ptr), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(batched W) failed with %d", (int)r);
+    } else {
         NLC_REQUIRE(d->weight && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "nlc_conv_tc: weight unaligned");
-        cuuint64_t gdim[2] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout};
-        cuuint64_t gstr[1] = {(cuuint64_t)ktot * esz};
-        cuuint32_t box[2] = {(cuuint32_t)chunk, (cuuint32_t)block_n};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = ctx->encode_tiled(&p.mapB, dt, 2, const_cast<void*>(d->weight), gdim, gstr, box, estr,
+        cuuint64_t gdim[4] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout, 1, 1};
+        cuuint64_t gstr[3] = {(cuuint64_t)ktot * esz, (cuuint64_t)ktot * esz * d->Cout, (cuuint64_t)ktot * esz * d->Cout};
+        cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)block_n, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = ctx->encode_tiled(&p.mapB, dt, 4, const_cast<void*>(d->weight), gdim, gstr, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
+    p.out_head_split = d->out_head_split;
+    NLC_REQUIRE(d->out_head_split % 8 == 0, "nlc_conv_tc: out_head_split must be a multiple of 8");
     p.bias = d->bias, p.rowvec = d->rowvec, p.ld_rowvec = d->ld_rowvec;
     p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;

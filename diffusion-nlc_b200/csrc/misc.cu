@@ -1,0 +1,175 @@
+// Small supporting kernels of the UNet executors: resampling/cast passes that produce tensor-core operands,
+// the timestep-embedding sinusoid, and the small fp32 dense layers (temb MLP, per-block temb projections,
+// sigma-model head).
+#include "common.h"
+#include "ptx.cuh"
+
+namespace nlc {
+
+// ---------------------------------------------------------------- resample: copy / nearest x2 / avgpool 2x2
+// x: NHWC fp32 [B,H,W,C] (pitch ld_x); outputs at the resampled resolution, fp32 and/or operand dtype.
+template <int MODE, bool TF32>
+__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C,
+                                                        float* __restrict__ yf, int ld_yf, void* __restrict__ yo,
+                                                        int ld_yo, long long total4) {
+    const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : H);
+    const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : W);
+    const int C4 = C >> 2;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C4) << 2;
+        long long pix = i / C4;
+        const int wo = static_cast<int>(pix % Wo);
+        pix /= Wo;
+        const int ho = static_cast<int>(pix % Ho);
+        const int n = static_cast<int>(pix / Ho);
+        float4 v;
+        if (MODE == 2) {
+            const float* p = x + ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * ld_x + c;
+            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p + ld_x));
+            const float4 d = __ldg(reinterpret_cast<const float4*>(p + static_cast<size_t>(W) * ld_x));
+            const float4 e = __ldg(reinterpret_cast<const float4*>(p + static_cast<size_t>(W) * ld_x + ld_x));
+            // same association as torch avg_pool2d: sum of the window, then divide
+            v.x = ((a.x + b.x) + (d.x + e.x)) * 0.25f;
+            v.y = ((a.y + b.y) + (d.y + e.y)) * 0.25f;
+            v.z = ((a.z + b.z) + (d.z + e.z)) * 0.25f;
+            v.w = ((a.w + b.w) + (d.w + e.w)) * 0.25f;
+        } else {
+            const int hi = MODE == 1 ? ho >> 1 : ho, wi = MODE == 1 ? wo >> 1 : wo;
+            v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(n) * H + hi) * W + wi) * ld_x + c));
+        }
+        const size_t opix = (static_cast<size_t>(n) * Ho + ho) * Wo + wo;
+        if (yf) *reinterpret_cast<float4*>(yf + opix * ld_yf + c) = v;
+        if (yo) {
+            if (TF32)
+                *reinterpret_cast<float4*>(static_cast<float*>(yo) + opix * ld_yo + c) =
+                    make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+            else
+                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(yo) + opix * ld_yo + c) =
+                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- timestep embedding
+__global__ void temb_kernel(const float* __restrict__ t, int B, const float* __restrict__ freqs, int half,
+                            int cos_first, float* __restrict__ out, int ld) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, k = i - b * half;
+    const float a = t[b] * freqs[k];
+    float s, c;
+    sincosf(a, &s, &c);
+    out[static_cast<size_t>(b) * ld + k] = cos_first ? c : s;
+    out[static_cast<size_t>(b) * ld + half + k] = cos_first ? s : c;
+}
+
+// ---------------------------------------------------------------- small dense layer (fp32 SIMT GEMM)
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == 1) return v / (1.0f + expf(-v));                            // SiLU
+    if (act == 2) return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));  // GELU (erf form, nn.GELU default)
+    return v;
+}
+
+constexpr int kLinBM = 32, kLinBN = 64, kLinBK = 32;
+// y[b,n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] )
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ld_x, int B, int K,
+                                                      const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                      int N, int act_in, int act_out, float* __restrict__ y, int ld_y) {
+    __shared__ float xs[kLinBK][kLinBM + 1];
+    __shared__ float ws[kLinBK][kLinBN + 1];
+    const int b0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each 2 rows x 4 cols
+    float acc[2][4] = {};
+    for (int k0 = 0; k0 < K; k0 += kLinBK) {
+        for (int i = threadIdx.x; i < kLinBM * kLinBK; i += 256) {
+            const int r = i / kLinBK, kk = i - r * kLinBK;
+            float v = 0.f;
+            if (b0 + r < B && k0 + kk < K) v = act_apply(x[static_cast<size_t>(b0 + r) * ld_x + k0 + kk], act_in);
+            xs[kk][r] = v;
+        }
+        for (int i = threadIdx.x; i < kLinBN * kLinBK; i += 256) {
+            const int r = i / kLinBK, kk = i - r * kLinBK;
+            float v = 0.f;
+            if (n0 + r < N && k0 + kk < K) v = Wt[static_cast<size_t>(n0 + r) * K + k0 + kk];
+            ws[kk][r] = v;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < kLinBK; ++kk) {
+            const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float w = ws[kk][tx + 16 * j];
+                acc[0][j] = fmaf(a0, w, acc[0][j]);
+                acc[1][j] = fmaf(a1, w, acc[1][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int b = b0 + ty * 2 + i;
+        if (b >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 16 * j;
+            if (n < N) y[static_cast<size_t>(b) * ld_y + n] = act_apply(acc[i][j] + (bias ? bias[n] : 0.f), act_out);
+        }
+    }
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int mode, float* y_f32,
+                            int ld_y_f32, void* y_op, int ld_y_op, int op_dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x && (y_f32 || y_op), "nlc_resample: null argument");
+    NLC_REQUIRE(mode >= 0 && mode <= 2 && C % 4 == 0 && ld_x % 4 == 0, "nlc_resample: bad mode/C");
+    NLC_REQUIRE(mode != 2 || (H % 2 == 0 && W % 2 == 0), "nlc_resample: avgpool needs even H, W");
+    NLC_REQUIRE(!y_f32 || ld_y_f32 % 4 == 0, "nlc_resample: ld_y_f32 %% 4");
+    NLC_REQUIRE(!y_op || ld_y_op % 4 == 0, "nlc_resample: ld_y_op %% 4");
+    const int Ho = mode == 1 ? 2 * H : (mode == 2 ? H / 2 : H);
+    const int Wo = mode == 1 ? 2 * W : (mode == 2 ? W / 2 : W);
+    const long long total4 = static_cast<long long>(B) * Ho * Wo * (C / 4);
+    long long blocks = (total4 + 255) / 256;
+    const long long cap = static_cast<long long>(ctx->sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    const bool tf32 = op_dtype == NLC_F32;
+#define NLC_RS(M, T)                                                                                              \
+    resample_kernel<M, T><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld_x, H, W, C, y_f32, ld_y_f32, y_op, \
+                                                                             ld_y_op, total4)
+    if (mode == 0) {
+        if (tf32) NLC_RS(0, true); else NLC_RS(0, false);
+    } else if (mode == 1) {
+        if (tf32) NLC_RS(1, true); else NLC_RS(1, false);
+    } else {
+        if (tf32) NLC_RS(2, true); else NLC_RS(2, false);
+    }
+#undef NLC_RS
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_timestep_embedding(nlc_ctx* ctx, const float* t, int B, const float* freqs, int half,
+                                      int cos_first, float* out, int ld_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && t && freqs && out && half > 0 && ld_out >= 2 * half, "nlc_timestep_embedding: bad argument");
+    const int total = B * half;
+    temb_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t, B, freqs, half, cos_first, out, ld_out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_linear(nlc_ctx* ctx, const float* x, int ld_x, int B, int K, const float* W, const float* bias,
+                          int N, int act_in, int act_out, float* y, int ld_y, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x && W && y && B > 0 && K > 0 && N > 0, "nlc_linear: bad argument");
+    dim3 grid((N + kLinBN - 1) / kLinBN, (B + kLinBM - 1) / kLinBM);
+    linear_kernel<<<grid, 256, 0, stream>>>(x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}

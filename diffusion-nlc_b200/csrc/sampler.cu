@@ -1,0 +1,353 @@
+// Sampler arithmetic around the networks: per-sample norms, the sigma refinement and
+// NLC correction with its searchsorted time lookup, eps normalisation, x0 prediction with clipping and every
+// pred_xprev variant of src/schedulers.py.  All of it is HBM-bound fp32 elementwise / reduction work, fused so
+// that each [B,3,R,R] tensor is read once per kernel with 16-byte accesses.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace nlc {
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = threadIdx.x < nw ? red[threadIdx.x] : 0.f;
+    if (warp == 0) {
+        v = warp_sum(v);
+        if (lane == 0) red[0] = v;
+    }
+    __syncthreads();
+    v = red[0];
+    __syncthreads();
+    return v;
+}
+
+// torch.linalg.vector_norm accumulates in fp32; we do too (pairwise through the shuffle tree).
+__device__ __forceinline__ float row_sumsq(const float* __restrict__ row, int d, float* red) {
+    float acc = 0.f;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    for (int i = threadIdx.x; i < (d >> 2); i += blockDim.x) {
+        const float4 v = __ldg(r4 + i);
+        acc += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+    return block_sum(acc, red);
+}
+
+__global__ void __launch_bounds__(1024) row_norm_kernel(const float* __restrict__ x, int d, float* __restrict__ out) {
+    __shared__ float red[32];
+    const float s = row_sumsq(x + static_cast<size_t>(blockIdx.x) * d, d, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = sqrtf(s);
+}
+
+__global__ void __launch_bounds__(1024) normalize_rows_kernel(float* __restrict__ x, int d) {
+    __shared__ float red[32];
+    float* row = x + static_cast<size_t>(blockIdx.x) * d;
+    const float nrm = sqrtf(row_sumsq(row, d, red));
+    // sqrt(d) * x / clamp(norm, 1e-12)  (src/utils.py:11-16): multiply first, then divide, like the reference
+    const float sd = sqrtf(static_cast<float>(d));
+    const float den = fmaxf(nrm, 1e-12f);
+    float4* r4 = reinterpret_cast<float4*>(row);
+    for (int i = threadIdx.x; i < (d >> 2); i += blockDim.x) {
+        float4 v = r4[i];
+        v.x = sd * v.x / den, v.y = sd * v.y / den, v.z = sd * v.z / den, v.w = sd * v.w / den;
+        r4[i] = v;
+    }
+}
+
+// first index i in [0, n] with table[i] >= v  (torch.searchsorted default side='left')
+__device__ __forceinline__ int lower_bound(const float* __restrict__ table, int n, float v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (table[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// single CTA over the B-vector (batch-global min for the time shift, src/experiments.py:411-412)
+__global__ void __launch_bounds__(1024)
+    refine_sigma_kernel(const float* __restrict__ norms, int B, float inv_sqrt_d, const float* __restrict__ sigma_in,
+                        int n_sigma_in, float norm_min, float norm_max, int refine, float t_fixed,
+                        const float* __restrict__ table, int n_table, int time_shift, float* __restrict__ sigma_out,
+                        float* __restrict__ t_out, float* __restrict__ in_scale_out) {
+    __shared__ int s_min;
+    if (threadIdx.x == 0) s_min = 0x7fffffff;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float s = sigma_in[n_sigma_in == 1 ? 0 : b];
+        int t = 0;
+        if (refine) {
+            const float nx = norms[b] * inv_sqrt_d;
+            const float lo = fmaxf(nx - norm_max, 0.f), hi = nx + norm_min;
+            s = fminf(fmaxf(s, lo), hi);
+            t = lower_bound(table, n_table, s);
+            atomicMin(&s_min, t);
+        }
+        sigma_out[b] = s;
+        if (in_scale_out) in_scale_out[b] = sqrtf(1.0f / (s * s + 1.0f));
+        if (!refine) t_out[b] = fminf(fmaxf(t_fixed, 0.f), 1000.f);
+    }
+    __syncthreads();
+    if (refine) {
+        const int shift = s_min > 0 ? time_shift : 0;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const int t = lower_bound(table, n_table, sigma_out[b]) - shift;
+            t_out[b] = fminf(fmaxf(static_cast<float>(t), 0.f), 1000.f);
+        }
+    }
+}
+
+__global__ void sigma_correct_kernel(const float* __restrict__ r, const float* __restrict__ sigma,
+                                     const float* __restrict__ sigma_prev, int n_prev, int B, int update_prev,
+                                     const float* __restrict__ table, int n_table, float* __restrict__ sigma_hat,
+                                     float* __restrict__ sigma_prev_hat, float* __restrict__ t_hat,
+                                     float* __restrict__ in_scale_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float s = sigma[b];
+    const float sp = sigma_prev[n_prev == 1 ? 0 : b];
+    const float dist = s * (1.0f + r[b]);
+    const float dist_prev = dist * (sp / s);
+    const int t = lower_bound(table, n_table, dist);
+    sigma_hat[b] = dist;
+    sigma_prev_hat[b] = update_prev ? dist_prev : sp;
+    t_hat[b] = fminf(fmaxf(static_cast<float>(t), 0.f), 1000.f);
+    if (in_scale_out) in_scale_out[b] = sqrtf(1.0f / (dist * dist + 1.0f));
+}
+
+// grid (chunks, B)
+__global__ void __launch_bounds__(256) pred_xstart_kernel(const float* __restrict__ xt, const float* __restrict__ eps,
+                                                           const float* __restrict__ sigma, int n_sigma, int d, int clip,
+                                                           float* __restrict__ x0) {
+    const int b = blockIdx.y;
+    const float s = sigma[n_sigma == 1 ? 0 : b];
+    const size_t base = static_cast<size_t>(b) * d;
+    const float4* x4 = reinterpret_cast<const float4*>(xt + base);
+    const float4* e4 = reinterpret_cast<const float4*>(eps + base);
+    float4* o4 = reinterpret_cast<float4*>(x0 + base);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (d >> 2); i += gridDim.x * blockDim.x) {
+        const float4 x = __ldg(x4 + i), e = __ldg(e4 + i);
+        float4 o = make_float4(x.x - s * e.x, x.y - s * e.y, x.z - s * e.z, x.w - s * e.w);
+        if (clip == NLC_CLIP_CLAMP) {
+            o.x = fminf(fmaxf(o.x, -1.f), 1.f), o.y = fminf(fmaxf(o.y, -1.f), 1.f);
+            o.z = fminf(fmaxf(o.z, -1.f), 1.f), o.w = fminf(fmaxf(o.w, -1.f), 1.f);
+        }
+        o4[i] = o;
+    }
+}
+
+struct XprevArgs {
+    int sched;
+    double eta;
+    const float *x0, *eps, *xt, *noise, *learned_v;
+    int logvar_mode;
+    float min_var_coef;
+    const float* sigma;
+    int n_sigma;
+    const float* sigma_prev;
+    int n_prev;
+    int d;
+    float* x_prev;
+    int* nan_flag;
+};
+
+// One thread-block slice of one sample. Scalars follow the reference's fp32 operation order.
+__global__ void __launch_bounds__(256) pred_xprev_kernel(const XprevArgs a) {
+    const int b = blockIdx.y;
+    const float st = a.sigma[a.n_sigma == 1 ? 0 : b];
+    const float sp = a.sigma_prev[a.n_prev == 1 ? 0 : b];
+    const float eta = static_cast<float>(a.eta);
+    // get_eps_logvar (src/schedulers.py:367-390)
+    float max_lv = 0.f, min_lv = 0.f;
+    if (a.logvar_mode != 0) {
+        float beta_t = (st * st - sp * sp) / (st * st + 1.0f);
+        beta_t = fmaxf(fabsf(beta_t), 1e-20f);
+        const float alpha_t = 1.0f / (st * st + 1.0f), alpha_prev = 1.0f / (sp * sp + 1.0f);
+        float coef = (1.0f - alpha_prev) / (1.0f - alpha_t);
+        coef = fminf(fmaxf(coef, 0.f), 1.f);
+        const float post_var = beta_t * coef;
+        max_lv = logf(beta_t);
+        min_lv = logf(fmaxf(post_var, a.min_var_coef));
+    }
+    const float abp_sqrt = sqrtf(1.0f / (sp * sp + 1.0f));  // sqrt(alpha_bar_prev)
+    const float mask = sp > 0.f ? 1.f : 0.f;
+    const float simple_signal = static_cast<float>(sqrt(1.0 - a.eta * a.eta)) * sp;
+    // DDPM_orig posterior coefficients (src/schedulers.py:581-599)
+    float pm1 = 0.f, pm2 = 0.f, ab_sqrt = 0.f;
+    if (a.sched == NLC_SCHED_DDPM_ORIG) {
+        const float alpha_bar = 1.0f / (st * st + 1.0f), alpha_bar_prev = 1.0f / (sp * sp + 1.0f);
+        const float alpha_t = alpha_bar / alpha_bar_prev, beta_t = 1.0f - alpha_t;
+        pm1 = beta_t * sqrtf(alpha_bar_prev) / (1.0f - alpha_bar);
+        pm2 = (1.0f - alpha_bar_prev) * sqrtf(alpha_t) / (1.0f - alpha_bar);
+        ab_sqrt = sqrtf(alpha_bar);
+    }
+    const size_t base = static_cast<size_t>(b) * a.d;
+    bool saw_nan = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (a.d >> 2); i += gridDim.x * blockDim.x) {
+        const float4 x0v = __ldg(reinterpret_cast<const float4*>(a.x0 + base) + i);
+        float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), xtv = ev, nv = ev, lv = ev;
+        const bool rederive = a.sched == NLC_SCHED_DDIM_SIMPLE_ORIG || a.sched == NLC_SCHED_DDIM_SIMPLE_DRAG ||
+                              a.sched == NLC_SCHED_DDIM_ORIG;
+        if (rederive || a.sched == NLC_SCHED_DDPM_ORIG) xtv = __ldg(reinterpret_cast<const float4*>(a.xt + base) + i);
+        if (!rederive && a.sched != NLC_SCHED_DDPM_ORIG) ev = __ldg(reinterpret_cast<const float4*>(a.eps + base) + i);
+        if (a.noise) nv = __ldg(reinterpret_cast<const float4*>(a.noise + base) + i);
+        if (a.logvar_mode == 1) lv = __ldg(reinterpret_cast<const float4*>(a.learned_v + base) + i);
+        const float X0[4] = {x0v.x, x0v.y, x0v.z, x0v.w};
+        const float XT[4] = {xtv.x, xtv.y, xtv.z, xtv.w};
+        const float NZ[4] = {nv.x, nv.y, nv.z, nv.w};
+        const float LV[4] = {lv.x, lv.y, lv.z, lv.w};
+        float E[4] = {ev.x, ev.y, ev.z, ev.w};
+        float O[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (rederive) E[k] = (XT[k] - X0[k]) / st;
+            float logvar = 0.f;
+            if (a.logvar_mode == 1) {
+                const float frac = (LV[k] + 1.0f) / 2.0f;
+                logvar = frac * max_lv + (1.0f - frac) * min_lv;
+            } else if (a.logvar_mode == 2) {
+                logvar = min_lv;
+            } else if (a.logvar_mode == 3) {
+                logvar = max_lv;
+            }
+            float o;
+            switch (a.sched) {
+                case NLC_SCHED_DDIM: {
+                    float noise_sigma = 0.f, nz = 0.f;
+                    if (a.eta > 0) {
+                        noise_sigma = eta * expf(0.5f * logvar) / abp_sqrt;
+                        nz = mask * NZ[k];
+                    }
+                    const float signal = sqrtf(fmaxf(sp * sp - noise_sigma * noise_sigma, 0.f));
+                    noise_sigma = sqrtf(sp * sp - signal * signal);
+                    o = X0[k] + signal * E[k] + noise_sigma * nz;
+                } break;
+                case NLC_SCHED_DDIM_ORIG: {
+                    float noise_sigma = 0.f, nz = 0.f;
+                    if (a.eta > 0) {
+                        noise_sigma = eta * expf(0.5f * logvar) / abp_sqrt;
+                        nz = mask * NZ[k];
+                    }
+                    const float signal = sqrtf(fmaxf(sp * sp - noise_sigma * noise_sigma, 0.f));
+                    o = X0[k] + signal * E[k] + noise_sigma * nz;
+                } break;
+                case NLC_SCHED_DDIM_SIMPLE:
+                case NLC_SCHED_DDIM_SIMPLE_ORIG: {
+                    o = X0[k] + simple_signal * E[k];
+                    if (a.eta > 0) o = o + (eta * sp) * NZ[k];
+                } break;
+                case NLC_SCHED_DDIM_SIMPLE_DRAG: {
+                    o = X0[k] + sp * E[k];
+                    if (a.eta > 0) o = o + (eta * sp) * NZ[k];
+                } break;
+                case NLC_SCHED_DDPM: {
+                    const float noise_sigma = expf(0.5f * logvar) / abp_sqrt;
+                    const float signal = sqrtf(fmaxf(sp * sp - noise_sigma * noise_sigma, 0.f));
+                    o = X0[k] + signal * E[k];
+                    o = o + noise_sigma * (mask * NZ[k]);
+                } break;
+                default: {  // NLC_SCHED_DDPM_ORIG
+                    const float zt = XT[k] * ab_sqrt;
+                    const float mean = pm1 * X0[k] + pm2 * zt;
+                    const float zprev = mean + mask * expf(0.5f * logvar) * NZ[k];
+                    o = zprev / abp_sqrt;
+                } break;
+            }
+            O[k] = o;
+            saw_nan |= (o != o);
+        }
+        reinterpret_cast<float4*>(a.x_prev + base)[i] = make_float4(O[0], O[1], O[2], O[3]);
+    }
+    if (a.nan_flag && saw_nan) atomicOr(a.nan_flag, 1);
+}
+
+static int row_grid(int sm_count, int B, int d) {
+    int chunks = 1;
+    while (static_cast<long long>(chunks) * B < 4LL * sm_count && chunks * 2 * 1024 <= d) chunks *= 2;
+    return chunks;
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" int nlc_row_norm(nlc_ctx* ctx, const float* x, int B, int d, float* out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x && out && d % 4 == 0, "nlc_row_norm: bad argument (d %% 4 == 0 required)");
+    row_norm_kernel<<<B, 1024, 0, stream>>>(x, d, out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_normalize_rows(nlc_ctx* ctx, float* x, int B, int d, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x && d % 4 == 0, "nlc_normalize_rows: bad argument (d %% 4 == 0 required)");
+    normalize_rows_kernel<<<B, 1024, 0, stream>>>(x, d);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_refine_sigma(nlc_ctx* ctx, const float* norms, int B, int d, const float* sigma_in, int n_sigma_in,
+                                float norm_min, float norm_max, int refine, float t_fixed, const float* sigma_table,
+                                int n_table, int time_shift, float* sigma_out, float* t_out, float* in_scale_out,
+                                void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && sigma_in && sigma_out && t_out, "nlc_refine_sigma: null argument");
+    NLC_REQUIRE(!refine || (norms && sigma_table), "nlc_refine_sigma: refine needs norms and the sigma table");
+    NLC_REQUIRE(n_sigma_in == 1 || n_sigma_in == B, "nlc_refine_sigma: n_sigma_in must be 1 or B");
+    refine_sigma_kernel<<<1, 1024, 0, stream>>>(norms, B, 1.0f / sqrtf(static_cast<float>(d)), sigma_in, n_sigma_in,
+                                                norm_min, norm_max, refine, t_fixed, sigma_table, n_table, time_shift,
+                                                sigma_out, t_out, in_scale_out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_sigma_correct(nlc_ctx* ctx, const float* r, const float* sigma, const float* sigma_prev, int n_prev,
+                                 int B, int update_prev, const float* sigma_table, int n_table, float* sigma_hat,
+                                 float* sigma_prev_hat, float* t_hat, float* in_scale_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && r && sigma && sigma_prev && sigma_table && sigma_hat && sigma_prev_hat && t_hat,
+                "nlc_sigma_correct: null argument");
+    NLC_REQUIRE(n_prev == 1 || n_prev == B, "nlc_sigma_correct: n_prev must be 1 or B");
+    sigma_correct_kernel<<<(B + 127) / 128, 128, 0, stream>>>(r, sigma, sigma_prev, n_prev, B, update_prev, sigma_table,
+                                                              n_table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_pred_xstart(nlc_ctx* ctx, const float* xt, const float* eps, const float* sigma, int n_sigma, int B,
+                               int d, int clip, float* x0, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && xt && eps && sigma && x0 && d % 4 == 0, "nlc_pred_xstart: bad argument");
+    NLC_REQUIRE(n_sigma == 1 || n_sigma == B, "nlc_pred_xstart: n_sigma must be 1 or B");
+    NLC_REQUIRE(clip == NLC_CLIP_NONE || clip == NLC_CLIP_CLAMP, "nlc_pred_xstart: clip mode %d unsupported", clip);
+    pred_xstart_kernel<<<dim3(row_grid(ctx->sm_count, B, d), B), 256, 0, stream>>>(xt, eps, sigma, n_sigma, d, clip, x0);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_pred_xprev(nlc_ctx* ctx, int sched, double eta, const float* x0, const float* eps, const float* xt,
+                              const float* noise, const float* learned_v, int logvar_mode, float min_var_coef,
+                              const float* sigma, int n_sigma, const float* sigma_prev, int n_prev, int B, int d,
+                              float* x_prev, int* nan_flag, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x0 && sigma && sigma_prev && x_prev && d % 4 == 0, "nlc_pred_xprev: bad argument");
+    NLC_REQUIRE(sched >= NLC_SCHED_DDIM && sched <= NLC_SCHED_DDIM_ORIG, "nlc_pred_xprev: unknown scheduler %d", sched);
+    const bool rederive = sched == NLC_SCHED_DDIM_SIMPLE_ORIG || sched == NLC_SCHED_DDIM_SIMPLE_DRAG ||
+                          sched == NLC_SCHED_DDIM_ORIG;
+    NLC_REQUIRE(!(rederive || sched == NLC_SCHED_DDPM_ORIG) || xt, "nlc_pred_xprev: this scheduler needs xt");
+    NLC_REQUIRE(rederive || sched == NLC_SCHED_DDPM_ORIG || eps, "nlc_pred_xprev: this scheduler needs eps");
+    const bool needs_noise = sched == NLC_SCHED_DDPM || sched == NLC_SCHED_DDPM_ORIG || eta > 0;
+    NLC_REQUIRE(!needs_noise || noise, "nlc_pred_xprev: noise tensor required (eta > 0 or DDPM)");
+    const bool needs_lv = sched == NLC_SCHED_DDPM || sched == NLC_SCHED_DDPM_ORIG ||
+                          ((sched == NLC_SCHED_DDIM || sched == NLC_SCHED_DDIM_ORIG) && eta > 0);
+    NLC_REQUIRE(!needs_lv || logvar_mode != 0, "nlc_pred_xprev: this scheduler needs a log-variance (sampler_var)");
+    NLC_REQUIRE(logvar_mode != 1 || learned_v, "nlc_pred_xprev: learned log-variance tensor missing");
+    XprevArgs a{sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_coef, sigma, n_sigma, sigma_prev,
+                n_prev, d, x_prev, nan_flag};
+    pred_xprev_kernel<<<dim3(row_grid(ctx->sm_count, B, d), B), 256, 0, stream>>>(a);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}

@@ -101,3 +101,114 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
     if out_op is not None:
         d.out_op, d.ld_out_op = out_op.ptr, out_op.ld
     _lib.check(_lib.lib().nlc_conv_tc(_ctx(srcs[0].t), C.byref(d), _stream()))
+
+
+def conv_in_nchw(x_nchw, in_scale, weight, bias, out_f32, out_op, op_dtype):
+    """Direct 3x3 conv on the sampler's NCHW fp32 image -> NHWC (nlc_conv_in_nchw)."""
+    B, Cin, H, W = x_nchw.shape
+    Cout = weight.shape[0]
+    _lib.check(_lib.lib().nlc_conv_in_nchw(
+        _ctx(x_nchw), _p(x_nchw), _p(in_scale), B, Cin, H, W, _p(weight), _p(bias), Cout,
+        C.c_void_p(out_f32.ptr) if out_f32 is not None else None, out_f32.ld if out_f32 is not None else 0,
+        C.c_void_p(out_op.ptr) if out_op is not None else None, out_op.ld if out_op is not None else 0,
+        op_dtype, _stream()))
+
+
+def conv_out_nchw(x_op, op_dtype, weight, bias, out_nchw):
+    """Direct 3x3 conv NHWC operand -> NCHW fp32 (nlc_conv_out_nchw)."""
+    Cout = weight.shape[0]
+    _lib.check(_lib.lib().nlc_conv_out_nchw(
+        _ctx(x_op.t), C.c_void_p(x_op.ptr), op_dtype, x_op.ld, x_op.B, x_op.C, x_op.H, x_op.W, _p(weight), _p(bias),
+        Cout, _p(out_nchw), _stream()))
+
+
+def groupnorm_ws(B, HW, C, groups):
+    return int(_lib.lib().nlc_groupnorm_ws(B, HW, C, groups))
+
+
+def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=None, shift=None):
+    """GroupNorm (+scale/shift, +SiLU) of fp32 NHWC `x` (Act) into operand `y_op` (Act)."""
+    ld_ss = scale.stride(0) if scale is not None else 0
+    _lib.check(_lib.lib().nlc_groupnorm(
+        _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H * x.W, x.C, groups, eps, _p(gamma), _p(beta), _p(scale),
+        _p(shift), ld_ss, 1 if silu else 0, C.c_void_p(y_op.ptr), y_op.ld, op_dtype, _p(ws), _stream()))
+
+
+def resample(x, mode, y_f32, y_op, op_dtype):
+    """mode 0 copy/cast, 1 nearest x2, 2 avgpool 2x2; x fp32 Act -> fp32 and/or operand Act."""
+    _lib.check(_lib.lib().nlc_resample(
+        _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, mode,
+        C.c_void_p(y_f32.ptr) if y_f32 is not None else None, y_f32.ld if y_f32 is not None else 0,
+        C.c_void_p(y_op.ptr) if y_op is not None else None, y_op.ld if y_op is not None else 0, op_dtype, _stream()))
+
+
+def attention_ws(op_dtype, B, T, heads, dh):
+    return int(_lib.lib().nlc_attention_ws(op_dtype, B, T, heads, dh))
+
+
+def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale, out, ws):
+    """qkv: Act [B,H,W,ld]; out: Act [B,H,W,heads*dh] (operand dtype)."""
+    T = qkv.H * qkv.W
+    _lib.check(_lib.lib().nlc_attention(
+        _ctx(qkv.t), C.c_void_p(qkv.ptr), op_dtype, qkv.ld, q_off, k_off, v_off, head_stride, qkv.B, T, heads, dh,
+        scale, C.c_void_p(out.ptr), out.ld, _p(ws), _stream()))
+
+
+def linear(x, W, bias, y, act_in=0, act_out=0):
+    """y = act_out(act_in(x) @ W.T + bias); x [B,K], W [N,K], y [B,N] fp32 (rows may be strided)."""
+    B, K = x.shape
+    N = W.shape[0]
+    assert W.is_contiguous() and W.shape[1] == K and x.stride(1) == 1 and y.stride(1) == 1
+    _lib.check(_lib.lib().nlc_linear(_ctx(x), _p(x), x.stride(0), B, K, _p(W), _p(bias), N, act_in, act_out, _p(y),
+                                     y.stride(0), _stream()))
+
+
+def timestep_embedding(t, freqs, cos_first, out):
+    B = t.shape[0]
+    half = freqs.shape[0]
+    _lib.check(_lib.lib().nlc_timestep_embedding(_ctx(t), _p(t), B, _p(freqs), half, 1 if cos_first else 0, _p(out),
+                                                 out.stride(0), _stream()))
+
+
+def row_norm(x, out):
+    B = x.shape[0]
+    d = x[0].numel()
+    _lib.check(_lib.lib().nlc_row_norm(_ctx(x), _p(x), B, d, _p(out), _stream()))
+
+
+def normalize_rows_(x):
+    B = x.shape[0]
+    d = x[0].numel()
+    _lib.check(_lib.lib().nlc_normalize_rows(_ctx(x), _p(x), B, d, _stream()))
+
+
+def refine_sigma(norms, B, d, sigma_in, norm_min, norm_max, refine, t_fixed, table, time_shift, sigma_out, t_out,
+                 in_scale_out):
+    _lib.check(_lib.lib().nlc_refine_sigma(
+        _ctx(sigma_in), _p(norms), B, d, _p(sigma_in), sigma_in.numel(), norm_min, norm_max, 1 if refine else 0,
+        float(t_fixed), _p(table), table.numel() if table is not None else 0, int(time_shift), _p(sigma_out),
+        _p(t_out), _p(in_scale_out), _stream()))
+
+
+def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out):
+    B = sigma.numel()
+    _lib.check(_lib.lib().nlc_sigma_correct(
+        _ctx(r), _p(r), _p(sigma), _p(sigma_prev), sigma_prev.numel(), B, 1 if update_prev else 0, _p(table),
+        table.numel(), _p(sigma_hat), _p(sigma_prev_hat), _p(t_hat), _p(in_scale_out), _stream()))
+
+
+def pred_xstart(xt, eps, sigma, clip, x0):
+    B = xt.shape[0]
+    d = xt[0].numel()
+    _lib.check(_lib.lib().nlc_pred_xstart(_ctx(xt), _p(xt), _p(eps), _p(sigma), sigma.numel(), B, d, clip, _p(x0),
+                                          _stream()))
+
+
+def pred_xprev(sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_coef, sigma, sigma_prev, x_prev,
+               nan_flag=None):
+    B = x0.shape[0]
+    d = x0[0].numel()
+    _lib.check(_lib.lib().nlc_pred_xprev(
+        _ctx(x0), sched, float(eta), _p(x0), _p(eps), _p(xt), _p(noise), _p(learned_v), logvar_mode,
+        float(min_var_coef), _p(sigma), sigma.numel(), _p(sigma_prev), sigma_prev.numel(), B, d, _p(x_prev),
+        _p(nan_flag), _stream()))

@@ -52,6 +52,8 @@ typedef struct {
     const void* ptr; /* operand tensor, bf16 (dtype NLC_BF16) or fp32 holding tf32-rounded values */
     int B, H, W, C;  /* logical NHWC extent                                                        */
     int ld;          /* elements between consecutive pixels                                        */
+    int64_t sh, sn;  /* element strides of H and B; 0 = dense (W*ld, H*W*ld). Non-dense strides let H   */
+                     /* index attention heads inside a [B,T,3C] qkv tensor.                         */
 } nlc_operand;
 
 typedef struct {
@@ -77,6 +79,10 @@ typedef struct {
     int nseg;
     nlc_kseg seg[NLC_MAX_SEG];
     const void* weight;
+    /* Batched right-hand operand (attention: S = Q K^T, O = P V): when wbatched.ptr != NULL it replaces
+     * `weight`; it is [B][H][Cout rows][K] with the strides given (C = K, W = Cout), and the tile at
+     * (image n, row h) multiplies with its own slice.  Requires Wo >= 128. */
+    nlc_operand wbatched;
     int Cout;
     int stride;
     int B, Ho, Wo;
@@ -90,6 +96,8 @@ typedef struct {
     int ld_out_f32;
     void* out_op; /* NHWC operand-dtype copy (bf16 / tf32-rounded fp32) or NULL */
     int ld_out_op;
+    int out_head_split; /* >0: output row (n,ho,wo) is written at pixel (n,wo), channel offset ho*out_head_split
+                           (merges attention heads back into [B,T,C]); 0: dense NHWC                  */
 } nlc_conv_desc;
 
 int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);
@@ -125,7 +133,8 @@ int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, in
  * AttentionOp (src/edm_networks.py:124-130).  softmax(scale * q k^T) v, fp32 math, output operand dtype. */
 int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld, int q_off, int k_off, int v_off,
                   int head_stride, int B, int T, int heads, int dh, float scale, void* out_op, int ld_out,
-                  void* stream);
+                  void* workspace /* nlc_attention_ws bytes, may be NULL when that is 0 */, void* stream);
+size_t nlc_attention_ws(int op_dtype, int B, int T, int heads, int dh);
 
 /* Small dense layers (timestep-embedding MLP, per-block temb projections, sigma head).
  * y[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] );  act: 0 none, 1 SiLU, 2 GELU(erf).
@@ -133,11 +142,12 @@ int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld, int q_off
 int nlc_linear(nlc_ctx* ctx, const float* x, int ld_x, int B, int K, const float* W, const float* bias, int N,
                int act_in, int act_out, float* y, int ld_y, void* stream);
 
-/* Sinusoidal timestep embedding. style 0: DDIM sin||cos with log(1e4)/(half-1) (src/unet_ddim.py:28-46);
- * style 1: ADM cos||sin with log(max_period)/half (src/nn_util.py:103-121);
- * style 2: EDM PositionalEmbedding cos||sin with endpoint option (src/edm_networks.py:212-225). */
-int nlc_timestep_embedding(nlc_ctx* ctx, const float* t, int B, int dim, int style, float max_period,
-                           int endpoint, float* out, void* stream);
+/* Sinusoidal timestep embedding out[b, :] = [sin|cos](t_b * freqs) (cos first when cos_first != 0).
+ * The frequency table is built on the host exactly as the reference does, so the three variants
+ * (src/unet_ddim.py:28-46 sin||cos, src/nn_util.py:103-121 cos||sin, src/edm_networks.py:212-225 cos||sin)
+ * share one kernel. */
+int nlc_timestep_embedding(nlc_ctx* ctx, const float* t, int B, const float* freqs, int half, int cos_first,
+                           float* out, int ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * D1 / S2 / S3 / S4 / S5 — the sampler arithmetic around the networks.
@@ -146,12 +156,15 @@ int nlc_timestep_embedding(nlc_ctx* ctx, const float* t, int B, int dim, int sty
 /* Per-sample L2 norm over d contiguous floats: vector_norm (src/utils.py:7-9). out[b] = ||x[b,:]||_2 */
 int nlc_row_norm(nlc_ctx* ctx, const float* x, int B, int d, float* out, void* stream);
 
-/* refine_prior_sigma + searchsorted (src/experiments.py:401-419, src/schedulers.py:185-190):
- *   nrm = ||x_b||/sqrt(d); sigma_b = clamp(sigma_in_b, max(nrm-norm_max,0), nrm+norm_min) when refine != 0
+/* refine_prior_sigma + searchsorted (src/experiments.py:401-419, src/schedulers.py:185-190), norms from
+ * nlc_row_norm:
+ *   nrm = norms_b/sqrt(d); sigma_b = clamp(sigma_in_b, max(nrm-norm_max,0), nrm+norm_min)      (refine != 0)
  *   t_b = clamp(first i with table[i] >= sigma_b  (- time_shift if min_b t > 0), 0, 1000)
- * sigma_in / sigma_prev_in have `n_sigma_in` entries (1 = broadcast scalar, B = per sample). */
-int nlc_refine_sigma(nlc_ctx* ctx, const float* xt, int B, int d, const float* sigma_in, int n_sigma_in,
-                     float norm_min, float norm_max, int refine, const float* sigma_table, int n_table,
+ *   refine == 0: sigma_b = sigma_in_b, t_b = clamp(t_fixed, 0, 1000)
+ *   in_scale_b = sqrt(1/(sigma_b^2+1))  (convert_coordinate, src/experiments.py:273-282)
+ * sigma_in has n_sigma_in entries (1 = broadcast scalar, B = per sample). */
+int nlc_refine_sigma(nlc_ctx* ctx, const float* norms, int B, int d, const float* sigma_in, int n_sigma_in,
+                     float norm_min, float norm_max, int refine, float t_fixed, const float* sigma_table, int n_table,
                      int time_shift, float* sigma_out, float* t_out, float* in_scale_out, void* stream);
 
 /* NLC correction (src/experiments.py:424-431): sigma_hat = sigma*(1+r); sigma_prev_hat = sigma_hat*sigma_prev/sigma
@@ -181,11 +194,12 @@ int nlc_pred_xstart(nlc_ctx* ctx, const float* xt, const float* eps, const float
 
 /* x_{t-1} for every pred_xprev variant (src/schedulers.py:432-449,465-473,487-496,505-514,548-562,581-599,
  * 609-627) including get_eps_logvar (:367-390).  logvar_mode: 0 none, 1 learned (v given), 2 fixedsmall,
- * 3 fixedlarge.  noise may be NULL when eta == 0.  Also returns ||x_{t-1}|| per sample and a NaN flag. */
-int nlc_pred_xprev(nlc_ctx* ctx, int sched, float eta, const float* x0, const float* eps, const float* xt,
+ * 3 fixedlarge.  noise (the reference's torch.randn_like draw) may be NULL when eta == 0.  nan_flag (1 int,
+ * caller-zeroed, may be NULL) is OR-ed with 1 when x_{t-1} holds a NaN (src/experiments.py:389). */
+int nlc_pred_xprev(nlc_ctx* ctx, int sched, double eta, const float* x0, const float* eps, const float* xt,
                    const float* noise, const float* learned_v, int logvar_mode, float min_var_coef,
                    const float* sigma, int n_sigma, const float* sigma_prev, int n_prev, int B, int d,
-                   float* x_prev, float* norm_out /*[B] or NULL*/, int* nan_flag /*1 int or NULL*/, void* stream);
+                   float* x_prev, int* nan_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * P0-P6 — DDNM constraint operators (functions/svd_operators.py) and the fused projection

@@ -1,0 +1,137 @@
+"""ORACLE support (test infrastructure): synthetic, seeded state_dicts with exactly the key names and shapes of
+the reference modules, so parity tests and the benchmark need neither checkpoints nor /root/reference.
+
+Key layouts follow the reference constructors: src/unet_ddim.py:214-321 (UNetModel) and :493-519 (SigmaModel).
+tests/test_oracle_vs_reference.py checks names and shapes against the real modules when the reference is present.
+Initialisation follows SURVEY §8(d): no all-zero parameter, non-trivial BatchNorm running statistics.
+"""
+import torch
+
+
+class _Init:
+    def __init__(self, seed):
+        self.g = torch.Generator().manual_seed(seed)
+        self.sd = {}
+
+    def randn(self, *shape):
+        return torch.randn(*shape, generator=self.g)
+
+    def conv(self, name, cin, cout, k, gain=1.0):
+        fan_in = cin * k * k
+        self.sd[name + ".weight"] = self.randn(cout, cin, k, k) * (gain / fan_in ** 0.5)
+        self.sd[name + ".bias"] = self.randn(cout) * 0.02
+
+    def linear(self, name, cin, cout, gain=1.0):
+        self.sd[name + ".weight"] = self.randn(cout, cin) * (gain / cin ** 0.5)
+        self.sd[name + ".bias"] = self.randn(cout) * 0.02
+
+    def norm(self, name, c):
+        self.sd[name + ".weight"] = 1.0 + 0.1 * self.randn(c)
+        self.sd[name + ".bias"] = 0.05 * self.randn(c)
+
+
+def _resblock(I, p, cin, cout, temb_ch=None):
+    I.norm(p + "norm1", cin)
+    I.conv(p + "conv1", cin, cout, 3)
+    if temb_ch is not None:
+        I.linear(p + "temb_proj", temb_ch, cout)
+    I.norm(p + "norm2", cout)
+    I.conv(p + "conv2", cout, cout, 3, gain=0.5)
+    if cin != cout:
+        I.conv(p + "nin_shortcut", cin, cout, 1)
+
+
+def _attn(I, p, c):
+    I.norm(p + "norm", c)
+    for n in ("q", "k", "v"):
+        I.conv(p + n, c, c, 1)
+    I.conv(p + "proj_out", c, c, 1, gain=0.5)
+
+
+def ddim_unet_state_dict(image_size, in_channels, model_channels, out_channels, num_res_blocks,
+                         attention_resolutions, channel_mult, seed=0):
+    """Same keys/shapes as src.unet_ddim.UNetModel(...).state_dict()."""
+    I = _Init(seed)
+    ch, temb_ch = model_channels, 4 * model_channels
+    I.linear("temb.dense.0", ch, temb_ch)
+    I.linear("temb.dense.1", temb_ch, temb_ch)
+    I.conv("conv_in", in_channels, ch, 3)
+    res = image_size
+    in_mult = (1,) + tuple(channel_mult)
+    L = len(channel_mult)
+    block_in = None
+    for lv in range(L):
+        block_in = ch * in_mult[lv]
+        block_out = ch * channel_mult[lv]
+        for ib in range(num_res_blocks):
+            _resblock(I, "down.%d.block.%d." % (lv, ib), block_in, block_out, temb_ch)
+            block_in = block_out
+            if res in attention_resolutions:
+                _attn(I, "down.%d.attn.%d." % (lv, ib), block_in)
+        if lv != L - 1:
+            I.conv("down.%d.downsample.conv" % lv, block_in, block_in, 3)
+            res //= 2
+    _resblock(I, "mid.block_1.", block_in, block_in, temb_ch)
+    _attn(I, "mid.attn_1.", block_in)
+    _resblock(I, "mid.block_2.", block_in, block_in, temb_ch)
+    for lv in reversed(range(L)):
+        block_out = ch * channel_mult[lv]
+        skip_in = ch * channel_mult[lv]
+        for ib in range(num_res_blocks + 1):
+            if ib == num_res_blocks:
+                skip_in = ch * in_mult[lv]
+            _resblock(I, "up.%d.block.%d." % (lv, ib), block_in + skip_in, block_out, temb_ch)
+            block_in = block_out
+            if res in attention_resolutions:
+                _attn(I, "up.%d.attn.%d." % (lv, ib), block_in)
+        if lv != 0:
+            I.conv("up.%d.upsample.conv" % lv, block_in, block_in, 3)
+            res *= 2
+    I.norm("norm_out", block_in)
+    I.conv("conv_out", block_in, out_channels, 3)
+    return I.sd
+
+
+def ddim_sigma_state_dict(dim, channels, n_blocks, seed=1, fc_dim=128):
+    """Same keys/shapes as src.unet_ddim.SigmaModel(dim, channels, n_blocks).state_dict()."""
+    I = _Init(seed)
+    idx = 0
+    d = dim
+    for i in range(n_blocks):
+        if d % 2 != 0:
+            d += 1
+        idx += 1  # ConstantPad2d / Identity
+        _resblock(I, "down_layer.%d." % idx, channels, channels)
+        idx += 1
+        if i == 0:
+            _attn(I, "down_layer.%d." % idx, channels)
+            idx += 1
+        I.conv("down_layer.%d.conv" % idx, channels, channels, 3)
+        idx += 1
+        d //= 2
+    hidden = channels * d * d
+    I.linear("fc_layer.1", hidden, fc_dim)
+    I.sd["fc_layer.2.weight"] = 1.0 + 0.1 * I.randn(fc_dim)
+    I.sd["fc_layer.2.bias"] = 0.05 * I.randn(fc_dim)
+    I.sd["fc_layer.2.running_mean"] = 0.1 * I.randn(fc_dim)
+    I.sd["fc_layer.2.running_var"] = 0.5 + torch.rand(fc_dim, generator=I.g)
+    I.sd["fc_layer.2.num_batches_tracked"] = torch.tensor(0)
+    I.linear("final_mlp", fc_dim, 1, gain=0.3)
+    return I.sd
+
+
+# The benchmark / parity configurations of BASELINE.json
+CONFIGS = {
+    # c1: CIFAR-10-shaped unet_ddim, 32x32
+    "c1": dict(unet=dict(image_size=32, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                         attention_resolutions=(16,), channel_mult=(1, 2, 2, 2)),
+               sigma=dict(dim=4, channels=256, n_blocks=2)),
+    # c2: CelebA-64 unet_ddim
+    "c2": dict(unet=dict(image_size=64, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=2,
+                         attention_resolutions=(16,), channel_mult=(1, 2, 2, 2, 4)),
+               sigma=dict(dim=4, channels=512, n_blocks=2)),
+    # tiny: fast CPU-side shape for unit tests (same topology, narrow)
+    "tiny": dict(unet=dict(image_size=16, in_channels=3, model_channels=128, out_channels=3, num_res_blocks=1,
+                           attention_resolutions=(8,), channel_mult=(1, 2)),
+                 sigma=dict(dim=8, channels=256, n_blocks=2)),
+}
