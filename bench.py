@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the NLC sampling hot path (BASELINE.json metric: DDIM+NLC images/sec).
+
+Workload (c2, BASELINE.json configs[1]): CelebA-64-shaped unet_ddim (ch128, mult 1,2,2,2,4, attn@16) + sigma-model,
+ddim_simple_orig eta=0.85, 100 sampling steps from sigma=100, style 'pred' + norm_eps + refine_prior_sigma, clamp
+clip, batch 256 per GPU, synthetic seeded weights.  One bench "step" = one full 100-timestep sampling pass of one
+batch (= 200 UNet-encoder + 100 decoder + 100 sigma-model evaluations per image).
+
+  value  : images/s with x_T resident in HBM and the result left on the device (kernel-only path)
+  e2e    : images/s through the public API (ImageExperiment.denoise_loop): CPU-generator noise, H2D of x_T from
+           pinned memory, D2H of the finished images, inside the timed region
+  roofline: tcgen05 implicit-GEMM conv kernel, algorithmic FLOPs / CUDA-event time of sampled launches
+  cpu_baseline: the oracle port (torch fp32, all host cores) on a bounded sample of the same workload
+
+`--impl reference` times the oracle port (the reference is pure Python and cannot travel to the GPU box) on the
+host cores for the same config.  N>1: one process per GPU under torchrun, batch sharded, NCCL all-gather of the
+finished images each pass; value = all ranks' images / max-over-ranks device time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(name="c2", R=64, steps=100, sampler="ddim_simple_orig", eta=0.85, start_sigma=100.0, style="pred",
+           norm_eps=True, refine=True, clip="clamp", norm_min=-2.0, norm_max=110.0, sigma_pred_threshold=960)
+GFLOP_PER_NFE = 60.57  # forward 48.10 + encode 12.22 + sigma 0.25 per sample
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1399.0), d.get("hbm_gbs", 6527.8), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons}
+
+
+def cpu_port_rate(n_steps, batch, threads):
+    """images/s of the oracle port on the host: `n_steps` NLC sampling steps at `batch`, extrapolated to 100."""
+    from oracle import ddim_net, sampler as S, weights
+    torch.set_num_threads(threads)
+    cfg = weights.CONFIGS[CFG["name"]]
+    sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
+    ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+    tab = S.Tables()
+    ts, sig, mvc = tab.ddim_schedule(CFG["start_sigma"], None, CFG["steps"])
+    d = 3 * CFG["R"] ** 2
+    g = torch.Generator().manual_seed(0)
+    shape = (batch, 3, CFG["R"], CFG["R"])
+    xT = torch.randn(shape, generator=g) / (1 / (sig[0] ** 2 + 1)).sqrt()
+    noises = [torch.randn(shape, generator=g) for _ in range(n_steps + 1)]
+    first = next(i for i, t in enumerate(ts.tolist()) if t <= CFG["sigma_pred_threshold"])  # NLC-active steps
+    args = dict(kind=CFG["sampler"], eta=CFG["eta"], style=CFG["style"], norm_eps=CFG["norm_eps"], refine=CFG["refine"],
+                norm_min=CFG["norm_min"] / d ** 0.5, norm_max=CFG["norm_max"] / d ** 0.5, clip=CFG["clip"])
+    fwd = lambda z, t: ddim_net.unet_forward(sd, z, t)
+    enc = lambda z, t: ddim_net.unet_encode(sd, z, t)
+    sg = lambda f: ddim_net.sigma_forward(ssd, f)
+    with torch.no_grad():
+        S.denoise_loop(tab, ts[first:first + 2].tolist(), sig[first:first + 2], mvc, fwd, enc, sg, xT, noises=noises, **args)
+        t0 = time.perf_counter()
+        S.denoise_loop(tab, ts[first:first + n_steps + 1].tolist(), sig[first:first + n_steps + 1], mvc, fwd, enc, sg,
+                       xT, noises=noises, **args)
+        dt = time.perf_counter() - t0
+    return batch / (dt / n_steps * CFG["steps"]), dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step = []
+    for _ in range(args.warmup):
+        cpu_port_rate(1, 2, threads)
+    for _ in range(args.steps):
+        rate, dt = cpu_port_rate(2, 4, threads)
+        per_step.append((rate, dt))
+    rate = sum(r for r, _ in per_step) / len(per_step)
+    line = {
+        "impl": "reference", "metric": "DDIM+NLC images/sec (CelebA-64 unet_ddim, 100 steps)", "value": rate,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * 256 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "c2: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, 100 steps, NLC pred",
+                   "per_gpu_batch": 256},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": "each step = 2 NLC timesteps at batch 4 of the c2 workload on the oracle port "
+                                   "(torch fp32, %d threads), extrapolated linearly to 100 timesteps" % threads},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nlc", choices=["nlc", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--timesteps", type=int, default=CFG["steps"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from nlc_b200 import ops
+    from nlc_b200.experiments import ImageExperiment
+    from nlc_b200.schedulers import get_sampler
+    from nlc_b200.unet_ddim import SigmaModel, UNetModel
+    from oracle import weights  # synthetic seeded state_dicts only (no oracle arithmetic on this arm)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    CFG["steps"] = args.timesteps
+    cfg = weights.CONFIGS[CFG["name"]]
+    B, R = args.batch, CFG["R"]
+    model = UNetModel(**cfg["unet"], precision=args.precision, device=dev).load_state_dict(
+        weights.ddim_unet_state_dict(**cfg["unet"], seed=3))
+    sigma_model = SigmaModel(**cfg["sigma"], precision=args.precision, device=dev).load_state_dict(
+        weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4))
+    sch = get_sampler(CFG["sampler"], 1000, CFG["steps"], start_sigma=CFG["start_sigma"], eta=CFG["eta"],
+                      sampler_var="none").to(dev)
+    exp = ImageExperiment(model, sch, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev)
+    exp.set_model(model, sigma_model, learn_epsvar=False)
+    exp.set_norm_maxmin(CFG["norm_min"], CFG["norm_max"])
+    exp.set_clip_fn(CFG["clip"])
+    shape = (B, 3, R, R)
+    loop_kw = dict(style=CFG["style"], norm_eps=CFG["norm_eps"], refine_prior_sigma=CFG["refine"], return_log=False,
+                   chunk_size=1, sigma_pred_threshold=CFG["sigma_pred_threshold"])
+    gathered = [torch.empty(shape, device=dev) for _ in range(world)] if world > 1 else None
+
+    conv_samples = []
+
+    def hook(ind, _):
+        # time the conv kernel on every 10th timestep of the timed passes (CUDA events on the launching stream)
+        ops.STATS.conv_timer = conv_samples if (ind + 1) % 10 == 0 and hook.active else None
+
+    hook.active = False
+    g_dev = torch.Generator(device=dev).manual_seed(99 + rank)
+    xT = torch.randn(shape, generator=g_dev, device=dev) * (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5
+
+    def one_pass_device():
+        out, _ = exp.denoise_loop(shape=shape, xT=xT, to_cpu=False, step_hook=hook, **loop_kw)
+        if world > 1:
+            dist.all_gather(gathered, out.contiguous())
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing
+    for _ in range(max(args.warmup, 1)):
+        one_pass_device()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ops.STATS.launches = 0
+    hook.active = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_pass_device()
+    e1.record()
+    barrier()
+    hook.active = False
+    ops.STATS.conv_timer = None
+    launches = ops.STATS.launches
+    clocks.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step / 1000.0)
+
+    # ---------------------------------------------------------------- end-to-end through the public API
+    pinned = torch.empty(shape, dtype=torch.float32).pin_memory()
+    gen = torch.Generator().manual_seed(4321 + rank)
+
+    def one_pass_e2e():
+        # the reference draws x_T on the CPU generator (src/experiments.py:268); pinned staging, H2D, loop, D2H
+        torch.randn(shape, generator=gen, out=pinned)
+        x = pinned.to(dev, non_blocking=True) * (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5
+        out, _ = exp.denoise_loop(shape=shape, xT=x, to_cpu=True, **loop_kw)
+        return out
+
+    one_pass_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 3))
+    for _ in range(n_e2e):
+        one_pass_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    if world > 1:
+        te = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    e2e_value = B * world / e2e_s
+    nbytes = B * 3 * R * R * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    tf_peak, hbm_peak, peak_src = peaks()
+    conv_ms = sum(a.elapsed_time(b) for _, a, b in conv_samples)
+    conv_fl = sum(f for f, _, _ in conv_samples)
+    achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
+    nfe_flops = GFLOP_PER_NFE * 1e9 * B * CFG["steps"]
+    roofline = {"bound": "tensor", "kernel": "nlc::conv_tc_kernel (tcgen05 implicit GEMM, %s)" % args.precision,
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "peak_source": peak_src, "traffic": None,
+                "launches_sampled": len(conv_samples),
+                "conv_share_of_step": (conv_ms / max(len(conv_samples), 1)) and None,
+                "whole_step_tflops": nfe_flops / (ms_per_step / 1000.0) / 1e12}
+    # share of the step spent in the conv kernel, from the sampled timesteps (1 in 10)
+    sampled_timesteps = max(1, args.steps * (CFG["steps"] // 10))
+    roofline["conv_share_of_step"] = (conv_ms / sampled_timesteps) / (ms_per_step / CFG["steps"]) if conv_ms > 0 else None
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_port_rate(2, 4, threads)
+        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": "2 NLC timesteps at batch 4 of the c2 workload on the oracle port (torch fp32, %d threads, "
+                         "%.1f s), extrapolated linearly to 100 timesteps" % (threads, dt)}
+
+    line = {
+        "metric": "DDIM+NLC images/sec (CelebA-64 unet_ddim, 100 steps)", "value": value, "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": "c2: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, %d steps, NLC pred"
+                               % CFG["steps"], "per_gpu_batch": B, "global_batch": B * world,
+                   "step": "one full %d-timestep sampling pass of one batch" % CFG["steps"],
+                   "l2": "activations per pass (GBs) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": "dp%d (batch sharded, NCCL all-gather of finished images)" % world},
+        "nfe_per_s": value * CFG["steps"],
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's sampler orchestration (src/experiments.py: ExperimentDiffusion,
+ImageExperiment) for the sampling path: `denoise_loop` and `get_denoise_vector` keep the reference's names,
+arguments and return values, and every per-step tensor operation is a libnlc_b200 kernel.
+
+Per NLC step (src/experiments.py:400-460):
+    row_norm -> refine_sigma (clamp + searchsorted) -> UNet.encode (input scale folded into conv_in)
+    -> sigma-model -> sigma_correct (sigma_hat, sigma_prev_hat, t_hat) -> UNet.forward -> normalize_rows
+then pred_xstart(+clip) -> [constraint projection] -> pred_xprev (src/experiments.py:346-390).
+
+Differences from the reference, all host-side and documented in DESIGN.md:
+  * `chunk_size` micro-batching (a memory-saving device of the reference) is accepted and ignored: samples are
+    independent, so results are identical;
+  * the NaN early-exit (`torch.isnan(xt).any()`, one host sync per step) reads a device flag every
+    `nan_check_every` steps instead;
+  * `return_log=True` returns the same lists but costs the same device->host copies as in the reference.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .schedulers import CLIP_CLAMP, CLIP_NONE, _as_f32
+
+
+class _Work:
+    """Per-batch-size scratch vectors of the step (all fp32, device)."""
+
+    def __init__(self, B, shape, device):
+        f = lambda *s: torch.empty(*s, device=device, dtype=torch.float32)
+        self.norms, self.sigma, self.t, self.scale = f(B), f(B), f(B), f(B)
+        self.sigma_hat, self.sigma_prev_hat, self.t_hat, self.scale_hat = f(B), f(B), f(B), f(B)
+        self.sigma_prev = f(B)
+        self.eps = f(B, *shape)
+        self.x0 = f(B, *shape)
+        self.xa, self.xb = f(B, *shape), f(B, *shape)
+        self.nan_flag = torch.zeros(1, device=device, dtype=torch.int32)
+
+
+class ExperimentDiffusion:
+    """src/experiments.py:87-551 (sampling methods)."""
+
+    def __init__(self, model, scheduler, batch_size, data_shape, save_folder, seed=0, device="cuda", dist_train=0,
+                 time_shift=0):
+        self.model = model
+        self.scheduler = scheduler
+        self.device = torch.device(device)
+        self.seed = seed
+        self.batch_size = batch_size
+        self.data_shape = tuple(data_shape)
+        self.shape = (batch_size,) + self.data_shape
+        self.dim = int(np.prod(data_shape))
+        self.dim_coord = len(data_shape)
+        self.save_folder = save_folder
+        self.dist_train = dist_train
+        self.time_shift = time_shift
+        self.clip_mode = CLIP_NONE
+        self.learn_epsvar = False
+        self.sigma_model = None
+        self.norm_min, self.norm_max = 0.0, 1.0
+        self.nan_check_every = 16
+        self.gen = self.new_gen()
+        self._work = {}
+
+    # ---------------------------------------------------------------- configuration (same names as the reference)
+    def set_model(self, model=None, sigma_model=None, learn_epsvar=True):
+        if model is not None:
+            self.model = model
+            self.learn_epsvar = learn_epsvar
+        else:
+            self.learn_epsvar = False
+        if sigma_model is not None:
+            self.sigma_model = sigma_model
+
+    def set_norm_maxmin(self, norm_min=None, norm_max=None):
+        # src/experiments.py:176-184
+        self.norm_min = norm_min / math.sqrt(self.dim) if norm_min is not None else 0.0
+        self.norm_max = norm_max / math.sqrt(self.dim) if norm_max is not None else 1.0
+
+    def set_clip_fn(self, clip_fn="none"):
+        # src/experiments.py:186-207
+        if clip_fn == "clamp":
+            self.clip_mode = CLIP_CLAMP
+        elif clip_fn == "dynamic":
+            raise NotImplementedError("dynamic thresholding (per-image 0.99 quantile) is not built yet")
+        else:
+            self.clip_mode = CLIP_NONE
+
+    def new_gen(self, seed=None):
+        return torch.manual_seed(self.seed if seed is None else seed)
+
+    def get_noise(self, shape=None, gen=None, norm_noise=False):
+        # src/experiments.py:263-271: CPU generator, then one host->device copy
+        shape = self.shape if shape is None else shape
+        gen = self.gen if gen is None else gen
+        noise = torch.randn(shape, generator=gen).to(self.device)
+        if norm_noise:
+            ops.normalize_rows_(noise)
+        return noise
+
+    def get_noise_xt(self, shape=None, gen=None, norm_noise=False, t=None, sigma=None):
+        # x_T = z / sqrt(alpha_bar) with alpha_bar = 1/(sigma^2+1)  (src/experiments.py:284-293,322-325)
+        zt = self.get_noise(shape=shape, gen=gen, norm_noise=norm_noise)
+        alpha_bar = 1 / (sigma.to(self.device) ** 2 + 1)
+        return zt / alpha_bar.sqrt(), zt
+
+    def convert_coordinate(self, xt, sigma):
+        return xt * (1 / (sigma ** 2 + 1)).sqrt()
+
+    def _w(self, B):
+        w = self._work.get(B)
+        if w is None:
+            w = _Work(B, self.data_shape, self.device)
+            self._work[B] = w
+        return w
+
+    # ---------------------------------------------------------------- D1: the fused step front-end
+    @torch.no_grad()
+    def get_denoise_vector(self, xt, t, sigma_t, sigma_prev, style="base", norm_eps=False, refine_prior_sigma=False,
+                           chunk_size=2):
+        """(eps, eps_logvar, sigma_t, sigma_prev) as in src/experiments.py:400-460.  sigma_t / sigma_prev come back
+        as [B,1,1,1] device tensors whenever the step made them per-sample (refine or 'pred*' styles)."""
+        B = xt.shape[0]
+        w = self._w(B)
+        sch = self.scheduler
+        sig_in = _as_f32(sigma_t, self.device)
+        sp_in = _as_f32(sigma_prev, self.device)
+        per_sample = refine_prior_sigma or "pred" in style or sig_in.numel() == B
+        if refine_prior_sigma:
+            ops.row_norm(xt, w.norms)
+            ops.refine_sigma(w.norms, B, self.dim, sig_in, self.norm_min, self.norm_max, True, 0.0, sch.sigma_table,
+                             self.time_shift, w.sigma, w.t, w.scale)
+        else:
+            t_vec = torch.is_tensor(t) and t.numel() == B and B > 1
+            ops.refine_sigma(None, B, self.dim, sig_in, 0.0, 0.0, False, 0.0 if t_vec else float(t), None, 0, w.sigma,
+                             w.t, w.scale)
+            if t_vec:
+                w.t.copy_(t.reshape(-1).to(torch.float32).clamp_(0.0, 1000.0))
+        sigma_cur, t_cur, scale_cur = w.sigma, w.t, w.scale
+        sp_cur = sp_in
+        if "pred" in style:
+            feat = self.model.encode_scaled(xt, t_cur, scale_cur)
+            r = self.sigma_model.forward_nhwc(feat)
+            ops.sigma_correct(r, sigma_cur, sp_in, style == "pred", sch.sigma_table, w.sigma_hat, w.sigma_prev_hat,
+                              w.t_hat, w.scale_hat)
+            sigma_cur, t_cur, scale_cur = w.sigma_hat, w.t_hat, w.scale_hat
+            sp_cur = w.sigma_prev_hat
+        elif refine_prior_sigma and sp_in.numel() == 1:
+            w.sigma_prev.copy_(sp_in.expand(B))
+            sp_cur = w.sigma_prev
+        out = self.model.forward_scaled(xt, t_cur, scale_cur)
+        if self.learn_epsvar:
+            C = out.shape[1] // 2
+            w.eps.copy_(out[:, :C])
+            learned = out[:, C:].contiguous()
+        else:
+            w.eps.copy_(out)
+            learned = None
+        if norm_eps:
+            ops.normalize_rows_(w.eps)
+        logvar = sch.get_eps_logvar(sigma_t=sigma_cur, sigma_prev=sp_cur, learned_logvar=learned)
+        if per_sample:
+            sp_ret = sp_cur.view(B, 1, 1, 1) if sp_cur.numel() == B else sp_cur
+            return w.eps, logvar, sigma_cur.view(B, 1, 1, 1), sp_ret
+        return w.eps, logvar, sigma_t, sigma_prev
+
+    # ---------------------------------------------------------------- L1: the DDIM-family loop
+    @torch.no_grad()
+    def denoise_loop(self, shape, gen=None, norm_init_noise=False, style="base", constrain_fn=None, norm_eps=False,
+                     refine_prior_sigma=False, xT=None, return_log=True, chunk_size=2, sigma_pred_threshold=1000,
+                     new_eta=None, constrain_loss=None, return_best=True, free_const_steps=-1, noise_fn=None,
+                     step_hook=None, to_cpu=True):
+        """src/experiments.py:329-397.  `noise_fn(ind, like)` (optional) supplies the per-step noise instead of
+        torch.randn_like (used by parity tests and by sharded runs that must reproduce the un-sharded stream);
+        `step_hook(ind, dict)` (optional) observes per-step device tensors without copying them; `to_cpu=False`
+        leaves the result on the device (the reference always returns a CPU tensor)."""
+        sch = self.scheduler
+        sch.reset_state()
+        sig = sch.sampling_sigmas
+        if xT is None:
+            xt, zt = self.get_noise_xt(shape=shape, gen=gen, norm_noise=norm_init_noise, sigma=sig[0])
+        else:
+            xt = xT
+            zt = self.convert_coordinate(xt, sigma=sig[0]) if return_log else None
+        B = xt.shape[0]
+        w = self._w(B)
+        w.nan_flag.zero_()
+        w.xa.copy_(xt)
+        xt, nxt = w.xa, w.xb
+        eps_list, z_list, x0_prec_list, x0_postc_list, const_loss_list = [], [], [], [], []
+        if return_log:
+            z_list = [zt.cpu()]
+        steps = sch.num_inference_steps
+        ts_host = sch.timesteps_host.tolist()
+        best_val, best_x0 = 10000, xt
+        x0 = xt
+        for ind in range(len(ts_host) - 1):
+            t = ts_host[ind]
+            if ind == steps - 1 and new_eta is not None:
+                sch.eta = new_eta
+            sigma_t, sigma_prev = sig[ind:ind + 1], sig[ind + 1:ind + 2]
+            cur_style, cur_refine = style, refine_prior_sigma
+            if t > sigma_pred_threshold:
+                cur_style, cur_refine = "base", False
+            eps, eps_logvar, sigma_t, sigma_prev = self.get_denoise_vector(
+                xt, t, sigma_t, sigma_prev, cur_style, norm_eps, refine_prior_sigma=cur_refine, chunk_size=chunk_size)
+            x0_hat = sch.pred_xstart(xt, eps, sigma_t, clip=self.clip_mode, out=w.x0)
+            if constrain_fn is not None and (free_const_steps <= 0 or ind <= free_const_steps):
+                x0 = constrain_fn(x0_hat)
+            else:
+                x0 = x0_hat
+            noise = noise_fn(ind, x0) if noise_fn is not None else None
+            sch.pred_xprev(x0=x0, eps=eps, sigma_t=sigma_t, sigma_prev=sigma_prev, xt=xt, log_variance=eps_logvar,
+                           noise=noise, out=nxt, nan_flag=w.nan_flag)
+            if step_hook is not None:
+                step_hook(ind, dict(xt=xt, eps=eps, x0_hat=x0_hat, x0=x0, x_prev=nxt, sigma_t=sigma_t,
+                                    sigma_prev=sigma_prev))
+            if constrain_loss is not None:
+                const, _ = constrain_loss(x0.clamp(-1, 1))
+                const_val = torch.mean(const)
+                if const_val < best_val:
+                    best_x0 = x0.clone()
+                    best_val = const_val
+                if return_log:
+                    const_loss_list.append(const.cpu())
+            else:
+                best_x0 = x0
+            if return_log:
+                z_list.append(self.convert_coordinate(nxt, sigma=sigma_prev).cpu())
+                eps_list.append(eps.cpu())
+                x0_prec_list.append(x0_hat.cpu())
+                x0_postc_list.append(x0.cpu())
+            xt, nxt = nxt, xt
+            if (ind + 1) % self.nan_check_every == 0 and int(w.nan_flag.item()) != 0:
+                break
+        result = best_x0 if return_best else x0
+        result = result.cpu() if to_cpu else result
+        return result, [z_list, eps_list, x0_prec_list, x0_postc_list, const_loss_list]
+
+
+class ImageExperiment(ExperimentDiffusion):
+    """src/experiments.py:553-559."""
+
+    def __init__(self, model, scheduler, batch_size=64, data_shape=(3, 32, 32), seed=0, device="cuda:0",
+                 save_folder="./", dist_train=False, time_shift=0):
+        super().__init__(model=model, scheduler=scheduler, batch_size=batch_size, data_shape=data_shape,
+                         save_folder=save_folder, seed=seed, device=device, dist_train=dist_train,
+                         time_shift=time_shift)

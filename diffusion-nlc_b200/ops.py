@@ -10,6 +10,17 @@ from ._lib import NLC_BF16, NLC_F32
 OP_DTYPES = {NLC_BF16: torch.bfloat16, NLC_F32: torch.float32}
 
 
+class _Stats:
+    """Launch accounting for bench.py: `launches` counts kernels enqueued through this module; when
+    `conv_timer` is a list, every nlc_conv_tc launch is bracketed by CUDA events on the launching stream and
+    (flops, start, stop) is appended."""
+    launches = 0
+    conv_timer = None
+
+
+STATS = _Stats()
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -100,7 +111,15 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.out_f32, d.ld_out_f32 = out_f32.ptr, out_f32.ld
     if out_op is not None:
         d.out_op, d.ld_out_op = out_op.ptr, out_op.ld
+    timer = STATS.conv_timer
+    if timer is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(_lib.lib().nlc_conv_tc(_ctx(srcs[0].t), C.byref(d), _stream()))
+    STATS.launches += 1
+    if timer is not None:
+        e1.record()
+        timer.append((2.0 * B * Ho * Wo * Cout * sum(sg[4] for sg in segs), e0, e1))
 
 
 def conv_in_nchw(x_nchw, in_scale, weight, bias, out_f32, out_op, op_dtype):
@@ -112,6 +131,7 @@ def conv_in_nchw(x_nchw, in_scale, weight, bias, out_f32, out_op, op_dtype):
         C.c_void_p(out_f32.ptr) if out_f32 is not None else None, out_f32.ld if out_f32 is not None else 0,
         C.c_void_p(out_op.ptr) if out_op is not None else None, out_op.ld if out_op is not None else 0,
         op_dtype, _stream()))
+    STATS.launches += 1
 
 
 def conv_out_nchw(x_op, op_dtype, weight, bias, out_nchw):
@@ -120,6 +140,7 @@ def conv_out_nchw(x_op, op_dtype, weight, bias, out_nchw):
     _lib.check(_lib.lib().nlc_conv_out_nchw(
         _ctx(x_op.t), C.c_void_p(x_op.ptr), op_dtype, x_op.ld, x_op.B, x_op.C, x_op.H, x_op.W, _p(weight), _p(bias),
         Cout, _p(out_nchw), _stream()))
+    STATS.launches += 1
 
 
 def groupnorm_ws(B, HW, C, groups):
@@ -132,6 +153,7 @@ def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=
     _lib.check(_lib.lib().nlc_groupnorm(
         _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H * x.W, x.C, groups, eps, _p(gamma), _p(beta), _p(scale),
         _p(shift), ld_ss, 1 if silu else 0, C.c_void_p(y_op.ptr), y_op.ld, op_dtype, _p(ws), _stream()))
+    STATS.launches += 2
 
 
 def resample(x, mode, y_f32, y_op, op_dtype):
@@ -140,6 +162,7 @@ def resample(x, mode, y_f32, y_op, op_dtype):
         _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, mode,
         C.c_void_p(y_f32.ptr) if y_f32 is not None else None, y_f32.ld if y_f32 is not None else 0,
         C.c_void_p(y_op.ptr) if y_op is not None else None, y_op.ld if y_op is not None else 0, op_dtype, _stream()))
+    STATS.launches += 1
 
 
 def attention_ws(op_dtype, B, T, heads, dh):
@@ -152,6 +175,7 @@ def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale,
     _lib.check(_lib.lib().nlc_attention(
         _ctx(qkv.t), C.c_void_p(qkv.ptr), op_dtype, qkv.ld, q_off, k_off, v_off, head_stride, qkv.B, T, heads, dh,
         scale, C.c_void_p(out.ptr), out.ld, _p(ws), _stream()))
+    STATS.launches += 4 if T >= 128 else 1
 
 
 def linear(x, W, bias, y, act_in=0, act_out=0):
@@ -161,6 +185,7 @@ def linear(x, W, bias, y, act_in=0, act_out=0):
     assert W.is_contiguous() and W.shape[1] == K and x.stride(1) == 1 and y.stride(1) == 1
     _lib.check(_lib.lib().nlc_linear(_ctx(x), _p(x), x.stride(0), B, K, _p(W), _p(bias), N, act_in, act_out, _p(y),
                                      y.stride(0), _stream()))
+    STATS.launches += 1
 
 
 def timestep_embedding(t, freqs, cos_first, out):
@@ -168,18 +193,21 @@ def timestep_embedding(t, freqs, cos_first, out):
     half = freqs.shape[0]
     _lib.check(_lib.lib().nlc_timestep_embedding(_ctx(t), _p(t), B, _p(freqs), half, 1 if cos_first else 0, _p(out),
                                                  out.stride(0), _stream()))
+    STATS.launches += 1
 
 
 def row_norm(x, out):
     B = x.shape[0]
     d = x[0].numel()
     _lib.check(_lib.lib().nlc_row_norm(_ctx(x), _p(x), B, d, _p(out), _stream()))
+    STATS.launches += 1
 
 
 def normalize_rows_(x):
     B = x.shape[0]
     d = x[0].numel()
     _lib.check(_lib.lib().nlc_normalize_rows(_ctx(x), _p(x), B, d, _stream()))
+    STATS.launches += 1
 
 
 def refine_sigma(norms, B, d, sigma_in, norm_min, norm_max, refine, t_fixed, table, time_shift, sigma_out, t_out,
@@ -188,6 +216,7 @@ def refine_sigma(norms, B, d, sigma_in, norm_min, norm_max, refine, t_fixed, tab
         _ctx(sigma_in), _p(norms), B, d, _p(sigma_in), sigma_in.numel(), norm_min, norm_max, 1 if refine else 0,
         float(t_fixed), _p(table), table.numel() if table is not None else 0, int(time_shift), _p(sigma_out),
         _p(t_out), _p(in_scale_out), _stream()))
+    STATS.launches += 1
 
 
 def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out):
@@ -195,6 +224,7 @@ def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_pre
     _lib.check(_lib.lib().nlc_sigma_correct(
         _ctx(r), _p(r), _p(sigma), _p(sigma_prev), sigma_prev.numel(), B, 1 if update_prev else 0, _p(table),
         table.numel(), _p(sigma_hat), _p(sigma_prev_hat), _p(t_hat), _p(in_scale_out), _stream()))
+    STATS.launches += 1
 
 
 def pred_xstart(xt, eps, sigma, clip, x0):
@@ -202,6 +232,7 @@ def pred_xstart(xt, eps, sigma, clip, x0):
     d = xt[0].numel()
     _lib.check(_lib.lib().nlc_pred_xstart(_ctx(xt), _p(xt), _p(eps), _p(sigma), sigma.numel(), B, d, clip, _p(x0),
                                           _stream()))
+    STATS.launches += 1
 
 
 def pred_xprev(sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_coef, sigma, sigma_prev, x_prev,
@@ -212,3 +243,4 @@ def pred_xprev(sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_c
         _ctx(x0), sched, float(eta), _p(x0), _p(eps), _p(xt), _p(noise), _p(learned_v), logvar_mode,
         float(min_var_coef), _p(sigma), sigma.numel(), _p(sigma_prev), sigma_prev.numel(), B, d, _p(x_prev),
         _p(nan_flag), _stream()))
+    STATS.launches += 1
