@@ -46,8 +46,7 @@ class OpDesc(C.Structure):
         ("task", C.c_int), ("channels", C.c_int), ("R", C.c_int), ("ratio", C.c_int),
         ("idx_host", C.c_void_p), ("n_idx", C.c_int64),
         ("U_small_host", C.c_void_p), ("V_small_host", C.c_void_p), ("sing_small_host", C.c_void_p),
-        ("m_small", C.c_int), ("zero_thresh", C.c_float),
-        ("perm_host", C.c_void_p), ("singulars_host", C.c_void_p), ("n_sing", C.c_int64),
+        ("m_small", C.c_int), ("mult_host", C.c_void_p), ("pinv_mult_host", C.c_void_p),
     ]
 
 
@@ -81,10 +80,12 @@ _SIGNATURES = {
     "nlc_op_create": (_I, [_P, C.POINTER(OpDesc), C.POINTER(_P)]),
     "nlc_op_destroy": (None, [_P]),
     "nlc_op_ydim": (_I64, [_P]),
-    "nlc_op_A": (_I, [_P, _P, _I, _P, _P]),
-    "nlc_op_At": (_I, [_P, _P, _I, _P, _P]),
-    "nlc_op_Apinv": (_I, [_P, _P, _I, _P, _P]),
+    "nlc_op_ws": (_SZ, [_P, _I]),
+    "nlc_op_A": (_I, [_P, _P, _I, _P, _P, _P]),
+    "nlc_op_At": (_I, [_P, _P, _I, _P, _P, _P]),
+    "nlc_op_Apinv": (_I, [_P, _P, _I, _P, _P, _P]),
     "nlc_op_project": (_I, [_P, _P, _P, _I, _P, _P, _P]),
+    "nlc_l1_diff_rows": (_I, [_P, _P, _P, _I, _I64, _P, _P]),
 }
 
 

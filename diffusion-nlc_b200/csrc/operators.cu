@@ -1,0 +1,503 @@
+// DDNM constraint operators: H = A, H^T = At, H^+ = A_pinv of functions/svd_operators.py and
+// the fused projection  x0_hat = x0 - A^+(A x0 - y)  of image_sample.py:376-379, in closed form on the NCHW image.
+//
+// The reference applies U, Sigma, V^T as chains of clone / reshape / permute / index_put / matmul launches on
+// flattened [B, 3R^2] rows; the permutations between the "spectral" ordering and the image cancel inside A, At and
+// A^+, which leaves per task:
+//   Inpainting  (:324-359)  gather / scatter of the kept (pixel, channel) entries
+//   Colorization(:627-667)  per-pixel dot with v0 = V_small[:,0] and its transpose
+//   SuperRes    (:479-533)  per r x r patch dot with v0 = V_small[:,0] and its transpose
+//   WalshHadamardCS (:211-251)  orthonormal 2-D fast Walsh-Hadamard transform (same butterfly order as the
+//                           reference's 1-D FWHT over R^2 entries) + a permutation gather
+//   SRConv (:851-931), Deblurring (:934-1014)  separable:  U_s (M o (V_s^T X V_s)) U_s^T  with a spectral
+//                           multiplier table M built by the host from the reference's own perm / singulars
+// All kernels are HBM-bound fp32 (the separable pair adds eight small fp32 GEMMs per image-channel).
+#include <string.h>
+
+#include <vector>
+
+#include "common.h"
+#include "ptx.cuh"
+
+struct nlc_op {
+    nlc_ctx* ctx;
+    int task, C, R, ratio, m;
+    int64_t ydim;
+    int* idx_a;   // INPAINT: kept[k] = pixel*3+c ; WHCS: invperm[q]
+    int* idx_b;   // INPAINT: pos2k[pixel*3+c] (-1 = missing)
+    int n_kept;
+    float u, s;
+    float* v0;    // COLOR: 3 ; SR_AVG: r*r
+    float *Us, *Vs, *mult, *pinv;  // SEPARABLE
+};
+
+namespace nlc {
+
+// ---------------------------------------------------------------- colourisation / avg-pool SR
+// mode 0: A, 1: At, 2: A_pinv, 3: project.  One thread per (sample, low-res pixel); P = patch edge (1 for colour).
+template <int MODE>
+__global__ void __launch_bounds__(256) needle_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                      float* __restrict__ out, int B, int C, int R, int r, int per_ch,
+                                                      float u, float s, const float* __restrict__ v0) {
+    // per_ch = 1: avg-pool SR (one measurement per channel and patch, v0 over the r*r patch)
+    // per_ch = 0: colourisation (one measurement per pixel, v0 over the 3 channels, r == 1)
+    const int yd = R / r;
+    const long long n_meas = per_ch ? static_cast<long long>(B) * C * yd * yd : static_cast<long long>(B) * R * R;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_meas) return;
+    const int K = per_ch ? r * r : C;
+    // element k of the needle lives at base + off(k)
+    size_t base;
+    if (per_ch) {
+        const int j = static_cast<int>(i % yd), ii = static_cast<int>((i / yd) % yd);
+        const long long bc = i / (static_cast<long long>(yd) * yd);
+        base = (static_cast<size_t>(bc) * R + static_cast<size_t>(ii) * r) * R + static_cast<size_t>(j) * r;
+    } else {
+        const long long b = i / (static_cast<long long>(R) * R), p = i - b * R * R;
+        base = static_cast<size_t>(b) * C * R * R + p;
+    }
+    auto off = [&](int k) -> size_t {
+        return per_ch ? static_cast<size_t>(k / r) * R + (k % r) : static_cast<size_t>(k) * R * R;
+    };
+    float meas = 0.f;
+    if (MODE == 0 || MODE == 3) {
+        float dot = 0.f;
+        for (int k = 0; k < K; ++k) dot = fmaf(v0[k], x[base + off(k)], dot);
+        meas = u * (s * dot);  // U * (singulars * Vt(x))
+        if (MODE == 0) {
+            out[i] = meas;
+            return;
+        }
+    }
+    float t;
+    if (MODE == 1) t = s * (u * y[i]);                       // V(add_zeros(singulars * Ut(y)))
+    else if (MODE == 2) t = (u * y[i]) * (1.0f / s);         // V(add_zeros(Ut(y) * 1/singulars))
+    else t = (u * (meas - y[i])) * (1.0f / s);               // A^+(A x0 - y)
+    for (int k = 0; k < K; ++k) {
+        const float v = v0[k] * t;
+        out[base + off(k)] = MODE == 3 ? x[base + off(k)] - v : v;
+    }
+}
+
+// ---------------------------------------------------------------- inpainting
+__global__ void inpaint_A_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int HW,
+                                 const int* __restrict__ kept, int n_kept) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * n_kept) return;
+    const int b = static_cast<int>(i / n_kept), k = static_cast<int>(i - static_cast<long long>(b) * n_kept);
+    const int j = kept[k], p = j / C, c = j - p * C;
+    y[i] = x[(static_cast<size_t>(b) * C + c) * HW + p];
+}
+// mode 1/2: scatter (At == A^+, all singulars are 1); mode 3: project
+template <int MODE>
+__global__ void inpaint_back_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                    int B, int C, int HW, const int* __restrict__ pos2k, int n_kept) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * C * HW) return;
+    const int p = static_cast<int>(i % HW);
+    const int c = static_cast<int>((i / HW) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(HW) * C));
+    const int k = pos2k[p * C + c];
+    if (MODE == 3) {
+        const float xv = x[i];
+        out[i] = k >= 0 ? xv - (xv - y[static_cast<size_t>(b) * n_kept + k]) : xv;
+    } else {
+        out[i] = k >= 0 ? y[static_cast<size_t>(b) * n_kept + k] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------- Walsh-Hadamard
+// rows: one CTA per image row, R/2 threads, butterflies h = 1 .. R/2 (the reference's first log2(R) stages)
+__global__ void fwht_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int R) {
+    extern __shared__ float row[];
+    const size_t base = static_cast<size_t>(blockIdx.x) * R;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) row[i] = in[base + i];
+    __syncthreads();
+    for (int h = 1; h < R; h <<= 1) {
+        for (int t = threadIdx.x; t < R / 2; t += blockDim.x) {
+            const int i = (t / h) * 2 * h + (t % h);
+            const float a = row[i], b = row[i + h];
+            row[i] = a + b;
+            row[i + h] = a - b;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < R; i += blockDim.x) out[base + i] = row[i];
+}
+// columns: CTA = 32 columns x R rows of one plane; stages h = R .. R^2/2 of the flattened transform, then / R.
+// If base != nullptr writes base - value (the projection's final subtraction).
+__global__ void __launch_bounds__(256) fwht_cols_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         const float* __restrict__ base, int R) {
+    extern __shared__ float tile[];  // [R][32]
+    const int plane = blockIdx.y, c0 = blockIdx.x * 32;
+    const size_t pbase = static_cast<size_t>(plane) * R * R;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < R; r += 8) tile[r * 32 + tx] = in[pbase + static_cast<size_t>(r) * R + c0 + tx];
+    __syncthreads();
+    for (int h = 1; h < R; h <<= 1) {
+        for (int t = ty; t < R / 2; t += 8) {
+            const int i = (t / h) * 2 * h + (t % h);
+            const float a = tile[i * 32 + tx], b = tile[(i + h) * 32 + tx];
+            tile[i * 32 + tx] = a + b;
+            tile[(i + h) * 32 + tx] = a - b;
+        }
+        __syncthreads();
+    }
+    const float fr = static_cast<float>(R);
+    for (int r = ty; r < R; r += 8) {
+        const size_t o = pbase + static_cast<size_t>(r) * R + c0 + tx;
+        const float v = tile[r * 32 + tx] / fr;
+        out[o] = base ? base[o] - v : v;
+    }
+}
+// y[b][j*C + c] = F[b][c][perm[j]], j < m  (gather through invperm: thread per spectral entry q)
+__global__ void whcs_gather_kernel(const float* __restrict__ F, float* __restrict__ y, int B, int C, int N, int m,
+                                   const int* __restrict__ invperm) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * C * N) return;
+    const int q = static_cast<int>(i % N);
+    const int c = static_cast<int>((i / N) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(N) * C));
+    const int j = invperm[q];
+    if (j < m) y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c] = F[i];
+}
+// temp[b][c][q] = j < m ? (F ? F[b][c][q] - y : y)[b][j*C+c] : 0
+__global__ void whcs_scatter_kernel(const float* __restrict__ F, const float* __restrict__ y, float* __restrict__ temp,
+                                    int B, int C, int N, int m, const int* __restrict__ invperm) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= static_cast<long long>(B) * C * N) return;
+    const int q = static_cast<int>(i % N);
+    const int c = static_cast<int>((i / N) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(N) * C));
+    const int j = invperm[q];
+    float v = 0.f;
+    if (j < m) {
+        const float yv = y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c];
+        v = F ? F[i] - yv : yv;
+    }
+    temp[i] = v;
+}
+
+// ---------------------------------------------------------------- strided batched fp32 GEMM (separable operators)
+// Cm[b][i][j] = epi( sum_k A[b*sab + i*sai + k*sak] * Bm[b*sbb + k*sbk + j*sbj] )
+// epi: * mult[(b % nch)*M*N + i*N + j] (if mult) ; - sub[b][i][j] (if sub) ; base[b][i][j] - value (if base)
+struct GemmArgs {
+    const float *A, *Bm, *mult, *sub, *base;
+    float* Cm;
+    long long sab, sai, sak, sbb, sbk, sbj;
+    int M, N, K, nch;
+};
+__global__ void __launch_bounds__(256) sgemm_strided_kernel(const GemmArgs g) {
+    __shared__ float As[16][64 + 1];
+    __shared__ float Bs[16][64 + 1];
+    const int b = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    const float* A = g.A + static_cast<long long>(b) * g.sab;
+    const float* Bm = g.Bm + static_cast<long long>(b) * g.sbb;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < g.K; k0 += 16) {
+        for (int t = threadIdx.x; t < 64 * 16; t += 256) {
+            // pick the faster-varying index per operand so that global reads coalesce along unit strides
+            int ii, kk;
+            if (g.sak == 1) { kk = t & 15; ii = t >> 4; } else { ii = t & 63; kk = t >> 6; }
+            float v = 0.f;
+            if (i0 + ii < g.M && k0 + kk < g.K) v = A[(i0 + ii) * g.sai + (k0 + kk) * g.sak];
+            As[kk][ii] = v;
+            int jj, k2;
+            if (g.sbk == 1) { k2 = t & 15; jj = t >> 4; } else { jj = t & 63; k2 = t >> 6; }
+            v = 0.f;
+            if (j0 + jj < g.N && k0 + k2 < g.K) v = Bm[(k0 + k2) * g.sbk + (j0 + jj) * g.sbj];
+            Bs[k2][jj] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], bb[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = As[kk][ty + 16 * r], bb[r] = Bs[kk][tx + 16 * r];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(a[r], bb[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+    const size_t cb = static_cast<size_t>(b) * g.M * g.N;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = i0 + ty + 16 * r;
+        if (i >= g.M) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + tx + 16 * c;
+            if (j >= g.N) continue;
+            const size_t o = static_cast<size_t>(i) * g.N + j;
+            float v = acc[r][c];
+            if (g.mult) v *= g.mult[static_cast<size_t>(b % g.nch) * g.M * g.N + o];
+            if (g.sub) v -= g.sub[cb + o];
+            if (g.base) v = g.base[cb + o] - v;
+            g.Cm[cb + o] = v;
+        }
+    }
+}
+
+__global__ void l1_diff_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
+                                    float* __restrict__ out) {
+    __shared__ float red[32];
+    const float* ar = a + static_cast<size_t>(blockIdx.x) * n;
+    const float* br = b + static_cast<size_t>(blockIdx.x) * n;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += fabsf(ar[i] - br[i]);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) out[blockIdx.x] = acc;
+    }
+}
+
+static inline unsigned blocks_for(long long n, int bs = 256) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+static int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const float* A, long long sab, long long sai,
+                       long long sak, const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm,
+                       const float* mult, int nch, const float* sub, const float* base) {
+    GemmArgs g{A, Bm, mult, sub, base, Cm, sab, sai, sak, sbb, sbk, sbj, M, N, K, nch};
+    dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
+    sgemm_strided_kernel<<<grid, 256, 0, st>>>(g);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+// separable forward:  out[b,c] = U_s ( mult_c o (V_s[:, :m]^T X V_s[:, :m]) ) U_s^T  (- sub)
+static int separable_A(nlc_op* op, const float* x, int B, float* y, float* ws, const float* sub, cudaStream_t st) {
+    const int R = op->R, m = op->m, n = B * op->C;
+    float* T1 = ws;                                        // [n][m][R]
+    float* T2 = T1 + static_cast<size_t>(n) * m * R;       // [n][m][m]
+    float* T3 = T2 + static_cast<size_t>(n) * m * m;       // [n][m][m]
+    int rc;
+    // T1 = V_s[:, :m]^T X          A(i,k) = Vs[k*R + i]
+    if ((rc = launch_gemm(st, n, m, R, R, op->Vs, 0, 1, R, x, static_cast<long long>(R) * R, R, 1, T1, nullptr, 1,
+                          nullptr, nullptr))) return rc;
+    // T2 = (T1 V_s[:, :m]) o mult  B(k,j) = Vs[k*R + j]
+    if ((rc = launch_gemm(st, n, m, m, R, T1, static_cast<long long>(m) * R, R, 1, op->Vs, 0, R, 1, T2, op->mult, op->C,
+                          nullptr, nullptr))) return rc;
+    // T3 = U_s T2
+    if ((rc = launch_gemm(st, n, m, m, m, op->Us, 0, m, 1, T2, static_cast<long long>(m) * m, m, 1, T3, nullptr, 1,
+                          nullptr, nullptr))) return rc;
+    // Y = T3 U_s^T (- sub)         B(k,j) = Us[j*m + k]
+    return launch_gemm(st, n, m, m, m, T3, static_cast<long long>(m) * m, m, 1, op->Us, 0, 1, m, y, nullptr, 1, sub,
+                       nullptr);
+}
+// separable backward: out[b,c] = V_s[:, :m] ( table_c o (U_s^T Y U_s) ) V_s[:, :m]^T   (base - value if base)
+static int separable_back(nlc_op* op, const float* y, int B, float* x, float* ws, const float* table, const float* base,
+                          cudaStream_t st) {
+    const int R = op->R, m = op->m, n = B * op->C;
+    float* W1 = ws;                                        // [n][m][m]
+    float* W2 = W1 + static_cast<size_t>(n) * m * m;       // [n][m][m]
+    float* X1 = W2 + static_cast<size_t>(n) * m * m;       // [n][R][m]
+    int rc;
+    if ((rc = launch_gemm(st, n, m, m, m, op->Us, 0, 1, m, y, static_cast<long long>(m) * m, m, 1, W1, nullptr, 1,
+                          nullptr, nullptr))) return rc;                                  // U_s^T Y
+    if ((rc = launch_gemm(st, n, m, m, m, W1, static_cast<long long>(m) * m, m, 1, op->Us, 0, m, 1, W2, table, op->C,
+                          nullptr, nullptr))) return rc;                                  // (W1 U_s) o table
+    if ((rc = launch_gemm(st, n, R, m, m, op->Vs, 0, R, 1, W2, static_cast<long long>(m) * m, m, 1, X1, nullptr, 1,
+                          nullptr, nullptr))) return rc;                                  // V_s[:, :m] W2
+    return launch_gemm(st, n, R, R, m, X1, static_cast<long long>(R) * m, m, 1, op->Vs, 0, 1, R, x, nullptr, 1, nullptr,
+                       base);                                                             // X1 V_s[:, :m]^T
+}
+
+template <typename T>
+static int to_device(T** dst, const T* src, size_t n) {
+    NLC_CHECK_CUDA(cudaMalloc(dst, n * sizeof(T)));
+    NLC_CHECK_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return NLC_OK;
+}
+
+static int fwht2d(nlc_op* op, const float* in, float* out, const float* base, int B, cudaStream_t st) {
+    const int R = op->R, planes = B * op->C;
+    fwht_rows_kernel<<<planes * R, R / 2 > 256 ? 256 : R / 2, R * sizeof(float), st>>>(in, out, R);
+    NLC_CHECK_LAUNCH();
+    const size_t smem = static_cast<size_t>(R) * 32 * sizeof(float);
+    NLC_CHECK_CUDA(cudaFuncSetAttribute(fwht_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    fwht_cols_kernel<<<dim3(R / 32, planes), 256, smem, st>>>(out, out, base, R);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
+    NLC_REQUIRE(ctx && d && out, "nlc_op_create: null argument");
+    NLC_REQUIRE(d->channels >= 1 && d->R >= 1, "nlc_op_create: bad geometry");
+    nlc_op* op = new nlc_op();
+    memset(op, 0, sizeof(*op));
+    op->ctx = ctx, op->task = d->task, op->C = d->channels, op->R = d->R, op->ratio = d->ratio;
+    const long long N = static_cast<long long>(d->R) * d->R, dim = N * d->channels;
+    int rc = NLC_OK;
+    switch (d->task) {
+        case NLC_OP_INPAINT: {
+            NLC_REQUIRE(d->idx_host && d->n_idx >= 0 && d->n_idx <= dim, "nlc_op_create: inpainting needs missing indices");
+            std::vector<int> pos2k(dim, 0), kept;
+            for (int64_t i = 0; i < d->n_idx; ++i) {
+                NLC_REQUIRE(d->idx_host[i] >= 0 && d->idx_host[i] < dim, "nlc_op_create: missing index out of range");
+                pos2k[d->idx_host[i]] = -1;
+            }
+            for (long long j = 0; j < dim; ++j)
+                if (pos2k[j] == 0) { pos2k[j] = static_cast<int>(kept.size()); kept.push_back(static_cast<int>(j)); }
+            op->n_kept = static_cast<int>(kept.size());
+            op->ydim = op->n_kept;
+            if ((rc = to_device(&op->idx_a, kept.data(), kept.size() ? kept.size() : 1)) ||
+                (rc = to_device(&op->idx_b, pos2k.data(), pos2k.size()))) return rc;
+        } break;
+        case NLC_OP_COLOR:
+        case NLC_OP_SR_AVG: {
+            const int K = d->task == NLC_OP_COLOR ? d->channels : d->ratio * d->ratio;
+            NLC_REQUIRE(d->U_small_host && d->V_small_host && d->sing_small_host, "nlc_op_create: SVD factors missing");
+            NLC_REQUIRE(d->task == NLC_OP_COLOR || (d->ratio >= 1 && d->R % d->ratio == 0), "nlc_op_create: bad ratio");
+            op->u = d->U_small_host[0], op->s = d->sing_small_host[0];
+            std::vector<float> v0(K);
+            for (int k = 0; k < K; ++k) v0[k] = d->V_small_host[k * K];  // first column of V_small
+            if ((rc = to_device(&op->v0, v0.data(), K))) return rc;
+            op->ydim = d->task == NLC_OP_COLOR ? N : d->channels * (N / (d->ratio * d->ratio));
+        } break;
+        case NLC_OP_WHCS: {
+            NLC_REQUIRE(d->idx_host && d->n_idx == N && d->ratio >= 1, "nlc_op_create: WH-CS needs perm[R*R]");
+            NLC_REQUIRE((d->R & (d->R - 1)) == 0 && d->R >= 32, "nlc_op_create: WH-CS needs R a power of two >= 32");
+            std::vector<int> inv(N);
+            for (long long j = 0; j < N; ++j) inv[d->idx_host[j]] = static_cast<int>(j);
+            if ((rc = to_device(&op->idx_a, inv.data(), inv.size()))) return rc;
+            op->ydim = dim / d->ratio;
+        } break;
+        case NLC_OP_SEPARABLE: {
+            NLC_REQUIRE(d->U_small_host && d->V_small_host && d->mult_host && d->pinv_mult_host && d->m_small >= 1 &&
+                            d->m_small <= d->R, "nlc_op_create: separable operator needs U_s, V_s and the tables");
+            op->m = d->m_small;
+            const size_t mm = static_cast<size_t>(op->m) * op->m;
+            if ((rc = to_device(&op->Us, d->U_small_host, mm)) || (rc = to_device(&op->Vs, d->V_small_host, N)) ||
+                (rc = to_device(&op->mult, d->mult_host, mm * d->channels)) ||
+                (rc = to_device(&op->pinv, d->pinv_mult_host, mm * d->channels))) return rc;
+            op->ydim = static_cast<int64_t>(d->channels) * mm;
+        } break;
+        default:
+            delete op;
+            return set_error(NLC_EINVAL, "nlc_op_create: unknown task %d", d->task);
+    }
+    *out = op;
+    return NLC_OK;
+}
+
+extern "C" void nlc_op_destroy(nlc_op* op) {
+    if (!op) return;
+    cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->v0);
+    cudaFree(op->Us), cudaFree(op->Vs), cudaFree(op->mult), cudaFree(op->pinv);
+    delete op;
+}
+
+extern "C" int64_t nlc_op_ydim(nlc_op* op) { return op ? op->ydim : 0; }
+
+extern "C" size_t nlc_op_ws(nlc_op* op, int B) {
+    if (!op) return 0;
+    const size_t plane = static_cast<size_t>(op->R) * op->R, n = static_cast<size_t>(B) * op->C;
+    if (op->task == NLC_OP_WHCS) return 2 * n * plane * sizeof(float);
+    if (op->task == NLC_OP_SEPARABLE) return 4 * n * plane * sizeof(float);
+    return 0;
+}
+
+// mode: 0 A, 1 At, 2 A_pinv, 3 project (in = x0, y = y, out = x0_hat)
+static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B, float* out, void* ws_, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(op && in && out && B >= 1, "nlc_op: null argument");
+    float* ws = static_cast<float*>(ws_);
+    const int C = op->C, R = op->R;
+    const long long N = static_cast<long long>(R) * R;
+    switch (op->task) {
+        case NLC_OP_COLOR:
+        case NLC_OP_SR_AVG: {
+            const int per_ch = op->task == NLC_OP_SR_AVG, r = per_ch ? op->ratio : 1;
+            const long long n_meas = per_ch ? static_cast<long long>(B) * C * (N / (r * r)) : static_cast<long long>(B) * N;
+            const unsigned g = blocks_for(n_meas);
+            // A reads x = in; At / A_pinv read y = in; project reads both
+            if (mode == 0) needle_kernel<0><<<g, 256, 0, st>>>(in, nullptr, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
+            else if (mode == 1) needle_kernel<1><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
+            else if (mode == 2) needle_kernel<2><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
+            else needle_kernel<3><<<g, 256, 0, st>>>(in, y, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
+            NLC_CHECK_LAUNCH();
+        } break;
+        case NLC_OP_INPAINT: {
+            if (mode == 0) {
+                if (op->n_kept > 0)
+                    inpaint_A_kernel<<<blocks_for(static_cast<long long>(B) * op->n_kept), 256, 0, st>>>(
+                        in, out, B, C, static_cast<int>(N), op->idx_a, op->n_kept);
+            } else if (mode == 3) {
+                inpaint_back_kernel<3><<<blocks_for(B * C * N), 256, 0, st>>>(in, y, out, B, C, static_cast<int>(N),
+                                                                             op->idx_b, op->n_kept);
+            } else {
+                inpaint_back_kernel<1><<<blocks_for(B * C * N), 256, 0, st>>>(nullptr, in, out, B, C, static_cast<int>(N),
+                                                                             op->idx_b, op->n_kept);
+            }
+            NLC_CHECK_LAUNCH();
+        } break;
+        case NLC_OP_WHCS: {
+            NLC_REQUIRE(ws, "nlc_op: WH-CS needs a workspace (nlc_op_ws)");
+            const int m = static_cast<int>(N / op->ratio);
+            float* F = ws;
+            float* T = ws + static_cast<size_t>(B) * C * N;
+            const unsigned g = blocks_for(B * C * N);
+            int rc;
+            if (mode == 0) {
+                if ((rc = fwht2d(op, in, F, nullptr, B, st))) return rc;
+                whcs_gather_kernel<<<g, 256, 0, st>>>(F, out, B, C, static_cast<int>(N), m, op->idx_a);
+                NLC_CHECK_LAUNCH();
+            } else if (mode == 3) {
+                if ((rc = fwht2d(op, in, F, nullptr, B, st))) return rc;
+                whcs_scatter_kernel<<<g, 256, 0, st>>>(F, y, T, B, C, static_cast<int>(N), m, op->idx_a);
+                NLC_CHECK_LAUNCH();
+                if ((rc = fwht2d(op, T, out, in, B, st))) return rc;  // out = x0 - fwht(T)
+            } else {
+                whcs_scatter_kernel<<<g, 256, 0, st>>>(nullptr, in, T, B, C, static_cast<int>(N), m, op->idx_a);
+                NLC_CHECK_LAUNCH();
+                if ((rc = fwht2d(op, T, out, nullptr, B, st))) return rc;
+            }
+        } break;
+        case NLC_OP_SEPARABLE: {
+            NLC_REQUIRE(ws, "nlc_op: separable operators need a workspace (nlc_op_ws)");
+            if (mode == 0) return separable_A(op, in, B, out, ws, nullptr, st);
+            if (mode == 1) return separable_back(op, in, B, out, ws, op->mult, nullptr, st);
+            if (mode == 2) return separable_back(op, in, B, out, ws, op->pinv, nullptr, st);
+            float* diff = ws + 3 * static_cast<size_t>(B) * C * N;  // A x0 - y
+            int rc;
+            if ((rc = separable_A(op, in, B, diff, ws, y, st))) return rc;
+            return separable_back(op, diff, B, out, ws, op->pinv, in, st);
+        }
+        default:
+            return set_error(NLC_EINVAL, "nlc_op: unknown task");
+    }
+    return NLC_OK;
+}
+
+extern "C" int nlc_op_A(nlc_op* op, const float* x, int B, float* y, void* ws, void* stream) {
+    return op_apply(op, 0, x, nullptr, B, y, ws, stream);
+}
+extern "C" int nlc_op_At(nlc_op* op, const float* y, int B, float* x, void* ws, void* stream) {
+    return op_apply(op, 1, y, nullptr, B, x, ws, stream);
+}
+extern "C" int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* ws, void* stream) {
+    return op_apply(op, 2, y, nullptr, B, x, ws, stream);
+}
+extern "C" int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, void* ws, void* stream) {
+    NLC_REQUIRE(y, "nlc_op_project: y is null");
+    return op_apply(op, 3, x0, y, B, x0_hat, ws, stream);
+}
+
+extern "C" int nlc_l1_diff_rows(nlc_ctx* ctx, const float* a, const float* b, int B, int64_t n, float* out,
+                                void* stream_) {
+    NLC_REQUIRE(ctx && a && b && out, "nlc_l1_diff_rows: null argument");
+    l1_diff_rows_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(a, b, n, out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}

@@ -1,0 +1,217 @@
+"""Host-side mirror of the reference's DDNM operators (functions/svd_operators.py) on libnlc_b200 kernels.
+
+Each class keeps the reference constructor and exposes `A`, `At`, `A_pinv` on `[B, C*R*R]` rows (NCHW-flattened
+images, as the reference's callers pass them: image_sample.py:376-379) plus the fused `project(x0, y)` =
+x0 - A_pinv(A(x0) - y).  The small SVDs are taken on the CPU with the same torch calls as the reference
+(`torch.svd(..., some=False)`), then uploaded once; nothing else runs in torch.
+
+Covered: Inpainting (:324-359), Colorization (:627-667), SuperResolution (:479-533), WalshHadamardCS (:211-251),
+SRConv (:851-931), Deblurring (:934-1014).  The spectral-domain accessors `U/Ut/V/Vt/singulars/add_zeros` and the
+DDNM+ `Lambda*` family are not part of the sampling path.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+INPAINT, COLOR, SR_AVG, WHCS, SEPARABLE = 1, 2, 3, 4, 5
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class A_functions:
+    """Base: owns the nlc_op handle and the per-batch workspace."""
+
+    def __init__(self, desc, keep, device):
+        self.device = torch.device(device)
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._ctx = _lib.ctx(idx)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().nlc_op_create(self._ctx, C.byref(desc), C.byref(h)))
+        del keep  # host arrays only had to outlive nlc_op_create
+        self._h = h
+        self.ydim = int(_lib.lib().nlc_op_ydim(h))
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.lib().nlc_op_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _workspace(self, B):
+        need = int(_lib.lib().nlc_op_ws(self._h, B))
+        if need == 0:
+            return None
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, device=self.device, dtype=torch.uint8)
+        return C.c_void_p(self._ws.data_ptr())
+
+    def _rows(self, v, n):
+        v = v.reshape(v.shape[0], -1)
+        assert v.shape[1] == n, "expected rows of length %d, got %d" % (n, v.shape[1])
+        return v.contiguous().float()
+
+    def A(self, vec):
+        x = self._rows(vec, self.xdim)
+        y = torch.empty(x.shape[0], self.ydim, device=x.device)
+        _lib.check(_lib.lib().nlc_op_A(self._h, x.data_ptr(), x.shape[0], y.data_ptr(), self._workspace(x.shape[0]),
+                                       _stream()))
+        return y
+
+    def At(self, vec):
+        y = self._rows(vec, self.ydim)
+        x = torch.empty(y.shape[0], self.xdim, device=y.device)
+        _lib.check(_lib.lib().nlc_op_At(self._h, y.data_ptr(), y.shape[0], x.data_ptr(), self._workspace(y.shape[0]),
+                                        _stream()))
+        return x
+
+    def A_pinv(self, vec):
+        y = self._rows(vec, self.ydim)
+        x = torch.empty(y.shape[0], self.xdim, device=y.device)
+        _lib.check(_lib.lib().nlc_op_Apinv(self._h, y.data_ptr(), y.shape[0], x.data_ptr(),
+                                           self._workspace(y.shape[0]), _stream()))
+        return x
+
+    def project(self, x0, y, out=None):
+        """x0 - A_pinv(A(x0) - y) in one fused pass; keeps x0's shape."""
+        x = self._rows(x0, self.xdim)
+        yy = self._rows(y, self.ydim)
+        o = torch.empty_like(x) if out is None else out
+        _lib.check(_lib.lib().nlc_op_project(self._h, x.data_ptr(), yy.data_ptr(), x.shape[0], o.data_ptr(),
+                                             self._workspace(x.shape[0]), _stream()))
+        return o.view(x0.shape)
+
+
+def _fptr(t):
+    return t.data_ptr()
+
+
+class Inpainting(A_functions):
+    def __init__(self, channels, img_dim, missing_indices, device):
+        self.channels, self.img_dim = channels, img_dim
+        self.xdim = channels * img_dim ** 2
+        miss = missing_indices.detach().cpu().to(torch.int64).contiguous()
+        d = _lib.OpDesc(task=INPAINT, channels=channels, R=img_dim, ratio=1, idx_host=_fptr(miss), n_idx=miss.numel())
+        super().__init__(d, (miss,), device)
+
+
+class Colorization(A_functions):
+    def __init__(self, img_dim, device):
+        self.channels, self.img_dim = 3, img_dim
+        self.xdim = 3 * img_dim ** 2
+        A = torch.Tensor([[0.3333, 0.3334, 0.3333]])
+        U, S, V = torch.svd(A, some=False)
+        U, S, V = U.contiguous(), S.contiguous(), V.contiguous()
+        d = _lib.OpDesc(task=COLOR, channels=3, R=img_dim, ratio=1, U_small_host=_fptr(U), V_small_host=_fptr(V),
+                        sing_small_host=_fptr(S))
+        super().__init__(d, (U, S, V), device)
+
+
+class SuperResolution(A_functions):
+    def __init__(self, channels, img_dim, ratio, device):
+        assert img_dim % ratio == 0
+        self.channels, self.img_dim, self.ratio = channels, img_dim, ratio
+        self.xdim = channels * img_dim ** 2
+        A = torch.Tensor([[1 / ratio ** 2] * ratio ** 2])
+        U, S, V = torch.svd(A, some=False)
+        U, S, V = U.contiguous(), S.contiguous(), V.contiguous()
+        d = _lib.OpDesc(task=SR_AVG, channels=channels, R=img_dim, ratio=ratio, U_small_host=_fptr(U),
+                        V_small_host=_fptr(V), sing_small_host=_fptr(S))
+        super().__init__(d, (U, S, V), device)
+
+
+class WalshHadamardCS(A_functions):
+    def __init__(self, channels, img_dim, ratio, perm, device):
+        self.channels, self.img_dim, self.ratio = channels, img_dim, ratio
+        self.xdim = channels * img_dim ** 2
+        p = perm.detach().cpu().to(torch.int64).contiguous()
+        d = _lib.OpDesc(task=WHCS, channels=channels, R=img_dim, ratio=ratio, idx_host=_fptr(p), n_idx=p.numel())
+        super().__init__(d, (p,), device)
+
+
+def _separable(self, U_s, V_s, mult, pinv, channels, img_dim, m, device):
+    U_s, V_s = U_s.contiguous().float(), V_s.contiguous().float()
+    mult, pinv = mult.contiguous().float(), pinv.contiguous().float()
+    d = _lib.OpDesc(task=SEPARABLE, channels=channels, R=img_dim, ratio=1, U_small_host=_fptr(U_s),
+                    V_small_host=_fptr(V_s), m_small=m, mult_host=_fptr(mult), pinv_mult_host=_fptr(pinv))
+    A_functions.__init__(self, d, (U_s, V_s, mult, pinv), device)
+
+
+def _zero_guarded_inverse(s):
+    f = 1.0 / s
+    f[s == 0] = 0.0
+    return f
+
+
+class SRConv(A_functions):
+    """Separable strided blur (bicubic SR).  A x = U_s ((s s^T) o (V_s^T X V_s)[:m,:m]) U_s^T per channel."""
+
+    def __init__(self, kernel, channels, img_dim, device, stride=1):
+        self.channels, self.img_dim, self.ratio = channels, img_dim, stride
+        self.xdim = channels * img_dim ** 2
+        m = img_dim // stride
+        kernel = kernel.detach().cpu().float()
+        half = kernel.shape[0] // 2
+        A_small = torch.zeros(m, img_dim)
+        for i in range(stride // 2, img_dim + stride // 2, stride):
+            for j in range(i - half, i + half):
+                je = j
+                if je < 0:
+                    je = -je - 1  # reflective padding
+                if je >= img_dim:
+                    je = (img_dim - 1) - (je - img_dim)
+                A_small[i // stride, je] += kernel[j - i + half]
+        U_s, s, V_s = torch.svd(A_small, some=False)
+        s = s.clone()
+        s[s < 3e-2] = 0
+        sing = torch.matmul(s.reshape(m, 1), s.reshape(1, m)).reshape(m * m)
+        mult = sing.repeat(channels, 1)
+        pinv = _zero_guarded_inverse(sing).repeat(channels, 1)
+        _separable(self, U_s, V_s, mult, pinv, channels, img_dim, m, device)
+
+
+class Deblurring(A_functions):
+    """Separable blur with zero padding.  The reference pairs the sorted singular values with the interleaved
+    (position, channel) spectral entries through `_singulars.repeat(1, 3)` (functions/svd_operators.py:995-996,
+    1006-1014); the multiplier tables below reproduce exactly that pairing."""
+
+    def __init__(self, kernel, channels, img_dim, device, ZERO=3e-2):
+        self.channels, self.img_dim = channels, img_dim
+        self.xdim = channels * img_dim ** 2
+        R = img_dim
+        kernel = kernel.detach().cpu().float()
+        half = kernel.shape[0] // 2
+        A_small = torch.zeros(R, R)
+        for i in range(R):
+            for j in range(i - half, i + half):
+                if 0 <= j < R:
+                    A_small[i, j] = kernel[j - i + half]
+        U_s, s, V_s = torch.svd(A_small, some=False)
+        s = s.clone()
+        s[s < ZERO] = 0
+        big = torch.matmul(s.reshape(R, 1), s.reshape(1, R)).reshape(R * R)
+        big_sorted, perm = big.sort(descending=True)
+        full = big_sorted.repeat(1, channels).reshape(-1)  # [S, S, S] concatenated, as in the reference
+        mult = torch.empty(channels, R * R)
+        mult[:, perm] = full.reshape(R * R, channels).t()
+        pinv = torch.empty(channels, R * R)
+        pinv[:, perm] = _zero_guarded_inverse(full).reshape(R * R, channels).t()
+        _separable(self, U_s, V_s, mult, pinv, channels, R, R, device)
+
+
+def l1_diff_rows(a, b):
+    """Per-sample ||a - b||_1 (Constraint_Function.loss, image_sample.py:325-333)."""
+    a2 = a.reshape(a.shape[0], -1).contiguous().float()
+    b2 = b.reshape(b.shape[0], -1).contiguous().float()
+    out = torch.empty(a2.shape[0], device=a2.device)
+    idx = a2.device.index if a2.device.index is not None else torch.cuda.current_device()
+    _lib.check(_lib.lib().nlc_l1_diff_rows(_lib.ctx(idx), a2.data_ptr(), b2.data_ptr(), a2.shape[0], a2.shape[1],
+                                           out.data_ptr(), _stream()))
+    return out

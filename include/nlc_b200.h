@@ -213,30 +213,34 @@ int nlc_pred_xprev(nlc_ctx* ctx, int sched, double eta, const float* x0, const f
 
 typedef struct nlc_op nlc_op;
 
+/* Host-side description of one operator.  The small SVD factors are computed by the host exactly as the
+ * reference does (torch.svd of the 1 x r^2 / 1 x 3 / R/f x R matrices, functions/svd_operators.py:486-488,
+ * 632-634, 878-885, 953-961) and handed over as plain arrays. */
 typedef struct {
     int task;
     int channels, R;
-    int ratio;                /* SR_AVG / WHCS                                         */
-    const int64_t* idx_host;  /* INPAINT: missing indices (pixel*3+c); WHCS: perm[R*R] */
+    int ratio;                    /* SR_AVG: pooling factor; WHCS: compression ratio                      */
+    const int64_t* idx_host;      /* INPAINT: missing indices (pixel*3+c); WHCS: perm[R*R]                 */
     int64_t n_idx;
-    /* SEPARABLE: small-matrix SVD factors computed by the host exactly as the reference does */
-    const float* U_small_host; /* [m_small, m_small]  */
-    const float* V_small_host; /* [R, R]              */
-    const float* sing_small_host; /* [m_small]        */
-    int m_small;               /* R/f (SRConv) or R (Deblurring)                        */
-    float zero_thresh;         /* singulars below this are zero (3e-2 in the reference) */
-    const int64_t* perm_host;  /* Deblurring/SRConv singular ordering                   */
-    const float* singulars_host; /* ordered singulars                                   */
-    int64_t n_sing;
+    const float* U_small_host;    /* COLOR / SR_AVG: [1,1]; SEPARABLE: [m,m] row-major                     */
+    const float* V_small_host;    /* COLOR: [3,3]; SR_AVG: [r^2,r^2]; SEPARABLE: [R,R] row-major           */
+    const float* sing_small_host; /* COLOR / SR_AVG: [1]                                                   */
+    int m_small;                  /* SEPARABLE: R/f (SRConv) or R (Deblurring)                             */
+    const float* mult_host;       /* SEPARABLE: [channels, m*m] spectral multipliers used by A and At      */
+    const float* pinv_mult_host;  /* SEPARABLE: [channels, m*m] zero-guarded reciprocals used by A^+       */
 } nlc_op_desc;
 
 int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out);
 void nlc_op_destroy(nlc_op* op);
-int64_t nlc_op_ydim(nlc_op* op);
-int nlc_op_A(nlc_op* op, const float* x, int B, float* y, void* stream);
-int nlc_op_At(nlc_op* op, const float* y, int B, float* x, void* stream);
-int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* stream);
-int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, float* l1_fwd, void* stream);
+int64_t nlc_op_ydim(nlc_op* op);          /* length of one measurement row y                               */
+size_t nlc_op_ws(nlc_op* op, int B);      /* workspace bytes the calls below need for batch B (may be 0)   */
+int nlc_op_A(nlc_op* op, const float* x, int B, float* y, void* workspace, void* stream);
+int nlc_op_At(nlc_op* op, const float* y, int B, float* x, void* workspace, void* stream);
+int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* workspace, void* stream);
+/* x0_hat = x0 - A^+(A x0 - y), fused (image_sample.py:376-379) */
+int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, void* workspace, void* stream);
+/* out[b] = sum_i |a[b,i] - b[b,i]|: the L1 constraint residuals of Constraint_Function.loss (image_sample.py:325-333) */
+int nlc_l1_diff_rows(nlc_ctx* ctx, const float* a, const float* b, int B, int64_t n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,321 @@
+"""ORACLE (test infrastructure, not product code) — CPU fp32 restatement of the reference's DDNM operators and of
+the constraint projection.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
+Pinned by tests/test_oracle_vs_reference.py (live against functions/svd_operators.py when /root/reference is
+present) and by tests/golden/operators_*.pt.
+
+Every operator is kept in the reference's own spectral form  A = U Sigma V^T,  A^T = V Sigma^T U^T,
+A^+ = V Sigma^+ U^T  (functions/svd_operators.py:52-80) with explicit `Vt / V / Ut / U / singulars` steps, so this
+file restates the algorithm rather than the closed forms the CUDA kernels use.
+  Inpainting :324-359   Colorization :627-667   SuperResolution :479-533   WalshHadamardCS :211-251
+  SRConv :851-931       Deblurring :934-1014    projection image_sample.py:376-379
+"""
+import torch
+
+
+class SpectralOp:
+    def A(self, x):
+        t = self.Vt(x)
+        s = self.singulars()
+        return self.U(s * t[:, :s.shape[0]])
+
+    def At(self, y):
+        t = self.Ut(y)
+        s = self.singulars()
+        return self.V(self.add_zeros(s * t[:, :s.shape[0]]))
+
+    def A_pinv(self, y):
+        t = self.Ut(y).clone()
+        s = self.singulars()
+        f = 1.0 / s
+        f[s == 0] = 0.0
+        t[:, :s.shape[0]] = t[:, :s.shape[0]] * f
+        return self.V(self.add_zeros(t))
+
+    def project(self, x0, y):
+        b = x0.shape[0]
+        return x0 - self.A_pinv(self.A(x0.reshape(b, -1)) - y.reshape(b, -1)).reshape(x0.shape)
+
+
+class Inpainting(SpectralOp):
+    def __init__(self, channels, R, missing):
+        self.C, self.R = channels, R
+        n = channels * R * R
+        self.missing = missing.long()
+        mask = torch.ones(n, dtype=torch.bool)
+        mask[self.missing] = False
+        self.kept = torch.nonzero(mask).reshape(-1)
+
+    def _interleave(self, x):  # NCHW flat -> pixel-major (pixel*C + c)
+        b = x.shape[0]
+        return x.reshape(b, self.C, -1).transpose(1, 2).reshape(b, -1)
+
+    def Vt(self, x):
+        t = self._interleave(x)
+        return torch.cat([t[:, self.kept], t[:, self.missing]], dim=1)
+
+    def V(self, v):
+        b = v.shape[0]
+        out = torch.zeros_like(v)
+        out[:, self.kept] = v[:, :self.kept.numel()]
+        out[:, self.missing] = v[:, self.kept.numel():]
+        return out.reshape(b, -1, self.C).transpose(1, 2).reshape(b, -1)
+
+    def U(self, v):
+        return v.reshape(v.shape[0], -1)
+
+    Ut = U
+
+    def singulars(self):
+        return torch.ones(self.kept.numel())
+
+    def add_zeros(self, v):
+        out = torch.zeros(v.shape[0], self.C * self.R * self.R)
+        out[:, :v.shape[1]] = v
+        return out
+
+
+class _Needle(SpectralOp):
+    """Shared by Colorization (needle = the 3 channels of a pixel) and SuperResolution (needle = an r x r patch):
+    a 1 x K matrix per needle, SVD'ed once."""
+
+    def _svd(self, row):
+        self.Us, self.Ss, self.Vs = torch.svd(torch.Tensor([row]), some=False)
+
+    def U(self, v):
+        return self.Us[0, 0] * v.reshape(v.shape[0], -1)
+
+    Ut = U
+
+
+class Colorization(_Needle):
+    def __init__(self, R):
+        self.C, self.R = 3, R
+        self._svd([0.3333, 0.3334, 0.3333])
+
+    def Vt(self, x):
+        b = x.shape[0]
+        needles = x.reshape(b, 3, -1).transpose(1, 2)  # [b, pixel, c]
+        rot = torch.matmul(self.Vs.t(), needles.reshape(-1, 3, 1)).reshape(b, -1, 3)
+        return rot.transpose(1, 2).reshape(b, -1)  # component-major
+
+    def V(self, v):
+        b = v.shape[0]
+        needles = v.reshape(b, 3, -1).transpose(1, 2)
+        rot = torch.matmul(self.Vs, needles.reshape(-1, 3, 1)).reshape(b, -1, 3)
+        return rot.transpose(1, 2).reshape(b, -1)
+
+    def singulars(self):
+        return self.Ss.repeat(self.R * self.R)
+
+    def add_zeros(self, v):
+        out = torch.zeros(v.shape[0], 3 * self.R * self.R)
+        out[:, :self.R * self.R] = v.reshape(v.shape[0], -1)
+        return out
+
+
+class SuperResolution(_Needle):
+    def __init__(self, channels, R, ratio):
+        self.C, self.R, self.r, self.yd = channels, R, ratio, R // ratio
+        self._svd([1 / ratio ** 2] * ratio ** 2)
+
+    def Vt(self, x):
+        b, r, yd = x.shape[0], self.r, self.yd
+        img = x.reshape(b, self.C, yd, r, yd, r).permute(0, 1, 2, 4, 3, 5).reshape(b, self.C, yd * yd, r * r)
+        rot = torch.matmul(self.Vs.t(), img.reshape(-1, r * r, 1)).reshape(b, self.C, yd * yd, r * r)
+        out = torch.zeros(b, self.C * self.R * self.R)
+        n0 = self.C * yd * yd
+        out[:, :n0] = rot[..., 0].reshape(b, n0)
+        for k in range(r * r - 1):
+            out[:, n0 + k::r * r - 1] = rot[..., k + 1].reshape(b, n0)
+        return out
+
+    def V(self, v):
+        b, r, yd = v.shape[0], self.r, self.yd
+        n0 = self.C * yd * yd
+        comp = torch.zeros(b, self.C, yd * yd, r * r)
+        comp[..., 0] = v[:, :n0].reshape(b, self.C, -1)
+        for k in range(r * r - 1):
+            comp[..., k + 1] = v[:, n0 + k::r * r - 1].reshape(b, self.C, -1)
+        rot = torch.matmul(self.Vs, comp.reshape(-1, r * r, 1)).reshape(b, self.C, yd, yd, r, r)
+        return rot.permute(0, 1, 2, 4, 3, 5).reshape(b, -1)
+
+    def singulars(self):
+        return self.Ss.repeat(self.C * self.yd * self.yd)
+
+    def add_zeros(self, v):
+        v = v.reshape(v.shape[0], -1)
+        out = torch.zeros(v.shape[0], v.shape[1] * self.r ** 2)
+        out[:, :v.shape[1]] = v
+        return out
+
+
+class WalshHadamardCS(SpectralOp):
+    def __init__(self, channels, R, ratio, perm):
+        self.C, self.R, self.ratio, self.perm = channels, R, ratio, perm.long()
+
+    def fwht(self, v):
+        b, n = v.shape[0], self.R * self.R
+        a = v.reshape(b, self.C, n).clone()
+        h = 1
+        while h < n:
+            a = a.reshape(b, self.C, -1, 2 * h)
+            lo, hi = a[..., :h].clone(), a[..., h:].clone()
+            a = torch.cat([lo + hi, lo - hi], dim=-1)
+            h *= 2
+        return a.reshape(b, self.C, n) / self.R
+
+    def Vt(self, x):
+        b = x.shape[0]
+        return self.fwht(x)[:, :, self.perm].transpose(1, 2).reshape(b, -1)
+
+    def V(self, v):
+        b = v.shape[0]
+        t = torch.zeros(b, self.C, self.R * self.R)
+        t[:, :, self.perm] = v.reshape(b, -1, self.C).transpose(1, 2)
+        return self.fwht(t).reshape(b, -1)
+
+    def U(self, v):
+        return v.reshape(v.shape[0], -1)
+
+    Ut = U
+
+    def singulars(self):
+        return torch.ones(self.C * self.R * self.R // self.ratio)
+
+    def add_zeros(self, v):
+        out = torch.zeros(v.shape[0], self.C * self.R * self.R)
+        out[:, :v.shape[1]] = v.reshape(v.shape[0], -1)
+        return out
+
+
+class _Separable(SpectralOp):
+    def _left(self, M, v, dim):
+        return torch.matmul(M, v.reshape(-1, dim, dim))
+
+    def _sandwich(self, L, img, Rm, b):
+        # L @ img @ Rm per (sample, channel); img given as [b, C, rows, cols]
+        return torch.matmul(torch.matmul(L, img.reshape(b * self.C, img.shape[-2], img.shape[-1])), Rm)
+
+
+class SRConv(_Separable):
+    def __init__(self, kernel, channels, R, stride):
+        self.C, self.R, self.ratio = channels, R, stride
+        m = self.m = R // stride
+        A_small = torch.zeros(m, R)
+        half = kernel.shape[0] // 2
+        for i in range(stride // 2, R + stride // 2, stride):
+            for j in range(i - half, i + half):
+                je = -j - 1 if j < 0 else ((R - 1) - (j - R) if j >= R else j)
+                A_small[i // stride, je] += kernel[j - i + half]
+        self.Us, s, self.Vs = torch.svd(A_small, some=False)
+        s[s < 3e-2] = 0
+        self.s_big = torch.outer(s, s).reshape(m * m)
+        first = [R * i + j for i in range(m) for j in range(m)]
+        rest = [R * i + j for i in range(m) for j in range(m, R)]
+        self.perm = torch.tensor(first + rest, dtype=torch.long)
+
+    def Vt(self, x):
+        b, R = x.shape[0], self.R
+        t = self._sandwich(self.Vs.t(), x.reshape(b, self.C, R, R), self.Vs, b).reshape(b, self.C, -1)
+        head = t[:, :, self.perm]
+        t = torch.cat([head, t[:, :, self.perm.numel():]], dim=2)
+        return t.transpose(1, 2).reshape(b, -1)
+
+    def V(self, v):
+        b, R, P = v.shape[0], self.R, self.perm.numel()
+        vv = v.reshape(b, R * R, self.C)
+        t = torch.zeros(b, R * R, self.C)
+        t[:, self.perm, :] = vv[:, :P, :]
+        t[:, P:, :] = vv[:, P:, :]
+        img = t.transpose(1, 2).reshape(b, self.C, R, R)
+        return self._sandwich(self.Vs, img, self.Vs.t(), b).reshape(b, -1)
+
+    def U(self, v):
+        b, m = v.shape[0], self.m
+        img = v.reshape(b, m * m, self.C).transpose(1, 2).reshape(b, self.C, m, m)
+        return self._sandwich(self.Us, img, self.Us.t(), b).reshape(b, -1)
+
+    def Ut(self, y):
+        b, m = y.shape[0], self.m
+        t = self._sandwich(self.Us.t(), y.reshape(b, self.C, m, m), self.Us, b).reshape(b, self.C, -1)
+        return t.transpose(1, 2).reshape(b, -1)
+
+    def singulars(self):
+        return self.s_big.repeat_interleave(3).reshape(-1)
+
+    def add_zeros(self, v):
+        v = v.reshape(v.shape[0], -1)
+        out = torch.zeros(v.shape[0], v.shape[1] * self.ratio ** 2)
+        out[:, :v.shape[1]] = v
+        return out
+
+
+class Deblurring(_Separable):
+    def __init__(self, kernel, channels, R, zero=3e-2):
+        self.C, self.R = channels, R
+        A_small = torch.zeros(R, R)
+        half = kernel.shape[0] // 2
+        for i in range(R):
+            for j in range(i - half, i + half):
+                if 0 <= j < R:
+                    A_small[i, j] = kernel[j - i + half]
+        self.Us, s, self.Vs = torch.svd(A_small, some=False)
+        s[s < zero] = 0
+        self.s_sorted, self.perm = torch.outer(s, s).reshape(R * R).sort(descending=True)
+
+    def _to_spec(self, M, x):
+        b, R = x.shape[0], self.R
+        t = self._sandwich(M.t(), x.reshape(b, self.C, R, R), M, b).reshape(b, self.C, -1)
+        return t[:, :, self.perm].transpose(1, 2).reshape(b, -1)
+
+    def _from_spec(self, M, v):
+        b, R = v.shape[0], self.R
+        t = torch.zeros(b, R * R, self.C)
+        t[:, self.perm, :] = v.reshape(b, R * R, self.C)
+        return self._sandwich(M, t.transpose(1, 2).reshape(b, self.C, R, R), M.t(), b).reshape(b, -1)
+
+    def Vt(self, x):
+        return self._to_spec(self.Vs, x)
+
+    def V(self, v):
+        return self._from_spec(self.Vs, v)
+
+    def Ut(self, y):
+        return self._to_spec(self.Us, y)
+
+    def U(self, v):
+        return self._from_spec(self.Us, v)
+
+    def singulars(self):
+        return self.s_sorted.repeat(1, 3).reshape(-1)  # concatenated, not interleaved: as in the reference
+
+    def add_zeros(self, v):
+        return v.reshape(v.shape[0], -1)
+
+
+def bicubic_kernel(factor):
+    """src/constraint_functions.py:252-269."""
+    import numpy as np
+
+    def cubic(x, a=-0.5):
+        ax = abs(x)
+        if ax <= 1:
+            return (a + 2) * ax ** 3 - (a + 3) * ax ** 2 + 1
+        if 1 < ax < 2:
+            return a * ax ** 3 - 5 * a * ax ** 2 + 8 * a * ax - 4 * a
+        return 0
+
+    k = np.zeros(factor * 4)
+    for i in range(factor * 4):
+        k[i] = cubic((1 / factor) * (i - np.floor(factor * 4 / 2) + 0.5))
+    k = torch.from_numpy(k / np.sum(k)).float()
+    return k / k.sum()
+
+
+def gauss_kernel(sigma=10):
+    """src/constraint_functions.py:274-279."""
+    pdf = lambda x: torch.exp(torch.Tensor([-0.5 * (x / sigma) ** 2]))
+    k = torch.Tensor([pdf(-2), pdf(-1), pdf(0), pdf(1), pdf(2)])
+    return k / k.sum()
