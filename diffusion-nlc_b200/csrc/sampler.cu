@@ -68,7 +68,7 @@ __device__ __forceinline__ int lower_bound(const float* __restrict__ table, int 
 
 // single CTA over the B-vector (batch-global min for the time shift, src/experiments.py:411-412)
 __global__ void __launch_bounds__(1024)
-    refine_sigma_kernel(const float* __restrict__ norms, int B, float inv_sqrt_d, const float* __restrict__ sigma_in,
+    refine_sigma_kernel(const float* __restrict__ norms, int B, float sqrt_d, const float* __restrict__ sigma_in,
                         int n_sigma_in, float norm_min, float norm_max, int refine, float t_fixed,
                         const float* __restrict__ table, int n_table, int time_shift, float* __restrict__ sigma_out,
                         float* __restrict__ t_out, float* __restrict__ in_scale_out) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(1024)
         float s = sigma_in[n_sigma_in == 1 ? 0 : b];
         int t = 0;
         if (refine) {
-            const float nx = norms[b] * inv_sqrt_d;
+            const float nx = norms[b] / sqrt_d;  // vector_norm(xt) / math.sqrt(dim)
             const float lo = fmaxf(nx - norm_max, 0.f), hi = nx + norm_min;
             s = fminf(fmaxf(s, lo), hi);
             t = lower_bound(table, n_table, s);
@@ -297,7 +297,7 @@ extern "C" int nlc_refine_sigma(nlc_ctx* ctx, const float* norms, int B, int d, 
     NLC_REQUIRE(ctx && sigma_in && sigma_out && t_out, "nlc_refine_sigma: null argument");
     NLC_REQUIRE(!refine || (norms && sigma_table), "nlc_refine_sigma: refine needs norms and the sigma table");
     NLC_REQUIRE(n_sigma_in == 1 || n_sigma_in == B, "nlc_refine_sigma: n_sigma_in must be 1 or B");
-    refine_sigma_kernel<<<1, 1024, 0, stream>>>(norms, B, 1.0f / sqrtf(static_cast<float>(d)), sigma_in, n_sigma_in,
+    refine_sigma_kernel<<<1, 1024, 0, stream>>>(norms, B, static_cast<float>(sqrt(static_cast<double>(d))), sigma_in, n_sigma_in,
                                                 norm_min, norm_max, refine, t_fixed, sigma_table, n_table, time_shift,
                                                 sigma_out, t_out, in_scale_out);
     NLC_CHECK_LAUNCH();

@@ -1,0 +1,130 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference (imported read-only from
+/root/reference).  Run here (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Fixtures are small float32 tensors; weights are not stored — they are regenerated from oracle/weights.py seeds
+(whose key names and shapes are checked against the reference modules by tests/test_oracle_vs_reference.py).
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import refimport  # noqa: E402
+from oracle import operators as O  # noqa: E402  (only for the blur kernels' construction helpers)
+from oracle import weights  # noqa: E402
+
+SAMPLER_CASES = [("ddim", 0.0, "none"), ("ddim_simple_orig", 0.85, "none"), ("ddim", 0.5, "fixedsmall"),
+                 ("ddpm", 1.0, "fixedlarge"), ("ddpm_orig", 1.0, "fixedsmall"), ("ddim_orig", 0.3, "fixedlarge"),
+                 ("ddim_simple", 0.2, "none"), ("ddim_simple_drag", 0.2, "none")]
+
+
+def main():
+    R = refimport.load()
+    torch.set_num_threads(4)
+    cfg = weights.CONFIGS["tiny"]
+    u, sg = cfg["unet"], cfg["sigma"]
+    sd = weights.ddim_unet_state_dict(**u, seed=3)
+    ssd = weights.ddim_sigma_state_dict(**sg, seed=4)
+    net = R.unet_ddim.UNetModel(**u).eval()
+    net.load_state_dict(sd)
+    snet = R.unet_ddim.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    snet.load_state_dict(ssd)
+
+    # ---- networks
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, u["image_size"], u["image_size"], generator=g)
+    t = torch.tensor([500.0, 37.0])
+    with torch.no_grad():
+        out = net(x, t)
+        feat = net.encode(x, t)
+        r = snet(feat)
+    torch.save(dict(x=x, t=t, out=out, feat=feat, r=r), os.path.join(HERE, "nets_tiny.pt"))
+
+    # ---- scheduler tables
+    tabs = {}
+    for name, kw in (("ddim50_s100", dict(sampler_name="ddim", inference_timesteps=50, start_sigma=100)),
+                     ("simple_orig100", dict(sampler_name="ddim_simple_orig", inference_timesteps=100, start_sigma=100,
+                                             eta=0.85)),
+                     ("ddim6_s20", dict(sampler_name="ddim", inference_timesteps=6, start_sigma=20.0))):
+        s = R.schedulers.get_sampler(train_timesteps=1000, **kw)
+        tabs[name] = dict(timesteps=s.timesteps.clone(), sigmas=s.sampling_sigmas.clone().float(),
+                          min_var_coef=torch.as_tensor(s.min_var_coef).clone().float(), table=s.sigmas.clone())
+    torch.save(tabs, os.path.join(HERE, "scheduler_tables.pt"))
+
+    # ---- the reference's own denoise_loop, per-step dumps
+    B, side = 2, u["image_size"]
+    shape = (B, 3, side, side)
+    loops = {}
+    for kind, eta, var in SAMPLER_CASES:
+        sch = R.schedulers.get_sampler(kind, 1000, 6, start_sigma=20.0, sampler_var=var, eta=eta)
+        sch.to("cpu")
+        exp = R.experiments.ImageExperiment(net, sch, batch_size=B, data_shape=(3, side, side), seed=5, device="cpu")
+        exp.set_model(net, snet, learn_epsvar=False)
+        exp.set_norm_maxmin(0.0, 30.0)
+        exp.set_clip_fn("clamp")
+        # the reference reseeds the *default* generator (new_gen -> torch.manual_seed) and then draws x_T and every
+        # step's randn_like from it; record the draws by replaying the same stream
+        torch.manual_seed(5)
+        z = torch.randn(shape)
+        need = kind in ("ddpm", "ddpm_orig") or eta > 0
+        noises = [torch.randn(shape) for _ in range(len(sch.timesteps) - 1)] if need else []
+        # observe (not modify) the reference's own update call: its inputs carry x_t and the corrected sigmas
+        rec = dict(xt=[], sigma_t=[], sigma_prev=[], x_prev=[])
+        orig = sch.pred_xprev
+
+        def spy(*a, _orig=orig, _rec=rec, **k):
+            out = _orig(*a, **k)
+            _rec["xt"].append(k["xt"].clone())
+            _rec["sigma_t"].append(torch.as_tensor(k["sigma_t"]).reshape(-1).clone())
+            _rec["sigma_prev"].append(torch.as_tensor(k["sigma_prev"]).reshape(-1).clone())
+            _rec["x_prev"].append(out.clone())
+            return out
+
+        sch.pred_xprev = spy
+        final, logs = exp.denoise_loop(shape=shape, gen=exp.new_gen(5), style="pred", norm_eps=True,
+                                       refine_prior_sigma=True, return_log=True, chunk_size=1)
+        loops["%s|%s|%s" % (kind, eta, var)] = dict(
+            z=z, noises=noises, final=final, eps=logs[1], x0_hat=logs[2], x0=logs[3],
+            xt=rec["xt"], sigma_t=rec["sigma_t"], sigma_prev=rec["sigma_prev"], x_prev=rec["x_prev"],
+            timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone())
+    torch.save(loops, os.path.join(HERE, "denoise_loop_tiny.pt"))
+
+    # ---- operators
+    ref = R.svd_operators
+    Rr, C, Bo = 32, 3, 2
+    g = torch.Generator().manual_seed(21)
+    xs = torch.rand(Bo, C * Rr * Rr, generator=g) * 2 - 1
+    x0 = torch.randn(Bo, C, Rr, Rr, generator=g)
+    mask = torch.ones(Rr, Rr)
+    mask[8:24, 8:24] = 0
+    mr = torch.nonzero(mask.reshape(-1) == 0).long().reshape(-1) * 3
+    missing = torch.cat([mr, mr + 1, mr + 2])
+    perm = torch.randperm(Rr * Rr, generator=torch.Generator().manual_seed(3))
+    ops = {
+        "inpainting": ref.Inpainting(C, Rr, missing, "cpu"),
+        "colorization": ref.Colorization(Rr, "cpu"),
+        "sr_averagepooling": ref.SuperResolution(C, Rr, 4, "cpu"),
+        "cs_walshhadamard": ref.WalshHadamardCS(C, Rr, 4, perm, "cpu"),
+        "sr_bicubic": ref.SRConv(O.bicubic_kernel(4), C, Rr, "cpu", stride=4),
+        "deblur_gauss": ref.Deblurring(O.gauss_kernel(), C, Rr, "cpu"),
+    }
+    gold = dict(x=xs, x0=x0, missing=missing, perm=perm)
+    for name, op in ops.items():
+        y = op.A(xs.clone())
+        proj = x0 - op.A_pinv(op.A(x0.reshape(Bo, -1)) - y).reshape(x0.shape)
+        gold[name] = dict(A=y, At=op.At(y.clone()), A_pinv=op.A_pinv(y.clone()), project=proj)
+    torch.save(gold, os.path.join(HERE, "operators_r32.pt"))
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".pt"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()

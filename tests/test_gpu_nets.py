@@ -1,0 +1,87 @@
+"""GPU parity of the UNet / sigma-model executors against the CPU oracle and the reference's golden outputs.
+
+Tolerances (max-norm relative error of the network output): tf32 operands 2e-3, bf16 operands 2e-2 — the
+accumulated effect of rounding every conv/GEMM operand to 2^-11 / 2^-9 through ~30 layers; measured values are
+about 3x below the bound (profiles/r01_net_parity_first.log)."""
+import os
+
+import pytest
+import torch
+
+from oracle import ddim_net, weights
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+TOL = {"tf32": 2e-3, "bf16": 2e-2}
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _models(name, prec):
+    from nlc_b200.unet_ddim import SigmaModel, UNetModel
+    cfg = weights.CONFIGS[name]
+    sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
+    ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+    m = UNetModel(**cfg["unet"], precision=prec, device=dev).load_state_dict(sd)
+    s = SigmaModel(**cfg["sigma"], precision=prec, device=dev).load_state_dict(ssd)
+    return cfg, sd, ssd, m, s
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_golden_reference_outputs(golden_dir, prec):
+    """Outputs of the unmodified reference modules (tests/golden/nets_tiny.pt)."""
+    _, _, _, m, s = _models("tiny", prec)
+    g = torch.load(os.path.join(golden_dir, "nets_tiny.pt"), weights_only=True)
+    out = m(g["x"].to(dev), g["t"].to(dev))
+    feat = m.encode(g["x"].to(dev), g["t"].to(dev))
+    assert out.shape == g["out"].shape and feat.shape == g["feat"].shape
+    assert _rel(out.cpu(), g["out"]) < TOL[prec]
+    assert _rel(feat.cpu(), g["feat"]) < TOL[prec]
+    r = s(g["feat"].to(dev))  # teacher-forced sigma head
+    assert r.shape == (2, 1, 1, 1)
+    assert (r.cpu() - g["r"]).abs().max() < (5e-4 if prec == "tf32" else 5e-3)
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("name,B", [("c1", 3), ("c2", 2)])
+def test_benchmark_architectures_vs_oracle(name, B, prec):
+    cfg, sd, ssd, m, s = _models(name, prec)
+    R = cfg["unet"]["image_size"]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, 3, R, R, generator=g)
+    t = torch.tensor([999.0, 250.0, 3.0][:B])
+    with torch.no_grad():
+        ref, feat = ddim_net.unet_forward(sd, x, t, return_feat=True)
+        r_ref = ddim_net.sigma_forward(ssd, feat)
+    out, f = m.forward_and_encode(x.to(dev), t.to(dev))
+    assert _rel(out.cpu(), ref) < TOL[prec]
+    assert _rel(f.cpu(), feat) < TOL[prec]
+    assert (s(f).cpu() - r_ref).abs().max() < (2e-3 if prec == "tf32" else 1e-2)
+
+
+def test_input_scale_folding_and_batch_independence():
+    """forward_scaled(x, t, scale) == forward(x*scale, t); rows do not interact (the property batch sharding rests
+    on): a batch of 6 equals two batches of 3 up to GroupNorm partial-merge order (1e-5)."""
+    cfg, sd, _, m, _ = _models("tiny", "tf32")
+    R = cfg["unet"]["image_size"]
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(6, 3, R, R, generator=g).to(dev)
+    t = torch.tensor([10.0, 100.0, 200.0, 400.0, 800.0, 990.0], device=dev)
+    sc = (torch.rand(6, generator=g) + 0.2).to(dev)
+    a = m.forward_scaled(x, t, sc).clone()
+    b = m.forward_scaled(x * sc.view(-1, 1, 1, 1), t, None).clone()
+    assert _rel(a, b) < 1e-5
+    lo = m.forward_scaled(x[:3].contiguous(), t[:3], sc[:3]).clone()
+    hi = m.forward_scaled(x[3:].contiguous(), t[3:], sc[3:]).clone()
+    assert _rel(torch.cat([lo, hi]), a) < 1e-5
+
+
+def test_load_state_dict_reports_missing_keys():
+    from nlc_b200.unet_ddim import UNetModel
+    cfg = weights.CONFIGS["tiny"]
+    sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
+    del sd["mid.attn_1.q.weight"]
+    with pytest.raises(KeyError):
+        UNetModel(**cfg["unet"], device=dev).load_state_dict(sd)

@@ -1,0 +1,225 @@
+"""GPU parity of the individual kernels behind the C ABI against plain torch fp32 (floating-point kernels keep a
+torch fp32 reference; tolerances are stated per test and reflect the operand precision: bf16 2^-9, tf32 2^-11)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _dt(name):
+    from nlc_b200._lib import NLC_BF16, NLC_F32
+    return NLC_BF16 if name == "bf16" else NLC_F32
+
+
+def _rnd(x, dt):
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16
+    return x.to(torch.bfloat16).float() if dt == NLC_BF16 else ops.round_tf32_(x.clone())
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, stride, pad(l,r,t,b), k
+    (4, 16, 16, 128, 128, 1, (1, 1, 1, 1), 3),
+    (5, 4, 4, 256, 512, 1, (1, 1, 1, 1), 3),       # ragged batch: 5 images of 16 pixels in 128-row tiles
+    (3, 32, 32, 256, 768, 1, (0, 0, 0, 0), 1),     # qkv-shaped 1x1
+    (4, 32, 32, 128, 128, 2, (0, 1, 0, 1), 3),     # DDIM Downsample: pad right/bottom, stride 2
+    (6, 8, 8, 256, 256, 2, (1, 1, 1, 1), 3),       # ADM Downsample: pad 1, stride 2
+    (1, 256, 256, 64, 64, 1, (1, 1, 1, 1), 3),     # widest tile row
+    (2, 2, 2, 512, 512, 1, (1, 1, 1, 1), 3),       # sigma-model 2x2 level
+    (130, 1, 1, 256, 128, 1, (0, 0, 0, 0), 1),     # 1x1 spatial, batch > one tile
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tc_matches_torch(dev, prec, case):
+    """Operands are pre-rounded to the operand dtype, so the only difference left is fp32 summation order:
+    tolerance 5e-5 of the output's max magnitude."""
+    from nlc_b200 import ops
+    B, H, W, Cin, Cout, stride, pad, k = case
+    dt = _dt(prec)
+    g = torch.Generator().manual_seed(1)
+    x = _rnd(torch.randn(B, Cin, H, W, generator=g).to(dev), dt)
+    w = _rnd((torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev), dt)
+    b = torch.randn(Cout, generator=g).to(dev)
+    ref = F.conv2d(F.pad(x, pad), w, b, stride=stride)
+    Ho, Wo = ref.shape[2:]
+    rowvec = torch.randn(B, Cout, generator=g).to(dev)
+    resid = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+    ref = (ref + rowvec[:, :, None, None] + resid.permute(0, 3, 1, 2)) * 0.5
+    tdt = ops.OP_DTYPES[dt]
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(tdt))
+    segs = [(0, kh - pad[2], kw - pad[0], 0, Cin) for kh in range(k) for kw in range(k)]
+    o32 = ops.Act(torch.full((B, Ho, Wo, Cout), float("nan"), device=dev))
+    oop = ops.Act(torch.zeros(B, Ho, Wo, Cout, device=dev, dtype=tdt))
+    ops.conv_tc([xa], segs, ops.pack_conv_weight(w, dt), Cout, B, Ho, Wo, dt, stride=stride, bias=b, rowvec=rowvec,
+                resid=ops.Act(resid), out_scale=0.5, out_f32=o32, out_op=oop)
+    torch.cuda.synchronize()
+    assert _rel(o32.t.permute(0, 3, 1, 2), ref) < 5e-5
+    assert _rel(oop.t.float().permute(0, 3, 1, 2), ref) < (8e-3 if prec == "bf16" else 1e-3)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+def test_conv_tc_fused_shortcut_and_channel_slices(dev, prec):
+    """3x3 over one source + 1x1 shortcut over a channel slice of a wider buffer, one accumulator."""
+    from nlc_b200 import ops
+    dt = _dt(prec)
+    B, H, C0, C1, Cout = 4, 16, 128, 256, 128
+    g = torch.Generator().manual_seed(2)
+    x0 = _rnd(torch.randn(B, C0, H, H, generator=g).to(dev), dt)
+    x1 = _rnd(torch.randn(B, C1, H, H, generator=g).to(dev), dt)
+    w0 = _rnd((torch.randn(Cout, C0, 3, 3, generator=g) / (C0 * 9) ** 0.5).to(dev), dt)
+    w1 = _rnd((torch.randn(Cout, C1, 1, 1, generator=g) / C1 ** 0.5).to(dev), dt)
+    ref = F.conv2d(x0, w0, padding=1) + F.conv2d(x1, w1)
+    tdt = ops.OP_DTYPES[dt]
+    buf = torch.zeros(B, H, H, C1 + 64, device=dev, dtype=tdt)
+    buf[..., 64:] = x1.permute(0, 2, 3, 1).to(tdt)
+    out_wide = torch.zeros(B, H, H, Cout + 128, device=dev)
+    out = ops.Act(out_wide, 128, Cout)
+    ops.conv_tc([ops.Act(x0.permute(0, 2, 3, 1).contiguous().to(tdt)), ops.Act(buf, 64, C1)],
+                ops.taps3x3(0, 0, C0) + [(1, 0, 0, 0, C1)], ops.pack_conv_weight(w0, dt, extra=w1), Cout, B, H, H, dt,
+                out_f32=out)
+    torch.cuda.synchronize()
+    assert _rel(out.dense().permute(0, 3, 1, 2), ref) < 5e-5
+    assert out_wide[..., :128].abs().max() == 0  # the neighbouring slice is untouched
+
+
+def test_conv_tc_rejects_bad_shapes(dev):
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16, NlcError
+    x = ops.Act(torch.zeros(1, 6, 6, 64, device=dev, dtype=torch.bfloat16))
+    w = torch.zeros(64, 64, device=dev, dtype=torch.bfloat16)
+    with pytest.raises(NlcError):  # 6x6 is not a power-of-two extent
+        ops.conv_tc([x], [(0, 0, 0, 0, 64)], w, 64, 1, 6, 6, NLC_BF16, out_f32=ops.Act(torch.zeros(1, 6, 6, 64, device=dev)))
+    x = ops.Act(torch.zeros(1, 8, 8, 48, device=dev, dtype=torch.bfloat16))
+    with pytest.raises(NlcError):  # 48 channels do not fill a 128-byte K chunk
+        ops.conv_tc([x], [(0, 0, 0, 0, 48)], w, 64, 1, 8, 8, NLC_BF16, out_f32=ops.Act(torch.zeros(1, 8, 8, 64, device=dev)))
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4)])
+@pytest.mark.parametrize("shape", [(3, 8, 8, 256), (2, 64, 64, 384), (5, 2, 2, 512), (2, 16, 16, 1024)])
+@pytest.mark.parametrize("silu,ss", [(True, False), (False, True)])
+def test_groupnorm(dev, prec, tol, shape, silu, ss):
+    """tolerance = one rounding of the output to the operand dtype (bf16 2^-8 / tf32 2^-11 of max |y|)."""
+    from nlc_b200 import ops
+    B, H, W, C = shape
+    dt = _dt(prec)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=g).to(dev) * 2 + 0.5
+    gam, bet = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    ref = F.group_norm(x, 32, gam, bet, eps=1e-6)
+    sc = sh = None
+    if ss:
+        sc, sh = torch.randn(B, C, generator=g).to(dev), torch.randn(B, C, generator=g).to(dev)
+        ref = ref * (1 + sc[:, :, None, None]) + sh[:, :, None, None]
+    if silu:
+        ref = F.silu(ref)
+    y = ops.Act(torch.zeros(B, H, W, C, device=dev, dtype=ops.OP_DTYPES[dt]))
+    ws = torch.zeros(ops.groupnorm_ws(B, H * W, C, 32), device=dev)
+    ops.groupnorm(ops.Act(x.permute(0, 2, 3, 1).contiguous()), 32, 1e-6, gam, bet, y, dt, ws, silu=silu, scale=sc, shift=sh)
+    assert _rel(y.t.float().permute(0, 3, 1, 2), ref) < tol
+
+
+def test_groupnorm_large_mean_is_stable(dev):
+    """Welford partials: a mean 1000x the standard deviation must not cancel."""
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_F32
+    B, H, W, C = 2, 32, 32, 128
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(B, C, H, W, generator=g) * 0.01 + 10.0).to(dev)
+    ref = F.group_norm(x.double(), 32, eps=1e-6).float()
+    y = ops.Act(torch.zeros(B, H, W, C, device=dev))
+    ws = torch.zeros(ops.groupnorm_ws(B, H * W, C, 32), device=dev)
+    ops.groupnorm(ops.Act(x.permute(0, 2, 3, 1).contiguous()), 32, 1e-6, None, None, y, NLC_F32, ws, silu=False)
+    assert (y.t.permute(0, 3, 1, 2) - ref).abs().max() < 2e-2  # fp32 input quantisation of x itself is ~1e-4 sigma
+
+
+ATTN_CASES = [(3, 16, 1, 512, False), (2, 64, 4, 64, True), (2, 64, 1, 256, False), (3, 256, 1, 256, False),
+              (2, 1024, 4, 64, False), (2, 256, 4, 64, True)]
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 8e-3), ("tf32", 1e-3)])
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention(dev, prec, tol, case):
+    from nlc_b200 import ops
+    B, T, heads, dh, legacy = case
+    dt = _dt(prec)
+    C = heads * dh
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(5)
+    qkv = _rnd(torch.randn(B, T, 3 * C, generator=g).to(dev), dt).to(tdt)
+    f = qkv.float()
+    if legacy:
+        v5 = f.view(B, T, heads, 3, dh)
+        q, k, v = v5[:, :, :, 0], v5[:, :, :, 1], v5[:, :, :, 2]
+        offs = (0, dh, 2 * dh, 3 * dh)
+    else:
+        q, k, v = [f[:, :, i * C:(i + 1) * C].view(B, T, heads, dh) for i in range(3)]
+        offs = (0, C, 2 * C, dh)
+    scale = dh ** -0.5
+    w = torch.softmax(torch.einsum("bthd,bshd->bhts", q, k) * scale, dim=-1)
+    ref = torch.einsum("bhts,bshd->bthd", w, v).reshape(B, T, C)
+    side = int(T ** 0.5)
+    out = ops.Act(torch.zeros(B, side, T // side, C, device=dev, dtype=tdt))
+    ws = torch.zeros(max(ops.attention_ws(dt, B, T, heads, dh), 16), device=dev, dtype=torch.uint8)
+    ops.attention(ops.Act(qkv.view(B, side, T // side, 3 * C)), dt, offs[0], offs[1], offs[2], offs[3], heads, dh, scale,
+                  out, ws)
+    assert _rel(out.t.float().view(B, T, C), ref) < tol
+
+
+def test_linear_and_embedding(dev):
+    from nlc_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(37, 300, generator=g).to(dev)
+    W = (torch.randn(130, 300, generator=g) / 17).to(dev)
+    b = torch.randn(130, generator=g).to(dev)
+    y = torch.zeros(37, 130, device=dev)
+    ops.linear(x, W, b, y, act_in=1, act_out=2)
+    assert _rel(y, F.gelu(F.linear(F.silu(x), W, b))) < 2e-6
+    t = torch.tensor([0.0, 1.0, 37.0, 999.0, 1000.0], device=dev)
+    freqs = torch.exp(torch.arange(64, dtype=torch.float32) * -(9.210340371976184 / 63)).to(dev)
+    out = torch.zeros(5, 128, device=dev)
+    ops.timestep_embedding(t, freqs, False, out)
+    arg = t[:, None] * freqs[None]
+    assert (out - torch.cat([arg.sin(), arg.cos()], 1)).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+def test_resample_and_boundary_convs(dev, prec):
+    from nlc_b200 import ops
+    dt = _dt(prec)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 64, 8, 8, generator=g).to(dev)
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous())
+    for mode, ref in ((0, x), (1, F.interpolate(x, scale_factor=2.0, mode="nearest")), (2, F.avg_pool2d(x, 2))):
+        B, C, Ho, Wo = ref.shape
+        yf = ops.Act(torch.zeros(B, Ho, Wo, C, device=dev))
+        ops.resample(xa, mode, yf, None, dt)
+        assert _rel(yf.t.permute(0, 3, 1, 2), ref) < 1e-6
+    B, R, C = 3, 16, 128
+    img = torch.randn(B, 3, R, R, generator=g).to(dev)
+    sc = (torch.rand(B, generator=g) + 0.5).to(dev)
+    w = (torch.randn(C, 3, 3, 3, generator=g) / 5).to(dev)
+    b = torch.randn(C, generator=g).to(dev)
+    yf = ops.Act(torch.zeros(B, R, R, C, device=dev))
+    yo = ops.Act(torch.zeros(B, R, R, C, device=dev, dtype=ops.OP_DTYPES[dt]))
+    ops.conv_in_nchw(img, sc, w, b, yf, yo, dt)
+    assert _rel(yf.t.permute(0, 3, 1, 2), F.conv2d(img * sc[:, None, None, None], w, b, padding=1)) < 2e-6
+    w2 = (torch.randn(3, C, 3, 3, generator=g) / 30).to(dev)
+    b2 = torch.randn(3, generator=g).to(dev)
+    out = torch.zeros(B, 3, R, R, device=dev)
+    ops.conv_out_nchw(yo, dt, w2, b2, out)
+    assert _rel(out, F.conv2d(yo.t.float().permute(0, 3, 1, 2), w2, b2, padding=1)) < 5e-6

@@ -1,0 +1,115 @@
+"""Host-side logic that needs no GPU: scheduler mirror vs oracle / golden tables, weight packing, activation
+views, and the world_size-2 sharding path over gloo."""
+import os
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle import sampler as S
+
+
+def test_scheduler_mirror_matches_golden(golden_dir):
+    from nlc_b200 import schedulers as M
+    g = torch.load(os.path.join(golden_dir, "scheduler_tables.pt"), weights_only=True)
+    for name, kw in (("ddim50_s100", dict(sampler_name="ddim", inference_timesteps=50, start_sigma=100)),
+                     ("simple_orig100", dict(sampler_name="ddim_simple_orig", inference_timesteps=100,
+                                             start_sigma=100, eta=0.85)),
+                     ("ddim6_s20", dict(sampler_name="ddim", inference_timesteps=6, start_sigma=20.0))):
+        s = M.get_sampler(train_timesteps=1000, **kw)
+        assert torch.equal(s.timesteps, g[name]["timesteps"])
+        assert torch.equal(s.sampling_sigmas.float(), g[name]["sigmas"])
+        assert torch.equal(s.sigmas, g[name]["table"])
+        assert float(s.min_var_coef) == float(g[name]["min_var_coef"])
+
+
+def test_scheduler_mirror_matches_oracle_tables():
+    from nlc_b200 import schedulers as M
+    tab = S.Tables()
+    for n, start in ((10, 50.0), (100, 100.0), (37, 3.0)):
+        s = M.get_sampler("ddim", 1000, n, start_sigma=start)
+        ts, sig, mvc = tab.ddim_schedule(start, None, n)
+        assert torch.equal(s.timesteps, ts) and torch.equal(s.sampling_sigmas, sig)
+        assert float(s.min_var_coef) == float(mvc)
+
+
+def test_unknown_sampler_and_ge_are_rejected():
+    from nlc_b200 import schedulers as M
+    with pytest.raises(NotImplementedError):
+        M.get_sampler("ge", 1000, 10)
+    with pytest.raises(NotImplementedError):
+        M.get_sampler("nope", 1000, 10)
+
+
+def test_pack_conv_weight_order():
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16, NLC_F32
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    k = ops.pack_conv_weight(w, NLC_F32)
+    assert k.shape == (2, 27)
+    # K index = (kh*3 + kw)*Cin + c
+    assert k[1, (1 * 3 + 2) * 3 + 1] == w[1, 1, 1, 2]
+    extra = torch.ones(2, 5, 1, 1)
+    assert ops.pack_conv_weight(w, NLC_BF16, extra=extra).shape == (2, 32)
+
+
+def test_tf32_rounding_matches_definition():
+    from nlc_b200 import ops
+    x = torch.tensor([1.0 + 2 ** -11, 1.0 + 2 ** -12, -3.1415927, 1e-30, 65504.0])
+    r = ops.round_tf32_(x.clone())
+    assert (r.view(torch.int32) & 0x1FFF).abs().sum() == 0
+    assert ((r - x).abs() <= x.abs() * 2 ** -11).all()
+    assert r[0] == 1.0 + 2 ** -10  # tie rounds away from zero
+
+
+def test_act_view_slicing():
+    from nlc_b200.ops import Act
+    t = torch.zeros(2, 4, 4, 96)
+    a = Act(t, 32, 64)
+    assert (a.B, a.H, a.W, a.C, a.ld) == (2, 4, 4, 64, 96)
+    assert a.ptr == t.data_ptr() + 32 * 4
+    assert a.slice(16, 8).ptr == t.data_ptr() + 48 * 4
+
+
+def test_shard_ranges_cover_the_batch():
+    from nlc_b200.parallel import shard_range
+    for B in (1, 7, 256, 257):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_range(B, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+
+
+def _worker(rank, ws, port, q):
+    import torch.distributed as dist
+    from nlc_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    B, shape = 5, (5, 3, 4, 4)
+    full = torch.randn(shape, generator=torch.Generator().manual_seed(77))
+    mine, = parallel.sharded_noise(shape, 77, rank, ws)
+    lo, hi = parallel.shard_range(B, rank, ws)
+    ok = torch.equal(mine, full[lo:hi])
+    # "finished images": every rank doubles its rows; the gather must equal the un-sharded result
+    gathered = parallel.gather_images(mine * 2, global_batch=B)
+    ok = ok and torch.equal(gathered, full * 2)
+    loss, nan, tmax = parallel.global_step_scalars(mine.abs().sum(), float(rank == 1), float(10 + rank))
+    ok = ok and abs(float(loss) - float(full.abs().sum())) < 1e-3 and bool(nan) and float(tmax) == 10 + ws - 1
+    sums = parallel.reduce_metric_sums(torch.tensor([float(hi - lo), 1.0]))
+    ok = ok and sums.tolist() == [float(B), float(ws)]
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_world_size_2_sharding_over_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]

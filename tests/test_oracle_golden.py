@@ -1,0 +1,103 @@
+"""The oracle (CPU restatement under oracle/) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  Bit-exact where the arithmetic is the same sequence of torch ops."""
+import os
+
+import pytest
+import torch
+
+from oracle import ddim_net, operators as O, sampler as S, weights
+
+torch.set_num_threads(4)
+
+
+def load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=True)
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = weights.CONFIGS["tiny"]
+    return (weights.ddim_unet_state_dict(**cfg["unet"], seed=3), weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4))
+
+
+def test_networks(golden_dir, tiny):
+    sd, ssd = tiny
+    g = load(golden_dir, "nets_tiny.pt")
+    with torch.no_grad():
+        out, feat = ddim_net.unet_forward(sd, g["x"], g["t"], return_feat=True)
+        enc = ddim_net.unet_encode(sd, g["x"], g["t"])
+        r = ddim_net.sigma_forward(ssd, feat)
+    assert torch.equal(out, g["out"]) and torch.equal(feat, g["feat"]) and torch.equal(enc, g["feat"])
+    assert torch.equal(r, g["r"])
+
+
+def test_scheduler_tables(golden_dir):
+    g = load(golden_dir, "scheduler_tables.pt")
+    tab = S.Tables()
+    for name, start, n in (("ddim50_s100", 100.0, 50), ("simple_orig100", 100.0, 100), ("ddim6_s20", 20.0, 6)):
+        ts, sig, mvc = tab.ddim_schedule(start, None, n)
+        assert torch.equal(ts, g[name]["timesteps"]), name
+        assert torch.equal(sig, g[name]["sigmas"]), name
+        assert torch.equal(tab.sigmas, g[name]["table"])
+        assert float(mvc) == float(g[name]["min_var_coef"])
+
+
+def test_denoise_loop_every_scheduler(golden_dir, tiny):
+    sd, ssd = tiny
+    g = load(golden_dir, "denoise_loop_tiny.pt")
+    tab = S.Tables()
+    fwd = lambda z, t: ddim_net.unet_forward(sd, z, t)
+    enc = lambda z, t: ddim_net.unet_encode(sd, z, t)
+    sgf = lambda f: ddim_net.sigma_forward(ssd, f)
+    d = 3 * 16 * 16
+    for key, case in g.items():
+        kind, eta, var = key.split("|")
+        ts, sig, mvc = tab.ddim_schedule(20.0, None, 6)
+        assert torch.equal(ts, case["timesteps"])
+        xT = case["z"] / (1 / (sig[0] ** 2 + 1)).sqrt()
+        log = []
+        with torch.no_grad():
+            x0 = S.denoise_loop(tab, ts.tolist(), sig, mvc, fwd, enc, sgf, xT, kind=kind, eta=float(eta),
+                                sampler_var=var, style="pred", norm_eps=True, refine=True, norm_min=0.0,
+                                norm_max=30.0 / d ** 0.5, noises=case["noises"] or None, log=log)
+        assert torch.equal(x0, case["final"]), key
+        for i, st in enumerate(log):
+            assert torch.equal(st["eps"], case["eps"][i]), (key, i)
+            assert torch.equal(st["x0_hat"], case["x0_hat"][i]), (key, i)
+
+
+def test_operators(golden_dir):
+    g = load(golden_dir, "operators_r32.pt")
+    R, C = 32, 3
+    ops = {
+        "inpainting": O.Inpainting(C, R, g["missing"]),
+        "colorization": O.Colorization(R),
+        "sr_averagepooling": O.SuperResolution(C, R, 4),
+        "cs_walshhadamard": O.WalshHadamardCS(C, R, 4, g["perm"]),
+        "sr_bicubic": O.SRConv(O.bicubic_kernel(4), C, R, 4),
+        "deblur_gauss": O.Deblurring(O.gauss_kernel(), C, R),
+    }
+    for name, op in ops.items():
+        y = op.A(g["x"].clone())
+        assert torch.equal(y, g[name]["A"]), name
+        assert torch.equal(op.At(y.clone()), g[name]["At"]), name
+        assert torch.equal(op.A_pinv(y.clone()), g[name]["A_pinv"]), name
+        assert torch.equal(op.project(g["x0"], y), g[name]["project"]), name
+
+
+def test_operator_identities():
+    """Known-answer properties of the reference operators: A A^+ y = y, projection feasibility and
+    idempotence."""
+    R, C, B = 32, 3, 2
+    gen = torch.Generator().manual_seed(0)
+    x = torch.rand(B, C * R * R, generator=gen) * 2 - 1
+    x0 = torch.randn(B, C, R, R, generator=gen)
+    perm = torch.randperm(R * R, generator=gen)
+    for op, tol in ((O.Colorization(R), 5e-6), (O.SuperResolution(C, R, 4), 5e-6),
+                    (O.WalshHadamardCS(C, R, 4, perm), 5e-6), (O.SRConv(O.bicubic_kernel(4), C, R, 4), 5e-5),
+                    (O.Deblurring(O.gauss_kernel(), C, R), 5e-5)):
+        y = op.A(x.clone())
+        assert (op.A(op.A_pinv(y.clone())) - y).abs().max() < tol * 20
+        p = op.project(x0, y)
+        assert (op.A(p.reshape(B, -1)) - y).abs().max() < tol * 20
+        assert (op.project(p, y) - p).abs().max() < 5e-4

@@ -1,0 +1,125 @@
+"""Live pin of the oracle (and of the host-side scheduler mirror) against the unmodified reference imported from
+/root/reference.  Skipped where the reference tree is absent (the GPU box); the committed golden vectors cover
+the same ground there."""
+import pytest
+import torch
+
+import refimport
+from oracle import ddim_net, operators as O, sampler as S, weights
+
+pytestmark = pytest.mark.skipif(not refimport.available(), reason="reference tree not present")
+torch.set_num_threads(4)
+
+
+@pytest.fixture(scope="module")
+def R():
+    return refimport.load()
+
+
+@pytest.mark.parametrize("name", ["tiny", "c1"])
+def test_state_dict_layout_and_networks(R, name):
+    cfg = weights.CONFIGS[name]
+    u, sg = cfg["unet"], cfg["sigma"]
+    sd = weights.ddim_unet_state_dict(**u, seed=3)
+    ssd = weights.ddim_sigma_state_dict(**sg, seed=4)
+    net = R.unet_ddim.UNetModel(**u).eval()
+    snet = R.unet_ddim.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    for mine, ref in ((sd, net.state_dict()), (ssd, snet.state_dict())):
+        assert set(mine) == set(ref)
+        assert all(mine[k].shape == ref[k].shape for k in mine)
+    net.load_state_dict(sd)
+    snet.load_state_dict(ssd)
+    x = torch.randn(2, 3, u["image_size"], u["image_size"])
+    t = torch.tensor([640.0, 12.0])
+    with torch.no_grad():
+        assert torch.equal(net(x, t), ddim_net.unet_forward(sd, x, t))
+        f = net.encode(x, t)
+        assert torch.equal(f, ddim_net.unet_encode(sd, x, t))
+        assert torch.equal(snet(f), ddim_net.sigma_forward(ssd, f))
+
+
+def test_c2_layout(R):
+    cfg = weights.CONFIGS["c2"]
+    sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
+    ref = R.unet_ddim.UNetModel(**cfg["unet"]).state_dict()
+    assert set(sd) == set(ref) and all(sd[k].shape == ref[k].shape for k in sd)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(sampler_name="ddim", inference_timesteps=50, start_sigma=100),
+    dict(sampler_name="ddim_simple_orig", inference_timesteps=100, eta=0.85),
+    dict(sampler_name="ddim", inference_timesteps=10, sigma_style="EDM", start_sigma=80, end_sigma=0.02),
+    dict(sampler_name="ddpm", inference_timesteps=20, sigma_style="Linear", start_sigma=50, end_sigma=0.05,
+         sampler_var="fixedsmall"),
+    dict(sampler_name="ddim", inference_timesteps=20, sigma_style="Scaled", start_sigma=50, end_sigma=0.05,
+         linear_scale=1.1),
+    dict(sampler_name="ddim", inference_timesteps=30, beta_schedule="cosine"),
+])
+def test_scheduler_mirror_tables(R, kw):
+    from nlc_b200 import schedulers as M
+    a = R.schedulers.get_sampler(train_timesteps=1000, **kw)
+    b = M.get_sampler(train_timesteps=1000, **kw)
+    assert torch.equal(a.timesteps, b.timesteps)
+    assert torch.equal(a.sampling_sigmas.float(), b.sampling_sigmas.float())
+    assert torch.equal(a.sigmas, b.sigmas)
+    assert float(a.min_var_coef) == float(b.min_var_coef)
+
+
+@pytest.mark.parametrize("kind,eta,var", [("ddim", 0.0, "none"), ("ddim_simple_orig", 0.85, "none"),
+                                          ("ddpm", 1.0, "fixedlarge"), ("ddpm_orig", 1.0, "fixedsmall")])
+def test_denoise_loop(R, kind, eta, var):
+    cfg = weights.CONFIGS["tiny"]
+    u, sg = cfg["unet"], cfg["sigma"]
+    sd = weights.ddim_unet_state_dict(**u, seed=3)
+    ssd = weights.ddim_sigma_state_dict(**sg, seed=4)
+    net = R.unet_ddim.UNetModel(**u).eval()
+    net.load_state_dict(sd)
+    snet = R.unet_ddim.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    snet.load_state_dict(ssd)
+    sch = R.schedulers.get_sampler(kind, 1000, 5, start_sigma=30.0, sampler_var=var, eta=eta)
+    B, shape = 2, (2, 3, 16, 16)
+    exp = R.experiments.ImageExperiment(net, sch, batch_size=B, data_shape=shape[1:], seed=9, device="cpu")
+    exp.set_model(net, snet, learn_epsvar=False)
+    exp.set_norm_maxmin(-2.0, 25.0)
+    exp.set_clip_fn("clamp")
+    out, _ = exp.denoise_loop(shape=shape, gen=exp.new_gen(9), style="pred", norm_eps=True, refine_prior_sigma=True,
+                              return_log=False, chunk_size=1)
+    tab = S.Tables()
+    ts, sig, mvc = tab.ddim_schedule(30.0, None, 5)
+    torch.manual_seed(9)
+    z = torch.randn(shape)
+    noises = [torch.randn(shape) for _ in range(len(ts) - 1)] if (eta > 0 or kind.startswith("ddpm")) else None
+    with torch.no_grad():
+        x0 = S.denoise_loop(tab, ts.tolist(), sig, mvc, lambda a, t: ddim_net.unet_forward(sd, a, t),
+                            lambda a, t: ddim_net.unet_encode(sd, a, t), lambda f: ddim_net.sigma_forward(ssd, f),
+                            z / (1 / (sig[0] ** 2 + 1)).sqrt(), kind=kind, eta=eta, sampler_var=var, style="pred",
+                            norm_eps=True, refine=True, norm_min=exp.norm_min, norm_max=exp.norm_max, noises=noises)
+    assert torch.equal(x0, out)
+
+
+def test_operators(R):
+    ref = R.svd_operators
+    Rr, C, B = 32, 3, 2
+    x = torch.rand(B, C * Rr * Rr) * 2 - 1
+    x0 = torch.randn(B, C, Rr, Rr)
+    mask = torch.ones(Rr, Rr)
+    mask[4:20, 10:30] = 0
+    mr = torch.nonzero(mask.reshape(-1) == 0).long().reshape(-1) * 3
+    missing = torch.cat([mr, mr + 1, mr + 2])
+    perm = torch.randperm(Rr * Rr)
+    pairs = [
+        (ref.Inpainting(C, Rr, missing, "cpu"), O.Inpainting(C, Rr, missing)),
+        (ref.Colorization(Rr, "cpu"), O.Colorization(Rr)),
+        (ref.SuperResolution(C, Rr, 2, "cpu"), O.SuperResolution(C, Rr, 2)),
+        (ref.WalshHadamardCS(C, Rr, 2, perm, "cpu"), O.WalshHadamardCS(C, Rr, 2, perm)),
+        (ref.SRConv(O.bicubic_kernel(2), C, Rr, "cpu", stride=2), O.SRConv(O.bicubic_kernel(2), C, Rr, 2)),
+        (ref.Deblurring(O.gauss_kernel(), C, Rr, "cpu"), O.Deblurring(O.gauss_kernel(), C, Rr)),
+        (ref.Deblurring(torch.Tensor([1 / 9] * 9), C, Rr, "cpu"), O.Deblurring(torch.Tensor([1 / 9] * 9), C, Rr)),
+    ]
+    for a, b in pairs:
+        y = a.A(x.clone())
+        assert torch.equal(y, b.A(x.clone()))
+        assert torch.equal(a.At(y.clone()), b.At(y.clone()))
+        assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
+        pr = x0 - a.A_pinv(a.A(x0.reshape(B, -1)) - y).reshape(x0.shape)
+        assert torch.equal(pr, b.project(x0, y))
