@@ -7,6 +7,13 @@
 
 namespace nlc {
 
+// The sampler formulas are evaluated op by op like the reference's torch expressions: the _rn intrinsics stop
+// nvcc from contracting a*b+c into an FMA, which would e.g. turn sqrt(sp^2 - sqrt(sp^2)^2) from 0 into NaN.
+#define MUL(a, b) __fmul_rn((a), (b))
+#define ADD(a, b) __fadd_rn((a), (b))
+#define SUB(a, b) __fsub_rn((a), (b))
+#define DIV(a, b) __fdiv_rn((a), (b))
+
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,14 +86,14 @@ __global__ void __launch_bounds__(1024)
         float s = sigma_in[n_sigma_in == 1 ? 0 : b];
         int t = 0;
         if (refine) {
-            const float nx = norms[b] / sqrt_d;  // vector_norm(xt) / math.sqrt(dim)
-            const float lo = fmaxf(nx - norm_max, 0.f), hi = nx + norm_min;
+            const float nx = DIV(norms[b], sqrt_d);  // vector_norm(xt) / math.sqrt(dim)
+            const float lo = fmaxf(SUB(nx, norm_max), 0.f), hi = ADD(nx, norm_min);
             s = fminf(fmaxf(s, lo), hi);
             t = lower_bound(table, n_table, s);
             atomicMin(&s_min, t);
         }
         sigma_out[b] = s;
-        if (in_scale_out) in_scale_out[b] = sqrtf(1.0f / (s * s + 1.0f));
+        if (in_scale_out) in_scale_out[b] = sqrtf(DIV(1.0f, ADD(MUL(s, s), 1.0f)));
         if (!refine) t_out[b] = fminf(fmaxf(t_fixed, 0.f), 1000.f);
     }
     __syncthreads();
@@ -108,13 +115,13 @@ __global__ void sigma_correct_kernel(const float* __restrict__ r, const float* _
     if (b >= B) return;
     const float s = sigma[b];
     const float sp = sigma_prev[n_prev == 1 ? 0 : b];
-    const float dist = s * (1.0f + r[b]);
-    const float dist_prev = dist * (sp / s);
+    const float dist = MUL(s, ADD(1.0f, r[b]));
+    const float dist_prev = MUL(dist, DIV(sp, s));
     const int t = lower_bound(table, n_table, dist);
     sigma_hat[b] = dist;
     sigma_prev_hat[b] = update_prev ? dist_prev : sp;
     t_hat[b] = fminf(fmaxf(static_cast<float>(t), 0.f), 1000.f);
-    if (in_scale_out) in_scale_out[b] = sqrtf(1.0f / (dist * dist + 1.0f));
+    if (in_scale_out) in_scale_out[b] = sqrtf(DIV(1.0f, ADD(MUL(dist, dist), 1.0f)));
 }
 
 // grid (chunks, B)
@@ -129,7 +136,8 @@ __global__ void __launch_bounds__(256) pred_xstart_kernel(const float* __restric
     float4* o4 = reinterpret_cast<float4*>(x0 + base);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (d >> 2); i += gridDim.x * blockDim.x) {
         const float4 x = __ldg(x4 + i), e = __ldg(e4 + i);
-        float4 o = make_float4(x.x - s * e.x, x.y - s * e.y, x.z - s * e.z, x.w - s * e.w);
+        float4 o = make_float4(SUB(x.x, MUL(s, e.x)), SUB(x.y, MUL(s, e.y)), SUB(x.z, MUL(s, e.z)),
+                               SUB(x.w, MUL(s, e.w)));
         if (clip == NLC_CLIP_CLAMP) {
             o.x = fminf(fmaxf(o.x, -1.f), 1.f), o.y = fminf(fmaxf(o.y, -1.f), 1.f);
             o.z = fminf(fmaxf(o.z, -1.f), 1.f), o.w = fminf(fmaxf(o.w, -1.f), 1.f);
@@ -160,28 +168,31 @@ __global__ void __launch_bounds__(256) pred_xprev_kernel(const XprevArgs a) {
     const float sp = a.sigma_prev[a.n_prev == 1 ? 0 : b];
     const float eta = static_cast<float>(a.eta);
     // get_eps_logvar (src/schedulers.py:367-390)
+    const float st2 = MUL(st, st), sp2 = MUL(sp, sp);
     float max_lv = 0.f, min_lv = 0.f;
     if (a.logvar_mode != 0) {
-        float beta_t = (st * st - sp * sp) / (st * st + 1.0f);
+        float beta_t = DIV(SUB(st2, sp2), ADD(st2, 1.0f));
         beta_t = fmaxf(fabsf(beta_t), 1e-20f);
-        const float alpha_t = 1.0f / (st * st + 1.0f), alpha_prev = 1.0f / (sp * sp + 1.0f);
-        float coef = (1.0f - alpha_prev) / (1.0f - alpha_t);
+        const float alpha_t = DIV(1.0f, ADD(st2, 1.0f)), alpha_prev = DIV(1.0f, ADD(sp2, 1.0f));
+        float coef = DIV(SUB(1.0f, alpha_prev), SUB(1.0f, alpha_t));
         coef = fminf(fmaxf(coef, 0.f), 1.f);
-        const float post_var = beta_t * coef;
+        const float post_var = MUL(beta_t, coef);
         max_lv = logf(beta_t);
         min_lv = logf(fmaxf(post_var, a.min_var_coef));
     }
-    const float abp_sqrt = sqrtf(1.0f / (sp * sp + 1.0f));  // sqrt(alpha_bar_prev)
+    const float abp_sqrt = sqrtf(DIV(1.0f, ADD(sp2, 1.0f)));  // sqrt(alpha_bar_prev)
     const float mask = sp > 0.f ? 1.f : 0.f;
-    const float simple_signal = static_cast<float>(sqrt(1.0 - a.eta * a.eta)) * sp;
+    const float simple_signal = MUL(static_cast<float>(sqrt(1.0 - a.eta * a.eta)), sp);
+    const float eta_sp = MUL(eta, sp);
     // DDPM_orig posterior coefficients (src/schedulers.py:581-599)
-    float pm1 = 0.f, pm2 = 0.f, ab_sqrt = 0.f;
+    float pm1 = 0.f, pm2 = 0.f, ab_sqrt = 0.f, abp_sqrt2 = 0.f;
     if (a.sched == NLC_SCHED_DDPM_ORIG) {
-        const float alpha_bar = 1.0f / (st * st + 1.0f), alpha_bar_prev = 1.0f / (sp * sp + 1.0f);
-        const float alpha_t = alpha_bar / alpha_bar_prev, beta_t = 1.0f - alpha_t;
-        pm1 = beta_t * sqrtf(alpha_bar_prev) / (1.0f - alpha_bar);
-        pm2 = (1.0f - alpha_bar_prev) * sqrtf(alpha_t) / (1.0f - alpha_bar);
+        const float alpha_bar = DIV(1.0f, ADD(st2, 1.0f)), alpha_bar_prev = DIV(1.0f, ADD(sp2, 1.0f));
+        const float alpha_t = DIV(alpha_bar, alpha_bar_prev), beta_t = SUB(1.0f, alpha_t);
+        pm1 = DIV(MUL(beta_t, sqrtf(alpha_bar_prev)), SUB(1.0f, alpha_bar));
+        pm2 = DIV(MUL(SUB(1.0f, alpha_bar_prev), sqrtf(alpha_t)), SUB(1.0f, alpha_bar));
         ab_sqrt = sqrtf(alpha_bar);
+        abp_sqrt2 = sqrtf(alpha_bar_prev);
     }
     const size_t base = static_cast<size_t>(b) * a.d;
     bool saw_nan = false;
@@ -202,11 +213,11 @@ __global__ void __launch_bounds__(256) pred_xprev_kernel(const XprevArgs a) {
         float O[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (rederive) E[k] = (XT[k] - X0[k]) / st;
+            if (rederive) E[k] = DIV(SUB(XT[k], X0[k]), st);
             float logvar = 0.f;
             if (a.logvar_mode == 1) {
-                const float frac = (LV[k] + 1.0f) / 2.0f;
-                logvar = frac * max_lv + (1.0f - frac) * min_lv;
+                const float frac = DIV(ADD(LV[k], 1.0f), 2.0f);
+                logvar = ADD(MUL(frac, max_lv), MUL(SUB(1.0f, frac), min_lv));
             } else if (a.logvar_mode == 2) {
                 logvar = min_lv;
             } else if (a.logvar_mode == 3) {
@@ -214,45 +225,37 @@ __global__ void __launch_bounds__(256) pred_xprev_kernel(const XprevArgs a) {
             }
             float o;
             switch (a.sched) {
-                case NLC_SCHED_DDIM: {
-                    float noise_sigma = 0.f, nz = 0.f;
-                    if (a.eta > 0) {
-                        noise_sigma = eta * expf(0.5f * logvar) / abp_sqrt;
-                        nz = mask * NZ[k];
-                    }
-                    const float signal = sqrtf(fmaxf(sp * sp - noise_sigma * noise_sigma, 0.f));
-                    noise_sigma = sqrtf(sp * sp - signal * signal);
-                    o = X0[k] + signal * E[k] + noise_sigma * nz;
-                } break;
+                case NLC_SCHED_DDIM:
                 case NLC_SCHED_DDIM_ORIG: {
                     float noise_sigma = 0.f, nz = 0.f;
                     if (a.eta > 0) {
-                        noise_sigma = eta * expf(0.5f * logvar) / abp_sqrt;
-                        nz = mask * NZ[k];
+                        noise_sigma = DIV(MUL(eta, expf(MUL(0.5f, logvar))), abp_sqrt);
+                        nz = MUL(mask, NZ[k]);
                     }
-                    const float signal = sqrtf(fmaxf(sp * sp - noise_sigma * noise_sigma, 0.f));
-                    o = X0[k] + signal * E[k] + noise_sigma * nz;
+                    const float signal = sqrtf(fmaxf(SUB(sp2, MUL(noise_sigma, noise_sigma)), 0.f));
+                    if (a.sched == NLC_SCHED_DDIM) noise_sigma = sqrtf(SUB(sp2, MUL(signal, signal)));
+                    o = ADD(ADD(X0[k], MUL(signal, E[k])), MUL(noise_sigma, nz));
                 } break;
                 case NLC_SCHED_DDIM_SIMPLE:
                 case NLC_SCHED_DDIM_SIMPLE_ORIG: {
-                    o = X0[k] + simple_signal * E[k];
-                    if (a.eta > 0) o = o + (eta * sp) * NZ[k];
+                    o = ADD(X0[k], MUL(simple_signal, E[k]));
+                    if (a.eta > 0) o = ADD(o, MUL(eta_sp, NZ[k]));
                 } break;
                 case NLC_SCHED_DDIM_SIMPLE_DRAG: {
-                    o = X0[k] + sp * E[k];
-                    if (a.eta > 0) o = o + (eta * sp) * NZ[k];
+                    o = ADD(X0[k], MUL(sp, E[k]));
+                    if (a.eta > 0) o = ADD(o, MUL(eta_sp, NZ[k]));
                 } break;
                 case NLC_SCHED_DDPM: {
-                    const float noise_sigma = expf(0.5f * logvar) / abp_sqrt;
-                    const float signal = sqrtf(fmaxf(sp * sp - noise_sigma * noise_sigma, 0.f));
-                    o = X0[k] + signal * E[k];
-                    o = o + noise_sigma * (mask * NZ[k]);
+                    const float noise_sigma = DIV(expf(MUL(0.5f, logvar)), abp_sqrt);
+                    const float signal = sqrtf(fmaxf(SUB(sp2, MUL(noise_sigma, noise_sigma)), 0.f));
+                    o = ADD(X0[k], MUL(signal, E[k]));
+                    o = ADD(o, MUL(noise_sigma, MUL(mask, NZ[k])));
                 } break;
                 default: {  // NLC_SCHED_DDPM_ORIG
-                    const float zt = XT[k] * ab_sqrt;
-                    const float mean = pm1 * X0[k] + pm2 * zt;
-                    const float zprev = mean + mask * expf(0.5f * logvar) * NZ[k];
-                    o = zprev / abp_sqrt;
+                    const float zt = MUL(XT[k], ab_sqrt);
+                    const float mean = ADD(MUL(pm1, X0[k]), MUL(pm2, zt));
+                    const float zprev = ADD(mean, MUL(MUL(mask, expf(MUL(0.5f, logvar))), NZ[k]));
+                    o = DIV(zprev, abp_sqrt2);
                 } break;
             }
             O[k] = o;

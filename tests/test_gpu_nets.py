@@ -63,7 +63,8 @@ def test_benchmark_architectures_vs_oracle(name, B, prec):
 
 def test_input_scale_folding_and_batch_independence():
     """forward_scaled(x, t, scale) == forward(x*scale, t); rows do not interact (the property batch sharding rests
-    on): a batch of 6 equals two batches of 3 up to GroupNorm partial-merge order (1e-5)."""
+    on): a batch of 6 equals two batches of 3.  Tolerance 2e-3: a last-bit difference in fp32 (scale applied after
+    instead of before conv_in; GroupNorm partial-merge order) can flip a tf32 operand rounding downstream."""
     cfg, sd, _, m, _ = _models("tiny", "tf32")
     R = cfg["unet"]["image_size"]
     g = torch.Generator().manual_seed(6)
@@ -72,10 +73,10 @@ def test_input_scale_folding_and_batch_independence():
     sc = (torch.rand(6, generator=g) + 0.2).to(dev)
     a = m.forward_scaled(x, t, sc).clone()
     b = m.forward_scaled(x * sc.view(-1, 1, 1, 1), t, None).clone()
-    assert _rel(a, b) < 1e-5
+    assert _rel(a, b) < 2e-3
     lo = m.forward_scaled(x[:3].contiguous(), t[:3], sc[:3]).clone()
     hi = m.forward_scaled(x[3:].contiguous(), t[3:], sc[3:]).clone()
-    assert _rel(torch.cat([lo, hi]), a) < 1e-5
+    assert _rel(torch.cat([lo, hi]), a) < 2e-3
 
 
 def test_load_state_dict_reports_missing_keys():

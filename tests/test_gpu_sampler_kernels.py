@@ -22,10 +22,10 @@ def test_row_norm_and_normalize():
         x = torch.randn(shape, generator=g) * 3
         n = torch.zeros(shape[0], device=dev)
         ops.row_norm(x.to(dev), n)
-        assert _rel(n.cpu(), S.vector_norm(x).reshape(-1)) < 1e-6
+        assert _rel(n.cpu(), S.vector_norm(x).reshape(-1)) < 3e-6
         y = x.to(dev).clone()
         ops.normalize_rows_(y)
-        assert _rel(y.cpu(), S.normalize(x, x[0].numel())) < 1e-6
+        assert _rel(y.cpu(), S.normalize(x, x[0].numel())) < 3e-6
 
 
 def test_refine_and_correct_match_the_oracle_bit_for_bit_in_t():
