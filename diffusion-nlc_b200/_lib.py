@@ -67,6 +67,7 @@ _SIGNATURES = {
     "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _P]),
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
+    "nlc_resample_op": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "nlc_attention": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P]),
     "nlc_attention_ws": (_SZ, [_I, _I, _I, _I, _I]),
     "nlc_linear": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P]),

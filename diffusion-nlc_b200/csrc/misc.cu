@@ -8,8 +8,20 @@ namespace nlc {
 
 // ---------------------------------------------------------------- resample: copy / nearest x2 / avgpool 2x2
 // x: NHWC fp32 [B,H,W,C] (pitch ld_x); outputs at the resampled resolution, fp32 and/or operand dtype.
-template <int MODE, bool TF32>
-__global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C,
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+}
+
+template <int MODE, bool TF32, typename TIN>
+__global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x, int ld_x, int H, int W, int C,
                                                         float* __restrict__ yf, int ld_yf, void* __restrict__ yo,
                                                         int ld_yo, long long total4) {
     const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : H);
@@ -25,11 +37,11 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
         const int n = static_cast<int>(pix / Ho);
         float4 v;
         if (MODE == 2) {
-            const float* p = x + ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * ld_x + c;
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p + ld_x));
-            const float4 d = __ldg(reinterpret_cast<const float4*>(p + static_cast<size_t>(W) * ld_x));
-            const float4 e = __ldg(reinterpret_cast<const float4*>(p + static_cast<size_t>(W) * ld_x + ld_x));
+            const TIN* p = x + ((static_cast<size_t>(n) * H + 2 * ho) * W + 2 * wo) * ld_x + c;
+            const float4 a = ld4<TIN>(p);
+            const float4 b = ld4<TIN>(p + ld_x);
+            const float4 d = ld4<TIN>(p + static_cast<size_t>(W) * ld_x);
+            const float4 e = ld4<TIN>(p + static_cast<size_t>(W) * ld_x + ld_x);
             // same association as torch avg_pool2d: sum of the window, then divide
             v.x = ((a.x + b.x) + (d.x + e.x)) * 0.25f;
             v.y = ((a.y + b.y) + (d.y + e.y)) * 0.25f;
@@ -37,7 +49,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
             v.w = ((a.w + b.w) + (d.w + e.w)) * 0.25f;
         } else {
             const int hi = MODE == 1 ? ho >> 1 : ho, wi = MODE == 1 ? wo >> 1 : wo;
-            v = __ldg(reinterpret_cast<const float4*>(x + ((static_cast<size_t>(n) * H + hi) * W + wi) * ld_x + c));
+            v = ld4<TIN>(x + ((static_cast<size_t>(n) * H + hi) * W + wi) * ld_x + c);
         }
         const size_t opix = (static_cast<size_t>(n) * Ho + ho) * Wo + wo;
         if (yf) *reinterpret_cast<float4*>(yf + opix * ld_yf + c) = v;
@@ -139,9 +151,9 @@ extern "C" int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
     const bool tf32 = op_dtype == NLC_F32;
-#define NLC_RS(M, T)                                                                                              \
-    resample_kernel<M, T><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld_x, H, W, C, y_f32, ld_y_f32, y_op, \
-                                                                             ld_y_op, total4)
+#define NLC_RS(M, T)                                                                                          \
+    resample_kernel<M, T, float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld_x, H, W, C, y_f32,      \
+                                                                                    ld_y_f32, y_op, ld_y_op, total4)
     if (mode == 0) {
         if (tf32) NLC_RS(0, true); else NLC_RS(0, false);
     } else if (mode == 1) {
@@ -150,6 +162,33 @@ extern "C" int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H
         if (tf32) NLC_RS(2, true); else NLC_RS(2, false);
     }
 #undef NLC_RS
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_resample_op(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int H, int W, int C,
+                               int mode, void* y_op, int ld_y, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x_op && y_op, "nlc_resample_op: null argument");
+    NLC_REQUIRE((mode == 1 || mode == 2) && C % 4 == 0 && ld_x % 4 == 0 && ld_y % 4 == 0, "nlc_resample_op: bad mode/C");
+    NLC_REQUIRE(mode != 2 || (H % 2 == 0 && W % 2 == 0), "nlc_resample_op: avgpool needs even H, W");
+    const int Ho = mode == 1 ? 2 * H : H / 2, Wo = mode == 1 ? 2 * W : W / 2;
+    const long long total4 = static_cast<long long>(B) * Ho * Wo * (C / 4);
+    long long blocks = (total4 + 255) / 256;
+    const long long cap = static_cast<long long>(ctx->sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    const unsigned g = static_cast<unsigned>(blocks);
+    if (op_dtype == NLC_F32) {
+        const float* x = static_cast<const float*>(x_op);
+        if (mode == 1) resample_kernel<1, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+        else resample_kernel<2, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+    } else {
+        const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_op);
+        if (mode == 1)
+            resample_kernel<1, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+        else
+            resample_kernel<2, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+    }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

@@ -165,6 +165,13 @@ def resample(x, mode, y_f32, y_op, op_dtype):
     STATS.launches += 1
 
 
+def resample_op(x_op, mode, y_op, op_dtype):
+    """mode 1 nearest x2, 2 avgpool 2x2 on an operand-dtype Act."""
+    _lib.check(_lib.lib().nlc_resample_op(_ctx(x_op.t), C.c_void_p(x_op.ptr), op_dtype, x_op.ld, x_op.B, x_op.H, x_op.W,
+                                          x_op.C, mode, C.c_void_p(y_op.ptr), y_op.ld, _stream()))
+    STATS.launches += 1
+
+
 def attention_ws(op_dtype, B, T, heads, dh):
     return int(_lib.lib().nlc_attention_ws(op_dtype, B, T, heads, dh))
 

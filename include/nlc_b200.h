@@ -128,6 +128,11 @@ size_t nlc_groupnorm_ws(int B, int HW, int C, int groups);
 int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int mode, float* y_f32,
                  int ld_y_f32, void* y_op, int ld_y_op, int op_dtype, void* stream);
 
+/* Same resampling on a tensor that is already in the operand dtype (ADM's resblock_updown pools / upsamples the
+ * activated tensor GN+SiLU(x) before the block's first conv, src/unet_adm.py:236-243). mode: 1 up2, 2 avgpool2 */
+int nlc_resample_op(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int H, int W, int C, int mode,
+                    void* y_op, int ld_y, void* stream);
+
 /* Fused softmax attention over NHWC tokens: qkv is [B, T, ld] with q at column q_off + h*dh, etc.
  * Replaces bmm/softmax/bmm (src/unet_ddim.py:193-207), QKVAttention(Legacy) (src/unet_adm.py:328-389),
  * AttentionOp (src/edm_networks.py:124-130).  softmax(scale * q k^T) v, fp32 math, output operand dtype. */

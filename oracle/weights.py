@@ -135,3 +135,121 @@ CONFIGS = {
                            attention_resolutions=(8,), channel_mult=(1, 2)),
                  sigma=dict(dim=8, channels=256, n_blocks=2)),
 }
+
+
+# ------------------------------------------------------------------------------------------------ ADM (src/unet_adm.py)
+def _adm_res(I, p, cin, cout, emb_ch=None, scale_shift=False):
+    I.norm(p + "in_layers.0", cin)
+    I.conv(p + "in_layers.2", cin, cout, 3)
+    if emb_ch is not None:
+        I.linear(p + "emb_layers.1", emb_ch, 2 * cout if scale_shift else cout, gain=0.5)
+    I.norm(p + "out_layers.0", cout)
+    I.conv(p + "out_layers.3", cout, cout, 3, gain=0.5)  # zero_module in the reference: re-drawn
+    if cin != cout:
+        I.conv(p + "skip_connection", cin, cout, 1)
+
+
+def _adm_attn(I, p, c):
+    I.norm(p + "norm", c)
+    I.sd[p + "qkv.weight"] = I.randn(3 * c, c, 1) / c ** 0.5
+    I.sd[p + "qkv.bias"] = I.randn(3 * c) * 0.02
+    I.sd[p + "proj_out.weight"] = I.randn(c, c, 1) * (0.5 / c ** 0.5)
+    I.sd[p + "proj_out.bias"] = I.randn(c) * 0.02
+
+
+def adm_unet_state_dict(image_size, model_channels, num_res_blocks, channel_mult, attention_resolutions,
+                        out_channels=6, use_scale_shift_norm=True, resblock_updown=True, seed=0, **_):
+    """Same keys/shapes as src.unet_adm.UNetModel(...).state_dict() (attention_resolutions are the reference's
+    downsample factors `ds`, src/script_util.py:170-172)."""
+    I = _Init(seed)
+    mc, emb = model_channels, 4 * model_channels
+    I.linear("time_embed.0", mc, emb)
+    I.linear("time_embed.2", emb, emb)
+    ch = int(channel_mult[0] * mc)
+    I.conv("input_blocks.0.0", 3, ch, 3)
+    chans, ds, idx = [ch], 1, 1
+    L = len(channel_mult)
+    for level, mult in enumerate(channel_mult):
+        for _ in range(num_res_blocks):
+            _adm_res(I, "input_blocks.%d.0." % idx, ch, int(mult * mc), emb, use_scale_shift_norm)
+            ch = int(mult * mc)
+            if ds in attention_resolutions:
+                _adm_attn(I, "input_blocks.%d.1." % idx, ch)
+            chans.append(ch)
+            idx += 1
+        if level != L - 1:
+            if resblock_updown:
+                _adm_res(I, "input_blocks.%d.0." % idx, ch, ch, emb, use_scale_shift_norm)
+            else:
+                I.conv("input_blocks.%d.0.op" % idx, ch, ch, 3)
+            chans.append(ch)
+            idx += 1
+            ds *= 2
+    _adm_res(I, "middle_block.0.", ch, ch, emb, use_scale_shift_norm)
+    _adm_attn(I, "middle_block.1.", ch)
+    _adm_res(I, "middle_block.2.", ch, ch, emb, use_scale_shift_norm)
+    idx = 0
+    for level, mult in list(enumerate(channel_mult))[::-1]:
+        for i in range(num_res_blocks + 1):
+            ich = chans.pop()
+            _adm_res(I, "output_blocks.%d.0." % idx, ch + ich, int(mc * mult), emb, use_scale_shift_norm)
+            ch = int(mc * mult)
+            j = 1
+            if ds in attention_resolutions:
+                _adm_attn(I, "output_blocks.%d.%d." % (idx, j), ch)
+                j += 1
+            if level and i == num_res_blocks:
+                if resblock_updown:
+                    _adm_res(I, "output_blocks.%d.%d." % (idx, j), ch, ch, emb, use_scale_shift_norm)
+                else:
+                    I.conv("output_blocks.%d.%d.conv" % (idx, j), ch, ch, 3)
+                ds //= 2
+            idx += 1
+    I.norm("out.0", ch)
+    I.conv("out.2", ch, out_channels, 3, gain=0.5)
+    return I.sd
+
+
+def adm_sigma_state_dict(dim, channels, n_blocks, seed=1, fc_dim=128):
+    """Same keys/shapes as src.unet_adm.SigmaModel(dim, channels, n_blocks).state_dict()."""
+    I = _Init(seed)
+    idx, d = 0, dim
+    for i in range(n_blocks):
+        if d % 2 != 0:
+            d += 1
+        idx += 1
+        _adm_res(I, "down_layer.%d." % idx, channels, channels)
+        idx += 1
+        if i == 0:
+            _adm_attn(I, "down_layer.%d." % idx, channels)
+            idx += 1
+        I.conv("down_layer.%d.op" % idx, channels, channels, 3)
+        idx += 1
+        d //= 2
+    I.linear("fc_layer.1", channels * d * d, fc_dim)
+    I.sd["fc_layer.2.weight"] = 1.0 + 0.1 * I.randn(fc_dim)
+    I.sd["fc_layer.2.bias"] = 0.05 * I.randn(fc_dim)
+    I.sd["fc_layer.2.running_mean"] = 0.1 * I.randn(fc_dim)
+    I.sd["fc_layer.2.running_var"] = 0.5 + torch.rand(fc_dim, generator=I.g)
+    I.sd["fc_layer.2.num_batches_tracked"] = torch.tensor(0)
+    I.linear("final_mlp", fc_dim, 1, gain=0.3)
+    return I.sd
+
+
+ADM_CONFIGS = {
+    # c4/c5: ImageNet-256 ADM (256x256_diffusion_uncond): attention at 32/16/8 -> ds 8,16,32
+    "adm256": dict(image_size=256, model_channels=256, num_res_blocks=2, channel_mult=(1, 1, 2, 2, 4, 4),
+                   attention_resolutions=(8, 16, 32), num_head_channels=64, num_heads=4, out_channels=6,
+                   use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=False,
+                   sigma=dict(dim=8, channels=1024, n_blocks=2)),
+    # same topology, two levels, for unit tests
+    "adm_tiny": dict(image_size=32, model_channels=128, num_res_blocks=1, channel_mult=(1, 2),
+                     attention_resolutions=(2,), num_head_channels=64, num_heads=4, out_channels=6,
+                     use_scale_shift_norm=True, resblock_updown=True, use_new_attention_order=False,
+                     sigma=dict(dim=16, channels=256, n_blocks=2)),
+    # no scale-shift, conv resampling, new attention order, fixed head count: the other code paths
+    "adm_alt": dict(image_size=32, model_channels=128, num_res_blocks=1, channel_mult=(1, 2),
+                    attention_resolutions=(1, 2), num_head_channels=-1, num_heads=2, out_channels=3,
+                    use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=True,
+                    sigma=dict(dim=16, channels=256, n_blocks=2)),
+}
