@@ -6,6 +6,8 @@ shared between layers, skip tensors are written straight into the channel slice 
 decoder block will read), and the plan is a flat list of closures.  Running a plan only enqueues kernels on the
 current stream, so it can be replayed or captured in a CUDA graph.
 """
+import os
+
 import torch
 
 from . import ops
@@ -45,10 +47,29 @@ class Engine:
         self.chunk = 64 if self.op_dtype == NLC_BF16 else 32
         self._scratch = {}
         self._named = {}
+        self._sizing = None
 
     # ------------------------------------------------------------------ buffers
+    def plan_two_pass(self, build):
+        """Run `build()` twice: a sizing pass on the meta device that only records the largest request per scratch
+        tag, then the real pass against scratch buffers allocated once at their final size (a scratch buffer that
+        grew between two layers of one plan would otherwise stay alive twice)."""
+        self._sizing = {}
+        try:
+            build()
+            sizes = self._sizing
+        finally:
+            self._sizing = None
+        for (tag, dtype), n in sizes.items():
+            t = self._scratch.get((tag, dtype))
+            if t is None or t.numel() < n:
+                self._scratch[(tag, dtype)] = torch.empty(n, device=self.device, dtype=dtype)
+        return build()
+
     def named(self, name, shape, dtype):
         """A buffer that lives as long as the plan (skip/concat tensors, outputs)."""
+        if self._sizing is not None:
+            return torch.empty(shape, device="meta", dtype=dtype)
         key = (name, tuple(shape), dtype)
         t = self._named.get(key)
         if t is None:
@@ -63,6 +84,9 @@ class Engine:
         for s in shape:
             n *= s
         key = (tag, dtype)
+        if self._sizing is not None:
+            self._sizing[key] = max(self._sizing.get(key, 0), n)
+            return torch.empty(shape, device="meta", dtype=dtype)
         t = self._scratch.get(key)
         if t is None or t.numel() < n:
             t = torch.empty(n, device=self.device, dtype=dtype)
@@ -99,7 +123,9 @@ class PlanCtx:
         self._gn_ws_floats = 0
         self._attn_ws_bytes = 0
 
-    def add(self, fn):
+    def add(self, fn, label=None):
+        if label is not None:
+            fn.label = label
         self.steps.append(fn)
 
     def gn_ws(self, B, HW, C, groups):
@@ -117,7 +143,8 @@ class PlanCtx:
 def emit_groupnorm(pc, x32, gamma, beta, groups, eps, y_op, silu=True, scale=None, shift=None):
     ws = pc.gn_ws(x32.B, x32.H * x32.W, x32.C, groups)
     dt = pc.eng.op_dtype
-    pc.add(lambda: ops.groupnorm(x32, groups, eps, gamma, beta, y_op, dt, ws(), silu=silu, scale=scale, shift=shift))
+    pc.add(lambda: ops.groupnorm(x32, groups, eps, gamma, beta, y_op, dt, ws(), silu=silu, scale=scale, shift=shift),
+           "groupnorm %dx%dx%d B%d" % (x32.H, x32.W, x32.C, x32.B))
 
 
 def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None, out_scale=1.0, stride=1, pad=1,
@@ -133,7 +160,8 @@ def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None
         srcs.append(extra_src)
         segs = segs + [(1, 0, 0, 0, extra_src.C)]
     pc.add(lambda: ops.conv_tc(srcs, segs, w_packed, Cout, B, Ho, Wo, dt, stride=stride, bias=bias, rowvec=rowvec,
-                               resid=resid, out_scale=out_scale, out_f32=dest.f32, out_op=dest.op))
+                               resid=resid, out_scale=out_scale, out_f32=dest.f32, out_op=dest.op),
+           "conv3x3 %dx%d %d->%d s%d B%d%s" % (Ho, Wo, src_op.C, Cout, stride, B, " +1x1" if extra_src is not None else ""))
 
 
 def emit_conv1x1(pc, src_op, w_packed, bias, Cout, dest, resid=None, out_scale=1.0):
@@ -141,15 +169,25 @@ def emit_conv1x1(pc, src_op, w_packed, bias, Cout, dest, resid=None, out_scale=1
     B, H, W = src_op.B, src_op.H, src_op.W
     segs = [(0, 0, 0, 0, src_op.C)]
     pc.add(lambda: ops.conv_tc([src_op], segs, w_packed, Cout, B, H, W, dt, bias=bias, resid=resid,
-                               out_scale=out_scale, out_f32=dest.f32, out_op=dest.op))
+                               out_scale=out_scale, out_f32=dest.f32, out_op=dest.op),
+           "conv1x1 %dx%d %d->%d B%d" % (H, W, src_op.C, Cout, B))
 
 
 def emit_attention(pc, qkv_op, q_off, k_off, v_off, head_stride, heads, dh, scale, out_op):
     ws = pc.attn_ws(qkv_op.B, qkv_op.H * qkv_op.W, heads, dh)
     dt = pc.eng.op_dtype
-    pc.add(lambda: ops.attention(qkv_op, dt, q_off, k_off, v_off, head_stride, heads, dh, scale, out_op, ws()))
+    pc.add(lambda: ops.attention(qkv_op, dt, q_off, k_off, v_off, head_stride, heads, dh, scale, out_op, ws()),
+           "attention T%d heads%d dh%d B%d" % (qkv_op.H * qkv_op.W, heads, dh, qkv_op.B))
 
 
 def run(steps):
+    if os.environ.get("NLC_SYNC") == "1":  # debugging aid: localise an asynchronous kernel fault to its plan step
+        for i, fn in enumerate(steps):
+            fn()
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:
+                raise RuntimeError("plan step %d (%s) faulted: %s" % (i, getattr(fn, "label", "?"), e)) from e
+        return
     for fn in steps:
         fn()

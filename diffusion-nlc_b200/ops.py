@@ -16,9 +16,29 @@ class _Stats:
     (flops, start, stop) is appended."""
     launches = 0
     conv_timer = None
+    op_timer = None  # list -> every wrapper below appends (name, start_event, stop_event, flops)
 
 
 STATS = _Stats()
+
+
+def _timed(name):
+    """Profiling aid (scripts/step_profile.py): bracket the wrapped launch with CUDA events on the launching
+    stream when STATS.op_timer is a list.  No effect otherwise."""
+    def deco(fn):
+        def wrapped(*a, **k):
+            t = STATS.op_timer
+            if t is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            t.append((name, e0, e1, 0.0))
+            return r
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
 
 
 def _stream():
@@ -111,17 +131,23 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.out_f32, d.ld_out_f32 = out_f32.ptr, out_f32.ld
     if out_op is not None:
         d.out_op, d.ld_out_op = out_op.ptr, out_op.ld
-    timer = STATS.conv_timer
-    if timer is not None:
+    timer, optimer = STATS.conv_timer, STATS.op_timer
+    if timer is not None or optimer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     _lib.check(_lib.lib().nlc_conv_tc(_ctx(srcs[0].t), C.byref(d), _stream()))
     STATS.launches += 1
-    if timer is not None:
+    if timer is not None or optimer is not None:
         e1.record()
-        timer.append((2.0 * B * Ho * Wo * Cout * sum(sg[4] for sg in segs), e0, e1))
+        flops = 2.0 * B * Ho * Wo * Cout * sum(sg[4] for sg in segs)
+        if timer is not None:
+            timer.append((flops, e0, e1))
+        if optimer is not None:
+            optimer.append(("conv_tc %dx%d K%d N%d s%d%s" % (Ho, Wo, sum(sg[4] for sg in segs), Cout, stride,
+                                                           " +f32" if out_f32 is not None else ""), e0, e1, flops))
 
 
+@_timed("conv_in_nchw")
 def conv_in_nchw(x_nchw, in_scale, weight, bias, out_f32, out_op, op_dtype):
     """Direct 3x3 conv on the sampler's NCHW fp32 image -> NHWC (nlc_conv_in_nchw)."""
     B, Cin, H, W = x_nchw.shape
@@ -134,6 +160,7 @@ def conv_in_nchw(x_nchw, in_scale, weight, bias, out_f32, out_op, op_dtype):
     STATS.launches += 1
 
 
+@_timed("conv_out_nchw")
 def conv_out_nchw(x_op, op_dtype, weight, bias, out_nchw):
     """Direct 3x3 conv NHWC operand -> NCHW fp32 (nlc_conv_out_nchw)."""
     Cout = weight.shape[0]
@@ -147,6 +174,7 @@ def groupnorm_ws(B, HW, C, groups):
     return int(_lib.lib().nlc_groupnorm_ws(B, HW, C, groups))
 
 
+@_timed("groupnorm")
 def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=None, shift=None):
     """GroupNorm (+scale/shift, +SiLU) of fp32 NHWC `x` (Act) into operand `y_op` (Act)."""
     ld_ss = scale.stride(0) if scale is not None else 0
@@ -156,6 +184,7 @@ def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=
     STATS.launches += 2
 
 
+@_timed("resample")
 def resample(x, mode, y_f32, y_op, op_dtype):
     """mode 0 copy/cast, 1 nearest x2, 2 avgpool 2x2; x fp32 Act -> fp32 and/or operand Act."""
     _lib.check(_lib.lib().nlc_resample(
@@ -165,6 +194,7 @@ def resample(x, mode, y_f32, y_op, op_dtype):
     STATS.launches += 1
 
 
+@_timed("resample_op")
 def resample_op(x_op, mode, y_op, op_dtype):
     """mode 1 nearest x2, 2 avgpool 2x2 on an operand-dtype Act."""
     _lib.check(_lib.lib().nlc_resample_op(_ctx(x_op.t), C.c_void_p(x_op.ptr), op_dtype, x_op.ld, x_op.B, x_op.H, x_op.W,
@@ -176,6 +206,7 @@ def attention_ws(op_dtype, B, T, heads, dh):
     return int(_lib.lib().nlc_attention_ws(op_dtype, B, T, heads, dh))
 
 
+@_timed("attention")
 def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale, out, ws):
     """qkv: Act [B,H,W,ld]; out: Act [B,H,W,heads*dh] (operand dtype)."""
     T = qkv.H * qkv.W
@@ -185,6 +216,7 @@ def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale,
     STATS.launches += 4 if T >= 128 else 1
 
 
+@_timed("linear")
 def linear(x, W, bias, y, act_in=0, act_out=0):
     """y = act_out(act_in(x) @ W.T + bias); x [B,K], W [N,K], y [B,N] fp32 (rows may be strided)."""
     B, K = x.shape
@@ -195,6 +227,7 @@ def linear(x, W, bias, y, act_in=0, act_out=0):
     STATS.launches += 1
 
 
+@_timed("timestep_embedding")
 def timestep_embedding(t, freqs, cos_first, out):
     B = t.shape[0]
     half = freqs.shape[0]
@@ -203,6 +236,7 @@ def timestep_embedding(t, freqs, cos_first, out):
     STATS.launches += 1
 
 
+@_timed("row_norm")
 def row_norm(x, out):
     B = x.shape[0]
     d = x[0].numel()
@@ -210,6 +244,7 @@ def row_norm(x, out):
     STATS.launches += 1
 
 
+@_timed("normalize_rows_")
 def normalize_rows_(x):
     B = x.shape[0]
     d = x[0].numel()
@@ -217,6 +252,7 @@ def normalize_rows_(x):
     STATS.launches += 1
 
 
+@_timed("refine_sigma")
 def refine_sigma(norms, B, d, sigma_in, norm_min, norm_max, refine, t_fixed, table, time_shift, sigma_out, t_out,
                  in_scale_out):
     _lib.check(_lib.lib().nlc_refine_sigma(
@@ -226,6 +262,7 @@ def refine_sigma(norms, B, d, sigma_in, norm_min, norm_max, refine, t_fixed, tab
     STATS.launches += 1
 
 
+@_timed("sigma_correct")
 def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out):
     B = sigma.numel()
     _lib.check(_lib.lib().nlc_sigma_correct(
@@ -234,6 +271,7 @@ def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_pre
     STATS.launches += 1
 
 
+@_timed("pred_xstart")
 def pred_xstart(xt, eps, sigma, clip, x0):
     B = xt.shape[0]
     d = xt[0].numel()
@@ -242,6 +280,7 @@ def pred_xstart(xt, eps, sigma, clip, x0):
     STATS.launches += 1
 
 
+@_timed("pred_xprev")
 def pred_xprev(sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_coef, sigma, sigma_prev, x_prev,
                nan_flag=None):
     B = x0.shape[0]

@@ -191,9 +191,12 @@ class UNetModel:
 
     # ------------------------------------------------------------------ plan
     def _plan(self, B):
-        if B in self._plans:
-            return self._plans[B]
-        assert self._loaded, "load_state_dict() first"
+        if B not in self._plans:
+            assert self._loaded, "load_state_dict() first"
+            self._plans[B] = self.eng.plan_two_pass(lambda: self._build_plan(B))
+        return self._plans[B]
+
+    def _build_plan(self, B):
         eng, R, ch = self.eng, self.resolution, self.ch
         f32, opt = torch.float32, eng.op_torch
         P = {}
@@ -328,7 +331,6 @@ class UNetModel:
         enc._gn_ws_floats = dec._gn_ws_floats = max(enc._gn_ws_floats, dec._gn_ws_floats)
         enc._attn_ws_bytes = dec._attn_ws_bytes = max(enc._attn_ws_bytes, dec._attn_ws_bytes)
         P["enc"], P["dec"] = enc.steps, dec.steps
-        self._plans[B] = P
         return P
 
     # ------------------------------------------------------------------ execution
@@ -435,8 +437,11 @@ class SigmaModel:
         return self.load_state_dict(m.state_dict())
 
     def _plan(self, B):
-        if B in self._plans:
-            return self._plans[B]
+        if B not in self._plans:
+            self._plans[B] = self.eng.plan_two_pass(lambda: self._build_plan(B))
+        return self._plans[B]
+
+    def _build_plan(self, B):
         eng, C = self.eng, self.channels
         f32 = torch.float32
         P = {"feat": eng.named("sig.feat", (B, self.dim, self.dim, C), f32)}
@@ -462,7 +467,6 @@ class SigmaModel:
         pc.add(lambda: ops.linear(flat, self.fc_w, self.fc_b, P["hid"], act_out=2))
         pc.add(lambda: ops.linear(P["hid"], self.out_w, self.out_b, P["r"]))
         P["steps"] = pc.steps
-        self._plans[B] = P
         return P
 
     def forward_nhwc(self, feat_nhwc):

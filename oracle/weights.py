@@ -9,11 +9,14 @@ import torch
 
 
 class _Init:
-    def __init__(self, seed):
+    def __init__(self, seed, shapes_only=False):
         self.g = torch.Generator().manual_seed(seed)
         self.sd = {}
+        self.shapes_only = shapes_only  # record torch.Size instead of drawing (layout checks of the big nets)
 
     def randn(self, *shape):
+        if self.shapes_only:
+            return torch.empty(*shape, device="meta")
         return torch.randn(*shape, generator=self.g)
 
     def conv(self, name, cin, cout, k, gain=1.0):
@@ -158,10 +161,11 @@ def _adm_attn(I, p, c):
 
 
 def adm_unet_state_dict(image_size, model_channels, num_res_blocks, channel_mult, attention_resolutions,
-                        out_channels=6, use_scale_shift_norm=True, resblock_updown=True, seed=0, **_):
+                        out_channels=6, use_scale_shift_norm=True, resblock_updown=True, seed=0, shapes_only=False,
+                        **_):
     """Same keys/shapes as src.unet_adm.UNetModel(...).state_dict() (attention_resolutions are the reference's
     downsample factors `ds`, src/script_util.py:170-172)."""
-    I = _Init(seed)
+    I = _Init(seed, shapes_only)
     mc, emb = model_channels, 4 * model_channels
     I.linear("time_embed.0", mc, emb)
     I.linear("time_embed.2", emb, emb)
@@ -207,6 +211,8 @@ def adm_unet_state_dict(image_size, model_channels, num_res_blocks, channel_mult
             idx += 1
     I.norm("out.0", ch)
     I.conv("out.2", ch, out_channels, 3, gain=0.5)
+    if shapes_only:
+        return {k: v.shape for k, v in I.sd.items()}
     return I.sd
 
 
@@ -252,4 +258,96 @@ ADM_CONFIGS = {
                     attention_resolutions=(1, 2), num_head_channels=-1, num_heads=2, out_channels=3,
                     use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=True,
                     sigma=dict(dim=16, channels=256, n_blocks=2)),
+}
+
+
+# ------------------------------------------------------------------------------------------ EDM (src/edm_networks.py)
+def _edm_block(I, p, cin, cout, emb_ch=None, attention=False, up=False, down=False):
+    I.norm(p + "norm0", cin)
+    I.conv(p + "conv0", cin, cout, 3)
+    if up or down:
+        I.sd[p + "conv0.resample_filter"] = torch.full((1, 1, 2, 2), 0.25)
+    if emb_ch is not None:
+        I.linear(p + "affine", emb_ch, cout, gain=0.5)
+    I.norm(p + "norm1", cout)
+    I.conv(p + "conv1", cout, cout, 3, gain=0.5)  # init_weight 1e-5 in the reference: re-drawn
+    if cin != cout or up or down:
+        I.conv(p + "skip", cin, cout, 1)
+        if up or down:
+            I.sd[p + "skip.resample_filter"] = torch.full((1, 1, 2, 2), 0.25)
+    if attention:
+        I.norm(p + "norm2", cout)
+        I.conv(p + "qkv", cout, 3 * cout, 1)
+        I.conv(p + "proj", cout, cout, 1, gain=0.5)
+
+
+def edm_unet_state_dict(img_resolution, in_channels, out_channels, model_channels, channel_mult, num_blocks,
+                        attn_resolutions, channel_mult_emb=4, seed=0, **_):
+    """Same keys/shapes as src.edm_networks.SongUNet(...) (second definition, DDPM++ configuration)."""
+    I = _Init(seed)
+    emb = model_channels * channel_mult_emb
+    I.linear("map_layer0", model_channels, emb)
+    I.linear("map_layer1", emb, emb)
+    cout = in_channels
+    skips = []
+    for level, mult in enumerate(channel_mult):
+        res = img_resolution >> level
+        if level == 0:
+            cin, cout = cout, model_channels
+            I.conv("enc.%dx%d_conv" % (res, res), cin, cout, 3)
+        else:
+            _edm_block(I, "enc.%dx%d_down." % (res, res), cout, cout, emb, down=True)
+        skips.append(cout)
+        for idx in range(num_blocks):
+            cin, cout = cout, model_channels * mult
+            _edm_block(I, "enc.%dx%d_block%d." % (res, res, idx), cin, cout, emb, attention=res in attn_resolutions)
+            skips.append(cout)
+    L = len(channel_mult)
+    for level, mult in reversed(list(enumerate(channel_mult))):
+        res = img_resolution >> level
+        if level == L - 1:
+            _edm_block(I, "dec.%dx%d_in0." % (res, res), cout, cout, emb, attention=True)
+            _edm_block(I, "dec.%dx%d_in1." % (res, res), cout, cout, emb)
+        else:
+            _edm_block(I, "dec.%dx%d_up." % (res, res), cout, cout, emb, up=True)
+        for idx in range(num_blocks + 1):
+            cin, cout = cout + skips.pop(), model_channels * mult
+            _edm_block(I, "dec.%dx%d_block%d." % (res, res, idx), cin, cout, emb,
+                       attention=(idx == num_blocks and res in attn_resolutions))
+        if level == 0:
+            I.norm("dec.%dx%d_aux_norm" % (res, res), cout)
+            I.conv("dec.%dx%d_aux_conv" % (res, res), cout, out_channels, 3, gain=0.5)
+    return I.sd
+
+
+def edm_sigma_state_dict(dim, channels, n_blocks, seed=1, fc_dim=128):
+    """Same keys/shapes as src.edm_networks.SigmaModel(dim, channels, n_blocks).state_dict()."""
+    I = _Init(seed)
+    idx, d = 0, dim
+    for i in range(n_blocks):
+        if d % 2 != 0:
+            d += 1
+        idx += 1
+        _edm_block(I, "down_layer.%d." % idx, channels, channels, None, attention=i % 2 == 0)
+        idx += 1
+        I.conv("down_layer.%d.conv" % idx, channels, channels, 3)
+        idx += 1
+        d //= 2
+    I.linear("fc_layer.1", channels * d * d, fc_dim)
+    I.sd["fc_layer.2.weight"] = 1.0 + 0.1 * I.randn(fc_dim)
+    I.sd["fc_layer.2.bias"] = 0.05 * I.randn(fc_dim)
+    I.sd["fc_layer.2.running_mean"] = 0.1 * I.randn(fc_dim)
+    I.sd["fc_layer.2.running_var"] = 0.5 + torch.rand(fc_dim, generator=I.g)
+    I.sd["fc_layer.2.num_batches_tracked"] = torch.tensor(0)
+    I.linear("final_mlp", fc_dim, 1, gain=0.3)
+    return I.sd
+
+
+EDM_CONFIGS = {
+    # c3: EDM ffhq-64 DDPM++ (SURVEY §8a N3)
+    "edm64": dict(img_resolution=64, in_channels=3, out_channels=3, model_channels=128, channel_mult=(1, 2, 2, 2),
+                  num_blocks=4, attn_resolutions=(16,), sigma=dict(dim=8, channels=256, n_blocks=2)),
+    # same topology, two levels, one block per level, for unit tests
+    "edm_tiny": dict(img_resolution=16, in_channels=3, out_channels=3, model_channels=128, channel_mult=(1, 2),
+                     num_blocks=1, attn_resolutions=(8,), sigma=dict(dim=8, channels=256, n_blocks=2)),
 }

@@ -121,10 +121,50 @@ def main():
         proj = x0 - op.A_pinv(op.A(x0.reshape(Bo, -1)) - y).reshape(x0.shape)
         gold[name] = dict(A=y, At=op.At(y.clone()), A_pinv=op.A_pinv(y.clone()), project=proj)
     torch.save(gold, os.path.join(HERE, "operators_r32.pt"))
+    adm()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def adm_reference_modules(name):
+    """The reference's ADM UNet + sigma-model for oracle/weights.ADM_CONFIGS[name], loaded with the seeded weights."""
+    import importlib
+    refimport.load()
+    UA = importlib.import_module("src.unet_adm")
+    cfg = dict(weights.ADM_CONFIGS[name])
+    sg = cfg.pop("sigma")
+    sd = weights.adm_unet_state_dict(**cfg, seed=3)
+    ssd = weights.adm_sigma_state_dict(**sg, seed=4)
+    keys = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
+            "num_heads", "num_head_channels", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order")
+    net = UA.UNetModel(in_channels=3, **{k: cfg[k] for k in keys}).eval()
+    snet = UA.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"], num_heads=cfg["num_heads"],
+                         num_head_channels=cfg["num_head_channels"],
+                         use_new_attention_order=cfg["use_new_attention_order"]).eval()
+    net.load_state_dict(sd)
+    snet.load_state_dict(ssd)
+    return cfg, sg, sd, ssd, net, snet
+
+
+def adm():
+    """ADM UNet / sigma-model outputs of the unmodified reference (src/unet_adm.py) -> nets_adm.pt"""
+    torch.set_num_threads(4)
+    gold = {}
+    for name in ("adm_tiny", "adm_alt"):
+        cfg, sg, sd, ssd, net, snet = adm_reference_modules(name)
+        g = torch.Generator().manual_seed(12)
+        x = torch.randn(2, 3, cfg["image_size"], cfg["image_size"], generator=g)
+        t = torch.tensor([731.0, 44.0])
+        with torch.no_grad():
+            out, feat = net(x, t), net.encode(x, t)
+            r = snet(feat)
+        gold[name] = dict(x=x, t=t, out=out, feat=feat, r=r)
+    torch.save(gold, os.path.join(HERE, "nets_adm.pt"))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1:
+        globals()[sys.argv[1]]()
+    else:
+        main()

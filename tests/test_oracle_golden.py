@@ -101,3 +101,19 @@ def test_operator_identities():
         p = op.project(x0, y)
         assert (op.A(p.reshape(B, -1)) - y).abs().max() < tol * 20
         assert (op.project(p, y) - p).abs().max() < 5e-4
+
+
+@pytest.mark.parametrize("name", ["adm_tiny", "adm_alt"])
+def test_adm_networks(golden_dir, name):
+    from oracle import adm_net
+    cfg = dict(weights.ADM_CONFIGS[name])
+    sg = cfg.pop("sigma")
+    sd = weights.adm_unet_state_dict(**cfg, seed=3)
+    ssd = weights.adm_sigma_state_dict(**sg, seed=4)
+    g = load(golden_dir, "nets_adm.pt")[name]
+    with torch.no_grad():
+        out, feat = adm_net.unet_forward(sd, g["x"], g["t"], cfg, return_feat=True)
+        enc = adm_net.unet_encode(sd, g["x"], g["t"], cfg)
+        r = adm_net.sigma_forward(ssd, feat, cfg)
+    assert torch.equal(out, g["out"]) and torch.equal(feat, g["feat"]) and torch.equal(enc, g["feat"])
+    assert torch.equal(r, g["r"])

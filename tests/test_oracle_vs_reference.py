@@ -123,3 +123,39 @@ def test_operators(R):
         assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
         pr = x0 - a.A_pinv(a.A(x0.reshape(B, -1)) - y).reshape(x0.shape)
         assert torch.equal(pr, b.project(x0, y))
+
+
+@pytest.mark.parametrize("name", ["adm_tiny", "adm_alt"])
+def test_adm_networks(R, name):
+    """oracle/adm_net.py == src/unet_adm.py (UNetModel forward/encode, SigmaModel), bit for bit."""
+    from oracle import adm_net
+    sys_path_golden = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", __import__("os").path.join(sys_path_golden, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    cfg, sg, sd, ssd, net, snet = mg.adm_reference_modules(name)
+    for mine, ref in ((sd, net.state_dict()), (ssd, snet.state_dict())):
+        assert set(mine) == set(ref)
+        assert all(mine[k].shape == ref[k].shape for k in mine)
+    x = torch.randn(2, 3, cfg["image_size"], cfg["image_size"])
+    t = torch.tensor([640.0, 12.0])
+    with torch.no_grad():
+        assert torch.equal(net(x, t), adm_net.unet_forward(sd, x, t, cfg))
+        f = net.encode(x, t)
+        assert torch.equal(f, adm_net.unet_encode(sd, x, t, cfg))
+        assert torch.equal(snet(f), adm_net.sigma_forward(ssd, f, cfg))
+
+
+def test_adm256_layout(R):
+    """Key names / shapes of the c4/c5 architecture (no forward: 553 M parameters)."""
+    import importlib
+    UA = importlib.import_module("src.unet_adm")
+    cfg = dict(weights.ADM_CONFIGS["adm256"])
+    cfg.pop("sigma")
+    keys = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
+            "num_heads", "num_head_channels", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order")
+    with torch.device("meta"):
+        ref = UA.UNetModel(in_channels=3, **{k: cfg[k] for k in keys}).state_dict()
+    shapes = weights.adm_unet_state_dict(**cfg, seed=0, shapes_only=True)
+    assert set(shapes) == set(ref) and all(tuple(shapes[k]) == tuple(ref[k].shape) for k in shapes)
