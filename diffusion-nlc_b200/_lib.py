@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libnlc_b200.so")
 
 NLC_F32 = 0
 NLC_BF16 = 1
+EDM_PARTS = 16
 MAX_SRC = 3
 MAX_SEG = 24
 
@@ -78,6 +79,10 @@ _SIGNATURES = {
     "nlc_normalize_rows": (_I, [_P, _P, _I, _I, _P]),
     "nlc_pred_xstart": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "nlc_pred_xprev": (_I, [_P, _I, C.c_double, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "nlc_edm_prepare": (_I, [_P, _P, _I, _I, _P, _P, _P]),
+    "nlc_edm_eps": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "nlc_edm_mix": (_I, [_P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I, _I, _P, _P, _P]),
+    "nlc_edm_axpy": (_I, [_P, _P, _P, _P, C.c_double, _P, _P, _I, _I, _P, _P]),
     "nlc_op_create": (_I, [_P, C.POINTER(OpDesc), C.POINTER(_P)]),
     "nlc_op_destroy": (None, [_P]),
     "nlc_op_ydim": (_I64, [_P]),

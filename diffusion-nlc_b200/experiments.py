@@ -246,3 +246,219 @@ class ImageExperiment(ExperimentDiffusion):
         super().__init__(model=model, scheduler=scheduler, batch_size=batch_size, data_shape=data_shape,
                          save_folder=save_folder, seed=seed, device=device, dist_train=dist_train,
                          time_shift=time_shift)
+
+
+class StackedRandomGenerator:
+    """src/experiments.py:71-85: one torch.Generator per sample, seeded by the sample's global index, so a batch
+    (or a shard of it) draws the same latents wherever it runs."""
+
+    def __init__(self, device, seeds):
+        self.generators = [torch.Generator(device).manual_seed(int(seed) % (1 << 32)) for seed in seeds]
+
+    def randn(self, size, **kwargs):
+        assert size[0] == len(self.generators)
+        return torch.stack([torch.randn(size[1:], generator=gen, **kwargs) for gen in self.generators])
+
+    def randn_like(self, input):
+        return self.randn(input.shape, dtype=input.dtype, layout=input.layout, device=input.device)
+
+
+class _EdmWork:
+    def __init__(self, B, shape, device):
+        f32 = lambda *s: torch.empty(*s, device=device, dtype=torch.float32)
+        f64 = lambda *s: torch.empty(*s, device=device, dtype=torch.float64)
+        from ._lib import EDM_PARTS
+        self.x32 = f32(B, *shape)
+        self.eps_raw, self.eps, self.eps_next, self.denoised = (f64(B, *shape) for _ in range(4))
+        self.e1, self.ne = f64(B, *shape), f64(B, *shape)
+        self.xa, self.xb, self.xh = f64(B, *shape), f64(B, *shape), f64(B, *shape)
+        self.parts = f64(B, EDM_PARTS)
+        self.parts3 = f64(B, EDM_PARTS, 3)
+
+
+def _is_single(t):
+    """`len(t.unsqueeze(-1)) == 1` of the reference (src/experiments.py:812-832)."""
+    return t.dim() == 0 or t.shape[0] == 1
+
+
+class EDMImageExperiment(ImageExperiment):
+    """src/experiments.py:756-961 (sampling methods): EDM preconditioning, NLC with the EDM sigma-model, Heun sampler.
+
+    The sample stays float64 on the device; every O(B*d) operation is a libnlc_b200 kernel (nlc_edm_*).  The
+    per-sample noise levels ([B] or scalar tensors) follow the reference's expressions literally, which also
+    reproduces its float32 / float64 type promotion (a 0-d float64 sigma times a float32 [B,1,1,1] correction is
+    float32, src/experiments.py:824)."""
+
+    def __init__(self, model, scheduler, batch_size=64, data_shape=(3, 32, 32), seed=0, device="cuda:0",
+                 save_folder="./", dist_train=False, time_shift=0, sigma_min=0.002, sigma_max=80, rho=7, S_churn=0,
+                 S_min=0, S_max=float("inf"), S_noise=1, sigma_data=0.5, P_mean=-1.2, P_std=1.2, num_timesteps=18):
+        super().__init__(model=model, scheduler=scheduler, batch_size=batch_size, data_shape=data_shape, seed=seed,
+                         device=device, save_folder=save_folder, dist_train=dist_train, time_shift=time_shift)
+        self.sigma_min, self.sigma_max, self.rho = sigma_min, sigma_max, rho
+        self.S_churn, self.S_min, self.S_max, self.S_noise = S_churn, S_min, S_max, S_noise
+        self.sigma_data, self.P_mean, self.P_std, self.num_timesteps = sigma_data, P_mean, P_std, num_timesteps
+        self._ework = {}
+
+    def _ew(self, B):
+        w = self._ework.get(B)
+        if w is None:
+            w = _EdmWork(B, self.data_shape, self.device)
+            self._ework[B] = w
+        return w
+
+    def _precond(self, sigma, B):
+        """c_skip, c_out, c_in, c_noise as [B] float32 (src/experiments.py:794-797)."""
+        sigma = sigma.to(self.device, torch.float32).reshape(-1)
+        sd = self.sigma_data
+        c_skip = sd ** 2 / (sigma ** 2 + sd ** 2)
+        c_out = sigma * sd / (sigma ** 2 + sd ** 2).sqrt()
+        c_in = 1 / (sd ** 2 + sigma ** 2).sqrt()
+        c_noise = sigma.log() / 4
+        return [c.expand(B).contiguous() for c in (c_skip, c_out, c_in, c_noise)]
+
+    @torch.no_grad()
+    def get_denoise_vector(self, xt, sigma_t, sigma_prev, style="base", norm_eps=False, refine_prior_sigma=False,
+                           _eps_out=None):
+        """(eps, denoised, sigma_t, sigma_prev) as in src/experiments.py:805-843; xt float64 [B,C,H,W]."""
+        B = xt.shape[0]
+        w = self._ew(B)
+        dev = self.device
+        sigma_t, sigma_prev = torch.as_tensor(sigma_t), torch.as_tensor(sigma_prev)
+        sigma_t_orig = sigma_t
+        xt = xt.contiguous()
+        ops.edm_prepare(xt, w.x32, w.parts if refine_prior_sigma else None)
+        if refine_prior_sigma:
+            norm_x = w.parts.sum(1).sqrt().view(B, 1, 1, 1) / math.sqrt(self.dim)
+            min_dist = torch.clamp(norm_x - self.norm_max, min=0)
+            max_dist = norm_x + self.norm_min
+            raw_sigma = torch.ones_like(norm_x) * sigma_t if _is_single(sigma_t) else sigma_t
+            sigma_t = torch.clamp(raw_sigma, min=min_dist, max=max_dist)
+            if _is_single(sigma_prev):
+                sigma_prev = torch.ones_like(norm_x) * sigma_prev
+        if "pred" in style:
+            _, _, c_in, c_noise = self._precond(sigma_t, B)
+            feat = self.model.encode_scaled(w.x32, c_noise, c_in)
+            r = self.sigma_model.forward_nhwc(feat).view(B, 1, 1, 1)
+            dist_hat = sigma_t * (1 + r)
+            dist_prev_hat = dist_hat * (sigma_prev / sigma_t)
+            sigma_t = dist_hat
+            if style == "pred":
+                sigma_prev = dist_prev_hat
+        # (dimensioned host tensors cannot meet device tensors; moving them does not change the dtype rules)
+        if _is_single(sigma_t_orig):
+            sigma_t_orig = sigma_t_orig.reshape(-1, 1, 1, 1).to(dev)
+        if _is_single(sigma_t):
+            sigma_t = sigma_t.reshape(-1, 1, 1, 1).to(dev)
+        if _is_single(sigma_prev):
+            sigma_prev = sigma_prev.reshape(-1, 1, 1, 1).to(dev)
+        used = sigma_t_orig if style == "pred_sigma" else sigma_t
+        c_skip, c_out, c_in, c_noise = self._precond(used, B)
+        F_x = self.model.forward_scaled(w.x32, c_noise, c_in)
+        div = used.to(dev, torch.float64).reshape(-1).expand(B).contiguous()
+        eps = _eps_out if _eps_out is not None else w.eps
+        if norm_eps:
+            ops.edm_eps(xt, w.x32, F_x, c_skip, c_out, div, w.eps_raw, w.denoised, w.parts)
+            den = torch.clamp(w.parts.sum(1).sqrt(), min=1e-12)
+            ops.edm_mix(w.eps_raw, den, None, None, None, None, 1.0, 0.0, eps)
+        else:
+            ops.edm_eps(xt, w.x32, F_x, c_skip, c_out, div, eps, w.denoised, None)
+        return eps, w.denoised, sigma_t, sigma_prev
+
+    def _vec64(self, v, B):
+        return torch.as_tensor(v).to(self.device, torch.float64).reshape(-1).expand(B).contiguous()
+
+    @torch.no_grad()
+    def edm_sampler(self, shape, gen=None, style="base,base", norm_eps="000", refine_prior_sigma=False, num_steps=None,
+                    sigma_scheduler="EDM", eps_ratio=0.5, eps_scale=1.0, use_second_order=True, latents=None,
+                    step_hook=None):
+        """src/experiments.py:847-918.  `latents` (optional) replaces gen.randn (parity tests, sharded runs);
+        `step_hook(i, dict)` observes per-step device tensors."""
+        norm_eps, norm_eps_combine = bool(int(norm_eps[0])), bool(int(norm_eps[1]))
+        style_t, style_next = style.split(",")
+        num_steps = self.num_timesteps if num_steps is None else num_steps
+        if latents is None:
+            latents = gen.randn(shape, device=self.device)
+        B = latents.shape[0]
+        w = self._ew(B)
+        # noise levels stay on the host (0-d float64 tensors): no device->host read in the loop
+        step_indices = torch.arange(num_steps, dtype=torch.float64)
+        if sigma_scheduler == "EDM":
+            sigma_steps = (self.sigma_max ** (1 / self.rho) + step_indices / (num_steps - 1) * (
+                self.sigma_min ** (1 / self.rho) - self.sigma_max ** (1 / self.rho))) ** self.rho
+        elif sigma_scheduler == "Linear":
+            sigma_steps = torch.tensor(np.exp(np.linspace(np.log(self.sigma_max), np.log(self.sigma_min), num_steps)))
+        else:
+            raise NotImplementedError
+        sigma_steps = torch.cat([torch.as_tensor(sigma_steps), torch.zeros_like(sigma_steps[:1])])
+        w.xa.copy_(latents.to(torch.float64) * sigma_steps[0])
+        x_next, x_spare = w.xa, w.xb
+        for i, (sigma_cur, sigma_next) in enumerate(zip(sigma_steps[:-1], sigma_steps[1:])):
+            x_cur = x_next
+            sigma_next0 = sigma_next
+            gamma = min(self.S_churn / num_steps, np.sqrt(2) - 1) if self.S_min <= sigma_cur <= self.S_max else 0
+            sigma_hat = torch.as_tensor(sigma_cur + gamma * sigma_cur)
+            sigma_hat0 = sigma_hat
+            if gamma > 0:
+                z = torch.randn_like(x_cur)
+                ops.edm_axpy(x_cur, z, None, 0.0, None,
+                             self._vec64((sigma_hat ** 2 - sigma_cur ** 2).sqrt() * self.S_noise, B), w.xh)
+                x_hat = w.xh
+            else:
+                x_hat = x_cur
+            eps, denoised, sigma_hat, sigma_next = self.get_denoise_vector(
+                x_hat, sigma_hat, sigma_next, style=style_t, norm_eps=norm_eps, refine_prior_sigma=refine_prior_sigma)
+            # eps <- eps * (sigma_hat / sigma_hat0)
+            ops.edm_mix(eps, None, self._vec64(sigma_hat / sigma_hat0, B), None, None, None, 1.0, 0.0, w.e1)
+            if "pred_partial" in style_t:
+                sigma_next = sigma_next0
+            if style_t == "pred_partial":
+                coef = sigma_next - sigma_hat0
+            else:
+                coef = sigma_next - sigma_hat
+            ops.edm_axpy(x_hat, w.e1, None, 0.0, None, self._vec64(coef, B), x_spare)
+            if style_t == "pred_partial3":
+                sigma_hat = sigma_hat0
+            if i < num_steps - 1 and use_second_order:
+                eps_next, denoised, sigma_next, _ = self.get_denoise_vector(
+                    x_spare, sigma_next, sigma_next * 0, style=style_next, norm_eps=norm_eps,
+                    refine_prior_sigma=refine_prior_sigma, _eps_out=w.eps_next)
+                s2 = self._vec64(sigma_next / sigma_next0, B)
+                if "pred_partial" in style_next:
+                    sigma_next = sigma_next0
+                # new_eps = eps_ratio * eps + (1 - eps_ratio) * eps_next * (sigma_next / sigma_next0)
+                ops.edm_mix(w.e1, None, None, eps_next, None, s2, eps_ratio, 1 - eps_ratio, w.ne, w.parts3)
+                den = mul = None
+                if norm_eps_combine:
+                    den = torch.clamp(w.parts3[:, :, 0].sum(1).sqrt(), min=1e-12)
+                if eps_scale is None:
+                    # CosineSimilarity(dim=1, eps=1e-6) between new_eps and eps (scale invariant, so the optional
+                    # normalisation of new_eps does not change it)
+                    s = w.parts3.sum(1)
+                    mul = s[:, 2] / (s[:, 0].sqrt().clamp_min(1e-6) * s[:, 1].sqrt().clamp_min(1e-6))
+                    mul = mul.contiguous()
+                ops.edm_axpy(x_hat, w.ne, den, eps_scale, mul, self._vec64(sigma_next - sigma_hat, B), x_spare)
+            if step_hook is not None:
+                step_hook(i, dict(x_hat=x_hat, x_next=x_spare, sigma_hat=sigma_hat, sigma_next=sigma_next, eps=w.e1))
+            x_next, x_spare = x_spare, x_next
+        return x_next
+
+    @torch.no_grad()
+    def evaluate_edm(self, n_samples, images_dir=None, gen=None, style="base,base", norm_eps="000",
+                     refine_prior_sigma=False, microbatch=-1, sigma_scheduler="EDM", eps_ratio=0.5, eps_scale=1.0,
+                     use_second_order=True, rank=0, world=1):
+        """Sampling part of src/experiments.py:923-961: per-sample seeds arange(n_samples) split into batches
+        (:929-933); batches are dealt round-robin to `world` ranks.  Returns the images in [0,1]
+        (`sample.add(1).div(2).clamp(0,1)`, :946); PNG writing and FID are outside the hot path."""
+        batch_size = microbatch if microbatch > 0 else self.batch_size
+        seeds = np.arange(n_samples)
+        num_batches = (len(seeds) - 1) // batch_size + 1
+        all_batches = torch.as_tensor(seeds).tensor_split(num_batches)
+        out = []
+        for i in range(rank, num_batches, world):
+            g = StackedRandomGenerator(self.device, all_batches[i])
+            shape = (len(all_batches[i]),) + self.data_shape
+            sample = self.edm_sampler(shape=shape, gen=g, style=style, norm_eps=norm_eps,
+                                      refine_prior_sigma=refine_prior_sigma, sigma_scheduler=sigma_scheduler,
+                                      eps_ratio=eps_ratio, eps_scale=eps_scale, use_second_order=use_second_order)
+            out.append(sample.add(1).div(2).clamp(0, 1))
+        return {"samples": torch.cat(out) if out else None}

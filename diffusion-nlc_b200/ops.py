@@ -290,3 +290,35 @@ def pred_xprev(sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_c
         float(min_var_coef), _p(sigma), sigma.numel(), _p(sigma_prev), sigma_prev.numel(), B, d, _p(x_prev),
         _p(nan_flag), _stream()))
     STATS.launches += 1
+
+
+# ---------------------------------------------------------------------------------------------- EDM sampler (fp64 state)
+@_timed("edm_prepare")
+def edm_prepare(x64, x32, sumsq_parts=None):
+    B, d = x64.shape[0], x64[0].numel()
+    _lib.check(_lib.lib().nlc_edm_prepare(_ctx(x64), _p(x64), B, d, _p(x32), _p(sumsq_parts), _stream()))
+    STATS.launches += 1
+
+
+@_timed("edm_eps")
+def edm_eps(x64, x32, F, c_skip, c_out, div, eps, denoised=None, sumsq_parts=None):
+    B, d = x64.shape[0], x64[0].numel()
+    _lib.check(_lib.lib().nlc_edm_eps(_ctx(x64), _p(x64), _p(x32), _p(F), _p(c_skip), _p(c_out), _p(div), B, d, _p(eps),
+                                      _p(denoised), _p(sumsq_parts), _stream()))
+    STATS.launches += 1
+
+
+@_timed("edm_mix")
+def edm_mix(e1, den1, s1, e2, den2, s2, w1, w2, out, sums_parts=None):
+    B, d = e1.shape[0], e1[0].numel()
+    _lib.check(_lib.lib().nlc_edm_mix(_ctx(e1), _p(e1), _p(den1), _p(s1), _p(e2), _p(den2), _p(s2), float(w1), float(w2),
+                                      B, d, _p(out), _p(sums_parts), _stream()))
+    STATS.launches += 1
+
+
+@_timed("edm_axpy")
+def edm_axpy(x_hat, e, den, eps_scale, mul, coef, x_next):
+    B, d = x_hat.shape[0], x_hat[0].numel()
+    _lib.check(_lib.lib().nlc_edm_axpy(_ctx(x_hat), _p(x_hat), _p(e), _p(den), float(eps_scale or 0.0), _p(mul),
+                                       _p(coef), B, d, _p(x_next), _stream()))
+    STATS.launches += 1

@@ -207,6 +207,36 @@ int nlc_pred_xprev(nlc_ctx* ctx, int sched, double eta, const float* x0, const f
                    float* x_prev, int* nan_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * L3 / D2 — EDM Heun sampler (src/experiments.py:777-843, 847-918).  The sample x is float64, the network runs in
+ * float32.  Per-sample reductions come back as NLC_EDM_PARTS partial sums per sample (fixed order).
+ * ---------------------------------------------------------------------------------------------- */
+#define NLC_EDM_PARTS 16
+
+/* x32 = float(x64) (the .to(torch.float32) of encode_edm / pred_edm, :778,:789);
+ * sumsq_parts[b][p] = partial sums of x64^2 (vector_norm of refine_prior_sigma, :808); may be NULL. */
+int nlc_edm_prepare(nlc_ctx* ctx, const double* x64, int B, int d, float* x32, double* sumsq_parts, void* stream);
+
+/* denoised = double(c_skip[b]*x32 + c_out[b]*F) (:801), eps = (x64 - denoised) / div[b] (:836-840);
+ * sumsq_parts = partial sums of eps^2 (normalize, src/utils.py:11-16).  denoised / sumsq_parts may be NULL. */
+int nlc_edm_eps(nlc_ctx* ctx, const double* x64, const float* x32, const float* F, const float* c_skip,
+                const float* c_out, const double* div, int B, int d, double* eps, double* denoised,
+                double* sumsq_parts, void* stream);
+
+/* v_i = [sqrt(d) * e_i / den_i[b]] * s_i[b]   (normalize, then the eps rescale sigma_hat/sigma_hat0, :884,:903)
+ * out = v_1                      when e2 == NULL
+ *     = w1 * v_1 + w2 * v_2      (Heun blend eps_ratio, :907)
+ * sums_parts[b][p] = partial sums of {out^2, v_1^2, out*v_1} (normalize of the blend / cosine-similarity scale,
+ * :908-916).  den_i, s_i, sums_parts may be NULL. */
+int nlc_edm_mix(nlc_ctx* ctx, const double* e1, const double* den1, const double* s1, const double* e2,
+                const double* den2, const double* s2, double w1, double w2, int B, int d, double* out,
+                double* sums_parts, void* stream);
+
+/* x_next = x_hat + coef[b] * post(e), post(e) = [sqrt(d)*e/den[b]] [/ eps_scale when != 0] [* mul[b]]
+ * (the Euler / Heun updates, :886-890,:917). */
+int nlc_edm_axpy(nlc_ctx* ctx, const double* x_hat, const double* e, const double* den, double eps_scale,
+                 const double* mul, const double* coef, int B, int d, double* x_next, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * P0-P6 — DDNM constraint operators (functions/svd_operators.py) and the fused projection
  * x0 <- x0 - A^+(A x0 - y)  (image_sample.py:376-379).  x is NCHW fp32 [B,3,R,R] flattened.
  * ---------------------------------------------------------------------------------------------- */

@@ -122,6 +122,7 @@ def main():
         gold[name] = dict(A=y, At=op.At(y.clone()), A_pinv=op.A_pinv(y.clone()), project=proj)
     torch.save(gold, os.path.join(HERE, "operators_r32.pt"))
     adm()
+    edm()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -161,6 +162,68 @@ def adm():
             r = snet(feat)
         gold[name] = dict(x=x, t=t, out=out, feat=feat, r=r)
     torch.save(gold, os.path.join(HERE, "nets_adm.pt"))
+
+
+EDM_CASES = [("pred_partial,pred", "00", False, 1.0), ("base,base", "00", False, 1.0), ("pred,pred_partial", "11", True, 1.0),
+             ("pred_sigma,pred_partial3", "10", False, None), ("pred_partial,pred", "01", True, 1.004)]
+
+
+def edm_reference_modules(name):
+    import importlib
+    refimport.load()
+    EN = importlib.import_module("src.edm_networks")
+    cfg = dict(weights.EDM_CONFIGS[name])
+    sg = cfg.pop("sigma")
+    sd = weights.edm_unet_state_dict(**cfg, seed=3)
+    ssd = weights.edm_sigma_state_dict(**sg, seed=4)
+    net = EN.SongUNet(**{k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}).eval()
+    snet = EN.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    net.load_state_dict(sd)
+    snet.load_state_dict(ssd)
+    return cfg, sg, sd, ssd, net, snet
+
+
+def edm():
+    """EDM network outputs and the reference's own edm_sampler (4 steps = 7 NFE), with every get_denoise_vector
+    call observed -> nets_edm.pt, edm_sampler_tiny.pt"""
+    R = refimport.load()
+    torch.set_num_threads(4)
+    cfg, sg, sd, ssd, net, snet = edm_reference_modules("edm_tiny")
+    Rr = cfg["img_resolution"]
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 3, Rr, Rr, generator=g)
+    c_noise = torch.tensor([0.91, -1.35])
+    with torch.no_grad():
+        out, feat = net(x, c_noise, None), net.encode(x, c_noise, None)
+        r = snet(feat)
+    torch.save(dict(x=x, c_noise=c_noise, out=out, feat=feat, r=r), os.path.join(HERE, "nets_edm.pt"))
+
+    B = 2
+    gold = {}
+    for style, ne, refine, es in EDM_CASES:
+        exp = R.experiments.EDMImageExperiment(net, None, batch_size=B, data_shape=(3, Rr, Rr), seed=1, device="cpu",
+                                               num_timesteps=4, sigma_min=0.002, sigma_max=80)
+        exp.set_model(net, snet, learn_epsvar=False)
+        exp.set_norm_maxmin(0.0, 30.0)
+        gen = R.experiments.StackedRandomGenerator("cpu", [0, 1])
+        latents = gen.randn((B, 3, Rr, Rr), device="cpu")
+        gen = R.experiments.StackedRandomGenerator("cpu", [0, 1])
+        calls = []
+        orig = exp.get_denoise_vector
+
+        def spy(xt, sigma_t, sigma_prev, _orig=orig, _calls=calls, **k):
+            res = _orig(xt, sigma_t, sigma_prev, **k)
+            f = lambda v: torch.as_tensor(v).reshape(-1).double().clone()
+            _calls.append(dict(xt=xt.clone(), sigma_in=f(sigma_t), sigma_prev_in=f(sigma_prev), style=k["style"],
+                               eps=res[0].clone(), sigma_t=f(res[2]), sigma_prev=f(res[3])))
+            return res
+
+        exp.get_denoise_vector = spy
+        with torch.no_grad():
+            final = exp.edm_sampler((B, 3, Rr, Rr), gen=gen, style=style, norm_eps=ne + "0", refine_prior_sigma=refine,
+                                    eps_scale=es)
+        gold["%s|%s|%d|%s" % (style, ne, int(refine), es)] = dict(latents=latents, final=final, calls=calls)
+    torch.save(gold, os.path.join(HERE, "edm_sampler_tiny.pt"))
 
 
 if __name__ == "__main__":

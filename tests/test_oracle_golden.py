@@ -117,3 +117,36 @@ def test_adm_networks(golden_dir, name):
         r = adm_net.sigma_forward(ssd, feat, cfg)
     assert torch.equal(out, g["out"]) and torch.equal(feat, g["feat"]) and torch.equal(enc, g["feat"])
     assert torch.equal(r, g["r"])
+
+
+def _edm_oracle():
+    from oracle import edm_net, sampler_edm
+    cfg = dict(weights.EDM_CONFIGS["edm_tiny"])
+    sg = cfg.pop("sigma")
+    sd = weights.edm_unet_state_dict(**cfg, seed=3)
+    ssd = weights.edm_sigma_state_dict(**sg, seed=4)
+    d = 3 * cfg["img_resolution"] ** 2
+    o = sampler_edm.EDM(lambda x, c: edm_net.unet_forward(sd, x, c, cfg), lambda x, c: edm_net.unet_encode(sd, x, c, cfg),
+                        lambda f: edm_net.sigma_forward(ssd, f), d, norm_min=0.0, norm_max=30.0 / d ** 0.5)
+    return cfg, sd, ssd, o
+
+
+def test_edm_networks(golden_dir):
+    from oracle import edm_net
+    cfg, sd, ssd, _ = _edm_oracle()
+    g = load(golden_dir, "nets_edm.pt")
+    with torch.no_grad():
+        out, feat = edm_net.unet_forward(sd, g["x"], g["c_noise"], cfg, return_feat=True)
+        r = edm_net.sigma_forward(ssd, feat)
+    assert torch.equal(out, g["out"]) and torch.equal(feat, g["feat"]) and torch.equal(r, g["r"])
+
+
+def test_edm_sampler_every_case(golden_dir):
+    _, _, _, o = _edm_oracle()
+    g = load(golden_dir, "edm_sampler_tiny.pt")
+    for key, case in g.items():
+        style, ne, refine, es = key.split("|")
+        with torch.no_grad():
+            x = o.sample(case["latents"], 4, style=style, norm_eps=ne + "0", refine=bool(int(refine)),
+                         eps_scale=None if es == "None" else float(es))
+        assert torch.equal(x, case["final"]), key

@@ -16,6 +16,17 @@ def R():
     return refimport.load()
 
 
+def _make_golden():
+    """tests/golden/make_golden.py as a module (it holds the builders of the reference modules)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    spec = importlib.util.spec_from_file_location("make_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 @pytest.mark.parametrize("name", ["tiny", "c1"])
 def test_state_dict_layout_and_networks(R, name):
     cfg = weights.CONFIGS[name]
@@ -129,12 +140,7 @@ def test_operators(R):
 def test_adm_networks(R, name):
     """oracle/adm_net.py == src/unet_adm.py (UNetModel forward/encode, SigmaModel), bit for bit."""
     from oracle import adm_net
-    sys_path_golden = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("make_golden", __import__("os").path.join(sys_path_golden, "make_golden.py"))
-    mg = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mg)
-    cfg, sg, sd, ssd, net, snet = mg.adm_reference_modules(name)
+    cfg, sg, sd, ssd, net, snet = _make_golden().adm_reference_modules(name)
     for mine, ref in ((sd, net.state_dict()), (ssd, snet.state_dict())):
         assert set(mine) == set(ref)
         assert all(mine[k].shape == ref[k].shape for k in mine)
@@ -159,3 +165,53 @@ def test_adm256_layout(R):
         ref = UA.UNetModel(in_channels=3, **{k: cfg[k] for k in keys}).state_dict()
     shapes = weights.adm_unet_state_dict(**cfg, seed=0, shapes_only=True)
     assert set(shapes) == set(ref) and all(tuple(shapes[k]) == tuple(ref[k].shape) for k in shapes)
+
+
+def test_edm_networks(R):
+    """oracle/edm_net.py == src/edm_networks.py (SongUNet forward/encode, SigmaModel), bit for bit."""
+    from oracle import edm_net
+    cfg, sg, sd, ssd, net, snet = _make_golden().edm_reference_modules("edm_tiny")
+    for mine, ref in ((sd, net.state_dict()), (ssd, snet.state_dict())):
+        assert set(mine) == set(ref)
+        assert all(mine[k].shape == ref[k].shape for k in mine)
+    x = torch.randn(2, 3, cfg["img_resolution"], cfg["img_resolution"])
+    c = torch.tensor([0.9, -1.2])
+    with torch.no_grad():
+        assert torch.equal(net(x, c, None), edm_net.unet_forward(sd, x, c, cfg))
+        f = net.encode(x, c, None)
+        assert torch.equal(f, edm_net.unet_encode(sd, x, c, cfg))
+        assert torch.equal(snet(f), edm_net.sigma_forward(ssd, f))
+
+
+def test_edm64_layout(R):
+    import importlib
+    EN = importlib.import_module("src.edm_networks")
+    cfg = dict(weights.EDM_CONFIGS["edm64"])
+    sg = cfg.pop("sigma")
+    ref = EN.SongUNet(**{k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}).state_dict()
+    sd = weights.edm_unet_state_dict(**cfg, seed=0)
+    assert set(sd) == set(ref) and all(sd[k].shape == ref[k].shape for k in sd)
+    sref = EN.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).state_dict()
+    ssd = weights.edm_sigma_state_dict(**sg, seed=0)
+    assert set(ssd) == set(sref) and all(ssd[k].shape == sref[k].shape for k in ssd)
+
+
+@pytest.mark.parametrize("style,ne,refine,es", [("pred_partial,pred", "00", False, 1.0), ("pred,pred_partial", "11", True, 1.0),
+                                                ("pred_sigma,pred_partial3", "10", False, None)])
+def test_edm_sampler(R, style, ne, refine, es):
+    """oracle/sampler_edm.py == EDMImageExperiment.edm_sampler (float64 result, torch.equal)."""
+    from oracle import edm_net, sampler_edm
+    cfg, sg, sd, ssd, net, snet = _make_golden().edm_reference_modules("edm_tiny")
+    B, Rr = 2, cfg["img_resolution"]
+    exp = R.experiments.EDMImageExperiment(net, None, batch_size=B, data_shape=(3, Rr, Rr), seed=1, device="cpu",
+                                           num_timesteps=3, sigma_min=0.002, sigma_max=80)
+    exp.set_model(net, snet, learn_epsvar=False)
+    exp.set_norm_maxmin(0.0, 30.0)
+    o = sampler_edm.EDM(lambda x, c: edm_net.unet_forward(sd, x, c, cfg), lambda x, c: edm_net.unet_encode(sd, x, c, cfg),
+                        lambda f: edm_net.sigma_forward(ssd, f), 3 * Rr * Rr, norm_min=exp.norm_min, norm_max=exp.norm_max)
+    with torch.no_grad():
+        ref = exp.edm_sampler((B, 3, Rr, Rr), gen=R.experiments.StackedRandomGenerator("cpu", [5, 6]), style=style,
+                              norm_eps=ne + "0", refine_prior_sigma=refine, eps_scale=es)
+        lat = R.experiments.StackedRandomGenerator("cpu", [5, 6]).randn((B, 3, Rr, Rr), device="cpu")
+        mine = o.sample(lat, 3, style=style, norm_eps=ne + "0", refine=refine, eps_scale=es)
+    assert ref.dtype == torch.float64 and torch.equal(ref, mine)
