@@ -74,8 +74,11 @@ _SIGNATURES = {
     "nlc_linear": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P]),
     "nlc_timestep_embedding": (_I, [_P, _P, _I, _P, _I, _I, _P, _I, _P]),
     "nlc_row_norm": (_I, [_P, _P, _I, _I, _P, _P]),
-    "nlc_refine_sigma": (_I, [_P, _P, _I, _I, _P, _I, _F, _F, _I, _F, _P, _I, _I, _P, _P, _P, _P]),
-    "nlc_sigma_correct": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _P, _P, _P, _P]),
+    "nlc_refine_sigma": (_I, [_P, _P, _I, _I, _P, _I, _F, _F, _I, _F, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "nlc_sigma_correct": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "nlc_dynamic_threshold": (_I, [_P, _P, _I, _I, C.c_double, _F, _P, _P]),
+    "nlc_sigma_estimate": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _I, _P, _I, C.POINTER(C.c_float * 4), _P, _P, _I, _P,
+                                _P, _P]),
     "nlc_normalize_rows": (_I, [_P, _P, _I, _I, _P]),
     "nlc_pred_xstart": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "nlc_pred_xprev": (_I, [_P, _I, C.c_double, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P, _P]),

@@ -73,24 +73,34 @@ __device__ __forceinline__ int lower_bound(const float* __restrict__ table, int 
     return lo;
 }
 
+// get_t_from_sigma: discrete = searchsorted (src/schedulers.py:185-190); continuous (slopes != NULL) = Interp1d of
+// (sigma table -> train timestep) (src/schedulers.py:210-220, src/torchinterp1d.py:96-148): the interval index is
+// clamp(searchsorted - 1, 0, n-2) and t = y[ind] + slope[ind] * (sigma - x[ind]) with y = arange(n).
+__device__ __forceinline__ float time_from_sigma(const float* __restrict__ table, const float* __restrict__ slopes,
+                                                 int n, float s) {
+    const int lb = lower_bound(table, n, s);
+    if (!slopes) return static_cast<float>(lb);
+    const int ind = min(max(lb - 1, 0), n - 2);
+    return ADD(static_cast<float>(ind), MUL(slopes[ind], SUB(s, table[ind])));
+}
+
 // single CTA over the B-vector (batch-global min for the time shift, src/experiments.py:411-412)
 __global__ void __launch_bounds__(1024)
     refine_sigma_kernel(const float* __restrict__ norms, int B, float sqrt_d, const float* __restrict__ sigma_in,
                         int n_sigma_in, float norm_min, float norm_max, int refine, float t_fixed,
-                        const float* __restrict__ table, int n_table, int time_shift, float* __restrict__ sigma_out,
-                        float* __restrict__ t_out, float* __restrict__ in_scale_out) {
-    __shared__ int s_min;
-    if (threadIdx.x == 0) s_min = 0x7fffffff;
+                        const float* __restrict__ table, const float* __restrict__ slopes, int n_table,
+                        int time_shift, float* __restrict__ sigma_out, float* __restrict__ t_out,
+                        float* __restrict__ in_scale_out) {
+    __shared__ int s_pos;  // 1 while every t so far is > 0  (t.min() > 0)
+    if (threadIdx.x == 0) s_pos = 1;
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         float s = sigma_in[n_sigma_in == 1 ? 0 : b];
-        int t = 0;
         if (refine) {
             const float nx = DIV(norms[b], sqrt_d);  // vector_norm(xt) / math.sqrt(dim)
             const float lo = fmaxf(SUB(nx, norm_max), 0.f), hi = ADD(nx, norm_min);
             s = fminf(fmaxf(s, lo), hi);
-            t = lower_bound(table, n_table, s);
-            atomicMin(&s_min, t);
+            if (!(time_from_sigma(table, slopes, n_table, s) > 0.f)) atomicAnd(&s_pos, 0);
         }
         sigma_out[b] = s;
         if (in_scale_out) in_scale_out[b] = sqrtf(DIV(1.0f, ADD(MUL(s, s), 1.0f)));
@@ -98,17 +108,18 @@ __global__ void __launch_bounds__(1024)
     }
     __syncthreads();
     if (refine) {
-        const int shift = s_min > 0 ? time_shift : 0;
+        const float shift = s_pos ? static_cast<float>(time_shift) : 0.f;
         for (int b = threadIdx.x; b < B; b += blockDim.x) {
-            const int t = lower_bound(table, n_table, sigma_out[b]) - shift;
-            t_out[b] = fminf(fmaxf(static_cast<float>(t), 0.f), 1000.f);
+            const float t = SUB(time_from_sigma(table, slopes, n_table, sigma_out[b]), shift);
+            t_out[b] = fminf(fmaxf(t, 0.f), 1000.f);
         }
     }
 }
 
 __global__ void sigma_correct_kernel(const float* __restrict__ r, const float* __restrict__ sigma,
                                      const float* __restrict__ sigma_prev, int n_prev, int B, int update_prev,
-                                     const float* __restrict__ table, int n_table, float* __restrict__ sigma_hat,
+                                     const float* __restrict__ table, const float* __restrict__ slopes, int n_table,
+                                     float* __restrict__ sigma_hat,
                                      float* __restrict__ sigma_prev_hat, float* __restrict__ t_hat,
                                      float* __restrict__ in_scale_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,10 +128,10 @@ __global__ void sigma_correct_kernel(const float* __restrict__ r, const float* _
     const float sp = sigma_prev[n_prev == 1 ? 0 : b];
     const float dist = MUL(s, ADD(1.0f, r[b]));
     const float dist_prev = MUL(dist, DIV(sp, s));
-    const int t = lower_bound(table, n_table, dist);
+    const float t = time_from_sigma(table, slopes, n_table, dist);
     sigma_hat[b] = dist;
     sigma_prev_hat[b] = update_prev ? dist_prev : sp;
-    t_hat[b] = fminf(fmaxf(static_cast<float>(t), 0.f), 1000.f);
+    t_hat[b] = fminf(fmaxf(t, 0.f), 1000.f);
     if (in_scale_out) in_scale_out[b] = sqrtf(DIV(1.0f, ADD(MUL(dist, dist), 1.0f)));
 }
 
@@ -272,6 +283,121 @@ static int row_grid(int sm_count, int B, int d) {
     return chunks;
 }
 
+
+// ---------------------------------------------------------------- dynamic thresholding (src/experiments.py:190-204)
+// s_b = clamp(quantile(|x_b|, q), 1, max_value);  x_b <- clamp(x_b, -s_b, s_b) / s_b.
+// torch.quantile (linear interpolation) = lerp(sorted[floor(rank)], sorted[ceil(rank)], frac(rank)) with
+// rank = q*(n-1) evaluated in fp32.  The two order statistics are found exactly by a 3-pass radix select over the
+// bit patterns of |x| (non-negative floats order like unsigned integers); one CTA per sample, the sample stays in L2.
+constexpr int kSelBins = 2048;
+constexpr int kSelCopies = 8;
+
+__device__ __forceinline__ uint32_t abs_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+
+__global__ void __launch_bounds__(1024)
+    dynamic_threshold_kernel(float* __restrict__ x, int d, int rank_lo, int rank_hi, float weight, float max_value,
+                             float* __restrict__ s_out) {
+    extern __shared__ uint32_t hist[];  // [kSelCopies][kSelBins]
+    __shared__ uint32_t sh_prefix, sh_k, sh_count_eq, sh_min_above;
+    float* row = x + static_cast<size_t>(blockIdx.x) * d;
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const int n4 = d >> 2;
+    const int copy = (threadIdx.x >> 5) & (kSelCopies - 1);
+    uint32_t prefix = 0, mask = 0, k = static_cast<uint32_t>(rank_lo);
+    const int shifts[3] = {21, 10, 0};
+    const uint32_t widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; ++pass) {
+        const int shift = shifts[pass];
+        const uint32_t bmask = (1u << widths[pass]) - 1u;
+        for (int i = threadIdx.x; i < kSelCopies * kSelBins; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = __ldg(r4 + i);
+            const uint32_t b[4] = {abs_bits(v.x), abs_bits(v.y), abs_bits(v.z), abs_bits(v.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((b[j] & mask) == prefix) atomicAdd(&hist[copy * kSelBins + ((b[j] >> shift) & bmask)], 1u);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kSelBins; i += blockDim.x) {
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < kSelCopies; ++j) c += hist[j * kSelBins + i];
+            hist[i] = c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t cum = 0, bin = 0;
+            for (; bin < bmask; ++bin) {
+                if (cum + hist[bin] > k) break;
+                cum += hist[bin];
+            }
+            sh_prefix = prefix | (bin << shift);
+            sh_k = k - cum;
+            sh_count_eq = hist[bin];
+        }
+        __syncthreads();
+        prefix = sh_prefix, k = sh_k;
+        mask |= bmask << shift;
+        __syncthreads();
+    }
+    // prefix = bits of sorted[rank_lo]; k = its index among the sh_count_eq equal values
+    const float v_lo = __uint_as_float(prefix);
+    float v_hi = v_lo;
+    if (rank_hi > rank_lo && k + 1 >= sh_count_eq) {  // the next order statistic is the smallest value above v_lo
+        if (threadIdx.x == 0) sh_min_above = 0x7f800000u;
+        __syncthreads();
+        uint32_t m = 0x7f800000u;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = __ldg(r4 + i);
+            const uint32_t b[4] = {abs_bits(v.x), abs_bits(v.y), abs_bits(v.z), abs_bits(v.w)};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (b[j] > prefix && b[j] < m) m = b[j];
+        }
+        atomicMin(&sh_min_above, m);
+        __syncthreads();
+        v_hi = __uint_as_float(sh_min_above);
+    }
+    // Tensor.lerp: w < 0.5 ? a + w*(b-a) : b - (b-a)*(1-w)
+    const float diff = SUB(v_hi, v_lo);
+    float q = weight < 0.5f ? ADD(v_lo, MUL(weight, diff)) : SUB(v_hi, MUL(diff, SUB(1.0f, weight)));
+    const float sc = fminf(fmaxf(q, 1.0f), max_value);
+    if (threadIdx.x == 0 && s_out) s_out[blockIdx.x] = sc;
+    float4* w4 = reinterpret_cast<float4*>(row);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        float4 v = w4[i];
+        v.x = DIV(fminf(fmaxf(v.x, -sc), sc), sc), v.y = DIV(fminf(fmaxf(v.y, -sc), sc), sc);
+        v.z = DIV(fminf(fmaxf(v.z, -sc), sc), sc), v.w = DIV(fminf(fmaxf(v.w, -sc), sc), sc);
+        w4[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------- projection_loop sigma feed-forward
+// image_sample.py:483-496: cur_norm = ||x_{t-1}||/sqrt(d); cur_dist = sqrt(cur_norm^2 + N^2 - 2 cur_norm N 0.99 + 1e-8);
+// sigma <- r0*sigma_prev_orig + r1*sigma_prev + r2*sigma_t*(cur_norm/last_norm) + r3*cur_dist; t <- get_t_from_sigma
+__global__ void sigma_estimate_kernel(const float* __restrict__ norms, float* __restrict__ last_norm, int B,
+                                      float sqrt_d, float norm_max, float sigma_prev_orig,
+                                      const float* __restrict__ sigma_prev, int n_prev,
+                                      const float* __restrict__ sigma_t, int n_t, float r0, float r1, float r2, float r3,
+                                      const float* __restrict__ table, const float* __restrict__ slopes, int n_table,
+                                      float* __restrict__ sigma_out, float* __restrict__ t_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float cur = DIV(norms[b], sqrt_d);
+    const float nm2 = static_cast<float>(static_cast<double>(norm_max) * static_cast<double>(norm_max));
+    float dist = ADD(MUL(cur, cur), nm2);
+    dist = SUB(dist, MUL(MUL(MUL(2.0f, cur), norm_max), 0.99f));
+    dist = sqrtf(ADD(dist, 1e-8f));
+    const float ratio = DIV(cur, last_norm[b]);
+    const float s1 = sigma_prev[n_prev == 1 ? 0 : b];
+    const float s2 = MUL(sigma_t[n_t == 1 ? 0 : b], ratio);
+    float s = ADD(ADD(ADD(MUL(r0, sigma_prev_orig), MUL(r1, s1)), MUL(r2, s2)), MUL(r3, dist));
+    sigma_out[b] = s;
+    t_out[b] = time_from_sigma(table, slopes, n_table, s);
+    last_norm[b] = cur;
+}
+
 }  // namespace nlc
 
 using namespace nlc;
@@ -294,28 +420,30 @@ extern "C" int nlc_normalize_rows(nlc_ctx* ctx, float* x, int B, int d, void* st
 
 extern "C" int nlc_refine_sigma(nlc_ctx* ctx, const float* norms, int B, int d, const float* sigma_in, int n_sigma_in,
                                 float norm_min, float norm_max, int refine, float t_fixed, const float* sigma_table,
-                                int n_table, int time_shift, float* sigma_out, float* t_out, float* in_scale_out,
-                                void* stream_) {
+                                const float* slopes, int n_table, int time_shift, float* sigma_out, float* t_out,
+                                float* in_scale_out, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && sigma_in && sigma_out && t_out, "nlc_refine_sigma: null argument");
     NLC_REQUIRE(!refine || (norms && sigma_table), "nlc_refine_sigma: refine needs norms and the sigma table");
     NLC_REQUIRE(n_sigma_in == 1 || n_sigma_in == B, "nlc_refine_sigma: n_sigma_in must be 1 or B");
     refine_sigma_kernel<<<1, 1024, 0, stream>>>(norms, B, static_cast<float>(sqrt(static_cast<double>(d))), sigma_in, n_sigma_in,
-                                                norm_min, norm_max, refine, t_fixed, sigma_table, n_table, time_shift,
-                                                sigma_out, t_out, in_scale_out);
+                                                norm_min, norm_max, refine, t_fixed, sigma_table, slopes, n_table,
+                                                time_shift, sigma_out, t_out, in_scale_out);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
 
 extern "C" int nlc_sigma_correct(nlc_ctx* ctx, const float* r, const float* sigma, const float* sigma_prev, int n_prev,
-                                 int B, int update_prev, const float* sigma_table, int n_table, float* sigma_hat,
-                                 float* sigma_prev_hat, float* t_hat, float* in_scale_out, void* stream_) {
+                                 int B, int update_prev, const float* sigma_table, const float* slopes, int n_table,
+                                 float* sigma_hat, float* sigma_prev_hat, float* t_hat, float* in_scale_out,
+                                 void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && r && sigma && sigma_prev && sigma_table && sigma_hat && sigma_prev_hat && t_hat,
                 "nlc_sigma_correct: null argument");
     NLC_REQUIRE(n_prev == 1 || n_prev == B, "nlc_sigma_correct: n_prev must be 1 or B");
     sigma_correct_kernel<<<(B + 127) / 128, 128, 0, stream>>>(r, sigma, sigma_prev, n_prev, B, update_prev, sigma_table,
-                                                              n_table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out);
+                                                              slopes, n_table, sigma_hat, sigma_prev_hat, t_hat,
+                                                              in_scale_out);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -351,6 +479,43 @@ extern "C" int nlc_pred_xprev(nlc_ctx* ctx, int sched, double eta, const float* 
     XprevArgs a{sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_coef, sigma, n_sigma, sigma_prev,
                 n_prev, d, x_prev, nan_flag};
     pred_xprev_kernel<<<dim3(row_grid(ctx->sm_count, B, d), B), 256, 0, stream>>>(a);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_dynamic_threshold(nlc_ctx* ctx, float* x, int B, int d, double ratio, float max_value, float* s_out,
+                                     void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x && B > 0 && d >= 4 && d % 4 == 0, "nlc_dynamic_threshold: bad argument (d %% 4 == 0 required)");
+    NLC_REQUIRE(ratio >= 0.0 && ratio <= 1.0, "nlc_dynamic_threshold: ratio must be in [0,1]");
+    // torch.quantile evaluates q * (n - 1) in the input dtype (fp32)
+    const float rank = static_cast<float>(ratio) * static_cast<float>(d - 1);
+    const float lo = floorf(rank);
+    const int rank_lo = static_cast<int>(lo), rank_hi = static_cast<int>(ceilf(rank));
+    const size_t smem = static_cast<size_t>(kSelCopies) * kSelBins * sizeof(uint32_t);
+    static bool configured = false;
+    if (!configured) {
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(dynamic_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+        configured = true;
+    }
+    dynamic_threshold_kernel<<<B, 1024, smem, stream>>>(x, d, rank_lo, rank_hi, rank - lo, max_value, s_out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_sigma_estimate(nlc_ctx* ctx, const float* norms, float* last_norm, int B, int d, float norm_max,
+                                  float sigma_prev_orig, const float* sigma_prev, int n_prev, const float* sigma_t,
+                                  int n_t, const float* rates4_host, const float* sigma_table, const float* slopes,
+                                  int n_table, float* sigma_out, float* t_out, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && norms && last_norm && sigma_prev && sigma_t && rates4_host && sigma_table && sigma_out && t_out,
+                "nlc_sigma_estimate: null argument");
+    NLC_REQUIRE((n_prev == 1 || n_prev == B) && (n_t == 1 || n_t == B), "nlc_sigma_estimate: vector lengths must be 1 or B");
+    sigma_estimate_kernel<<<(B + 127) / 128, 128, 0, stream>>>(
+        norms, last_norm, B, static_cast<float>(sqrt(static_cast<double>(d))), norm_max, sigma_prev_orig, sigma_prev,
+        n_prev, sigma_t, n_t, rates4_host[0], rates4_host[1], rates4_host[2], rates4_host[3], sigma_table, slopes,
+        n_table, sigma_out, t_out);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

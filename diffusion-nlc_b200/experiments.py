@@ -22,6 +22,8 @@ import torch
 from . import ops
 from .schedulers import CLIP_CLAMP, CLIP_NONE, _as_f32
 
+CLIP_DYNAMIC = 2
+
 
 class _Work:
     """Per-batch-size scratch vectors of the step (all fp32, device)."""
@@ -82,7 +84,9 @@ class ExperimentDiffusion:
         if clip_fn == "clamp":
             self.clip_mode = CLIP_CLAMP
         elif clip_fn == "dynamic":
-            raise NotImplementedError("dynamic thresholding (per-image 0.99 quantile) is not built yet")
+            # partial(_threshold_sample, dynamic_thresholding_ratio=0.99, sample_max_value=100), :204
+            self.clip_mode = CLIP_DYNAMIC
+            self.dynamic_ratio, self.dynamic_max = 0.99, 100.0
         else:
             self.clip_mode = CLIP_NONE
 
@@ -129,7 +133,7 @@ class ExperimentDiffusion:
         if refine_prior_sigma:
             ops.row_norm(xt, w.norms)
             ops.refine_sigma(w.norms, B, self.dim, sig_in, self.norm_min, self.norm_max, True, 0.0, sch.sigma_table,
-                             self.time_shift, w.sigma, w.t, w.scale)
+                             self.time_shift, w.sigma, w.t, w.scale, slopes=sch.slopes_table)
         else:
             t_vec = torch.is_tensor(t) and t.numel() == B and B > 1
             ops.refine_sigma(None, B, self.dim, sig_in, 0.0, 0.0, False, 0.0 if t_vec else float(t), None, 0, w.sigma,
@@ -142,7 +146,7 @@ class ExperimentDiffusion:
             feat = self.model.encode_scaled(xt, t_cur, scale_cur)
             r = self.sigma_model.forward_nhwc(feat)
             ops.sigma_correct(r, sigma_cur, sp_in, style == "pred", sch.sigma_table, w.sigma_hat, w.sigma_prev_hat,
-                              w.t_hat, w.scale_hat)
+                              w.t_hat, w.scale_hat, slopes=sch.slopes_table)
             sigma_cur, t_cur, scale_cur = w.sigma_hat, w.t_hat, w.scale_hat
             sp_cur = w.sigma_prev_hat
         elif refine_prior_sigma and sp_in.numel() == 1:
@@ -163,6 +167,107 @@ class ExperimentDiffusion:
             sp_ret = sp_cur.view(B, 1, 1, 1) if sp_cur.numel() == B else sp_cur
             return w.eps, logvar, sigma_cur.view(B, 1, 1, 1), sp_ret
         return w.eps, logvar, sigma_t, sigma_prev
+
+    def _pred_xstart_clipped(self, xt, eps, sigma_t, out):
+        """pred_xstart + clip_denoise_fn (src/schedulers.py:407-409, src/experiments.py:186-207)."""
+        if self.clip_mode == CLIP_DYNAMIC:
+            x0 = self.scheduler.pred_xstart(xt, eps, sigma_t, clip=CLIP_NONE, out=out)
+            ops.dynamic_threshold_(x0, self.dynamic_ratio, self.dynamic_max)
+            return x0
+        return self.scheduler.pred_xstart(xt, eps, sigma_t, clip=self.clip_mode, out=out)
+
+    # ---------------------------------------------------------------- L2: sigma feed-forward loop
+    @torch.no_grad()
+    def projection_loop(self, shape, gen=None, norm_init_noise=False, style="base", constrain_fn=None, norm_eps=False,
+                        refine_prior_sigma=False, xT=None, return_log=False, chunk_size=2,
+                        sigma_estimate_rate=(1, 0, 0, 0), constrain_loss=None, stop_condition=0.0, max_T=None,
+                        sigma_pred_threshold=1000, new_eta=None, recal_sigma_prev=False, noise_fn=None, step_hook=None,
+                        to_cpu=True, stop_check_every=1):
+        """The module-level `projection_loop` of image_sample.py:431-519 (`--sampling project`): like denoise_loop but
+        the next step's sigma is an estimate fed forward from this step,
+            sigma <- r0*sigma_prev_orig + r1*sigma_prev + r2*sigma_t*||x_{t-1}||/||x_t|| + r3*dist(||x_{t-1}||),
+        and its time is looked up from it (per sample).  The batch-global decisions of the reference (`t.max() >
+        sigma_pred_threshold`, the mean constraint loss against `stop_condition`, :471,:514) read one scalar from the
+        device per step, as the reference does; `stop_check_every` > 1 batches the stop test."""
+        sch = self.scheduler
+        sch.reset_state()
+        sig = sch.sampling_sigmas
+        T = sig.numel()
+        if max_T is None:
+            max_T = len(sch.timesteps_host) - 1
+        if xT is None:
+            xt, zt = self.get_noise_xt(shape=shape, gen=gen, norm_noise=norm_init_noise, sigma=sig[0])
+        else:
+            xt = xT
+            zt = self.convert_coordinate(xt, sigma=sig[0]) if return_log else None
+        B = xt.shape[0]
+        w = self._w(B)
+        w.nan_flag.zero_()
+        w.xa.copy_(xt)
+        xt, nxt = w.xa, w.xb
+        f = lambda: torch.empty(B, device=self.device, dtype=torch.float32)
+        last_norm, cur_norms, sig_est, t_est = f(), f(), f(), f()
+        ops.row_norm(xt, last_norm)
+        last_norm.div_(math.sqrt(self.dim))
+        sigma_t = sig[0:1]
+        t = sch.timesteps_host[0]
+        t_max = float(t)
+        sig_host = sig.cpu()
+        rates = [float(r) for r in sigma_estimate_rate]
+        z_list, eps_list, x0_prec_list, x0_postc_list, sigma_list, const_loss_list = [], [], [], [], [], []
+        if return_log:
+            z_list, sigma_list = [zt.cpu()], [sigma_t.cpu()]
+        best_val, best_x0, x0, const_val = 10000, xt, xt, None
+        steps = len(sch.timesteps_host)
+        for ind in range(max_T):
+            if ind == steps - 1 and new_eta is not None:
+                sch.eta = new_eta
+            sp_orig = sig[T - 1:T] if ind >= T - 1 else sig[ind + 1:ind + 2]
+            if recal_sigma_prev:
+                sigma_prev = _as_f32(sigma_t, self.device) * (sig[ind + 1] / sig[ind])
+            else:
+                sigma_prev = sp_orig
+            cur_style, cur_refine = style, refine_prior_sigma
+            if t_max > sigma_pred_threshold:
+                cur_style, cur_refine = "base", False
+            eps, eps_logvar, sigma_t, sigma_prev = self.get_denoise_vector(
+                xt, t, sigma_t, sigma_prev, cur_style, norm_eps, refine_prior_sigma=cur_refine, chunk_size=chunk_size)
+            x0_hat = self._pred_xstart_clipped(xt, eps, sigma_t, w.x0)
+            x0 = constrain_fn(x0_hat) if constrain_fn is not None else x0_hat
+            noise = noise_fn(ind, x0) if noise_fn is not None else None
+            sch.pred_xprev(x0=x0, eps=eps, sigma_t=sigma_t, sigma_prev=sigma_prev, xt=xt, log_variance=eps_logvar,
+                           noise=noise, out=nxt, nan_flag=w.nan_flag)
+            ops.row_norm(nxt, cur_norms)
+            ops.sigma_estimate(cur_norms, last_norm, self.dim, self.norm_max, float(sig_host[min(ind + 1, T - 1)]),
+                               _as_f32(sigma_prev, self.device), _as_f32(sigma_t, self.device), rates, sch.sigma_table,
+                               sch.slopes_table, sig_est, t_est)
+            if step_hook is not None:
+                step_hook(ind, dict(xt=xt, eps=eps, x0_hat=x0_hat, x0=x0, x_prev=nxt, sigma_t=sigma_t,
+                                    sigma_prev=sigma_prev, sigma_next=sig_est, t_next=t_est))
+            sigma_used, sigma_prev_used = sigma_t, sigma_prev
+            sigma_t, t = sig_est.clone(), t_est.clone()
+            t_max = float(t.max())  # one scalar D2H per step, as `t.max() > sigma_pred_threshold` in the reference
+            if constrain_loss is not None:
+                const, _ = constrain_loss(x0.clamp(-1, 1))
+                const_val = torch.mean(const)
+                if const_val < best_val:
+                    best_x0, best_val = x0.clone(), const_val
+                if return_log:
+                    const_loss_list.append(const.cpu())
+            else:
+                best_x0 = x0
+            if return_log:
+                z_list.append(self.convert_coordinate(nxt, sigma=sigma_prev_used).cpu())
+                eps_list.append(eps.cpu())
+                x0_prec_list.append(x0_hat.cpu())
+                x0_postc_list.append(x0.cpu())
+                sigma_list.append(sigma_t.cpu())
+            xt, nxt = nxt, xt
+            if (ind + 1) % stop_check_every == 0:
+                if int(w.nan_flag.item()) != 0 or (const_val is not None and float(const_val) <= stop_condition):
+                    break
+        result = best_x0.cpu() if to_cpu else best_x0
+        return result, [z_list, eps_list, x0_prec_list, x0_postc_list, sigma_list, const_loss_list]
 
     # ---------------------------------------------------------------- L1: the DDIM-family loop
     @torch.no_grad()
@@ -204,7 +309,7 @@ class ExperimentDiffusion:
                 cur_style, cur_refine = "base", False
             eps, eps_logvar, sigma_t, sigma_prev = self.get_denoise_vector(
                 xt, t, sigma_t, sigma_prev, cur_style, norm_eps, refine_prior_sigma=cur_refine, chunk_size=chunk_size)
-            x0_hat = sch.pred_xstart(xt, eps, sigma_t, clip=self.clip_mode, out=w.x0)
+            x0_hat = self._pred_xstart_clipped(xt, eps, sigma_t, w.x0)
             if constrain_fn is not None and (free_const_steps <= 0 or ind <= free_const_steps):
                 x0 = constrain_fn(x0_hat)
             else:

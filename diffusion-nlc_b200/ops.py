@@ -254,20 +254,42 @@ def normalize_rows_(x):
 
 @_timed("refine_sigma")
 def refine_sigma(norms, B, d, sigma_in, norm_min, norm_max, refine, t_fixed, table, time_shift, sigma_out, t_out,
-                 in_scale_out):
+                 in_scale_out, slopes=None):
     _lib.check(_lib.lib().nlc_refine_sigma(
         _ctx(sigma_in), _p(norms), B, d, _p(sigma_in), sigma_in.numel(), norm_min, norm_max, 1 if refine else 0,
-        float(t_fixed), _p(table), table.numel() if table is not None else 0, int(time_shift), _p(sigma_out),
-        _p(t_out), _p(in_scale_out), _stream()))
+        float(t_fixed), _p(table), _p(slopes), table.numel() if table is not None else 0, int(time_shift),
+        _p(sigma_out), _p(t_out), _p(in_scale_out), _stream()))
     STATS.launches += 1
 
 
 @_timed("sigma_correct")
-def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out):
+def sigma_correct(r, sigma, sigma_prev, update_prev, table, sigma_hat, sigma_prev_hat, t_hat, in_scale_out,
+                  slopes=None):
     B = sigma.numel()
     _lib.check(_lib.lib().nlc_sigma_correct(
         _ctx(r), _p(r), _p(sigma), _p(sigma_prev), sigma_prev.numel(), B, 1 if update_prev else 0, _p(table),
-        table.numel(), _p(sigma_hat), _p(sigma_prev_hat), _p(t_hat), _p(in_scale_out), _stream()))
+        _p(slopes), table.numel(), _p(sigma_hat), _p(sigma_prev_hat), _p(t_hat), _p(in_scale_out), _stream()))
+    STATS.launches += 1
+
+
+@_timed("dynamic_threshold")
+def dynamic_threshold_(x, ratio, max_value, s_out=None):
+    """In place: x_b <- clamp(x_b, -s_b, s_b)/s_b with s_b = clamp(quantile(|x_b|, ratio), 1, max_value)."""
+    B, d = x.shape[0], x[0].numel()
+    _lib.check(_lib.lib().nlc_dynamic_threshold(_ctx(x), _p(x), B, d, float(ratio), float(max_value), _p(s_out),
+                                                _stream()))
+    STATS.launches += 1
+
+
+@_timed("sigma_estimate")
+def sigma_estimate(norms, last_norm, d, norm_max, sigma_prev_orig, sigma_prev, sigma_t, rates, table, slopes,
+                   sigma_out, t_out):
+    B = norms.numel()
+    r4 = (C.c_float * 4)(*[float(v) for v in rates])
+    _lib.check(_lib.lib().nlc_sigma_estimate(
+        _ctx(norms), _p(norms), _p(last_norm), B, d, float(norm_max), float(sigma_prev_orig), _p(sigma_prev),
+        sigma_prev.numel(), _p(sigma_t), sigma_t.numel(), C.byref(r4), _p(table), _p(slopes), table.numel(),
+        _p(sigma_out), _p(t_out), _stream()))
     STATS.launches += 1
 
 

@@ -30,9 +30,23 @@ class LogVar:
         self.mode, self.learned = mode, learned
 
 
+def _interp1d(x, y, xnew):
+    """1-D linear interpolation with the reference's arithmetic (src/torchinterp1d.py:96-148): interval index
+    clamp(searchsorted(x, xnew) - 1, 0, n-2), slopes (y[1:]-y[:-1]) / (eps + (x[1:]-x[:-1])) with eps =
+    finfo(y.dtype).eps, result y[ind] + slopes[ind] * (xnew - x[ind]).  Returns (values, slopes)."""
+    eps = torch.finfo(y.dtype).eps
+    ind = torch.searchsorted(x.contiguous(), xnew.contiguous()) - 1
+    ind = torch.clamp(ind, 0, x.shape[0] - 1 - 1)
+    slopes = (y[1:] - y[:-1]) / (eps + (x[1:] - x[:-1]))
+    return y[ind] + slopes[ind] * (xnew - x[ind]), slopes
+
+
 def _even_steps(n_total, n_pick):
     """`space_timesteps(n_total, str(n_pick))` (src/schedulers.py:38-91) for a single section: n_pick indices in
-    [0, n_total) at (fractional) stride (n_total-1)/(n_pick-1), rounded half-to-even like Python's round()."""
+    [0, n_total) at (fractional) stride (n_total-1)/(n_pick-1), rounded half-to-even like Python's round().
+    A fractional n_total (continuous_t) is a section of floor(n_total)+1 steps (size_per + extra, :73-77)."""
+    if n_total != int(n_total):
+        n_total = n_total // 1 + 1
     if n_total < n_pick:
         raise ValueError("cannot divide section of %d steps into %d" % (n_total, n_pick))
     stride = 1 if n_pick <= 1 else (n_total - 1) / (n_pick - 1)
@@ -110,8 +124,14 @@ class Scheduler:
             setattr(self, name, getattr(self, name).to(device))
         self.timesteps_host = self.timesteps.cpu()
         self.timesteps = self.timesteps.to(device)
+        # continuous_t keeps numpy-born float64 sampling sigmas in the reference (src/schedulers.py:254-271); every
+        # use multiplies them into float32 tensors, i.e. rounds them to float32 first: done once here
         self.sampling_sigmas = self.sampling_sigmas.to(torch.float32).contiguous()
         self.sigma_table = self.sigmas.to(torch.float32).contiguous()
+        self.slopes_table = None
+        if self.continuous_t:  # Interp1d(sigma table -> train timestep) slopes for the device-side time lookup
+            _, sl = _interp1d(self.sigmas.cpu(), self.train_timesteps.float().cpu(), self.sigmas.cpu()[:1])
+            self.slopes_table = sl.to(device, torch.float32).contiguous()
         self.min_var_coef_host = float(self.min_var_coef)
         return self
 
@@ -123,9 +143,26 @@ class Scheduler:
     def sigma_to_t(self, sigma):
         return torch.searchsorted(self.sigmas, torch.as_tensor(sigma, dtype=self.sigmas.dtype, device=self.sigmas.device))
 
+    def sigma_to_t_interp(self, sigma):
+        """src/schedulers.py:210-220 (set-up only; the per-step lookup is done by the kernels)."""
+        xnew = torch.as_tensor(sigma).to(self.sigmas.device).squeeze()
+        if xnew.dim() == 0:
+            xnew = xnew.unsqueeze(0)
+        t, _ = _interp1d(self.sigmas, self.train_timesteps.float(), xnew)
+        return t.float()
+
+    def t_to_sigma_interp(self, t):
+        """src/schedulers.py:192-203."""
+        xnew = t.to(self.sigmas.device).squeeze()
+        if xnew.dim() == 0:
+            xnew = xnew.unsqueeze(0)
+        y_new, _ = _interp1d(self.train_timesteps.float(), self.alphas_cumprod, xnew)
+        sigma = (1 / y_new - 1).sqrt()
+        return torch.where(t >= 0, sigma, self.final_sigma).float()
+
     def get_t_from_sigma(self, sigma):
         if self.continuous_t:
-            raise NotImplementedError("continuous_t (Interp1d time lookup, src/schedulers.py:192-220)")
+            return self.sigma_to_t_interp(sigma)
         return self.sigma_to_t(sigma)
 
     def sigma(self, timestep):
@@ -134,21 +171,23 @@ class Scheduler:
 
     def get_sigma(self, timestep):
         if self.continuous_t:
-            raise NotImplementedError("continuous_t")
+            return self.t_to_sigma_interp(timestep)
         return self.sigma(timestep)
 
     def set_timesteps_sigma(self, start, end, num_inference_steps, style="DDIM", scale=1, continuous_t=False):
         """src/schedulers.py:227-284."""
-        if continuous_t:
-            raise NotImplementedError("continuous_t sampling is not wired in this build")
-        self.continuous_t = False
+        self.continuous_t = bool(continuous_t)
         self.num_inference_steps = num_inference_steps
         n = num_inference_steps if self.set_alpha_to_one else num_inference_steps + 1
+        sig = None
         if style == "DDIM":
-            t_hi = int(self.get_t_from_sigma(start).item())
-            t_lo = int(self.get_t_from_sigma(end).item())
+            t_hi = self.get_t_from_sigma(start).item()
+            t_lo = self.get_t_from_sigma(end).item()
             picks = _even_steps(t_hi + 1 - t_lo, n)
-            ts = torch.tensor(t_lo + np.array(sorted(picks, reverse=True)), dtype=torch.long)
+            ts = torch.tensor(t_lo + np.array(sorted(picks, reverse=True)),
+                              dtype=torch.float32 if self.continuous_t else torch.long)
+            if self.continuous_t:
+                sig = self.get_sigma(ts)
         elif style == "EDM":
             rho = 7  # fp32 tensor arithmetic, like the reference (start/end are 0-d fp32 tensors there)
             s0, s1 = torch.as_tensor(start, dtype=torch.float32), torch.as_tensor(end, dtype=torch.float32)
@@ -156,21 +195,26 @@ class Scheduler:
                                for i in range(n)])
             ts = self.get_t_from_sigma(sig)
         elif style == "Linear":
-            lo, hi = np.log(np.float32(float(start))), np.log(np.float32(float(end)))  # fp32 logs, fp64 linspace
-            sig = torch.tensor(np.exp(np.linspace(lo, hi, n)))
-            ts = self.get_t_from_sigma(sig.to(self.sigmas.dtype))
+            # literally the reference's expression: np.log of a 0-d fp32 torch tensor is torch's fp32 log
+            sig = torch.tensor(np.exp(np.linspace(np.log(start), np.log(end), n)))
+            ts = self.get_t_from_sigma(sig if self.continuous_t else sig.to(self.sigmas.dtype))
         elif style == "Scaled":
-            l0, l1 = np.log(np.float32(float(start))), np.log(np.float32(float(end)))
+            l0, l1 = np.log(start), np.log(end)
             diff = l1 - l0
             a_t = scale ** np.arange(n - 1)
             csum = np.cumsum(a_t)
             logs = np.insert(l0 + diff / csum[-1] * csum, 0, l0)
-            ts = self.get_t_from_sigma(torch.tensor(np.exp(logs)).to(self.sigmas.dtype))
+            sig = torch.tensor(np.exp(logs))
+            ts = self.get_t_from_sigma(sig if self.continuous_t else sig.to(self.sigmas.dtype))
         else:
             raise ValueError("Invalid style!")
-        ts = torch.tensor(_dedup_descending(ts.squeeze().tolist()), dtype=torch.long)
-        self.timesteps = ts
-        self.sampling_sigmas = self.get_sigma(ts)
+        if self.continuous_t:
+            self.timesteps = ts.squeeze()
+            self.sampling_sigmas = sig.squeeze()
+        else:
+            ts = torch.tensor(_dedup_descending(ts.squeeze().tolist()), dtype=torch.long)
+            self.timesteps = ts
+            self.sampling_sigmas = self.get_sigma(ts)
         if self.set_alpha_to_one:
             self.timesteps = torch.cat([self.timesteps, torch.tensor([-1])])
             self.sampling_sigmas = torch.cat([self.sampling_sigmas, torch.tensor([self.final_sigma])])
@@ -261,7 +305,10 @@ def get_sampler(sampler_name, train_timesteps, inference_timesteps, beta_start=0
         else:
             start_sigma = min(s.sigmas[start_t], s.sigmas[-1])
     else:
-        start_sigma = torch.as_tensor(min(start_sigma, s.sigmas[-1]), dtype=torch.float32)
+        # torch.tensor(min(...)) in the reference keeps a Python int an int64 tensor, whose np.log is float64
+        # (src/schedulers.py:717-718): the log-linear schedules depend on it
+        v = min(start_sigma, s.sigmas[-1])
+        start_sigma = v.clone() if torch.is_tensor(v) else torch.tensor(v)
     if end_sigma is None or end_sigma <= 0:
         end_sigma = s.sigmas[0] if (end_t is None or end_t < 0) else s.sigmas[end_t]
     s.set_timesteps_sigma(start=start_sigma, end=end_sigma, num_inference_steps=inference_timesteps,

@@ -167,16 +167,35 @@ int nlc_row_norm(nlc_ctx* ctx, const float* x, int B, int d, float* out, void* s
  *   t_b = clamp(first i with table[i] >= sigma_b  (- time_shift if min_b t > 0), 0, 1000)
  *   refine == 0: sigma_b = sigma_in_b, t_b = clamp(t_fixed, 0, 1000)
  *   in_scale_b = sqrt(1/(sigma_b^2+1))  (convert_coordinate, src/experiments.py:273-282)
- * sigma_in has n_sigma_in entries (1 = broadcast scalar, B = per sample). */
+ * sigma_in has n_sigma_in entries (1 = broadcast scalar, B = per sample).
+ * slopes == NULL: discrete time (searchsorted).  slopes != NULL (continuous_t): the n_table-1 interval slopes of
+ * Interp1d(sigma table -> arange(n_table)) built by the host exactly as src/torchinterp1d.py:137-142 does, and
+ * t = ind + slopes[ind]*(sigma - table[ind]), ind = clamp(searchsorted-1, 0, n_table-2) (src/schedulers.py:210-220). */
 int nlc_refine_sigma(nlc_ctx* ctx, const float* norms, int B, int d, const float* sigma_in, int n_sigma_in,
-                     float norm_min, float norm_max, int refine, float t_fixed, const float* sigma_table, int n_table,
-                     int time_shift, float* sigma_out, float* t_out, float* in_scale_out, void* stream);
+                     float norm_min, float norm_max, int refine, float t_fixed, const float* sigma_table,
+                     const float* slopes, int n_table, int time_shift, float* sigma_out, float* t_out,
+                     float* in_scale_out, void* stream);
 
 /* NLC correction (src/experiments.py:424-431): sigma_hat = sigma*(1+r); sigma_prev_hat = sigma_hat*sigma_prev/sigma
  * (style pred) or sigma_prev (pred_partial); t_hat = clamp(searchsorted(table, sigma_hat)); in_scale = 1/sqrt(s^2+1) */
 int nlc_sigma_correct(nlc_ctx* ctx, const float* r, const float* sigma, const float* sigma_prev, int n_prev, int B,
-                      int update_prev, const float* sigma_table, int n_table, float* sigma_hat,
+                      int update_prev, const float* sigma_table, const float* slopes, int n_table, float* sigma_hat,
                       float* sigma_prev_hat, float* t_hat, float* in_scale_out, void* stream);
+
+/* Dynamic thresholding, in place (src/experiments.py:190-204 with the driver's partial(..., 0.99, 100)):
+ * s_b = clamp(quantile(|x_b|, ratio), 1, max_value), x_b <- clamp(x_b, -s_b, s_b) / s_b.  The quantile is
+ * torch.quantile's (linear interpolation between the two exact order statistics).  s_out [B] may be NULL. */
+int nlc_dynamic_threshold(nlc_ctx* ctx, float* x, int B, int d, double ratio, float max_value, float* s_out,
+                          void* stream);
+
+/* projection_loop's sigma feed-forward (image_sample.py:483-496), norms = nlc_row_norm(x_{t-1}):
+ *   cur = norms/sqrt(d); dist = sqrt(cur^2 + norm_max^2 - 2*cur*norm_max*0.99 + 1e-8)
+ *   sigma_out = r0*sigma_prev_orig + r1*sigma_prev + r2*sigma_t*(cur/last_norm) + r3*dist
+ *   t_out = get_t_from_sigma(sigma_out) (unclamped, like the reference); last_norm <- cur (in place) */
+int nlc_sigma_estimate(nlc_ctx* ctx, const float* norms, float* last_norm, int B, int d, float norm_max,
+                       float sigma_prev_orig, const float* sigma_prev, int n_prev, const float* sigma_t, int n_t,
+                       const float* rates4_host, const float* sigma_table, const float* slopes, int n_table,
+                       float* sigma_out, float* t_out, void* stream);
 
 /* eps normalisation (src/utils.py:11-16): eps_b <- sqrt(d) * eps_b / max(||eps_b||, 1e-12), in place. */
 int nlc_normalize_rows(nlc_ctx* ctx, float* x, int B, int d, void* stream);
@@ -191,6 +210,7 @@ int nlc_normalize_rows(nlc_ctx* ctx, float* x, int B, int d, void* stream);
 
 #define NLC_CLIP_NONE 0
 #define NLC_CLIP_CLAMP 1
+#define NLC_CLIP_DYNAMIC 2 /* host-side: pred_xstart without clip, then nlc_dynamic_threshold */
 
 /* x0_hat = clip(x_t - sigma_b * eps)  — Scheduler.pred_xstart + clamp clip (src/schedulers.py:407-409,
  * src/experiments.py:186-188). */

@@ -24,21 +24,56 @@ class Tables:
         prev = torch.cat([torch.ones(1), self.alphas_cumprod[:-1]])
         self.posterior_variance = self.betas * (1.0 - prev) / (1.0 - self.alphas_cumprod)
 
+    continuous = False  # continuous_t (src/schedulers.py:232): Interp1d time lookup instead of searchsorted
+
+    @staticmethod
+    def _interp(x, y, xnew):
+        """src/torchinterp1d.py:96-148 for 1-D x, y."""
+        eps = torch.finfo(y.dtype).eps
+        ind = torch.clamp(torch.searchsorted(x.contiguous(), xnew.contiguous()) - 1, 0, x.shape[0] - 2)
+        slopes = (y[1:] - y[:-1]) / (eps + (x[1:] - x[:-1]))
+        return y[ind] + slopes[ind] * (xnew - x[ind])
+
     def t_of_sigma(self, sigma):
+        if self.continuous:  # sigma_to_t_interp (:210-220)
+            shape = sigma.shape
+            xnew = sigma.squeeze()
+            xnew = xnew.unsqueeze(0) if xnew.dim() == 0 else xnew
+            t = self._interp(self.sigmas, torch.arange(len(self.sigmas)).float(), xnew.reshape(-1)).float()
+            return t.reshape(xnew.shape) if len(shape) else t
         return torch.searchsorted(self.sigmas, sigma)  # first index with table >= sigma (:185-190)
+
+    def sigma_of_t(self, t):
+        """t_to_sigma_interp (:192-203)."""
+        y = self._interp(torch.arange(len(self.sigmas)).float(), self.alphas_cumprod, t)
+        return torch.where(t >= 0, (1 / y - 1).sqrt(), torch.zeros(())).float()
 
     def ddim_schedule(self, start_sigma, end_sigma, n_steps):
         """Timesteps and sigmas of style 'DDIM' with set_alpha_to_one (src/schedulers.py:237-284)."""
         start = torch.as_tensor(min(float(start_sigma), float(self.sigmas[-1])), dtype=torch.float32) \
             if start_sigma is not None else self.sigmas[-1]
         end = self.sigmas[0] if end_sigma is None else torch.as_tensor(end_sigma, dtype=torch.float32)
-        t_hi, t_lo = int(self.t_of_sigma(start)), int(self.t_of_sigma(end))
-        span = t_hi + 1 - t_lo
+        if self.continuous:
+            t_hi, t_lo = self.t_of_sigma(start).item(), self.t_of_sigma(end).item()
+            span = t_hi + 1 - t_lo
+            if span != int(span):
+                span = span // 1 + 1  # space_timesteps on a fractional count (:73-77)
+        else:
+            t_hi, t_lo = int(self.t_of_sigma(start)), int(self.t_of_sigma(end))
+            span = t_hi + 1 - t_lo
         stride = 1 if n_steps <= 1 else (span - 1) / (n_steps - 1)
         picks, cur = set(), 0.0
         for _ in range(n_steps):
             picks.add(round(cur))
             cur += stride
+        if self.continuous:
+            ts = torch.tensor(t_lo + np.array(sorted(picks, reverse=True)), dtype=torch.float32)
+            sig = self.sigma_of_t(ts)
+            ts = torch.cat([ts, torch.tensor([-1])])
+            sig = torch.cat([sig, torch.zeros(1)])
+            s_t, s_p = sig[-3], sig[-2]
+            beta_t = (s_t ** 2 - s_p ** 2) / (s_t ** 2 + 1)
+            return ts, sig, beta_t * (1 - 1 / (s_p ** 2 + 1)) / (1 - 1 / (s_t ** 2 + 1))
         ts = [t_lo + v for v in sorted(picks, reverse=True)]
         # strictly decreasing repair (:15-31)
         n = len(ts)
@@ -158,6 +193,51 @@ def denoise_vector(tab, model_fwd, model_enc, sigma_fn, xt, t, sigma_t, sigma_pr
     return out, learned, sigma_t, sigma_prev
 
 
+def clip_x0(x0_hat, clip):
+    """clip_denoise_fn (src/experiments.py:186-207)."""
+    if clip == "clamp":
+        return x0_hat.clamp(-1, 1)
+    if clip == "dynamic":
+        b = x0_hat.shape[0]
+        s = torch.quantile(x0_hat.reshape(b, -1).abs(), 0.99, dim=1).clamp(min=1, max=100).view(b, 1, 1, 1)
+        return torch.clamp(x0_hat, -s, s) / s
+    return x0_hat
+
+
+def projection_loop(tab, ts, sig, min_var_coef, model_fwd, model_enc, sigma_fn, xT, kind="ddim", eta=0.0,
+                    sampler_var="none", style="pred", norm_eps=True, refine=True, norm_min=0.0, norm_max=1.0,
+                    clip="clamp", constrain_fn=None, noises=None, sigma_pred_threshold=1000, rates=(1, 0, 0, 0),
+                    max_T=None, recal_sigma_prev=False, log=None):
+    """The module-level projection_loop of image_sample.py:431-519 (no constraint loss / early stop)."""
+    dim = xT[0].numel()
+    xt = x0 = xT
+    sigma_t, t = sig[0], ts[0]
+    last_norm = vector_norm(xt) / math.sqrt(dim)
+    T = len(sig)
+    max_T = len(ts) - 1 if max_T is None else max_T
+    for ind in range(max_T):
+        sp_orig = sig[-1] if ind >= T - 1 else sig[ind + 1]
+        sigma_prev = sigma_t * (sig[ind + 1] / sig[ind]) if recal_sigma_prev else sp_orig
+        cur_style, cur_refine = (style, refine) if not (torch.as_tensor(t).max() > sigma_pred_threshold) else ("base", False)
+        eps, learned, sigma_t, sigma_prev = denoise_vector(tab, model_fwd, model_enc, sigma_fn, xt, t, sigma_t,
+                                                           sigma_prev, cur_style, norm_eps, cur_refine, norm_min,
+                                                           norm_max)
+        logvar = eps_logvar(sigma_t, sigma_prev, min_var_coef, sampler_var, learned)
+        x0_hat = clip_x0(xt - sigma_t * eps, clip)
+        x0 = constrain_fn(x0_hat) if constrain_fn is not None else x0_hat
+        x_prev = pred_xprev(kind, eta, x0, eps, sigma_t, sigma_prev, xt, logvar,
+                            noises[ind] if noises is not None else None)
+        cur_norm = vector_norm(x_prev) / math.sqrt(dim)
+        cur_dist = torch.sqrt(cur_norm ** 2 + norm_max ** 2 - 2 * cur_norm * norm_max * 0.99 + 1e-8)
+        new_sigma = rates[0] * sp_orig + rates[1] * sigma_prev + rates[2] * (sigma_t * (cur_norm / last_norm)) \
+            + rates[3] * cur_dist
+        if log is not None:
+            log.append(dict(xt=xt, eps=eps, x0=x0, x_prev=x_prev, sigma_t=torch.as_tensor(sigma_t).reshape(-1),
+                            sigma_next=new_sigma.reshape(-1)))
+        sigma_t, t, last_norm, xt = new_sigma, tab.t_of_sigma(new_sigma), cur_norm, x_prev
+    return x0
+
+
 def denoise_loop(tab, ts, sig, min_var_coef, model_fwd, model_enc, sigma_fn, xT, kind="ddim", eta=0.0,
                  sampler_var="none", style="pred", norm_eps=True, refine=True, norm_min=0.0, norm_max=1.0, clip="clamp",
                  constrain_fn=None, noises=None, sigma_pred_threshold=1000, learn_epsvar=False, log=None):
@@ -173,13 +253,7 @@ def denoise_loop(tab, ts, sig, min_var_coef, model_fwd, model_enc, sigma_fn, xT,
                                                            sigma_prev, cur_style, norm_eps, cur_refine, norm_min,
                                                            norm_max, learn_epsvar=learn_epsvar)
         logvar = eps_logvar(sigma_t, sigma_prev, min_var_coef, sampler_var, learned)
-        x0_hat = xt - sigma_t * eps
-        if clip == "clamp":
-            x0_hat = x0_hat.clamp(-1, 1)
-        elif clip == "dynamic":
-            b = x0_hat.shape[0]
-            s = torch.quantile(x0_hat.reshape(b, -1).abs(), 0.99, dim=1).clamp(min=1, max=100).view(b, 1, 1, 1)
-            x0_hat = torch.clamp(x0_hat, -s, s) / s
+        x0_hat = clip_x0(xt - sigma_t * eps, clip)
         x0 = constrain_fn(x0_hat) if constrain_fn is not None else x0_hat
         noise = noises[ind] if noises is not None else None
         x_prev = pred_xprev(kind, eta, x0, eps, sigma_t, sigma_prev, xt, logvar, noise)

@@ -123,6 +123,7 @@ def main():
     torch.save(gold, os.path.join(HERE, "operators_r32.pt"))
     adm()
     edm()
+    loops2()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -162,6 +163,78 @@ def adm():
             r = snet(feat)
         gold[name] = dict(x=x, t=t, out=out, feat=feat, r=r)
     torch.save(gold, os.path.join(HERE, "nets_adm.pt"))
+
+
+LOOP2_CASES = [  # (loop, continuous_t, clip, rates, sampler, eta)
+    ("denoise", True, "clamp", None, "ddim", 0.0),
+    ("denoise", True, "dynamic", None, "ddim_simple_orig", 0.85),
+    ("project", True, "dynamic", [0.5, 0.2, 0.2, 0.1], "ddim_simple_orig", 0.85),
+    ("project", False, "clamp", [1, 0, 0, 0], "ddim", 0.0),
+    ("project", True, "clamp", [0, 1, 0, 0], "ddim", 0.0),
+]
+
+
+def image_sample_module():
+    """The reference's driver module (holds the module-level projection_loop); plotting / SSIM imports are stubbed."""
+    import importlib
+    import types
+    refimport.load()
+    for name in ("skimage", "skimage.metrics", "cv2"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["skimage.metrics"], "structural_similarity"):
+        sys.modules["skimage.metrics"].structural_similarity = None
+        sys.modules["skimage"].metrics = sys.modules["skimage.metrics"]
+    return importlib.import_module("image_sample")
+
+
+def loops2():
+    """continuous_t, dynamic thresholding and the sigma feed-forward projection_loop, observed on the reference
+    -> loops2_tiny.pt"""
+    R = refimport.load()
+    IS = image_sample_module()
+    torch.set_num_threads(4)
+    cfg = weights.CONFIGS["tiny"]
+    u, sg = cfg["unet"], cfg["sigma"]
+    net = R.unet_ddim.UNetModel(**u).eval()
+    net.load_state_dict(weights.ddim_unet_state_dict(**u, seed=3))
+    snet = R.unet_ddim.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    snet.load_state_dict(weights.ddim_sigma_state_dict(**sg, seed=4))
+    B, side = 2, u["image_size"]
+    shape = (B, 3, side, side)
+    gold = {}
+    for loop, cont, clip, rates, kind, eta in LOOP2_CASES:
+        sch = R.schedulers.get_sampler(kind, 1000, 6, start_sigma=20.0, eta=eta, continuous_t=cont)
+        exp = R.experiments.ImageExperiment(net, sch, batch_size=B, data_shape=shape[1:], seed=5, device="cpu")
+        exp.set_model(net, snet, learn_epsvar=False)
+        exp.set_norm_maxmin(0.0, 30.0)
+        exp.set_clip_fn(clip)
+        torch.manual_seed(5)
+        z = torch.randn(shape)
+        noises = [torch.randn(shape) for _ in range(len(sch.timesteps) - 1)] if eta > 0 else []
+        rec = dict(xt=[], sigma_t=[], sigma_prev=[], x_prev=[], x0=[])
+        orig = sch.pred_xprev
+
+        def spy(*a, _orig=orig, _rec=rec, **k):
+            out = _orig(*a, **k)
+            _rec["xt"].append(k["xt"].clone())
+            _rec["x0"].append(k["x0"].clone())
+            _rec["sigma_t"].append(torch.as_tensor(k["sigma_t"]).reshape(-1).clone())
+            _rec["sigma_prev"].append(torch.as_tensor(k["sigma_prev"]).reshape(-1).clone())
+            _rec["x_prev"].append(out.clone())
+            return out
+
+        sch.pred_xprev = spy
+        kw = dict(shape=shape, gen=exp.new_gen(5), style="pred", norm_eps=True, refine_prior_sigma=True, chunk_size=1)
+        if loop == "denoise":
+            final, _ = exp.denoise_loop(return_log=False, **kw)
+        else:
+            final, _ = IS.projection_loop(exp, sigma_estimate_rate=rates, **kw)
+        gold["%s|%d|%s|%s|%s|%s" % (loop, int(cont), clip, rates, kind, eta)] = dict(
+            z=z, noises=noises, final=final, timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone(), **rec)
+    torch.save(gold, os.path.join(HERE, "loops2_tiny.pt"))
 
 
 EDM_CASES = [("pred_partial,pred", "00", False, 1.0), ("base,base", "00", False, 1.0), ("pred,pred_partial", "11", True, 1.0),

@@ -150,3 +150,29 @@ def test_edm_sampler_every_case(golden_dir):
             x = o.sample(case["latents"], 4, style=style, norm_eps=ne + "0", refine=bool(int(refine)),
                          eps_scale=None if es == "None" else float(es))
         assert torch.equal(x, case["final"]), key
+
+
+def test_continuous_t_dynamic_clip_and_projection_loop(golden_dir, tiny):
+    """tests/golden/loops2_tiny.pt: the reference's denoise_loop with continuous_t / dynamic thresholding and the
+    module-level projection_loop of image_sample.py (sigma feed-forward)."""
+    sd, ssd = tiny
+    g = load(golden_dir, "loops2_tiny.pt")
+    fwd = lambda z, t: ddim_net.unet_forward(sd, z, t)
+    enc = lambda z, t: ddim_net.unet_encode(sd, z, t)
+    sgf = lambda f: ddim_net.sigma_forward(ssd, f)
+    d = 3 * 16 * 16
+    for key, case in g.items():
+        loop, cont, clip, rates, kind, eta = key.split("|")
+        tab = S.Tables()
+        tab.continuous = bool(int(cont))
+        ts, sig, mvc = tab.ddim_schedule(20.0, None, 6)
+        assert torch.equal(ts.float(), case["timesteps"].float()) and torch.equal(sig, case["sigmas"].float())
+        xT = case["z"] / (1 / (sig[0] ** 2 + 1)).sqrt()
+        kw = dict(kind=kind, eta=float(eta), style="pred", norm_eps=True, refine=True, norm_min=0.0,
+                  norm_max=30.0 / d ** 0.5, clip=clip, noises=case["noises"] or None)
+        with torch.no_grad():
+            if loop == "denoise":
+                x0 = S.denoise_loop(tab, ts.tolist(), sig, mvc, fwd, enc, sgf, xT, **kw)
+            else:
+                x0 = S.projection_loop(tab, ts, sig, mvc, fwd, enc, sgf, xT, rates=eval(rates), **kw)
+        assert torch.equal(x0, case["final"]), key

@@ -65,13 +65,22 @@ def test_c2_layout(R):
     dict(sampler_name="ddim", inference_timesteps=20, sigma_style="Scaled", start_sigma=50, end_sigma=0.05,
          linear_scale=1.1),
     dict(sampler_name="ddim", inference_timesteps=30, beta_schedule="cosine"),
+    dict(sampler_name="ddim", inference_timesteps=50, start_sigma=100, continuous_t=True),
+    dict(sampler_name="ddim", inference_timesteps=10, sigma_style="EDM", start_sigma=80, end_sigma=0.02, continuous_t=True),
+    dict(sampler_name="ddpm", inference_timesteps=20, sigma_style="Linear", start_sigma=50, end_sigma=0.05,
+         sampler_var="fixedsmall", continuous_t=True),
+    dict(sampler_name="ddim", inference_timesteps=20, sigma_style="Linear", start_sigma=50.0, end_sigma=0.05),
+    dict(sampler_name="ddim", inference_timesteps=20, sigma_style="Scaled", start_sigma=50, end_sigma=0.05,
+         linear_scale=1.1, continuous_t=True),
 ])
 def test_scheduler_mirror_tables(R, kw):
     from nlc_b200 import schedulers as M
     a = R.schedulers.get_sampler(train_timesteps=1000, **kw)
     b = M.get_sampler(train_timesteps=1000, **kw)
-    assert torch.equal(a.timesteps, b.timesteps)
-    assert torch.equal(a.sampling_sigmas.float(), b.sampling_sigmas.float())
+    assert a.timesteps.dtype == b.timesteps.dtype and torch.equal(a.timesteps, b.timesteps)
+    assert a.sampling_sigmas.dtype == b.sampling_sigmas.dtype and torch.equal(a.sampling_sigmas, b.sampling_sigmas)
+    s = torch.rand(9) * 90 + 0.01
+    assert torch.equal(a.get_t_from_sigma(s.view(-1, 1, 1, 1)).reshape(-1), b.get_t_from_sigma(s.view(-1, 1, 1, 1)).reshape(-1))
     assert torch.equal(a.sigmas, b.sigmas)
     assert float(a.min_var_coef) == float(b.min_var_coef)
 
@@ -215,3 +224,42 @@ def test_edm_sampler(R, style, ne, refine, es):
         lat = R.experiments.StackedRandomGenerator("cpu", [5, 6]).randn((B, 3, Rr, Rr), device="cpu")
         mine = o.sample(lat, 3, style=style, norm_eps=ne + "0", refine=refine, eps_scale=es)
     assert ref.dtype == torch.float64 and torch.equal(ref, mine)
+
+
+@pytest.mark.parametrize("cont,clip,rates,kind,eta", [(False, "clamp", [1, 0, 0, 0], "ddim", 0.0),
+                                                      (True, "dynamic", [0.5, 0.2, 0.2, 0.1], "ddim_simple_orig", 0.85)])
+def test_projection_loop_and_continuous_t(R, cont, clip, rates, kind, eta):
+    """oracle/sampler.py projection_loop / continuous-t denoise_loop == image_sample.projection_loop /
+    ImageExperiment.denoise_loop of the reference (torch.equal)."""
+    IS = _make_golden().image_sample_module()
+    cfg = weights.CONFIGS["tiny"]
+    u, sg = cfg["unet"], cfg["sigma"]
+    sd = weights.ddim_unet_state_dict(**u, seed=3)
+    ssd = weights.ddim_sigma_state_dict(**sg, seed=4)
+    net = R.unet_ddim.UNetModel(**u).eval()
+    net.load_state_dict(sd)
+    snet = R.unet_ddim.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    snet.load_state_dict(ssd)
+    shape = (2, 3, 16, 16)
+    sch = R.schedulers.get_sampler(kind, 1000, 4, start_sigma=30.0, eta=eta, continuous_t=cont)
+    exp = R.experiments.ImageExperiment(net, sch, batch_size=2, data_shape=shape[1:], seed=9, device="cpu")
+    exp.set_model(net, snet, learn_epsvar=False)
+    exp.set_norm_maxmin(-2.0, 25.0)
+    exp.set_clip_fn(clip)
+    kw = dict(shape=shape, style="pred", norm_eps=True, refine_prior_sigma=True, chunk_size=1)
+    ref_p, _ = IS.projection_loop(exp, gen=exp.new_gen(9), sigma_estimate_rate=rates, **kw)
+    ref_d, _ = exp.denoise_loop(gen=exp.new_gen(9), return_log=False, **kw)
+    tab = S.Tables()
+    tab.continuous = cont
+    ts, sig, mvc = tab.ddim_schedule(30.0, None, 4)
+    torch.manual_seed(9)
+    z = torch.randn(shape)
+    noises = [torch.randn(shape) for _ in range(len(ts) - 1)] if eta > 0 else None
+    f = (lambda a, t: ddim_net.unet_forward(sd, a, t), lambda a, t: ddim_net.unet_encode(sd, a, t),
+         lambda x: ddim_net.sigma_forward(ssd, x))
+    okw = dict(kind=kind, eta=eta, style="pred", norm_eps=True, refine=True, norm_min=exp.norm_min,
+               norm_max=exp.norm_max, clip=clip, noises=noises)
+    xT = z / (1 / (sig[0] ** 2 + 1)).sqrt()
+    with torch.no_grad():
+        assert torch.equal(S.projection_loop(tab, ts, sig, mvc, *f, xT, rates=rates, **okw), ref_p)
+        assert torch.equal(S.denoise_loop(tab, ts.tolist(), sig, mvc, *f, xT, **okw), ref_d)
