@@ -38,7 +38,7 @@ class ConvDesc(C.Structure):
         ("bias", C.c_void_p), ("rowvec", C.c_void_p), ("ld_rowvec", C.c_int),
         ("resid", C.c_void_p), ("ld_resid", C.c_int), ("out_scale", C.c_float),
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int), ("out_op", C.c_void_p), ("ld_out_op", C.c_int),
-        ("out_head_split", C.c_int),
+        ("out_head_split", C.c_int), ("stats", C.c_void_p), ("stats_nblk", C.c_int),
     ]
 
 
@@ -64,8 +64,9 @@ _SIGNATURES = {
     "nlc_sm_count": (_I, [_P]),
     "nlc_conv_tc": (_I, [_P, C.POINTER(ConvDesc), _P]),
     "nlc_conv_in_nchw": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _I, _P]),
+    "nlc_im2col_in": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
     "nlc_conv_out_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
-    "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _P]),
+    "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P]),
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "nlc_resample_op": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

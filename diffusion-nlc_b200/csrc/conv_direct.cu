@@ -78,6 +78,55 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------- im2col of the network input
+// The input convolution (3 -> C) as a tensor-core GEMM: each pixel's 3x3xCin receptive field (27 values for RGB),
+// scaled by the per-sample input scale, is laid out as one K-major operand row [tap*Cin + ci], zero-padded to one
+// 128-byte swizzle row (64 bf16 / 32 tf32); nlc_conv_tc then runs it as a 1x1 convolution with K = 64 | 32.
+// Replaces the CUDA-core conv_in kernel above on the hot path: that one is bound by fp32 FMA issue, this one by the
+// HBM write of the output.
+template <bool TF32>
+__global__ void __launch_bounds__(256)
+    im2col_in_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, int B, int Cin, int H, int W,
+                     void* __restrict__ patches) {
+    constexpr int KP = TF32 ? 32 : 64;
+    const long long npix = static_cast<long long>(B) * H * W;
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int w = static_cast<int>(pix % W);
+        const int h = static_cast<int>((pix / W) % H);
+        const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+        const float sc = in_scale ? in_scale[n] : 1.0f;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        const float* xn = x + static_cast<size_t>(n) * Cin * H * W;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci)
+                    if (ci < Cin) v[tap * Cin + ci] = __ldg(xn + (static_cast<size_t>(ci) * H + hh) * W + ww) * sc;
+            }
+        }
+        if (TF32) {
+            float4* o = reinterpret_cast<float4*>(static_cast<float*>(patches) + static_cast<size_t>(pix) * KP);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                o[i] = make_float4(round_tf32(v[4 * i]), round_tf32(v[4 * i + 1]), round_tf32(v[4 * i + 2]),
+                                   round_tf32(v[4 * i + 3]));
+        } else {
+            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(patches) + static_cast<size_t>(pix) * KP);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+#pragma unroll
+            for (int i = 4; i < 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- conv_out: NHWC operand -> NCHW fp32
 // one warp per group of 4 consecutive pixels of a row; lanes split the input channels; weights in smem as
 // [tap][co][ci].  COUT is a template parameter so the accumulators stay in registers.
@@ -237,4 +286,23 @@ extern "C" int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, i
                                       out_nchw, stream);
     return launch_conv_out<__nv_bfloat16>(ctx, static_cast<const __nv_bfloat16*>(x_op), ld_x, B, Cin, H, W, weight,
                                           bias, Cout, out_nchw, stream);
+}
+
+extern "C" int nlc_im2col_in(nlc_ctx* ctx, const float* x_nchw, const float* in_scale, int B, int Cin, int H, int W,
+                             void* patches_op, int op_dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x_nchw && patches_op, "nlc_im2col_in: null argument");
+    NLC_REQUIRE(Cin >= 1 && Cin <= 3, "nlc_im2col_in: Cin=%d unsupported (1..3: 9*Cin must fit one 32-element K row)", Cin);
+    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32, "nlc_im2col_in: bad op_dtype");
+    NLC_REQUIRE((reinterpret_cast<uintptr_t>(patches_op) & 15) == 0, "nlc_im2col_in: patches must be 16-byte aligned");
+    const long long npix = static_cast<long long>(B) * H * W;
+    long long blocks = (npix + 255) / 256;
+    const long long cap = static_cast<long long>(ctx->sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    if (op_dtype == NLC_F32)
+        im2col_in_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op);
+    else
+        im2col_in_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
 }

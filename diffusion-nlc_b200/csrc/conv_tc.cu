@@ -51,6 +51,8 @@ struct ConvKParams {
     int ld_out_op;
     int out_head_split;
     int w_batched;
+    float* stats;    // GroupNorm partials of the fp32 output: [pixel/32][stats_nblk][2] = (mean, M2) over 32 px x 4 ch
+    int stats_nblk;
 };
 
 template <int BLOCK_N>
@@ -59,9 +61,61 @@ struct ConvCfg {
     static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
     static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
-    static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024: manual alignment slack
+    static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
+    static constexpr int kEpiBytes = 4 * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
+    static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: alignment slack
 };
+
+// GroupNorm statistics of the tile the epilogue holds in registers, so that the consumer's GroupNorm never re-reads
+// the tensor for them.  One warp = 32 consecutive pixels, f[] = 32 consecutive channels of this lane's pixel.
+// For each of the 8 four-channel blocks the warp writes (mean, M2) over its 32 x 4 values: per-lane two-pass
+// moments of the 4 channels, shifted by lane 0's block mean (a bf16-rounded pivot: any value near the mean removes
+// the cancellation), then a transposing butterfly that reduces the 16 running sums in 16 shuffles.
+__device__ __forceinline__ void gn_partials(const float (&f)[32], int lane, float* __restrict__ dst) {
+    float m[8], v[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        m[j] = 0.25f * ((f[4 * j] + f[4 * j + 1]) + (f[4 * j + 2] + f[4 * j + 3]));
+        const float a = f[4 * j] - m[j], b = f[4 * j + 1] - m[j], c = f[4 * j + 2] - m[j], d = f[4 * j + 3] - m[j];
+        v[8 + j] = (a * a + b * b) + (c * c + d * d);
+    }
+    float pv[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t pk = __shfl_sync(0xffffffffu, pack_bf16x2(m[2 * i], m[2 * i + 1]), 0);
+        pv[2 * i] = __uint_as_float(pk << 16);
+        pv[2 * i + 1] = __uint_as_float(pk & 0xffff0000u);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float dm = m[j] - pv[j];
+        v[j] = dm;
+        v[8 + j] += 4.0f * dm * dm;
+    }
+    // lanes end up holding: bit4 -> {sum of (m - p), sum of squares}, bits 3..1 -> block j
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+    float w8[8], w4[4], w2[2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        w8[i] = (h16 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 8], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        w4[i] = (h8 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[i] : w8[i + 4], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+        w2[i] = (h4 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, h4 ? w4[i] : w4[i + 2], 4);
+    float z = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w2[0] : w2[1], 2);
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    const float s2 = __shfl_xor_sync(0xffffffffu, z, 16);
+    if ((lane & 17) == 0) {  // bit4 == 0 (holds s1), bit0 == 0 (one of the two duplicates)
+        const float p4a = h8 ? pv[4] : pv[0], p4b = h8 ? pv[5] : pv[1], p4c = h8 ? pv[6] : pv[2], p4d = h8 ? pv[7] : pv[3];
+        const float p2a = h4 ? p4c : p4a, p2b = h4 ? p4d : p4b;
+        const float piv = h2 ? p2b : p2a;
+        const int j = (lane >> 1) & 7;
+        // mean = p + s1/32;  M2 = sum (x-p)^2 - 128 (mean-p)^2 = s2 - s1^2/8
+        *reinterpret_cast<float2*>(dst + 2 * j) = make_float2(piv + z * (1.0f / 32.0f), fmaxf(s2 - z * z * 0.125f, 0.0f));
+    }
+}
 
 template <int BLOCK_N, bool TF32>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
@@ -176,13 +230,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
+        // Each warp owns TMEM lanes [32*quad, 32*quad+32) = 32 consecutive output pixels; a lane holds one pixel's
+        // 32 channels of the current column chunk.  Global traffic goes through a per-warp 32x32 fp32 staging block
+        // (16-byte chunks XOR-swizzled by the row, conflict-free both ways) so that every load / store instruction
+        // touches 4 full 128-byte rows instead of 32 partial ones.
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-        const int row = quad * 32 + lane;
+        float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes) + quad * 1024;
         const int brick = p.BW * p.BH;
+        const int row = quad * 32 + lane;
         const int bn = row / brick;
-        const int r2 = row - bn * brick;
-        const int bh = r2 / p.BW;
-        const int bw = r2 - bh * p.BW;
+        // the warp's first row inside the tile (its 32 rows are consecutive pixels of one image: DESIGN.md §3)
+        const int row0 = quad * 32;
+        const int bn0 = row0 / brick;
+        const int r20 = row0 - bn0 * brick;
+        const int bh0 = r20 / p.BW;
+        const int bw0 = r20 - bh0 * p.BW;
+        const int sub_r4 = lane >> 3, sub_c4 = lane & 7;  // fp32 pattern: 4 rows x 8 chunks per instruction
+        const int sub_r8 = lane >> 2, sub_c8 = lane & 3;  // bf16 pattern: 8 rows x 4 (8-channel) chunks
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -192,14 +256,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const int rem = m_tile - tn * tiles_per_img;
             const int th = rem / p.tiles_w;
             const int tw = rem - th * p.tiles_w;
-            const int n = tn * p.BN + bn;
-            const int ho = th * p.BH + bh;
-            const int wo = tw * p.BW + bw;
+            const int n = tn * p.BN + bn;  // this lane's image (bias row of the per-sample vector)
             const bool valid = n < p.B;
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            const int n0 = tn * p.BN + bn0, ho0 = th * p.BH + bh0, wo0 = tw * p.BW + bw0;
             // dense NHWC row, or (attention head merge) row (n,wo) with a channel offset of ho*split
-            const size_t pix = p.out_head_split ? static_cast<size_t>(n) * p.Wo + wo
-                                                : (static_cast<size_t>(n) * p.Ho + ho) * p.Wo + wo;
-            const int hs_off = p.out_head_split * ho;
+            const size_t pix0 = p.out_head_split ? static_cast<size_t>(n0) * p.Wo + wo0
+                                                 : (static_cast<size_t>(n0) * p.Ho + ho0) * p.Wo + wo0;
+            const int hs_off = p.out_head_split * ho0;
 
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after_sync();
@@ -208,68 +272,97 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int c = 0; c < BLOCK_N; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c, v);
+                const int col0 = n_tile * BLOCK_N + c;
+                const int ocol0 = col0 + hs_off;
+                if (p.resid) {  // coalesced gather of the residual block while the TMEM load is in flight
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + sub_r4;
+                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if ((vmask >> r) & 1)
+                            t = __ldg(reinterpret_cast<const float4*>(p.resid + (pix0 + r) * p.ld_resid + col0) + sub_c4);
+                        *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                    }
+                    __syncwarp();
+                }
                 tmem_ld_wait();
-                if (valid) {
-                    const int col0 = n_tile * BLOCK_N + c;
-                    const int ocol0 = col0 + hs_off;
-                    float f[32];
+                float f[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    if (p.bias) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (p.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = __ldg(b4 + i);
-                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 t = __ldg(b4 + i);
+                        f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                    }
+                }
+                if (p.rowvec && valid) {
+                    const float4* b4 =
+                        reinterpret_cast<const float4*>(p.rowvec + static_cast<size_t>(n) * p.ld_rowvec + col0);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 t = __ldg(b4 + i);
+                        f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                    }
+                }
+                if (p.resid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2));
+                        f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                    }
+                    __syncwarp();
+                }
+                if (p.out_scale != 1.0f) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
+                }
+                if (p.stats) gn_partials(f, lane, p.stats + (((pix0 + lane) >> 5) * p.stats_nblk + (col0 >> 2)) * 2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
+                        make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                __syncwarp();
+                if (p.out_f32) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + sub_r4;
+                        if ((vmask >> r) & 1)
+                            reinterpret_cast<float4*>(p.out_f32 + (pix0 + r) * p.ld_out_f32 + ocol0)[sub_c4] =
+                                *reinterpret_cast<const float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2));
+                    }
+                }
+                if (p.out_op) {
+                    if (TF32) {
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + sub_r4;
+                            if ((vmask >> r) & 1) {
+                                const float4 t = *reinterpret_cast<const float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2));
+                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + (pix0 + r) * p.ld_out_op +
+                                                          ocol0)[sub_c4] =
+                                    make_float4(round_tf32(t.x), round_tf32(t.y), round_tf32(t.z), round_tf32(t.w));
+                            }
                         }
-                    }
-                    if (p.rowvec) {
-                        const float4* b4 =
-                            reinterpret_cast<const float4*>(p.rowvec + static_cast<size_t>(n) * p.ld_rowvec + col0);
+                    } else {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = __ldg(b4 + i);
-                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
-                        }
-                    }
-                    if (p.resid) {
-                        const float4* b4 = reinterpret_cast<const float4*>(p.resid + pix * p.ld_resid + col0);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float4 t = __ldg(b4 + i);
-                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
-                        }
-                    }
-                    if (p.out_scale != 1.0f) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
-                    }
-                    if (p.out_f32) {
-                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + pix * p.ld_out_f32 + ocol0);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            o4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    }
-                    if (p.out_op) {
-                        if (TF32) {
-                            float4* o4 =
-                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + pix * p.ld_out_op + ocol0);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                o4[i] = make_float4(round_tf32(f[4 * i]), round_tf32(f[4 * i + 1]),
-                                                    round_tf32(f[4 * i + 2]), round_tf32(f[4 * i + 3]));
-                        } else {
-                            uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_op) +
-                                                                 pix * p.ld_out_op + ocol0);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                o4[i] = make_uint4(pack_bf16x2(f[8 * i], f[8 * i + 1]),
-                                                   pack_bf16x2(f[8 * i + 2], f[8 * i + 3]),
-                                                   pack_bf16x2(f[8 * i + 4], f[8 * i + 5]),
-                                                   pack_bf16x2(f[8 * i + 6], f[8 * i + 7]));
+                        for (int it = 0; it < 4; ++it) {
+                            const int r = it * 8 + sub_r8;
+                            if ((vmask >> r) & 1) {
+                                const float4 a =
+                                    *reinterpret_cast<const float4*>(stg + r * 32 + (((2 * sub_c8) ^ (r & 7)) << 2));
+                                const float4 b =
+                                    *reinterpret_cast<const float4*>(stg + r * 32 + (((2 * sub_c8 + 1) ^ (r & 7)) << 2));
+                                reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_op) +
+                                                         (pix0 + r) * p.ld_out_op + ocol0)[sub_c8] =
+                                    make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y),
+                                               pack_bf16x2(b.z, b.w));
+                            }
                         }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before_sync();
             __syncwarp();
@@ -416,6 +509,13 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     }
     p.out_head_split = d->out_head_split;
     NLC_REQUIRE(d->out_head_split % 8 == 0, "nlc_conv_tc: out_head_split must be a multiple of 8");
+    if (d->stats) {
+        NLC_REQUIRE(p.BN == 1 && d->out_head_split == 0 && d->stats_nblk >= d->Cout / 4 &&
+                        (reinterpret_cast<uintptr_t>(d->stats) & 7) == 0,
+                    "nlc_conv_tc: fused GroupNorm partials need Ho*Wo >= 128, dense NHWC output and an 8-byte aligned "
+                    "buffer of >= Cout/4 blocks per 32 pixels");
+        p.stats = d->stats, p.stats_nblk = d->stats_nblk;
+    }
     p.bias = d->bias, p.rowvec = d->rowvec, p.ld_rowvec = d->ld_rowvec;
     p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;

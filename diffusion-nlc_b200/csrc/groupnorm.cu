@@ -79,33 +79,120 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
     }
 }
 
-// grid (apply_chunks, B); dynamic smem: 2*C floats (per-channel a, b with y = x*a + b)
-template <bool TF32>
-__global__ void __launch_bounds__(kGnThreads)
-    gn_apply_kernel(const float* __restrict__ x, int ld_x, int HW, int C, int groups, float eps,
-                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int ld_ss, int do_silu, void* __restrict__ y, int ld_y,
-                    int stat_chunks, const float* __restrict__ ws, int rows_per_chunk) {
-    extern __shared__ float gn_smem[];
-    float* ca = gn_smem;
-    float* cb = gn_smem + C;
-    __shared__ float s_mean[64], s_rstd[64];
-    const int chunk = blockIdx.x, n = blockIdx.y;
-    for (int g = threadIdx.x; g < groups; g += kGnThreads) {
+// ---------------------------------------------------------------- statistics -> (mean, rstd) per (sample, group)
+// (a) from the Welford partials of gn_stats_kernel; grid (B), one thread per group
+__global__ void gn_finalize_welford_kernel(const float* __restrict__ ws, int stat_chunks, int groups, float eps,
+                                           float* __restrict__ mr) {
+    const int n = blockIdx.x;
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         Wf acc = {0.f, 0.f, 0.f};
         for (int k = 0; k < stat_chunks; ++k) {
             const float* o = ws + ((static_cast<size_t>(n) * stat_chunks + k) * groups + g) * 3;
             acc = wf_merge(acc, Wf{o[0], o[1], o[2]});
         }
-        s_mean[g] = acc.mean;
-        s_rstd[g] = rsqrtf(acc.m2 / acc.n + eps);
+        mr[(n * groups + g) * 2] = acc.mean;
+        mr[(n * groups + g) * 2 + 1] = rsqrtf(acc.m2 / acc.n + eps);
+    }
+}
+
+__device__ __forceinline__ float gn_block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    v = threadIdx.x < (kGnThreads >> 5) ? red[threadIdx.x] : 0.f;
+    if (warp == 0) {
+        v = warp_sum(v);
+        if (lane == 0) red[0] = v;
     }
     __syncthreads();
+    v = red[0];
+    __syncthreads();
+    return v;
+}
+
+// (b) from the (32 pixel x 4 channel) partials written by the producing conv's epilogue (conv_tc.cu, gn_partials):
+// all partials have the same count (128), so the merge is "mean of means" + Chan's between-block term, evaluated in
+// two passes over the (L2-resident) partials.  grid (groups, B)
+__global__ void __launch_bounds__(kGnThreads)
+    gn_finalize_blocks_kernel(const float* __restrict__ stats, int stats_nblk, int n_rowgroups, int blocks_per_group,
+                              float eps, float* __restrict__ mr) {
+    __shared__ float red[kGnThreads / 32];
+    const int g = blockIdx.x, n = blockIdx.y;
+    const float2* base = reinterpret_cast<const float2*>(stats) + static_cast<size_t>(n) * n_rowgroups * stats_nblk +
+                         g * blocks_per_group;
+    const int total = n_rowgroups * blocks_per_group;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < total; i += kGnThreads) {
+        const int rg = i / blocks_per_group, k = i - rg * blocks_per_group;
+        s += __ldg(base + static_cast<size_t>(rg) * stats_nblk + k).x;
+    }
+    const float mean = gn_block_sum(s, red) / static_cast<float>(total);
+    float m2 = 0.f;
+    for (int i = threadIdx.x; i < total; i += kGnThreads) {
+        const int rg = i / blocks_per_group, k = i - rg * blocks_per_group;
+        const float2 p = __ldg(base + static_cast<size_t>(rg) * stats_nblk + k);
+        const float d = p.x - mean;
+        m2 += p.y + 128.0f * d * d;
+    }
+    m2 = gn_block_sum(m2, red);
+    if (threadIdx.x == 0) {
+        mr[(n * gridDim.x + g) * 2] = mean;
+        mr[(n * gridDim.x + g) * 2 + 1] = rsqrtf(m2 / (128.0f * static_cast<float>(total)) + eps);
+    }
+}
+
+// ---------------------------------------------------------------- apply
+template <bool TF32>
+__device__ __forceinline__ void gn_store8(void* __restrict__ y, size_t off, const float (&f)[8]) {
+    if (TF32) {
+        float* yp = static_cast<float*>(y) + off;
+        reinterpret_cast<float4*>(yp)[0] =
+            make_float4(round_tf32(f[0]), round_tf32(f[1]), round_tf32(f[2]), round_tf32(f[3]));
+        reinterpret_cast<float4*>(yp)[1] =
+            make_float4(round_tf32(f[4]), round_tf32(f[5]), round_tf32(f[6]), round_tf32(f[7]));
+    } else {
+        __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y) + off;
+        *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    }
+}
+
+__device__ __forceinline__ void gn_act8(const float4 v0, const float4 v1, const float* __restrict__ ca,
+                                        const float* __restrict__ cb, int do_silu, float (&f)[8]) {
+    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const float4 a0 = *reinterpret_cast<const float4*>(ca), a1 = *reinterpret_cast<const float4*>(ca + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(cb), b1 = *reinterpret_cast<const float4*>(cb + 4);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        f[k] = fmaf(x[k], a[k], b[k]);
+        if (do_silu) f[k] = silu(f[k]);
+    }
+}
+
+// MODE 0: y[pix] = act(x[pix]);  MODE 1: the 2x2 outputs of an input pixel get its value (nearest x2);
+// MODE 2: y[opix] = mean of act over the 2x2 input window (avg_pool2d of the activated tensor).
+// grid (chunks, B); dynamic smem 2*C floats: y = act(x*ca[c] + cb[c]).  Four independent 32-byte loads in flight
+// per thread.
+constexpr int kGnUnroll = 4;
+template <bool TF32, int MODE>
+__global__ void __launch_bounds__(kGnThreads)
+    gn_apply_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C, int groups,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int ld_ss, int do_silu, const float* __restrict__ mr,
+                    void* __restrict__ y, int ld_y, int items_per_chunk) {
+    extern __shared__ __align__(16) float gn_smem[];
+    float* ca = gn_smem;
+    float* cb = gn_smem + C;
+    const int chunk = blockIdx.x, n = blockIdx.y;
     const int cpg = C / groups;
     for (int c = threadIdx.x; c < C; c += kGnThreads) {
         const int g = c / cpg;
-        float a = s_rstd[g] * (gamma ? gamma[c] : 1.f);
-        float b = (beta ? beta[c] : 0.f) - s_mean[g] * a;
+        const float mean = mr[(n * groups + g) * 2], rstd = mr[(n * groups + g) * 2 + 1];
+        float a = rstd * (gamma ? gamma[c] : 1.f);
+        float b = (beta ? beta[c] : 0.f) - mean * a;
         if (scale) {
             const float sc = 1.f + scale[static_cast<size_t>(n) * ld_ss + c];
             a *= sc;
@@ -115,29 +202,70 @@ __global__ void __launch_bounds__(kGnThreads)
     }
     __syncthreads();
     const int C8 = C >> 3;
-    const size_t row0 = static_cast<size_t>(n) * HW + static_cast<size_t>(chunk) * rows_per_chunk;
-    const int total = rows_per_chunk * C8;
-    for (int i = threadIdx.x; i < total; i += kGnThreads) {
-        const int r = i / C8, c = (i - r * C8) << 3;
-        const float* xp = x + (row0 + r) * ld_x + c;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(xp));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(xp + 4));
-        float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    // work items = (pixel, 8-channel block); pixels are input pixels (MODE 0, 1) or output pixels (MODE 2)
+    const int Wp = MODE == 2 ? W >> 1 : W;
+    const int Hp = MODE == 2 ? H >> 1 : H;
+    // (items of one image fit 32 bits: the host checks H*W*C/8 < 2^31)
+    const int npix = Hp * Wp;
+    const int item0 = chunk * items_per_chunk;
+    int item_end = item0 + items_per_chunk;
+    if (item_end > npix * C8) item_end = npix * C8;
+    const size_t img_in = static_cast<size_t>(n) * H * W;
+    for (int i0 = item0 + threadIdx.x; i0 < item_end; i0 += kGnUnroll * kGnThreads) {
+        float4 v[kGnUnroll][MODE == 2 ? 8 : 2];
+        int cc[kGnUnroll];
+        int pp[kGnUnroll];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            f[k] = fmaf(f[k], ca[c + k], cb[c + k]);
-            if (do_silu) f[k] = silu(f[k]);
+        for (int u = 0; u < kGnUnroll; ++u) {
+            const int i = i0 + u * kGnThreads;
+            if (i < item_end) {
+                const int pix = i / C8;
+                const int c = (i - pix * C8) << 3;
+                cc[u] = c, pp[u] = pix;
+                if (MODE == 2) {
+                    const int ho = pix / Wp, wo = pix - ho * Wp;
+                    const float* xp = x + (img_in + static_cast<size_t>(2 * ho) * W + 2 * wo) * ld_x + c;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float* xq = xp + (static_cast<size_t>(q >> 1) * W + (q & 1)) * ld_x;
+                        v[u][2 * q] = __ldg(reinterpret_cast<const float4*>(xq));
+                        v[u][2 * q + 1] = __ldg(reinterpret_cast<const float4*>(xq + 4));
+                    }
+                } else {
+                    const float* xp = x + (img_in + pix) * ld_x + c;
+                    v[u][0] = __ldg(reinterpret_cast<const float4*>(xp));
+                    v[u][1] = __ldg(reinterpret_cast<const float4*>(xp + 4));
+                }
+            }
         }
-        if (TF32) {
-            float* yp = static_cast<float*>(y) + (row0 + r) * ld_y + c;
-            reinterpret_cast<float4*>(yp)[0] =
-                make_float4(round_tf32(f[0]), round_tf32(f[1]), round_tf32(f[2]), round_tf32(f[3]));
-            reinterpret_cast<float4*>(yp)[1] =
-                make_float4(round_tf32(f[4]), round_tf32(f[5]), round_tf32(f[6]), round_tf32(f[7]));
-        } else {
-            __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y) + (row0 + r) * ld_y + c;
-            *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                       pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+#pragma unroll
+        for (int u = 0; u < kGnUnroll; ++u) {
+            const int i = i0 + u * kGnThreads;
+            if (i < item_end) {
+                const int c = cc[u];
+                const int pix = pp[u];
+                float f[8];
+                if (MODE == 2) {
+                    float t[4][8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) gn_act8(v[u][2 * q], v[u][2 * q + 1], ca + c, cb + c, do_silu, t[q]);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = ((t[0][k] + t[1][k]) + (t[2][k] + t[3][k])) * 0.25f;
+                    gn_store8<TF32>(y, (static_cast<size_t>(n) * npix + pix) * ld_y + c, f);
+                } else {
+                    gn_act8(v[u][0], v[u][1], ca + c, cb + c, do_silu, f);
+                    if (MODE == 0) {
+                        gn_store8<TF32>(y, (img_in + pix) * ld_y + c, f);
+                    } else {
+                        const int h = pix / W, w = pix - h * W;
+                        const size_t o = (static_cast<size_t>(n) * 4 * H * W + static_cast<size_t>(2 * h) * 2 * W + 2 * w);
+                        gn_store8<TF32>(y, o * ld_y + c, f);
+                        gn_store8<TF32>(y, (o + 1) * ld_y + c, f);
+                        gn_store8<TF32>(y, (o + 2 * W) * ld_y + c, f);
+                        gn_store8<TF32>(y, (o + 2 * W + 1) * ld_y + c, f);
+                    }
+                }
+            }
         }
     }
 }
@@ -150,19 +278,39 @@ static int pick_chunks(int B, int HW, int sm_count, int min_rows) {
     return chunks;
 }
 
+template <bool TF32, int MODE>
+static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, int groups, const float* gamma,
+                        const float* beta, const float* scale, const float* shift, int ld_ss, int do_silu,
+                        const float* mr, void* y, int ld_y, int sm_count, cudaStream_t stream) {
+    const long long npix = MODE == 2 ? static_cast<long long>(H / 2) * (W / 2) : static_cast<long long>(H) * W;
+    const long long items = npix * (C / 8);
+    // enough CTAs for ~16 per SM (4 resident), each with at least one full unrolled sweep
+    long long chunks = (16LL * sm_count + B - 1) / B;
+    const long long max_chunks = (items + kGnUnroll * kGnThreads - 1) / (kGnUnroll * kGnThreads);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    const int per = static_cast<int>((items + chunks - 1) / chunks);
+    chunks = (items + per - 1) / per;
+    const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
+    gn_apply_kernel<TF32, MODE><<<dim3(static_cast<unsigned>(chunks), B), kGnThreads, smem, stream>>>(
+        x, ld_x, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y, ld_y, per);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
 }  // namespace nlc
 
 using namespace nlc;
 
 extern "C" size_t nlc_groupnorm_ws(int B, int HW, int C, int groups) {
     (void)HW, (void)C;
-    return static_cast<size_t>(B) * kGnMaxChunks * groups * 3;
+    return static_cast<size_t>(B) * kGnMaxChunks * groups * 3 + static_cast<size_t>(B) * groups * 2;
 }
 
-extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int HW, int C, int groups, float eps,
+extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int groups, float eps,
                              const float* gamma, const float* beta, const float* scale, const float* shift,
-                             int ld_ss, int do_silu, void* y_op, int ld_y, int op_dtype, float* workspace,
-                             void* stream_) {
+                             int ld_ss, int do_silu, const float* stats, int stats_nblk, int resample, void* y_op,
+                             int ld_y, int op_dtype, float* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && x && y_op && workspace, "nlc_groupnorm: null argument");
     NLC_REQUIRE(groups >= 1 && groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0 && C % 8 == 0,
@@ -172,25 +320,39 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
                 "nlc_groupnorm: tensors must be 16-byte aligned");
     NLC_REQUIRE((scale == nullptr) == (shift == nullptr), "nlc_groupnorm: scale and shift come together");
     NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32, "nlc_groupnorm: bad op_dtype");
+    NLC_REQUIRE(static_cast<long long>(H) * W * (C / 8) < (1LL << 31), "nlc_groupnorm: image too large");
+    NLC_REQUIRE(resample >= 0 && resample <= 2 && (resample != 2 || (H % 2 == 0 && W % 2 == 0)),
+                "nlc_groupnorm: resample mode %d unsupported for %dx%d", resample, H, W);
+    const int HW = H * W;
+    float* mr = workspace + static_cast<size_t>(B) * kGnMaxChunks * groups * 3;  // [B][groups][2]
 
-    const int stat_chunks = pick_chunks(B, HW, ctx->sm_count, 1);
-    const int C4 = C / 4;
-    const int row_lanes = C4 >= kGnThreads ? 1 : kGnThreads / C4;
-    const size_t smem_stats = static_cast<size_t>(row_lanes) * C4 * sizeof(Wf);
-    gn_stats_kernel<<<dim3(stat_chunks, B), kGnThreads, smem_stats, stream>>>(x, ld_x, HW, C, groups,
-                                                                               HW / stat_chunks, workspace);
-    NLC_CHECK_LAUNCH();
-
-    const int apply_chunks = pick_chunks(B, HW, ctx->sm_count, 1);
-    const size_t smem_apply = static_cast<size_t>(2) * C * sizeof(float);
-    if (op_dtype == NLC_F32)
-        gn_apply_kernel<true><<<dim3(apply_chunks, B), kGnThreads, smem_apply, stream>>>(
-            x, ld_x, HW, C, groups, eps, gamma, beta, scale, shift, ld_ss, do_silu, y_op, ld_y, stat_chunks, workspace,
-            HW / apply_chunks);
-    else
-        gn_apply_kernel<false><<<dim3(apply_chunks, B), kGnThreads, smem_apply, stream>>>(
-            x, ld_x, HW, C, groups, eps, gamma, beta, scale, shift, ld_ss, do_silu, y_op, ld_y, stat_chunks, workspace,
-            HW / apply_chunks);
-    NLC_CHECK_LAUNCH();
-    return NLC_OK;
+    if (stats) {
+        NLC_REQUIRE(HW % 32 == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0 && stats_nblk >= C / 4,
+                    "nlc_groupnorm: conv-epilogue partials need H*W %% 32 == 0 and an 8-byte aligned buffer");
+        gn_finalize_blocks_kernel<<<dim3(groups, B), kGnThreads, 0, stream>>>(stats, stats_nblk, HW / 32,
+                                                                               (C / groups) / 4, eps, mr);
+        NLC_CHECK_LAUNCH();
+    } else {
+        const int stat_chunks = pick_chunks(B, HW, ctx->sm_count, 1);
+        const int C4 = C / 4;
+        const int row_lanes = C4 >= kGnThreads ? 1 : kGnThreads / C4;
+        const size_t smem_stats = static_cast<size_t>(row_lanes) * C4 * sizeof(Wf);
+        gn_stats_kernel<<<dim3(stat_chunks, B), kGnThreads, smem_stats, stream>>>(x, ld_x, HW, C, groups,
+                                                                                   HW / stat_chunks, workspace);
+        NLC_CHECK_LAUNCH();
+        gn_finalize_welford_kernel<<<B, 64, 0, stream>>>(workspace, stat_chunks, groups, eps, mr);
+        NLC_CHECK_LAUNCH();
+    }
+#define NLC_GN_APPLY(T, M)                                                                                        \
+    return launch_apply<T, M>(x, ld_x, B, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y_op, ld_y, \
+                              ctx->sm_count, stream)
+    if (op_dtype == NLC_F32) {
+        if (resample == 0) NLC_GN_APPLY(true, 0);
+        if (resample == 1) NLC_GN_APPLY(true, 1);
+        NLC_GN_APPLY(true, 2);
+    }
+    if (resample == 0) NLC_GN_APPLY(false, 0);
+    if (resample == 1) NLC_GN_APPLY(false, 1);
+    NLC_GN_APPLY(false, 2);
+#undef NLC_GN_APPLY
 }

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_groupnorm, run
+from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_groupnorm, run
 from .ops import Act
 
 GN_EPS = 1e-6
@@ -86,18 +86,21 @@ def _emit_block(pc, w, x, dest, emb=None):
     eng = pc.eng
     dt = eng.op_dtype
     B, H, W = x.B, x.H, x.W
-    a0 = eng.act_op("ub.a0", B, H, W, w.cin)
-    emit_groupnorm(pc, x.f32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True)
     skip_src = x.op
-    if w.up or w.down:
+    if not (w.up or w.down):
+        a0 = eng.act_op("ub.a0", B, H, W, w.cin)
+        emit_groupnorm(pc, x.f32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True)
+    else:
+        # Conv2d(up/down) with the [1,1] filter (src/edm_networks.py:85-93): nearest x2 / 2x2 average of the
+        # activated tensor, written directly by the GroupNorm apply pass; the skip branch resamples x itself
         mode = 1 if w.up else 2
-        H, W = (2 * H, 2 * W) if w.up else (H // 2, W // 2)
-        a0r = eng.act_op("ub.a0r", B, H, W, w.cin)
-        xs = eng.act_op("ub.xs", B, H, W, w.cin)
         src32 = x.f32
-        pc.add(lambda a0=a0: ops.resample_op(a0, mode, a0r, dt), "resample_op")
+        H, W = (2 * H, 2 * W) if w.up else (H // 2, W // 2)
+        a0 = eng.act_op("ub.a0r", B, H, W, w.cin)
+        emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True, resample=mode)
+        xs = eng.act_op("ub.xs", B, H, W, w.cin)
         pc.add(lambda: ops.resample(src32, mode, None, xs, dt), "resample")
-        a0, skip_src = a0r, xs
+        skip_src = xs
     rowvec = emb[:, w.emb_off:w.emb_off + w.cout] if (emb is not None and w.with_emb) else None
     res_dest = dest
     if w.attn:
@@ -158,6 +161,7 @@ class SongUNet:
         self.freqs = ((1 / 10000) ** freqs).to(eng.device)
         p = "enc.%dx%d_conv." % (R, R)
         self.cin_w, self.cin_b = eng.dev32(sd[p + "weight"]), eng.dev32(sd[p + "bias"])
+        self.cin_wp = ops.pack_conv_in_weight(self.cin_w, eng.op_dtype)
         self.enc, self.dec = [], []  # lists of (res, _BlockW, concat?)
         L = len(self.channel_mult)
         for level in range(L):
@@ -248,11 +252,11 @@ class SongUNet:
 
         def skip_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(Act(c32, c1, skip_ch[k]), Act(c16, c1, skip_ch[k]))
+            return Feat(eng.with_stats(Act(c32, c1, skip_ch[k])), Act(c16, c1, skip_ch[k]))
 
         def head_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(Act(c32, 0, c1), Act(c16, 0, c1))
+            return Feat(eng.with_stats(Act(c32, 0, c1)), Act(c16, 0, c1))
 
         aff = P["aff"]
         enc = PlanCtx(eng, B)
@@ -264,8 +268,8 @@ class SongUNet:
         enc.add(lambda: ops.linear(P["emb"], self.aw[:P["emb_n"][0]], self.ab[:P["emb_n"][0]],
                                    aff[:, :P["emb_n"][0]]), "affine (all blocks)")
         d0 = skip_feat(0)
-        enc.add(lambda: ops.conv_in_nchw(x_in, in_scale if P["use_scale"][0] else None, self.cin_w, self.cin_b,
-                                         d0.f32, d0.op, dt), "conv_in")
+        emit_conv_in(enc, x_in, lambda: in_scale if P["use_scale"][0] else None, self.cin_wp, self.cin_b,
+                     self.cin_w.shape[0], d0, w_f32=self.cin_w)
         cur = d0
         for k, (res, w) in enumerate(self.enc, start=1):
             dest = skip_feat(k)
@@ -284,7 +288,7 @@ class SongUNet:
         for i, (res, w, is_cat) in enumerate(self.dec):
             if is_cat:
                 c32, c16, _ = cat[k]
-                x = Feat(Act(c32), Act(c16))
+                x = Feat(eng.with_stats(Act(c32)), Act(c16))
                 k -= 1
             else:
                 x = cur

@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from ._lib import NLC_BF16, NLC_F32
-from .ops import Act
+from .ops import Act, GnStats
 
 PRECISIONS = {"bf16": NLC_BF16, "tf32": NLC_F32}
 
@@ -47,7 +47,10 @@ class Engine:
         self.chunk = 64 if self.op_dtype == NLC_BF16 else 32
         self._scratch = {}
         self._named = {}
+        self._named_stats = {}
         self._sizing = None
+        # GroupNorm statistics from the producing conv's epilogue (NLC_FUSE_GN_STATS=0 restores the separate pass)
+        self.fuse_gn_stats = os.environ.get("NLC_FUSE_GN_STATS", "1") != "0"
 
     # ------------------------------------------------------------------ buffers
     def plan_two_pass(self, build):
@@ -94,14 +97,37 @@ class Engine:
         return t[:n].view(*shape)
 
     def act_f32(self, tag, B, H, W, C):
-        return Act(self.scratch(tag, (B, H, W, C), torch.float32))
+        """fp32 scratch activation; when a conv epilogue can write GroupNorm partials for it, a (fresh) stats holder
+        over the tag's stats scratch comes with it."""
+        a = Act(self.scratch(tag, (B, H, W, C), torch.float32))
+        if self.fuse_gn_stats and GnStats.eligible(B, H, W, C):
+            st = self.scratch(tag + ".stats", (B * H * W // 32, C // 4, 2), torch.float32)
+            if self._sizing is None:
+                a.stats = GnStats(st)
+        return a
+
+    def with_stats(self, act):
+        """Attach the stats holder of a plan-lifetime (named) fp32 buffer to a view of it."""
+        t = act.t
+        if self._sizing is not None or not self.fuse_gn_stats or t.dtype != torch.float32:
+            return act
+        B, H, W, C = t.shape
+        if not GnStats.eligible(B, H, W, C):
+            return act
+        key = t.data_ptr()
+        st = self._named_stats.get(key)
+        if st is None:
+            st = GnStats(torch.empty((B * H * W // 32, C // 4, 2), device=self.device, dtype=torch.float32))
+            self._named_stats[key] = st
+        act.stats = st
+        return act
 
     def act_op(self, tag, B, H, W, C):
         return Act(self.scratch(tag, (B, H, W, C), self.op_torch))
 
     def bytes_allocated(self):
         tot = 0
-        for t in list(self._scratch.values()) + list(self._named.values()):
+        for t in list(self._scratch.values()) + list(self._named.values()) + [s.t for s in self._named_stats.values()]:
             tot += t.numel() * t.element_size()
         return tot
 
@@ -140,11 +166,24 @@ class PlanCtx:
 
 
 # ---------------------------------------------------------------------- block emitters
-def emit_groupnorm(pc, x32, gamma, beta, groups, eps, y_op, silu=True, scale=None, shift=None):
+def emit_groupnorm(pc, x32, gamma, beta, groups, eps, y_op, silu=True, scale=None, shift=None, resample=0):
+    """resample 1 / 2: y_op is the activated tensor nearest-x2 upsampled / 2x2 average pooled."""
     ws = pc.gn_ws(x32.B, x32.H * x32.W, x32.C, groups)
     dt = pc.eng.op_dtype
-    pc.add(lambda: ops.groupnorm(x32, groups, eps, gamma, beta, y_op, dt, ws(), silu=silu, scale=scale, shift=shift),
-           "groupnorm %dx%dx%d B%d" % (x32.H, x32.W, x32.C, x32.B))
+    fused = x32.stats is not None and x32.stats.covers(x32.c0, x32.C)
+    pc.add(lambda: ops.groupnorm(x32, groups, eps, gamma, beta, y_op, dt, ws(), silu=silu, scale=scale, shift=shift,
+                                 use_stats=fused, resample=resample),
+           "groupnorm %dx%dx%d B%d%s%s" % (x32.H, x32.W, x32.C, x32.B, " fused-stats" if fused else "",
+                                          (" up2", " pool2")[resample - 1] if resample else ""))
+
+
+def _want_stats(dest, Cout):
+    """True when the conv writing `dest` should also write GroupNorm partials (and records the coverage)."""
+    a = dest.f32
+    if a is None or a.stats is None or Cout % 4 != 0 or a.c0 % 4 != 0:
+        return False
+    a.stats.covered.append((a.c0, a.c0 + Cout))
+    return True
 
 
 def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None, out_scale=1.0, stride=1, pad=1,
@@ -159,17 +198,38 @@ def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None
     if extra_src is not None:
         srcs.append(extra_src)
         segs = segs + [(1, 0, 0, 0, extra_src.C)]
+    st = _want_stats(dest, Cout)
     pc.add(lambda: ops.conv_tc(srcs, segs, w_packed, Cout, B, Ho, Wo, dt, stride=stride, bias=bias, rowvec=rowvec,
-                               resid=resid, out_scale=out_scale, out_f32=dest.f32, out_op=dest.op),
+                               resid=resid, out_scale=out_scale, out_f32=dest.f32, out_op=dest.op, stats=st),
            "conv3x3 %dx%d %d->%d s%d B%d%s" % (Ho, Wo, src_op.C, Cout, stride, B, " +1x1" if extra_src is not None else ""))
+
+
+def emit_conv_in(pc, x_nchw, in_scale_fn, w_packed, bias, Cout, dest, w_f32=None):
+    """The network's input convolution.  bf16 mode: im2col of the NCHW image (per-sample input scale folded in)
+    followed by a K = 64 tensor-core GEMM.  tf32 (accuracy) mode: the fp32 CUDA-core kernel, so that the first layer
+    stays exact as in the reference (rounding the image itself to tf32 costs sigma_hat ~1e-4 and with it the
+    occasional time-bucket flip, tests/test_gpu_sampler.py).  `in_scale_fn()` returns the [B] scale or None."""
+    eng = pc.eng
+    dt = eng.op_dtype
+    if dt == NLC_F32 and w_f32 is not None:
+        pc.add(lambda: ops.conv_in_nchw(x_nchw, in_scale_fn(), w_f32, bias, dest.f32, dest.op, dt), "conv_in (fp32)")
+        return
+    B, _, H, W = x_nchw.shape
+    kp = eng.chunk
+    patches = eng.act_op("im2col", B, H, W, kp)
+    pc.add(lambda: ops.im2col_in(x_nchw, in_scale_fn(), patches, dt), "im2col_in %dx%d B%d" % (H, W, B))
+    st = _want_stats(dest, Cout)
+    pc.add(lambda: ops.conv_tc([patches], [(0, 0, 0, 0, kp)], w_packed, Cout, B, H, W, dt, bias=bias, out_f32=dest.f32,
+                               out_op=dest.op, stats=st), "conv_in %dx%d ->%d B%d" % (H, W, Cout, B))
 
 
 def emit_conv1x1(pc, src_op, w_packed, bias, Cout, dest, resid=None, out_scale=1.0):
     dt = pc.eng.op_dtype
     B, H, W = src_op.B, src_op.H, src_op.W
     segs = [(0, 0, 0, 0, src_op.C)]
+    st = _want_stats(dest, Cout)
     pc.add(lambda: ops.conv_tc([src_op], segs, w_packed, Cout, B, H, W, dt, bias=bias, resid=resid,
-                               out_scale=out_scale, out_f32=dest.f32, out_op=dest.op),
+                               out_scale=out_scale, out_f32=dest.f32, out_op=dest.op, stats=st),
            "conv1x1 %dx%d %d->%d B%d" % (H, W, src_op.C, Cout, B))
 
 

@@ -22,7 +22,7 @@ class _Stats:
 STATS = _Stats()
 
 
-def _timed(name):
+def _timed(name, name_detail=None):
     """Profiling aid (scripts/step_profile.py): bracket the wrapped launch with CUDA events on the launching
     stream when STATS.op_timer is a list.  No effect otherwise."""
     def deco(fn):
@@ -34,7 +34,7 @@ def _timed(name):
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            t.append((name, e0, e1, 0.0))
+            t.append((name if not callable(name_detail) else name + name_detail(*a, **k), e0, e1, 0.0))
             return r
         wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
         return wrapped
@@ -59,12 +59,13 @@ class Act:
     `ld` (= Ctot) is the pixel pitch in elements, so a view can be one half of a concatenation buffer
     (torch.cat at src/unet_ddim.py:353 never materialises separately)."""
 
-    __slots__ = ("t", "c0", "C")
+    __slots__ = ("t", "c0", "C", "stats")
 
-    def __init__(self, t, c0=0, C=None):
+    def __init__(self, t, c0=0, C=None, stats=None):
         assert t.dim() == 4 and t.is_contiguous(), "Act wants a contiguous [B,H,W,C] tensor"
         self.t, self.c0 = t, c0
         self.C = t.shape[3] - c0 if C is None else C
+        self.stats = stats  # GnStats of the underlying buffer (fp32 activations that a GroupNorm may read)
 
     B = property(lambda s: s.t.shape[0])
     H = property(lambda s: s.t.shape[1])
@@ -74,11 +75,34 @@ class Act:
     ptr = property(lambda s: s.t.data_ptr() + s.c0 * s.t.element_size())
 
     def slice(self, c0, C):
-        return Act(self.t, self.c0 + c0, C)
+        return Act(self.t, self.c0 + c0, C, self.stats)
 
     def dense(self):
         """[B,H,W,C] torch view (for tests)."""
         return self.t[..., self.c0:self.c0 + self.C]
+
+
+class GnStats:
+    """GroupNorm partial statistics of one fp32 NHWC buffer, written by the epilogues of the convolutions that
+    produce it (nlc_conv_desc.stats): `t` is [B*H*W/32, Ctot/4, 2] (mean, M2 per 32 pixels x 4 channels);
+    `covered` records, at plan time, which channel ranges have a producer that writes them."""
+
+    __slots__ = ("t", "covered")
+
+    def __init__(self, t):
+        self.t, self.covered = t, []
+
+    def covers(self, c0, C):
+        need = c0
+        for lo, hi in sorted(self.covered):
+            if lo <= need < hi:
+                need = hi
+        return need >= c0 + C
+
+    @staticmethod
+    def eligible(B, H, W, C):
+        """What the conv epilogue needs: a tile inside one image (H*W >= 128) and whole 4-channel blocks."""
+        return H * W >= 128 and (H * W) % 32 == 0 and C % 4 == 0
 
 
 def round_tf32_(w):
@@ -107,7 +131,7 @@ def taps3x3(src, c0, nch, pad=1):
 
 
 def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, rowvec=None, resid=None,
-            out_scale=1.0, out_f32=None, out_op=None):
+            out_scale=1.0, out_f32=None, out_op=None, stats=False):
     """Tensor-core implicit GEMM (nlc_conv_tc). srcs: list[Act]; segs: list of (src, dh, dw, c0, nch);
     resid/out_f32/out_op: Act or None; rowvec: [B, Cout] fp32 tensor."""
     d = _lib.ConvDesc()
@@ -131,6 +155,9 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.out_f32, d.ld_out_f32 = out_f32.ptr, out_f32.ld
     if out_op is not None:
         d.out_op, d.ld_out_op = out_op.ptr, out_op.ld
+    if stats:  # GroupNorm partials of the fp32 output, at its channel offset inside the buffer's stats tensor
+        st = out_f32.stats.t
+        d.stats, d.stats_nblk = st.data_ptr() + (out_f32.c0 // 4) * 8, st.shape[1]
     timer, optimer = STATS.conv_timer, STATS.op_timer
     if timer is not None or optimer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -160,6 +187,24 @@ def conv_in_nchw(x_nchw, in_scale, weight, bias, out_f32, out_op, op_dtype):
     STATS.launches += 1
 
 
+@_timed("im2col_in")
+def im2col_in(x_nchw, in_scale, patches, op_dtype):
+    """NCHW fp32 image -> [B,H,W,64|32] K-major 3x3 patches in the operand dtype (nlc_im2col_in)."""
+    B, Cin, H, W = x_nchw.shape
+    _lib.check(_lib.lib().nlc_im2col_in(_ctx(x_nchw), _p(x_nchw), _p(in_scale), B, Cin, H, W, C.c_void_p(patches.ptr),
+                                        op_dtype, _stream()))
+    STATS.launches += 1
+
+
+def pack_conv_in_weight(w, op_dtype):
+    """torch [Cout,Cin,3,3] -> [Cout, 64|32]: column tap*Cin + ci, zero-padded to one 128-byte K row."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    kp = 64 if op_dtype == NLC_BF16 else 32
+    k = torch.zeros(Cout, kp, dtype=torch.float32, device=w.device)
+    k[:, :9 * Cin] = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, -1)
+    return k.to(torch.bfloat16).contiguous() if op_dtype == NLC_BF16 else round_tf32_(k)
+
+
 @_timed("conv_out_nchw")
 def conv_out_nchw(x_op, op_dtype, weight, bias, out_nchw):
     """Direct 3x3 conv NHWC operand -> NCHW fp32 (nlc_conv_out_nchw)."""
@@ -174,14 +219,23 @@ def groupnorm_ws(B, HW, C, groups):
     return int(_lib.lib().nlc_groupnorm_ws(B, HW, C, groups))
 
 
-@_timed("groupnorm")
-def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=None, shift=None):
-    """GroupNorm (+scale/shift, +SiLU) of fp32 NHWC `x` (Act) into operand `y_op` (Act)."""
+@_timed("groupnorm", lambda x, *a, **k: " %dx%d C%d%s%s" % (x.H, x.W, x.C, " fused" if k.get("use_stats") else "",
+                                                         " rs%d" % k["resample"] if k.get("resample") else ""))
+def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=None, shift=None, use_stats=False,
+              resample=0):
+    """GroupNorm (+scale/shift, +SiLU) of fp32 NHWC `x` (Act) into operand `y_op` (Act).  use_stats: merge the
+    partials the producing convolutions wrote (x.stats) instead of a statistics pass; resample 1/2: write the
+    activated tensor nearest-x2 upsampled / 2x2 average pooled."""
     ld_ss = scale.stride(0) if scale is not None else 0
+    st_ptr, st_nblk = None, 0
+    if use_stats:
+        st = x.stats.t
+        st_ptr, st_nblk = C.c_void_p(st.data_ptr() + (x.c0 // 4) * 8), st.shape[1]
     _lib.check(_lib.lib().nlc_groupnorm(
-        _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H * x.W, x.C, groups, eps, _p(gamma), _p(beta), _p(scale),
-        _p(shift), ld_ss, 1 if silu else 0, C.c_void_p(y_op.ptr), y_op.ld, op_dtype, _p(ws), _stream()))
-    STATS.launches += 2
+        _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, groups, eps, _p(gamma), _p(beta), _p(scale),
+        _p(shift), ld_ss, 1 if silu else 0, st_ptr, st_nblk, resample, C.c_void_p(y_op.ptr), y_op.ld, op_dtype, _p(ws),
+        _stream()))
+    STATS.launches += 2 if use_stats else 3
 
 
 @_timed("resample")

@@ -19,7 +19,7 @@ import math
 import torch
 
 from . import ops
-from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_groupnorm, run
+from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_groupnorm, run
 from .ops import Act
 
 GN_EPS = 1e-5  # GroupNorm32 default, src/nn_util.py:93-100
@@ -82,18 +82,21 @@ def _emit_resblock(pc, w, x, dest, emb=None):
     eng = pc.eng
     dt = eng.op_dtype
     B, H, W = x.B, x.H, x.W
-    a1 = eng.act_op("rb.a1", B, H, W, w.cin)
-    emit_groupnorm(pc, x.f32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True)
     resid = x.f32
-    if w.updown is not None:
+    if w.updown is None:
+        a1 = eng.act_op("rb.a1", B, H, W, w.cin)
+        emit_groupnorm(pc, x.f32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True)
+    else:
+        # h_upd / x_upd (src/unet_adm.py:236-243): the activated tensor is written already resampled by the
+        # GroupNorm apply pass; x itself is resampled in fp32 for the residual add
         mode = 1 if w.updown == "up" else 2
-        H, W = (2 * H, 2 * W) if mode == 1 else (H // 2, W // 2)
-        a1r = eng.act_op("rb.a1r", B, H, W, w.cin)
-        xr = eng.act_f32("rb.xr", B, H, W, w.cin)
         src32 = x.f32
-        pc.add(lambda a1=a1: ops.resample_op(a1, mode, a1r, dt), "resample_op (h_upd)")
+        H, W = (2 * H, 2 * W) if mode == 1 else (H // 2, W // 2)
+        a1 = eng.act_op("rb.a1r", B, H, W, w.cin)
+        emit_groupnorm(pc, src32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True, resample=mode)
+        xr = eng.act_f32("rb.xr", B, H, W, w.cin)
         pc.add(lambda: ops.resample(src32, mode, xr, None, dt), "resample (x_upd)")
-        a1, resid = a1r, xr
+        resid = xr
     h = eng.act_f32("rb.h", B, H, W, w.cout)
     rowvec = scale = shift = None
     if emb is not None and w.emb_w is not None:
@@ -166,6 +169,7 @@ class UNetModel:
         # timestep_embedding (src/nn_util.py:113-116): exp(-log(1e4) * arange(half) / half), cos || sin
         self.freqs = torch.exp(-math.log(10000) * torch.arange(0, half, dtype=torch.float32) / half).to(eng.device)
         self.cin_w, self.cin_b = eng.dev32(sd["input_blocks.0.0.weight"]), eng.dev32(sd["input_blocks.0.0.bias"])
+        self.cin_wp = ops.pack_conv_in_weight(self.cin_w, eng.op_dtype)
 
         def attn(p, heads):
             return _AttnW(eng, sd, p, heads, self.num_head_channels, self.use_new_attention_order)
@@ -330,15 +334,15 @@ class UNetModel:
 
         def skip_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(Act(c32, c1, self.skip_ch[k]), Act(c16, c1, self.skip_ch[k]))
+            return Feat(eng.with_stats(Act(c32, c1, self.skip_ch[k])), Act(c16, c1, self.skip_ch[k]))
 
         def head_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(Act(c32, 0, c1), Act(c16, 0, c1))
+            return Feat(eng.with_stats(Act(c32, 0, c1)), Act(c16, 0, c1))
 
         def cat_feat(k):
             c32, c16, _ = cat[k]
-            return Feat(Act(c32), Act(c16))
+            return Feat(eng.with_stats(Act(c32)), Act(c16))
 
         emb = P["emb"]
         enc = PlanCtx(eng, B)
@@ -351,8 +355,8 @@ class UNetModel:
         enc.add(lambda: ops.linear(P["temb"], self.ew[:P["emb_n"][0]], self.eb[:P["emb_n"][0]],
                                    emb[:, :P["emb_n"][0]], act_in=1))
         d0 = skip_feat(0)
-        enc.add(lambda: ops.conv_in_nchw(x_in, in_scale if P["use_scale"][0] else None, self.cin_w, self.cin_b,
-                                         d0.f32, d0.op, dt))
+        emit_conv_in(enc, x_in, lambda: in_scale if P["use_scale"][0] else None, self.cin_wp, self.cin_b,
+                     self.cin_w.shape[0], d0, w_f32=self.cin_w)
         cur = d0
         for k, blk in enumerate(self.input_blocks, start=1):
             cur = self._emit_block(enc, blk, cur, skip_feat(k), emb, B)

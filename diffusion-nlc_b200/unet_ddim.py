@@ -13,7 +13,7 @@ import math
 import torch
 
 from . import ops
-from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_groupnorm, run
+from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_groupnorm, run
 from .ops import Act
 
 GN_EPS = 1e-6  # Normalize(), src/unet_ddim.py:54-55
@@ -128,6 +128,7 @@ class UNetModel:
         self.t0w, self.t0b = eng.dev32(sd["temb.dense.0.weight"]), eng.dev32(sd["temb.dense.0.bias"])
         self.t1w, self.t1b = eng.dev32(sd["temb.dense.1.weight"]), eng.dev32(sd["temb.dense.1.bias"])
         self.cin_w, self.cin_b = eng.dev32(sd["conv_in.weight"]), eng.dev32(sd["conv_in.bias"])
+        self.cin_wp = ops.pack_conv_in_weight(self.cin_w, eng.op_dtype)
         half = self.ch // 2
         # get_timestep_embedding (src/unet_ddim.py:38-41): exp(arange(half) * -(log(1e4)/(half-1))) in fp32
         emb = math.log(10000) / (half - 1)
@@ -234,15 +235,15 @@ class UNetModel:
         def skip_feat(k):
             c32, c16, c1 = cat[k]
             c_skip = hs_shapes[k][0]
-            return Feat(Act(c32, c1, c_skip), Act(c16, c1, c_skip))
+            return Feat(eng.with_stats(Act(c32, c1, c_skip)), Act(c16, c1, c_skip))
 
         def head_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(Act(c32, 0, c1), Act(c16, 0, c1))
+            return Feat(eng.with_stats(Act(c32, 0, c1)), Act(c16, 0, c1))
 
         def cat_feat(k):
             c32, c16, _ = cat[k]
-            return Feat(Act(c32), Act(c16))
+            return Feat(eng.with_stats(Act(c32)), Act(c16))
 
         # ---- encoder (shared by forward and encode)
         enc = PlanCtx(eng, B)
@@ -257,8 +258,8 @@ class UNetModel:
         enc.add(lambda: ops.linear(P["temb"], self.tpw[:P["tp_n"][0]], self.tpb[:P["tp_n"][0]],
                                    tp[:, :P["tp_n"][0]], act_in=1))
         P["use_scale"] = [False]
-        enc.add(lambda: ops.conv_in_nchw(x_in, in_scale if P["use_scale"][0] else None, self.cin_w, self.cin_b,
-                                         d0.f32, d0.op, dt))
+        emit_conv_in(enc, x_in, lambda: in_scale if P["use_scale"][0] else None, self.cin_wp, self.cin_b,
+                     self.cin_w.shape[0], d0, w_f32=self.cin_w)
         k = 0
         cur = d0
         res = R

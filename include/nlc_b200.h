@@ -98,6 +98,11 @@ typedef struct {
     int ld_out_op;
     int out_head_split; /* >0: output row (n,ho,wo) is written at pixel (n,wo), channel offset ho*out_head_split
                            (merges attention heads back into [B,T,C]); 0: dense NHWC                  */
+    float* stats;       /* optional: GroupNorm partials of the fp32 result, written by the epilogue so that the next
+                           GroupNorm (nlc_groupnorm with `stats`) skips its statistics pass.  Layout
+                           [B*Ho*Wo/32][stats_nblk][2] = (mean, M2) over 32 consecutive pixels x 4 channels; the
+                           pointer is pre-offset to this output's first 4-channel block.  Needs Ho*Wo >= 128. */
+    int stats_nblk;     /* 4-channel blocks per pixel group in the stats buffer (= its total channels / 4)    */
 } nlc_conv_desc;
 
 int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);
@@ -109,6 +114,12 @@ int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);
 int nlc_conv_in_nchw(nlc_ctx* ctx, const float* x_nchw, const float* in_scale /*[B] or NULL*/, int B, int Cin, int H,
                      int W, const float* weight, const float* bias, int Cout, float* out_f32, int ld_out_f32,
                      void* out_op, int ld_out_op, int op_dtype, void* stream);
+/* The input convolution on the tensor cores: patches[(n,h,w), tap*Cin + ci] = in_scale[n] * x[n, ci, h+kh-1, w+kw-1]
+ * (zero outside the image), one 128-byte K row per pixel (64 bf16 / 32 tf32-rounded fp32 elements, zero tail), to be
+ * multiplied by nlc_conv_tc as a 1x1 convolution with the 3x3 weights packed [Cout][tap*Cin + ci] (same conv as
+ * nlc_conv_in_nchw; src/unet_ddim.py:301, src/unet_adm.py:480, src/edm_networks.py:786).  Cin <= 3. */
+int nlc_im2col_in(nlc_ctx* ctx, const float* x_nchw, const float* in_scale /*[B] or NULL*/, int B, int Cin, int H,
+                  int W, void* patches_op, int op_dtype, void* stream);
 int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int Cin, int H, int W,
                       const float* weight, const float* bias, int Cout, float* out_nchw, void* stream);
 
@@ -116,11 +127,16 @@ int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, in
  * Replaces Normalize/GroupNorm32 + nonlinearity (src/unet_ddim.py:54-55,139-146; src/nn_util.py:17-19;
  * src/unet_adm.py:236-252).  Statistics are fp32 Welford partials per (sample, pixel chunk, group), merged by
  * the apply pass.  x is NHWC fp32 with C channels in `groups` groups.
- *   y = ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c]  -> SiLU (if silu) -> operand dtype */
-int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int HW, int C, int groups, float eps,
+ *   y = ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c]  -> SiLU (if silu) -> operand dtype
+ * `stats` != NULL: the statistics pass is skipped; the per-(32 pixel, 4 channel) partials the producing
+ * nlc_conv_tc wrote are merged instead (x is then read exactly once).  `resample` applies ADM's resblock_updown
+ * h_upd (src/unet_adm.py:236-243) / the EDM block's conv0 resampling (src/edm_networks.py:85-93) to the activated
+ * tensor while it is written: y is [B,2H,2W,C] (1) or [B,H/2,W/2,C] (2). */
+int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int groups, float eps,
                   const float* gamma, const float* beta, const float* scale, const float* shift, int ld_ss,
-                  int silu, void* y_op, int ld_y, int op_dtype, float* workspace /* >= nlc_groupnorm_ws floats */,
-                  void* stream);
+                  int silu, const float* stats /* nullable: partials written by nlc_conv_tc */, int stats_nblk,
+                  int resample /* 0 none, 1 nearest x2, 2 avgpool 2x2 of the activated tensor */, void* y_op,
+                  int ld_y, int op_dtype, float* workspace /* >= nlc_groupnorm_ws floats */, void* stream);
 size_t nlc_groupnorm_ws(int B, int HW, int C, int groups);
 
 /* fp32 NHWC -> operand dtype, optionally nearest-neighbour x2 upsampled (Upsample.forward,

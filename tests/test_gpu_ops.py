@@ -223,3 +223,84 @@ def test_resample_and_boundary_convs(dev, prec):
     out = torch.zeros(B, 3, R, R, device=dev)
     ops.conv_out_nchw(yo, dt, w2, b2, out)
     assert _rel(out, F.conv2d(yo.t.float().permute(0, 3, 1, 2), w2, b2, padding=1)) < 5e-6
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 256, 128), (3, 64, 64, 128, 128, 128), (1, 256, 256, 64, 192, 64),
+                                   (2, 32, 8, 64, 384, 128)])
+def test_groupnorm_from_conv_epilogue_statistics(dev, prec, tol, shape):
+    """The conv epilogue's per-(32 px, 4 ch) partials + nlc_groupnorm(stats=...) == F.group_norm of the conv output,
+    including a GroupNorm over a *concatenation* whose two halves were written by different convolutions (group
+    boundaries straddle the seam: 256+128 channels in 32 groups of 12) and a large common offset (mean >> std)."""
+    from nlc_b200 import ops
+    B, H, W, Cin, Cout, Cb = shape
+    dt = _dt(prec)
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(9)
+    x = _rnd(torch.randn(B, Cin, H, W, generator=g).to(dev), dt)
+    Ct = Cout + Cb  # second producer: a 1x1 conv writing the tail channels of the same buffer
+    w1 = _rnd((torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev), dt)
+    w2 = _rnd((torch.randn(Cb, Cin, 1, 1, generator=g) / Cin ** 0.5).to(dev), dt)
+    b1 = (torch.randn(Cout, generator=g) + 30.0).to(dev)  # large mean
+    b2 = torch.randn(Cb, generator=g).to(dev)
+    ref_t = torch.cat([F.conv2d(x, w1, b1, padding=1), F.conv2d(x, w2, b2)], dim=1)
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(tdt))
+    buf = torch.zeros(B, H, W, Ct, device=dev)
+    st = ops.GnStats(torch.zeros(B * H * W // 32, Ct // 4, 2, device=dev))
+    o1, o2 = ops.Act(buf, 0, Cout, st), ops.Act(buf, Cout, Cb, st)
+    ops.conv_tc([xa], ops.taps3x3(0, 0, Cin), ops.pack_conv_weight(w1, dt), Cout, B, H, W, dt, bias=b1, out_f32=o1, stats=True)
+    ops.conv_tc([xa], [(0, 0, 0, 0, Cin)], ops.pack_conv_weight(w2, dt), Cb, B, H, W, dt, bias=b2, out_f32=o2, stats=True)
+    assert _rel(buf.permute(0, 3, 1, 2), ref_t) < 5e-5
+    gam, bet = torch.randn(Ct, generator=g).to(dev), torch.randn(Ct, generator=g).to(dev)
+    ref = F.silu(F.group_norm(buf.permute(0, 3, 1, 2), 32, gam, bet, eps=1e-5))
+    y = ops.Act(torch.zeros(B, H, W, Ct, device=dev, dtype=tdt))
+    ws = torch.zeros(ops.groupnorm_ws(B, H * W, Ct, 32), device=dev)
+    ops.groupnorm(ops.Act(buf, 0, Ct, st), 32, 1e-5, gam, bet, y, dt, ws, silu=True, use_stats=True)
+    assert _rel(y.t.float().permute(0, 3, 1, 2), ref) < tol
+    # the statistics themselves: merged partials vs torch, per (sample, group)
+    mr = ws[B * 64 * 32 * 3:].view(B, 32, 2)
+    xg = buf.permute(0, 3, 1, 2).reshape(B, 32, -1).double()
+    assert (mr[:, :, 0].double() - xg.mean(2)).abs().max() < 1e-4 * xg.abs().max()
+    assert ((mr[:, :, 1].double() - (xg.var(2, unbiased=False) + 1e-5).rsqrt()) / mr[:, :, 1].double()).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_groupnorm_with_fused_resample(dev, prec, tol, mode):
+    """resample=1: nearest x2 of silu(gn(x)); resample=2: avg_pool2d(silu(gn(x)), 2) (ADM resblock_updown h_upd)."""
+    from nlc_b200 import ops
+    dt = _dt(prec)
+    B, H, W, C = 3, 16, 8, 128
+    g = torch.Generator().manual_seed(10)
+    x = torch.randn(B, C, H, W, generator=g).to(dev) * 2 + 0.3
+    gam, bet = torch.randn(C, generator=g).to(dev), torch.randn(C, generator=g).to(dev)
+    sc, sh = torch.randn(B, C, generator=g).to(dev) * 0.3, torch.randn(B, C, generator=g).to(dev)
+    a = F.silu(F.group_norm(x, 32, gam, bet, eps=1e-5) * (1 + sc[:, :, None, None]) + sh[:, :, None, None])
+    ref = F.interpolate(a, scale_factor=2.0, mode="nearest") if mode == 1 else F.avg_pool2d(a, 2)
+    Ho, Wo = ref.shape[2:]
+    y = ops.Act(torch.zeros(B, Ho, Wo, C, device=dev, dtype=ops.OP_DTYPES[dt]))
+    ws = torch.zeros(ops.groupnorm_ws(B, H * W, C, 32), device=dev)
+    ops.groupnorm(ops.Act(x.permute(0, 2, 3, 1).contiguous()), 32, 1e-5, gam, bet, y, dt, ws, silu=True, scale=sc, shift=sh,
+                  resample=mode)
+    assert _rel(y.t.float().permute(0, 3, 1, 2), ref) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 6e-4)])
+def test_input_conv_on_tensor_cores(dev, prec, tol):
+    """im2col (per-sample input scale folded in) + K=64|32 GEMM == F.conv2d(x*scale, w, b); tolerance = one operand
+    rounding of the 27-term dot product."""
+    from nlc_b200 import ops
+    dt = _dt(prec)
+    g = torch.Generator().manual_seed(12)
+    B, H, W, Cout = 3, 32, 16, 128
+    x = torch.randn(B, 3, H, W, generator=g).to(dev) * 3
+    sc = (torch.rand(B, generator=g) + 0.1).to(dev)
+    w = (torch.randn(Cout, 3, 3, 3, generator=g) / 27 ** 0.5).to(dev)
+    b = torch.randn(Cout, generator=g).to(dev)
+    ref = F.conv2d(x * sc.view(-1, 1, 1, 1), w, b, padding=1)
+    kp = 64 if prec == "bf16" else 32
+    patches = ops.Act(torch.empty(B, H, W, kp, device=dev, dtype=ops.OP_DTYPES[dt]))
+    ops.im2col_in(x, sc, patches, dt)
+    out = ops.Act(torch.zeros(B, H, W, Cout, device=dev))
+    ops.conv_tc([patches], [(0, 0, 0, 0, kp)], ops.pack_conv_in_weight(w, dt), Cout, B, H, W, dt, bias=b, out_f32=out)
+    assert _rel(out.t.permute(0, 3, 1, 2), ref) < tol
