@@ -1,6 +1,8 @@
 // Context lifetime and error reporting of the C ABI (include/nlc_b200.h).
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace nlc {
@@ -51,6 +53,8 @@ nlc_ctx* nlc_create(int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->encode_tiled = reinterpret_cast<nlc::encode_tiled_fn>(fn);
+    const char* e = getenv("NLC_CTA_PAIRS");
+    ctx->use_cta_pairs = !(e && e[0] == '0');
     return ctx;
 }
 

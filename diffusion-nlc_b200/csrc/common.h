@@ -44,4 +44,5 @@ struct nlc_ctx {
     int device;
     int sm_count;
     nlc::encode_tiled_fn encode_tiled;
+    int use_cta_pairs;  // tcgen05 cta_group::2 conv kernel for large layers (NLC_CTA_PAIRS=0 disables)
 };

@@ -12,8 +12,8 @@
 //     convolutions use the tensor map's traversal stride, and the nine taps re-read the brick from L2;
 //   * a ResNet block's 1x1 shortcut and a concat are just more K segments over another tensor map.
 //
-// One persistent CTA per SM, 6 warps:  warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
-// warps 2-5 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype stores).
+// One persistent CTA per SM, 10 warps:  warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
+// warps 2-9 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype stores).
 // smem ring of STAGES x (16 KB A + BLOCK_N*128 B W); two TMEM accumulators so the epilogue of tile i
 // overlaps the main loop of tile i+1.
 #include "common.h"
@@ -24,7 +24,8 @@ namespace nlc {
 constexpr int kBlockM = 128;
 constexpr int kChunkBytes = 128;                      // one swizzle row = one K chunk
 constexpr int kAStageBytes = kBlockM * kChunkBytes;   // 16 KB
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: they split the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 
 struct ConvSegDev {
     int map, dh, dw, c0, nchunk;
@@ -37,6 +38,7 @@ struct ConvKParams {
     int BW, BH, BN;
     int tiles_w, tiles_h, tiles_n;
     int num_m_tiles, num_n_tiles, num_tiles;
+    int num_m_units;  // M tiles (1-CTA kernel) or M tile pairs (CTA-pair kernel); num_tiles = num_m_units * num_n_tiles
     int Cout, nseg, total_chunks;
     ConvSegDev seg[NLC_MAX_SEG];
     const float* bias;
@@ -55,14 +57,17 @@ struct ConvKParams {
     int stats_nblk;
 };
 
-template <int BLOCK_N>
+// CTA2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128
+// rows of A and one half of the B tile, so the weights cross L2->SM once per pair.
+template <int BLOCK_N, bool CTA2>
 struct ConvCfg {
-    static constexpr int kBStageBytes = BLOCK_N * kChunkBytes;
+    static constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // B rows staged by this CTA
+    static constexpr int kBStageBytes = kBRows * kChunkBytes;
     static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kStages = CTA2 ? (BLOCK_N == 256 ? 6 : 8) : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
     static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
     static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
-    static constexpr int kEpiBytes = 4 * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
+    static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: alignment slack
 };
 
@@ -117,11 +122,16 @@ __device__ __forceinline__ void gn_partials(const float (&f)[32], int lane, floa
     }
 }
 
-template <int BLOCK_N, bool TF32>
+template <int BLOCK_N, bool TF32, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N>;
+    using Cfg = ConvCfg<BLOCK_N, CTA2>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kChunkElems = TF32 ? 32 : 64;
+    // work units: tiles for the 1-CTA kernel, 256-row tile pairs for the CTA-pair kernel (both CTAs of a pair walk
+    // the same sequence; CTA `rank` owns M tile 2*unit + rank)
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const int unit0 = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int unit_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -146,13 +156,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty[a], CTA2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
         }
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    if (warp == 2) {
+        if (CTA2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot); else tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    }
     tc_fence_before_sync();
     __syncthreads();
+    if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything remote touches them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -163,9 +176,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-                const int n_tile = tile / p.num_m_tiles;
-                const int m_tile = tile - n_tile * p.num_m_tiles;
+            for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+                const int n_tile = unit / p.num_m_units;
+                const int m_tile = CTA2 ? 2 * (unit - n_tile * p.num_m_units) + static_cast<int>(rank)
+                                        : unit - n_tile * p.num_m_units;
                 const int tn = m_tile / tiles_per_img;
                 const int rem = m_tile - tn * tiles_per_img;
                 const int th = rem / p.tiles_w;
@@ -178,11 +192,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
                         uint8_t* sb = sa + kAStageBytes;
-                        mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-                        tma_load_4d(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
-                                    h0 + sg.dh, n0);
-                        tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
-                                    p.w_batched ? th : 0, p.w_batched ? n0 : 0);
+                        if (CTA2) {
+                            // both CTAs' bytes land on the leader's barrier (a tile past the end is all zero fill)
+                            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                            tma_load_4d_pair(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
+                                             h0 + sg.dh, n0);
+                            tma_load_4d_pair(sb, &p.mapB, &full[stage], kchunk * kChunkElems,
+                                             n_tile * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows, 0, 0);
+                        } else {
+                            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                            tma_load_4d(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
+                                        h0 + sg.dh, n0);
+                            tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
+                                        p.w_batched ? th : 0, p.w_batched ? n0 : 0);
+                        }
                         ++kchunk;
                         if (++stage == kStages) {
                             stage = 0;
@@ -194,13 +217,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, kBlockM, BLOCK_N);
+        if (lane == 0 && rank == 0) {  // the pair's leader issues for both CTAs
+            constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, CTA2 ? 2 * kBlockM : kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -212,18 +235,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     const uint64_t bdesc = umma_desc_sw128(sa + kAStageBytes);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // 4 x 32 B K-steps inside the 128 B swizzle row
-                        if (TF32)
+                        if (CTA2) {
+                            if (TF32)
+                                umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                            else
+                                umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                        } else if (TF32) {
                             umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-                        else
+                        } else {
                             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                        }
                     }
-                    umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
+                    // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+                    if (CTA2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+                if (CTA2) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);  // accumulator -> epilogue(s)
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -235,7 +265,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // (16-byte chunks XOR-swizzled by the row, conflict-free both ways) so that every load / store instruction
         // touches 4 full 128-byte rows instead of 32 partial ones.
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
-        float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes) + quad * 1024;
+        const int half = (warp - 2) >> 2;  // the two warps of a lane quarter take alternate 32-column chunks
+        float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes) + (warp - 2) * 1024;
         const int brick = p.BW * p.BH;
         const int row = quad * 32 + lane;
         const int bn = row / brick;
@@ -249,9 +280,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int sub_r8 = lane >> 2, sub_c8 = lane & 3;  // bf16 pattern: 8 rows x 4 (8-channel) chunks
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-            const int n_tile = tile / p.num_m_tiles;
-            const int m_tile = tile - n_tile * p.num_m_tiles;
+        for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+            const int n_tile = unit / p.num_m_units;
+            const int m_tile = CTA2 ? 2 * (unit - n_tile * p.num_m_units) + static_cast<int>(rank)
+                                    : unit - n_tile * p.num_m_units;
             const int tn = m_tile / tiles_per_img;
             const int rem = m_tile - tn * tiles_per_img;
             const int th = rem / p.tiles_w;
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 32) {
+            for (int c = 32 * half; c < BLOCK_N; c += 32 * (kEpiWarps / 4)) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(taddr + c, v);
                 const int col0 = n_tile * BLOCK_N + c;
@@ -318,7 +350,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
                 }
-                if (p.stats) gn_partials(f, lane, p.stats + (((pix0 + lane) >> 5) * p.stats_nblk + (col0 >> 2)) * 2);
+                if (p.stats && vmask == 0xffffffffu)  // (the odd tail tile of a CTA pair is entirely out of range)
+                    gn_partials(f, lane, p.stats + (((pix0 + lane) >> 5) * p.stats_nblk + (col0 >> 2)) * 2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
@@ -366,7 +399,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) {
+                if (CTA2) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
@@ -374,24 +409,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
     tc_fence_before_sync();
     __syncthreads();
+    if (CTA2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the peer still uses its smem / barriers
     if (warp == 2) {
         tc_fence_after_sync();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        if (CTA2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-template <int BLOCK_N, bool TF32>
+template <int BLOCK_N, bool TF32, bool CTA2>
 static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N>;
+    using Cfg = ConvCfg<BLOCK_N, CTA2>;
     static bool configured = false;
     if (!configured) {
-        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            Cfg::kSmemBytes));
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, TF32, CTA2>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
-    conv_tc_kernel<BLOCK_N, TF32><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+    if (CTA2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, TF32, CTA2>, p));
+    } else {
+        conv_tc_kernel<BLOCK_N, TF32, CTA2><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+    }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -440,8 +488,13 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
         block_n = 256;
     else if (d->Cout % 128 == 0 && p.num_m_tiles * (d->Cout / 128) >= ctx->sm_count)
         block_n = 128;
+    // CTA pairs (256-row tiles, the B tile shared by two SMs) when there is at least one pair tile per SM pair;
+    // the batched right-hand operand of the attention GEMMs differs per M tile and stays on the 1-CTA kernel
+    const bool pair = ctx->use_cta_pairs && d->wbatched.ptr == nullptr && block_n >= 128 &&
+                      ((p.num_m_tiles + 1) / 2) * (d->Cout / block_n) >= ctx->sm_count / 2;
     p.num_n_tiles = d->Cout / block_n;
-    p.num_tiles = p.num_m_tiles * p.num_n_tiles;
+    p.num_m_units = pair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
+    p.num_tiles = p.num_m_units * p.num_n_tiles;
 
     int ktot = 0;
     p.nseg = d->nseg;
@@ -500,7 +553,7 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
         NLC_REQUIRE(d->weight && (reinterpret_cast<uintptr_t>(d->weight) & 15) == 0, "nlc_conv_tc: weight unaligned");
         cuuint64_t gdim[4] = {(cuuint64_t)ktot, (cuuint64_t)d->Cout, 1, 1};
         cuuint64_t gstr[3] = {(cuuint64_t)ktot * esz, (cuuint64_t)ktot * esz * d->Cout, (cuuint64_t)ktot * esz * d->Cout};
-        cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)block_n, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)(pair ? block_n / 2 : block_n), 1, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = ctx->encode_tiled(&p.mapB, dt, 4, const_cast<void*>(d->weight), gdim, gstr, box, estr,
                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -520,13 +573,22 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;
 
+    if (pair) {
+        const int pairs = p.num_tiles < ctx->sm_count / 2 ? p.num_tiles : ctx->sm_count / 2;
+        if (tf32) {
+            if (block_n == 256) return launch_conv<256, true, true>(p, 2 * pairs, stream);
+            return launch_conv<128, true, true>(p, 2 * pairs, stream);
+        }
+        if (block_n == 256) return launch_conv<256, false, true>(p, 2 * pairs, stream);
+        return launch_conv<128, false, true>(p, 2 * pairs, stream);
+    }
     const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
     if (tf32) {
-        if (block_n == 256) return launch_conv<256, true>(p, grid, stream);
-        if (block_n == 128) return launch_conv<128, true>(p, grid, stream);
-        return launch_conv<64, true>(p, grid, stream);
+        if (block_n == 256) return launch_conv<256, true, false>(p, grid, stream);
+        if (block_n == 128) return launch_conv<128, true, false>(p, grid, stream);
+        return launch_conv<64, true, false>(p, grid, stream);
     }
-    if (block_n == 256) return launch_conv<256, false>(p, grid, stream);
-    if (block_n == 128) return launch_conv<128, false>(p, grid, stream);
-    return launch_conv<64, false>(p, grid, stream);
+    if (block_n == 256) return launch_conv<256, false, false>(p, grid, stream);
+    if (block_n == 128) return launch_conv<128, false, false>(p, grid, stream);
+    return launch_conv<64, false, false>(p, grid, stream);
 }

@@ -304,3 +304,47 @@ def test_input_conv_on_tensor_cores(dev, prec, tol):
     out = ops.Act(torch.zeros(B, H, W, Cout, device=dev))
     ops.conv_tc([patches], [(0, 0, 0, 0, kp)], ops.pack_conv_in_weight(w, dt), Cout, B, H, W, dt, bias=b, out_f32=out)
     assert _rel(out.t.permute(0, 3, 1, 2), ref) < tol
+
+
+PAIR_CASES = [
+    # B, H, W, Cin, Cout, stride, pad, k     -- sizes at which nlc_conv_tc selects the CTA-pair (cta_group::2) kernel
+    (40, 32, 32, 128, 256, 1, (1, 1, 1, 1), 3),    # 320 M tiles, BLOCK_N 256
+    (149, 8, 16, 128, 256, 1, (1, 1, 1, 1), 3),    # odd tile count: the last pair has one CTA with nothing to store
+    (80, 16, 16, 64, 128, 1, (1, 1, 1, 1), 3),     # BLOCK_N 128 pairs
+    (48, 32, 32, 128, 512, 2, (0, 1, 0, 1), 3),    # stride 2, two N tiles
+    (20, 64, 64, 192, 256, 1, (0, 0, 0, 0), 1),    # 1x1, K = 192 (three chunks)
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("case", PAIR_CASES)
+def test_conv_tc_cta_pair_kernel(dev, prec, case):
+    """Same contract as test_conv_tc_matches_torch, plus GroupNorm partials, on the 256-row CTA-pair tiles."""
+    from nlc_b200 import ops
+    B, H, W, Cin, Cout, stride, pad, k = case
+    dt = _dt(prec)
+    g = torch.Generator().manual_seed(21)
+    x = _rnd(torch.randn(B, Cin, H, W, generator=g).to(dev), dt)
+    w = _rnd((torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev), dt)
+    b = torch.randn(Cout, generator=g).to(dev)
+    ref = F.conv2d(F.pad(x, pad), w, b, stride=stride)
+    Ho, Wo = ref.shape[2:]
+    rowvec = torch.randn(B, Cout, generator=g).to(dev)
+    resid = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+    ref = (ref + rowvec[:, :, None, None] + resid.permute(0, 3, 1, 2)) * 0.5
+    tdt = ops.OP_DTYPES[dt]
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(tdt))
+    segs = [(0, kh - pad[2], kw - pad[0], 0, Cin) for kh in range(k) for kw in range(k)]
+    st = ops.GnStats(torch.zeros(B * Ho * Wo // 32, Cout // 4, 2, device=dev)) if Ho * Wo >= 128 else None
+    o32 = ops.Act(torch.full((B, Ho, Wo, Cout), float("nan"), device=dev), 0, Cout, st)
+    oop = ops.Act(torch.zeros(B, Ho, Wo, Cout, device=dev, dtype=tdt))
+    ops.conv_tc([xa], segs, ops.pack_conv_weight(w, dt), Cout, B, Ho, Wo, dt, stride=stride, bias=b, rowvec=rowvec,
+                resid=ops.Act(resid), out_scale=0.5, out_f32=o32, out_op=oop, stats=st is not None)
+    torch.cuda.synchronize()
+    assert _rel(o32.t.permute(0, 3, 1, 2), ref) < 5e-5
+    assert _rel(oop.t.float().permute(0, 3, 1, 2), ref) < (8e-3 if prec == "bf16" else 1e-3)
+    if st is not None:
+        blk = o32.t.view(B * Ho * Wo // 32, 32, Cout // 4, 4).permute(0, 2, 1, 3).reshape(-1, Cout // 4, 128).double()
+        assert (st.t[:, :, 0].double() - blk.mean(2)).abs().max() < 1e-5 * blk.abs().max()
+        m2 = ((blk - blk.mean(2, keepdim=True)) ** 2).sum(2)
+        assert ((st.t[:, :, 1].double() - m2) / m2.clamp_min(1e-6)).abs().max() < 1e-3
