@@ -172,17 +172,19 @@ __device__ __forceinline__ void gn_act8(const float4 v0, const float4 v1, const 
     }
 }
 
+// (kGnUnroll independent 32-byte loads per thread, two CTAs per SM: ~128 KB of reads in flight per SM)
 // MODE 0: y[pix] = act(x[pix]);  MODE 1: the 2x2 outputs of an input pixel get its value (nearest x2);
 // MODE 2: y[opix] = mean of act over the 2x2 input window (avg_pool2d of the activated tensor).
 // grid (chunks, B); dynamic smem 2*C floats: y = act(x*ca[c] + cb[c]).  Four independent 32-byte loads in flight
 // per thread.
-constexpr int kGnUnroll = 4;
+constexpr int kGnUnrollMax = 8;
 template <bool TF32, int MODE>
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
     gn_apply_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C, int groups,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                     const float* __restrict__ shift, int ld_ss, int do_silu, const float* __restrict__ mr,
                     void* __restrict__ y, int ld_y, int items_per_chunk) {
+    constexpr int kGnUnroll = MODE == 2 ? 2 : kGnUnrollMax;  // MODE 2 items are four times as wide
     extern __shared__ __align__(16) float gn_smem[];
     float* ca = gn_smem;
     float* cb = gn_smem + C;
@@ -286,7 +288,7 @@ static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, in
     const long long items = npix * (C / 8);
     // enough CTAs for ~16 per SM (4 resident), each with at least one full unrolled sweep
     long long chunks = (16LL * sm_count + B - 1) / B;
-    const long long max_chunks = (items + kGnUnroll * kGnThreads - 1) / (kGnUnroll * kGnThreads);
+    const long long max_chunks = (items + kGnUnrollMax * kGnThreads - 1) / (kGnUnrollMax * kGnThreads);
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     const int per = static_cast<int>((items + chunks - 1) / chunks);
