@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nlc", choices=["nlc", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--timesteps", type=int, default=CFG["steps"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

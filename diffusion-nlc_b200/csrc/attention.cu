@@ -19,16 +19,16 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T>
-__device__ __forceinline__ T from_f32(float v);
+__device__ __forceinline__ T from_f32(float v, int rnd);
 template <>
-__device__ __forceinline__ float from_f32<float>(float v) { return round_tf32(v); }
+__device__ __forceinline__ float from_f32<float>(float v, int rnd) { return op_f32(v, rnd); }
 template <>
-__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v, int) { return __float2bfloat16_rn(v); }
 
 // ---------------------------------------------------------------- row softmax: one warp per row
 template <typename OutT>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, OutT* __restrict__ P,
-                                                            long long rows, int T) {
+                                                            long long rows, int T, int rnd) {
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
     const float inv = 1.0f / sum;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-        if (i < per) p[lane + 32 * i] = from_f32<OutT>(v[i] * inv);
+        if (i < per) p[lane + 32 * i] = from_f32<OutT>(v[i] * inv, rnd);
 }
 
 // ---------------------------------------------------------------- V [T, dh] (pitch ld) -> V^T [dh, T]
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) transpose_heads_kernel(const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256)
     attn_small_kernel(const T* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int head_stride, int Tn,
-                      int heads, int dh, float scale, T* __restrict__ out, int ld_out) {
+                      int heads, int dh, float scale, T* __restrict__ out, int ld_out, int rnd) {
     extern __shared__ float sm[];
     const int pitch = dh + 1;
     float* sk = sm;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256)
                     }
                 }
             }
-            if (c < dh) out[(static_cast<size_t>(b) * Tn + t) * ld_out + h * dh + c] = from_f32<T>(acc * inv);
+            if (c < dh) out[(static_cast<size_t>(b) * Tn + t) * ld_out + h * dh + c] = from_f32<T>(acc * inv, rnd);
         }
         __syncwarp();
     }
@@ -146,7 +146,7 @@ using namespace nlc;
 
 extern "C" size_t nlc_attention_ws(int op_dtype, int B, int T, int heads, int dh) {
     if (T < 128) return 0;
-    const size_t esz = op_dtype == NLC_F32 ? 4 : 2;
+    const size_t esz = op_dtype != NLC_BF16 ? 4 : 2;
     const size_t bh = static_cast<size_t>(B) * heads;
     return bh * T * T * 4 + bh * T * T * esz + bh * dh * T * esz + 1024;
 }
@@ -156,23 +156,25 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
                              void* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && qkv && out_op, "nlc_attention: null argument");
-    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32, "nlc_attention: bad op_dtype");
-    const size_t esz = op_dtype == NLC_F32 ? 4 : 2;
+    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32 || op_dtype == NLC_F32X3, "nlc_attention: bad op_dtype");
+    const bool f32c = op_dtype != NLC_BF16;  // fp32 containers (tf32-rounded, or plain fp32 for NLC_F32X3)
+    const int rnd = op_dtype == NLC_F32;
+    const size_t esz = f32c ? 4 : 2;
     if (T < 128) {
         const size_t smem = (static_cast<size_t>(2) * T * (dh + 1) + 8 * dh) * sizeof(float);
         NLC_REQUIRE(smem <= 227 * 1024, "nlc_attention: T=%d dh=%d needs %zu B of shared memory", T, dh, smem);
-        if (op_dtype == NLC_F32) {
+        if (f32c) {
             NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 227 * 1024));
             attn_small_kernel<float><<<B * heads, 256, smem, stream>>>(static_cast<const float*>(qkv), ld, q_off, k_off,
                                                                        v_off, head_stride, T, heads, dh, scale,
-                                                                       static_cast<float*>(out_op), ld_out);
+                                                                       static_cast<float*>(out_op), ld_out, rnd);
         } else {
             NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<__nv_bfloat16>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attn_small_kernel<__nv_bfloat16><<<B * heads, 256, smem, stream>>>(
                 static_cast<const __nv_bfloat16*>(qkv), ld, q_off, k_off, v_off, head_stride, T, heads, dh, scale,
-                static_cast<__nv_bfloat16*>(out_op), ld_out);
+                static_cast<__nv_bfloat16*>(out_op), ld_out, rnd);
         }
         NLC_CHECK_LAUNCH();
         return NLC_OK;
@@ -189,7 +191,7 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
     // V^T
     {
         dim3 grid(T / 32, dh / 32, static_cast<unsigned>(bh));
-        if (op_dtype == NLC_F32)
+        if (f32c)
             transpose_heads_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(q8 + v_off * esz), ld,
                                                                     head_stride, T, heads, dh, static_cast<float*>(VT));
         else
@@ -219,10 +221,10 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
     {
         const long long rows = static_cast<long long>(bh) * T;
         const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-        if (op_dtype == NLC_F32)
-            softmax_rows_kernel<float><<<grid, 256, 0, stream>>>(S, static_cast<float*>(P), rows, T);
+        if (f32c)
+            softmax_rows_kernel<float><<<grid, 256, 0, stream>>>(S, static_cast<float*>(P), rows, T, rnd);
         else
-            softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(S, static_cast<__nv_bfloat16*>(P), rows, T);
+            softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(S, static_cast<__nv_bfloat16*>(P), rows, T, rnd);
         NLC_CHECK_LAUNCH();
     }
     // O = P V, heads merged back into [B, T, heads*dh]

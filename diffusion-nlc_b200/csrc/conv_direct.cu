@@ -14,7 +14,7 @@ template <bool TF32>
 __global__ void __launch_bounds__(256)
     conv_in_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, int B, int Cin, int H, int W,
                    const float* __restrict__ wt, const float* __restrict__ bias, int Cout, float* __restrict__ yf,
-                   int ld_yf, void* __restrict__ yo, int ld_yo) {
+                   int ld_yf, void* __restrict__ yo, int ld_yo, int rnd) {
     extern __shared__ float sw[];  // [9*Cin][Cout]
     const int K = 9 * Cin;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
@@ -66,9 +66,9 @@ __global__ void __launch_bounds__(256)
             if (TF32) {
                 float* o = static_cast<float*>(yo) + static_cast<size_t>(pix) * ld_yo + cg * 8;
                 *reinterpret_cast<float4*>(o) =
-                    make_float4(round_tf32(acc[0]), round_tf32(acc[1]), round_tf32(acc[2]), round_tf32(acc[3]));
+                    make_float4(op_f32(acc[0], rnd), op_f32(acc[1], rnd), op_f32(acc[2], rnd), op_f32(acc[3], rnd));
                 *reinterpret_cast<float4*>(o + 4) =
-                    make_float4(round_tf32(acc[4]), round_tf32(acc[5]), round_tf32(acc[6]), round_tf32(acc[7]));
+                    make_float4(op_f32(acc[4], rnd), op_f32(acc[5], rnd), op_f32(acc[6], rnd), op_f32(acc[7], rnd));
             } else {
                 __nv_bfloat16* o = static_cast<__nv_bfloat16*>(yo) + static_cast<size_t>(pix) * ld_yo + cg * 8;
                 *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256)
 template <bool TF32>
 __global__ void __launch_bounds__(256)
     im2col_in_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, int B, int Cin, int H, int W,
-                     void* __restrict__ patches) {
+                     void* __restrict__ patches, int rnd) {
     constexpr int KP = TF32 ? 32 : 64;
     const long long npix = static_cast<long long>(B) * H * W;
     for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(256)
             float4* o = reinterpret_cast<float4*>(static_cast<float*>(patches) + static_cast<size_t>(pix) * KP);
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                o[i] = make_float4(round_tf32(v[4 * i]), round_tf32(v[4 * i + 1]), round_tf32(v[4 * i + 2]),
-                                   round_tf32(v[4 * i + 3]));
+                o[i] = make_float4(op_f32(v[4 * i], rnd), op_f32(v[4 * i + 1], rnd), op_f32(v[4 * i + 2], rnd),
+                                   op_f32(v[4 * i + 3], rnd));
         } else {
             uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(patches) + static_cast<size_t>(pix) * KP);
 #pragma unroll
@@ -259,16 +259,17 @@ extern "C" int nlc_conv_in_nchw(nlc_ctx* ctx, const float* x_nchw, const float* 
     long long blocks = (npix + ppb - 1) / ppb;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    if (op_dtype == NLC_F32) {
+    const int rnd = op_dtype == NLC_F32;
+    if (op_dtype != NLC_BF16) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
         conv_in_kernel<true><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
-            x_nchw, in_scale, B, Cin, H, W, weight, bias, Cout, out_f32, ld_out_f32, out_op, ld_out_op);
+            x_nchw, in_scale, B, Cin, H, W, weight, bias, Cout, out_f32, ld_out_f32, out_op, ld_out_op, rnd);
     } else {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
         conv_in_kernel<false><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
-            x_nchw, in_scale, B, Cin, H, W, weight, bias, Cout, out_f32, ld_out_f32, out_op, ld_out_op);
+            x_nchw, in_scale, B, Cin, H, W, weight, bias, Cout, out_f32, ld_out_f32, out_op, ld_out_op, rnd);
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
@@ -281,7 +282,7 @@ extern "C" int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, i
     NLC_REQUIRE(Cin % 128 == 0 && W % kOutPix == 0 && ld_x % 4 == 0, "nlc_conv_out_nchw: Cin=%d W=%d unsupported", Cin,
                 W);
     NLC_REQUIRE(static_cast<size_t>(9) * Cout * Cin * 4 <= 200 * 1024, "nlc_conv_out_nchw: weights exceed shared memory");
-    if (op_dtype == NLC_F32)
+    if (op_dtype != NLC_BF16)
         return launch_conv_out<float>(ctx, static_cast<const float*>(x_op), ld_x, B, Cin, H, W, weight, bias, Cout,
                                       out_nchw, stream);
     return launch_conv_out<__nv_bfloat16>(ctx, static_cast<const __nv_bfloat16*>(x_op), ld_x, B, Cin, H, W, weight,
@@ -293,16 +294,17 @@ extern "C" int nlc_im2col_in(nlc_ctx* ctx, const float* x_nchw, const float* in_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && x_nchw && patches_op, "nlc_im2col_in: null argument");
     NLC_REQUIRE(Cin >= 1 && Cin <= 3, "nlc_im2col_in: Cin=%d unsupported (1..3: 9*Cin must fit one 32-element K row)", Cin);
-    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32, "nlc_im2col_in: bad op_dtype");
+    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32 || op_dtype == NLC_F32X3, "nlc_im2col_in: bad op_dtype");
+    const int rnd = op_dtype == NLC_F32;
     NLC_REQUIRE((reinterpret_cast<uintptr_t>(patches_op) & 15) == 0, "nlc_im2col_in: patches must be 16-byte aligned");
     const long long npix = static_cast<long long>(B) * H * W;
     long long blocks = (npix + 255) / 256;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    if (op_dtype == NLC_F32)
-        im2col_in_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op);
+    if (op_dtype != NLC_BF16)
+        im2col_in_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
     else
-        im2col_in_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op);
+        im2col_in_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

@@ -16,6 +16,14 @@
 // warps 2-9 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype stores).
 // smem ring of STAGES x (16 KB A + BLOCK_N*128 B W); two TMEM accumulators so the epilogue of tile i
 // overlaps the main loop of tile i+1.
+//
+// Operand modes (template MODE): 0 = bf16 (kind::f16), 1 = tf32 (kind::tf32 on fp32 containers pre-rounded by the
+// producers), 2 = fp32 (NLC_F32X3): operands arrive as plain fp32; four extra "split" warps rewrite every stage in
+// shared memory into a tf32 high part (in place) and a tf32 low part (second half of the stage), and the issuer runs
+// three MMAs per K step, A_hi.W_hi + A_lo.W_hi + A_hi.W_lo, which recovers fp32-accurate products (the dropped
+// A_lo.W_lo term is ~2^-22 relative).  Because the tensor core's own accumulation truncates, every K chunk gets a
+// fresh TMEM accumulator and the epilogue warps sum the chunks in registers.  This is the accuracy mode behind the
+// <=1e-4 per-step parity tests.
 #include "common.h"
 #include "ptx.cuh"
 
@@ -26,6 +34,8 @@ constexpr int kChunkBytes = 128;                      // one swizzle row = one K
 constexpr int kAStageBytes = kBlockM * kChunkBytes;   // 16 KB
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: they split the column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kSplitWarps = 4;                     // MODE 2 only: warps 2+kEpiWarps.. split fp32 stages into hi/lo
+constexpr int kThreadsX3 = kThreads + 32 * kSplitWarps;
 
 struct ConvSegDev {
     int map, dh, dw, c0, nchunk;
@@ -59,14 +69,17 @@ struct ConvKParams {
 
 // CTA2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128
 // rows of A and one half of the B tile, so the weights cross L2->SM once per pair.
-template <int BLOCK_N, bool CTA2>
+template <int BLOCK_N, bool CTA2, bool X3 = false>
 struct ConvCfg {
     static constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;  // B rows staged by this CTA
     static constexpr int kBStageBytes = kBRows * kChunkBytes;
-    static constexpr int kStageBytes = kAStageBytes + kBStageBytes;
-    static constexpr int kStages = CTA2 ? (BLOCK_N == 256 ? 6 : 8) : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8));
+    static constexpr int kLoadBytes = kAStageBytes + kBStageBytes;     // what TMA delivers per stage
+    static constexpr int kStageBytes = X3 ? 2 * kLoadBytes : kLoadBytes;  // X3: [A_hi | W_hi | A_lo | W_lo]
+    static constexpr int kStages =
+        X3 ? (BLOCK_N == 128 ? 3 : 4)
+           : (CTA2 ? (BLOCK_N == 256 ? 6 : 8) : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8)));
     static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
-    static constexpr int kBarBytes = ((2 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
+    static constexpr int kBarBytes = ((3 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
     static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: alignment slack
 };
@@ -122,9 +135,13 @@ __device__ __forceinline__ void gn_partials(const float (&f)[32], int lane, floa
     }
 }
 
-template <int BLOCK_N, bool TF32, bool CTA2>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N, CTA2>;
+template <int BLOCK_N, int MODE, bool CTA2>
+__global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
+    conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+    constexpr bool TF32 = MODE != 0;  // fp32 containers, kind::tf32
+    constexpr bool X3 = MODE == 2;    // unrounded fp32 operands, split in shared memory, three MMAs per K step
+    static_assert(!(X3 && CTA2) && !(X3 && BLOCK_N == 256), "the fp32 mode runs on the 1-CTA kernel with N <= 128");
+    using Cfg = ConvCfg<BLOCK_N, CTA2, X3>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kChunkElems = TF32 ? 32 : 64;
     // work units: tiles for the 1-CTA kernel, 256-row tile pairs for the CTA-pair kernel (both CTAs of a pair walk
@@ -138,7 +155,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + kStages;
-    uint64_t* tfull = bars + 2 * kStages;
+    uint64_t* split = bars + 2 * kStages;  // X3: stage has been split into hi/lo (one arrive per split thread)
+    uint64_t* tfull = bars + 3 * kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -153,6 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
+            mbar_init(&split[s], 32 * kSplitWarps);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
@@ -194,13 +213,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         uint8_t* sb = sa + kAStageBytes;
                         if (CTA2) {
                             // both CTAs' bytes land on the leader's barrier (a tile past the end is all zero fill)
-                            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+                            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kLoadBytes);
                             tma_load_4d_pair(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
                                              h0 + sg.dh, n0);
                             tma_load_4d_pair(sb, &p.mapB, &full[stage], kchunk * kChunkElems,
                                              n_tile * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows, 0, 0);
                         } else {
-                            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+                            mbar_expect_tx(&full[stage], Cfg::kLoadBytes);
                             tma_load_4d(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
                                         h0 + sg.dh, n0);
                             tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
@@ -223,6 +242,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            if (X3) {
+                // One TMEM accumulator per K chunk: the tensor core accumulates with truncation (round toward zero), so a
+                // long in-TMEM sum drifts by ~n * 2^-25 of its magnitude (1e-5 at K = 2304).  Each chunk's 12 MMAs
+                // (low-order terms first, while the accumulator is still tiny) therefore go to a fresh accumulator and
+                // the epilogue warps add the chunks up in registers with round-to-nearest.
+                for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+                    for (int kc = 0; kc < p.total_chunks; ++kc) {
+                        mbar_wait(&tempty[acc], acc_phase ^ 1);
+                        mbar_wait(&split[stage], phase);
+                        tc_fence_after_sync();
+                        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                        const uint64_t ahi = umma_desc_sw128(sa), bhi = umma_desc_sw128(sa + kAStageBytes);
+                        const uint64_t alo = umma_desc_sw128(sa + Cfg::kLoadBytes);
+                        const uint64_t blo = umma_desc_sw128(sa + Cfg::kLoadBytes + kAStageBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, k != 0);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
+                        umma_commit(&empty[stage]);
+                        umma_commit(&tfull[acc]);
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                        acc ^= 1;
+                        if (acc == 0) acc_phase ^= 1;
+                    }
+                }
+            } else {
             for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
@@ -257,9 +308,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+            }
+        }
+    } else if (X3 && warp >= 2 + kEpiWarps) {
+        // ------------------------------------------------------------ fp32 split (MODE 2 only)
+        // hi = tf32(v) in place, lo = tf32(v - hi) at the same (swizzled) offset of the stage's second half; the
+        // subtraction is exact in fp32, so hi + lo carries 21+ mantissa bits of v into the tensor core.
+        const int tid = static_cast<int>(threadIdx.x) - 32 * (2 + kEpiWarps);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+            for (int kc = 0; kc < p.total_chunks; ++kc) {
+                mbar_wait(&full[stage], phase);
+                float4* hi = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes);
+                float4* lo = reinterpret_cast<float4*>(smem + stage * Cfg::kStageBytes + Cfg::kLoadBytes);
+#pragma unroll 4
+                for (int i = tid; i < Cfg::kLoadBytes / 16; i += 32 * kSplitWarps) {
+                    const float4 v = hi[i];
+                    const float4 h = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+                    hi[i] = h;
+                    lo[i] = make_float4(round_tf32(v.x - h.x), round_tf32(v.y - h.y), round_tf32(v.z - h.z),
+                                        round_tf32(v.w - h.w));
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&split[stage]);
+                if (++stage == kStages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         // Each warp owns TMEM lanes [32*quad, 32*quad+32) = 32 consecutive output pixels; a lane holds one pixel's
         // 32 channels of the current column chunk.  Global traffic goes through a per-warp 32x32 fp32 staging block
         // (16-byte chunks XOR-swizzled by the row, conflict-free both ways) so that every load / store instruction
@@ -297,13 +377,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                                  : (static_cast<size_t>(n0) * p.Ho + ho0) * p.Wo + wo0;
             const int hs_off = p.out_head_split * ho0;
 
-            mbar_wait(&tfull[acc], acc_phase);
-            tc_fence_after_sync();
+            // X3: the K chunks arrive one accumulator at a time and are summed here, in registers (round to nearest)
+            constexpr int kNJ = X3 ? BLOCK_N / (32 * (kEpiWarps / 4)) : 1;  // column chunks owned by this warp
+            float accr[kNJ][32];
+            if (X3) {
+#pragma unroll
+                for (int j = 0; j < kNJ; ++j)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) accr[j][i] = 0.f;
+                for (int kc = 0; kc < p.total_chunks; ++kc) {
+                    mbar_wait(&tfull[acc], acc_phase);
+                    tc_fence_after_sync();
+                    const uint32_t ta = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N + 32 * half;
+#pragma unroll
+                    for (int j = 0; j < kNJ; ++j) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(ta + 32 * (kEpiWarps / 4) * j, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) accr[j][i] += __uint_as_float(v[i]);
+                    }
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
+                }
+            } else {
+                mbar_wait(&tfull[acc], acc_phase);
+                tc_fence_after_sync();
+            }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
             for (int c = 32 * half; c < BLOCK_N; c += 32 * (kEpiWarps / 4)) {
                 uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c, v);
+                if (!X3) tmem_ld_32x32b_x32(taddr + c, v);
                 const int col0 = n_tile * BLOCK_N + c;
                 const int ocol0 = col0 + hs_off;
                 if (p.resid) {  // coalesced gather of the residual block while the TMEM load is in flight
@@ -317,10 +425,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     }
                     __syncwarp();
                 }
-                tmem_ld_wait();
                 float f[32];
+                if (X3) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    for (int i = 0; i < 32; ++i) f[i] = (kNJ == 2 && c >= 32 * (kEpiWarps / 4)) ? accr[kNJ - 1][i] : accr[0][i];
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                }
                 if (p.bias) {
                     const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -375,7 +488,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                                 const float4 t = *reinterpret_cast<const float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2));
                                 reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + (pix0 + r) * p.ld_out_op +
                                                           ocol0)[sub_c4] =
-                                    make_float4(round_tf32(t.x), round_tf32(t.y), round_tf32(t.z), round_tf32(t.w));
+                                    X3 ? t : make_float4(round_tf32(t.x), round_tf32(t.y), round_tf32(t.z),
+                                                         round_tf32(t.w));
                             }
                         }
                     } else {
@@ -397,13 +511,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 }
                 __syncwarp();
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) {
-                if (CTA2) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
+            if (!X3) {
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTA2) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
     }
 
@@ -418,27 +534,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
-template <int BLOCK_N, bool TF32, bool CTA2>
+template <int BLOCK_N, int MODE, bool CTA2>
 static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N, CTA2>;
+    using Cfg = ConvCfg<BLOCK_N, CTA2, MODE == 2>;
+    constexpr int kLaunchThreads = MODE == 2 ? kThreadsX3 : kThreads;
     static bool configured = false;
     if (!configured) {
-        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, TF32, CTA2>,
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, CTA2>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured = true;
     }
     if (CTA2) {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads);
+        cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kLaunchThreads);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, TF32, CTA2>, p));
+        NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, CTA2>, p));
     } else {
-        conv_tc_kernel<BLOCK_N, TF32, CTA2><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(p);
+        conv_tc_kernel<BLOCK_N, MODE, CTA2><<<grid, kLaunchThreads, Cfg::kSmemBytes, stream>>>(p);
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
@@ -451,8 +568,10 @@ using namespace nlc;
 extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && d, "nlc_conv_tc: null argument");
-    NLC_REQUIRE(d->dtype == NLC_BF16 || d->dtype == NLC_F32, "nlc_conv_tc: dtype must be NLC_BF16 or NLC_F32");
-    const bool tf32 = d->dtype == NLC_F32;
+    NLC_REQUIRE(d->dtype == NLC_BF16 || d->dtype == NLC_F32 || d->dtype == NLC_F32X3,
+                "nlc_conv_tc: dtype must be NLC_BF16, NLC_F32 or NLC_F32X3");
+    const bool x3 = d->dtype == NLC_F32X3;
+    const bool tf32 = d->dtype != NLC_BF16;  // fp32 containers
     const int esz = tf32 ? 4 : 2;
     const int chunk = kChunkBytes / esz;
     NLC_REQUIRE(d->nsrc >= 1 && d->nsrc <= NLC_MAX_SRC, "nlc_conv_tc: nsrc %d out of range", d->nsrc);
@@ -484,13 +603,13 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.Cout = d->Cout;
 
     int block_n = 64;
-    if (d->Cout % 256 == 0 && p.num_m_tiles * (d->Cout / 256) >= ctx->sm_count)
+    if (!x3 && d->Cout % 256 == 0 && p.num_m_tiles * (d->Cout / 256) >= ctx->sm_count)
         block_n = 256;
     else if (d->Cout % 128 == 0 && p.num_m_tiles * (d->Cout / 128) >= ctx->sm_count)
         block_n = 128;
     // CTA pairs (256-row tiles, the B tile shared by two SMs) when there is at least one pair tile per SM pair;
     // the batched right-hand operand of the attention GEMMs differs per M tile and stays on the 1-CTA kernel
-    const bool pair = ctx->use_cta_pairs && d->wbatched.ptr == nullptr && block_n >= 128 &&
+    const bool pair = !x3 && ctx->use_cta_pairs && d->wbatched.ptr == nullptr && block_n >= 128 &&
                       ((p.num_m_tiles + 1) / 2) * (d->Cout / block_n) >= ctx->sm_count / 2;
     p.num_n_tiles = d->Cout / block_n;
     p.num_m_units = pair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
@@ -576,19 +695,23 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     if (pair) {
         const int pairs = p.num_tiles < ctx->sm_count / 2 ? p.num_tiles : ctx->sm_count / 2;
         if (tf32) {
-            if (block_n == 256) return launch_conv<256, true, true>(p, 2 * pairs, stream);
-            return launch_conv<128, true, true>(p, 2 * pairs, stream);
+            if (block_n == 256) return launch_conv<256, 1, true>(p, 2 * pairs, stream);
+            return launch_conv<128, 1, true>(p, 2 * pairs, stream);
         }
-        if (block_n == 256) return launch_conv<256, false, true>(p, 2 * pairs, stream);
-        return launch_conv<128, false, true>(p, 2 * pairs, stream);
+        if (block_n == 256) return launch_conv<256, 0, true>(p, 2 * pairs, stream);
+        return launch_conv<128, 0, true>(p, 2 * pairs, stream);
     }
     const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-    if (tf32) {
-        if (block_n == 256) return launch_conv<256, true, false>(p, grid, stream);
-        if (block_n == 128) return launch_conv<128, true, false>(p, grid, stream);
-        return launch_conv<64, true, false>(p, grid, stream);
+    if (x3) {
+        if (block_n == 128) return launch_conv<128, 2, false>(p, grid, stream);
+        return launch_conv<64, 2, false>(p, grid, stream);
     }
-    if (block_n == 256) return launch_conv<256, false, false>(p, grid, stream);
-    if (block_n == 128) return launch_conv<128, false, false>(p, grid, stream);
-    return launch_conv<64, false, false>(p, grid, stream);
+    if (tf32) {
+        if (block_n == 256) return launch_conv<256, 1, false>(p, grid, stream);
+        if (block_n == 128) return launch_conv<128, 1, false>(p, grid, stream);
+        return launch_conv<64, 1, false>(p, grid, stream);
+    }
+    if (block_n == 256) return launch_conv<256, 0, false>(p, grid, stream);
+    if (block_n == 128) return launch_conv<128, 0, false>(p, grid, stream);
+    return launch_conv<64, 0, false>(p, grid, stream);
 }

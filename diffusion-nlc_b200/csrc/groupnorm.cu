@@ -144,13 +144,13 @@ __global__ void __launch_bounds__(kGnThreads)
 
 // ---------------------------------------------------------------- apply
 template <bool TF32>
-__device__ __forceinline__ void gn_store8(void* __restrict__ y, size_t off, const float (&f)[8]) {
+__device__ __forceinline__ void gn_store8(void* __restrict__ y, size_t off, const float (&f)[8], int rnd) {
     if (TF32) {
         float* yp = static_cast<float*>(y) + off;
         reinterpret_cast<float4*>(yp)[0] =
-            make_float4(round_tf32(f[0]), round_tf32(f[1]), round_tf32(f[2]), round_tf32(f[3]));
+            make_float4(op_f32(f[0], rnd), op_f32(f[1], rnd), op_f32(f[2], rnd), op_f32(f[3], rnd));
         reinterpret_cast<float4*>(yp)[1] =
-            make_float4(round_tf32(f[4]), round_tf32(f[5]), round_tf32(f[6]), round_tf32(f[7]));
+            make_float4(op_f32(f[4], rnd), op_f32(f[5], rnd), op_f32(f[6], rnd), op_f32(f[7], rnd));
     } else {
         __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y) + off;
         *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
     gn_apply_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C, int groups,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                     const float* __restrict__ shift, int ld_ss, int do_silu, const float* __restrict__ mr,
-                    void* __restrict__ y, int ld_y, int items_per_chunk) {
+                    void* __restrict__ y, int ld_y, int items_per_chunk, int rnd) {
     constexpr int kGnUnroll = MODE == 2 ? 2 : kGnUnrollMax;  // MODE 2 items are four times as wide
     extern __shared__ __align__(16) float gn_smem[];
     float* ca = gn_smem;
@@ -253,18 +253,18 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                     for (int q = 0; q < 4; ++q) gn_act8(v[u][2 * q], v[u][2 * q + 1], ca + c, cb + c, do_silu, t[q]);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[k] = ((t[0][k] + t[1][k]) + (t[2][k] + t[3][k])) * 0.25f;
-                    gn_store8<TF32>(y, (static_cast<size_t>(n) * npix + pix) * ld_y + c, f);
+                    gn_store8<TF32>(y, (static_cast<size_t>(n) * npix + pix) * ld_y + c, f, rnd);
                 } else {
                     gn_act8(v[u][0], v[u][1], ca + c, cb + c, do_silu, f);
                     if (MODE == 0) {
-                        gn_store8<TF32>(y, (img_in + pix) * ld_y + c, f);
+                        gn_store8<TF32>(y, (img_in + pix) * ld_y + c, f, rnd);
                     } else {
                         const int h = pix / W, w = pix - h * W;
                         const size_t o = (static_cast<size_t>(n) * 4 * H * W + static_cast<size_t>(2 * h) * 2 * W + 2 * w);
-                        gn_store8<TF32>(y, o * ld_y + c, f);
-                        gn_store8<TF32>(y, (o + 1) * ld_y + c, f);
-                        gn_store8<TF32>(y, (o + 2 * W) * ld_y + c, f);
-                        gn_store8<TF32>(y, (o + 2 * W + 1) * ld_y + c, f);
+                        gn_store8<TF32>(y, o * ld_y + c, f, rnd);
+                        gn_store8<TF32>(y, (o + 1) * ld_y + c, f, rnd);
+                        gn_store8<TF32>(y, (o + 2 * W) * ld_y + c, f, rnd);
+                        gn_store8<TF32>(y, (o + 2 * W + 1) * ld_y + c, f, rnd);
                     }
                 }
             }
@@ -283,7 +283,7 @@ static int pick_chunks(int B, int HW, int sm_count, int min_rows) {
 template <bool TF32, int MODE>
 static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, int groups, const float* gamma,
                         const float* beta, const float* scale, const float* shift, int ld_ss, int do_silu,
-                        const float* mr, void* y, int ld_y, int sm_count, cudaStream_t stream) {
+                        const float* mr, void* y, int ld_y, int sm_count, int rnd, cudaStream_t stream) {
     const long long npix = MODE == 2 ? static_cast<long long>(H / 2) * (W / 2) : static_cast<long long>(H) * W;
     const long long items = npix * (C / 8);
     // enough CTAs for ~16 per SM (4 resident), each with at least one full unrolled sweep
@@ -295,7 +295,7 @@ static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, in
     chunks = (items + per - 1) / per;
     const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
     gn_apply_kernel<TF32, MODE><<<dim3(static_cast<unsigned>(chunks), B), kGnThreads, smem, stream>>>(
-        x, ld_x, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y, ld_y, per);
+        x, ld_x, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y, ld_y, per, rnd);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -321,7 +321,8 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
                     (reinterpret_cast<uintptr_t>(y_op) & 15) == 0,
                 "nlc_groupnorm: tensors must be 16-byte aligned");
     NLC_REQUIRE((scale == nullptr) == (shift == nullptr), "nlc_groupnorm: scale and shift come together");
-    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32, "nlc_groupnorm: bad op_dtype");
+    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32 || op_dtype == NLC_F32X3, "nlc_groupnorm: bad op_dtype");
+    const int rnd = op_dtype == NLC_F32;  // NLC_F32X3 keeps the operand copy unrounded
     NLC_REQUIRE(static_cast<long long>(H) * W * (C / 8) < (1LL << 31), "nlc_groupnorm: image too large");
     NLC_REQUIRE(resample >= 0 && resample <= 2 && (resample != 2 || (H % 2 == 0 && W % 2 == 0)),
                 "nlc_groupnorm: resample mode %d unsupported for %dx%d", resample, H, W);
@@ -347,8 +348,8 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
     }
 #define NLC_GN_APPLY(T, M)                                                                                        \
     return launch_apply<T, M>(x, ld_x, B, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y_op, ld_y, \
-                              ctx->sm_count, stream)
-    if (op_dtype == NLC_F32) {
+                              ctx->sm_count, rnd, stream)
+    if (op_dtype != NLC_BF16) {
         if (resample == 0) NLC_GN_APPLY(true, 0);
         if (resample == 1) NLC_GN_APPLY(true, 1);
         NLC_GN_APPLY(true, 2);

@@ -23,7 +23,7 @@ __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
 template <int MODE, bool TF32, typename TIN>
 __global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x, int ld_x, int H, int W, int C,
                                                         float* __restrict__ yf, int ld_yf, void* __restrict__ yo,
-                                                        int ld_yo, long long total4) {
+                                                        int ld_yo, long long total4, int rnd) {
     const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : H);
     const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : W);
     const int C4 = C >> 2;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x
         if (yo) {
             if (TF32)
                 *reinterpret_cast<float4*>(static_cast<float*>(yo) + opix * ld_yo + c) =
-                    make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+                    make_float4(op_f32(v.x, rnd), op_f32(v.y, rnd), op_f32(v.z, rnd), op_f32(v.w, rnd));
             else
                 *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(yo) + opix * ld_yo + c) =
                     make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
@@ -150,10 +150,11 @@ extern "C" int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H
     long long blocks = (total4 + 255) / 256;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    const bool tf32 = op_dtype == NLC_F32;
+    const bool tf32 = op_dtype != NLC_BF16;
+    const int rnd = op_dtype == NLC_F32;
 #define NLC_RS(M, T)                                                                                          \
     resample_kernel<M, T, float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld_x, H, W, C, y_f32,      \
-                                                                                    ld_y_f32, y_op, ld_y_op, total4)
+                                                                                    ld_y_f32, y_op, ld_y_op, total4, rnd)
     if (mode == 0) {
         if (tf32) NLC_RS(0, true); else NLC_RS(0, false);
     } else if (mode == 1) {
@@ -178,16 +179,17 @@ extern "C" int nlc_resample_op(nlc_ctx* ctx, const void* x_op, int op_dtype, int
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
     const unsigned g = static_cast<unsigned>(blocks);
-    if (op_dtype == NLC_F32) {
+    const int rnd = op_dtype == NLC_F32;
+    if (op_dtype != NLC_BF16) {
         const float* x = static_cast<const float*>(x_op);
-        if (mode == 1) resample_kernel<1, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
-        else resample_kernel<2, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+        if (mode == 1) resample_kernel<1, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+        else resample_kernel<2, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     } else {
         const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_op);
         if (mode == 1)
-            resample_kernel<1, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+            resample_kernel<1, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
         else
-            resample_kernel<2, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4);
+            resample_kernel<2, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;

@@ -262,4 +262,7 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// Operand-copy value in an fp32 container: tf32-rounded (NLC_F32) or untouched (NLC_F32X3, split later by the conv).
+__device__ __forceinline__ float op_f32(float x, int rnd) { return rnd ? round_tf32(x) : x; }
+
 }  // namespace nlc

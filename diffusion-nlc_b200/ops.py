@@ -5,9 +5,9 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import NLC_BF16, NLC_F32
+from ._lib import NLC_BF16, NLC_F32, NLC_F32X3
 
-OP_DTYPES = {NLC_BF16: torch.bfloat16, NLC_F32: torch.float32}
+OP_DTYPES = {NLC_BF16: torch.bfloat16, NLC_F32: torch.float32, NLC_F32X3: torch.float32}
 
 
 class _Stats:
@@ -122,6 +122,8 @@ def pack_conv_weight(w, op_dtype, extra=None):
     k = k.contiguous()
     if op_dtype == NLC_BF16:
         return k.to(torch.bfloat16).contiguous()
+    if op_dtype == NLC_F32X3:
+        return k.clone()  # split into tf32 hi + lo by the kernel
     return round_tf32_(k.clone())
 
 
@@ -202,7 +204,9 @@ def pack_conv_in_weight(w, op_dtype):
     kp = 64 if op_dtype == NLC_BF16 else 32
     k = torch.zeros(Cout, kp, dtype=torch.float32, device=w.device)
     k[:, :9 * Cin] = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, -1)
-    return k.to(torch.bfloat16).contiguous() if op_dtype == NLC_BF16 else round_tf32_(k)
+    if op_dtype == NLC_BF16:
+        return k.to(torch.bfloat16).contiguous()
+    return k if op_dtype == NLC_F32X3 else round_tf32_(k)
 
 
 @_timed("conv_out_nchw")

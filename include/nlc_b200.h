@@ -31,8 +31,11 @@ extern "C" {
 #define NLC_ECUDA (-2)    /* CUDA runtime / driver error      */
 #define NLC_ENOTSUP (-3)  /* valid but not implemented        */
 
-#define NLC_F32 0
-#define NLC_BF16 1
+/* Operand modes of the tensor-core path.  Every producer writes the "operand copy" of an activation in this type. */
+#define NLC_F32 0   /* fp32 containers holding tf32-rounded values; one kind::tf32 MMA per K step              */
+#define NLC_BF16 1  /* bf16; kind::f16 MMA (the throughput mode)                                              */
+#define NLC_F32X3 2 /* plain fp32 operands and weights; nlc_conv_tc splits them into tf32 hi+lo parts in shared */
+                    /* memory and issues three MMAs per K step: fp32-accurate products (the accuracy mode)     */
 
 typedef struct nlc_ctx nlc_ctx;
 
@@ -73,7 +76,7 @@ typedef struct {
  * second source (torch.nn.Conv2d calls at src/unet_ddim.py:109-135,141,148-156). `weight` is
  * [Cout][sum nch] in the operand dtype, K ordered like seg[]. */
 typedef struct {
-    int dtype; /* NLC_BF16 (kind::f16) or NLC_F32 (kind::tf32) */
+    int dtype; /* NLC_BF16 (kind::f16), NLC_F32 (kind::tf32) or NLC_F32X3 (3 x kind::tf32 on split fp32) */
     int nsrc;
     nlc_operand src[NLC_MAX_SRC];
     int nseg;
