@@ -213,17 +213,25 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
     int item_end = item0 + items_per_chunk;
     if (item_end > npix * C8) item_end = npix * C8;
     const size_t img_in = static_cast<size_t>(n) * H * W;
+    // (pixel, channel block) of each unrolled item, advanced incrementally: one integer division per thread, not per item
+    int cc[kGnUnroll];
+    int pp[kGnUnroll];
+#pragma unroll
+    for (int u = 0; u < kGnUnroll; ++u) {
+        const int i = item0 + static_cast<int>(threadIdx.x) + u * kGnThreads;
+        pp[u] = i / C8;
+        cc[u] = (i - pp[u] * C8) << 3;
+    }
+    const int step_pix = (kGnUnroll * kGnThreads) / C8;
+    const int step_c = ((kGnUnroll * kGnThreads) - step_pix * C8) << 3;
     for (int i0 = item0 + threadIdx.x; i0 < item_end; i0 += kGnUnroll * kGnThreads) {
         float4 v[kGnUnroll][MODE == 2 ? 8 : 2];
-        int cc[kGnUnroll];
-        int pp[kGnUnroll];
 #pragma unroll
         for (int u = 0; u < kGnUnroll; ++u) {
             const int i = i0 + u * kGnThreads;
             if (i < item_end) {
-                const int pix = i / C8;
-                const int c = (i - pix * C8) << 3;
-                cc[u] = c, pp[u] = pix;
+                const int pix = pp[u];
+                const int c = cc[u];
                 if (MODE == 2) {
                     const int ho = pix / Wp, wo = pix - ho * Wp;
                     const float* xp = x + (img_in + static_cast<size_t>(2 * ho) * W + 2 * wo) * ld_x + c;
@@ -268,6 +276,8 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                     }
                 }
             }
+            cc[u] += step_c, pp[u] += step_pix;
+            if (cc[u] >= C) cc[u] -= C, ++pp[u];
         }
     }
 }

@@ -249,7 +249,9 @@ __device__ __forceinline__ float warp_max(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU.EX2 + MUFU.RCP (an IEEE division here makes the GroupNorm apply pass issue-bound, not
+// HBM-bound: profiles/r01c_ncu_gn_apply.md).  ~3 ulp; x -> -inf gives -0 like the exact form.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
