@@ -295,6 +295,29 @@ class Deblurring(_Separable):
         return v.reshape(v.shape[0], -1)
 
 
+def constraint_inv_transform(op, deg, y, channels, R):
+    """Constraint_Function.inv_transform for proj='svd' (image_sample.py:312-323)."""
+    b = y.shape[0]
+    Apy = op.A_pinv(y).view(b, channels, R, R)
+    if deg[:6] == "deblur":
+        Apy = y.view(b, channels, R, R)
+    elif deg == "colorization":
+        Apy = y.view(b, 1, R, R).repeat(1, 3, 1, 1)
+    elif deg == "inpainting":
+        Apy = Apy + op.A_pinv(op.A(torch.ones_like(Apy).reshape(b, -1))).reshape(*Apy.shape) - 1
+    return Apy
+
+
+def constraint_loss(op, deg, x, y, channels, R):
+    """Constraint_Function.loss (image_sample.py:325-333): per-sample L1 of (A x - y) and of (inv_transform(y) - x)."""
+    b = x.shape[0]
+    y_hat = op.A(x.reshape(b, -1))
+    x_hat = constraint_inv_transform(op, deg, y, channels, R)
+    fwd = torch.linalg.vector_norm(y_hat - y.reshape(b, -1), ord=1, dim=1)
+    bwd = torch.linalg.vector_norm((x_hat - x).reshape(b, -1), ord=1, dim=1)
+    return fwd, bwd
+
+
 def bicubic_kernel(factor):
     """src/constraint_functions.py:252-269."""
     import numpy as np

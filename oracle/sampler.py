@@ -240,11 +240,14 @@ def projection_loop(tab, ts, sig, min_var_coef, model_fwd, model_enc, sigma_fn, 
 
 def denoise_loop(tab, ts, sig, min_var_coef, model_fwd, model_enc, sigma_fn, xT, kind="ddim", eta=0.0,
                  sampler_var="none", style="pred", norm_eps=True, refine=True, norm_min=0.0, norm_max=1.0, clip="clamp",
-                 constrain_fn=None, noises=None, sigma_pred_threshold=1000, learn_epsvar=False, log=None):
+                 constrain_fn=None, noises=None, sigma_pred_threshold=1000, learn_epsvar=False, log=None,
+                 constrain_loss=None):
     """src/experiments.py:329-397 with the clip functions of :186-207.  `noises[ind]` replaces torch.randn_like.
-    `log` (a list) receives one dict of tensors per step."""
+    `log` (a list) receives one dict of tensors per step.  With `constrain_loss` the x0 of the step with the lowest
+    batch-mean constraint loss is returned (best-x0 tracking, :371-381); otherwise the last x0."""
     xt = xT
     x0 = xt
+    best_val, best_x0 = 10000, xt
     for ind in range(len(ts) - 1):
         t = ts[ind]
         sigma_t, sigma_prev = sig[ind], sig[ind + 1]
@@ -257,8 +260,15 @@ def denoise_loop(tab, ts, sig, min_var_coef, model_fwd, model_enc, sigma_fn, xT,
         x0 = constrain_fn(x0_hat) if constrain_fn is not None else x0_hat
         noise = noises[ind] if noises is not None else None
         x_prev = pred_xprev(kind, eta, x0, eps, sigma_t, sigma_prev, xt, logvar, noise)
+        const = None
+        if constrain_loss is not None:
+            const, _ = constrain_loss(x0.clamp(-1, 1))
+            if torch.mean(const) < best_val:
+                best_x0, best_val = x0.clone(), torch.mean(const)
+        else:
+            best_x0 = x0
         if log is not None:
-            log.append(dict(xt=xt, eps=eps, x0_hat=x0_hat, x0=x0, x_prev=x_prev,
+            log.append(dict(xt=xt, eps=eps, x0_hat=x0_hat, x0=x0, x_prev=x_prev, const=const,
                             sigma_t=torch.as_tensor(sigma_t).reshape(-1), sigma_prev=torch.as_tensor(sigma_prev).reshape(-1)))
         xt = x_prev
-    return x0
+    return best_x0

@@ -124,6 +124,7 @@ def main():
     adm()
     edm()
     loops2()
+    loops3()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -235,6 +236,77 @@ def loops2():
         gold["%s|%d|%s|%s|%s|%s" % (loop, int(cont), clip, rates, kind, eta)] = dict(
             z=z, noises=noises, final=final, timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone(), **rec)
     torch.save(gold, os.path.join(HERE, "loops2_tiny.pt"))
+
+
+CONSTRAINED_TASKS = [("sr_averagepooling", 4), ("inpainting_box", 1), ("colorization", 1), ("cs_walshhadamard", 4)]
+
+
+def loops3():
+    """DDNM-constrained restoration with NLC (configs c4/c5) on the unmodified reference: ADM UNet with the learned
+    variance head (adm_tiny), ddim_simple_orig eta 0.85, dynamic clip, the `svd` projection x0 - A^+(A x0 - y) built
+    the way image_sample.py:359-383,636-648 builds it (Constraint_Function over the reference's own svd_operators;
+    `get_constraint_function` itself is not callable)  -> loops3_constrained.pt"""
+    from functools import partial
+    R = refimport.load()
+    IS = image_sample_module()
+    torch.set_num_threads(4)
+    cfg, sg, sd, ssd, net, snet = adm_reference_modules("adm_tiny")
+    side, B, C = cfg["image_size"], 2, 3
+    shape = (B, C, side, side)
+    ref = R.svd_operators
+    mask = torch.ones(side, side)
+    q = side // 4
+    mask[q:3 * q, q:3 * q] = 0
+    mr = torch.nonzero(mask.reshape(-1) == 0).long().reshape(-1) * 3
+    missing = torch.cat([mr, mr + 1, mr + 2])
+    perm = torch.randperm(side * side, generator=torch.Generator().manual_seed(3))
+    gold = dict(missing=missing, perm=perm, mask=mask)
+    for task, scale in CONSTRAINED_TASKS:
+        A_funcs = {"sr_averagepooling": lambda: ref.SuperResolution(C, side, scale, "cpu"),
+                   "inpainting_box": lambda: ref.Inpainting(C, side, missing, "cpu"),
+                   "colorization": lambda: ref.Colorization(side, "cpu"),
+                   "cs_walshhadamard": lambda: ref.WalshHadamardCS(C, side, scale, perm, "cpu")}[task]()
+        A, Ap = A_funcs.A, A_funcs.A_pinv
+
+        def affine_svd(x0_t, y, lambda_t, A, Ap):  # image_sample.py:376-379
+            return x0_t - Ap(A(x0_t.reshape(x0_t.size(0), -1)) - y.reshape(y.size(0), -1)).reshape(*x0_t.size())
+
+        deg = "inpainting" if task.startswith("inpainting") else task
+        con = IS.Constraint_Function(deg, A, Ap, partial(affine_svd, A=A, Ap=Ap), proj="svd", channels=C,
+                                     image_size=side, lr=1.0)
+        g = torch.Generator().manual_seed(31)
+        x_true = torch.rand(shape, generator=g) * 2 - 1
+        y = con.transform(x_true)  # image_sample.py:638
+        constrain_fn = partial(con.constraint_fn, y=y, lambda_t=con.lr)  # :647
+        constrain_loss = partial(con.loss, y=y)  # :648
+        sch = R.schedulers.get_sampler("ddim_simple_orig", 1000, 5, start_sigma=20.0, eta=0.85, sampler_var="learned")
+        exp = R.experiments.ImageExperiment(net, sch, batch_size=B, data_shape=shape[1:], seed=5, device="cpu")
+        exp.set_model(net, snet, learn_epsvar=True)
+        exp.set_norm_maxmin(0.0, 30.0)
+        exp.set_clip_fn("dynamic")
+        torch.manual_seed(5)
+        z = torch.randn(shape)
+        noises = [torch.randn(shape) for _ in range(len(sch.timesteps) - 1)]
+        rec = dict(xt=[], sigma_t=[], sigma_prev=[], x_prev=[], x0=[], eps=[])
+        orig = sch.pred_xprev
+
+        def spy(*a, _orig=orig, _rec=rec, **k):
+            out = _orig(*a, **k)
+            for name in ("xt", "x0", "eps"):
+                _rec[name].append(k[name].clone())
+            _rec["sigma_t"].append(torch.as_tensor(k["sigma_t"]).reshape(-1).clone())
+            _rec["sigma_prev"].append(torch.as_tensor(k["sigma_prev"]).reshape(-1).clone())
+            _rec["x_prev"].append(out.clone())
+            return out
+
+        sch.pred_xprev = spy
+        final, logs = exp.denoise_loop(shape=shape, gen=exp.new_gen(5), style="pred", constrain_fn=constrain_fn,
+                                       norm_eps=True, refine_prior_sigma=True, return_log=True, chunk_size=1,
+                                       constrain_loss=constrain_loss, sigma_pred_threshold=960)
+        gold["%s|%d" % (task, scale)] = dict(
+            x_true=x_true, y=y, z=z, noises=noises, final=final, x0_hat=logs[2], const=logs[4],
+            timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone(), **rec)
+    torch.save(gold, os.path.join(HERE, "loops3_constrained.pt"))
 
 
 EDM_CASES = [("pred_partial,pred", "00", False, 1.0), ("base,base", "00", False, 1.0), ("pred,pred_partial", "11", True, 1.0),

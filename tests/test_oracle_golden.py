@@ -176,3 +176,51 @@ def test_continuous_t_dynamic_clip_and_projection_loop(golden_dir, tiny):
             else:
                 x0 = S.projection_loop(tab, ts, sig, mvc, fwd, enc, sgf, xT, rates=eval(rates), **kw)
         assert torch.equal(x0, case["final"]), key
+
+
+def test_constrained_restoration_loops(golden_dir):
+    """tests/golden/loops3_constrained.pt: the reference's denoise_loop with the DDNM `svd` projection and best-x0
+    tracking (configs c4/c5: ADM learned-variance net, ddim_simple_orig, dynamic clip) for SR x4, box inpainting,
+    colourisation and Walsh-Hadamard CS.  The operators run in spectral form here and the networks are the functional
+    restatement, so the per-step tensors agree to fp32 round-off (1e-5), not bit for bit."""
+    from functools import partial
+    from oracle import adm_net
+    g = load(golden_dir, "loops3_constrained.pt")
+    cfg = dict(weights.ADM_CONFIGS["adm_tiny"])
+    sg = cfg.pop("sigma")
+    sd = weights.adm_unet_state_dict(**cfg, seed=3)
+    ssd = weights.adm_sigma_state_dict(**sg, seed=4)
+    R, C = cfg["image_size"], 3
+    d = C * R * R
+    fwd = lambda z, t: adm_net.unet_forward(sd, z, t, cfg)
+    enc = lambda z, t: adm_net.unet_encode(sd, z, t, cfg)
+    sgf = lambda f: adm_net.sigma_forward(ssd, f, cfg)
+    for key, case in g.items():
+        if "|" not in key:
+            continue
+        task, scale = key.split("|")
+        op = {"sr_averagepooling": lambda: O.SuperResolution(C, R, int(scale)),
+              "inpainting_box": lambda: O.Inpainting(C, R, g["missing"]),
+              "colorization": lambda: O.Colorization(R),
+              "cs_walshhadamard": lambda: O.WalshHadamardCS(C, R, int(scale), g["perm"])}[task]()
+        deg = "inpainting" if task.startswith("inpainting") else task
+        y = op.A(case["x_true"].reshape(2, -1))
+        assert (y - case["y"].reshape(2, -1)).abs().max() < 1e-5, key
+        tab = S.Tables()
+        ts, sig, mvc = tab.ddim_schedule(20.0, None, 5)
+        assert torch.equal(ts, case["timesteps"]) and torch.equal(sig, case["sigmas"].float())
+        xT = case["z"] / (1 / (sig[0] ** 2 + 1)).sqrt()
+        log = []
+        with torch.no_grad():
+            x0 = S.denoise_loop(tab, ts.tolist(), sig, mvc, fwd, enc, sgf, xT, kind="ddim_simple_orig", eta=0.85,
+                                sampler_var="learned", style="pred", norm_eps=True, refine=True, norm_min=0.0,
+                                norm_max=30.0 / d ** 0.5, clip="dynamic", noises=case["noises"],
+                                constrain_fn=lambda v: op.project(v, case["y"]), sigma_pred_threshold=960,
+                                learn_epsvar=True, log=log,
+                                constrain_loss=lambda v: O.constraint_loss(op, deg, v, case["y"], C, R))
+        for i, st in enumerate(log):
+            for name in ("xt", "x0", "x_prev", "eps"):
+                ref = case[name][i]
+                assert (st[name] - ref).abs().max() <= 2e-5 * ref.abs().max(), (key, i, name)
+            assert (st["const"] - case["const"][i]).abs().max() <= 1e-4 * case["const"][i].abs().max(), (key, i)
+        assert (x0 - case["final"]).abs().max() <= 2e-5 * case["final"].abs().max(), key
