@@ -29,10 +29,36 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = dict(name="c2", R=64, steps=100, sampler="ddim_simple_orig", eta=0.85, start_sigma=100.0, style="pred",
-           norm_eps=True, refine=True, clip="clamp", norm_min=-2.0, norm_max=110.0, sigma_pred_threshold=960)
-GFLOP_PER_NFE = 60.57  # forward 48.10 + encode 12.22 + sigma 0.25 per sample
-CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH = 6, 32  # bounded CPU sample: ~10-20 s of host work on a 16-core box
+# Workloads.  c2 (BASELINE.json configs[1]) is the default and the one the driver's bench line is quoted on; c4 / c5 are
+# the ADM-256 restoration configs (configs[3], configs[4]), run with `--workload c4|c5|c5cs` for the ADM-256 numbers of
+# the north-star (tensor-pipe utilisation of the conv/attention GEMMs at batch 64 per GPU).  GFLOP per NFE: SURVEY §8(d).
+_NLC = dict(sampler="ddim_simple_orig", eta=0.85, start_sigma=100.0, style="pred", norm_eps=True, refine=True,
+            norm_min=-2.0, norm_max=110.0, sigma_pred_threshold=960)
+WORKLOADS = {
+    "c2": dict(_NLC, name="c2", arch="ddim", R=64, steps=100, clip="clamp", batch=256, gflop_per_nfe=60.57,
+               constraint=None, learn_epsvar=False, sampler_var="none",
+               label="c2: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, %d steps, NLC pred",
+               metric="DDIM+NLC images/sec (CelebA-64 unet_ddim, 100 steps)"),
+    "c4": dict(_NLC, name="adm256", arch="adm", R=256, steps=10, clip="dynamic", batch=32, gflop_per_nfe=2823.91,
+               constraint=("sr_averagepooling", 4.0), learn_epsvar=True, sampler_var="learned",
+               label="c4: ADM-256 UNet + sigma-model, DDNM SR x4 (svd projection), ddim_simple_orig eta 0.85, dynamic "
+                     "clip, %d steps, NLC pred",
+               metric="DDIM+NLC images/sec (ADM-256, DDNM SR x4)"),
+    "c5": dict(_NLC, name="adm256", arch="adm", R=256, steps=10, clip="dynamic", batch=64, gflop_per_nfe=2823.91,
+               constraint=("colorization", 1.0), learn_epsvar=True, sampler_var="learned",
+               label="c5: ADM-256 UNet + sigma-model, DDNM colourisation (svd projection), ddim_simple_orig eta 0.85, "
+                     "dynamic clip, %d steps, NLC pred",
+               metric="DDIM+NLC images/sec (ADM-256, DDNM colourisation)"),
+    "c5cs": dict(_NLC, name="adm256", arch="adm", R=256, steps=10, clip="dynamic", batch=64, gflop_per_nfe=2823.91,
+                 constraint=("cs_walshhadamard", 4.0), learn_epsvar=True, sampler_var="learned",
+                 label="c5: ADM-256 UNet + sigma-model, DDNM Walsh-Hadamard CS x4 (svd projection), ddim_simple_orig eta "
+                       "0.85, dynamic clip, %d steps, NLC pred",
+                 metric="DDIM+NLC images/sec (ADM-256, DDNM WH-CS x4)"),
+}
+CFG = dict(WORKLOADS["c2"])
+ADM_KEYS = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
+            "num_heads", "num_head_channels", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order")
+CPU_SAMPLE = {"ddim": (6, 32), "adm": (1, 2)}  # (timesteps, batch) of the bounded CPU sample: ~10-20 s of host work
 
 
 def peaks():
@@ -76,12 +102,27 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_port_rate(n_steps, batch, threads):
-    """images/s of the oracle port on the host: `n_steps` NLC sampling steps at `batch`, extrapolated to 100."""
-    from oracle import ddim_net, sampler as S, weights
+    """images/s of the oracle port on the host: `n_steps` NLC sampling steps at `batch`, extrapolated to the
+    workload's step count.  The constraint projection is left out of the CPU sample (it is <1 % of a step)."""
+    from oracle import sampler as S, weights
     torch.set_num_threads(threads)
-    cfg = weights.CONFIGS[CFG["name"]]
-    sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
-    ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+    if CFG["arch"] == "adm":
+        from oracle import adm_net
+        cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
+        sg = cfg.pop("sigma")
+        sd = weights.adm_unet_state_dict(**cfg, seed=3)
+        ssd = weights.adm_sigma_state_dict(**sg, seed=4)
+        fwd = lambda z, t: adm_net.unet_forward(sd, z, t, cfg)
+        enc = lambda z, t: adm_net.unet_encode(sd, z, t, cfg)
+        sg_fn = lambda f: adm_net.sigma_forward(ssd, f, cfg)
+    else:
+        from oracle import ddim_net
+        cfg = weights.CONFIGS[CFG["name"]]
+        sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
+        ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+        fwd = lambda z, t: ddim_net.unet_forward(sd, z, t)
+        enc = lambda z, t: ddim_net.unet_encode(sd, z, t)
+        sg_fn = lambda f: ddim_net.sigma_forward(ssd, f)
     tab = S.Tables()
     ts, sig, mvc = tab.ddim_schedule(CFG["start_sigma"], None, CFG["steps"])
     d = 3 * CFG["R"] ** 2
@@ -90,18 +131,29 @@ def cpu_port_rate(n_steps, batch, threads):
     xT = torch.randn(shape, generator=g) / (1 / (sig[0] ** 2 + 1)).sqrt()
     noises = [torch.randn(shape, generator=g) for _ in range(n_steps + 1)]
     first = next(i for i, t in enumerate(ts.tolist()) if t <= CFG["sigma_pred_threshold"])  # NLC-active steps
+    first = min(first, len(ts) - 2 - n_steps)
     args = dict(kind=CFG["sampler"], eta=CFG["eta"], style=CFG["style"], norm_eps=CFG["norm_eps"], refine=CFG["refine"],
-                norm_min=CFG["norm_min"] / d ** 0.5, norm_max=CFG["norm_max"] / d ** 0.5, clip=CFG["clip"])
-    fwd = lambda z, t: ddim_net.unet_forward(sd, z, t)
-    enc = lambda z, t: ddim_net.unet_encode(sd, z, t)
-    sg = lambda f: ddim_net.sigma_forward(ssd, f)
+                norm_min=CFG["norm_min"] / d ** 0.5, norm_max=CFG["norm_max"] / d ** 0.5, clip=CFG["clip"],
+                sampler_var=CFG["sampler_var"], learn_epsvar=CFG["learn_epsvar"])
     with torch.no_grad():
-        S.denoise_loop(tab, ts[first:first + 2].tolist(), sig[first:first + 2], mvc, fwd, enc, sg, xT, noises=noises, **args)
+        if CFG["arch"] != "adm":  # warm-up (the ADM sample is a single 10+ s step: no separate warm-up)
+            S.denoise_loop(tab, ts[first:first + 2].tolist(), sig[first:first + 2], mvc, fwd, enc, sg_fn, xT,
+                           noises=noises, **args)
         t0 = time.perf_counter()
-        S.denoise_loop(tab, ts[first:first + n_steps + 1].tolist(), sig[first:first + n_steps + 1], mvc, fwd, enc, sg,
+        S.denoise_loop(tab, ts[first:first + n_steps + 1].tolist(), sig[first:first + n_steps + 1], mvc, fwd, enc, sg_fn,
                        xT, noises=noises, **args)
         dt = time.perf_counter() - t0
     return batch / (dt / n_steps * CFG["steps"]), dt
+
+
+def _select(args):
+    CFG.clear()
+    CFG.update(WORKLOADS[args.workload])
+    if args.timesteps:
+        CFG["steps"] = args.timesteps
+    if args.batch:
+        CFG["batch"] = args.batch
+    CFG["label"] = CFG["label"] % CFG["steps"]
 
 
 def run_reference(args):
@@ -109,28 +161,51 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    n_steps, batch = CPU_SAMPLE[CFG["arch"]]
     per_step = []
-    for _ in range(args.warmup):
+    for _ in range(args.warmup if CFG["arch"] != "adm" else 0):
         cpu_port_rate(1, 4, threads)
     for _ in range(args.steps):
-        rate, dt = cpu_port_rate(CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH, threads)
-        per_step.append((rate, dt))
+        per_step.append(cpu_port_rate(n_steps, batch, threads))
     rate = sum(r for r, _ in per_step) / len(per_step)
     line = {
-        "impl": "reference", "metric": "DDIM+NLC images/sec (CelebA-64 unet_ddim, 100 steps)", "value": rate,
+        "impl": "reference", "metric": CFG["metric"], "value": rate,
         "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * 256 / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1000.0 * CFG["batch"] / rate, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "c2: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, 100 steps, NLC pred",
-                   "per_gpu_batch": 256},
+        "config": {"workload": CFG["label"], "per_gpu_batch": CFG["batch"]},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "each step = %d NLC timesteps at batch %d of the c2 workload on the oracle port "
-                                   "(torch fp32, %d threads, %.1f s per step), extrapolated linearly to 100 timesteps"
-                                   % (CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH, threads,
-                                      sum(d for _, d in per_step) / len(per_step))},
+                         "sample": "each step = %d NLC timesteps at batch %d of the workload on the oracle port "
+                                   "(torch fp32, %d threads, %.1f s per step), extrapolated linearly to %d timesteps"
+                                   % (n_steps, batch, threads, sum(d for _, d in per_step) / len(per_step),
+                                      CFG["steps"])},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def build_models(precision, dev):
+    """The workload's UNet + sigma-model executors with seeded synthetic weights (oracle/weights.py only provides the
+    state_dicts; no oracle arithmetic runs on this arm)."""
+    from oracle import weights
+    if CFG["arch"] == "adm":
+        from nlc_b200.unet_adm import SigmaModel, UNetModel
+        cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
+        sg = cfg.pop("sigma")
+        model = UNetModel(in_channels=3, precision=precision, device=dev, **{k: cfg[k] for k in ADM_KEYS}).load_state_dict(
+            weights.adm_unet_state_dict(**cfg, seed=3))
+        sigma_model = SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"],
+                                 num_heads=cfg["num_heads"], num_head_channels=cfg["num_head_channels"],
+                                 precision=precision, device=dev).load_state_dict(
+            weights.adm_sigma_state_dict(**sg, seed=4))
+        return model, sigma_model
+    from nlc_b200.unet_ddim import SigmaModel, UNetModel
+    cfg = weights.CONFIGS[CFG["name"]]
+    model = UNetModel(**cfg["unet"], precision=precision, device=dev).load_state_dict(
+        weights.ddim_unet_state_dict(**cfg["unet"], seed=3))
+    sigma_model = SigmaModel(**cfg["sigma"], precision=precision, device=dev).load_state_dict(
+        weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4))
+    return model, sigma_model
 
 
 def main():
@@ -139,20 +214,20 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="nlc", choices=["nlc", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
-    ap.add_argument("--timesteps", type=int, default=CFG["steps"])
+    ap.add_argument("--timesteps", type=int, default=0, help="sampling steps per pass (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _select(args)
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
-    from nlc_b200 import ops
+    from nlc_b200 import constraint_functions as CF, ops
     from nlc_b200.experiments import ImageExperiment
     from nlc_b200.schedulers import get_sampler
-    from nlc_b200.unet_ddim import SigmaModel, UNetModel
-    from oracle import weights  # synthetic seeded state_dicts only (no oracle arithmetic on this arm)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,32 +237,40 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    CFG["steps"] = args.timesteps
-    cfg = weights.CONFIGS[CFG["name"]]
-    B, R = args.batch, CFG["R"]
-    model = UNetModel(**cfg["unet"], precision=args.precision, device=dev).load_state_dict(
-        weights.ddim_unet_state_dict(**cfg["unet"], seed=3))
-    sigma_model = SigmaModel(**cfg["sigma"], precision=args.precision, device=dev).load_state_dict(
-        weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4))
+    B, R = CFG["batch"], CFG["R"]
+    model, sigma_model = build_models(args.precision, dev)
     sch = get_sampler(CFG["sampler"], 1000, CFG["steps"], start_sigma=CFG["start_sigma"], eta=CFG["eta"],
-                      sampler_var="none").to(dev)
+                      sampler_var=CFG["sampler_var"]).to(dev)
     exp = ImageExperiment(model, sch, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev)
-    exp.set_model(model, sigma_model, learn_epsvar=False)
+    exp.set_model(model, sigma_model, learn_epsvar=CFG["learn_epsvar"])
     exp.set_norm_maxmin(CFG["norm_min"], CFG["norm_max"])
     exp.set_clip_fn(CFG["clip"])
     shape = (B, 3, R, R)
     loop_kw = dict(style=CFG["style"], norm_eps=CFG["norm_eps"], refine_prior_sigma=CFG["refine"], return_log=False,
                    chunk_size=1, sigma_pred_threshold=CFG["sigma_pred_threshold"])
+    g_dev = torch.Generator(device=dev).manual_seed(99 + rank)
+    y_bytes = 0
+    if CFG["constraint"] is not None:
+        # DDNM restoration: synthetic ground truth x ~ U(-1,1), measurement y = A x, projection + loss every step
+        # (image_sample.py:636-665); the CS permutation is drawn once on the CPU with a fixed seed
+        from functools import partial
+        task, scale = CFG["constraint"]
+        con = CF.get_constraint_function(task, constraint_scale=scale, device=dev, image_size=R, channels=3,
+                                         perm=torch.randperm(R * R, generator=torch.Generator().manual_seed(7)))
+        x_true = torch.rand(shape, generator=g_dev, device=dev) * 2 - 1
+        y = con.transform(x_true)
+        y_bytes = y.numel() * 4
+        loop_kw.update(constrain_fn=partial(con.constraint_fn, y=y, lambda_t=con.lr),
+                       constrain_loss=partial(con.loss, y=y))
     gathered = [torch.empty(shape, device=dev) for _ in range(world)] if world > 1 else None
 
     conv_samples = []
+    every = 10 if CFG["steps"] >= 20 else 2  # conv kernels are timed on every 10th (2nd) timestep of the timed passes
 
     def hook(ind, _):
-        # time the conv kernel on every 10th timestep of the timed passes (CUDA events on the launching stream)
-        ops.STATS.conv_timer = conv_samples if (ind + 1) % 10 == 5 and hook.active else None
+        ops.STATS.conv_timer = conv_samples if (ind + 1) % every == every // 2 and hook.active else None
 
     hook.active = False
-    g_dev = torch.Generator(device=dev).manual_seed(99 + rank)
     xT = torch.randn(shape, generator=g_dev, device=dev) * (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5
 
     def one_pass_device():
@@ -263,38 +346,41 @@ def main():
     conv_ms = sum(a.elapsed_time(b) for _, a, b in conv_samples)
     conv_fl = sum(f for f, _, _ in conv_samples)
     achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    nfe_flops = GFLOP_PER_NFE * 1e9 * B * CFG["steps"]
+    nfe_flops = CFG["gflop_per_nfe"] * 1e9 * B * CFG["steps"]
+    sampled_timesteps = max(1, args.steps * sum(1 for i in range(CFG["steps"]) if (i + 1) % every == every // 2))
     roofline = {"bound": "tensor", "kernel": "nlc::conv_tc_kernel (tcgen05 implicit GEMM, %s)" % args.precision,
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src,
+                # dram__bytes_read+write of one launch of the step's top shape (3x3 conv 128->128 at 64x64, batch 256:
+                # 1.074 GB algorithmic) from the ncu --set full capture in profiles/r01_ncu_conv_tc_summary.md
+                "traffic": 1.021e9 if CFG["name"] == "c2" and B == 256 else None,
                 "launches_sampled": len(conv_samples),
-                "conv_share_of_step": (conv_ms / max(len(conv_samples), 1)) and None,
+                # share of the step spent in the conv kernel, from the sampled timesteps
+                "conv_share_of_step": (conv_ms / sampled_timesteps) / (ms_per_step / CFG["steps"]) if conv_ms > 0 else None,
                 "whole_step_tflops": nfe_flops / (ms_per_step / 1000.0) / 1e12}
-    # share of the step spent in the conv kernel, from the sampled timesteps (1 in 10)
-    sampled_timesteps = max(1, args.steps * (CFG["steps"] // 10))
-    roofline["conv_share_of_step"] = (conv_ms / sampled_timesteps) / (ms_per_step / CFG["steps"]) if conv_ms > 0 else None
 
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, dt = cpu_port_rate(CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH, threads)
+        n_steps, batch = CPU_SAMPLE[CFG["arch"]]
+        rate, dt = cpu_port_rate(n_steps, batch, threads)
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": "%d NLC timesteps at batch %d of the c2 workload on the oracle port (torch fp32, %d threads, "
-                         "%.1f s), extrapolated linearly to 100 timesteps" % (CPU_SAMPLE_STEPS, CPU_SAMPLE_BATCH,
-                                                                              threads, dt)}
+               "sample": "%d NLC timesteps at batch %d of the workload on the oracle port (torch fp32, %d threads, "
+                         "%.1f s), extrapolated linearly to %d timesteps" % (n_steps, batch, threads, dt, CFG["steps"])}
 
     line = {
-        "metric": "DDIM+NLC images/sec (CelebA-64 unet_ddim, 100 steps)", "value": value, "unit": "images/s",
+        "metric": CFG["metric"], "value": value, "unit": "images/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": "c2: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, %d steps, NLC pred"
-                               % CFG["steps"], "per_gpu_batch": B, "global_batch": B * world,
+        "config": {"workload": CFG["label"], "per_gpu_batch": B, "global_batch": B * world,
                    "step": "one full %d-timestep sampling pass of one batch" % CFG["steps"],
                    "l2": "activations per pass (GBs) exceed the 126 MB L2; no explicit flush",
                    "parallelism": "dp%d (batch sharded, NCCL all-gather of finished images)" % world},
         "nfe_per_s": value * CFG["steps"],
+        "ms_per_timestep": ms_per_step / CFG["steps"],
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes},
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes + y_bytes,
+                "d2h_bytes_per_step": nbytes},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

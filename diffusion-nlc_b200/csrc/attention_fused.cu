@@ -1,0 +1,328 @@
+// Fused multi-head self-attention on the tensor cores for the ADM attention levels (32x32 / 16x16: T = 1024 / 256
+// tokens, 64-channel heads; src/unet_adm.py:328-389 QKVAttentionLegacy / QKVAttention): S = Q K^T, softmax and
+// O = P V in one kernel, so the T x T logits and probabilities never touch HBM (the unfused path in attention.cu
+// writes and re-reads 6 bytes per logit: 1.6 GB per 32x32 attention block at batch 32).
+//
+// One persistent CTA per SM walks (image, head, 128-query block) tiles.  Per tile, with key blocks of 128 tokens:
+//   pass 1:  S_kb = Q K_kb^T (tcgen05, TMEM)  ->  softmax warps keep the running row maximum (no exp)
+//   pass 2:  S_kb again  ->  p = exp2((s - max) * scale*log2e), row sums in registers, P as bf16 into shared memory in
+//            the K-major SWIZZLE_128B operand layout  ->  O += P V_kb (tcgen05, accumulator stays in TMEM)
+//   epilogue: O / rowsum -> bf16 -> out[(n, token), head*64 + c]   (heads merged back into [B, T, C])
+// Recomputing S (0.27 GFLOP per tile, tensor-core time ~2 us) is cheaper than rescaling O in TMEM and keeps the exp
+// count at one per logit, which is what bounds the kernel (MUFU: 16 ex2 per clock per SM).
+//
+// Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax / epilogue (one query row per thread, TMEM lane = row).
+// V is consumed as V^T [B, heads, 64, T] (written by transpose_heads_kernel) so that both GEMMs see K-major operands.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace nlc {
+
+constexpr int kFaDh = 64;                       // head dimension
+constexpr int kFaBlock = 128;                   // queries per tile, keys per block
+constexpr int kFaStages = 4;                    // K / V^T ring
+constexpr int kFaTileBytes = kFaBlock * 128;    // 128 rows x 64 bf16 = 16 KB (Q, K block, one half of P)
+constexpr int kFaVtBytes = kFaDh * 128;         // 64 rows (channels) x 64 keys: 8 KB, two per key block
+constexpr int kFaStageBytes = kFaTileBytes + 2 * kFaVtBytes;  // 32 KB
+constexpr int kFaPBytes = 2 * kFaTileBytes;     // P block: two K chunks of 64 keys
+constexpr int kFaThreads = 64 + 128;
+constexpr int kFaSmem = kFaTileBytes + kFaStages * kFaStageBytes + 2 * kFaPBytes + 256 + 1024;
+constexpr int kFaTmemCols = 512;                // S double buffer (2 x 128) + O (64) -> next power of two
+
+struct FaParams {
+    CUtensorMap mapQ, mapK, mapVt;
+    int B, T, heads;
+    int n_qblk, n_kblk, n_tiles;
+    float scale_log2e;
+    __nv_bfloat16* out;
+    int ld_out;
+};
+
+__global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_constant__ FaParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + kFaTileBytes;
+    uint8_t* sP = sKV + kFaStages * kFaStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kFaPBytes);
+    uint64_t* kv_full = bars;                    // [kFaStages]
+    uint64_t* kv_empty = kv_full + kFaStages;    // [kFaStages]
+    uint64_t* q_full = kv_empty + kFaStages;
+    uint64_t* q_empty = q_full + 1;
+    uint64_t* s_full = q_empty + 1;              // [2]
+    uint64_t* s_empty = s_full + 2;              // [2]
+    uint64_t* p_full = s_empty + 2;              // [2]
+    uint64_t* p_empty = p_full + 2;              // [2]
+    uint64_t* o_full = p_empty + 2;
+    uint64_t* o_empty = o_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.mapQ);
+        tma_prefetch_desc(&p.mapK);
+        tma_prefetch_desc(&p.mapVt);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kFaStages; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 4);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&p_empty[i], 1);
+        }
+        mbar_init(o_full, 1);
+        mbar_init(o_empty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc<kFaTmemCols>(tmem_slot);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + 2 * kFaBlock;
+    const int nkb = p.n_kblk;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t kv_it = 0, tile_it = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
+                const int qb = tile % p.n_qblk;
+                const int bh = tile / p.n_qblk;
+                const int h = bh % p.heads, n = bh / p.heads;
+                mbar_wait(q_empty, (tile_it & 1) ^ 1);
+                mbar_expect_tx(q_full, kFaTileBytes);
+                tma_load_4d(sQ, &p.mapQ, q_full, 0, qb * kFaBlock, h, n);
+                for (int pass = 0; pass < 2; ++pass) {
+                    for (int kb = 0; kb < nkb; ++kb, ++kv_it) {
+                        const int st = kv_it % kFaStages;
+                        mbar_wait(&kv_empty[st], ((kv_it / kFaStages) & 1) ^ 1);
+                        uint8_t* sk = sKV + st * kFaStageBytes;
+                        mbar_expect_tx(&kv_full[st], pass ? kFaStageBytes : kFaTileBytes);
+                        tma_load_4d(sk, &p.mapK, &kv_full[st], 0, kb * kFaBlock, h, n);
+                        if (pass) {
+                            tma_load_3d(sk + kFaTileBytes, &p.mapVt, &kv_full[st], kb * kFaBlock, 0, bh);
+                            tma_load_3d(sk + kFaTileBytes + kFaVtBytes, &p.mapVt, &kv_full[st], kb * kFaBlock + 64, 0, bh);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc(1, kFaBlock, kFaBlock);  // 128 x 128, bf16
+            constexpr uint32_t idesc_o = umma_idesc(1, kFaBlock, kFaDh);     // 128 x 64
+            const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+            uint32_t kv_it = 0, s_it = 0, p_it = 0, tile_it = 0;
+            // S block `s_it` = Q K^T of the K tile in ring slot `kv_it`
+            auto issue_s = [&](uint32_t kv, uint32_t si) {
+                const int st = kv % kFaStages;
+                const int sb = si & 1;
+                mbar_wait(&s_empty[sb], ((si >> 1) & 1) ^ 1);
+                mbar_wait(&kv_full[st], (kv / kFaStages) & 1);
+                tc_fence_after_sync();
+                const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * kFaBlock, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+            };
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
+                mbar_wait(q_full, tile_it & 1);
+                tc_fence_after_sync();
+                // pass 1: logits only (row maxima)
+                for (int kb = 0; kb < nkb; ++kb, ++kv_it, ++s_it) {
+                    issue_s(kv_it, s_it);
+                    umma_commit(&kv_empty[kv_it % kFaStages]);
+                    umma_commit(&s_full[s_it & 1]);
+                }
+                // pass 2: S(kb+1) is issued before P(kb) is awaited, so Q K^T overlaps the softmax of the previous block
+                issue_s(kv_it, s_it);
+                umma_commit(&s_full[s_it & 1]);
+                mbar_wait(o_empty, (tile_it & 1) ^ 1);  // the previous tile's O has been read out of TMEM
+                for (int kb = 0; kb < nkb; ++kb, ++p_it) {
+                    if (kb + 1 < nkb) {
+                        issue_s(kv_it + kb + 1, s_it + kb + 1);
+                        umma_commit(&s_full[(s_it + kb + 1) & 1]);
+                    } else {
+                        umma_commit(q_empty);  // every Q K^T of this tile has been issued: Q may be overwritten once done
+                    }
+                    const int pb = p_it & 1;
+                    const int st = (kv_it + kb) % kFaStages;
+                    mbar_wait(&p_full[pb], (p_it >> 1) & 1);
+                    tc_fence_after_sync();
+                    const uint32_t pbase = smem_u32(sP + pb * kFaPBytes);
+                    const uint32_t vbase = smem_u32(sKV + st * kFaStageBytes + kFaTileBytes);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint64_t pdesc = umma_desc_sw128(pbase + c * kFaTileBytes);
+                        const uint64_t vdesc = umma_desc_sw128(vbase + c * kFaVtBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_o, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (kb | c | k) != 0);
+                    }
+                    umma_commit(&kv_empty[st]);
+                    umma_commit(&p_empty[pb]);
+                }
+                umma_commit(o_full);
+                kv_it += nkb;
+                s_it += nkb;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax + epilogue: one query row per thread
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const uint32_t lane_addr = static_cast<uint32_t>(quad * 32) << 16;
+        uint32_t s_it = 0, p_it = 0, tile_it = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
+            const int qb = tile % p.n_qblk;
+            const int bh = tile / p.n_qblk;
+            const int h = bh % p.heads, n = bh / p.heads;
+            // pass 1: running maximum of the raw logits
+            float m = -INFINITY;
+            for (int kb = 0; kb < nkb; ++kb, ++s_it) {
+                const int sb = s_it & 1;
+                mbar_wait(&s_full[sb], (s_it >> 1) & 1);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int c = 0; c < kFaBlock; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * kFaBlock + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[sb]);
+            }
+            const float mc = m * p.scale_log2e;
+            // pass 2: probabilities (unnormalised) -> shared memory, row sum in a register
+            float sum = 0.f;
+            for (int kb = 0; kb < nkb; ++kb, ++s_it, ++p_it) {
+                const int sb = s_it & 1, pb = p_it & 1;
+                mbar_wait(&s_full[sb], (s_it >> 1) & 1);
+                tc_fence_after_sync();
+                mbar_wait(&p_empty[pb], ((p_it >> 1) & 1) ^ 1);  // O += P V of two blocks ago has finished reading it
+                uint8_t* prow = sP + pb * kFaPBytes + row * 128;
+#pragma unroll 1
+                for (int c = 0; c < kFaBlock; c += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * kFaBlock + c, v);
+                    tmem_ld_wait();
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float a = exp2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mc));
+                        const float b = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mc));
+                        sum += a + b;
+                        pk[i] = pack_bf16x2(a, b);
+                    }
+                    // keys [c, c+32) = 16-byte chunks j0..j0+3 of K chunk (c / 64); SWIZZLE_128B: chunk ^ (row & 7)
+                    uint8_t* dst = prow + (c >> 6) * kFaTileBytes;
+                    const int j0 = (c & 63) >> 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(dst + (((j0 + j) ^ (row & 7)) << 4)) =
+                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[sb]);
+                fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&p_full[pb]);
+            }
+            // epilogue: O / sum -> bf16 -> out[(n, q), h*64 + c]
+            mbar_wait(o_full, tile_it & 1);
+            tc_fence_after_sync();
+            const float inv = 1.0f / sum;
+            __nv_bfloat16* orow = p.out + (static_cast<size_t>(n) * p.T + qb * kFaBlock + row) * p.ld_out + h * kFaDh;
+#pragma unroll 1
+            for (int c = 0; c < kFaDh; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_o + lane_addr + c, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        w[i] = pack_bf16x2(__uint_as_float(v[8 * j + 2 * i]) * inv, __uint_as_float(v[8 * j + 2 * i + 1]) * inv);
+                    *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty);
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<kFaTmemCols>(tmem_base);
+    }
+}
+
+}  // namespace nlc
+
+using namespace nlc;
+
+// Internal entry (declared in attention.cu): q/k inside the qkv tensor, V^T already in `vt` as [B*heads, 64, T].
+int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, int k_off, int head_stride, int B, int T,
+                             int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream) {
+    NLC_REQUIRE(T % kFaBlock == 0 && T >= kFaBlock, "nlc_attention(fused): T=%d must be a multiple of %d", T, kFaBlock);
+    NLC_REQUIRE(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && head_stride % 8 == 0 && ld_out % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(vt) & 15) == 0,
+                "nlc_attention(fused): tensors must be 16-byte aligned");
+    FaParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B, p.T = T, p.heads = heads;
+    p.n_qblk = T / kFaBlock, p.n_kblk = T / kFaBlock;
+    p.n_tiles = B * heads * p.n_qblk;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.out = static_cast<__nv_bfloat16*>(out), p.ld_out = ld_out;
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
+    for (int which = 0; which < 2; ++which) {
+        // (channel within head, token, head, image)
+        cuuint64_t gdim[4] = {(cuuint64_t)kFaDh, (cuuint64_t)T, (cuuint64_t)heads, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(heads > 1 ? head_stride : kFaDh) * 2,
+                              (cuuint64_t)T * ld * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kFaDh, (cuuint32_t)kFaBlock, 1, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = ctx->encode_tiled(which ? &p.mapK : &p.mapQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                       const_cast<__nv_bfloat16*>(base + (which ? k_off : q_off)), gdim, gstr, box, estr,
+                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_attention(fused): cuTensorMapEncodeTiled(%s) failed with %d",
+                    which ? "K" : "Q", (int)r);
+    }
+    {
+        // V^T: (token, channel, image*head)
+        cuuint64_t gdim[3] = {(cuuint64_t)T, (cuuint64_t)kFaDh, (cuuint64_t)B * heads};
+        cuuint64_t gstr[2] = {(cuuint64_t)T * 2, (cuuint64_t)T * kFaDh * 2};
+        cuuint32_t box[3] = {64, (cuuint32_t)kFaDh, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ctx->encode_tiled(&p.mapVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(vt), gdim, gstr, box,
+                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_attention(fused): cuTensorMapEncodeTiled(V^T) failed with %d", (int)r);
+    }
+    static bool configured = false;
+    if (!configured) {
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
+        configured = true;
+    }
+    const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+    attn_fused_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(p);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
