@@ -144,10 +144,30 @@ __global__ void __launch_bounds__(256)
 
 using namespace nlc;
 
+// attention_fused.cu
+int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, int k_off, int head_stride, int B, int T,
+                             int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream);
+
+// The fused kernel serves bf16, 64-channel heads and T a multiple of 128 (the ADM 32x32 / 16x16 levels); everything
+// else (fp32-container accuracy modes, the single-head dh = C blocks of unet_ddim / SongUNet) takes the GEMM + softmax
+// + GEMM path below.  NLC_FUSED_ATTN=0 disables it (A/B measurements).
+static bool fused_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NLC_FUSED_ATTN");
+        v = !(e && e[0] == '0');
+    }
+    return v != 0;
+}
+static bool use_fused(int op_dtype, int T, int dh) {
+    return op_dtype == NLC_BF16 && dh == 64 && T >= 128 && T % 128 == 0 && fused_enabled();
+}
+
 extern "C" size_t nlc_attention_ws(int op_dtype, int B, int T, int heads, int dh) {
     if (T < 128) return 0;
     const size_t esz = op_dtype != NLC_BF16 ? 4 : 2;
     const size_t bh = static_cast<size_t>(B) * heads;
+    if (use_fused(op_dtype, T, dh)) return bh * dh * T * esz + 1024;  // V^T only
     return bh * T * T * 4 + bh * T * T * esz + bh * dh * T * esz + 1024;
 }
 
@@ -182,10 +202,11 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
     NLC_REQUIRE(workspace, "nlc_attention: workspace required for T >= 128");
     NLC_REQUIRE(T % 64 == 0 && T <= 1024 && dh % 64 == 0, "nlc_attention: T=%d dh=%d unsupported", T, dh);
     const size_t bh = static_cast<size_t>(B) * heads;
+    const bool fused = use_fused(op_dtype, T, dh);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     float* S = reinterpret_cast<float*>(ws);
     void* P = ws + bh * T * T * 4;
-    void* VT = static_cast<uint8_t*>(P) + bh * T * T * esz;
+    void* VT = fused ? static_cast<void*>(ws) : static_cast<void*>(static_cast<uint8_t*>(P) + bh * T * T * esz);
     const uint8_t* q8 = static_cast<const uint8_t*>(qkv);
 
     // V^T
@@ -200,6 +221,9 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
                 static_cast<__nv_bfloat16*>(VT));
         NLC_CHECK_LAUNCH();
     }
+    if (fused)
+        return nlc_attention_fused_bf16(ctx, qkv, ld, q_off, k_off, head_stride, B, T, heads, scale, VT, out_op, ld_out,
+                                        stream);
     // S = scale * Q K^T   ("image" = sample, "row" = head, "column" = query token)
     {
         nlc_conv_desc d;

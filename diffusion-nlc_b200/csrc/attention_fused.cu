@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float a = exp2f(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mc));
-                        const float b = exp2f(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mc));
+                        const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mc));
+                        const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mc));
                         sum += a + b;
                         pk[i] = pack_bf16x2(a, b);
                     }

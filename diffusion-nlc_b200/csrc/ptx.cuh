@@ -264,6 +264,11 @@ __device__ __forceinline__ float round_tf32(float x) {
     return __uint_as_float(r);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2, flush-to-zero
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // Operand-copy value in an fp32 container: tf32-rounded (NLC_F32) or untouched (NLC_F32X3, split later by the conv).
 __device__ __forceinline__ float op_f32(float x, int rnd) { return rnd ? round_tf32(x) : x; }
 

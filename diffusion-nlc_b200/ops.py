@@ -271,7 +271,7 @@ def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale,
     _lib.check(_lib.lib().nlc_attention(
         _ctx(qkv.t), C.c_void_p(qkv.ptr), op_dtype, qkv.ld, q_off, k_off, v_off, head_stride, qkv.B, T, heads, dh,
         scale, C.c_void_p(out.ptr), out.ld, _p(ws), _stream()))
-    STATS.launches += 4 if T >= 128 else 1
+    STATS.launches += (2 if (op_dtype == NLC_BF16 and dh == 64 and T % 128 == 0) else 4) if T >= 128 else 1
 
 
 @_timed("linear")

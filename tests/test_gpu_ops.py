@@ -148,7 +148,10 @@ def test_groupnorm_large_mean_is_stable(dev):
 
 
 ATTN_CASES = [(3, 16, 1, 512, False), (2, 64, 4, 64, True), (2, 64, 1, 256, False), (3, 256, 1, 256, False),
-              (2, 1024, 4, 64, False), (2, 256, 4, 64, True)]
+              (2, 1024, 4, 64, False), (2, 256, 4, 64, True),
+              # the fused tcgen05 kernel (bf16, 64-channel heads, T % 128 == 0): one key block, odd batch, more tiles
+              # than SMs (several tiles per persistent CTA), both qkv orders
+              (3, 128, 2, 64, True), (1, 512, 8, 64, False), (5, 256, 16, 64, True), (3, 1024, 8, 64, True)]
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16", 8e-3), ("tf32", 1e-3)])
@@ -172,7 +175,7 @@ def test_attention(dev, prec, tol, case):
     scale = dh ** -0.5
     w = torch.softmax(torch.einsum("bthd,bshd->bhts", q, k) * scale, dim=-1)
     ref = torch.einsum("bhts,bshd->bthd", w, v).reshape(B, T, C)
-    side = int(T ** 0.5)
+    side = 1 << ((T.bit_length() - 1) // 2)  # H x W = T (T is a power of two, not always a square)
     out = ops.Act(torch.zeros(B, side, T // side, C, device=dev, dtype=tdt))
     ws = torch.zeros(max(ops.attention_ws(dt, B, T, heads, dh), 16), device=dev, dtype=torch.uint8)
     ops.attention(ops.Act(qkv.view(B, side, T // side, 3 * C)), dt, offs[0], offs[1], offs[2], offs[3], heads, dh, scale,
