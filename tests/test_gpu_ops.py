@@ -316,6 +316,11 @@ PAIR_CASES = [
     (80, 16, 16, 64, 128, 1, (1, 1, 1, 1), 3),     # BLOCK_N 128 pairs
     (48, 32, 32, 128, 512, 2, (0, 1, 0, 1), 3),    # stride 2, two N tiles
     (20, 64, 64, 192, 256, 1, (0, 0, 0, 0), 1),    # 1x1, K = 192 (three chunks)
+    # W >= 128: an M tile is 128 pixels of one image row (the ADM 256x256 / 128x128 levels)
+    (2, 128, 128, 128, 256, 1, (1, 1, 1, 1), 3),   # one tile per image row
+    (1, 256, 256, 64, 128, 1, (1, 1, 1, 1), 3),    # two tiles per row, BLOCK_N 128
+    (3, 128, 128, 192, 512, 1, (1, 1, 1, 1), 3),   # three K chunks per tap, two N tiles, odd batch
+    (2, 128, 128, 128, 256, 1, (0, 0, 0, 0), 1),   # 1x1
 ]
 
 
@@ -351,3 +356,25 @@ def test_conv_tc_cta_pair_kernel(dev, prec, case):
         assert (st.t[:, :, 0].double() - blk.mean(2)).abs().max() < 1e-5 * blk.abs().max()
         m2 = ((blk - blk.mean(2, keepdim=True)) ** 2).sum(2)
         assert ((st.t[:, :, 1].double() - m2) / m2.clamp_min(1e-6)).abs().max() < 1e-3
+
+
+def test_conv_tc_pair_kernel_fused_shortcut_wide_rows(dev):
+    """The CTA-pair kernel with a mixed segment list at 128-pixel rows: 3x3 over one source + the ResNet block's 1x1
+    shortcut over a channel slice of a second, wider buffer, bf16."""
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16
+    B, H, C0, C1, Cout = 2, 128, 128, 192, 256
+    g = torch.Generator().manual_seed(23)
+    x0 = _rnd(torch.randn(B, C0, H, H, generator=g).to(dev), NLC_BF16)
+    x1 = _rnd(torch.randn(B, C1, H, H, generator=g).to(dev), NLC_BF16)
+    w0 = _rnd((torch.randn(Cout, C0, 3, 3, generator=g) / (C0 * 9) ** 0.5).to(dev), NLC_BF16)
+    w1 = _rnd((torch.randn(Cout, C1, 1, 1, generator=g) / C1 ** 0.5).to(dev), NLC_BF16)
+    ref = F.conv2d(x0, w0, padding=1) + F.conv2d(x1, w1)
+    buf = torch.zeros(B, H, H, C1 + 64, device=dev, dtype=torch.bfloat16)
+    buf[..., 64:] = x1.permute(0, 2, 3, 1).to(torch.bfloat16)
+    out = ops.Act(torch.zeros(B, H, H, Cout, device=dev))
+    ops.conv_tc([ops.Act(x0.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)), ops.Act(buf, 64, C1)],
+                ops.taps3x3(0, 0, C0) + [(1, 0, 0, 0, C1)], ops.pack_conv_weight(w0, NLC_BF16, extra=w1), Cout, B, H, H,
+                NLC_BF16, out_f32=out)
+    torch.cuda.synchronize()
+    assert _rel(out.t.permute(0, 3, 1, 2), ref) < 5e-5
