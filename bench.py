@@ -39,6 +39,10 @@ WORKLOADS = {
                constraint=None, learn_epsvar=False, sampler_var="none",
                label="c2: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, %d steps, NLC pred",
                metric="DDIM+NLC images/sec (CelebA-64 unet_ddim, 100 steps)"),
+    "c3": dict(name="edm64", arch="edm", R=64, steps=18, batch=512, gflop_per_nfe=108.07, nfe_per_pass=35,
+               style="pred_partial,pred", norm_eps="000", refine=False, constraint=None, norm_min=-2.0, norm_max=110.0,
+               label="c3: EDM SongUNet-64 (DDPM++) + sigma-model, Heun sampler, %d steps = 35 NFE, NLC pred_partial,pred",
+               metric="EDM Heun+NLC images/sec (SongUNet-64, 35 NFE)"),
     "c4": dict(_NLC, name="adm256", arch="adm", R=256, steps=10, clip="dynamic", batch=32, gflop_per_nfe=2823.91,
                constraint=("sr_averagepooling", 4.0), learn_epsvar=True, sampler_var="learned",
                label="c4: ADM-256 UNet + sigma-model, DDNM SR x4 (svd projection), ddim_simple_orig eta 0.85, dynamic "
@@ -58,7 +62,7 @@ WORKLOADS = {
 CFG = dict(WORKLOADS["c2"])
 ADM_KEYS = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
             "num_heads", "num_head_channels", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order")
-CPU_SAMPLE = {"ddim": (6, 32), "adm": (1, 2)}  # (timesteps, batch) of the bounded CPU sample: ~10-20 s of host work
+CPU_SAMPLE = {"ddim": (6, 32), "adm": (1, 2), "edm": (3, 16)}  # (timesteps, batch) of the bounded CPU sample: ~10-20 s of host work
 
 
 def peaks():
@@ -106,6 +110,24 @@ def cpu_port_rate(n_steps, batch, threads):
     workload's step count.  The constraint projection is left out of the CPU sample (it is <1 % of a step)."""
     from oracle import sampler as S, weights
     torch.set_num_threads(threads)
+    if CFG["arch"] == "edm":
+        # `n_steps` Heun steps (2 NFE each, the last one Euler only) of the reference's sigma ladder at `batch`
+        from oracle import edm_net, sampler_edm
+        cfg = dict(weights.EDM_CONFIGS[CFG["name"]])
+        sg = cfg.pop("sigma")
+        sd = weights.edm_unet_state_dict(**cfg, seed=3)
+        ssd = weights.edm_sigma_state_dict(**sg, seed=4)
+        d = 3 * CFG["R"] ** 2
+        o = sampler_edm.EDM(lambda x, c: edm_net.unet_forward(sd, x, c, cfg), lambda x, c: edm_net.unet_encode(sd, x, c, cfg),
+                            lambda f: edm_net.sigma_forward(ssd, f), d, norm_min=CFG["norm_min"] / d ** 0.5,
+                            norm_max=CFG["norm_max"] / d ** 0.5)
+        lat = torch.randn(batch, 3, CFG["R"], CFG["R"], generator=torch.Generator().manual_seed(0))
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            o.sample(lat, n_steps, style=CFG["style"], norm_eps=CFG["norm_eps"], refine=CFG["refine"])
+            dt = time.perf_counter() - t0
+        nfe = 2 * n_steps - 1
+        return batch / (dt / nfe * CFG["nfe_per_pass"]), dt
     if CFG["arch"] == "adm":
         from oracle import adm_net
         cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
@@ -188,6 +210,15 @@ def build_models(precision, dev):
     """The workload's UNet + sigma-model executors with seeded synthetic weights (oracle/weights.py only provides the
     state_dicts; no oracle arithmetic runs on this arm)."""
     from oracle import weights
+    if CFG["arch"] == "edm":
+        from nlc_b200.edm_networks import SigmaModel, SongUNet
+        cfg = dict(weights.EDM_CONFIGS[CFG["name"]])
+        sg = cfg.pop("sigma")
+        model = SongUNet(precision=precision, device=dev, **cfg).load_state_dict(
+            weights.edm_unet_state_dict(**cfg, seed=3))
+        sigma_model = SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"], precision=precision,
+                                 device=dev).load_state_dict(weights.edm_sigma_state_dict(**sg, seed=4))
+        return model, sigma_model
     if CFG["arch"] == "adm":
         from nlc_b200.unet_adm import SigmaModel, UNetModel
         cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
@@ -239,31 +270,10 @@ def main():
 
     B, R = CFG["batch"], CFG["R"]
     model, sigma_model = build_models(args.precision, dev)
-    sch = get_sampler(CFG["sampler"], 1000, CFG["steps"], start_sigma=CFG["start_sigma"], eta=CFG["eta"],
-                      sampler_var=CFG["sampler_var"]).to(dev)
-    exp = ImageExperiment(model, sch, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev)
-    exp.set_model(model, sigma_model, learn_epsvar=CFG["learn_epsvar"])
-    exp.set_norm_maxmin(CFG["norm_min"], CFG["norm_max"])
-    exp.set_clip_fn(CFG["clip"])
     shape = (B, 3, R, R)
-    loop_kw = dict(style=CFG["style"], norm_eps=CFG["norm_eps"], refine_prior_sigma=CFG["refine"], return_log=False,
-                   chunk_size=1, sigma_pred_threshold=CFG["sigma_pred_threshold"])
     g_dev = torch.Generator(device=dev).manual_seed(99 + rank)
     y_bytes = 0
-    if CFG["constraint"] is not None:
-        # DDNM restoration: synthetic ground truth x ~ U(-1,1), measurement y = A x, projection + loss every step
-        # (image_sample.py:636-665); the CS permutation is drawn once on the CPU with a fixed seed
-        from functools import partial
-        task, scale = CFG["constraint"]
-        con = CF.get_constraint_function(task, constraint_scale=scale, device=dev, image_size=R, channels=3,
-                                         perm=torch.randperm(R * R, generator=torch.Generator().manual_seed(7)))
-        x_true = torch.rand(shape, generator=g_dev, device=dev) * 2 - 1
-        y = con.transform(x_true)
-        y_bytes = y.numel() * 4
-        loop_kw.update(constrain_fn=partial(con.constraint_fn, y=y, lambda_t=con.lr),
-                       constrain_loss=partial(con.loss, y=y))
-    gathered = [torch.empty(shape, device=dev) for _ in range(world)] if world > 1 else None
-
+    gathered = None
     conv_samples = []
     every = 10 if CFG["steps"] >= 20 else 2  # conv kernels are timed on every 10th (2nd) timestep of the timed passes
 
@@ -271,10 +281,55 @@ def main():
         ops.STATS.conv_timer = conv_samples if (ind + 1) % every == every // 2 and hook.active else None
 
     hook.active = False
-    xT = torch.randn(shape, generator=g_dev, device=dev) * (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5
+    if CFG["arch"] == "edm":
+        from nlc_b200.experiments import EDMImageExperiment
+        exp = EDMImageExperiment(model, None, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev,
+                                 num_timesteps=CFG["steps"])
+        exp.set_model(model, sigma_model, learn_epsvar=False)
+        exp.set_norm_maxmin(CFG["norm_min"], CFG["norm_max"])
+        edm_kw = dict(style=CFG["style"], norm_eps=CFG["norm_eps"], refine_prior_sigma=CFG["refine"])
+        lat_dev = torch.randn(shape, generator=g_dev, device=dev)
+        out_dtype, x_scale = torch.float64, 1.0
+        if world > 1:
+            gathered = [torch.empty(shape, device=dev, dtype=torch.float64) for _ in range(world)]
+
+        def sample(x_in, to_cpu, with_hook):
+            out = exp.edm_sampler(shape, latents=x_in, step_hook=hook if with_hook else None, **edm_kw)
+            return out.cpu() if to_cpu else out
+    else:
+        sch = get_sampler(CFG["sampler"], 1000, CFG["steps"], start_sigma=CFG["start_sigma"], eta=CFG["eta"],
+                          sampler_var=CFG["sampler_var"]).to(dev)
+        exp = ImageExperiment(model, sch, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev)
+        exp.set_model(model, sigma_model, learn_epsvar=CFG["learn_epsvar"])
+        exp.set_norm_maxmin(CFG["norm_min"], CFG["norm_max"])
+        exp.set_clip_fn(CFG["clip"])
+        loop_kw = dict(style=CFG["style"], norm_eps=CFG["norm_eps"], refine_prior_sigma=CFG["refine"], return_log=False,
+                       chunk_size=1, sigma_pred_threshold=CFG["sigma_pred_threshold"])
+        if CFG["constraint"] is not None:
+            # DDNM restoration: synthetic ground truth x ~ U(-1,1), measurement y = A x, projection + loss every step
+            # (image_sample.py:636-665); the CS permutation is drawn once on the CPU with a fixed seed
+            from functools import partial
+            task, scale = CFG["constraint"]
+            con = CF.get_constraint_function(task, constraint_scale=scale, device=dev, image_size=R, channels=3,
+                                             perm=torch.randperm(R * R, generator=torch.Generator().manual_seed(7)))
+            x_true = torch.rand(shape, generator=g_dev, device=dev) * 2 - 1
+            y = con.transform(x_true)
+            y_bytes = y.numel() * 4
+            loop_kw.update(constrain_fn=partial(con.constraint_fn, y=y, lambda_t=con.lr),
+                           constrain_loss=partial(con.loss, y=y))
+        x_scale = (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5
+        lat_dev = torch.randn(shape, generator=g_dev, device=dev) * x_scale
+        out_dtype = torch.float32
+        if world > 1:
+            gathered = [torch.empty(shape, device=dev) for _ in range(world)]
+
+        def sample(x_in, to_cpu, with_hook):
+            out, _ = exp.denoise_loop(shape=shape, xT=x_in, to_cpu=to_cpu, step_hook=hook if with_hook else None,
+                                      **loop_kw)
+            return out
 
     def one_pass_device():
-        out, _ = exp.denoise_loop(shape=shape, xT=xT, to_cpu=False, step_hook=hook, **loop_kw)
+        out = sample(lat_dev, False, True)
         if world > 1:
             dist.all_gather(gathered, out.contiguous())
         return out
@@ -315,11 +370,13 @@ def main():
     gen = torch.Generator().manual_seed(4321 + rank)
 
     def one_pass_e2e():
-        # the reference draws x_T on the CPU generator (src/experiments.py:268); pinned staging, H2D, loop, D2H
+        # the reference draws the initial noise on the host side (src/experiments.py:268; per-sample generators for EDM):
+        # pinned staging, H2D, the whole sampling loop through the public API, D2H of the finished images
         torch.randn(shape, generator=gen, out=pinned)
-        x = pinned.to(dev, non_blocking=True) * (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5
-        out, _ = exp.denoise_loop(shape=shape, xT=x, to_cpu=True, **loop_kw)
-        return out
+        x = pinned.to(dev, non_blocking=True)
+        if x_scale != 1.0:
+            x = x * x_scale
+        return sample(x, True, False)
 
     one_pass_e2e()
     barrier()
@@ -335,6 +392,7 @@ def main():
         e2e_s = float(te.item())
     e2e_value = B * world / e2e_s
     nbytes = B * 3 * R * R * 4
+    out_bytes = B * 3 * R * R * (8 if out_dtype == torch.float64 else 4)
 
     if rank != 0:
         if world > 1:
@@ -346,7 +404,8 @@ def main():
     conv_ms = sum(a.elapsed_time(b) for _, a, b in conv_samples)
     conv_fl = sum(f for f, _, _ in conv_samples)
     achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
-    nfe_flops = CFG["gflop_per_nfe"] * 1e9 * B * CFG["steps"]
+    nfe_per_pass = CFG.get("nfe_per_pass", CFG["steps"])
+    nfe_flops = CFG["gflop_per_nfe"] * 1e9 * B * nfe_per_pass
     sampled_timesteps = max(1, args.steps * sum(1 for i in range(CFG["steps"]) if (i + 1) % every == every // 2))
     roofline = {"bound": "tensor", "kernel": "nlc::conv_tc_kernel (tcgen05 implicit GEMM, %s)" % args.precision,
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
@@ -376,11 +435,11 @@ def main():
                    "step": "one full %d-timestep sampling pass of one batch" % CFG["steps"],
                    "l2": "activations per pass (GBs) exceed the 126 MB L2; no explicit flush",
                    "parallelism": "dp%d (batch sharded, NCCL all-gather of finished images)" % world},
-        "nfe_per_s": value * CFG["steps"],
+        "nfe_per_s": value * nfe_per_pass,
         "ms_per_timestep": ms_per_step / CFG["steps"],
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes + y_bytes,
-                "d2h_bytes_per_step": nbytes},
+                "d2h_bytes_per_step": out_bytes},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
