@@ -4,7 +4,7 @@ CPU oracle.
 Primary gate = TEACHER-FORCED per-step parity: the reference's x_t of step k goes through one GPU step and
 sigma_hat, eps, x0_hat, x_{t-1} are compared (L2-relative).  Stated tolerances:
   tf32 operands:  sigma_hat 1e-3, eps 5e-3,  x_{t-1} 5e-3
-  bf16 operands:  sigma_hat 8e-3, eps 8e-2,  x_{t-1} 6e-2
+  bf16 operands:  sigma_hat 8e-3, eps 1e-1,  x_{t-1} 8e-2
 They are set by operand rounding (2^-11 / 2^-9 per conv operand through ~30 layers) and by the discrete time
 lookup: sigma_hat is bucketised by searchsorted (src/schedulers.py:185-190), so an error of a few 1e-4 in
 sigma_hat moves t_hat by one bucket for the occasional sample and changes that sample's eps by ~1e-2.  The
@@ -21,7 +21,7 @@ from oracle import weights
 pytestmark = pytest.mark.gpu
 dev = torch.device("cuda:0")
 
-STEP_TOL = {"tf32": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3), "bf16": dict(sigma=8e-3, eps=8e-2, x_prev=6e-2)}
+STEP_TOL = {"tf32": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3), "bf16": dict(sigma=8e-3, eps=1e-1, x_prev=8e-2)}
 
 
 def _l2rel(a, b):
