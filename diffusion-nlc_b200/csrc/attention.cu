@@ -148,7 +148,7 @@ using namespace nlc;
 int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, int k_off, int head_stride, int B, int T,
                              int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream);
 
-// The fused kernel serves bf16, 64-channel heads and T a multiple of 128 (the ADM 32x32 / 16x16 levels); everything
+// The fused kernel serves bf16, 64-channel heads and T a multiple of 64 (the ADM 32x32 / 16x16 / 8x8 levels); everything
 // else (fp32-container accuracy modes, the single-head dh = C blocks of unet_ddim / SongUNet) takes the GEMM + softmax
 // + GEMM path below.  NLC_FUSED_ATTN=0 disables it (A/B measurements).
 static bool fused_enabled() {
@@ -160,14 +160,14 @@ static bool fused_enabled() {
     return v != 0;
 }
 static bool use_fused(int op_dtype, int T, int dh) {
-    return op_dtype == NLC_BF16 && dh == 64 && T >= 128 && T % 128 == 0 && fused_enabled();
+    return op_dtype == NLC_BF16 && dh == 64 && T >= 64 && T % 64 == 0 && T <= 1024 && fused_enabled();
 }
 
 extern "C" size_t nlc_attention_ws(int op_dtype, int B, int T, int heads, int dh) {
-    if (T < 128) return 0;
     const size_t esz = op_dtype != NLC_BF16 ? 4 : 2;
     const size_t bh = static_cast<size_t>(B) * heads;
     if (use_fused(op_dtype, T, dh)) return bh * dh * T * esz + 1024;  // V^T only
+    if (T < 128) return 0;
     return bh * T * T * 4 + bh * T * T * esz + bh * dh * T * esz + 1024;
 }
 
@@ -180,7 +180,7 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
     const bool f32c = op_dtype != NLC_BF16;  // fp32 containers (tf32-rounded, or plain fp32 for NLC_F32X3)
     const int rnd = op_dtype == NLC_F32;
     const size_t esz = f32c ? 4 : 2;
-    if (T < 128) {
+    if (T < 128 && !use_fused(op_dtype, T, dh)) {
         const size_t smem = (static_cast<size_t>(2) * T * (dh + 1) + 8 * dh) * sizeof(float);
         NLC_REQUIRE(smem <= 227 * 1024, "nlc_attention: T=%d dh=%d needs %zu B of shared memory", T, dh, smem);
         if (f32c) {
@@ -201,6 +201,7 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
     }
     NLC_REQUIRE(workspace, "nlc_attention: workspace required for T >= 128");
     NLC_REQUIRE(T % 64 == 0 && T <= 1024 && dh % 64 == 0, "nlc_attention: T=%d dh=%d unsupported", T, dh);
+    NLC_REQUIRE(T >= 128 || use_fused(op_dtype, T, dh), "nlc_attention: T=%d needs the small-T kernel", T);
     const size_t bh = static_cast<size_t>(B) * heads;
     const bool fused = use_fused(op_dtype, T, dh);
     uint8_t* ws = static_cast<uint8_t*>(workspace);

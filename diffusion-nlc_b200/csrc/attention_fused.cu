@@ -3,7 +3,7 @@
 // O = P V in one kernel, so the T x T logits and probabilities never touch HBM (the unfused path in attention.cu
 // writes and re-reads 6 bytes per logit: 1.6 GB per 32x32 attention block at batch 32).
 //
-// One persistent CTA per SM walks (image, head, 128-query block) tiles.  Per tile, with key blocks of 128 tokens:
+// Persistent CTAs, two per SM, walk (image, head, 128-query block) tiles.  Per tile, with key blocks of 64 tokens:
 //   pass 1:  S_kb = Q K_kb^T (tcgen05, TMEM)  ->  softmax warps keep the running row maximum (no exp)
 //   pass 2:  S_kb again  ->  p = exp2((s - max) * scale*log2e), row sums in registers, P as bf16 into shared memory in
 //            the K-major SWIZZLE_128B operand layout  ->  O += P V_kb (tcgen05, accumulator stays in TMEM)
@@ -12,6 +12,9 @@
 // count at one per logit, which is what bounds the kernel (MUFU: 16 ex2 per clock per SM).
 //
 // Warps: 0 = TMA producer, 1 = MMA issuer, 2..5 = softmax / epilogue (one query row per thread, TMEM lane = row).
+// Two CTAs share an SM (112 KB of shared memory and 256 TMEM columns each): the softmax of one hides the TMA / MMA
+// latencies of the other, and every scheduler has two softmax warps to issue from (ncu on the first, one-CTA version:
+// 9 % warps active, 32 % issue-active, 195 us for the 32x32 level at batch 32).
 // V is consumed as V^T [B, heads, 64, T] (written by transpose_heads_kernel) so that both GEMMs see K-major operands.
 #include "common.h"
 #include "ptx.cuh"
@@ -19,15 +22,17 @@
 namespace nlc {
 
 constexpr int kFaDh = 64;                       // head dimension
-constexpr int kFaBlock = 128;                   // queries per tile, keys per block
+constexpr int kFaBlock = 128;                   // queries per tile
+constexpr int kFaKeys = 64;                     // keys per block
 constexpr int kFaStages = 4;                    // K / V^T ring
-constexpr int kFaTileBytes = kFaBlock * 128;    // 128 rows x 64 bf16 = 16 KB (Q, K block, one half of P)
-constexpr int kFaVtBytes = kFaDh * 128;         // 64 rows (channels) x 64 keys: 8 KB, two per key block
-constexpr int kFaStageBytes = kFaTileBytes + 2 * kFaVtBytes;  // 32 KB
-constexpr int kFaPBytes = 2 * kFaTileBytes;     // P block: two K chunks of 64 keys
+constexpr int kFaTileBytes = kFaBlock * 128;    // 128 rows x 64 bf16 = 16 KB (Q, one P block)
+constexpr int kFaKBytes = kFaKeys * 128;        // 64 keys x 64 channels: 8 KB
+constexpr int kFaVtBytes = kFaDh * 128;         // 64 channels x 64 keys: 8 KB
+constexpr int kFaStageBytes = kFaKBytes + kFaVtBytes;  // 16 KB
+constexpr int kFaPBytes = kFaTileBytes;         // P block: 128 queries x 64 keys
 constexpr int kFaThreads = 64 + 128;
-constexpr int kFaSmem = kFaTileBytes + kFaStages * kFaStageBytes + 2 * kFaPBytes + 256 + 1024;
-constexpr int kFaTmemCols = 512;                // S double buffer (2 x 128) + O (64) -> next power of two
+constexpr int kFaSmem = kFaTileBytes + kFaStages * kFaStageBytes + 2 * kFaPBytes + 256;  // 112.25 KB: two CTAs per SM
+constexpr int kFaTmemCols = 256;                // S double buffer (2 x 64) + O (64) -> next power of two
 
 struct FaParams {
     CUtensorMap mapQ, mapK, mapVt;
@@ -38,9 +43,8 @@ struct FaParams {
     int ld_out;
 };
 
-__global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_constant__ FaParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_constant__ FaParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];  // (the swizzled tiles need 1024-byte alignment; checked below)
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + kFaTileBytes;
     uint8_t* sP = sKV + kFaStages * kFaStageBytes;
@@ -58,6 +62,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+        printf("nlc: attn_fused_kernel dynamic shared memory is not 1024-byte aligned\n");
+        __trap();
+    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.mapQ);
         tma_prefetch_desc(&p.mapK);
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_o = tmem_base + 2 * kFaBlock;
+    const uint32_t tmem_o = tmem_base + 2 * kFaKeys;
     const int nkb = p.n_kblk;
 
     if (warp == 0) {
@@ -104,12 +112,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                         const int st = kv_it % kFaStages;
                         mbar_wait(&kv_empty[st], ((kv_it / kFaStages) & 1) ^ 1);
                         uint8_t* sk = sKV + st * kFaStageBytes;
-                        mbar_expect_tx(&kv_full[st], pass ? kFaStageBytes : kFaTileBytes);
-                        tma_load_4d(sk, &p.mapK, &kv_full[st], 0, kb * kFaBlock, h, n);
-                        if (pass) {
-                            tma_load_3d(sk + kFaTileBytes, &p.mapVt, &kv_full[st], kb * kFaBlock, 0, bh);
-                            tma_load_3d(sk + kFaTileBytes + kFaVtBytes, &p.mapVt, &kv_full[st], kb * kFaBlock + 64, 0, bh);
-                        }
+                        mbar_expect_tx(&kv_full[st], pass ? kFaStageBytes : kFaKBytes);
+                        tma_load_4d(sk, &p.mapK, &kv_full[st], 0, kb * kFaKeys, h, n);
+                        if (pass) tma_load_3d(sk + kFaKBytes, &p.mapVt, &kv_full[st], kb * kFaKeys, 0, bh);
                     }
                 }
             }
@@ -117,8 +122,8 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc(1, kFaBlock, kFaBlock);  // 128 x 128, bf16
-            constexpr uint32_t idesc_o = umma_idesc(1, kFaBlock, kFaDh);     // 128 x 64
+            constexpr uint32_t idesc_s = umma_idesc(1, kFaBlock, kFaKeys);  // 128 queries x 64 keys, bf16
+            constexpr uint32_t idesc_o = umma_idesc(1, kFaBlock, kFaDh);    // 128 queries x 64 channels
             const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
             uint32_t kv_it = 0, s_it = 0, p_it = 0, tile_it = 0;
             // S block `s_it` = Q K^T of the K tile in ring slot `kv_it`
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                 tc_fence_after_sync();
                 const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * kFaBlock, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * kFaKeys, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
             };
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
                 mbar_wait(q_full, tile_it & 1);
@@ -156,16 +161,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                     const int st = (kv_it + kb) % kFaStages;
                     mbar_wait(&p_full[pb], (p_it >> 1) & 1);
                     tc_fence_after_sync();
-                    const uint32_t pbase = smem_u32(sP + pb * kFaPBytes);
-                    const uint32_t vbase = smem_u32(sKV + st * kFaStageBytes + kFaTileBytes);
+                    const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + pb * kFaPBytes));
+                    const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes + kFaKBytes));
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint64_t pdesc = umma_desc_sw128(pbase + c * kFaTileBytes);
-                        const uint64_t vdesc = umma_desc_sw128(vbase + c * kFaVtBytes);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem_o, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (kb | c | k) != 0);
-                    }
+                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (kb | k) != 0);
                     umma_commit(&kv_empty[st]);
                     umma_commit(&p_empty[pb]);
                 }
@@ -190,10 +189,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                 const int sb = s_it & 1;
                 mbar_wait(&s_full[sb], (s_it >> 1) & 1);
                 tc_fence_after_sync();
-#pragma unroll 1
-                for (int c = 0; c < kFaBlock; c += 32) {
+#pragma unroll
+                for (int c = 0; c < kFaKeys; c += 32) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * kFaBlock + c, v);
+                    tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * kFaKeys + c, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
@@ -211,10 +210,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                 tc_fence_after_sync();
                 mbar_wait(&p_empty[pb], ((p_it >> 1) & 1) ^ 1);  // O += P V of two blocks ago has finished reading it
                 uint8_t* prow = sP + pb * kFaPBytes + row * 128;
-#pragma unroll 1
-                for (int c = 0; c < kFaBlock; c += 32) {
+#pragma unroll
+                for (int c = 0; c < kFaKeys; c += 32) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * kFaBlock + c, v);
+                    tmem_ld_32x32b_x32(tmem_base + lane_addr + sb * kFaKeys + c, v);
                     tmem_ld_wait();
                     uint32_t pk[16];
 #pragma unroll
@@ -224,9 +223,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
                         sum += a + b;
                         pk[i] = pack_bf16x2(a, b);
                     }
-                    // keys [c, c+32) = 16-byte chunks j0..j0+3 of K chunk (c / 64); SWIZZLE_128B: chunk ^ (row & 7)
-                    uint8_t* dst = prow + (c >> 6) * kFaTileBytes;
-                    const int j0 = (c & 63) >> 3;
+                    // keys [c, c+32) = 16-byte chunks j0..j0+3 of the row; SWIZZLE_128B: chunk ^ (row & 7)
+                    uint8_t* dst = prow;
+                    const int j0 = c >> 3;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<uint4*>(dst + (((j0 + j) ^ (row & 7)) << 4)) =
@@ -242,6 +241,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
             mbar_wait(o_full, tile_it & 1);
             tc_fence_after_sync();
             const float inv = 1.0f / sum;
+            const bool row_ok = qb * kFaBlock + row < p.T;  // rows past T were zero-filled by TMA: nothing to store
             __nv_bfloat16* orow = p.out + (static_cast<size_t>(n) * p.T + qb * kFaBlock + row) * p.ld_out + h * kFaDh;
 #pragma unroll 1
             for (int c = 0; c < kFaDh; c += 32) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_fused_kernel(const __grid_
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         w[i] = pack_bf16x2(__uint_as_float(v[8 * j + 2 * i]) * inv, __uint_as_float(v[8 * j + 2 * i + 1]) * inv);
-                    *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
+                    if (row_ok) *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
             tc_fence_before_sync();
@@ -278,7 +278,7 @@ using namespace nlc;
 // Internal entry (declared in attention.cu): q/k inside the qkv tensor, V^T already in `vt` as [B*heads, 64, T].
 int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, int k_off, int head_stride, int B, int T,
                              int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream) {
-    NLC_REQUIRE(T % kFaBlock == 0 && T >= kFaBlock, "nlc_attention(fused): T=%d must be a multiple of %d", T, kFaBlock);
+    NLC_REQUIRE(T % kFaKeys == 0 && T >= kFaKeys, "nlc_attention(fused): T=%d must be a multiple of %d", T, kFaKeys);
     NLC_REQUIRE(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && head_stride % 8 == 0 && ld_out % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
                     (reinterpret_cast<uintptr_t>(vt) & 15) == 0,
@@ -286,7 +286,7 @@ int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, i
     FaParams p;
     memset(&p, 0, sizeof(p));
     p.B = B, p.T = T, p.heads = heads;
-    p.n_qblk = T / kFaBlock, p.n_kblk = T / kFaBlock;
+    p.n_qblk = (T + kFaBlock - 1) / kFaBlock, p.n_kblk = T / kFaKeys;  // (a last query tile may be half empty)
     p.n_tiles = B * heads * p.n_qblk;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.out = static_cast<__nv_bfloat16*>(out), p.ld_out = ld_out;
@@ -296,7 +296,7 @@ int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, i
         cuuint64_t gdim[4] = {(cuuint64_t)kFaDh, (cuuint64_t)T, (cuuint64_t)heads, (cuuint64_t)B};
         cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(heads > 1 ? head_stride : kFaDh) * 2,
                               (cuuint64_t)T * ld * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kFaDh, (cuuint32_t)kFaBlock, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kFaDh, (cuuint32_t)(which ? kFaKeys : kFaBlock), 1, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = ctx->encode_tiled(which ? &p.mapK : &p.mapQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                                        const_cast<__nv_bfloat16*>(base + (which ? k_off : q_off)), gdim, gstr, box, estr,
@@ -309,7 +309,7 @@ int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, i
         // V^T: (token, channel, image*head)
         cuuint64_t gdim[3] = {(cuuint64_t)T, (cuuint64_t)kFaDh, (cuuint64_t)B * heads};
         cuuint64_t gstr[2] = {(cuuint64_t)T * 2, (cuuint64_t)T * kFaDh * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)kFaDh, 1};
+        cuuint32_t box[3] = {(cuuint32_t)kFaKeys, (cuuint32_t)kFaDh, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = ctx->encode_tiled(&p.mapVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(vt), gdim, gstr, box,
                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -319,9 +319,12 @@ int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, i
     static bool configured = false;
     if (!configured) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
+        // two CTAs per SM need the whole 228 KB as shared memory (the default carveout only guarantees one)
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    const int grid = p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count;
+    const int grid = p.n_tiles < 2 * ctx->sm_count ? p.n_tiles : 2 * ctx->sm_count;
     attn_fused_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(p);
     NLC_CHECK_LAUNCH();
     return NLC_OK;

@@ -264,14 +264,16 @@ def attention_ws(op_dtype, B, T, heads, dh):
     return int(_lib.lib().nlc_attention_ws(op_dtype, B, T, heads, dh))
 
 
-@_timed("attention")
+@_timed("attention", lambda qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, *a, **k: " T%d heads%d dh%d" % (
+    qkv.H * qkv.W, heads, dh))
 def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale, out, ws):
     """qkv: Act [B,H,W,ld]; out: Act [B,H,W,heads*dh] (operand dtype)."""
     T = qkv.H * qkv.W
     _lib.check(_lib.lib().nlc_attention(
         _ctx(qkv.t), C.c_void_p(qkv.ptr), op_dtype, qkv.ld, q_off, k_off, v_off, head_stride, qkv.B, T, heads, dh,
         scale, C.c_void_p(out.ptr), out.ld, _p(ws), _stream()))
-    STATS.launches += (2 if (op_dtype == NLC_BF16 and dh == 64 and T % 128 == 0) else 4) if T >= 128 else 1
+    fused = op_dtype == NLC_BF16 and dh == 64 and T % 64 == 0 and 64 <= T <= 1024
+    STATS.launches += 2 if fused else (4 if T >= 128 else 1)
 
 
 @_timed("linear")
