@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libnlc_b200.so")
 
 NLC_F32 = 0
 NLC_BF16 = 1
+NLC_F16 = 3  # fp16 operands: kind::f16 at the bf16 rate, 3 more mantissa bits
 NLC_F32X3 = 2  # plain fp32 operands, split into tf32 hi+lo inside nlc_conv_tc (accuracy mode)
 EDM_PARTS = 16
 MAX_SRC = 3

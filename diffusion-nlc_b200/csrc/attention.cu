@@ -18,12 +18,16 @@ template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <typename T>
 __device__ __forceinline__ T from_f32(float v, int rnd);
 template <>
 __device__ __forceinline__ float from_f32<float>(float v, int rnd) { return op_f32(v, rnd); }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v, int) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v, int) { return __float2half_rn(v); }
 
 // ---------------------------------------------------------------- row softmax: one warp per row
 template <typename OutT>
@@ -145,10 +149,10 @@ __global__ void __launch_bounds__(256)
 using namespace nlc;
 
 // attention_fused.cu
-int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, int k_off, int head_stride, int B, int T,
-                             int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream);
+int nlc_attention_fused_16(nlc_ctx* ctx, const void* qkv, int f16, int ld, int q_off, int k_off, int head_stride, int B,
+                           int T, int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream);
 
-// The fused kernel serves bf16, 64-channel heads and T a multiple of 64 (the ADM 32x32 / 16x16 / 8x8 levels); everything
+// The fused kernel serves bf16 / fp16, 64-channel heads and T a multiple of 64 (the ADM 32x32 / 16x16 / 8x8 levels); everything
 // else (fp32-container accuracy modes, the single-head dh = C blocks of unet_ddim / SongUNet) takes the GEMM + softmax
 // + GEMM path below.  NLC_FUSED_ATTN=0 disables it (A/B measurements).
 static bool fused_enabled() {
@@ -160,11 +164,11 @@ static bool fused_enabled() {
     return v != 0;
 }
 static bool use_fused(int op_dtype, int T, int dh) {
-    return op_dtype == NLC_BF16 && dh == 64 && T >= 64 && T % 64 == 0 && T <= 1024 && fused_enabled();
+    return dtype_is16(op_dtype) && dh == 64 && T >= 64 && T % 64 == 0 && T <= 1024 && fused_enabled();
 }
 
 extern "C" size_t nlc_attention_ws(int op_dtype, int B, int T, int heads, int dh) {
-    const size_t esz = op_dtype != NLC_BF16 ? 4 : 2;
+    const size_t esz = dtype_is16(op_dtype) ? 2 : 4;
     const size_t bh = static_cast<size_t>(B) * heads;
     if (use_fused(op_dtype, T, dh)) return bh * dh * T * esz + 1024;  // V^T only
     if (T < 128) return 0;
@@ -176,9 +180,10 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
                              void* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && qkv && out_op, "nlc_attention: null argument");
-    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32 || op_dtype == NLC_F32X3, "nlc_attention: bad op_dtype");
-    const bool f32c = op_dtype != NLC_BF16;  // fp32 containers (tf32-rounded, or plain fp32 for NLC_F32X3)
-    const int rnd = op_dtype == NLC_F32;
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_attention: bad op_dtype");
+    const bool f32c = !dtype_is16(op_dtype);  // fp32 containers (tf32-rounded, or plain fp32 for NLC_F32X3)
+    const bool f16 = op_dtype == NLC_F16;
+    const int rnd = dtype_fmt(op_dtype);
     const size_t esz = f32c ? 4 : 2;
     if (T < 128 && !use_fused(op_dtype, T, dh)) {
         const size_t smem = (static_cast<size_t>(2) * T * (dh + 1) + 8 * dh) * sizeof(float);
@@ -189,6 +194,12 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
             attn_small_kernel<float><<<B * heads, 256, smem, stream>>>(static_cast<const float*>(qkv), ld, q_off, k_off,
                                                                        v_off, head_stride, T, heads, dh, scale,
                                                                        static_cast<float*>(out_op), ld_out, rnd);
+        } else if (f16) {
+            NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                227 * 1024));
+            attn_small_kernel<__half><<<B * heads, 256, smem, stream>>>(static_cast<const __half*>(qkv), ld, q_off, k_off,
+                                                                       v_off, head_stride, T, heads, dh, scale,
+                                                                       static_cast<__half*>(out_op), ld_out, rnd);
         } else {
             NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<__nv_bfloat16>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -223,8 +234,8 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
         NLC_CHECK_LAUNCH();
     }
     if (fused)
-        return nlc_attention_fused_bf16(ctx, qkv, ld, q_off, k_off, head_stride, B, T, heads, scale, VT, out_op, ld_out,
-                                        stream);
+        return nlc_attention_fused_16(ctx, qkv, f16 ? 1 : 0, ld, q_off, k_off, head_stride, B, T, heads, scale, VT, out_op,
+                                      ld_out, stream);
     // S = scale * Q K^T   ("image" = sample, "row" = head, "column" = query token)
     {
         nlc_conv_desc d;
@@ -248,6 +259,8 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
         const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
         if (f32c)
             softmax_rows_kernel<float><<<grid, 256, 0, stream>>>(S, static_cast<float*>(P), rows, T, rnd);
+        else if (f16)
+            softmax_rows_kernel<__half><<<grid, 256, 0, stream>>>(S, static_cast<__half*>(P), rows, T, rnd);
         else
             softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(S, static_cast<__nv_bfloat16*>(P), rows, T, rnd);
         NLC_CHECK_LAUNCH();

@@ -39,7 +39,8 @@ struct FaParams {
     int B, T, heads;
     int n_qblk, n_kblk, n_tiles;
     float scale_log2e;
-    __nv_bfloat16* out;
+    int f16;  // operands, P and the output are fp16 (else bf16)
+    __nv_bfloat16* out;  // (16-bit elements of either format)
     int ld_out;
 };
 
@@ -122,8 +123,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc(1, kFaBlock, kFaKeys);  // 128 queries x 64 keys, bf16
-            constexpr uint32_t idesc_o = umma_idesc(1, kFaBlock, kFaDh);    // 128 queries x 64 channels
+            const uint32_t idesc_s = umma_idesc(p.f16 ? 0 : 1, kFaBlock, kFaKeys);  // 128 queries x 64 keys
+            const uint32_t idesc_o = umma_idesc(p.f16 ? 0 : 1, kFaBlock, kFaDh);    // 128 queries x 64 channels
             const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
             uint32_t kv_it = 0, s_it = 0, p_it = 0, tile_it = 0;
             // S block `s_it` = Q K^T of the K tile in ring slot `kv_it`
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
                         const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2e, -mc));
                         const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2e, -mc));
                         sum += a + b;
-                        pk[i] = pack_bf16x2(a, b);
+                        pk[i] = pack_op16x2(a, b, p.f16);
                     }
                     // keys [c, c+32) = 16-byte chunks j0..j0+3 of the row; SWIZZLE_128B: chunk ^ (row & 7)
                     uint8_t* dst = prow;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
                     uint32_t w[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        w[i] = pack_bf16x2(__uint_as_float(v[8 * j + 2 * i]) * inv, __uint_as_float(v[8 * j + 2 * i + 1]) * inv);
+                        w[i] = pack_op16x2(__uint_as_float(v[8 * j + 2 * i]) * inv, __uint_as_float(v[8 * j + 2 * i + 1]) * inv, p.f16);
                     if (row_ok) *reinterpret_cast<uint4*>(orow + c + 8 * j) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
@@ -276,8 +277,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
 using namespace nlc;
 
 // Internal entry (declared in attention.cu): q/k inside the qkv tensor, V^T already in `vt` as [B*heads, 64, T].
-int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, int k_off, int head_stride, int B, int T,
-                             int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream) {
+int nlc_attention_fused_16(nlc_ctx* ctx, const void* qkv, int f16, int ld, int q_off, int k_off, int head_stride, int B,
+                           int T, int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream) {
     NLC_REQUIRE(T % kFaKeys == 0 && T >= kFaKeys, "nlc_attention(fused): T=%d must be a multiple of %d", T, kFaKeys);
     NLC_REQUIRE(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && head_stride % 8 == 0 && ld_out % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
@@ -289,6 +290,7 @@ int nlc_attention_fused_bf16(nlc_ctx* ctx, const void* qkv, int ld, int q_off, i
     p.n_qblk = (T + kFaBlock - 1) / kFaBlock, p.n_kblk = T / kFaKeys;  // (a last query tile may be half empty)
     p.n_tiles = B * heads * p.n_qblk;
     p.scale_log2e = scale * 1.4426950408889634f;
+    p.f16 = f16;
     p.out = static_cast<__nv_bfloat16*>(out), p.ld_out = ld_out;
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
     for (int which = 0; which < 2; ++which) {

@@ -34,6 +34,12 @@ int set_error(int code, const char* fmt, ...);
         if (!(cond)) return nlc::set_error(NLC_EINVAL, __VA_ARGS__);  \
     } while (0)
 
+// Operand dtype helpers: 16-bit operands (bf16 / fp16) against fp32 containers (tf32-rounded / plain), and the one-bit
+// "format" flag the kernels take: fp32 containers -> round to tf32 (NLC_F32), 16-bit -> fp16 instead of bf16 (NLC_F16).
+inline bool dtype_valid(int dt) { return dt == NLC_F32 || dt == NLC_BF16 || dt == NLC_F32X3 || dt == NLC_F16; }
+inline bool dtype_is16(int dt) { return dt == NLC_BF16 || dt == NLC_F16; }
+inline int dtype_fmt(int dt) { return dt == NLC_F32 || dt == NLC_F16; }
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

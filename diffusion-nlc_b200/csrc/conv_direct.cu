@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256)
                     make_float4(op_f32(acc[4], rnd), op_f32(acc[5], rnd), op_f32(acc[6], rnd), op_f32(acc[7], rnd));
             } else {
                 __nv_bfloat16* o = static_cast<__nv_bfloat16*>(yo) + static_cast<size_t>(pix) * ld_yo + cg * 8;
-                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
-                                                          pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+                *reinterpret_cast<uint4*>(o) = make_uint4(pack_op16x2(acc[0], acc[1], rnd), pack_op16x2(acc[2], acc[3], rnd),
+                                                          pack_op16x2(acc[4], acc[5], rnd), pack_op16x2(acc[6], acc[7], rnd));
             }
         }
     }
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(256)
             uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(patches) + static_cast<size_t>(pix) * KP);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                o[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+                o[i] = make_uint4(pack_op16x2(v[8 * i], v[8 * i + 1], rnd), pack_op16x2(v[8 * i + 2], v[8 * i + 3], rnd),
+                                  pack_op16x2(v[8 * i + 4], v[8 * i + 5], rnd), pack_op16x2(v[8 * i + 6], v[8 * i + 7], rnd));
 #pragma unroll
             for (int i = 4; i < 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
         }
@@ -136,6 +136,13 @@ template <>
 __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
     const float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void load4<__half>(const __half* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
 }
 template <>
 __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
@@ -259,8 +266,9 @@ extern "C" int nlc_conv_in_nchw(nlc_ctx* ctx, const float* x_nchw, const float* 
     long long blocks = (npix + ppb - 1) / ppb;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    const int rnd = op_dtype == NLC_F32;
-    if (op_dtype != NLC_BF16) {
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_conv_in_nchw: bad op_dtype");
+    const int rnd = dtype_fmt(op_dtype);
+    if (!dtype_is16(op_dtype)) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
         conv_in_kernel<true><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
@@ -282,9 +290,13 @@ extern "C" int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, i
     NLC_REQUIRE(Cin % 128 == 0 && W % kOutPix == 0 && ld_x % 4 == 0, "nlc_conv_out_nchw: Cin=%d W=%d unsupported", Cin,
                 W);
     NLC_REQUIRE(static_cast<size_t>(9) * Cout * Cin * 4 <= 200 * 1024, "nlc_conv_out_nchw: weights exceed shared memory");
-    if (op_dtype != NLC_BF16)
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_conv_out_nchw: bad op_dtype");
+    if (!dtype_is16(op_dtype))
         return launch_conv_out<float>(ctx, static_cast<const float*>(x_op), ld_x, B, Cin, H, W, weight, bias, Cout,
                                       out_nchw, stream);
+    if (op_dtype == NLC_F16)
+        return launch_conv_out<__half>(ctx, static_cast<const __half*>(x_op), ld_x, B, Cin, H, W, weight, bias, Cout,
+                                       out_nchw, stream);
     return launch_conv_out<__nv_bfloat16>(ctx, static_cast<const __nv_bfloat16*>(x_op), ld_x, B, Cin, H, W, weight,
                                           bias, Cout, out_nchw, stream);
 }
@@ -294,14 +306,14 @@ extern "C" int nlc_im2col_in(nlc_ctx* ctx, const float* x_nchw, const float* in_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && x_nchw && patches_op, "nlc_im2col_in: null argument");
     NLC_REQUIRE(Cin >= 1 && Cin <= 3, "nlc_im2col_in: Cin=%d unsupported (1..3: 9*Cin must fit one 32-element K row)", Cin);
-    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32 || op_dtype == NLC_F32X3, "nlc_im2col_in: bad op_dtype");
-    const int rnd = op_dtype == NLC_F32;
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_im2col_in: bad op_dtype");
+    const int rnd = dtype_fmt(op_dtype);
     NLC_REQUIRE((reinterpret_cast<uintptr_t>(patches_op) & 15) == 0, "nlc_im2col_in: patches must be 16-byte aligned");
     const long long npix = static_cast<long long>(B) * H * W;
     long long blocks = (npix + 255) / 256;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    if (op_dtype != NLC_BF16)
+    if (!dtype_is16(op_dtype))
         im2col_in_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
     else
         im2col_in_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);

@@ -63,6 +63,7 @@ struct ConvKParams {
     int ld_out_op;
     int out_head_split;
     int w_batched;
+    int f16;         // 16-bit operands are fp16 (kind::f16 with the f16 format bits), not bf16
     float* stats;    // GroupNorm partials of the fp32 output: [pixel/32][stats_nblk][2] = (mean, M2) over 32 px x 4 ch
     int stats_nblk;
 };
@@ -237,7 +238,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0 && rank == 0) {  // the pair's leader issues for both CTAs
-            constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, CTA2 ? 2 * kBlockM : kBlockM, BLOCK_N);
+            // operand format bits: tf32, or for the 16-bit modes bf16 / fp16 (same kind::f16 instruction)
+            const uint32_t idesc = umma_idesc(TF32 ? 2 : (p.f16 ? 0 : 1), CTA2 ? 2 * kBlockM : kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -503,8 +505,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                                     *reinterpret_cast<const float4*>(stg + r * 32 + (((2 * sub_c8 + 1) ^ (r & 7)) << 2));
                                 reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_op) +
                                                          (pix0 + r) * p.ld_out_op + ocol0)[sub_c8] =
-                                    make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y),
-                                               pack_bf16x2(b.z, b.w));
+                                    make_uint4(pack_op16x2(a.x, a.y, p.f16), pack_op16x2(a.z, a.w, p.f16),
+                                               pack_op16x2(b.x, b.y, p.f16), pack_op16x2(b.z, b.w, p.f16));
                             }
                         }
                     }
@@ -568,10 +570,9 @@ using namespace nlc;
 extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && d, "nlc_conv_tc: null argument");
-    NLC_REQUIRE(d->dtype == NLC_BF16 || d->dtype == NLC_F32 || d->dtype == NLC_F32X3,
-                "nlc_conv_tc: dtype must be NLC_BF16, NLC_F32 or NLC_F32X3");
+    NLC_REQUIRE(dtype_valid(d->dtype), "nlc_conv_tc: dtype must be NLC_BF16, NLC_F16, NLC_F32 or NLC_F32X3");
     const bool x3 = d->dtype == NLC_F32X3;
-    const bool tf32 = d->dtype != NLC_BF16;  // fp32 containers
+    const bool tf32 = !dtype_is16(d->dtype);  // fp32 containers
     const int esz = tf32 ? 4 : 2;
     const int chunk = kChunkBytes / esz;
     NLC_REQUIRE(d->nsrc >= 1 && d->nsrc <= NLC_MAX_SRC, "nlc_conv_tc: nsrc %d out of range", d->nsrc);
@@ -628,7 +629,9 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     }
     p.total_chunks = ktot / chunk;
 
+    // (TMA only moves the 16-bit elements: the bf16 element type serves fp16 tensors as well)
     const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    p.f16 = d->dtype == NLC_F16;
     for (int s = 0; s < d->nsrc; ++s) {
         const nlc_operand& o = d->src[s];
         NLC_REQUIRE(o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && (static_cast<size_t>(o.ld) * esz) % 16 == 0,

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(kGnThreads)
 
 // ---------------------------------------------------------------- apply
 template <bool TF32>
+// `rnd` is the operand format flag (common.h dtype_fmt): fp32 containers -> round to tf32; 16-bit -> fp16, not bf16
 __device__ __forceinline__ void gn_store8(void* __restrict__ y, size_t off, const float (&f)[8], int rnd) {
     if (TF32) {
         float* yp = static_cast<float*>(y) + off;
@@ -153,8 +154,8 @@ __device__ __forceinline__ void gn_store8(void* __restrict__ y, size_t off, cons
             make_float4(op_f32(f[4], rnd), op_f32(f[5], rnd), op_f32(f[6], rnd), op_f32(f[7], rnd));
     } else {
         __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y) + off;
-        *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                   pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(yp) = make_uint4(pack_op16x2(f[0], f[1], rnd), pack_op16x2(f[2], f[3], rnd),
+                                                   pack_op16x2(f[4], f[5], rnd), pack_op16x2(f[6], f[7], rnd));
     }
 }
 
@@ -331,8 +332,8 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
                     (reinterpret_cast<uintptr_t>(y_op) & 15) == 0,
                 "nlc_groupnorm: tensors must be 16-byte aligned");
     NLC_REQUIRE((scale == nullptr) == (shift == nullptr), "nlc_groupnorm: scale and shift come together");
-    NLC_REQUIRE(op_dtype == NLC_BF16 || op_dtype == NLC_F32 || op_dtype == NLC_F32X3, "nlc_groupnorm: bad op_dtype");
-    const int rnd = op_dtype == NLC_F32;  // NLC_F32X3 keeps the operand copy unrounded
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_groupnorm: bad op_dtype");
+    const int rnd = dtype_fmt(op_dtype);  // tf32 rounding (NLC_F32; NLC_F32X3 stays unrounded) / fp16 instead of bf16
     NLC_REQUIRE(static_cast<long long>(H) * W * (C / 8) < (1LL << 31), "nlc_groupnorm: image too large");
     NLC_REQUIRE(resample >= 0 && resample <= 2 && (resample != 2 || (H % 2 == 0 && W % 2 == 0)),
                 "nlc_groupnorm: resample mode %d unsupported for %dx%d", resample, H, W);
@@ -359,7 +360,7 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
 #define NLC_GN_APPLY(T, M)                                                                                        \
     return launch_apply<T, M>(x, ld_x, B, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y_op, ld_y, \
                               ctx->sm_count, rnd, stream)
-    if (op_dtype != NLC_BF16) {
+    if (!dtype_is16(op_dtype)) {
         if (resample == 0) NLC_GN_APPLY(true, 0);
         if (resample == 1) NLC_GN_APPLY(true, 1);
         NLC_GN_APPLY(true, 2);

@@ -13,6 +13,13 @@ __device__ __forceinline__ float4 ld4(const T* p);
 template <>
 __device__ __forceinline__ float4 ld4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 template <>
+__device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+template <>
 __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
     const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
     const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
@@ -59,7 +66,7 @@ __global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x
                     make_float4(op_f32(v.x, rnd), op_f32(v.y, rnd), op_f32(v.z, rnd), op_f32(v.w, rnd));
             else
                 *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(yo) + opix * ld_yo + c) =
-                    make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+                    make_uint2(pack_op16x2(v.x, v.y, rnd), pack_op16x2(v.z, v.w, rnd));
         }
     }
 }
@@ -150,8 +157,9 @@ extern "C" int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H
     long long blocks = (total4 + 255) / 256;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    const bool tf32 = op_dtype != NLC_BF16;
-    const int rnd = op_dtype == NLC_F32;
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_resample: bad op_dtype");
+    const bool tf32 = !dtype_is16(op_dtype);
+    const int rnd = dtype_fmt(op_dtype);
 #define NLC_RS(M, T)                                                                                          \
     resample_kernel<M, T, float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld_x, H, W, C, y_f32,      \
                                                                                     ld_y_f32, y_op, ld_y_op, total4, rnd)
@@ -179,11 +187,18 @@ extern "C" int nlc_resample_op(nlc_ctx* ctx, const void* x_op, int op_dtype, int
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
     const unsigned g = static_cast<unsigned>(blocks);
-    const int rnd = op_dtype == NLC_F32;
-    if (op_dtype != NLC_BF16) {
+    NLC_REQUIRE(dtype_valid(op_dtype), "nlc_resample_op: bad op_dtype");
+    const int rnd = dtype_fmt(op_dtype);
+    if (!dtype_is16(op_dtype)) {
         const float* x = static_cast<const float*>(x_op);
         if (mode == 1) resample_kernel<1, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
         else resample_kernel<2, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+    } else if (op_dtype == NLC_F16) {
+        const __half* x = static_cast<const __half*>(x_op);
+        if (mode == 1)
+            resample_kernel<1, false, __half><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+        else
+            resample_kernel<2, false, __half><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     } else {
         const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_op);
         if (mode == 1)

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace nlc {
@@ -256,6 +257,14 @@ __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __e
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
+}
+// Two floats -> one packed pair in the 16-bit operand type: fp16 (f16 != 0) or bf16.
+__device__ __forceinline__ uint32_t pack_op16x2(float a, float b, int f16) {
+    if (f16) {
+        __half2 t = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&t);
+    }
+    return pack_bf16x2(a, b);
 }
 // fp32 -> tf32 (round to nearest, ties away), returned as fp32 bits with the low 13 mantissa bits cleared.
 __device__ __forceinline__ float round_tf32(float x) {

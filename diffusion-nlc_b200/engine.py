@@ -11,12 +11,13 @@ import os
 import torch
 
 from . import ops
-from ._lib import NLC_BF16, NLC_F32, NLC_F32X3
+from ._lib import NLC_BF16, NLC_F16, NLC_F32, NLC_F32X3
 from .ops import Act, GnStats
 
-# bf16: throughput mode.  tf32: one kind::tf32 MMA on tf32-rounded fp32 operands (what cuDNN does for the reference's
+# bf16 / fp16: throughput modes (same MMA rate; fp16 keeps 3 more mantissa bits and is the reference's own reduced
+# precision, src/fp16_util.py).  tf32: one kind::tf32 MMA on tf32-rounded fp32 operands (what cuDNN does for the reference's
 # default GPU run).  fp32: the accuracy mode, unrounded fp32 operands and weights, 3 x tf32 split products.
-PRECISIONS = {"bf16": NLC_BF16, "tf32": NLC_F32, "fp32": NLC_F32X3}
+PRECISIONS = {"bf16": NLC_BF16, "fp16": NLC_F16, "tf32": NLC_F32, "fp32": NLC_F32X3}
 
 
 class Feat:
@@ -46,7 +47,7 @@ class Engine:
         self.precision = precision
         self.op_dtype = PRECISIONS[precision]
         self.op_torch = ops.OP_DTYPES[self.op_dtype]
-        self.chunk = 64 if self.op_dtype == NLC_BF16 else 32
+        self.chunk = 64 if self.op_dtype in (NLC_BF16, NLC_F16) else 32
         self._scratch = {}
         self._named = {}
         self._named_stats = {}
@@ -213,7 +214,7 @@ def emit_conv_in(pc, x_nchw, in_scale_fn, w_packed, bias, Cout, dest, w_f32=None
     occasional time-bucket flip, tests/test_gpu_sampler.py).  `in_scale_fn()` returns the [B] scale or None."""
     eng = pc.eng
     dt = eng.op_dtype
-    if dt != NLC_BF16 and w_f32 is not None:
+    if dt not in (NLC_BF16, NLC_F16) and w_f32 is not None:
         pc.add(lambda: ops.conv_in_nchw(x_nchw, in_scale_fn(), w_f32, bias, dest.f32, dest.op, dt), "conv_in (fp32)")
         return
     B, _, H, W = x_nchw.shape

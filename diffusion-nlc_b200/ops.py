@@ -5,9 +5,9 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import NLC_BF16, NLC_F32, NLC_F32X3
+from ._lib import NLC_BF16, NLC_F16, NLC_F32, NLC_F32X3
 
-OP_DTYPES = {NLC_BF16: torch.bfloat16, NLC_F32: torch.float32, NLC_F32X3: torch.float32}
+OP_DTYPES = {NLC_BF16: torch.bfloat16, NLC_F16: torch.float16, NLC_F32: torch.float32, NLC_F32X3: torch.float32}
 
 
 class _Stats:
@@ -120,8 +120,8 @@ def pack_conv_weight(w, op_dtype, extra=None):
     if extra is not None:
         k = torch.cat([k, extra.detach().float().reshape(Cout, -1)], dim=1)
     k = k.contiguous()
-    if op_dtype == NLC_BF16:
-        return k.to(torch.bfloat16).contiguous()
+    if op_dtype in (NLC_BF16, NLC_F16):
+        return k.to(OP_DTYPES[op_dtype]).contiguous()
     if op_dtype == NLC_F32X3:
         return k.clone()  # split into tf32 hi + lo by the kernel
     return round_tf32_(k.clone())
@@ -201,11 +201,11 @@ def im2col_in(x_nchw, in_scale, patches, op_dtype):
 def pack_conv_in_weight(w, op_dtype):
     """torch [Cout,Cin,3,3] -> [Cout, 64|32]: column tap*Cin + ci, zero-padded to one 128-byte K row."""
     Cout, Cin = w.shape[0], w.shape[1]
-    kp = 64 if op_dtype == NLC_BF16 else 32
+    kp = 64 if op_dtype in (NLC_BF16, NLC_F16) else 32
     k = torch.zeros(Cout, kp, dtype=torch.float32, device=w.device)
     k[:, :9 * Cin] = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, -1)
-    if op_dtype == NLC_BF16:
-        return k.to(torch.bfloat16).contiguous()
+    if op_dtype in (NLC_BF16, NLC_F16):
+        return k.to(OP_DTYPES[op_dtype]).contiguous()
     return k if op_dtype == NLC_F32X3 else round_tf32_(k)
 
 
@@ -272,7 +272,7 @@ def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale,
     _lib.check(_lib.lib().nlc_attention(
         _ctx(qkv.t), C.c_void_p(qkv.ptr), op_dtype, qkv.ld, q_off, k_off, v_off, head_stride, qkv.B, T, heads, dh,
         scale, C.c_void_p(out.ptr), out.ld, _p(ws), _stream()))
-    fused = op_dtype == NLC_BF16 and dh == 64 and T % 64 == 0 and 64 <= T <= 1024
+    fused = op_dtype in (NLC_BF16, NLC_F16) and dh == 64 and T % 64 == 0 and 64 <= T <= 1024
     STATS.launches += 2 if fused else (4 if T >= 128 else 1)
 
 

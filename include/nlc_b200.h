@@ -36,6 +36,8 @@ extern "C" {
 #define NLC_BF16 1  /* bf16; kind::f16 MMA (the throughput mode)                                              */
 #define NLC_F32X3 2 /* plain fp32 operands and weights; nlc_conv_tc splits them into tf32 hi+lo parts in shared */
                     /* memory and issues three MMAs per K step: fp32-accurate products (the accuracy mode)     */
+#define NLC_F16 3   /* fp16; kind::f16 MMA at the bf16 rate with 3 more mantissa bits (the reference's own      */
+                    /* reduced-precision mode is fp16 too: src/fp16_util.py:15-22, UNetModel.convert_to_fp16)   */
 
 typedef struct nlc_ctx nlc_ctx;
 
@@ -52,7 +54,7 @@ int nlc_sm_count(nlc_ctx* ctx);
  * ---------------------------------------------------------------------------------------------- */
 
 typedef struct {
-    const void* ptr; /* operand tensor, bf16 (dtype NLC_BF16) or fp32 holding tf32-rounded values */
+    const void* ptr; /* operand tensor: bf16 / fp16 (NLC_BF16 / NLC_F16) or fp32 (tf32-rounded, or plain: NLC_F32X3) */
     int B, H, W, C;  /* logical NHWC extent                                                        */
     int ld;          /* elements between consecutive pixels                                        */
     int64_t sh, sn;  /* element strides of H and B; 0 = dense (W*ld, H*W*ld). Non-dense strides let H   */
@@ -76,7 +78,7 @@ typedef struct {
  * second source (torch.nn.Conv2d calls at src/unet_ddim.py:109-135,141,148-156). `weight` is
  * [Cout][sum nch] in the operand dtype, K ordered like seg[]. */
 typedef struct {
-    int dtype; /* NLC_BF16 (kind::f16), NLC_F32 (kind::tf32) or NLC_F32X3 (3 x kind::tf32 on split fp32) */
+    int dtype; /* NLC_BF16 / NLC_F16 (kind::f16), NLC_F32 (kind::tf32) or NLC_F32X3 (3 x kind::tf32 on split fp32) */
     int nsrc;
     nlc_operand src[NLC_MAX_SRC];
     int nseg;

@@ -20,14 +20,16 @@ def _rel(a, b):
 
 
 def _dt(name):
-    from nlc_b200._lib import NLC_BF16, NLC_F32
-    return NLC_BF16 if name == "bf16" else NLC_F32
+    from nlc_b200._lib import NLC_BF16, NLC_F16, NLC_F32
+    return {"bf16": NLC_BF16, "fp16": NLC_F16}.get(name, NLC_F32)
 
 
 def _rnd(x, dt):
     from nlc_b200 import ops
-    from nlc_b200._lib import NLC_BF16
-    return x.to(torch.bfloat16).float() if dt == NLC_BF16 else ops.round_tf32_(x.clone())
+    from nlc_b200._lib import NLC_BF16, NLC_F16
+    if dt in (NLC_BF16, NLC_F16):
+        return x.to(ops.OP_DTYPES[dt]).float()
+    return ops.round_tf32_(x.clone())
 
 
 CONV_CASES = [
@@ -43,7 +45,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32", "fp16"])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_conv_tc_matches_torch(dev, prec, case):
     """Operands are pre-rounded to the operand dtype, so the only difference left is fp32 summation order:
@@ -109,7 +111,7 @@ def test_conv_tc_rejects_bad_shapes(dev):
         ops.conv_tc([x], [(0, 0, 0, 0, 48)], w, 64, 1, 8, 8, NLC_BF16, out_f32=ops.Act(torch.zeros(1, 8, 8, 64, device=dev)))
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4)])
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4), ("fp16", 8e-4)])
 @pytest.mark.parametrize("shape", [(3, 8, 8, 256), (2, 64, 64, 384), (5, 2, 2, 512), (2, 16, 16, 1024)])
 @pytest.mark.parametrize("silu,ss", [(True, False), (False, True)])
 def test_groupnorm(dev, prec, tol, shape, silu, ss):
@@ -154,7 +156,7 @@ ATTN_CASES = [(3, 16, 1, 512, False), (2, 64, 4, 64, True), (2, 64, 1, 256, Fals
               (3, 128, 2, 64, True), (1, 512, 8, 64, False), (5, 256, 16, 64, True), (3, 1024, 8, 64, True)]
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16", 8e-3), ("tf32", 1e-3)])
+@pytest.mark.parametrize("prec,tol", [("bf16", 8e-3), ("tf32", 1e-3), ("fp16", 1e-3)])
 @pytest.mark.parametrize("case", ATTN_CASES)
 def test_attention(dev, prec, tol, case):
     from nlc_b200 import ops
@@ -200,7 +202,7 @@ def test_linear_and_embedding(dev):
     assert (out - torch.cat([arg.sin(), arg.cos()], 1)).abs().max() < 2e-6
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32", "fp16"])
 def test_resample_and_boundary_convs(dev, prec):
     from nlc_b200 import ops
     dt = _dt(prec)
@@ -267,7 +269,7 @@ def test_groupnorm_from_conv_epilogue_statistics(dev, prec, tol, shape):
     assert ((mr[:, :, 1].double() - (xg.var(2, unbiased=False) + 1e-5).rsqrt()) / mr[:, :, 1].double()).abs().max() < 2e-4
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4)])
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4), ("fp16", 8e-4)])
 @pytest.mark.parametrize("mode", [1, 2])
 def test_groupnorm_with_fused_resample(dev, prec, tol, mode):
     """resample=1: nearest x2 of silu(gn(x)); resample=2: avg_pool2d(silu(gn(x)), 2) (ADM resblock_updown h_upd)."""
@@ -288,7 +290,7 @@ def test_groupnorm_with_fused_resample(dev, prec, tol, mode):
     assert _rel(y.t.float().permute(0, 3, 1, 2), ref) < tol
 
 
-@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 6e-4)])
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 6e-4), ("fp16", 6e-4)])
 def test_input_conv_on_tensor_cores(dev, prec, tol):
     """im2col (per-sample input scale folded in) + K=64|32 GEMM == F.conv2d(x*scale, w, b); tolerance = one operand
     rounding of the 27-term dot product."""
@@ -301,7 +303,7 @@ def test_input_conv_on_tensor_cores(dev, prec, tol):
     w = (torch.randn(Cout, 3, 3, 3, generator=g) / 27 ** 0.5).to(dev)
     b = torch.randn(Cout, generator=g).to(dev)
     ref = F.conv2d(x * sc.view(-1, 1, 1, 1), w, b, padding=1)
-    kp = 64 if prec == "bf16" else 32
+    kp = 32 if prec == "tf32" else 64
     patches = ops.Act(torch.empty(B, H, W, kp, device=dev, dtype=ops.OP_DTYPES[dt]))
     ops.im2col_in(x, sc, patches, dt)
     out = ops.Act(torch.zeros(B, H, W, Cout, device=dev))
@@ -324,7 +326,7 @@ PAIR_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", ["bf16", "tf32"])
+@pytest.mark.parametrize("prec", ["bf16", "tf32", "fp16"])
 @pytest.mark.parametrize("case", PAIR_CASES)
 def test_conv_tc_cta_pair_kernel(dev, prec, case):
     """Same contract as test_conv_tc_matches_torch, plus GroupNorm partials, on the 256-row CTA-pair tiles."""

@@ -21,7 +21,8 @@ from oracle import weights
 pytestmark = pytest.mark.gpu
 dev = torch.device("cuda:0")
 
-STEP_TOL = {"tf32": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3), "bf16": dict(sigma=8e-3, eps=1e-1, x_prev=8e-2)}
+STEP_TOL = {"tf32": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3), "fp16": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3),
+             "bf16": dict(sigma=8e-3, eps=1e-1, x_prev=8e-2)}
 
 
 def _l2rel(a, b):
@@ -51,7 +52,7 @@ def golden_loops(golden_dir):
     return torch.load(os.path.join(golden_dir, "denoise_loop_tiny.pt"), weights_only=True)
 
 
-@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("prec", ["tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("key", ["ddim|0.0|none", "ddim_simple_orig|0.85|none", "ddim|0.5|fixedsmall",
                                  "ddpm|1.0|fixedlarge", "ddpm_orig|1.0|fixedsmall", "ddim_orig|0.3|fixedlarge",
                                  "ddim_simple|0.2|none", "ddim_simple_drag|0.2|none"])
@@ -82,7 +83,7 @@ def test_teacher_forced_steps_against_reference_dumps(golden_loops, prec, key):
         assert _l2rel(xpr.cpu(), case["x_prev"][i]) < 1e-5, (key, i)
 
 
-@pytest.mark.parametrize("prec,min_psnr", [("tf32", 40.0), ("bf16", 30.0)])
+@pytest.mark.parametrize("prec,min_psnr", [("tf32", 40.0), ("bf16", 30.0), ("fp16", 45.0)])
 def test_free_running_trajectory_psnr(golden_loops, prec, min_psnr):
     """ddim_simple_orig (the driver default, image_sample.py:56,65) re-derives eps from the clipped x0 each step and
     is contractive even for random-init weights; deterministic DDIM is not and is gated by the
