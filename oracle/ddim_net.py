@@ -23,7 +23,7 @@ def timestep_embedding(t, dim):
     # src/unet_ddim.py:28-46: sin || cos, frequencies exp(-i * log(1e4)/(half-1))
     half = dim // 2
     k = math.log(10000) / (half - 1)
-    freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -k)
+    freqs = torch.exp(torch.arange(half, dtype=torch.float32) * -k).to(t.device)
     arg = t.float()[:, None] * freqs[None, :]
     out = torch.cat([torch.sin(arg), torch.cos(arg)], dim=1)
     if dim % 2 == 1:
