@@ -93,6 +93,10 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 
 constexpr int kLinBM = 32, kLinBN = 64, kLinBK = 32;
 // y[b,n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] )
+// The layers behind this are weight-streaming (ADM's fused emb_layers: [32,1024] x [1024, ~40k] = 164 MB of weights per
+// call), so the kernel is built to keep loads in flight: 128-bit global loads of the next K chunk are issued into
+// registers before the FMAs of the current one (VEC: rows 16-byte aligned and K % 4 == 0; otherwise scalar loads).
+template <bool VEC>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ld_x, int B, int K,
                                                       const float* __restrict__ Wt, const float* __restrict__ bias,
                                                       int N, int act_in, int act_out, float* __restrict__ y, int ld_y) {
@@ -101,31 +105,64 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
     const int b0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, each 2 rows x 4 cols
     float acc[2][4] = {};
-    for (int k0 = 0; k0 < K; k0 += kLinBK) {
-        for (int i = threadIdx.x; i < kLinBM * kLinBK; i += 256) {
-            const int r = i / kLinBK, kk = i - r * kLinBK;
-            float v = 0.f;
-            if (b0 + r < B && k0 + kk < K) v = act_apply(x[static_cast<size_t>(b0 + r) * ld_x + k0 + kk], act_in);
-            xs[kk][r] = v;
-        }
-        for (int i = threadIdx.x; i < kLinBN * kLinBK; i += 256) {
-            const int r = i / kLinBK, kk = i - r * kLinBK;
-            float v = 0.f;
-            if (n0 + r < N && k0 + kk < K) v = Wt[static_cast<size_t>(n0 + r) * K + k0 + kk];
-            ws[kk][r] = v;
-        }
-        __syncthreads();
+    if (VEC) {
+        // per thread and chunk: one float4 of x (row xr, columns xk..xk+3), two float4 of W (rows wr, wr + 32)
+        const int xr = threadIdx.x >> 3, xk = (threadIdx.x & 7) << 2;
+        const int wr = threadIdx.x >> 3, wk = (threadIdx.x & 7) << 2;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto load = [&](int k0, float4& vx, float4& vw0, float4& vw1) {
+            vx = (b0 + xr < B && k0 + xk < K) ? __ldg(reinterpret_cast<const float4*>(x + static_cast<size_t>(b0 + xr) * ld_x + k0 + xk)) : zero;
+            vw0 = (n0 + wr < N && k0 + wk < K) ? __ldg(reinterpret_cast<const float4*>(Wt + static_cast<size_t>(n0 + wr) * K + k0 + wk)) : zero;
+            vw1 = (n0 + wr + 32 < N && k0 + wk < K) ? __ldg(reinterpret_cast<const float4*>(Wt + static_cast<size_t>(n0 + wr + 32) * K + k0 + wk)) : zero;
+        };
+        float4 vx, vw0, vw1;
+        load(0, vx, vw0, vw1);
+        for (int k0 = 0; k0 < K; k0 += kLinBK) {
+            xs[xk][xr] = act_apply(vx.x, act_in), xs[xk + 1][xr] = act_apply(vx.y, act_in);
+            xs[xk + 2][xr] = act_apply(vx.z, act_in), xs[xk + 3][xr] = act_apply(vx.w, act_in);
+            ws[wk][wr] = vw0.x, ws[wk + 1][wr] = vw0.y, ws[wk + 2][wr] = vw0.z, ws[wk + 3][wr] = vw0.w;
+            ws[wk][wr + 32] = vw1.x, ws[wk + 1][wr + 32] = vw1.y, ws[wk + 2][wr + 32] = vw1.z, ws[wk + 3][wr + 32] = vw1.w;
+            __syncthreads();
+            if (k0 + kLinBK < K) load(k0 + kLinBK, vx, vw0, vw1);  // in flight while the FMAs below run
 #pragma unroll 8
-        for (int kk = 0; kk < kLinBK; ++kk) {
-            const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+            for (int kk = 0; kk < kLinBK; ++kk) {
+                const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float w = ws[kk][tx + 16 * j];
-                acc[0][j] = fmaf(a0, w, acc[0][j]);
-                acc[1][j] = fmaf(a1, w, acc[1][j]);
+                for (int j = 0; j < 4; ++j) {
+                    const float w = ws[kk][tx + 16 * j];
+                    acc[0][j] = fmaf(a0, w, acc[0][j]);
+                    acc[1][j] = fmaf(a1, w, acc[1][j]);
+                }
             }
+            __syncthreads();
         }
-        __syncthreads();
+    } else {
+        for (int k0 = 0; k0 < K; k0 += kLinBK) {
+            for (int i = threadIdx.x; i < kLinBM * kLinBK; i += 256) {
+                const int r = i / kLinBK, kk = i - r * kLinBK;
+                float v = 0.f;
+                if (b0 + r < B && k0 + kk < K) v = act_apply(x[static_cast<size_t>(b0 + r) * ld_x + k0 + kk], act_in);
+                xs[kk][r] = v;
+            }
+            for (int i = threadIdx.x; i < kLinBN * kLinBK; i += 256) {
+                const int r = i / kLinBK, kk = i - r * kLinBK;
+                float v = 0.f;
+                if (n0 + r < N && k0 + kk < K) v = Wt[static_cast<size_t>(n0 + r) * K + k0 + kk];
+                ws[kk][r] = v;
+            }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < kLinBK; ++kk) {
+                const float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float w = ws[kk][tx + 16 * j];
+                    acc[0][j] = fmaf(a0, w, acc[0][j]);
+                    acc[1][j] = fmaf(a1, w, acc[1][j]);
+                }
+            }
+            __syncthreads();
+        }
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -225,7 +262,12 @@ extern "C" int nlc_linear(nlc_ctx* ctx, const float* x, int ld_x, int B, int K, 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && x && W && y && B > 0 && K > 0 && N > 0, "nlc_linear: bad argument");
     dim3 grid((N + kLinBN - 1) / kLinBN, (B + kLinBM - 1) / kLinBM);
-    linear_kernel<<<grid, 256, 0, stream>>>(x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
+    const bool vec = K % 4 == 0 && ld_x % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+    if (vec)
+        linear_kernel<true><<<grid, 256, 0, stream>>>(x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
+    else
+        linear_kernel<false><<<grid, 256, 0, stream>>>(x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

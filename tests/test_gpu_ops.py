@@ -194,6 +194,16 @@ def test_linear_and_embedding(dev):
     y = torch.zeros(37, 130, device=dev)
     ops.linear(x, W, b, y, act_in=1, act_out=2)
     assert _rel(y, F.gelu(F.linear(F.silu(x), W, b))) < 2e-6
+    # K not a multiple of 4 (scalar-load path), and a strided row view of a wider buffer (vector path, ld_x > K)
+    x1, W1 = torch.randn(5, 301, generator=g).to(dev), (torch.randn(70, 301, generator=g) / 17).to(dev)
+    y1 = torch.zeros(5, 70, device=dev)
+    ops.linear(x1, W1, None, y1)
+    assert _rel(y1, F.linear(x1, W1)) < 2e-6
+    wide = torch.randn(33, 1024 + 64, generator=g).to(dev)
+    W2 = (torch.randn(4100, 1024, generator=g) / 32).to(dev)
+    ywide = torch.zeros(33, 4100 + 12, device=dev)
+    ops.linear(wide[:, 64:], W2, None, ywide[:, 12:], act_in=1)
+    assert _rel(ywide[:, 12:], F.linear(F.silu(wide[:, 64:]), W2)) < 2e-6 and ywide[:, :12].abs().max() == 0
     t = torch.tensor([0.0, 1.0, 37.0, 999.0, 1000.0], device=dev)
     freqs = torch.exp(torch.arange(64, dtype=torch.float32) * -(9.210340371976184 / 63)).to(dev)
     out = torch.zeros(5, 128, device=dev)
