@@ -71,6 +71,24 @@ __global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x
     }
 }
 
+// ---------------------------------------------------------------- first C channels of an NHWC fp32 tensor -> NCHW
+// (output of the tensor-core conv_out, whose 3 | 6 real channels sit in a 64-channel padded tile)
+__global__ void __launch_bounds__(256) nhwc_head_to_nchw_kernel(const float* __restrict__ x, int ld, long long npix,
+                                                                 int HW, int C, float* __restrict__ out) {
+    for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
+         pix += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long n = pix / HW;
+        const int hw = static_cast<int>(pix - n * HW);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + pix * ld));
+        const float4 b = C > 4 ? __ldg(reinterpret_cast<const float4*>(x + pix * ld) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float* o = out + n * C * HW + hw;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            if (c < C) o[static_cast<size_t>(c) * HW] = v[c];
+    }
+}
+
 // ---------------------------------------------------------------- timestep embedding
 __global__ void temb_kernel(const float* __restrict__ t, int B, const float* __restrict__ freqs, int half,
                             int cos_first, float* __restrict__ out, int ld) {
@@ -243,6 +261,21 @@ extern "C" int nlc_resample_op(nlc_ctx* ctx, const void* x_op, int op_dtype, int
         else
             resample_kernel<2, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     }
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_nhwc_head_to_nchw(nlc_ctx* ctx, const float* x, int ld, int B, int H, int W, int C, float* out_nchw,
+                                     void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && x && out_nchw && C >= 1 && C <= 8 && ld >= 8 && ld % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(x) & 15) == 0,
+                "nlc_nhwc_head_to_nchw: C=%d (1..8) ld=%d (>= 8, %% 4) unsupported", C, ld);
+    const long long npix = static_cast<long long>(B) * H * W;
+    long long blocks = (npix + 255) / 256;
+    const long long cap = static_cast<long long>(ctx->sm_count) * 16;
+    if (blocks > cap) blocks = cap;
+    nhwc_head_to_nchw_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld, npix, H * W, C, out_nchw);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

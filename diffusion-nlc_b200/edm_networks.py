@@ -18,7 +18,8 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_groupnorm, run
+from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
+                     emit_groupnorm, run)
 from .ops import Act
 
 GN_EPS = 1e-6
@@ -182,6 +183,8 @@ class SongUNet:
         p = "dec.%dx%d_aux_" % (R, R)
         self.no_w, self.no_b = eng.dev32(sd[p + "norm.weight"]), eng.dev32(sd[p + "norm.bias"])
         self.cout_w, self.cout_b = eng.dev32(sd[p + "conv.weight"]), eng.dev32(sd[p + "conv.bias"])
+        self.cout_packed = (ops.pack_conv_out_weight(self.cout_w, self.cout_b, eng.op_dtype)
+                            if eng.chunk == 64 and self.cout_w.shape[0] <= 8 else None)
         order = [b for _, b in self.enc]
         n_enc = len(order)
         order += [b for _, b, _ in self.dec]
@@ -304,7 +307,7 @@ class SongUNet:
             cur = dest
         a = eng.act_op("ub.a0", B, R, R, cur.C)
         emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, _groups(cur.C), GN_EPS, a, silu=True)
-        dec.add(lambda: ops.conv_out_nchw(a, dt, self.cout_w, self.cout_b, P["out"]), "conv_out")
+        emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         m = max(enc._gn_ws_floats, dec._gn_ws_floats)
         enc._gn_ws_floats = dec._gn_ws_floats = m
         m = max(enc._attn_ws_bytes, dec._attn_ws_bytes)

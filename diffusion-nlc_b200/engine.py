@@ -226,6 +226,25 @@ def emit_conv_in(pc, x_nchw, in_scale_fn, w_packed, bias, Cout, dest, w_f32=None
                                out_op=dest.op, stats=st), "conv_in %dx%d ->%d B%d" % (H, W, Cout, B))
 
 
+def emit_conv_out(pc, src_op, w_f32, bias_f32, packed, out_nchw):
+    """The network's output convolution (C -> 3 | 6 channels, NCHW fp32 for the sampler).  16-bit modes: one 64-channel
+    tensor-core tile (weights zero-padded, `packed` = ops.pack_conv_out_weight(...)) into an fp32 scratch, then the
+    real channels are copied out as NCHW; the fp32-container (accuracy) modes keep the fp32 CUDA-core kernel."""
+    eng = pc.eng
+    dt = eng.op_dtype
+    Cout = w_f32.shape[0]
+    if dt not in (NLC_BF16, NLC_F16) or packed is None or Cout > 8:
+        pc.add(lambda: ops.conv_out_nchw(src_op, dt, w_f32, bias_f32, out_nchw), "conv_out (fp32 direct)")
+        return
+    wp, bp = packed
+    B, H, W = src_op.B, src_op.H, src_op.W
+    tmp = Act(eng.scratch("conv_out.tmp", (B, H, W, wp.shape[0]), torch.float32))
+    segs = ops.taps3x3(0, 0, src_op.C)
+    pc.add(lambda: ops.conv_tc([src_op], segs, wp, wp.shape[0], B, H, W, dt, bias=bp, out_f32=tmp),
+           "conv_out %dx%d %d->%d (padded to %d) B%d" % (H, W, src_op.C, Cout, wp.shape[0], B))
+    pc.add(lambda: ops.nhwc_head_to_nchw(tmp, Cout, out_nchw), "conv_out -> NCHW")
+
+
 def emit_conv1x1(pc, src_op, w_packed, bias, Cout, dest, resid=None, out_scale=1.0):
     dt = pc.eng.op_dtype
     B, H, W = src_op.B, src_op.H, src_op.W

@@ -198,6 +198,18 @@ def im2col_in(x_nchw, in_scale, patches, op_dtype):
     STATS.launches += 1
 
 
+def pack_conv_out_weight(w, bias, op_dtype, n_pad=64):
+    """torch [Cout<=8, Cin, 3, 3] (+bias) -> ([n_pad, 9*Cin] K-major operand weights, [n_pad] fp32 bias), zero rows
+    past Cout: the output convolution as one 64-channel tensor-core tile."""
+    Cout, Cin = w.shape[0], w.shape[1]
+    wp = torch.zeros(n_pad, Cin, 3, 3, dtype=torch.float32, device=w.device)
+    wp[:Cout] = w.detach().float()
+    bp = torch.zeros(n_pad, dtype=torch.float32, device=w.device)
+    if bias is not None:
+        bp[:Cout] = bias.detach().float()
+    return pack_conv_weight(wp, op_dtype), bp
+
+
 def pack_conv_in_weight(w, op_dtype):
     """torch [Cout,Cin,3,3] -> [Cout, 64|32]: column tap*Cin + ci, zero-padded to one 128-byte K row."""
     Cout, Cin = w.shape[0], w.shape[1]
@@ -216,6 +228,14 @@ def conv_out_nchw(x_op, op_dtype, weight, bias, out_nchw):
     _lib.check(_lib.lib().nlc_conv_out_nchw(
         _ctx(x_op.t), C.c_void_p(x_op.ptr), op_dtype, x_op.ld, x_op.B, x_op.C, x_op.H, x_op.W, _p(weight), _p(bias),
         Cout, _p(out_nchw), _stream()))
+    STATS.launches += 1
+
+
+@_timed("nhwc_head_to_nchw")
+def nhwc_head_to_nchw(x, n_ch, out_nchw):
+    """First n_ch (<= 8) channels of an fp32 NHWC Act -> NCHW fp32 (nlc_nhwc_head_to_nchw)."""
+    _lib.check(_lib.lib().nlc_nhwc_head_to_nchw(_ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H, x.W, n_ch, _p(out_nchw),
+                                                _stream()))
     STATS.launches += 1
 
 

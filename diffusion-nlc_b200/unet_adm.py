@@ -19,7 +19,8 @@ import math
 import torch
 
 from . import ops
-from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_groupnorm, run
+from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
+                     emit_groupnorm, run)
 from .ops import Act
 
 GN_EPS = 1e-5  # GroupNorm32 default, src/nn_util.py:93-100
@@ -225,6 +226,8 @@ class UNetModel:
                 idx += 1
         self.no_w, self.no_b = eng.dev32(sd["out.0.weight"]), eng.dev32(sd["out.0.bias"])
         self.cout_w, self.cout_b = eng.dev32(sd["out.2.weight"]), eng.dev32(sd["out.2.bias"])
+        self.cout_packed = (ops.pack_conv_out_weight(self.cout_w, self.cout_b, eng.op_dtype)
+                            if eng.chunk == 64 and self.cout_w.shape[0] <= 8 else None)
 
         # one GEMM for every block's emb_layers; encoder + middle first so that encode() uses a prefix
         order = [l[1] for blk in self.input_blocks for l in blk if l[0] == "res"]
@@ -389,7 +392,7 @@ class UNetModel:
             k -= 1
         a = eng.act_op("rb.a1", B, R, R, cur.C)
         emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
-        dec.add(lambda: ops.conv_out_nchw(a, dt, self.cout_w, self.cout_b, P["out"]))
+        emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         m = max(enc._gn_ws_floats, mid._gn_ws_floats, dec._gn_ws_floats)
         enc._gn_ws_floats = mid._gn_ws_floats = dec._gn_ws_floats = m
         m = max(enc._attn_ws_bytes, mid._attn_ws_bytes, dec._attn_ws_bytes)

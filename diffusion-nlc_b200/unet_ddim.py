@@ -13,7 +13,8 @@ import math
 import torch
 
 from . import ops
-from .engine import Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_groupnorm, run
+from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
+                     emit_groupnorm, run)
 from .ops import Act
 
 GN_EPS = 1e-6  # Normalize(), src/unet_ddim.py:54-55
@@ -163,6 +164,8 @@ class UNetModel:
             self.up.append(lvl)
         self.no_w, self.no_b = eng.dev32(sd["norm_out.weight"]), eng.dev32(sd["norm_out.bias"])
         self.cout_w, self.cout_b = eng.dev32(sd["conv_out.weight"]), eng.dev32(sd["conv_out.bias"])
+        self.cout_packed = (ops.pack_conv_out_weight(self.cout_w, self.cout_b, eng.op_dtype)
+                            if eng.chunk == 64 and self.cout_w.shape[0] <= 8 else None)
 
         # one GEMM for every block's temb projection; encoder blocks first so encode() uses a prefix
         order = [b for lvl in self.down for b in lvl["block"]] + [self.mid1, self.mid2]
@@ -328,7 +331,7 @@ class UNetModel:
                 emit_conv3x3(dec, upo, lvl["up"][0], lvl["up"][1], cur.C, head_feat(k))
         a = eng.act_op("rb.a1", B, R, R, cur.C)
         emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
-        dec.add(lambda: ops.conv_out_nchw(a, dt, self.cout_w, self.cout_b, P["out"]))
+        emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         enc._gn_ws_floats = dec._gn_ws_floats = max(enc._gn_ws_floats, dec._gn_ws_floats)
         enc._attn_ws_bytes = dec._attn_ws_bytes = max(enc._attn_ws_bytes, dec._attn_ws_bytes)
         P["enc"], P["dec"] = enc.steps, dec.steps

@@ -127,6 +127,11 @@ int nlc_im2col_in(nlc_ctx* ctx, const float* x_nchw, const float* in_scale /*[B]
                   int W, void* patches_op, int op_dtype, void* stream);
 int nlc_conv_out_nchw(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int Cin, int H, int W,
                       const float* weight, const float* bias, int Cout, float* out_nchw, void* stream);
+/* The output convolution on the tensor cores (16-bit modes): nlc_conv_tc with the C -> 3|6 weights zero-padded to one
+ * 64-channel tile writes NHWC fp32 [B,H,W,ld]; this copies its first C (<= 8) channels into the sampler's NCHW eps
+ * tensor (src/unet_ddim.py:362, src/unet_adm.py:664, src/edm_networks.py:876). */
+int nlc_nhwc_head_to_nchw(nlc_ctx* ctx, const float* x, int ld, int B, int H, int W, int C, float* out_nchw,
+                          void* stream);
 
 /* GroupNorm (+ optional SiLU, + optional per-sample scale/shift) producing the next conv's operand.
  * Replaces Normalize/GroupNorm32 + nonlinearity (src/unet_ddim.py:54-55,139-146; src/nn_util.py:17-19;
