@@ -142,9 +142,42 @@ __global__ void __launch_bounds__(kGnThreads)
     }
 }
 
+// Same merge with one warp per (sample, group) for small images (<= 512 partials per group: no block barriers, eight
+// groups per CTA instead of one CTA each; at 64x64 the block version above was 3 % of a c2 step in launch and barrier
+// latency).  grid ceil(B * groups / 8)
+__global__ void __launch_bounds__(256)
+    gn_finalize_blocks_warp_kernel(const float* __restrict__ stats, int stats_nblk, int n_rowgroups, int blocks_per_group,
+                                   int groups, int n_pairs, float eps, float* __restrict__ mr) {
+    const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pair >= n_pairs) return;
+    const int lane = threadIdx.x & 31;
+    const int n = pair / groups, g = pair - n * groups;
+    const float2* base = reinterpret_cast<const float2*>(stats) + static_cast<size_t>(n) * n_rowgroups * stats_nblk +
+                         g * blocks_per_group;
+    const int total = n_rowgroups * blocks_per_group;
+    float s = 0.f;
+    for (int i = lane; i < total; i += 32) {
+        const int rg = i / blocks_per_group, k = i - rg * blocks_per_group;
+        s += __ldg(base + static_cast<size_t>(rg) * stats_nblk + k).x;
+    }
+    const float mean = warp_sum(s) / static_cast<float>(total);
+    float m2 = 0.f;
+    for (int i = lane; i < total; i += 32) {
+        const int rg = i / blocks_per_group, k = i - rg * blocks_per_group;
+        const float2 p = __ldg(base + static_cast<size_t>(rg) * stats_nblk + k);
+        const float d = p.x - mean;
+        m2 += p.y + 128.0f * d * d;
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+        mr[pair * 2] = mean;
+        mr[pair * 2 + 1] = rsqrtf(m2 / (128.0f * static_cast<float>(total)) + eps);
+    }
+}
+
 // ---------------------------------------------------------------- apply
-template <bool TF32>
 // `rnd` is the operand format flag (common.h dtype_fmt): fp32 containers -> round to tf32; 16-bit -> fp16, not bf16
+template <bool TF32>
 __device__ __forceinline__ void gn_store8(void* __restrict__ y, size_t off, const float (&f)[8], int rnd) {
     if (TF32) {
         float* yp = static_cast<float*>(y) + off;
@@ -343,8 +376,12 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
     if (stats) {
         NLC_REQUIRE(HW % 32 == 0 && (reinterpret_cast<uintptr_t>(stats) & 7) == 0 && stats_nblk >= C / 4,
                     "nlc_groupnorm: conv-epilogue partials need H*W %% 32 == 0 and an 8-byte aligned buffer");
-        gn_finalize_blocks_kernel<<<dim3(groups, B), kGnThreads, 0, stream>>>(stats, stats_nblk, HW / 32,
-                                                                               (C / groups) / 4, eps, mr);
+        const int bpg = (C / groups) / 4;
+        if ((HW / 32) * bpg <= 512)
+            gn_finalize_blocks_warp_kernel<<<(B * groups + 7) / 8, 256, 0, stream>>>(stats, stats_nblk, HW / 32, bpg,
+                                                                                      groups, B * groups, eps, mr);
+        else
+            gn_finalize_blocks_kernel<<<dim3(groups, B), kGnThreads, 0, stream>>>(stats, stats_nblk, HW / 32, bpg, eps, mr);
         NLC_CHECK_LAUNCH();
     } else {
         const int stat_chunks = pick_chunks(B, HW, ctx->sm_count, 1);
