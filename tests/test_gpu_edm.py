@@ -127,7 +127,7 @@ def test_denoise_vector_teacher_forced(golden_edm, prec, key):
         assert _l2rel(mine.expand(2), ref.expand(2)) < tol_s, (key, c["style"])
 
 
-@pytest.mark.parametrize("prec,db", [("tf32", 50.0), ("bf16", 35.0), ("fp16", 50.0)])
+@pytest.mark.parametrize("prec,db", [("tf32", 50.0), ("bf16", 35.0), ("fp16", 45.0)])
 @pytest.mark.parametrize("key", ["pred_partial,pred|00|0|1.0", "base,base|00|0|1.0", "pred_partial,pred|01|1|1.004",
                                  "pred_sigma,pred_partial3|10|0|None"])
 def test_heun_sampler_free_running(golden_edm, prec, db, key):

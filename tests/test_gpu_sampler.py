@@ -4,7 +4,8 @@ CPU oracle.
 Primary gate = TEACHER-FORCED per-step parity: the reference's x_t of step k goes through one GPU step and
 sigma_hat, eps, x0_hat, x_{t-1} are compared (L2-relative).  Stated tolerances:
   tf32 operands:  sigma_hat 1e-3, eps 5e-3,  x_{t-1} 5e-3
-  bf16 operands:  sigma_hat 8e-3, eps 1e-1,  x_{t-1} 8e-2
+  bf16 operands:  sigma_hat 8e-3, eps 6e-2,  x_{t-1} 6e-2   (per sample; 1e-1 for a sample one time bucket off,
+                  tests/parity_util.py)
 They are set by operand rounding (2^-11 / 2^-9 per conv operand through ~30 layers) and by the discrete time
 lookup: sigma_hat is bucketised by searchsorted (src/schedulers.py:185-190), so an error of a few 1e-4 in
 sigma_hat moves t_hat by one bucket for the occasional sample and changes that sample's eps by ~1e-2.  The
@@ -17,12 +18,13 @@ import pytest
 import torch
 
 from oracle import weights
+from parity_util import assert_step_close, bucket_distance
 
 pytestmark = pytest.mark.gpu
 dev = torch.device("cuda:0")
 
 STEP_TOL = {"tf32": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3), "fp16": dict(sigma=1e-3, eps=5e-3, x_prev=5e-3),
-             "bf16": dict(sigma=8e-3, eps=1e-1, x_prev=8e-2)}
+             "bf16": dict(sigma=8e-3, eps=6e-2, x_prev=6e-2)}
 
 
 def _l2rel(a, b):
@@ -69,11 +71,12 @@ def test_teacher_forced_steps_against_reference_dumps(golden_loops, prec, key):
                                                    sch.sampling_sigmas[i + 1:i + 2], "pred", True, True)
         assert _l2rel(s_t.reshape(-1).cpu(), case["sigma_t"][i]) < tol["sigma"], (key, i)
         assert _l2rel(s_p.reshape(-1).cpu(), case["sigma_prev"][i]) < tol["sigma"], (key, i)
-        assert _l2rel(eps.cpu(), case["eps"][i]) < tol["eps"], (key, i)
+        dist = bucket_distance(sch, s_t.reshape(-1).cpu(), case["sigma_t"][i])
+        assert_step_close("eps", eps.cpu(), case["eps"][i], tol["eps"], dist, (key, i))
         x0h = sch.pred_xstart(xt, eps, s_t, clip=exp.clip_mode)
         noise = case["noises"][i].to(dev) if case["noises"] else None
         xp = sch.pred_xprev(x0=x0h, eps=eps, sigma_t=s_t, sigma_prev=s_p, xt=xt, log_variance=lv, noise=noise)
-        assert _l2rel(xp.cpu(), case["x_prev"][i]) < tol["x_prev"], (key, i)
+        assert_step_close("x_prev", xp.cpu(), case["x_prev"][i], tol["x_prev"], dist, (key, i))
         # the update arithmetic alone, fed with the reference's eps and sigmas: fp32-exact (1e-5)
         ref_st, ref_sp = case["sigma_t"][i].to(dev), case["sigma_prev"][i].to(dev)
         x0r = sch.pred_xstart(xt, case["eps"][i].to(dev), ref_st, clip=exp.clip_mode)
