@@ -150,9 +150,11 @@ using namespace nlc;
 
 // attention_fused.cu
 int nlc_attention_fused_16(nlc_ctx* ctx, const void* qkv, int f16, int ld, int q_off, int k_off, int head_stride, int B,
-                           int T, int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream);
+                           int T, int heads, int dh, float scale, const void* vt, void* out, int ld_out,
+                           cudaStream_t stream);
 
-// The fused kernel serves bf16 / fp16, 64-channel heads and T a multiple of 64 (the ADM 32x32 / 16x16 / 8x8 levels); everything
+// The fused kernel serves bf16 / fp16, head dimension 64 (ADM) or 256 (single-head unet_ddim / SongUNet blocks) and T a
+// multiple of 64; everything
 // else (fp32-container accuracy modes, the single-head dh = C blocks of unet_ddim / SongUNet) takes the GEMM + softmax
 // + GEMM path below.  NLC_FUSED_ATTN=0 disables it (A/B measurements).
 static bool fused_enabled() {
@@ -164,7 +166,7 @@ static bool fused_enabled() {
     return v != 0;
 }
 static bool use_fused(int op_dtype, int T, int dh) {
-    return dtype_is16(op_dtype) && dh == 64 && T >= 64 && T % 64 == 0 && T <= 1024 && fused_enabled();
+    return dtype_is16(op_dtype) && (dh == 64 || dh == 256) && T >= 64 && T % 64 == 0 && T <= 1024 && fused_enabled();
 }
 
 extern "C" size_t nlc_attention_ws(int op_dtype, int B, int T, int heads, int dh) {
@@ -234,8 +236,8 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
         NLC_CHECK_LAUNCH();
     }
     if (fused)
-        return nlc_attention_fused_16(ctx, qkv, f16 ? 1 : 0, ld, q_off, k_off, head_stride, B, T, heads, scale, VT, out_op,
-                                      ld_out, stream);
+        return nlc_attention_fused_16(ctx, qkv, f16 ? 1 : 0, ld, q_off, k_off, head_stride, B, T, heads, dh, scale, VT,
+                                      out_op, ld_out, stream);
     // S = scale * Q K^T   ("image" = sample, "row" = head, "column" = query token)
     {
         nlc_conv_desc d;

@@ -1,5 +1,6 @@
-// Fused multi-head self-attention on the tensor cores for the ADM attention levels (32x32 / 16x16: T = 1024 / 256
-// tokens, 64-channel heads; src/unet_adm.py:328-389 QKVAttentionLegacy / QKVAttention): S = Q K^T, softmax and
+// Fused self-attention on the tensor cores: the ADM levels (T = 64 / 256 / 1024 tokens, 64-channel heads) and the
+// single-head blocks of unet_ddim / SongUNet (T = 256, head dimension = C = 256; src/unet_ddim.py:186-207,
+// src/edm_networks.py:124-130).  ADM: src/unet_adm.py:328-389 QKVAttentionLegacy / QKVAttention): S = Q K^T, softmax and
 // O = P V in one kernel, so the T x T logits and probabilities never touch HBM (the unfused path in attention.cu
 // writes and re-reads 6 bytes per logit: 1.6 GB per 32x32 attention block at batch 32).
 //
@@ -21,18 +22,27 @@
 
 namespace nlc {
 
-constexpr int kFaDh = 64;                       // head dimension
 constexpr int kFaBlock = 128;                   // queries per tile
 constexpr int kFaKeys = 64;                     // keys per block
-constexpr int kFaStages = 4;                    // K / V^T ring
-constexpr int kFaTileBytes = kFaBlock * 128;    // 128 rows x 64 bf16 = 16 KB (Q, one P block)
-constexpr int kFaKBytes = kFaKeys * 128;        // 64 keys x 64 channels: 8 KB
-constexpr int kFaVtBytes = kFaDh * 128;         // 64 channels x 64 keys: 8 KB
-constexpr int kFaStageBytes = kFaKBytes + kFaVtBytes;  // 16 KB
+constexpr int kFaTileBytes = kFaBlock * 128;    // 128 rows x 64 elements = 16 KB (one Q chunk, one P block)
 constexpr int kFaPBytes = kFaTileBytes;         // P block: 128 queries x 64 keys
 constexpr int kFaThreads = 64 + 128;
-constexpr int kFaSmem = kFaTileBytes + kFaStages * kFaStageBytes + 2 * kFaPBytes + 256;  // 112.25 KB: two CTAs per SM
-constexpr int kFaTmemCols = 256;                // S double buffer (2 x 64) + O (64) -> next power of two
+
+// DH = head dimension: 64 (ADM: two CTAs per SM, 112 KB and 256 TMEM columns each) or 256 (single-head blocks: one CTA per
+// SM).  Q, K are staged as DH/64 K-major chunks of 64 channels; V^T as one [DH rows x 64 keys] tile.
+template <int DH>
+struct FaCfg {
+    static constexpr int kChunks = DH / 64;
+    static constexpr int kQBytes = kChunks * kFaTileBytes;
+    static constexpr int kKChunkBytes = kFaKeys * 128;              // 64 keys x 64 channels: 8 KB
+    static constexpr int kKBytes = kChunks * kKChunkBytes;
+    static constexpr int kVtBytes = DH * 128;                       // DH channels x 64 keys
+    static constexpr int kStageBytes = kKBytes + kVtBytes;
+    static constexpr int kStages = DH == 64 ? 4 : 2;
+    static constexpr int kSmem = kQBytes + kStages * kStageBytes + 2 * kFaPBytes + 256;
+    static constexpr int kTmemCols = DH == 64 ? 256 : 512;          // S double buffer (2 x 64) + O (DH) -> power of two
+    static constexpr int kCtasPerSm = DH == 64 ? 2 : 1;
+};
 
 struct FaParams {
     CUtensorMap mapQ, mapK, mapVt;
@@ -40,14 +50,19 @@ struct FaParams {
     int n_qblk, n_kblk, n_tiles;
     float scale_log2e;
     int f16;  // operands, P and the output are fp16 (else bf16)
+    cudaStream_t stream;
     __nv_bfloat16* out;  // (16-bit elements of either format)
     int ld_out;
 };
 
-__global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_constant__ FaParams p) {
+template <int DH>
+__global__ void __launch_bounds__(kFaThreads, FaCfg<DH>::kCtasPerSm) attn_fused_kernel(const __grid_constant__ FaParams p) {
+    using Cfg = FaCfg<DH>;
+    constexpr int kFaStages = Cfg::kStages;
+    constexpr int kFaStageBytes = Cfg::kStageBytes;
     extern __shared__ __align__(1024) uint8_t smem[];  // (the swizzled tiles need 1024-byte alignment; checked below)
     uint8_t* sQ = smem;
-    uint8_t* sKV = sQ + kFaTileBytes;
+    uint8_t* sKV = sQ + Cfg::kQBytes;
     uint8_t* sP = sKV + kFaStages * kFaStageBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kFaPBytes);
     uint64_t* kv_full = bars;                    // [kFaStages]
@@ -89,7 +104,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
         mbar_init(o_empty, 4);
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc<kFaTmemCols>(tmem_slot);
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -106,16 +121,20 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
                 const int bh = tile / p.n_qblk;
                 const int h = bh % p.heads, n = bh / p.heads;
                 mbar_wait(q_empty, (tile_it & 1) ^ 1);
-                mbar_expect_tx(q_full, kFaTileBytes);
-                tma_load_4d(sQ, &p.mapQ, q_full, 0, qb * kFaBlock, h, n);
+                mbar_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+                for (int c = 0; c < Cfg::kChunks; ++c)
+                    tma_load_4d(sQ + c * kFaTileBytes, &p.mapQ, q_full, c * 64, qb * kFaBlock, h, n);
                 for (int pass = 0; pass < 2; ++pass) {
                     for (int kb = 0; kb < nkb; ++kb, ++kv_it) {
                         const int st = kv_it % kFaStages;
                         mbar_wait(&kv_empty[st], ((kv_it / kFaStages) & 1) ^ 1);
                         uint8_t* sk = sKV + st * kFaStageBytes;
-                        mbar_expect_tx(&kv_full[st], pass ? kFaStageBytes : kFaKBytes);
-                        tma_load_4d(sk, &p.mapK, &kv_full[st], 0, kb * kFaKeys, h, n);
-                        if (pass) tma_load_3d(sk + kFaKBytes, &p.mapVt, &kv_full[st], kb * kFaKeys, 0, bh);
+                        mbar_expect_tx(&kv_full[st], pass ? kFaStageBytes : Cfg::kKBytes);
+#pragma unroll
+                        for (int c = 0; c < Cfg::kChunks; ++c)
+                            tma_load_4d(sk + c * Cfg::kKChunkBytes, &p.mapK, &kv_full[st], c * 64, kb * kFaKeys, h, n);
+                        if (pass) tma_load_3d(sk + Cfg::kKBytes, &p.mapVt, &kv_full[st], kb * kFaKeys, 0, bh);
                     }
                 }
             }
@@ -124,8 +143,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             const uint32_t idesc_s = umma_idesc(p.f16 ? 0 : 1, kFaBlock, kFaKeys);  // 128 queries x 64 keys
-            const uint32_t idesc_o = umma_idesc(p.f16 ? 0 : 1, kFaBlock, kFaDh);    // 128 queries x 64 channels
-            const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ));
+            const uint32_t idesc_o = umma_idesc(p.f16 ? 0 : 1, kFaBlock, DH);       // 128 queries x DH channels
+            const uint32_t q_addr = smem_u32(sQ);
             uint32_t kv_it = 0, s_it = 0, p_it = 0, tile_it = 0;
             // S block `s_it` = Q K^T of the K tile in ring slot `kv_it`
             auto issue_s = [&](uint32_t kv, uint32_t si) {
@@ -134,9 +153,15 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
                 mbar_wait(&s_empty[sb], ((si >> 1) & 1) ^ 1);
                 mbar_wait(&kv_full[st], (kv / kFaStages) & 1);
                 tc_fence_after_sync();
-                const uint64_t kdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes));
+                const uint32_t k_addr = smem_u32(sKV + st * kFaStageBytes);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + sb * kFaKeys, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+                for (int c = 0; c < Cfg::kChunks; ++c) {
+                    const uint64_t qdesc = umma_desc_sw128(q_addr + c * kFaTileBytes);
+                    const uint64_t kdesc = umma_desc_sw128(k_addr + c * Cfg::kKChunkBytes);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tmem_base + sb * kFaKeys, qdesc + 2 * k, kdesc + 2 * k, idesc_s, (c | k) != 0);
+                }
             };
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
                 mbar_wait(q_full, tile_it & 1);
@@ -163,7 +188,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
                     mbar_wait(&p_full[pb], (p_it >> 1) & 1);
                     tc_fence_after_sync();
                     const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + pb * kFaPBytes));
-                    const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes + kFaKBytes));
+                    const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes + Cfg::kKBytes));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (kb | k) != 0);
                     umma_commit(&kv_empty[st]);
@@ -243,9 +268,9 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
             tc_fence_after_sync();
             const float inv = 1.0f / sum;
             const bool row_ok = qb * kFaBlock + row < p.T;  // rows past T were zero-filled by TMA: nothing to store
-            __nv_bfloat16* orow = p.out + (static_cast<size_t>(n) * p.T + qb * kFaBlock + row) * p.ld_out + h * kFaDh;
+            __nv_bfloat16* orow = p.out + (static_cast<size_t>(n) * p.T + qb * kFaBlock + row) * p.ld_out + h * DH;
 #pragma unroll 1
-            for (int c = 0; c < kFaDh; c += 32) {
+            for (int c = 0; c < DH; c += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32b_x32(tmem_o + lane_addr + c, v);
                 tmem_ld_wait();
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
     __syncthreads();
     if (warp == 2) {
         tc_fence_after_sync();
-        tmem_dealloc<kFaTmemCols>(tmem_base);
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
@@ -277,8 +302,27 @@ __global__ void __launch_bounds__(kFaThreads, 2) attn_fused_kernel(const __grid_
 using namespace nlc;
 
 // Internal entry (declared in attention.cu): q/k inside the qkv tensor, V^T already in `vt` as [B*heads, 64, T].
+template <int DH>
+static int launch_fused(nlc_ctx* ctx, const FaParams& p) {
+    using Cfg = FaCfg<DH>;
+    static bool configured = false;
+    if (!configured) {
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        // two CTAs per SM need the whole 228 KB as shared memory (the default carveout only guarantees one)
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
+    const int slots = Cfg::kCtasPerSm * ctx->sm_count;
+    attn_fused_kernel<DH><<<p.n_tiles < slots ? p.n_tiles : slots, kFaThreads, Cfg::kSmem, p.stream>>>(p);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
 int nlc_attention_fused_16(nlc_ctx* ctx, const void* qkv, int f16, int ld, int q_off, int k_off, int head_stride, int B,
-                           int T, int heads, float scale, const void* vt, void* out, int ld_out, cudaStream_t stream) {
+                           int T, int heads, int dh, float scale, const void* vt, void* out, int ld_out,
+                           cudaStream_t stream) {
+    NLC_REQUIRE(dh == 64 || dh == 256, "nlc_attention(fused): head dimension %d unsupported (64, 256)", dh);
     NLC_REQUIRE(T % kFaKeys == 0 && T >= kFaKeys, "nlc_attention(fused): T=%d must be a multiple of %d", T, kFaKeys);
     NLC_REQUIRE(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && head_stride % 8 == 0 && ld_out % 8 == 0 &&
                     (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
@@ -291,14 +335,15 @@ int nlc_attention_fused_16(nlc_ctx* ctx, const void* qkv, int f16, int ld, int q
     p.n_tiles = B * heads * p.n_qblk;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.f16 = f16;
+    p.stream = stream;
     p.out = static_cast<__nv_bfloat16*>(out), p.ld_out = ld_out;
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(qkv);
     for (int which = 0; which < 2; ++which) {
         // (channel within head, token, head, image)
-        cuuint64_t gdim[4] = {(cuuint64_t)kFaDh, (cuuint64_t)T, (cuuint64_t)heads, (cuuint64_t)B};
-        cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(heads > 1 ? head_stride : kFaDh) * 2,
+        cuuint64_t gdim[4] = {(cuuint64_t)dh, (cuuint64_t)T, (cuuint64_t)heads, (cuuint64_t)B};
+        cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, (cuuint64_t)(heads > 1 ? head_stride : dh) * 2,
                               (cuuint64_t)T * ld * 2};
-        cuuint32_t box[4] = {(cuuint32_t)kFaDh, (cuuint32_t)(which ? kFaKeys : kFaBlock), 1, 1};
+        cuuint32_t box[4] = {64, (cuuint32_t)(which ? kFaKeys : kFaBlock), 1, 1};  // one 64-channel chunk per load
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = ctx->encode_tiled(which ? &p.mapK : &p.mapQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                                        const_cast<__nv_bfloat16*>(base + (which ? k_off : q_off)), gdim, gstr, box, estr,
@@ -309,25 +354,14 @@ int nlc_attention_fused_16(nlc_ctx* ctx, const void* qkv, int f16, int ld, int q
     }
     {
         // V^T: (token, channel, image*head)
-        cuuint64_t gdim[3] = {(cuuint64_t)T, (cuuint64_t)kFaDh, (cuuint64_t)B * heads};
-        cuuint64_t gstr[2] = {(cuuint64_t)T * 2, (cuuint64_t)T * kFaDh * 2};
-        cuuint32_t box[3] = {(cuuint32_t)kFaKeys, (cuuint32_t)kFaDh, 1};
+        cuuint64_t gdim[3] = {(cuuint64_t)T, (cuuint64_t)dh, (cuuint64_t)B * heads};
+        cuuint64_t gstr[2] = {(cuuint64_t)T * 2, (cuuint64_t)T * dh * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kFaKeys, (cuuint32_t)dh, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = ctx->encode_tiled(&p.mapVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(vt), gdim, gstr, box,
                                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_attention(fused): cuTensorMapEncodeTiled(V^T) failed with %d", (int)r);
     }
-    static bool configured = false;
-    if (!configured) {
-        NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmem));
-        // two CTAs per SM need the whole 228 KB as shared memory (the default carveout only guarantees one)
-        NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                            cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
-    const int grid = p.n_tiles < 2 * ctx->sm_count ? p.n_tiles : 2 * ctx->sm_count;
-    attn_fused_kernel<<<grid, kFaThreads, kFaSmem, stream>>>(p);
-    NLC_CHECK_LAUNCH();
-    return NLC_OK;
+    return dh == 64 ? launch_fused<64>(ctx, p) : launch_fused<256>(ctx, p);
 }

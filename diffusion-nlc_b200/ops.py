@@ -293,7 +293,7 @@ def attention(qkv, op_dtype, q_off, k_off, v_off, head_stride, heads, dh, scale,
     _lib.check(_lib.lib().nlc_attention(
         _ctx(qkv.t), C.c_void_p(qkv.ptr), op_dtype, qkv.ld, q_off, k_off, v_off, head_stride, qkv.B, T, heads, dh,
         scale, C.c_void_p(out.ptr), out.ld, _p(ws), _stream()))
-    fused = op_dtype in (NLC_BF16, NLC_F16) and dh == 64 and T % 64 == 0 and 64 <= T <= 1024
+    fused = op_dtype in (NLC_BF16, NLC_F16) and dh in (64, 256) and T % 64 == 0 and 64 <= T <= 1024
     STATS.launches += 2 if fused else (4 if T >= 128 else 1)
 
 

@@ -153,7 +153,9 @@ ATTN_CASES = [(3, 16, 1, 512, False), (2, 64, 4, 64, True), (2, 64, 1, 256, Fals
               (2, 1024, 4, 64, False), (2, 256, 4, 64, True),
               # the fused tcgen05 kernel (bf16, 64-channel heads, T % 128 == 0): one key block, odd batch, more tiles
               # than SMs (several tiles per persistent CTA), both qkv orders
-              (3, 128, 2, 64, True), (1, 512, 8, 64, False), (5, 256, 16, 64, True), (3, 1024, 8, 64, True)]
+              (3, 128, 2, 64, True), (1, 512, 8, 64, False), (5, 256, 16, 64, True), (3, 1024, 8, 64, True),
+              # head dimension 256 (unet_ddim / SongUNet single-head blocks): one CTA per SM, four 64-channel chunks
+              (160, 256, 1, 256, False), (2, 1024, 1, 256, False), (3, 128, 2, 256, True)]
 
 
 @pytest.mark.parametrize("prec,tol", [("bf16", 8e-3), ("tf32", 1e-3), ("fp16", 1e-3)])
