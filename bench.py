@@ -247,7 +247,7 @@ def main():
     ap.add_argument("--impl", default="nlc", choices=["nlc", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32", "fp32"])
     ap.add_argument("--timesteps", type=int, default=0, help="sampling steps per pass (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

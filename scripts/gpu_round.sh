@@ -19,9 +19,11 @@ head -4 $O/${TAG}_step_profile_c2_b256.log $O/${TAG}_step_profile_adm256_b32.log
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2100 -c 2200 --csv \
     --log-file $O/${TAG}_launches_c2_bench.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
     > $O/${TAG}_ncu_run.log 2>&1; echo "ncu launch list rc=$?"
+if [ "${NCU_FULL:-0}" = "1" ]; then
 for k in attn_fused_kernel:0:3 gn_apply_kernel:8:3 conv_tc_kernel:30:6; do
   name=${k%%:*}; rest=${k#*:}; skip=${rest%%:*}; cnt=${rest#*:}
   ncu --set full --clock-control none --import-source on -k regex:$name --launch-skip $skip --launch-count $cnt \
       -f -o $O/${TAG}_ncu_adm_$name python scripts/step_profile.py adm256 32 bf16 1 > $O/${TAG}_ncu_adm_$name.log 2>&1
   echo "ncu full $name rc=$?"
 done
+fi
