@@ -56,6 +56,8 @@ struct ConvKParams {
     int ld_rowvec;
     const float* resid;
     int ld_resid;
+    int resid_mode;            // 0 same size, 1 nearest x2 of a half-size tensor, 2 2x2 average of a double-size tensor
+    int log2_wo, log2_ho;      // (power-of-two extents: pixel index -> (n, ho, wo) by shifts)
     float out_scale;
     float* out_f32;
     int ld_out_f32;
@@ -417,13 +419,55 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 const int col0 = n_tile * BLOCK_N + c;
                 const int ocol0 = col0 + hs_off;
                 if (p.resid) {  // coalesced gather of the residual block while the TMEM load is in flight
+                    // (one loop per mode, so that the eight loads of a lane stay back to back: with the mode test inside
+                    // the loop the compiler serialised them and the residual layers lost 25 %)
+                    if (p.resid_mode == 0) {
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = it * 4 + sub_r4;
-                        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if ((vmask >> r) & 1)
-                            t = __ldg(reinterpret_cast<const float4*>(p.resid + (pix0 + r) * p.ld_resid + col0) + sub_c4);
-                        *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + sub_r4;
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((vmask >> r) & 1)
+                                t = __ldg(reinterpret_cast<const float4*>(p.resid + (pix0 + r) * p.ld_resid + col0) + sub_c4);
+                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                        }
+                    } else if (p.resid_mode == 1) {
+                        // resampled skip path: the residual lives at half resolution (nearest x2)
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + sub_r4;
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((vmask >> r) & 1) {
+                                const size_t q = pix0 + r;
+                                const size_t wo = q & (static_cast<size_t>(p.Wo) - 1);
+                                const size_t ho = (q >> p.log2_wo) & (static_cast<size_t>(p.Ho) - 1);
+                                const size_t nn = q >> (p.log2_wo + p.log2_ho);
+                                const size_t src = (nn * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
+                                t = __ldg(reinterpret_cast<const float4*>(p.resid + src * p.ld_resid + col0) + sub_c4);
+                            }
+                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                        }
+                    } else {
+                        // ... at double resolution (2x2 average; same association as avg_pool2d / resample_kernel)
+#pragma unroll 2
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + sub_r4;
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((vmask >> r) & 1) {
+                                const size_t q = pix0 + r;
+                                const size_t wo = q & (static_cast<size_t>(p.Wo) - 1);
+                                const size_t ho = (q >> p.log2_wo) & (static_cast<size_t>(p.Ho) - 1);
+                                const size_t nn = q >> (p.log2_wo + p.log2_ho);
+                                const size_t w2 = 2 * static_cast<size_t>(p.Wo);
+                                const float* s0 = p.resid + ((nn * 2 * p.Ho + 2 * ho) * w2 + 2 * wo) * p.ld_resid + col0;
+                                const float4 a = __ldg(reinterpret_cast<const float4*>(s0) + sub_c4);
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(s0 + p.ld_resid) + sub_c4);
+                                const float4 d = __ldg(reinterpret_cast<const float4*>(s0 + w2 * p.ld_resid) + sub_c4);
+                                const float4 e = __ldg(reinterpret_cast<const float4*>(s0 + (w2 + 1) * p.ld_resid) + sub_c4);
+                                t = make_float4(((a.x + b.x) + (d.x + e.x)) * 0.25f, ((a.y + b.y) + (d.y + e.y)) * 0.25f,
+                                                ((a.z + b.z) + (d.z + e.z)) * 0.25f, ((a.w + b.w) + (d.w + e.w)) * 0.25f);
+                            }
+                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                        }
                     }
                     __syncwarp();
                 }
@@ -691,6 +735,12 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
                     "buffer of >= Cout/4 blocks per 32 pixels");
         p.stats = d->stats, p.stats_nblk = d->stats_nblk;
     }
+    NLC_REQUIRE(d->resid_mode >= 0 && d->resid_mode <= 2 && (d->resid_mode == 0 || (d->resid && !d->out_head_split)) &&
+                    (d->resid_mode != 1 || (d->Ho % 2 == 0 && d->Wo % 2 == 0)),
+                "nlc_conv_tc: resid_mode %d needs a residual, a dense output and (mode 1) even extents", d->resid_mode);
+    p.resid_mode = d->resid_mode;
+    for (p.log2_wo = 0; (1 << p.log2_wo) < d->Wo; ++p.log2_wo) {}
+    for (p.log2_ho = 0; (1 << p.log2_ho) < d->Ho; ++p.log2_ho) {}
     p.bias = d->bias, p.rowvec = d->rowvec, p.ld_rowvec = d->ld_rowvec;
     p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;

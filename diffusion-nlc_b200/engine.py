@@ -190,7 +190,7 @@ def _want_stats(dest, Cout):
 
 
 def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None, out_scale=1.0, stride=1, pad=1,
-                 extra_src=None):
+                 extra_src=None, resid_mode=0):
     """3x3 conv over operand `src_op` (+ optional fused 1x1 over `extra_src`, already packed behind the 3x3
     weights) into Feat `dest` (fp32 and/or operand copy)."""
     dt = pc.eng.op_dtype
@@ -203,7 +203,8 @@ def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None
         segs = segs + [(1, 0, 0, 0, extra_src.C)]
     st = _want_stats(dest, Cout)
     pc.add(lambda: ops.conv_tc(srcs, segs, w_packed, Cout, B, Ho, Wo, dt, stride=stride, bias=bias, rowvec=rowvec,
-                               resid=resid, out_scale=out_scale, out_f32=dest.f32, out_op=dest.op, stats=st),
+                               resid=resid, out_scale=out_scale, out_f32=dest.f32, out_op=dest.op, stats=st,
+                               resid_mode=resid_mode),
            "conv3x3 %dx%d %d->%d s%d B%d%s" % (Ho, Wo, src_op.C, Cout, stride, B, " +1x1" if extra_src is not None else ""))
 
 

@@ -133,7 +133,7 @@ def taps3x3(src, c0, nch, pad=1):
 
 
 def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, rowvec=None, resid=None,
-            out_scale=1.0, out_f32=None, out_op=None, stats=False):
+            out_scale=1.0, out_f32=None, out_op=None, stats=False, resid_mode=0):
     """Tensor-core implicit GEMM (nlc_conv_tc). srcs: list[Act]; segs: list of (src, dh, dw, c0, nch);
     resid/out_f32/out_op: Act or None; rowvec: [B, Cout] fp32 tensor."""
     d = _lib.ConvDesc()
@@ -152,6 +152,7 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.rowvec, d.ld_rowvec = rowvec.data_ptr(), rowvec.stride(0)
     if resid is not None:
         d.resid, d.ld_resid = resid.ptr, resid.ld
+        d.resid_mode = resid_mode  # 1 / 2: the residual is at half / double resolution (nearest x2 / 2x2 average)
     d.out_scale = out_scale
     if out_f32 is not None:
         d.out_f32, d.ld_out_f32 = out_f32.ptr, out_f32.ld

@@ -83,21 +83,20 @@ def _emit_resblock(pc, w, x, dest, emb=None):
     eng = pc.eng
     dt = eng.op_dtype
     B, H, W = x.B, x.H, x.W
-    resid = x.f32
+    resid, resid_mode = x.f32, 0
     if w.updown is None:
         a1 = eng.act_op("rb.a1", B, H, W, w.cin)
         emit_groupnorm(pc, x.f32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True)
     else:
         # h_upd / x_upd (src/unet_adm.py:236-243): the activated tensor is written already resampled by the
-        # GroupNorm apply pass; x itself is resampled in fp32 for the residual add
+        # GroupNorm apply pass; x_upd is never materialised: the second conv's epilogue reads x at its own resolution
+        # (nearest x2 / 2x2 average, nlc_conv_desc.resid_mode)
         mode = 1 if w.updown == "up" else 2
         src32 = x.f32
         H, W = (2 * H, 2 * W) if mode == 1 else (H // 2, W // 2)
         a1 = eng.act_op("rb.a1r", B, H, W, w.cin)
         emit_groupnorm(pc, src32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True, resample=mode)
-        xr = eng.act_f32("rb.xr", B, H, W, w.cin)
-        pc.add(lambda: ops.resample(src32, mode, xr, None, dt), "resample (x_upd)")
-        resid = xr
+        resid_mode = mode
     h = eng.act_f32("rb.h", B, H, W, w.cout)
     rowvec = scale = shift = None
     if emb is not None and w.emb_w is not None:
@@ -113,7 +112,7 @@ def _emit_resblock(pc, w, x, dest, emb=None):
         assert x.op is not None and w.updown is None
         emit_conv3x3(pc, a2, w.w2, w.b2, w.cout, dest, extra_src=x.op)
     else:
-        emit_conv3x3(pc, a2, w.w2, w.b2, w.cout, dest, resid=resid)
+        emit_conv3x3(pc, a2, w.w2, w.b2, w.cout, dest, resid=resid, resid_mode=resid_mode)
 
 
 def _emit_attnblock(pc, w, x, dest):

@@ -108,6 +108,10 @@ typedef struct {
                            [B*Ho*Wo/32][stats_nblk][2] = (mean, M2) over 32 consecutive pixels x 4 channels; the
                            pointer is pre-offset to this output's first 4-channel block.  Needs Ho*Wo >= 128. */
     int stats_nblk;     /* 4-channel blocks per pixel group in the stats buffer (= its total channels / 4)    */
+    int resid_mode;     /* 0: resid is [B,Ho,Wo,.]; 1: resid is [B,Ho/2,Wo/2,.] and is added nearest-upsampled x2;
+                           2: resid is [B,2Ho,2Wo,.] and its 2x2 average is added (sum of the window, then * 0.25).
+                           Folds ADM's x_upd (src/unet_adm.py:236-243, Upsample / Downsample without conv of the
+                           skip path, :81-140) into the conv that consumes it.                                   */
 } nlc_conv_desc;
 
 int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);

@@ -392,3 +392,30 @@ def test_conv_tc_pair_kernel_fused_shortcut_wide_rows(dev):
                 NLC_BF16, out_f32=out)
     torch.cuda.synchronize()
     assert _rel(out.t.permute(0, 3, 1, 2), ref) < 5e-5
+
+
+@pytest.mark.parametrize("mode,shape", [(1, (3, 32, 32)), (2, (3, 32, 32)), (1, (40, 8, 8)), (2, (40, 8, 8)),
+                                        (1, (2, 128, 128)), (2, (1, 128, 128))])
+def test_conv_tc_resampled_residual(dev, mode, shape):
+    """nlc_conv_desc.resid_mode: the residual is read at half (1: nearest x2) / double (2: 2x2 average) resolution by
+    the epilogue, bit-identical to adding the separately resampled tensor (ADM resblock_updown x_upd)."""
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16
+    B, H, W = shape
+    C = 128
+    g = torch.Generator().manual_seed(31)
+    x = _rnd(torch.randn(B, C, H, W, generator=g).to(dev), NLC_BF16)
+    w = _rnd((torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(dev), NLC_BF16)
+    rs = (H // 2, W // 2) if mode == 1 else (2 * H, 2 * W)
+    resid = torch.randn(B, rs[0], rs[1], C, generator=g).to(dev)
+    full = torch.empty(B, H, W, C, device=dev)
+    ops.resample(ops.Act(resid), mode, ops.Act(full), None, NLC_BF16)
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    wp = ops.pack_conv_weight(w, NLC_BF16)
+    a, b = ops.Act(torch.zeros(B, H, W, C, device=dev)), ops.Act(torch.zeros(B, H, W, C, device=dev))
+    ops.conv_tc([xa], ops.taps3x3(0, 0, C), wp, C, B, H, W, NLC_BF16, resid=ops.Act(full), out_f32=a)
+    ops.conv_tc([xa], ops.taps3x3(0, 0, C), wp, C, B, H, W, NLC_BF16, resid=ops.Act(resid), out_f32=b, resid_mode=mode)
+    torch.cuda.synchronize()
+    assert torch.equal(a.t, b.t)
+    ref = F.conv2d(x, w, padding=1) + full.permute(0, 3, 1, 2)
+    assert _rel(b.t.permute(0, 3, 1, 2), ref) < 5e-5
