@@ -381,6 +381,20 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                                                  : (static_cast<size_t>(n0) * p.Ho + ho0) * p.Wo + wo0;
             const int hs_off = p.out_head_split * ho0;
 
+            // Residual rows of the chunk about to be processed are fetched one chunk ahead (mode 0): the first chunk's
+            // loads are issued before the accumulator wait, every later chunk's while the previous one is being stored.
+            float4 rpre[8];
+            const bool pre = p.resid != nullptr && p.resid_mode == 0;
+            auto prefetch_resid = [&](int c_next) {
+                const float* rp = p.resid + pix0 * p.ld_resid + n_tile * BLOCK_N + c_next;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + sub_r4;
+                    rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if ((vmask >> r) & 1) rpre[it] = __ldg(reinterpret_cast<const float4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c4);
+                }
+            };
+            if (pre) prefetch_resid(32 * half);
             // X3: the K chunks arrive one accumulator at a time and are summed here, in registers (round to nearest)
             constexpr int kNJ = X3 ? BLOCK_N / (32 * (kEpiWarps / 4)) : 1;  // column chunks owned by this warp
             float accr[kNJ][32];
@@ -425,11 +439,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 #pragma unroll
                         for (int it = 0; it < 8; ++it) {
                             const int r = it * 4 + sub_r4;
-                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if ((vmask >> r) & 1)
-                                t = __ldg(reinterpret_cast<const float4*>(p.resid + (pix0 + r) * p.ld_resid + col0) + sub_c4);
-                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = rpre[it];
                         }
+                        if (c + 32 * (kEpiWarps / 4) < BLOCK_N) prefetch_resid(c + 32 * (kEpiWarps / 4));
                     } else if (p.resid_mode == 1) {
                         // resampled skip path: the residual lives at half resolution (nearest x2)
 #pragma unroll
