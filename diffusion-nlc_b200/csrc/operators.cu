@@ -258,6 +258,33 @@ __global__ void l1_diff_rows_kernel(const float* __restrict__ a, const float* __
     }
 }
 
+// Per-sample restoration metrics of a finished batch (image_sample.py:671-679): s = clamp((x+1)/2, 0, 1) is the image
+// that gets written out; mse = mean((s - orig)^2) (PSNR = 10 log10(1/mse) is taken on the host), l1 = ||(2s-1) - (2 orig
+// - 1)||_1 (`cons_orig`).  One CTA per sample, one pass; `s_out` (nullable) receives s.
+__global__ void image_metrics_kernel(const float* __restrict__ x, const float* __restrict__ orig, long long n,
+                                     float* __restrict__ s_out, float* __restrict__ mse, float* __restrict__ l1) {
+    __shared__ float red[2][32];
+    const size_t base = static_cast<size_t>(blockIdx.x) * n;
+    float a2 = 0.f, a1 = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float s = fminf(fmaxf(__fmul_rn(__fadd_rn(x[base + i], 1.0f), 0.5f), 0.0f), 1.0f);
+        const float o = orig[base + i];
+        const float d = s - o;
+        a2 = fmaf(d, d, a2);
+        a1 += fabsf(__fadd_rn(__fmul_rn(2.0f, s), -1.0f) - __fadd_rn(__fmul_rn(2.0f, o), -1.0f));
+        if (s_out) s_out[base + i] = s;
+    }
+    a2 = warp_sum(a2), a1 = warp_sum(a1);
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = a2, red[1][threadIdx.x >> 5] = a1;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a2 = threadIdx.x < (blockDim.x >> 5) ? red[0][threadIdx.x] : 0.f;
+        a1 = threadIdx.x < (blockDim.x >> 5) ? red[1][threadIdx.x] : 0.f;
+        a2 = warp_sum(a2), a1 = warp_sum(a1);
+        if (threadIdx.x == 0) mse[blockIdx.x] = a2 / static_cast<float>(n), l1[blockIdx.x] = a1;
+    }
+}
+
 static inline unsigned blocks_for(long long n, int bs = 256) { return static_cast<unsigned>((n + bs - 1) / bs); }
 
 static int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const float* A, long long sab, long long sai,
@@ -492,6 +519,14 @@ extern "C" int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* w
 extern "C" int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, void* ws, void* stream) {
     NLC_REQUIRE(y, "nlc_op_project: y is null");
     return op_apply(op, 3, x0, y, B, x0_hat, ws, stream);
+}
+
+extern "C" int nlc_image_metrics(nlc_ctx* ctx, const float* x, const float* orig01, int B, int64_t n, float* sample01_out,
+                                 float* mse_out, float* l1_out, void* stream_) {
+    NLC_REQUIRE(ctx && x && orig01 && mse_out && l1_out && B > 0 && n > 0, "nlc_image_metrics: bad argument");
+    image_metrics_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream_)>>>(x, orig01, n, sample01_out, mse_out, l1_out);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
 }
 
 extern "C" int nlc_l1_diff_rows(nlc_ctx* ctx, const float* a, const float* b, int B, int64_t n, float* out,

@@ -327,6 +327,15 @@ int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0
 /* out[b] = sum_i |a[b,i] - b[b,i]|: the L1 constraint residuals of Constraint_Function.loss (image_sample.py:325-333) */
 int nlc_l1_diff_rows(nlc_ctx* ctx, const float* a, const float* b, int B, int64_t n, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY section 8(f) rank 1 (first slice): per-sample restoration metrics of a finished batch on the device instead
+ * of the PNG -> disk -> reload round trip (image_sample.py:671-679): s = clamp((x+1)/2, 0, 1);
+ * mse[b] = mean((s - orig)^2); l1[b] = ||(2s-1) - (2 orig - 1)||_1.  x is the sampler output in [-1,1] coordinates,
+ * orig01 the ground truth in [0,1], both [B, n] fp32; sample01_out (nullable) receives s.
+ * ---------------------------------------------------------------------------------------------- */
+int nlc_image_metrics(nlc_ctx* ctx, const float* x, const float* orig01, int B, int64_t n, float* sample01_out,
+                      float* mse_out, float* l1_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
