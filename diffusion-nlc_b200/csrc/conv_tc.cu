@@ -659,15 +659,32 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.num_m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
     p.Cout = d->Cout;
 
+    // Tile configuration: BLOCK_N in {64, 128, 256} x {one CTA, CTA pair}, chosen by a small cost model instead of "the
+    // widest tile that still gives every SM one".  Cost of a launch ~ waves x time per K chunk, where a chunk costs
+    // max(MMA time = 2*BLOCK_N clocks, operand latency / ring depth): with ~3000 clocks of TMA latency under load the
+    // narrow tiles are bound by bytes in flight, so two waves of 64-wide tiles lose to one (partial) wave of CTA pairs.
+    // (The batched right-hand operand of the attention GEMMs differs per M tile and stays on the 1-CTA kernel; the
+    // fp32 split mode has 1-CTA kernels for N <= 128 only.)
     int block_n = 64;
-    if (!x3 && d->Cout % 256 == 0 && p.num_m_tiles * (d->Cout / 256) >= ctx->sm_count)
-        block_n = 256;
-    else if (d->Cout % 128 == 0 && p.num_m_tiles * (d->Cout / 128) >= ctx->sm_count)
-        block_n = 128;
-    // CTA pairs (256-row tiles, the B tile shared by two SMs) when there is at least one pair tile per SM pair;
-    // the batched right-hand operand of the attention GEMMs differs per M tile and stays on the 1-CTA kernel
-    const bool pair = !x3 && ctx->use_cta_pairs && d->wbatched.ptr == nullptr && block_n >= 128 &&
-                      ((p.num_m_tiles + 1) / 2) * (d->Cout / block_n) >= ctx->sm_count / 2;
+    bool pair = false;
+    {
+        double best = 1e300;
+        for (int bn = 64; bn <= 256; bn *= 2) {
+            if (d->Cout % bn != 0 || (x3 && bn == 256)) continue;
+            for (int pr = 0; pr < 2; ++pr) {
+                if (pr && (x3 || !ctx->use_cta_pairs || d->wbatched.ptr != nullptr || bn < 128)) continue;
+                const long long units = (pr ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * static_cast<long long>(d->Cout / bn);
+                const int slots = pr ? ctx->sm_count / 2 : ctx->sm_count;
+                const long long waves = (units + slots - 1) / slots;
+                const int stages = x3 ? (bn == 128 ? 3 : 4) : (pr ? (bn == 256 ? 6 : 8) : (bn == 256 ? 4 : (bn == 128 ? 6 : 8)));
+                const double mma = (x3 ? 6.0 : (tf32 ? 4.0 : 2.0)) * bn;  // clocks per 128-byte K chunk per CTA
+                const double chunk = mma > 3000.0 / stages ? mma : 3000.0 / stages;
+                // prefer the wider tile on ties (fewer operand bytes per FLOP)
+                const double cost = static_cast<double>(waves) * chunk * (1.0 - 1e-3 * (bn / 64) - 1e-3 * pr);
+                if (cost < best) best = cost, block_n = bn, pair = pr != 0;
+            }
+        }
+    }
     p.num_n_tiles = d->Cout / block_n;
     p.num_m_units = pair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
     p.num_tiles = p.num_m_units * p.num_n_tiles;
