@@ -1,0 +1,98 @@
+"""Size-independent properties at BASELINE.json's full sizes (configs c4 / c5: the 552 M-parameter ADM-256 UNet, 256x256
+operators), where the CPU oracle would take minutes per sample:
+  * the network is finite, deterministic and has no cross-sample coupling (a batch of 3 equals the same images run as
+    batches of 2 + 1: what batch sharding over GPUs rests on), in the bf16 throughput mode and its fp16 sibling;
+  * the four DDNM operators of c4 / c5 at R = 256: one projection makes x feasible (A x = y), is idempotent, and
+    A A^+ y = y (exact pseudo-inverse on the measurement space);
+  * one constrained NLC step end to end (encode -> sigma-model -> forward -> dynamic clip -> projection -> update)."""
+from functools import partial
+
+import pytest
+import torch
+
+from oracle import weights
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+KEYS = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
+        "num_heads", "num_head_channels", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order")
+
+
+@pytest.fixture(scope="module")
+def adm256():
+    from nlc_b200.unet_adm import SigmaModel, UNetModel
+    cfg = dict(weights.ADM_CONFIGS["adm256"])
+    sg = cfg.pop("sigma")
+    sd = weights.adm_unet_state_dict(**cfg, seed=3)
+    ssd = weights.adm_sigma_state_dict(**sg, seed=4)
+    models = {}
+    for prec in ("bf16", "fp16"):
+        m = UNetModel(in_channels=3, precision=prec, device=dev, **{k: cfg[k] for k in KEYS}).load_state_dict(sd)
+        s = SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"], num_heads=cfg["num_heads"],
+                       num_head_channels=cfg["num_head_channels"], precision=prec, device=dev).load_state_dict(ssd)
+        models[prec] = (m, s)
+    return models
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_adm256_forward_is_finite_and_batch_independent(adm256, prec):
+    m, s = adm256[prec]
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(3, 3, 256, 256, generator=g).to(dev)
+    t = torch.tensor([900.0, 400.0, 20.0], device=dev)
+    sc = torch.tensor([0.05, 0.3, 0.9], device=dev)
+    full = m.forward_scaled(x, t, sc).clone()
+    assert full.shape == (3, 6, 256, 256) and torch.isfinite(full).all()
+    again = m.forward_scaled(x, t, sc).clone()
+    assert torch.equal(full, again)  # same plan, same launches: bit-reproducible
+    a = m.forward_scaled(x[:2].contiguous(), t[:2], sc[:2]).clone()
+    b = m.forward_scaled(x[2:].contiguous(), t[2:], sc[2:]).clone()
+    parts = torch.cat([a, b])
+    rel = ((parts - full).abs().max() / full.abs().max()).item()
+    assert rel < 2e-2 if prec == "bf16" else rel < 4e-3, rel  # tile / reduction-order differences only
+    feat = m.encode_scaled(x, t, sc)
+    r = s.forward_nhwc(feat)
+    assert r.shape[0] == 3 and torch.isfinite(r).all()
+
+
+@pytest.mark.parametrize("task,scale", [("sr_averagepooling", 4.0), ("inpainting_box", 1.0), ("colorization", 1.0),
+                                        ("cs_walshhadamard", 4.0)])
+def test_operators_at_256(task, scale):
+    from nlc_b200 import constraint_functions as CF
+    R, B = 256, 2
+    g = torch.Generator().manual_seed(10)
+    con = CF.get_constraint_function(task, constraint_scale=scale, device=dev, image_size=R, channels=3,
+                                     perm=torch.randperm(R * R, generator=g))
+    x = (torch.rand(B, 3, R, R, generator=g) * 2 - 1).to(dev)
+    y = con.transform(x)
+    x0 = torch.randn(B, 3, R, R, generator=g).to(dev)
+    p = con.constraint_fn(x0, y)
+    ymax = y.abs().max()
+    assert (con.transform(p) - y).abs().max() < 2e-5 * max(ymax.item(), 1.0)       # feasible after one projection
+    assert (con.constraint_fn(p, y) - p).abs().max() < 1e-4                          # idempotent
+    assert (con.A(con.Ap(y)) - y.reshape(B, -1)).abs().max() < 2e-5 * max(ymax.item(), 1.0)  # A A^+ = I on range(A)
+
+
+def test_one_constrained_step_at_full_size(adm256):
+    from nlc_b200 import constraint_functions as CF
+    from nlc_b200.experiments import ImageExperiment
+    from nlc_b200.schedulers import get_sampler
+    m, s = adm256["bf16"]
+    R, B = 256, 2
+    sch = get_sampler("ddim_simple_orig", 1000, 2, start_sigma=100.0, eta=0.85, sampler_var="learned").to(dev)
+    exp = ImageExperiment(m, sch, batch_size=B, data_shape=(3, R, R), seed=1, device=dev)
+    exp.set_model(m, s, learn_epsvar=True)
+    exp.set_norm_maxmin(-2.0, 110.0)
+    exp.set_clip_fn("dynamic")
+    con = CF.get_constraint_function("sr_averagepooling", constraint_scale=4.0, device=dev, image_size=R, channels=3)
+    g = torch.Generator().manual_seed(11)
+    x_true = (torch.rand(B, 3, R, R, generator=g) * 2 - 1).to(dev)
+    y = con.transform(x_true)
+    xT = (torch.randn(B, 3, R, R, generator=g) * (float(sch.sampling_sigmas[0]) ** 2 + 1) ** 0.5).to(dev)
+    out, _ = exp.denoise_loop(shape=(B, 3, R, R), xT=xT, style="pred", norm_eps=True, refine_prior_sigma=True,
+                              return_log=False, chunk_size=1, sigma_pred_threshold=960,
+                              constrain_fn=partial(con.constraint_fn, y=y, lambda_t=con.lr),
+                              constrain_loss=partial(con.loss, y=y))
+    assert out.shape == (B, 3, R, R) and torch.isfinite(out).all()
+    f, _ = con.loss(out.to(dev), y)
+    assert (f / y[0].numel()).max() < 1e-4  # the returned x0 satisfies the measurement
