@@ -50,6 +50,7 @@ class OpDesc(C.Structure):
         ("idx_host", C.c_void_p), ("n_idx", C.c_int64),
         ("U_small_host", C.c_void_p), ("V_small_host", C.c_void_p), ("sing_small_host", C.c_void_p),
         ("m_small", C.c_int), ("mult_host", C.c_void_p), ("pinv_mult_host", C.c_void_p),
+        ("U_small2_host", C.c_void_p), ("V_small2_host", C.c_void_p),
     ]
 
 

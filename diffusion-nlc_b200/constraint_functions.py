@@ -86,8 +86,11 @@ def svd_constraint(fn, fn_scale=4, device="cuda", base_mask_dir="store/inp_masks
         return ops_svd.Deblurring(torch.Tensor([1 / 9] * 9), channels, image_size, device)
     if fn == "deblur_gauss":
         return ops_svd.Deblurring(_gauss_kernel(5, 10), channels, image_size, device)
-    if fn in ("cs_blockbased", "denoising", "deblur_aniso"):
-        raise NotImplementedError("%s (CS / Denoising / Deblurring2D) is outside this build's scope (SURVEY §8f)" % fn)
+    if fn == "deblur_aniso":  # src/constraint_functions.py:280-292: 9 taps, sigma 1 along rows, sigma 20 along columns
+        k1, k2 = _gauss_kernel(9, 1), _gauss_kernel(9, 20)
+        return ops_svd.Deblurring2D(k1, k2, channels, image_size, device)
+    if fn in ("cs_blockbased", "denoising"):
+        raise NotImplementedError("%s (block CS / Denoising) is outside this build's scope (SURVEY §8f)" % fn)
     return None
 
 

@@ -28,7 +28,9 @@ struct nlc_op {
     int n_kept;
     float u, s;
     float* v0;    // COLOR: 3 ; SR_AVG: r*r
-    float *Us, *Vs, *mult, *pinv;  // SEPARABLE
+    float *Us, *Vs, *mult, *pinv;  // SEPARABLE (left factors; also right factors unless Us2 / Vs2 are set)
+    float *Us2, *Vs2;              // SEPARABLE: right factors (== Us / Vs for one-kernel operators)
+    bool own2;
 };
 
 namespace nlc {
@@ -297,7 +299,8 @@ static int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const fl
     return NLC_OK;
 }
 
-// separable forward:  out[b,c] = U_s ( mult_c o (V_s[:, :m]^T X V_s[:, :m]) ) U_s^T  (- sub)
+// separable forward:  out[b,c] = U_s ( mult_c o (V_s[:, :m]^T X V2_s[:, :m]) ) U2_s^T  (- sub);  U2 = U, V2 = V unless the
+// operator blurs rows and columns with different kernels
 static int separable_A(nlc_op* op, const float* x, int B, float* y, float* ws, const float* sub, cudaStream_t st) {
     const int R = op->R, m = op->m, n = B * op->C;
     float* T1 = ws;                                        // [n][m][R]
@@ -308,13 +311,13 @@ static int separable_A(nlc_op* op, const float* x, int B, float* y, float* ws, c
     if ((rc = launch_gemm(st, n, m, R, R, op->Vs, 0, 1, R, x, static_cast<long long>(R) * R, R, 1, T1, nullptr, 1,
                           nullptr, nullptr))) return rc;
     // T2 = (T1 V_s[:, :m]) o mult  B(k,j) = Vs[k*R + j]
-    if ((rc = launch_gemm(st, n, m, m, R, T1, static_cast<long long>(m) * R, R, 1, op->Vs, 0, R, 1, T2, op->mult, op->C,
+    if ((rc = launch_gemm(st, n, m, m, R, T1, static_cast<long long>(m) * R, R, 1, op->Vs2, 0, R, 1, T2, op->mult, op->C,
                           nullptr, nullptr))) return rc;
     // T3 = U_s T2
     if ((rc = launch_gemm(st, n, m, m, m, op->Us, 0, m, 1, T2, static_cast<long long>(m) * m, m, 1, T3, nullptr, 1,
                           nullptr, nullptr))) return rc;
     // Y = T3 U_s^T (- sub)         B(k,j) = Us[j*m + k]
-    return launch_gemm(st, n, m, m, m, T3, static_cast<long long>(m) * m, m, 1, op->Us, 0, 1, m, y, nullptr, 1, sub,
+    return launch_gemm(st, n, m, m, m, T3, static_cast<long long>(m) * m, m, 1, op->Us2, 0, 1, m, y, nullptr, 1, sub,
                        nullptr);
 }
 // separable backward: out[b,c] = V_s[:, :m] ( table_c o (U_s^T Y U_s) ) V_s[:, :m]^T   (base - value if base)
@@ -327,11 +330,11 @@ static int separable_back(nlc_op* op, const float* y, int B, float* x, float* ws
     int rc;
     if ((rc = launch_gemm(st, n, m, m, m, op->Us, 0, 1, m, y, static_cast<long long>(m) * m, m, 1, W1, nullptr, 1,
                           nullptr, nullptr))) return rc;                                  // U_s^T Y
-    if ((rc = launch_gemm(st, n, m, m, m, W1, static_cast<long long>(m) * m, m, 1, op->Us, 0, m, 1, W2, table, op->C,
+    if ((rc = launch_gemm(st, n, m, m, m, W1, static_cast<long long>(m) * m, m, 1, op->Us2, 0, m, 1, W2, table, op->C,
                           nullptr, nullptr))) return rc;                                  // (W1 U_s) o table
     if ((rc = launch_gemm(st, n, R, m, m, op->Vs, 0, R, 1, W2, static_cast<long long>(m) * m, m, 1, X1, nullptr, 1,
                           nullptr, nullptr))) return rc;                                  // V_s[:, :m] W2
-    return launch_gemm(st, n, R, R, m, X1, static_cast<long long>(R) * m, m, 1, op->Vs, 0, 1, R, x, nullptr, 1, nullptr,
+    return launch_gemm(st, n, R, R, m, X1, static_cast<long long>(R) * m, m, 1, op->Vs2, 0, 1, R, x, nullptr, 1, nullptr,
                        base);                                                             // X1 V_s[:, :m]^T
 }
 
@@ -408,6 +411,13 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
             if ((rc = to_device(&op->Us, d->U_small_host, mm)) || (rc = to_device(&op->Vs, d->V_small_host, N)) ||
                 (rc = to_device(&op->mult, d->mult_host, mm * d->channels)) ||
                 (rc = to_device(&op->pinv, d->pinv_mult_host, mm * d->channels))) return rc;
+            op->Us2 = op->Us, op->Vs2 = op->Vs, op->own2 = false;
+            if (d->U_small2_host || d->V_small2_host) {
+                NLC_REQUIRE(d->U_small2_host && d->V_small2_host, "nlc_op_create: U_small2 and V_small2 come together");
+                if ((rc = to_device(&op->Us2, d->U_small2_host, mm)) || (rc = to_device(&op->Vs2, d->V_small2_host, N)))
+                    return rc;
+                op->own2 = true;
+            }
             op->ydim = static_cast<int64_t>(d->channels) * mm;
         } break;
         default:
@@ -422,6 +432,7 @@ extern "C" void nlc_op_destroy(nlc_op* op) {
     if (!op) return;
     cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->v0);
     cudaFree(op->Us), cudaFree(op->Vs), cudaFree(op->mult), cudaFree(op->pinv);
+    if (op->own2) cudaFree(op->Us2), cudaFree(op->Vs2);
     delete op;
 }
 

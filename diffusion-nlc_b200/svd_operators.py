@@ -136,12 +136,17 @@ class WalshHadamardCS(A_functions):
         super().__init__(d, (p,), device)
 
 
-def _separable(self, U_s, V_s, mult, pinv, channels, img_dim, m, device):
+def _separable(self, U_s, V_s, mult, pinv, channels, img_dim, m, device, U2_s=None, V2_s=None):
     U_s, V_s = U_s.contiguous().float(), V_s.contiguous().float()
     mult, pinv = mult.contiguous().float(), pinv.contiguous().float()
     d = _lib.OpDesc(task=SEPARABLE, channels=channels, R=img_dim, ratio=1, U_small_host=_fptr(U_s),
                     V_small_host=_fptr(V_s), m_small=m, mult_host=_fptr(mult), pinv_mult_host=_fptr(pinv))
-    A_functions.__init__(self, d, (U_s, V_s, mult, pinv), device)
+    keep = [U_s, V_s, mult, pinv]
+    if U2_s is not None:  # different right-hand factors (Deblurring2D)
+        U2_s, V2_s = U2_s.contiguous().float(), V2_s.contiguous().float()
+        d.U_small2_host, d.V_small2_host = _fptr(U2_s), _fptr(V2_s)
+        keep += [U2_s, V2_s]
+    A_functions.__init__(self, d, tuple(keep), device)
 
 
 def _zero_guarded_inverse(s):
@@ -204,6 +209,40 @@ class Deblurring(A_functions):
         pinv = torch.empty(channels, R * R)
         pinv[:, perm] = _zero_guarded_inverse(full).reshape(R * R, channels).t()
         _separable(self, U_s, V_s, mult, pinv, channels, R, R, device)
+
+
+class Deblurring2D(A_functions):
+    """Anisotropic blur (functions/svd_operators.py:1094-1165): kernel1 along the rows, kernel2 along the columns, zero
+    padding, the same singular-value pairing as Deblurring."""
+
+    def __init__(self, kernel1, kernel2, channels, img_dim, device, ZERO=3e-2):
+        self.channels, self.img_dim = channels, img_dim
+        self.xdim = channels * img_dim ** 2
+        R = img_dim
+
+        def small(kernel):
+            kernel = kernel.detach().cpu().float()
+            half = kernel.shape[0] // 2
+            A = torch.zeros(R, R)
+            for i in range(R):
+                for j in range(i - half, i + half):
+                    if 0 <= j < R:
+                        A[i, j] = kernel[j - i + half]
+            U, s, V = torch.svd(A, some=False)
+            s = s.clone()
+            s[s < ZERO] = 0
+            return U, s, V
+
+        U1, s1, V1 = small(kernel1)
+        U2, s2, V2 = small(kernel2)
+        big = torch.matmul(s1.reshape(R, 1), s2.reshape(1, R)).reshape(R * R)
+        big_sorted, perm = big.sort(descending=True)
+        full = big_sorted.repeat(1, channels).reshape(-1)
+        mult = torch.empty(channels, R * R)
+        mult[:, perm] = full.reshape(R * R, channels).t()
+        pinv = torch.empty(channels, R * R)
+        pinv[:, perm] = _zero_guarded_inverse(full).reshape(R * R, channels).t()
+        _separable(self, U1, V1, mult, pinv, channels, R, R, device, U2_s=U2, V2_s=V2)
 
 
 def l1_diff_rows(a, b):

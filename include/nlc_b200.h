@@ -313,6 +313,9 @@ typedef struct {
     int m_small;                  /* SEPARABLE: R/f (SRConv) or R (Deblurring)                             */
     const float* mult_host;       /* SEPARABLE: [channels, m*m] spectral multipliers used by A and At      */
     const float* pinv_mult_host;  /* SEPARABLE: [channels, m*m] zero-guarded reciprocals used by A^+       */
+    const float* U_small2_host;   /* SEPARABLE, optional: right-hand factors when rows and columns are blurred   */
+    const float* V_small2_host;   /* by different kernels (Deblurring2D, functions/svd_operators.py:1094-1165):  */
+                                  /* A x = U (mult o (V^T X V2)) U2^T; NULL = same as U_small / V_small          */
 } nlc_op_desc;
 
 int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out);

@@ -9,7 +9,7 @@ Every operator is kept in the reference's own spectral form  A = U Sigma V^T,  A
 A^+ = V Sigma^+ U^T  (functions/svd_operators.py:52-80) with explicit `Vt / V / Ut / U / singulars` steps, so this
 file restates the algorithm rather than the closed forms the CUDA kernels use.
   Inpainting :324-359   Colorization :627-667   SuperResolution :479-533   WalshHadamardCS :211-251
-  SRConv :851-931       Deblurring :934-1014    projection image_sample.py:376-379
+  SRConv :851-931       Deblurring :934-1014    Deblurring2D :1094-1165    projection image_sample.py:376-379
 """
 import torch
 
@@ -293,6 +293,67 @@ class Deblurring(_Separable):
 
     def add_zeros(self, v):
         return v.reshape(v.shape[0], -1)
+
+
+class Deblurring2D(_Separable):
+    """Anisotropic blur (functions/svd_operators.py:1094-1165): kernel1 acts on the rows (left matrices U1, V1), kernel2 on
+    the columns (right matrices U2, V2); singular values s1 (x) s2 sorted descending, pairing as in Deblurring."""
+
+    def __init__(self, kernel1, kernel2, channels, R, zero=3e-2):
+        self.C, self.R = channels, R
+
+        def small(kernel):
+            A = torch.zeros(R, R)
+            half = kernel.shape[0] // 2
+            for i in range(R):
+                for j in range(i - half, i + half):
+                    if 0 <= j < R:
+                        A[i, j] = kernel[j - i + half]
+            return torch.svd(A, some=False)
+
+        self.U1, s1, self.V1 = small(kernel1)
+        self.U2, s2, self.V2 = small(kernel2)
+        s1[s1 < zero] = 0
+        s2[s2 < zero] = 0
+        self.s_sorted, self.perm = torch.matmul(s1.reshape(R, 1), s2.reshape(1, R)).reshape(R * R).sort(descending=True)
+
+    def _to_spec(self, L, Rm, x):
+        b, R = x.shape[0], self.R
+        t = self._sandwich(L.t(), x.reshape(b, self.C, R, R), Rm, b).reshape(b, self.C, -1)
+        return t[:, :, self.perm].transpose(1, 2).reshape(b, -1)
+
+    def _from_spec(self, L, Rm, v):
+        b, R = v.shape[0], self.R
+        t = torch.zeros(b, R * R, self.C)
+        t[:, self.perm, :] = v.reshape(b, R * R, self.C)
+        return self._sandwich(L, t.transpose(1, 2).reshape(b, self.C, R, R), Rm.t(), b).reshape(b, -1)
+
+    def Vt(self, x):
+        return self._to_spec(self.V1, self.V2, x)
+
+    def V(self, v):
+        return self._from_spec(self.V1, self.V2, v)
+
+    def Ut(self, y):
+        return self._to_spec(self.U1, self.U2, y)
+
+    def U(self, v):
+        return self._from_spec(self.U1, self.U2, v)
+
+    def singulars(self):
+        return self.s_sorted.repeat(1, 3).reshape(-1)
+
+    def add_zeros(self, v):
+        return v.reshape(v.shape[0], -1)
+
+
+def aniso_kernels():
+    """src/constraint_functions.py:280-292: 9 taps, sigma 1 (rows) and sigma 20 (columns), each normalised."""
+    def k(sigma):
+        pdf = lambda x: torch.exp(torch.Tensor([-0.5 * (x / sigma) ** 2]))
+        kk = torch.Tensor([pdf(i) for i in range(-4, 5)])
+        return kk / kk.sum()
+    return k(1), k(20)
 
 
 def constraint_inv_transform(op, deg, y, channels, R):

@@ -125,6 +125,7 @@ def main():
     edm()
     loops2()
     loops3()
+    operators2()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
@@ -236,6 +237,23 @@ def loops2():
         gold["%s|%d|%s|%s|%s|%s" % (loop, int(cont), clip, rates, kind, eta)] = dict(
             z=z, noises=noises, final=final, timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone(), **rec)
     torch.save(gold, os.path.join(HERE, "loops2_tiny.pt"))
+
+
+def operators2():
+    """Operators added after the first golden set: the anisotropic blur Deblurring2D with the reference's deblur_aniso
+    kernels (src/constraint_functions.py:280-292)  -> operators2_r32.pt"""
+    R = refimport.load()
+    ref = R.svd_operators
+    Rr, C, Bo = 32, 3, 2
+    g = torch.Generator().manual_seed(22)
+    xs = torch.rand(Bo, C * Rr * Rr, generator=g) * 2 - 1
+    x0 = torch.randn(Bo, C, Rr, Rr, generator=g)
+    k1, k2 = O.aniso_kernels()
+    op = ref.Deblurring2D(k1, k2, C, Rr, "cpu")
+    y = op.A(xs.clone())
+    proj = x0 - op.A_pinv(op.A(x0.reshape(Bo, -1)) - y).reshape(x0.shape)
+    gold = dict(x=xs, x0=x0, deblur_aniso=dict(A=y, At=op.At(y.clone()), A_pinv=op.A_pinv(y.clone()), project=proj))
+    torch.save(gold, os.path.join(HERE, "operators2_r32.pt"))
 
 
 CONSTRAINED_TASKS = [("sr_averagepooling", 4), ("inpainting_box", 1), ("colorization", 1), ("cs_walshhadamard", 4)]

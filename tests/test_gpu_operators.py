@@ -24,16 +24,20 @@ def _build(name, R, C, missing=None, perm=None):
         return P.WalshHadamardCS(C, R, 4, perm, dev)
     if name == "sr_bicubic":
         return P.SRConv(O.bicubic_kernel(4), C, R, dev, stride=4)
+    if name == "deblur_aniso":
+        return P.Deblurring2D(*O.aniso_kernels(), C, R, dev)
     return P.Deblurring(O.gauss_kernel(), C, R, dev)
 
 
-NAMES = ["inpainting", "colorization", "sr_averagepooling", "cs_walshhadamard", "sr_bicubic", "deblur_gauss"]
+NAMES = ["inpainting", "colorization", "sr_averagepooling", "cs_walshhadamard", "sr_bicubic", "deblur_gauss",
+         "deblur_aniso"]
 
 
 @pytest.mark.parametrize("name", NAMES)
 def test_against_reference_golden(golden_dir, name):
-    g = torch.load(os.path.join(golden_dir, "operators_r32.pt"), weights_only=True)
-    op = _build(name, 32, 3, g["missing"], g["perm"])
+    g = torch.load(os.path.join(golden_dir, "operators2_r32.pt" if name == "deblur_aniso" else "operators_r32.pt"),
+                   weights_only=True)
+    op = _build(name, 32, 3, g.get("missing"), g.get("perm"))
     y = op.A(g["x"].to(dev))
     tol = 2e-6 if name in ("inpainting", "colorization", "sr_averagepooling", "cs_walshhadamard") else 2e-4
     assert (y.cpu() - g[name]["A"]).abs().max() < tol

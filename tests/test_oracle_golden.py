@@ -178,6 +178,18 @@ def test_continuous_t_dynamic_clip_and_projection_loop(golden_dir, tiny):
         assert torch.equal(x0, case["final"]), key
 
 
+def test_anisotropic_deblurring(golden_dir):
+    """tests/golden/operators2_r32.pt: functions/svd_operators.py Deblurring2D with the deblur_aniso kernels."""
+    g = load(golden_dir, "operators2_r32.pt")
+    op = O.Deblurring2D(*O.aniso_kernels(), 3, 32)
+    ref = g["deblur_aniso"]
+    y = op.A(g["x"])
+    assert (y - ref["A"]).abs().max() < 5e-5
+    assert (op.At(ref["A"]) - ref["At"]).abs().max() < 5e-5
+    assert (op.A_pinv(ref["A"]) - ref["A_pinv"]).abs().max() < 5e-3 * ref["A_pinv"].abs().max()
+    assert (op.project(g["x0"], ref["A"]) - ref["project"]).abs().max() < 5e-3 * ref["project"].abs().max()
+
+
 def test_constrained_restoration_loops(golden_dir):
     """tests/golden/loops3_constrained.pt: the reference's denoise_loop with the DDNM `svd` projection and best-x0
     tracking (configs c4/c5: ADM learned-variance net, ddim_simple_orig, dynamic clip) for SR x4, box inpainting,

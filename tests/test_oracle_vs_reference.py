@@ -135,6 +135,7 @@ def test_operators(R):
         (ref.SRConv(O.bicubic_kernel(2), C, Rr, "cpu", stride=2), O.SRConv(O.bicubic_kernel(2), C, Rr, 2)),
         (ref.Deblurring(O.gauss_kernel(), C, Rr, "cpu"), O.Deblurring(O.gauss_kernel(), C, Rr)),
         (ref.Deblurring(torch.Tensor([1 / 9] * 9), C, Rr, "cpu"), O.Deblurring(torch.Tensor([1 / 9] * 9), C, Rr)),
+        (ref.Deblurring2D(*O.aniso_kernels(), C, Rr, "cpu"), O.Deblurring2D(*O.aniso_kernels(), C, Rr)),
     ]
     for a, b in pairs:
         y = a.A(x.clone())
