@@ -12,8 +12,9 @@
 //     convolutions use the tensor map's traversal stride, and the nine taps re-read the brick from L2;
 //   * a ResNet block's 1x1 shortcut and a concat are just more K segments over another tensor map.
 //
-// One persistent CTA per SM, 10 warps:  warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
-// warps 2-9 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype stores).
+// One persistent CTA per SM, 11 warps:  warp 0 = TMA producer of the A (activation) tiles, warp 1 = MMA issuer (one
+// elected thread), warps 2-9 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype
+// stores), warp 10 = TMA producer of the W (weight) tiles.
 // smem ring of STAGES x (16 KB A + BLOCK_N*128 B W); two TMEM accumulators so the epilogue of tile i
 // overlaps the main loop of tile i+1.
 //
@@ -33,9 +34,9 @@ constexpr int kBlockM = 128;
 constexpr int kChunkBytes = 128;                      // one swizzle row = one K chunk
 constexpr int kAStageBytes = kBlockM * kChunkBytes;   // 16 KB
 constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: they split the column chunks
-constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;  // warp 0 TMA (A tiles), warp 1 MMA, warps 2.. epilogue, last warp TMA (W tiles)
 constexpr int kSplitWarps = 4;                     // MODE 2 only: warps 2+kEpiWarps.. split fp32 stages into hi/lo
-constexpr int kThreadsX3 = kThreads + 32 * kSplitWarps;
+constexpr int kThreadsX3 = 64 + 32 * kEpiWarps + 32 * kSplitWarps;  // (one producer warp; the split warps follow the epilogue)
 
 struct ConvSegDev {
     int map, dh, dw, c0, nchunk;
@@ -219,14 +220,16 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                             if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kLoadBytes);
                             tma_load_4d_pair(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
                                              h0 + sg.dh, n0);
-                            tma_load_4d_pair(sb, &p.mapB, &full[stage], kchunk * kChunkElems,
-                                             n_tile * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows, 0, 0);
+                            if (X3)
+                                tma_load_4d_pair(sb, &p.mapB, &full[stage], kchunk * kChunkElems,
+                                                 n_tile * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows, 0, 0);
                         } else {
                             mbar_expect_tx(&full[stage], Cfg::kLoadBytes);
                             tma_load_4d(sa, &p.mapA[sg.map], &full[stage], sg.c0 + j * kChunkElems, w0 + sg.dw,
                                         h0 + sg.dh, n0);
-                            tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
-                                        p.w_batched ? th : 0, p.w_batched ? n0 : 0);
+                            if (X3)  // (the other modes have a second producer warp for the W tiles, below)
+                                tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
+                                            p.w_batched ? th : 0, p.w_batched ? n0 : 0);
                         }
                         ++kchunk;
                         if (++stage == kStages) {
@@ -312,6 +315,38 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
+            }
+        }
+    } else if (!X3 && warp == 2 + kEpiWarps) {
+        // ------------------------------------------------------------ second TMA producer: the W (right-hand) tiles
+        // One thread has ~250 clocks per K chunk at BLOCK_N = 128; waiting for the slot, arming the barrier and issuing
+        // two tensor loads does not fit, so the A and W loads of a stage are issued by two warps.  The A producer arms
+        // the stage's barrier with the byte count of both (a transaction that completes before the expect is legal:
+        // the phase cannot complete until the arrive that comes with it).
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+                const int n_tile = unit / p.num_m_units;
+                const int m_tile = CTA2 ? 2 * (unit - n_tile * p.num_m_units) + static_cast<int>(rank)
+                                        : unit - n_tile * p.num_m_units;
+                const int tn = m_tile / tiles_per_img;
+                const int th = (m_tile - tn * tiles_per_img) / p.tiles_w;
+                const int n0 = tn * p.BN;
+                for (int kchunk = 0; kchunk < p.total_chunks; ++kchunk) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sb = smem + stage * Cfg::kStageBytes + kAStageBytes;
+                    if (CTA2)
+                        tma_load_4d_pair(sb, &p.mapB, &full[stage], kchunk * kChunkElems,
+                                         n_tile * BLOCK_N + static_cast<int>(rank) * Cfg::kBRows, 0, 0);
+                    else
+                        tma_load_4d(sb, &p.mapB, &full[stage], kchunk * kChunkElems, n_tile * BLOCK_N,
+                                    p.w_batched ? th : 0, p.w_batched ? n0 : 0);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
             }
         }
     } else if (X3 && warp >= 2 + kEpiWarps) {
