@@ -1,0 +1,102 @@
+"""Out-of-bounds guards (compute-sanitizer is not available on the GPU pool): every kernel writes its output into the
+middle of a larger buffer filled with a sentinel, and the guard bands on both sides must come back untouched.  Covers
+the kernels added late in round 1 (small-image GroupNorm, fused attention at both head dimensions, the tensor-core
+output convolution and its NCHW head copy, linear, image metrics, the resampled-residual conv epilogue)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+SENT = 12345.0
+GUARD = 4096
+
+
+def _sent(dtype):
+    return 0xA5 if dtype == torch.uint8 else SENT
+
+
+def guarded(shape, dtype=torch.float32):
+    n = 1
+    for s in shape:
+        n *= s
+    buf = torch.full((n + 2 * GUARD,), _sent(dtype), device=dev, dtype=dtype)
+    return buf, buf[GUARD:GUARD + n].view(*shape)
+
+
+def intact(buf, n):
+    s = torch.tensor(_sent(buf.dtype), dtype=buf.dtype)
+    return bool((buf[:GUARD] == s).all() and (buf[GUARD + n:] == s).all())
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16", "tf32"])
+def test_groupnorm_small_and_large(prec):
+    from nlc_b200 import ops
+    from nlc_b200.engine import PRECISIONS
+    dt = PRECISIONS[prec]
+    for (B, H, W, C) in [(3, 8, 8, 256), (5, 4, 4, 512), (2, 2, 2, 1024), (2, 32, 32, 128)]:
+        x = torch.randn(B, H, W, C, device=dev)
+        buf, y = guarded((B, H, W, C), ops.OP_DTYPES[dt])
+        ws = torch.zeros(ops.groupnorm_ws(B, H * W, C, 32), device=dev)
+        ops.groupnorm(ops.Act(x), 32, 1e-5, torch.ones(C, device=dev), torch.zeros(C, device=dev), ops.Act(y), dt, ws)
+        torch.cuda.synchronize()
+        assert intact(buf, y.numel()) and torch.isfinite(y.float()).all() and (y.float() != SENT).all()
+
+
+@pytest.mark.parametrize("case", [(3, 64, 4, 64), (2, 256, 16, 64), (1, 1024, 8, 64), (5, 256, 1, 256), (3, 64, 2, 256)])
+def test_fused_attention(case):
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16
+    B, T, heads, dh = case
+    C = heads * dh
+    side = 1 << ((T.bit_length() - 1) // 2)
+    qkv = torch.randn(B, side, T // side, 3 * C, device=dev).to(torch.bfloat16)
+    buf, out = guarded((B, side, T // side, C), torch.bfloat16)
+    nws = max(ops.attention_ws(NLC_BF16, B, T, heads, dh), 16)
+    wbuf, ws = guarded((nws,), torch.uint8)
+    ops.attention(ops.Act(qkv), NLC_BF16, 0, C, 2 * C, dh, heads, dh, dh ** -0.5, ops.Act(out), ws)
+    torch.cuda.synchronize()
+    assert intact(buf, out.numel()) and torch.isfinite(out.float()).all()
+    assert intact(wbuf, nws)
+
+
+def test_conv_out_head_linear_metrics_and_resampled_residual():
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_BF16, lib, ctx
+    import ctypes as C
+    B, H, W, Cin = 3, 32, 32, 128
+    # tensor-core conv_out: padded 64-channel tile -> NCHW head copy
+    a = ops.Act(torch.randn(B, H, W, Cin, device=dev).to(torch.bfloat16))
+    wp, bp = ops.pack_conv_out_weight(torch.randn(6, Cin, 3, 3, device=dev) * 0.05, torch.randn(6, device=dev), NLC_BF16)
+    tbuf, tmp = guarded((B, H, W, 64))
+    ops.conv_tc([a], ops.taps3x3(0, 0, Cin), wp, 64, B, H, W, NLC_BF16, bias=bp, out_f32=ops.Act(tmp))
+    obuf, out = guarded((B, 6, H, W))
+    ops.nhwc_head_to_nchw(ops.Act(tmp), 6, out)
+    torch.cuda.synchronize()
+    assert intact(tbuf, tmp.numel()) and intact(obuf, out.numel()) and (out != SENT).all()
+    assert torch.equal(out, tmp[..., :6].permute(0, 3, 1, 2))
+    # linear, ragged sizes
+    x = torch.randn(37, 516, device=dev)
+    Wm = torch.randn(1001, 516, device=dev)
+    ybuf, y = guarded((37, 1001))
+    ops.linear(x, Wm, None, y)
+    torch.cuda.synchronize()
+    assert intact(ybuf, y.numel()) and (y != SENT).all()
+    # image metrics
+    n = 3 * 17 * 9
+    mbuf, m = guarded((5,))
+    lbuf, l1 = guarded((5,))
+    sbuf, s01 = guarded((5, n))
+    xs, xo = torch.randn(5, n, device=dev), torch.rand(5, n, device=dev)
+    rc = lib().nlc_image_metrics(ctx(0), xs.data_ptr(), xo.data_ptr(), 5, n, C.c_void_p(s01.data_ptr()), m.data_ptr(),
+                                 l1.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc == 0 and intact(mbuf, 5) and intact(lbuf, 5) and intact(sbuf, s01.numel())
+    # conv with the residual read at half / double resolution
+    for mode, rs in ((1, (H // 2, W // 2)), (2, (2 * H, 2 * W))):
+        resid = torch.randn(B, rs[0], rs[1], Cin, device=dev)
+        w3 = ops.pack_conv_weight(torch.randn(Cin, Cin, 3, 3, device=dev) * 0.03, NLC_BF16)
+        fbuf, f = guarded((B, H, W, Cin))
+        ops.conv_tc([a], ops.taps3x3(0, 0, Cin), w3, Cin, B, H, W, NLC_BF16, resid=ops.Act(resid), out_f32=ops.Act(f),
+                    resid_mode=mode)
+        torch.cuda.synchronize()
+        assert intact(fbuf, f.numel()) and (f != SENT).all()
