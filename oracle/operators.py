@@ -10,8 +10,39 @@ A^+ = V Sigma^+ U^T  (functions/svd_operators.py:52-80) with explicit `Vt / V / 
 file restates the algorithm rather than the closed forms the CUDA kernels use.
   Inpainting :324-359   Colorization :627-667   SuperResolution :479-533   WalshHadamardCS :211-251
   SRConv :851-931       Deblurring :934-1014    Deblurring2D :1094-1165    projection image_sample.py:376-379
+DDNM+ (noisy measurements): `A_pinv_eta` :82-91 and the per-class `Lambda` / `Lambda_noise`
+(:253-320, :361-439, :464-476, :535-623, :669-736, :1016-1091) are restated once, on the base class, as
+  Lambda(v)          = V( lambda o V^T v )
+  Lambda_noise(v, e) = V( d1 o P v ) + V( d2 o P e )        P = the re-ordering half of V^T, without its rotation
+with the three per-component tables of `ddnm_tables`; `Denoising` :442-476 and the block-wise `CS` :101-160 and
+`GeneralA` :173-208 operators follow the same spectral form.
 """
 import torch
+
+
+def ddnm_tables(s, a, sigma_y, sigma_t, eta):
+    """The per-spectral-component factors of DDNM+ for zero-padded singular values `s` (one entry per component of
+    V^T x): lambda of Eq. 17 and the noise scales d1 (fresh noise), d2 (predicted noise) of Eq. 51, as the reference's
+    Lambda / Lambda_noise build them (e.g. functions/svd_operators.py:256-270, 282-303).  `a` and `sigma_t` are fp32
+    scalars (0-dim tensors at the reference's call site, functions/svd_ddnm.py:121-132), `sigma_y` and `eta` Python
+    floats; every product below is therefore taken in fp32, in the reference's order."""
+    a = torch.as_tensor(a, dtype=torch.float32).reshape(())
+    st = torch.as_tensor(sigma_t, dtype=torch.float32).reshape(())
+    one = torch.ones_like(s)
+    root = (1 - eta ** 2) ** 0.5
+    inv = 1.0 / s
+    inv[s == 0] = 0.0
+    lam, d1, d2 = one.clone(), one * st * eta, one * st * root
+    if a != 0 and sigma_y != 0:
+        thr = a * sigma_y * inv
+        below, above, null = st < thr, st > thr, s == 0
+        lam = torch.where(below, s * st * root / a / sigma_y, lam)
+        resid = st ** 2 - a ** 2 * sigma_y ** 2 * inv ** 2
+        d1 = torch.where(above, torch.sqrt(torch.where(above, resid, torch.zeros_like(resid))), d1)
+        d2 = torch.where(below | above, torch.zeros_like(d2), d2)
+        d1 = torch.where(null, one * st * eta, d1)
+        d2 = torch.where(null, one * st * root, d2)
+    return lam, d1, d2
 
 
 class SpectralOp:
@@ -36,6 +67,35 @@ class SpectralOp:
     def project(self, x0, y):
         b = x0.shape[0]
         return x0 - self.A_pinv(self.A(x0.reshape(b, -1)) - y.reshape(b, -1)).reshape(x0.shape)
+
+    # ---- DDNM+ -----------------------------------------------------------------------------------------------
+    def A_pinv_eta(self, y, eta):
+        """Regularised pseudo-inverse V diag(s / (s^2 + eta)) U^T (functions/svd_operators.py:82-91)."""
+        t = self.Ut(y).clone()
+        s = self.singulars()
+        t[:, :s.shape[0]] = t[:, :s.shape[0]] * (s / (s * s + eta))
+        return self.V(self.add_zeros(t))
+
+    def lambda_singulars(self):
+        """Singular value of every component of Vt(x), zero on the null space."""
+        s = self.singulars()
+        out = torch.zeros(self.C * self.R * self.R)
+        out[:s.shape[0]] = s
+        return out
+
+    def reorder(self, x):
+        """P x: the re-ordering half of V^T (image entries put in the spectral order, no rotation): what Lambda_noise
+        applies to the noise vectors.  Equals Vt where V is a permutation."""
+        return self.Vt(x)
+
+    def Lambda(self, v, a, sigma_y, sigma_t, eta):
+        lam, _, _ = ddnm_tables(self.lambda_singulars(), a, sigma_y, sigma_t, eta)
+        return self.V(lam * self.Vt(v.reshape(v.shape[0], -1)))
+
+    def Lambda_noise(self, v, a, sigma_y, sigma_t, eta, eps):
+        _, d1, d2 = ddnm_tables(self.lambda_singulars(), a, sigma_y, sigma_t, eta)
+        b = v.shape[0]
+        return self.V(d1 * self.reorder(v.reshape(b, -1))) + self.V(d2 * self.reorder(eps.reshape(b, -1)))
 
 
 class Inpainting(SpectralOp):
@@ -109,6 +169,9 @@ class Colorization(_Needle):
     def singulars(self):
         return self.Ss.repeat(self.R * self.R)
 
+    def reorder(self, x):  # channel k of a pixel stands in for component k (functions/svd_operators.py:698-699)
+        return x.reshape(x.shape[0], -1)
+
     def add_zeros(self, v):
         out = torch.zeros(v.shape[0], 3 * self.R * self.R)
         out[:, :self.R * self.R] = v.reshape(v.shape[0], -1)
@@ -120,16 +183,27 @@ class SuperResolution(_Needle):
         self.C, self.R, self.r, self.yd = channels, R, ratio, R // ratio
         self._svd([1 / ratio ** 2] * ratio ** 2)
 
-    def Vt(self, x):
+    def _patches(self, x):
         b, r, yd = x.shape[0], self.r, self.yd
-        img = x.reshape(b, self.C, yd, r, yd, r).permute(0, 1, 2, 4, 3, 5).reshape(b, self.C, yd * yd, r * r)
-        rot = torch.matmul(self.Vs.t(), img.reshape(-1, r * r, 1)).reshape(b, self.C, yd * yd, r * r)
+        return x.reshape(b, self.C, yd, r, yd, r).permute(0, 1, 2, 4, 3, 5).reshape(b, self.C, yd * yd, r * r)
+
+    def _spectral_order(self, comp):  # [b, C, patches, r*r] -> component 0 of every patch first, the rest interleaved
+        b, r, yd = comp.shape[0], self.r, self.yd
         out = torch.zeros(b, self.C * self.R * self.R)
         n0 = self.C * yd * yd
-        out[:, :n0] = rot[..., 0].reshape(b, n0)
+        out[:, :n0] = comp[..., 0].reshape(b, n0)
         for k in range(r * r - 1):
-            out[:, n0 + k::r * r - 1] = rot[..., k + 1].reshape(b, n0)
+            out[:, n0 + k::r * r - 1] = comp[..., k + 1].reshape(b, n0)
         return out
+
+    def Vt(self, x):
+        b, r, yd = x.shape[0], self.r, self.yd
+        img = self._patches(x)
+        rot = torch.matmul(self.Vs.t(), img.reshape(-1, r * r, 1)).reshape(b, self.C, yd * yd, r * r)
+        return self._spectral_order(rot)
+
+    def reorder(self, x):  # patch entry k stands in for component k (functions/svd_operators.py:575-581)
+        return self._spectral_order(self._patches(x))
 
     def V(self, v):
         b, r, yd = v.shape[0], self.r, self.yd
@@ -176,6 +250,10 @@ class WalshHadamardCS(SpectralOp):
         t[:, :, self.perm] = v.reshape(b, -1, self.C).transpose(1, 2)
         return self.fwht(t).reshape(b, -1)
 
+    def reorder(self, x):  # functions/svd_operators.py:277-280: the permutation without the transform
+        b = x.shape[0]
+        return x.reshape(b, self.C, -1)[:, :, self.perm].transpose(1, 2).reshape(b, -1)
+
     def U(self, v):
         return v.reshape(v.shape[0], -1)
 
@@ -199,7 +277,17 @@ class _Separable(SpectralOp):
         return torch.matmul(torch.matmul(L, img.reshape(b * self.C, img.shape[-2], img.shape[-1])), Rm)
 
 
-class SRConv(_Separable):
+class _NoLambda:
+    """The reference defines no Lambda / Lambda_noise for these classes (the base raises, :93-97)."""
+
+    def Lambda(self, *a, **k):
+        raise NotImplementedError()
+
+    def Lambda_noise(self, *a, **k):
+        raise NotImplementedError()
+
+
+class SRConv(_NoLambda, _Separable):
     def __init__(self, kernel, channels, R, stride):
         self.C, self.R, self.ratio = channels, R, stride
         m = self.m = R // stride
@@ -262,8 +350,17 @@ class Deblurring(_Separable):
                 if 0 <= j < R:
                     A_small[i, j] = kernel[j - i + half]
         self.Us, s, self.Vs = torch.svd(A_small, some=False)
+        s_orig = s.clone()
         s[s < zero] = 0
         self.s_sorted, self.perm = torch.outer(s, s).reshape(R * R).sort(descending=True)
+        self.s_orig_sorted = torch.outer(s_orig, s_orig).reshape(R * R)[self.perm]  # un-thresholded (:957-966)
+
+    def lambda_singulars(self):  # Lambda pairs position q with the un-thresholded value, for all channels (:1021,1033)
+        return self.s_orig_sorted.repeat_interleave(self.C)
+
+    def reorder(self, x):  # :1045-1049
+        b = x.shape[0]
+        return x.reshape(b, self.C, -1)[:, :, self.perm].transpose(1, 2).reshape(b, -1)
 
     def _to_spec(self, M, x):
         b, R = x.shape[0], self.R
@@ -295,7 +392,7 @@ class Deblurring(_Separable):
         return v.reshape(v.shape[0], -1)
 
 
-class Deblurring2D(_Separable):
+class Deblurring2D(_NoLambda, _Separable):
     """Anisotropic blur (functions/svd_operators.py:1094-1165): kernel1 acts on the rows (left matrices U1, V1), kernel2 on
     the columns (right matrices U2, V2); singular values s1 (x) s2 sorted descending, pairing as in Deblurring."""
 
@@ -345,6 +442,33 @@ class Deblurring2D(_Separable):
 
     def add_zeros(self, v):
         return v.reshape(v.shape[0], -1)
+
+
+class Denoising(SpectralOp):
+    """A = I (functions/svd_operators.py:442-476): all singular values are 1, so Lambda / Lambda_noise are scalars."""
+
+    def __init__(self, channels, R):
+        self.C, self.R = channels, R
+
+    def Vt(self, x):
+        return x.reshape(x.shape[0], -1).clone()
+
+    V = U = Ut = add_zeros = Vt
+
+    def singulars(self):
+        return torch.ones(self.C * self.R * self.R)
+
+    def Lambda(self, v, a, sigma_y, sigma_t, eta):  # :464-469 (no a / sigma_y zero guard there)
+        a, st = torch.as_tensor(a, dtype=torch.float32), torch.as_tensor(sigma_t, dtype=torch.float32)
+        if st < a * sigma_y:
+            return v * (st * (1 - eta ** 2) ** 0.5 / a / sigma_y).item()
+        return v
+
+    def Lambda_noise(self, v, a, sigma_y, sigma_t, eta, eps):  # :471-476
+        a, st = torch.as_tensor(a, dtype=torch.float32), torch.as_tensor(sigma_t, dtype=torch.float32)
+        if st >= a * sigma_y:
+            return v * torch.sqrt(st ** 2 - a ** 2 * sigma_y ** 2).item()
+        return v * st * eta
 
 
 def aniso_kernels():

@@ -389,6 +389,105 @@ def edm():
     torch.save(gold, os.path.join(HERE, "edm_sampler_tiny.pt"))
 
 
+DDNM_REGIMES = [(0.9, 0.1, 0.05, 0.85), (0.9, 0.1, 0.3, 0.85), (0.9, 0.1, 0.6, 0.5), (0.9, 0.0, 0.3, 0.85),
+                (0.3, 0.5, 0.12, 0.0)]  # (a, sigma_y, sigma_t, eta): both sides of sigma_t <> a sigma_y / s, and sigma_y = 0
+DDNM_LOOPS = [("colorization", 0.1), ("sr_averagepooling", 0.2), ("inpainting", 0.05), ("cs_walshhadamard", 0.1),
+              ("deblur_gauss", 0.05), ("denoising", 0.3), ("sr_averagepooling", None), ("deblur_gauss", None)]
+
+
+def _ddnm_ops(ref, Rr, C, missing, perm):
+    return {"inpainting": ref.Inpainting(C, Rr, missing, "cpu"), "colorization": ref.Colorization(Rr, "cpu"),
+            "sr_averagepooling": ref.SuperResolution(C, Rr, 4, "cpu"),
+            "cs_walshhadamard": ref.WalshHadamardCS(C, Rr, 4, perm, "cpu"),
+            "deblur_gauss": ref.Deblurring(O.gauss_kernel(), C, Rr, "cpu"), "denoising": ref.Denoising(C, Rr, "cpu")}
+
+
+def ddnm():
+    """DDNM+ on the unmodified reference: Lambda / Lambda_noise / A_pinv_eta of every operator
+    class that defines them (functions/svd_operators.py) in five (a, sigma_y, sigma_t, eta) regimes -> ddnm_ops_r32.pt, and
+    per-step dumps of functions/svd_ddnm.py ddnm_diffusion / ddnm_plus_diffusion (adm_tiny network, 4 sampling steps with
+    one time-travel detour) -> ddnm_loops_r32.pt.  The loops hard-code `.to('cuda')`; the only change made here is to redirect
+    those moves to the CPU while the loop runs."""
+    import importlib
+    import types
+    R = refimport.load()
+    ref = R.svd_operators
+    sys.modules.setdefault("torchvision", types.ModuleType("torchvision"))
+    if not hasattr(sys.modules["torchvision"], "utils"):
+        sys.modules["torchvision"].utils = types.ModuleType("torchvision.utils")
+        sys.modules["torchvision.utils"] = sys.modules["torchvision"].utils
+    SD = importlib.import_module("functions.svd_ddnm")
+    torch.set_num_threads(4)
+    Rr, C, Bo = 32, 3, 2
+    g = torch.Generator().manual_seed(41)
+    v = torch.randn(Bo, C * Rr * Rr, generator=g)
+    e = torch.randn(Bo, C * Rr * Rr, generator=g)
+    mask = torch.ones(Rr, Rr)
+    mask[8:24, 8:24] = 0
+    mr = torch.nonzero(mask.reshape(-1) == 0).long().reshape(-1) * 3
+    missing = torch.cat([mr, mr + 1, mr + 2])
+    perm = torch.randperm(Rr * Rr, generator=torch.Generator().manual_seed(3))
+    ops = _ddnm_ops(ref, Rr, C, missing, perm)
+    gold = dict(v=v, e=e, missing=missing, perm=perm, regimes=DDNM_REGIMES)
+    for name, op in ops.items():
+        rec = dict(Lambda=[], Lambda_noise=[])
+        for a, sy, st, eta in DDNM_REGIMES:
+            a_t, st_t = torch.tensor(a), torch.tensor(st)  # 0-dim fp32, as functions/svd_ddnm.py:121-132 passes them
+            rec["Lambda"].append(op.Lambda(v.clone(), a_t, sy, st_t, eta))
+            rec["Lambda_noise"].append(op.Lambda_noise(v.clone(), a_t, sy, st_t, eta, e.clone()))
+        if name != "denoising":
+            yy = op.A(v.clone())
+            rec["y"] = yy
+            rec["A_pinv_eta"] = [op.A_pinv_eta(yy.clone(), 0.01), op.A_pinv_eta(yy.clone(), 0.5)]
+        gold[name] = rec
+    torch.save(gold, os.path.join(HERE, "ddnm_ops_r32.pt"))
+
+    # ---- loops
+    cfg, sg, sd, ssd, net, snet = adm_reference_modules("adm_tiny")
+    betas = torch.linspace(1e-4, 2e-2, 1000)  # the DDNM configs' linear schedule
+    config = types.SimpleNamespace(diffusion=types.SimpleNamespace(num_diffusion_timesteps=1000),
+                                   time_travel=types.SimpleNamespace(T_sampling=4, travel_length=2, travel_repeat=2))
+    loops = dict(betas=betas, T_sampling=4, travel_length=2, travel_repeat=2, eta=0.85, missing=missing, perm=perm)
+    orig_to, orig_randn_like = torch.Tensor.to, torch.randn_like
+
+    def to_cpu(self, *a, **k):
+        a = tuple("cpu" if (isinstance(x, str) and x.startswith("cuda")) else x for x in a)
+        return orig_to(self, *a, **k)
+
+    for name, sigma_y in DDNM_LOOPS:
+        op = ops[name]
+        gg = torch.Generator().manual_seed(51)
+        x_true = torch.rand(Bo, C, Rr, Rr, generator=gg) * 2 - 1
+        y = op.A(x_true.reshape(Bo, -1).clone())
+        if sigma_y:
+            y = y + sigma_y * torch.randn(y.shape, generator=gg)
+        xT = torch.randn(Bo, C, Rr, Rr, generator=gg)
+        rec = dict(xt=[], t=[], et=[], z=[])
+
+        def model(x, t, _rec=rec):
+            out = net(x, t)
+            _rec["xt"].append(x.clone()), _rec["t"].append(t.clone()), _rec["et"].append(out[:, :3].clone())
+            return out
+
+        def randn_like(x, _rec=rec, _g=gg):
+            z = torch.randn(x.shape, generator=_g)
+            _rec["z"].append(z.clone())
+            return z
+
+        torch.Tensor.to, torch.randn_like = to_cpu, randn_like
+        try:
+            if sigma_y is None:
+                xs, x0s = SD.ddnm_diffusion(xT.clone(), model, betas, 0.85, op, y, config=config)
+            else:
+                xs, x0s = SD.ddnm_plus_diffusion(xT.clone(), model, betas, 0.85, op, y, sigma_y, config=config)
+        finally:
+            torch.Tensor.to, torch.randn_like = orig_to, orig_randn_like
+        loops["%s|%s" % (name, sigma_y)] = dict(x_true=x_true, y=y, xT=xT, x_last=xs[0], x0_last=x0s[0], **rec)
+    torch.save(loops, os.path.join(HERE, "ddnm_loops_r32.pt"))
+    for f in ("ddnm_ops_r32.pt", "ddnm_loops_r32.pt"):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()[sys.argv[1]]()

@@ -144,6 +144,17 @@ def test_operators(R):
         assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
         pr = x0 - a.A_pinv(a.A(x0.reshape(B, -1)) - y).reshape(x0.shape)
         assert torch.equal(pr, b.project(x0, y))
+        assert torch.equal(a.A_pinv_eta(y.clone(), 0.05), b.A_pinv_eta(y.clone(), 0.05))
+        if not hasattr(a, "_singulars_orig") and type(a).__name__ in ("SRConv", "Deblurring2D"):
+            continue  # no Lambda in the reference
+        # DDNM+ terms on random regimes: 0-dim fp32 a / sigma_t as functions/svd_ddnm.py passes them
+        v, e = torch.randn(B, C * Rr * Rr), torch.randn(B, C * Rr * Rr)
+        for _ in range(4):
+            a_t, st_t = torch.rand(()) * 0.9 + 0.1, torch.rand(()) * 0.9 + 0.05
+            sy, eta = float(torch.rand(())) * 0.5, float(torch.rand(()))
+            assert torch.equal(a.Lambda(v.clone(), a_t, sy, st_t, eta), b.Lambda(v.clone(), a_t, sy, st_t, eta))
+            assert torch.equal(a.Lambda_noise(v.clone(), a_t, sy, st_t, eta, e.clone()),
+                               b.Lambda_noise(v.clone(), a_t, sy, st_t, eta, e.clone()))
 
 
 @pytest.mark.parametrize("name", ["adm_tiny", "adm_alt"])
