@@ -50,8 +50,13 @@ class OpDesc(C.Structure):
         ("idx_host", C.c_void_p), ("n_idx", C.c_int64),
         ("U_small_host", C.c_void_p), ("V_small_host", C.c_void_p), ("sing_small_host", C.c_void_p),
         ("m_small", C.c_int), ("mult_host", C.c_void_p), ("pinv_mult_host", C.c_void_p),
-        ("U_small2_host", C.c_void_p), ("V_small2_host", C.c_void_p),
+        ("U_small2_host", C.c_void_p), ("V_small2_host", C.c_void_p), ("lambda_sing_host", C.c_void_p),
     ]
+
+
+class DdnmCoef(C.Structure):
+    """nlc_ddnm_coef (include/nlc_b200.h)."""
+    _fields_ = [("a", C.c_float), ("sigma_t", C.c_float), ("sigma_y", C.c_double), ("eta", C.c_double)]
 
 
 _lib = None
@@ -100,6 +105,11 @@ _SIGNATURES = {
     "nlc_op_At": (_I, [_P, _P, _I, _P, _P, _P]),
     "nlc_op_Apinv": (_I, [_P, _P, _I, _P, _P, _P]),
     "nlc_op_project": (_I, [_P, _P, _P, _I, _P, _P, _P]),
+    "nlc_op_Apinv_eta": (_I, [_P, _P, _I, C.c_double, _P, _P, _P]),
+    "nlc_op_lambda": (_I, [_P, _P, _I, C.POINTER(DdnmCoef), _P, _P, _P]),
+    "nlc_op_lambda_noise": (_I, [_P, _P, _P, _I, C.POINTER(DdnmCoef), _P, _P, _P]),
+    "nlc_ddnm_step": (_I, [_P, _P, _P, _I64, _P, _P, _I, _F, _F, C.c_double, C.c_double, _I, _P, _P, _P, _P]),
+    "nlc_ddnm_renoise": (_I, [_P, _P, _P, _I64, _F, _P, _P]),
     "nlc_l1_diff_rows": (_I, [_P, _P, _P, _I, _I64, _P, _P]),
 }
 

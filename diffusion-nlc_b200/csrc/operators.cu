@@ -16,27 +16,14 @@
 
 #include <vector>
 
-#include "common.h"
+#include "operators.h"
 #include "ptx.cuh"
-
-struct nlc_op {
-    nlc_ctx* ctx;
-    int task, C, R, ratio, m;
-    int64_t ydim;
-    int* idx_a;   // INPAINT: kept[k] = pixel*3+c ; WHCS: invperm[q]
-    int* idx_b;   // INPAINT: pos2k[pixel*3+c] (-1 = missing)
-    int n_kept;
-    float u, s;
-    float* v0;    // COLOR: 3 ; SR_AVG: r*r
-    float *Us, *Vs, *mult, *pinv;  // SEPARABLE (left factors; also right factors unless Us2 / Vs2 are set)
-    float *Us2, *Vs2;              // SEPARABLE: right factors (== Us / Vs for one-kernel operators)
-    bool own2;
-};
 
 namespace nlc {
 
 // ---------------------------------------------------------------- colourisation / avg-pool SR
-// mode 0: A, 1: At, 2: A_pinv, 3: project.  One thread per (sample, low-res pixel); P = patch edge (1 for colour).
+// mode 0: A, 1: At, 2: A_pinv, 3: project, 4: A_pinv_eta (s := s / (s^2 + eta), functions/svd_operators.py:82-91).
+// One thread per (sample, low-res pixel); P = patch edge (1 for colour).
 template <int MODE>
 __global__ void __launch_bounds__(256) needle_kernel(const float* __restrict__ x, const float* __restrict__ y,
                                                       float* __restrict__ out, int B, int C, int R, int r, int per_ch,
@@ -74,6 +61,7 @@ __global__ void __launch_bounds__(256) needle_kernel(const float* __restrict__ x
     float t;
     if (MODE == 1) t = s * (u * y[i]);                       // V(add_zeros(singulars * Ut(y)))
     else if (MODE == 2) t = (u * y[i]) * (1.0f / s);         // V(add_zeros(Ut(y) * 1/singulars))
+    else if (MODE == 4) t = (u * y[i]) * s;                  // the caller passes s / (s^2 + eta)
     else t = (u * (meas - y[i])) * (1.0f / s);               // A^+(A x0 - y)
     for (int k = 0; k < K; ++k) {
         const float v = v0[k] * t;
@@ -93,7 +81,7 @@ __global__ void inpaint_A_kernel(const float* __restrict__ x, float* __restrict_
 // mode 1/2: scatter (At == A^+, all singulars are 1); mode 3: project
 template <int MODE>
 __global__ void inpaint_back_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
-                                    int B, int C, int HW, const int* __restrict__ pos2k, int n_kept) {
+                                    int B, int C, int HW, const int* __restrict__ pos2k, int n_kept, float f) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * C * HW) return;
     const int p = static_cast<int>(i % HW);
@@ -104,7 +92,7 @@ __global__ void inpaint_back_kernel(const float* __restrict__ x, const float* __
         const float xv = x[i];
         out[i] = k >= 0 ? xv - (xv - y[static_cast<size_t>(b) * n_kept + k]) : xv;
     } else {
-        out[i] = k >= 0 ? y[static_cast<size_t>(b) * n_kept + k] : 0.f;
+        out[i] = k >= 0 ? __fmul_rn(y[static_cast<size_t>(b) * n_kept + k], f) : 0.f;  // f = 1 (At, A^+), 1/(1+eta)
     }
 }
 
@@ -127,9 +115,9 @@ __global__ void fwht_rows_kernel(const float* __restrict__ in, float* __restrict
     for (int i = threadIdx.x; i < R; i += blockDim.x) out[base + i] = row[i];
 }
 // columns: CTA = 32 columns x R rows of one plane; stages h = R .. R^2/2 of the flattened transform, then / R.
-// If base != nullptr writes base - value (the projection's final subtraction).
+// The epilogue (operators.h) folds the projection's final subtraction / the DDNM step's x_{t-1} assembly into the store.
 __global__ void __launch_bounds__(256) fwht_cols_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                         const float* __restrict__ base, int R) {
+                                                         const Epilogue e, int R, int C) {
     extern __shared__ float tile[];  // [R][32]
     const int plane = blockIdx.y, c0 = blockIdx.x * 32;
     const size_t pbase = static_cast<size_t>(plane) * R * R;
@@ -148,8 +136,15 @@ __global__ void __launch_bounds__(256) fwht_cols_kernel(const float* __restrict_
     const float fr = static_cast<float>(R);
     for (int r = ty; r < R; r += 8) {
         const size_t o = pbase + static_cast<size_t>(r) * R + c0 + tx;
-        const float v = tile[r * 32 + tx] / fr;
-        out[o] = base ? base[o] - v : v;
+        float v = tile[r * 32 + tx] / fr;
+        if (e.base) v = e.alpha * e.base[o] + e.beta * v;
+        if (e.add1) v += e.g1 * e.add1[o];
+        if (e.add2) {
+            const size_t o2 = e.add2_stride ? static_cast<size_t>(plane / C) * e.add2_stride +
+                                                  (static_cast<size_t>(plane % C) * R + r) * R + c0 + tx : o;
+            v += e.g2 * e.add2[o2];
+        }
+        out[o] = v;
     }
 }
 // y[b][j*C + c] = F[b][c][perm[j]], j < m  (gather through invperm: thread per spectral entry q)
@@ -165,7 +160,7 @@ __global__ void whcs_gather_kernel(const float* __restrict__ F, float* __restric
 }
 // temp[b][c][q] = j < m ? (F ? F[b][c][q] - y : y)[b][j*C+c] : 0
 __global__ void whcs_scatter_kernel(const float* __restrict__ F, const float* __restrict__ y, float* __restrict__ temp,
-                                    int B, int C, int N, int m, const int* __restrict__ invperm) {
+                                    int B, int C, int N, int m, const int* __restrict__ invperm, float f) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * C * N) return;
     const int q = static_cast<int>(i % N);
@@ -175,7 +170,7 @@ __global__ void whcs_scatter_kernel(const float* __restrict__ F, const float* __
     float v = 0.f;
     if (j < m) {
         const float yv = y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c];
-        v = F ? F[i] - yv : yv;
+        v = F ? F[i] - yv : __fmul_rn(yv, f);  // f = 1 (At, A^+) or 1 / (1 + eta)
     }
     temp[i] = v;
 }
@@ -184,7 +179,8 @@ __global__ void whcs_scatter_kernel(const float* __restrict__ F, const float* __
 // Cm[b][i][j] = epi( sum_k A[b*sab + i*sai + k*sak] * Bm[b*sbb + k*sbk + j*sbj] )
 // epi: * mult[(b % nch)*M*N + i*N + j] (if mult) ; - sub[b][i][j] (if sub) ; base[b][i][j] - value (if base)
 struct GemmArgs {
-    const float *A, *Bm, *mult, *sub, *base;
+    const float *A, *Bm, *mult, *sub, *base, *add;
+    float alpha, beta;
     float* Cm;
     long long sab, sai, sak, sbb, sbk, sbj;
     int M, N, K, nch;
@@ -237,7 +233,8 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const GemmArgs g) {
             float v = acc[r][c];
             if (g.mult) v *= g.mult[static_cast<size_t>(b % g.nch) * g.M * g.N + o];
             if (g.sub) v -= g.sub[cb + o];
-            if (g.base) v = g.base[cb + o] - v;
+            if (g.base) v = g.alpha * g.base[cb + o] + g.beta * v;  // projection: alpha 1, beta -1
+            if (g.add) v += g.add[cb + o];
             g.Cm[cb + o] = v;
         }
     }
@@ -287,12 +284,10 @@ __global__ void image_metrics_kernel(const float* __restrict__ x, const float* _
     }
 }
 
-static inline unsigned blocks_for(long long n, int bs = 256) { return static_cast<unsigned>((n + bs - 1) / bs); }
-
-static int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const float* A, long long sab, long long sai,
-                       long long sak, const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm,
-                       const float* mult, int nch, const float* sub, const float* base) {
-    GemmArgs g{A, Bm, mult, sub, base, Cm, sab, sai, sak, sbb, sbk, sbj, M, N, K, nch};
+int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const float* A, long long sab, long long sai,
+                long long sak, const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm, const float* mult,
+                int nch, const float* sub, const float* base, float alpha, float beta, const float* add) {
+    GemmArgs g{A, Bm, mult, sub, base, add, alpha, beta, Cm, sab, sai, sak, sbb, sbk, sbj, M, N, K, nch};
     dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
     sgemm_strided_kernel<<<grid, 256, 0, st>>>(g);
     NLC_CHECK_LAUNCH();
@@ -301,7 +296,7 @@ static int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const fl
 
 // separable forward:  out[b,c] = U_s ( mult_c o (V_s[:, :m]^T X V2_s[:, :m]) ) U2_s^T  (- sub);  U2 = U, V2 = V unless the
 // operator blurs rows and columns with different kernels
-static int separable_A(nlc_op* op, const float* x, int B, float* y, float* ws, const float* sub, cudaStream_t st) {
+int separable_A(nlc_op* op, const float* x, int B, float* y, float* ws, const float* sub, cudaStream_t st) {
     const int R = op->R, m = op->m, n = B * op->C;
     float* T1 = ws;                                        // [n][m][R]
     float* T2 = T1 + static_cast<size_t>(n) * m * R;       // [n][m][m]
@@ -345,14 +340,14 @@ static int to_device(T** dst, const T* src, size_t n) {
     return NLC_OK;
 }
 
-static int fwht2d(nlc_op* op, const float* in, float* out, const float* base, int B, cudaStream_t st) {
+int fwht2d(nlc_op* op, const float* in, float* out, const Epilogue& epi, int B, cudaStream_t st) {
     const int R = op->R, planes = B * op->C;
     fwht_rows_kernel<<<planes * R, R / 2 > 256 ? 256 : R / 2, R * sizeof(float), st>>>(in, out, R);
     NLC_CHECK_LAUNCH();
     const size_t smem = static_cast<size_t>(R) * 32 * sizeof(float);
     NLC_CHECK_CUDA(cudaFuncSetAttribute(fwht_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(smem)));
-    fwht_cols_kernel<<<dim3(R / 32, planes), 256, smem, st>>>(out, out, base, R);
+    fwht_cols_kernel<<<dim3(R / 32, planes), 256, smem, st>>>(out, out, epi, R, op->C);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -392,7 +387,9 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
             op->u = d->U_small_host[0], op->s = d->sing_small_host[0];
             std::vector<float> v0(K);
             for (int k = 0; k < K; ++k) v0[k] = d->V_small_host[k * K];  // first column of V_small
-            if ((rc = to_device(&op->v0, v0.data(), K))) return rc;
+            if ((rc = to_device(&op->v0, v0.data(), K)) ||
+                (rc = to_device(&op->Vfull, d->V_small_host, static_cast<size_t>(K) * K))) return rc;
+            op->K = K;
             op->ydim = d->task == NLC_OP_COLOR ? N : d->channels * (N / (d->ratio * d->ratio));
         } break;
         case NLC_OP_WHCS: {
@@ -418,8 +415,12 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
                     return rc;
                 op->own2 = true;
             }
+            if (d->lambda_sing_host && (rc = to_device(&op->lam_s, d->lambda_sing_host, mm))) return rc;
             op->ydim = static_cast<int64_t>(d->channels) * mm;
         } break;
+        case NLC_OP_DENOISE:
+            op->ydim = dim;
+            break;
         default:
             delete op;
             return set_error(NLC_EINVAL, "nlc_op_create: unknown task %d", d->task);
@@ -430,7 +431,7 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
 
 extern "C" void nlc_op_destroy(nlc_op* op) {
     if (!op) return;
-    cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->v0);
+    cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->v0), cudaFree(op->Vfull), cudaFree(op->lam_s);
     cudaFree(op->Us), cudaFree(op->Vs), cudaFree(op->mult), cudaFree(op->pinv);
     if (op->own2) cudaFree(op->Us2), cudaFree(op->Vs2);
     delete op;
@@ -442,12 +443,28 @@ extern "C" size_t nlc_op_ws(nlc_op* op, int B) {
     if (!op) return 0;
     const size_t plane = static_cast<size_t>(op->R) * op->R, n = static_cast<size_t>(B) * op->C;
     if (op->task == NLC_OP_WHCS) return 2 * n * plane * sizeof(float);
-    if (op->task == NLC_OP_SEPARABLE) return 4 * n * plane * sizeof(float);
+    // separable: T1..T3 + the residual A x0 - y, + one plane set of noise terms and the per-step tables of the DDNM step
+    if (op->task == NLC_OP_SEPARABLE) return (5 * n + 3 + op->C) * plane * sizeof(float);
     return 0;
 }
 
-// mode: 0 A, 1 At, 2 A_pinv, 3 project (in = x0, y = y, out = x0_hat)
-static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B, float* out, void* ws_, void* stream_) {
+// f / (f^2 + eta) per table entry (A_pinv_eta of the separable operators)
+__global__ void pinv_eta_table_kernel(const float* __restrict__ mult, float eta, long long n, float* __restrict__ out) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fdiv_rn(mult[i], __fadd_rn(__fmul_rn(mult[i], mult[i]), eta));
+}
+// Denoising (A = I): mode 0/1/2 copy (x f for A_pinv_eta), 3 project = x0 - (x0 - y)
+__global__ void identity_op_kernel(const float* __restrict__ in, const float* __restrict__ y, float* __restrict__ out,
+                                   long long n, int mode, float f) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = in[i];
+    out[i] = mode == 3 ? __fsub_rn(v, __fsub_rn(v, y[i])) : (mode == 4 ? __fmul_rn(v, f) : v);
+}
+
+// mode: 0 A, 1 At, 2 A_pinv, 3 project (in = x0, y = y, out = x0_hat), 4 A_pinv_eta
+static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B, float* out, void* ws_, void* stream_,
+                    double eta = 0.0) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(op && in && out && B >= 1, "nlc_op: null argument");
     float* ws = static_cast<float*>(ws_);
@@ -463,6 +480,9 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
             if (mode == 0) needle_kernel<0><<<g, 256, 0, st>>>(in, nullptr, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
             else if (mode == 1) needle_kernel<1><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
             else if (mode == 2) needle_kernel<2><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
+            else if (mode == 4)
+                needle_kernel<4><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u,
+                                                    op->s / (op->s * op->s + static_cast<float>(eta)), op->v0);
             else needle_kernel<3><<<g, 256, 0, st>>>(in, y, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
             NLC_CHECK_LAUNCH();
         } break;
@@ -473,10 +493,11 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
                         in, out, B, C, static_cast<int>(N), op->idx_a, op->n_kept);
             } else if (mode == 3) {
                 inpaint_back_kernel<3><<<blocks_for(B * C * N), 256, 0, st>>>(in, y, out, B, C, static_cast<int>(N),
-                                                                             op->idx_b, op->n_kept);
+                                                                             op->idx_b, op->n_kept, 1.f);
             } else {
+                const float f = mode == 4 ? 1.0f / (1.0f * 1.0f + static_cast<float>(eta)) : 1.f;
                 inpaint_back_kernel<1><<<blocks_for(B * C * N), 256, 0, st>>>(nullptr, in, out, B, C, static_cast<int>(N),
-                                                                             op->idx_b, op->n_kept);
+                                                                             op->idx_b, op->n_kept, f);
             }
             NLC_CHECK_LAUNCH();
         } break;
@@ -488,18 +509,21 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
             const unsigned g = blocks_for(B * C * N);
             int rc;
             if (mode == 0) {
-                if ((rc = fwht2d(op, in, F, nullptr, B, st))) return rc;
+                if ((rc = fwht2d(op, in, F, Epilogue(), B, st))) return rc;
                 whcs_gather_kernel<<<g, 256, 0, st>>>(F, out, B, C, static_cast<int>(N), m, op->idx_a);
                 NLC_CHECK_LAUNCH();
             } else if (mode == 3) {
-                if ((rc = fwht2d(op, in, F, nullptr, B, st))) return rc;
-                whcs_scatter_kernel<<<g, 256, 0, st>>>(F, y, T, B, C, static_cast<int>(N), m, op->idx_a);
+                if ((rc = fwht2d(op, in, F, Epilogue(), B, st))) return rc;
+                whcs_scatter_kernel<<<g, 256, 0, st>>>(F, y, T, B, C, static_cast<int>(N), m, op->idx_a, 1.f);
                 NLC_CHECK_LAUNCH();
-                if ((rc = fwht2d(op, T, out, in, B, st))) return rc;  // out = x0 - fwht(T)
+                Epilogue e;
+                e.base = in, e.alpha = 1.f, e.beta = -1.f;
+                if ((rc = fwht2d(op, T, out, e, B, st))) return rc;  // out = x0 - fwht(T)
             } else {
-                whcs_scatter_kernel<<<g, 256, 0, st>>>(nullptr, in, T, B, C, static_cast<int>(N), m, op->idx_a);
+                const float f = mode == 4 ? 1.0f / (1.0f * 1.0f + static_cast<float>(eta)) : 1.f;
+                whcs_scatter_kernel<<<g, 256, 0, st>>>(nullptr, in, T, B, C, static_cast<int>(N), m, op->idx_a, f);
                 NLC_CHECK_LAUNCH();
-                if ((rc = fwht2d(op, T, out, nullptr, B, st))) return rc;
+                if ((rc = fwht2d(op, T, out, Epilogue(), B, st))) return rc;
             }
         } break;
         case NLC_OP_SEPARABLE: {
@@ -507,11 +531,24 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
             if (mode == 0) return separable_A(op, in, B, out, ws, nullptr, st);
             if (mode == 1) return separable_back(op, in, B, out, ws, op->mult, nullptr, st);
             if (mode == 2) return separable_back(op, in, B, out, ws, op->pinv, nullptr, st);
+            if (mode == 4) {
+                float* tab = ws + 5 * static_cast<size_t>(B) * C * N;
+                const long long nt = static_cast<long long>(C) * op->m * op->m;
+                pinv_eta_table_kernel<<<blocks_for(nt), 256, 0, st>>>(op->mult, static_cast<float>(eta), nt, tab);
+                NLC_CHECK_LAUNCH();
+                return separable_back(op, in, B, out, ws, tab, nullptr, st);
+            }
             float* diff = ws + 3 * static_cast<size_t>(B) * C * N;  // A x0 - y
             int rc;
             if ((rc = separable_A(op, in, B, diff, ws, y, st))) return rc;
             return separable_back(op, diff, B, out, ws, op->pinv, in, st);
         }
+        case NLC_OP_DENOISE: {
+            NLC_REQUIRE(mode != 3 || y, "nlc_op: y is null");
+            identity_op_kernel<<<blocks_for(B * C * N), 256, 0, st>>>(in, y, out, B * C * N, mode,
+                                                                     1.0f / (1.0f * 1.0f + static_cast<float>(eta)));
+            NLC_CHECK_LAUNCH();
+        } break;
         default:
             return set_error(NLC_EINVAL, "nlc_op: unknown task");
     }
@@ -526,6 +563,9 @@ extern "C" int nlc_op_At(nlc_op* op, const float* y, int B, float* x, void* ws, 
 }
 extern "C" int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* ws, void* stream) {
     return op_apply(op, 2, y, nullptr, B, x, ws, stream);
+}
+extern "C" int nlc_op_Apinv_eta(nlc_op* op, const float* y, int B, double eta, float* x, void* ws, void* stream) {
+    return op_apply(op, 4, y, nullptr, B, x, ws, stream, eta);
 }
 extern "C" int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, void* ws, void* stream) {
     NLC_REQUIRE(y, "nlc_op_project: y is null");

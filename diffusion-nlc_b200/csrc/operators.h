@@ -1,0 +1,50 @@
+// Shared between operators.cu (A, A^T, A^+, projection) and ddnm.cu (DDNM+ terms and the fused DDNM reverse step):
+// the operator object and the transform / GEMM launchers both files build their pipelines from.
+#pragma once
+#include "common.h"
+
+struct nlc_op {
+    nlc_ctx* ctx;
+    int task, C, R, ratio, m;
+    int64_t ydim;
+    int* idx_a;   // INPAINT: kept[k] = pixel*3+c ; WHCS: invperm[q]
+    int* idx_b;   // INPAINT: pos2k[pixel*3+c] (-1 = missing)
+    int n_kept;
+    float u, s;
+    float* v0;    // COLOR: 3 ; SR_AVG: r*r
+    float* Vfull; // COLOR / SR_AVG: the whole K x K V_small, row-major (Lambda / Lambda_noise rotate with it)
+    int K;        // needle length: 3 (colour) or r*r
+    float *Us, *Vs, *mult, *pinv;  // SEPARABLE (left factors; also right factors unless Us2 / Vs2 are set)
+    float *Us2, *Vs2;              // SEPARABLE: right factors (== Us / Vs for one-kernel operators)
+    float* lam_s;                  // SEPARABLE: [m*m] singular value per spectral position for Lambda (nullptr: none)
+    bool own2;
+};
+
+namespace nlc {
+
+// out = alpha * base + beta * value + g1 * add1 + g2 * add2   (terms with a null pointer are absent; base == nullptr
+// leaves the plain transform)
+struct Epilogue {
+    const float* base = nullptr;
+    float alpha = 1.f, beta = 1.f;
+    const float* add1 = nullptr;
+    float g1 = 0.f;
+    const float* add2 = nullptr;
+    float g2 = 0.f;
+    long long add2_stride = 0;  // elements between the samples of add2 (0 = dense C*R*R): a [B,6,R,R] network output
+};
+
+// orthonormal 2-D fast Walsh-Hadamard transform of B*C planes (the reference's 1-D FWHT over R^2 entries)
+int fwht2d(nlc_op* op, const float* in, float* out, const Epilogue& epi, int B, cudaStream_t st);
+
+// Cm[b] = epi( A[b] * Bm[b] ): strided batched fp32 GEMM; epi = (* mult[(b % nch)]) (- sub) (alpha*base + beta*v) (+ add)
+int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const float* A, long long sab, long long sai,
+                long long sak, const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm, const float* mult,
+                int nch, const float* sub, const float* base, float alpha = 1.f, float beta = -1.f,
+                const float* add = nullptr);
+
+int separable_A(nlc_op* op, const float* x, int B, float* y, float* ws, const float* sub, cudaStream_t st);
+
+inline unsigned blocks_for(long long n, int bs = 256) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+}  // namespace nlc

@@ -6,8 +6,11 @@ x0 - A_pinv(A(x0) - y).  The small SVDs are taken on the CPU with the same torch
 (`torch.svd(..., some=False)`), then uploaded once; nothing else runs in torch.
 
 Covered: Inpainting (:324-359), Colorization (:627-667), SuperResolution (:479-533), WalshHadamardCS (:211-251),
-SRConv (:851-931), Deblurring (:934-1014).  The spectral-domain accessors `U/Ut/V/Vt/singulars/add_zeros` and the
-DDNM+ `Lambda*` family are not part of the sampling path.
+SRConv (:851-931), Deblurring (:934-1014), Deblurring2D (:1094-1165), Denoising (:442-476), and the DDNM+ family
+(SURVEY §8f rank 2): `A_pinv_eta` (:82-91), `Lambda` / `Lambda_noise` of every class that defines them (SRConv and
+Deblurring2D raise NotImplementedError as the reference's base class does, :93-97) and the fused reverse step
+`ddnm_step` used by svd_ddnm.py.  The spectral-domain accessors `U/Ut/V/Vt/singulars/add_zeros` are not exposed: the
+kernels work in closed form on the image.
 """
 import ctypes as C
 
@@ -16,7 +19,12 @@ import torch
 
 from . import _lib
 
-INPAINT, COLOR, SR_AVG, WHCS, SEPARABLE = 1, 2, 3, 4, 5
+INPAINT, COLOR, SR_AVG, WHCS, SEPARABLE, DENOISE = 1, 2, 3, 4, 5, 6
+
+
+def _f32(v):
+    """A scalar as the fp32 value the reference computes with (0-dim tensors at its call sites)."""
+    return float(torch.as_tensor(v, dtype=torch.float32))
 
 
 def _stream():
@@ -79,6 +87,60 @@ class A_functions:
                                            self._workspace(y.shape[0]), _stream()))
         return x
 
+    def A_pinv_eta(self, vec, eta):
+        """V diag(s / (s^2 + eta)) U^T (functions/svd_operators.py:82-91)."""
+        y = self._rows(vec, self.ydim)
+        x = torch.empty(y.shape[0], self.xdim, device=y.device)
+        _lib.check(_lib.lib().nlc_op_Apinv_eta(self._h, y.data_ptr(), y.shape[0], float(eta), x.data_ptr(),
+                                               self._workspace(y.shape[0]), _stream()))
+        return x
+
+    _has_lambda = True
+
+    def _coef(self, a, sigma_y, sigma_t, eta):
+        if not self._has_lambda:
+            raise NotImplementedError()  # as the reference's base class (functions/svd_operators.py:93-97)
+        return _lib.DdnmCoef(a=_f32(a), sigma_t=_f32(sigma_t), sigma_y=float(sigma_y), eta=float(eta))
+
+    def Lambda(self, vec, a, sigma_y, sigma_t, eta):
+        """V (lambda o V^T vec), Eq. 17 of DDNM+ (e.g. functions/svd_operators.py:535-570)."""
+        c = self._coef(a, sigma_y, sigma_t, eta)
+        v = self._rows(vec, self.xdim)
+        out = torch.empty_like(v)
+        _lib.check(_lib.lib().nlc_op_lambda(self._h, v.data_ptr(), v.shape[0], C.byref(c), out.data_ptr(),
+                                            self._workspace(v.shape[0]), _stream()))
+        return out
+
+    def Lambda_noise(self, vec, a, sigma_y, sigma_t, eta, epsilon):
+        """V (d1 o P vec) + V (d2 o P epsilon), Eq. 51 (e.g. :572-623)."""
+        c = self._coef(a, sigma_y, sigma_t, eta)
+        v = self._rows(vec, self.xdim)
+        e = self._rows(epsilon, self.xdim)
+        out = torch.empty_like(v)
+        _lib.check(_lib.lib().nlc_op_lambda_noise(self._h, v.data_ptr(), e.data_ptr(), v.shape[0], C.byref(c),
+                                                  out.data_ptr(), self._workspace(v.shape[0]), _stream()))
+        return out
+
+    def ddnm_step(self, xt, et, z, y, at, at_next, eta, sigma_y=None):
+        """One fused reverse step of functions/svd_ddnm.py (:40-66 when sigma_y is None, :101-132 otherwise):
+        returns (x0_t, x_next).  `et` may be the [B, 2C, R, R] output of a learned-variance head: its first C
+        channels are read in place."""
+        if sigma_y is not None and not self._has_lambda:
+            raise NotImplementedError()
+        B = xt.shape[0]
+        x = self._rows(xt, self.xdim)
+        zz = self._rows(z, self.xdim)
+        yy = self._rows(y, self.ydim)
+        e = et.reshape(B, -1).contiguous().float()
+        assert e.shape[1] >= self.xdim
+        x0 = torch.empty_like(x)
+        xn = torch.empty_like(x)
+        _lib.check(_lib.lib().nlc_ddnm_step(self._h, x.data_ptr(), e.data_ptr(), e.shape[1], zz.data_ptr(), yy.data_ptr(),
+                                            B, _f32(at), _f32(at_next), float(eta),
+                                            0.0 if sigma_y is None else float(sigma_y), 0 if sigma_y is None else 1,
+                                            x0.data_ptr(), xn.data_ptr(), self._workspace(B), _stream()))
+        return x0.view(xt.shape), xn.view(xt.shape)
+
     def project(self, x0, y, out=None):
         """x0 - A_pinv(A(x0) - y) in one fused pass; keeps x0's shape."""
         x = self._rows(x0, self.xdim)
@@ -100,6 +162,15 @@ class Inpainting(A_functions):
         miss = missing_indices.detach().cpu().to(torch.int64).contiguous()
         d = _lib.OpDesc(task=INPAINT, channels=channels, R=img_dim, ratio=1, idx_host=_fptr(miss), n_idx=miss.numel())
         super().__init__(d, (miss,), device)
+
+
+class Denoising(A_functions):
+    """A = I (functions/svd_operators.py:442-476)."""
+
+    def __init__(self, channels, img_dim, device):
+        self.channels, self.img_dim = channels, img_dim
+        self.xdim = channels * img_dim ** 2
+        super().__init__(_lib.OpDesc(task=DENOISE, channels=channels, R=img_dim, ratio=1), (), device)
 
 
 class Colorization(A_functions):
@@ -136,12 +207,17 @@ class WalshHadamardCS(A_functions):
         super().__init__(d, (p,), device)
 
 
-def _separable(self, U_s, V_s, mult, pinv, channels, img_dim, m, device, U2_s=None, V2_s=None):
+def _separable(self, U_s, V_s, mult, pinv, channels, img_dim, m, device, U2_s=None, V2_s=None, lambda_sing=None):
     U_s, V_s = U_s.contiguous().float(), V_s.contiguous().float()
     mult, pinv = mult.contiguous().float(), pinv.contiguous().float()
     d = _lib.OpDesc(task=SEPARABLE, channels=channels, R=img_dim, ratio=1, U_small_host=_fptr(U_s),
                     V_small_host=_fptr(V_s), m_small=m, mult_host=_fptr(mult), pinv_mult_host=_fptr(pinv))
     keep = [U_s, V_s, mult, pinv]
+    self._has_lambda = lambda_sing is not None
+    if lambda_sing is not None:  # singular value per spectral position for Lambda / Lambda_noise
+        lambda_sing = lambda_sing.contiguous().float()
+        d.lambda_sing_host = _fptr(lambda_sing)
+        keep.append(lambda_sing)
     if U2_s is not None:  # different right-hand factors (Deblurring2D)
         U2_s, V2_s = U2_s.contiguous().float(), V2_s.contiguous().float()
         d.U_small2_host, d.V_small2_host = _fptr(U2_s), _fptr(V2_s)
@@ -199,6 +275,7 @@ class Deblurring(A_functions):
                 if 0 <= j < R:
                     A_small[i, j] = kernel[j - i + half]
         U_s, s, V_s = torch.svd(A_small, some=False)
+        s_orig = s.clone()
         s = s.clone()
         s[s < ZERO] = 0
         big = torch.matmul(s.reshape(R, 1), s.reshape(1, R)).reshape(R * R)
@@ -208,7 +285,10 @@ class Deblurring(A_functions):
         mult[:, perm] = full.reshape(R * R, channels).t()
         pinv = torch.empty(channels, R * R)
         pinv[:, perm] = _zero_guarded_inverse(full).reshape(R * R, channels).t()
-        _separable(self, U_s, V_s, mult, pinv, channels, R, R, device)
+        # Lambda pairs spectral position q with the un-thresholded product at perm[q], the same for every channel
+        # (:957-966, 1021-1033): in image-spectral order that is simply outer(s_orig, s_orig)
+        lam_s = torch.matmul(s_orig.reshape(R, 1), s_orig.reshape(1, R)).reshape(R * R)
+        _separable(self, U_s, V_s, mult, pinv, channels, R, R, device, lambda_sing=lam_s)
 
 
 class Deblurring2D(A_functions):

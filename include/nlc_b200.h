@@ -295,6 +295,7 @@ int nlc_edm_axpy(nlc_ctx* ctx, const double* x_hat, const double* e, const doubl
 #define NLC_OP_SR_AVG 3    /* SuperResolution     :479-533                              */
 #define NLC_OP_WHCS 4      /* WalshHadamardCS     :211-251                              */
 #define NLC_OP_SEPARABLE 5 /* SRConv :851-931 and Deblurring :934-1014 (Kronecker SVD)  */
+#define NLC_OP_DENOISE 6   /* Denoising           :442-476 (A = I)                      */
 
 typedef struct nlc_op nlc_op;
 
@@ -316,6 +317,9 @@ typedef struct {
     const float* U_small2_host;   /* SEPARABLE, optional: right-hand factors when rows and columns are blurred   */
     const float* V_small2_host;   /* by different kernels (Deblurring2D, functions/svd_operators.py:1094-1165):  */
                                   /* A x = U (mult o (V^T X V2)) U2^T; NULL = same as U_small / V_small          */
+    const float* lambda_sing_host; /* SEPARABLE, optional: [m*m] singular value per spectral position (row-major) that  */
+                                  /* Lambda / Lambda_noise use (Deblurring: the un-thresholded products, :957-966,     */
+                                  /* 1021); NULL = the class has no Lambda (SRConv, Deblurring2D)                       */
 } nlc_op_desc;
 
 int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out);
@@ -327,6 +331,40 @@ int nlc_op_At(nlc_op* op, const float* y, int B, float* x, void* workspace, void
 int nlc_op_Apinv(nlc_op* op, const float* y, int B, float* x, void* workspace, void* stream);
 /* x0_hat = x0 - A^+(A x0 - y), fused (image_sample.py:376-379) */
 int nlc_op_project(nlc_op* op, const float* x0, const float* y, int B, float* x0_hat, void* workspace, void* stream);
+/* V diag(s / (s^2 + eta)) U^T y: the regularised pseudo-inverse A_functions.A_pinv_eta (functions/svd_operators.py:82-91) */
+int nlc_op_Apinv_eta(nlc_op* op, const float* y, int B, double eta, float* x, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SURVEY section 8(f) rank 2 — DDNM+ (noisy measurements): the operators' Lambda / Lambda_noise
+ * (functions/svd_operators.py:253-320, 361-439, 464-476, 535-623, 669-736, 1016-1091) and one fused reverse step of
+ * functions/svd_ddnm.py ddnm_diffusion (:40-66) / ddnm_plus_diffusion (:101-132).
+ *   Lambda(v)          = V (lambda o V^T v)                       Eq. 17
+ *   Lambda_noise(v, e) = V (d1 o P v) + V (d2 o P e)              Eq. 51 (P: the re-ordering half of V^T)
+ * lambda, d1, d2 are per spectral component functions of its singular value and of the four scalars below; `a` and
+ * `sigma_t` are fp32 at the reference's call site (0-dim tensors, functions/svd_ddnm.py:121-132), sigma_y and eta Python
+ * floats.  Operators without a Lambda in the reference (SRConv, Deblurring2D) return NLC_EINVAL.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    float a;        /* sqrt(alpha_bar_{t-1}) */
+    float sigma_t;  /* sqrt(1 - alpha_bar_{t-1}) */
+    double sigma_y; /* std of the measurement noise */
+    double eta;
+} nlc_ddnm_coef;
+int nlc_op_lambda(nlc_op* op, const float* v, int B, const nlc_ddnm_coef* c, float* out, void* workspace, void* stream);
+int nlc_op_lambda_noise(nlc_op* op, const float* v, const float* eps, int B, const nlc_ddnm_coef* c, float* out,
+                        void* workspace, void* stream);
+/* One reverse step, fused:  x0_t = (xt - et sqrt(1 - at)) / sqrt(at);
+ *   plus = 0:  x_next = sqrt(at_next) (x0_t - A^+(A x0_t - y)) + c1 z + c2 et        (:52-62)
+ *   plus = 1:  x_next = sqrt(at_next) (x0_t - Lambda A^+(A x0_t - y)) + Lambda_noise(z, et)   (:118-132)
+ * xt, z, x0_t, x_next are [B, C*R*R]; et is the network output, sample b at et + b * et_stride (its first C channels are
+ * used: et_stride = 2*C*R*R for a learned-variance head); at / at_next are compute_alpha's fp32 values (:10-13). */
+int nlc_ddnm_step(nlc_op* op, const float* xt, const float* et, int64_t et_stride, const float* z, const float* y, int B,
+                  float at, float at_next, double eta, double sigma_y, int plus, float* x0_t, float* x_next,
+                  void* workspace, void* stream);
+/* Time-travel step (:67-73, 133-139): x_next = sqrt(at_next) x0_t + z sqrt(1 - at_next) */
+int nlc_ddnm_renoise(nlc_ctx* ctx, const float* x0_t, const float* z, int64_t n, float at_next, float* x_next,
+                     void* stream);
+
 /* out[b] = sum_i |a[b,i] - b[b,i]|: the L1 constraint residuals of Constraint_Function.loss (image_sample.py:325-333) */
 int nlc_l1_diff_rows(nlc_ctx* ctx, const float* a, const float* b, int B, int64_t n, float* out, void* stream);
 
