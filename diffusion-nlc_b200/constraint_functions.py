@@ -89,8 +89,10 @@ def svd_constraint(fn, fn_scale=4, device="cuda", base_mask_dir="store/inp_masks
     if fn == "deblur_aniso":  # src/constraint_functions.py:280-292: 9 taps, sigma 1 along rows, sigma 20 along columns
         k1, k2 = _gauss_kernel(9, 1), _gauss_kernel(9, 20)
         return ops_svd.Deblurring2D(k1, k2, channels, image_size, device)
-    if fn in ("cs_blockbased", "denoising"):
-        raise NotImplementedError("%s (block CS / Denoising) is outside this build's scope (SURVEY §8f)" % fn)
+    if fn == "cs_blockbased":  # src/constraint_functions.py:212-215
+        return ops_svd.CS(channels, image_size, fn_scale, device)
+    if fn == "denoising":  # :242-244
+        return ops_svd.Denoising(channels, image_size, device)
     return None
 
 

@@ -304,6 +304,16 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ z,
     const long long b = i / per_sample;
     out[i] = __fadd_rn(__fmul_rn(g1, z[i]), __fmul_rn(g2, e[static_cast<size_t>(b) * e_stride + (i - b * per_sample)]));
 }
+// x <- a x + c1 z + c2 e in place (x holds x0_hat)
+__global__ void __launch_bounds__(256) assemble_kernel(float* __restrict__ x, const float* __restrict__ z,
+                                                        const float* __restrict__ e, long long e_stride,
+                                                        long long per_sample, int B, float a, float c1, float c2) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= per_sample * B) return;
+    const long long b = i / per_sample;
+    x[i] = __fadd_rn(__fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(c1, z[i])),
+                     __fmul_rn(c2, e[static_cast<size_t>(b) * e_stride + (i - b * per_sample)]));
+}
 __global__ void __launch_bounds__(256) renoise_kernel(const float* __restrict__ x0, const float* __restrict__ z,
                                                        long long n, float a, float sig, float* __restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -326,7 +336,8 @@ static int launch_needle(nlc_op* op, int mode, const float* in1, const float* in
 static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, long long s2, const float* z,
                       const float* y, float* out1, float* out0, int B, const Step& sc, float* ws, cudaStream_t st) {
     const int C = op->C, R = op->R;
-    const long long plane = static_cast<long long>(R) * R, per_sample = C * plane, total = per_sample * B;
+    const long long plane = static_cast<long long>(R) * R;
+    const long long per_sample = op->task == NLC_OP_GENERAL ? op->nx : C * plane, total = per_sample * B;
     if (s2 == 0) s2 = per_sample;
     int rc;
     switch (op->task) {
@@ -438,6 +449,17 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
             return launch_gemm(st, n, R, R, m, W2, static_cast<long long>(R) * m, m, 1, op->Vs2, 0, 1, R, out1, nullptr, 1,
                                nullptr, out0, sc.a, -sc.a, ADD);
         }
+        case NLC_OP_BLOCKCS:
+        case NLC_OP_GENERAL: {  // no closed form kept for these: x0, the library projection, then the x_next assembly
+            NLC_REQUIRE(mode == M_STEP && !sc.plus,
+                        "DDNM+: this operator class defines no Lambda / Lambda_noise in the reference (CS, GeneralA)");
+            x0_kernel<<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            NLC_CHECK_LAUNCH();
+            if ((rc = nlc_op_project(op, out0, y, B, out1, ws, st))) return rc;
+            assemble_kernel<<<blocks_for(total), 256, 0, st>>>(out1, z, in2, s2, per_sample, B, sc.a, sc.c1, sc.c2);
+            NLC_CHECK_LAUNCH();
+            return NLC_OK;
+        }
         default:
             return set_error(NLC_EINVAL, "DDNM+: unknown task");
     }
@@ -482,7 +504,7 @@ extern "C" int nlc_ddnm_step(nlc_op* op, const float* xt, const float* et, int64
                              float* x_next, void* ws, void* stream) {
     NLC_REQUIRE(op && xt && et && z && y && x0_t && x_next && B >= 1, "nlc_ddnm_step: null argument");
     NLC_REQUIRE(at > 0.f && at <= 1.f && at_next > 0.f && at_next <= 1.f, "nlc_ddnm_step: alpha_bar out of (0, 1]");
-    const long long dim = static_cast<long long>(op->C) * op->R * op->R;
+    const long long dim = op->task == NLC_OP_GENERAL ? op->nx : static_cast<long long>(op->C) * op->R * op->R;
     NLC_REQUIRE(et_stride == 0 || et_stride >= dim, "nlc_ddnm_step: et_stride shorter than one image");
     return ddnm_apply(op, M_STEP, xt, et, et_stride, z, y, x_next, x0_t, B, make_step(at, at_next, eta, sigma_y, plus),
                       static_cast<float*>(ws), static_cast<cudaStream_t>(stream));

@@ -11,6 +11,10 @@
 //                           reference's 1-D FWHT over R^2 entries) + a permutation gather
 //   SRConv (:851-931), Deblurring (:934-1014)  separable:  U_s (M o (V_s^T X V_s)) U_s^T  with a spectral
 //                           multiplier table M built by the host from the reference's own perm / singulars
+//   CS (:101-160)           block-wise compressed sensing: every 32 x 32 patch times the first cs columns of a 1024 x 1024
+//                           orthogonal V_small: patchify -> one [patches, 1024] x [1024, cs] fp32 GEMM (-> unpatchify)
+//   GeneralA (:173-208)     dense U, s, V of an arbitrary small A: two fp32 GEMMs around a per-column scale
+//   Denoising (:442-476)    A = I
 // All kernels are HBM-bound fp32 (the separable pair adds eight small fp32 GEMMs per image-channel).
 #include <string.h>
 
@@ -421,6 +425,24 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
         case NLC_OP_DENOISE:
             op->ydim = dim;
             break;
+        case NLC_OP_BLOCKCS: {
+            const int E = d->ratio, EE = E * E;
+            NLC_REQUIRE(E >= 1 && d->R % E == 0 && d->V_small_host && d->m_small >= 1 && d->m_small <= EE,
+                        "nlc_op_create: block CS needs the patch edge (ratio), V_small[E^2,E^2] and 1 <= cs_size <= E^2");
+            op->m = d->m_small;
+            if ((rc = to_device(&op->Vs, d->V_small_host, static_cast<size_t>(EE) * EE))) return rc;
+            op->ydim = static_cast<int64_t>(d->channels) * (d->R / E) * (d->R / E) * op->m;
+        } break;
+        case NLC_OP_GENERAL: {
+            const int64_t nx = d->n_idx, ny = d->m_small;
+            NLC_REQUIRE(nx >= 1 && ny >= 1 && ny <= nx && d->U_small_host && d->V_small_host && d->sing_small_host,
+                        "nlc_op_create: GeneralA needs U[ny,ny], V[nx,nx], singulars[ny] with ny <= nx");
+            op->m = static_cast<int>(ny), op->nx = nx;
+            if ((rc = to_device(&op->Us, d->U_small_host, static_cast<size_t>(ny) * ny)) ||
+                (rc = to_device(&op->Vs, d->V_small_host, static_cast<size_t>(nx) * nx)) ||
+                (rc = to_device(&op->v0, d->sing_small_host, static_cast<size_t>(ny)))) return rc;
+            op->ydim = ny;
+        } break;
         default:
             delete op;
             return set_error(NLC_EINVAL, "nlc_op_create: unknown task %d", d->task);
@@ -445,7 +467,35 @@ extern "C" size_t nlc_op_ws(nlc_op* op, int B) {
     if (op->task == NLC_OP_WHCS) return 2 * n * plane * sizeof(float);
     // separable: T1..T3 + the residual A x0 - y, + one plane set of noise terms and the per-step tables of the DDNM step
     if (op->task == NLC_OP_SEPARABLE) return (5 * n + 3 + op->C) * plane * sizeof(float);
+    if (op->task == NLC_OP_BLOCKCS) return 3 * n * plane * sizeof(float);
+    if (op->task == NLC_OP_GENERAL) return static_cast<size_t>(B) * (2 * op->m + op->nx) * sizeof(float);
     return 0;
+}
+
+// ---------------------------------------------------------------- block CS: 32 x 32 patches <-> rows of a [patches, 1024] matrix
+// dir 0: Pm[(bc*np + p)*E*E + pi*E + pj] = x[bc][bi*E+pi][bj*E+pj];  dir 1: the inverse, out = base ? base - v : v * f
+__global__ void __launch_bounds__(256) patch_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                          const float* __restrict__ base, long long total, int R, int E,
+                                                          int dir, float f) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;  // image-order index
+    if (i >= total) return;
+    const int col = static_cast<int>(i % R), row = static_cast<int>((i / R) % R);
+    const long long bc = i / (static_cast<long long>(R) * R);
+    const int yd = R / E;
+    const long long p = static_cast<long long>(row / E) * yd + col / E;
+    const long long j = ((bc * yd * yd + p) * E + row % E) * E + col % E;
+    if (dir == 0) out[j] = in[i];
+    else out[i] = base ? base[i] - in[j] : __fmul_rn(in[j], f);
+}
+// GeneralA: T[b][j] *= f(s[j]);  kind 0: s, 1: zero-guarded 1/s, 2: s / (s^2 + eta)
+__global__ void __launch_bounds__(256) scale_cols_kernel(float* __restrict__ T, long long total, int ny,
+                                                          const float* __restrict__ s, int kind, float eta) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float sv = s[i % ny];
+    const float f = kind == 0 ? sv : (kind == 1 ? (sv == 0.f ? 0.f : __fdiv_rn(1.f, sv))
+                                                : __fdiv_rn(sv, __fadd_rn(__fmul_rn(sv, sv), eta)));
+    T[i] = __fmul_rn(T[i], f);
 }
 
 // f / (f^2 + eta) per table entry (A_pinv_eta of the separable operators)
@@ -549,6 +599,54 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
                                                                      1.0f / (1.0f * 1.0f + static_cast<float>(eta)));
             NLC_CHECK_LAUNCH();
         } break;
+        case NLC_OP_BLOCKCS: {
+            NLC_REQUIRE(ws, "nlc_op: block CS needs a workspace (nlc_op_ws)");
+            const int E = op->ratio, EE = E * E, cs = op->m;
+            const long long total = static_cast<long long>(B) * C * N, np = total / EE;
+            float *Pm = ws, *D = ws + total, *Pm2 = ws + 2 * total;
+            const unsigned g = blocks_for(total);
+            int rc;
+            if (mode == 0 || mode == 3) {  // Y = patches . V[:, :cs]  (- y)
+                patch_rows_kernel<<<g, 256, 0, st>>>(in, Pm, nullptr, total, R, E, 0, 1.f);
+                NLC_CHECK_LAUNCH();
+                if ((rc = launch_gemm(st, 1, static_cast<int>(np), cs, EE, Pm, 0, EE, 1, op->Vs, 0, EE, 1,
+                                      mode == 0 ? out : D, nullptr, 1, mode == 3 ? y : nullptr, nullptr))) return rc;
+                if (mode == 0) break;
+            }
+            // patches = Y . V[:, :cs]^T  (all singular values are 1: A^T = A^+), then back to the image
+            if ((rc = launch_gemm(st, 1, static_cast<int>(np), EE, cs, mode == 3 ? D : in, 0, cs, 1, op->Vs, 0, 1, EE, Pm2,
+                                  nullptr, 1, nullptr, nullptr))) return rc;
+            patch_rows_kernel<<<g, 256, 0, st>>>(Pm2, out, mode == 3 ? in : nullptr, total, R, E, 1,
+                                                 mode == 4 ? 1.0f / (1.0f * 1.0f + static_cast<float>(eta)) : 1.f);
+            NLC_CHECK_LAUNCH();
+        } break;
+        case NLC_OP_GENERAL: {
+            NLC_REQUIRE(ws, "nlc_op: GeneralA needs a workspace (nlc_op_ws)");
+            const int ny = op->m;
+            const int nx = static_cast<int>(op->nx);
+            float *T = ws, *D = ws + static_cast<size_t>(B) * ny;
+            const long long tn = static_cast<long long>(B) * ny;
+            int rc;
+            const float* yin = in;
+            if (mode == 0 || mode == 3) {  // (x V[:, :ny]) o s, then . U^T (- y)
+                if ((rc = launch_gemm(st, 1, B, ny, nx, in, 0, nx, 1, op->Vs, 0, nx, 1, T, nullptr, 1, nullptr, nullptr)))
+                    return rc;
+                scale_cols_kernel<<<blocks_for(tn), 256, 0, st>>>(T, tn, ny, op->v0, 0, 0.f);
+                NLC_CHECK_LAUNCH();
+                if ((rc = launch_gemm(st, 1, B, ny, ny, T, 0, ny, 1, op->Us, 0, 1, ny, mode == 0 ? out : D, nullptr, 1,
+                                      mode == 3 ? y : nullptr, nullptr))) return rc;
+                if (mode == 0) break;
+                yin = D;
+            }
+            // (y U) o f(s), then . V[:, :ny]^T
+            if ((rc = launch_gemm(st, 1, B, ny, ny, yin, 0, ny, 1, op->Us, 0, ny, 1, T, nullptr, 1, nullptr, nullptr)))
+                return rc;
+            scale_cols_kernel<<<blocks_for(tn), 256, 0, st>>>(T, tn, ny, op->v0, mode == 1 ? 0 : (mode == 4 ? 2 : 1),
+                                                             static_cast<float>(eta));
+            NLC_CHECK_LAUNCH();
+            return launch_gemm(st, 1, B, nx, ny, T, 0, ny, 1, op->Vs, 0, 1, nx, out, nullptr, 1, nullptr,
+                               mode == 3 ? in : nullptr);
+        }
         default:
             return set_error(NLC_EINVAL, "nlc_op: unknown task");
     }

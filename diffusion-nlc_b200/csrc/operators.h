@@ -9,6 +9,7 @@ struct nlc_op {
     int64_t ydim;
     int* idx_a;   // INPAINT: kept[k] = pixel*3+c ; WHCS: invperm[q]
     int* idx_b;   // INPAINT: pos2k[pixel*3+c] (-1 = missing)
+    int* idx_c;   // INPAINT: the same table in image order, pos2k_planar[c*HW + pixel] (128-bit loads next to the image)
     int n_kept;
     float u, s;
     float* v0;    // COLOR: 3 ; SR_AVG: r*r
@@ -18,6 +19,7 @@ struct nlc_op {
     float *Us2, *Vs2;              // SEPARABLE: right factors (== Us / Vs for one-kernel operators)
     float* lam_s;                  // SEPARABLE: [m*m] singular value per spectral position for Lambda (nullptr: none)
     bool own2;
+    int64_t nx;                    // GENERAL: columns of A (Vs is [nx,nx], Us [m,m], v0 the m singular values)
 };
 
 namespace nlc {
@@ -32,6 +34,13 @@ struct Epilogue {
     const float* add2 = nullptr;
     float g2 = 0.f;
     long long add2_stride = 0;  // elements between the samples of add2 (0 = dense C*R*R): a [B,6,R,R] network output
+    // WH-CS: work on the transform output itself (spectral position q = r*R + c, kept when invperm[q] < m), before the
+    // terms above:  ymeas   -> value = kept ? value - ymeas[b][invperm[q]*C + c] : 0   (the projection's residual)
+    //               ygather -> kept values go to ygather[b][invperm[q]*C + c], nothing else is written (A x)
+    const int* invperm = nullptr;
+    int m = 0;
+    const float* ymeas = nullptr;
+    float* ygather = nullptr;
 };
 
 // orthonormal 2-D fast Walsh-Hadamard transform of B*C planes (the reference's 1-D FWHT over R^2 entries)

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 
-INPAINT, COLOR, SR_AVG, WHCS, SEPARABLE, DENOISE = 1, 2, 3, 4, 5, 6
+INPAINT, COLOR, SR_AVG, WHCS, SEPARABLE, DENOISE, BLOCKCS, GENERAL = 1, 2, 3, 4, 5, 6, 7, 8
 
 
 def _f32(v):
@@ -171,6 +171,43 @@ class Denoising(A_functions):
         self.channels, self.img_dim = channels, img_dim
         self.xdim = channels * img_dim ** 2
         super().__init__(_lib.OpDesc(task=DENOISE, channels=channels, R=img_dim, ratio=1), (), device)
+
+
+class CS(A_functions):
+    """Block-wise compressed sensing (functions/svd_operators.py:101-160).  The reference draws a 1024 x 1024 Gaussian
+    matrix and keeps its right singular vectors; the same draw (global CPU generator) is made here unless `V_small` is
+    given, and the SVD runs on the CPU (the reference's runs where `device` says: any orthogonal basis is a valid
+    instance of the operator, the bases differ)."""
+    _has_lambda = False
+
+    def __init__(self, channels, img_dim, ratio, device, V_small=None):
+        E = 32
+        assert img_dim % E == 0
+        self.channels, self.img_dim, self.y_dim, self.ratio = channels, img_dim, img_dim // E, E
+        self.xdim = channels * img_dim ** 2
+        if V_small is None:
+            _, _, V_small = torch.svd(torch.randn(E ** 2, E ** 2), some=False)
+        V_small = V_small.detach().cpu().float().contiguous()
+        self.cs_size = int(E * E * ratio)
+        d = _lib.OpDesc(task=BLOCKCS, channels=channels, R=img_dim, ratio=E, V_small_host=_fptr(V_small),
+                        m_small=self.cs_size)
+        super().__init__(d, (V_small,), device)
+
+
+class GeneralA(A_functions):
+    """Dense SVD of an arbitrary (small) matrix A [ny, nx] (functions/svd_operators.py:173-208)."""
+    _has_lambda = False
+
+    def __init__(self, A, device=None):
+        device = A.device if device is None else device
+        U, s, V = torch.svd(A.detach().cpu().float(), some=False)
+        s = s.clone()
+        s[s < 1e-3] = 0
+        U, s, V = U.contiguous(), s.contiguous(), V.contiguous()
+        self.xdim = V.shape[0]
+        d = _lib.OpDesc(task=GENERAL, channels=1, R=1, ratio=1, n_idx=V.shape[0], U_small_host=_fptr(U),
+                        V_small_host=_fptr(V), sing_small_host=_fptr(s), m_small=U.shape[0])
+        super().__init__(d, (U, s, V), device)
 
 
 class Colorization(A_functions):

@@ -296,6 +296,8 @@ int nlc_edm_axpy(nlc_ctx* ctx, const double* x_hat, const double* e, const doubl
 #define NLC_OP_WHCS 4      /* WalshHadamardCS     :211-251                              */
 #define NLC_OP_SEPARABLE 5 /* SRConv :851-931 and Deblurring :934-1014 (Kronecker SVD)  */
 #define NLC_OP_DENOISE 6   /* Denoising           :442-476 (A = I)                      */
+#define NLC_OP_BLOCKCS 7   /* CS (block-wise compressed sensing) :101-160               */
+#define NLC_OP_GENERAL 8   /* GeneralA (dense SVD of an arbitrary small A) :173-208     */
 
 typedef struct nlc_op nlc_op;
 
@@ -305,13 +307,15 @@ typedef struct nlc_op nlc_op;
 typedef struct {
     int task;
     int channels, R;
-    int ratio;                    /* SR_AVG: pooling factor; WHCS: compression ratio                      */
+    int ratio;                    /* SR_AVG: pooling factor; WHCS: compression ratio; BLOCKCS: patch edge (32) */
     const int64_t* idx_host;      /* INPAINT: missing indices (pixel*3+c); WHCS: perm[R*R]                 */
-    int64_t n_idx;
-    const float* U_small_host;    /* COLOR / SR_AVG: [1,1]; SEPARABLE: [m,m] row-major                     */
-    const float* V_small_host;    /* COLOR: [3,3]; SR_AVG: [r^2,r^2]; SEPARABLE: [R,R] row-major           */
-    const float* sing_small_host; /* COLOR / SR_AVG: [1]                                                   */
-    int m_small;                  /* SEPARABLE: R/f (SRConv) or R (Deblurring)                             */
+    int64_t n_idx;                /* length of idx_host; GENERAL: nx, the number of columns of A            */
+    const float* U_small_host;    /* COLOR / SR_AVG: [1,1]; SEPARABLE: [m,m] row-major; GENERAL: [ny,ny]   */
+    const float* V_small_host;    /* COLOR: [3,3]; SR_AVG: [r^2,r^2]; SEPARABLE: [R,R]; BLOCKCS: [E^2,E^2]; */
+                                  /* GENERAL: [nx,nx]; all row-major                                        */
+    const float* sing_small_host; /* COLOR / SR_AVG: [1]; GENERAL: [ny] (already thresholded)              */
+    int m_small;                  /* SEPARABLE: R/f (SRConv) or R (Deblurring); BLOCKCS: cs_size = measurements */
+                                  /* kept per patch; GENERAL: ny, the number of rows of A                   */
     const float* mult_host;       /* SEPARABLE: [channels, m*m] spectral multipliers used by A and At      */
     const float* pinv_mult_host;  /* SEPARABLE: [channels, m*m] zero-guarded reciprocals used by A^+       */
     const float* U_small2_host;   /* SEPARABLE, optional: right-hand factors when rows and columns are blurred   */

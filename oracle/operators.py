@@ -471,6 +471,94 @@ class Denoising(SpectralOp):
         return v * st * eta
 
 
+class CS(_NoLambda, SpectralOp):
+    """Block-wise compressed sensing (functions/svd_operators.py:101-160): every E x E patch (E = 32) is rotated by the
+    transpose of an E^2 x E^2 orthogonal `V_small` (the right singular vectors of a random matrix, drawn by the
+    constructor there; passed in here) and its first `cs_size = int(E^2 ratio)` components are the measurement; all
+    singular values are 1.  Spectral order: the kept components of all patches first, then the dropped ones."""
+
+    def __init__(self, channels, R, ratio, V_small, E=32):
+        self.C, self.R, self.E, self.yd = channels, R, E, R // E
+        self.Vs = V_small
+        self.cs = int(E * E * ratio)
+
+    def _patches(self, x):
+        b, E, yd = x.shape[0], self.E, self.yd
+        return x.reshape(b, self.C, yd, E, yd, E).permute(0, 1, 2, 4, 3, 5).reshape(b, self.C, yd * yd, E * E)
+
+    def Vt(self, x):
+        b, E = x.shape[0], self.E
+        rot = torch.matmul(self.Vs.t(), self._patches(x).reshape(-1, E * E, 1)).reshape(b, self.C, -1, E * E)
+        return torch.cat([rot[..., :self.cs].reshape(b, -1), rot[..., self.cs:].reshape(b, -1)], dim=1)
+
+    def V(self, v):
+        b, E, yd = v.shape[0], self.E, self.yd
+        n_kept = self.C * yd * yd * self.cs
+        comp = torch.cat([v[:, :n_kept].reshape(b, self.C * yd * yd, self.cs),
+                          v[:, n_kept:].reshape(b, self.C * yd * yd, E * E - self.cs)], dim=2)
+        rot = torch.matmul(self.Vs, comp.reshape(-1, E * E, 1)).reshape(b, self.C, yd, yd, E, E)
+        return rot.permute(0, 1, 2, 4, 3, 5).reshape(b, -1)
+
+    def U(self, v):
+        return v.reshape(v.shape[0], -1)
+
+    Ut = U
+
+    def singulars(self):
+        return torch.ones(self.cs * self.C * self.yd * self.yd)
+
+    def add_zeros(self, v):
+        out = torch.zeros(v.shape[0], self.C * self.R * self.R)
+        out[:, :v.shape[1]] = v.reshape(v.shape[0], -1)
+        return out
+
+
+class GeneralA(_NoLambda, SpectralOp):
+    """Dense SVD of an arbitrary small matrix A [ny, nx] (functions/svd_operators.py:173-208); singular values below
+    1e-3 are dropped."""
+
+    def __init__(self, A):
+        self.Um, self.s, self.Vm = torch.svd(A, some=False)
+        self.s = self.s.clone()
+        self.s[self.s < 1e-3] = 0
+
+    @staticmethod
+    def _mv(M, v):
+        return torch.matmul(M, v.reshape(v.shape[0], -1, 1)).reshape(v.shape[0], M.shape[0])
+
+    def V(self, v):
+        return self._mv(self.Vm, v)
+
+    def Vt(self, v):
+        return self._mv(self.Vm.t(), v)
+
+    def U(self, v):
+        return self._mv(self.Um, v)
+
+    def Ut(self, v):
+        return self._mv(self.Um.t(), v)
+
+    def singulars(self):
+        return self.s
+
+    def add_zeros(self, v):
+        out = torch.zeros(v.shape[0], self.Vm.shape[0])
+        out[:, :self.Um.shape[0]] = v.reshape(v.shape[0], -1)
+        return out
+
+
+def hadamard_basis(n, seed):
+    """A reproducible n x n orthogonal matrix with entries +-1/sqrt(n) (exact in fp32 for n a power of 4): a Sylvester
+    Hadamard matrix with seeded row signs and column order.  Stands in for CS's random right singular vectors in the
+    golden fixtures, where a 1024 x 1024 matrix is too large to store and an SVD is not reproducible across machines."""
+    H = torch.ones(1, 1)
+    while H.shape[0] < n:
+        H = torch.cat([torch.cat([H, H], dim=1), torch.cat([H, -H], dim=1)], dim=0)
+    g = torch.Generator().manual_seed(seed)
+    signs = (torch.randint(0, 2, (n,), generator=g) * 2 - 1).float()
+    return (signs[:, None] * H[:, torch.randperm(n, generator=g)]) / n ** 0.5
+
+
 def aniso_kernels():
     """src/constraint_functions.py:280-292: 9 taps, sigma 1 (rows) and sigma 20 (columns), each normalised."""
     def k(sigma):

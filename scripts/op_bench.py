@@ -1,0 +1,92 @@
+"""Operator and DDNM-step kernels against the HBM roofline at the benchmark size
+R = 256, batch 64: CUDA-event time per call (20 calls after 5 warm-ups; every call touches 4-6 tensors of 50 MB each, more
+than the 126 MB L2), algorithmic bytes = the tensors a fused implementation has to read and write once, achieved
+GB/s against MEASURED_PEAKS.json's copy bandwidth.  Calls are replayed from a CUDA graph (see timeit).
+
+    python scripts/op_bench.py [B] [R]
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nlc_b200  # noqa: E402,F401
+from nlc_b200 import svd_operators as P  # noqa: E402
+from oracle import operators as O  # noqa: E402  (blur kernel construction helpers only)
+
+
+def timeit(fn, n=20, warm=5):
+    """Time per call on the device.  The calls are captured once into a CUDA graph (n calls per replay) so that the
+    host-side cost of the Python wrapper (ctypes, torch.empty) does not hide behind or pad the kernels: these kernels
+    run for 20-100 us, the same order as one eager call's host time."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(n):
+                fn()
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    graph.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def main():
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    R = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+    dev = torch.device("cuda:0")
+    peak = 6527.8
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    C = 3
+    d = C * R * R
+    gen = torch.Generator().manual_seed(1)
+    mask = torch.ones(R, R)
+    mask[R // 4:3 * R // 4, R // 4:3 * R // 4] = 0
+    mr = torch.nonzero(mask.reshape(-1) == 0).long().reshape(-1) * 3
+    missing = torch.cat([mr, mr + 1, mr + 2])
+    ops = {
+        "colorization": P.Colorization(R, dev),
+        "sr_averagepooling x4": P.SuperResolution(C, R, 4, dev),
+        "inpainting box": P.Inpainting(C, R, missing, dev),
+        "cs_walshhadamard x4": P.WalshHadamardCS(C, R, 4, torch.randperm(R * R, generator=gen), dev),
+        "deblur_gauss": P.Deblurring(O.gauss_kernel(), C, R, dev),
+        "denoising": P.Denoising(C, R, dev),
+    }
+    xt = torch.randn(B, C, R, R, device=dev)
+    et = torch.randn(B, 2 * C, R, R, device=dev)
+    z = torch.randn(B, C, R, R, device=dev)
+    print("B=%d R=%d  HBM peak %.0f GB/s (MEASURED_PEAKS.json)" % (B, R, peak))
+    print("%-22s %-12s %9s %9s %8s %6s" % ("operator", "call", "ms", "alg MB", "GB/s", "frac"))
+    for name, op in ops.items():
+        y = op.A(xt.reshape(B, -1))
+        img = 4.0 * B * d / 1e6
+        ym = 4.0 * B * op.ydim / 1e6
+        out = torch.empty(B, d, device=dev)
+        calls = [
+            ("project", lambda: op.project(xt, y, out=out), 2 * img + ym),            # R x0, R y, W x0_hat
+            ("ddnm_step", lambda: op.ddnm_step(xt, et, z, y, 0.5, 0.6, 0.85, None), 5 * img + ym),   # R xt et z y, W x0 x_next
+            ("ddnm+_step", lambda: op.ddnm_step(xt, et, z, y, 0.5, 0.6, 0.85, 0.1), 5 * img + ym),
+        ]
+        for cname, fn, mb in calls:
+            ms = timeit(fn)
+            gbs = mb / ms
+            print("%-22s %-12s %9.3f %9.1f %8.0f %6.2f" % (name, cname, ms, mb, gbs, gbs / peak))
+
+
+if __name__ == "__main__":
+    main()

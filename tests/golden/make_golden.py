@@ -488,6 +488,35 @@ def ddnm():
         print(f, os.path.getsize(os.path.join(HERE, f)))
 
 
+def operators3():
+    """Block-wise CS (functions/svd_operators.py:101-160, with its random basis replaced by oracle.hadamard_basis so that
+    the fixture does not have to store a 1024 x 1024 matrix) and GeneralA (:173-208) on a stored 40 x 96 matrix
+    -> operators3.pt"""
+    R = refimport.load()
+    ref = R.svd_operators
+    g = torch.Generator().manual_seed(23)
+    Rr, C, Bo = 64, 3, 2
+    op = ref.CS(C, Rr, 0.25, "cpu")
+    op.V_small = O.hadamard_basis(1024, 7)
+    op.Vt_small = op.V_small.transpose(0, 1)
+    xs = torch.rand(Bo, C * Rr * Rr, generator=g) * 2 - 1
+    x0 = torch.randn(Bo, C, Rr, Rr, generator=g)
+    y = op.A(xs.clone())
+    proj = x0 - op.A_pinv(op.A(x0.reshape(Bo, -1)) - y).reshape(x0.shape)
+    gold = dict(cs=dict(x=xs, x0=x0, A=y, At=op.At(y.clone()), A_pinv=op.A_pinv(y.clone()),
+                        A_pinv_eta=op.A_pinv_eta(y.clone(), 0.1), project=proj))
+    Am = torch.randn(40, 96, generator=g)
+    ga = ref.GeneralA(Am.clone())
+    xg = torch.randn(3, 96, generator=g)
+    x0g = torch.randn(3, 96, generator=g)
+    yg = ga.A(xg.clone())
+    gold["general"] = dict(Amat=Am, x=xg, x0=x0g, A=yg, At=ga.At(yg.clone()), A_pinv=ga.A_pinv(yg.clone()),
+                           A_pinv_eta=ga.A_pinv_eta(yg.clone(), 0.1),
+                           project=x0g - ga.A_pinv(ga.A(x0g.clone()) - yg))
+    torch.save(gold, os.path.join(HERE, "operators3.pt"))
+    print("operators3.pt", os.path.getsize(os.path.join(HERE, "operators3.pt")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()[sys.argv[1]]()

@@ -1,6 +1,7 @@
 """GPU parity of the DDNM operators (rows P0-P6): bit-level agreement with the reference's golden outputs at R=32
 (tolerance 2e-6 absolute: fp32, FMA contraction only) and size-independent properties at the benchmark size
 R=256 (A A^+ y = y, projection feasibility |A x^ - y|, idempotence)."""
+import math
 import os
 
 import pytest
@@ -76,8 +77,9 @@ def test_constraint_function_glue():
     gen = torch.Generator().manual_seed(10)
     x = (torch.rand(B, 3, R, R, generator=gen) * 2 - 1).to(dev)
     for task in ("sr_averagepooling", "colorization", "inpainting_box", "deblur_gauss", "sr_bicubic",
-                 "cs_walshhadamard"):
-        con = CF.get_constraint_function(task, constraint_scale=4.0, device=dev, image_size=R,
+                 "cs_walshhadamard", "cs_blockbased", "denoising"):
+        scale = 0.25 if task == "cs_blockbased" else 4.0  # block CS takes the kept fraction (cs_ratio)
+        con = CF.get_constraint_function(task, constraint_scale=scale, device=dev, image_size=R,
                                          perm=torch.randperm(R * R, generator=gen))
         y = con.transform(x)
         x0 = torch.randn(B, 3, R, R, generator=gen).to(dev)
@@ -87,5 +89,44 @@ def test_constraint_function_glue():
         assert fwd.device.type == "cpu" and fwd.shape == (B,) and bwd.shape == (B,)
         f0, _ = con.loss(x, y)
         assert f0.max() < 1e-2  # the ground truth satisfies its own measurement
-    with pytest.raises(NotImplementedError):
-        CF.svd_constraint("cs_blockbased")
+    assert CF.svd_constraint("no_such_task") is None
+
+
+def test_block_cs_and_general_a(golden_dir):
+    """functions/svd_operators.py CS (:101-160) and GeneralA (:173-208) against the reference's golden outputs
+    (tests/golden/operators3.pt), then CS at 256 x 256 through properties."""
+    from nlc_b200 import svd_operators as P
+    g = torch.load(os.path.join(golden_dir, "operators3.pt"), weights_only=True)
+    V = O.hadamard_basis(1024, 7)
+    for key, op in (("cs", P.CS(3, 64, 0.25, dev, V_small=V)), ("general", P.GeneralA(g["general"]["Amat"], dev))):
+        c = g[key]
+        assert op.ydim == c["A"].shape[1]
+        for got, want in ((op.A(c["x"].to(dev)), c["A"]), (op.At(c["A"].to(dev)), c["At"]),
+                          (op.A_pinv(c["A"].to(dev)), c["A_pinv"]), (op.A_pinv_eta(c["A"].to(dev), 0.1), c["A_pinv_eta"]),
+                          (op.project(c["x0"].to(dev), c["A"].to(dev)), c["project"])):
+            assert (got.cpu().reshape(want.shape) - want).abs().max() <= 1e-5 * want.abs().max(), key
+        with pytest.raises(NotImplementedError):
+            op.Lambda(c["x"].to(dev), 0.9, 0.1, 0.3, 0.85)
+        # the plain DDNM step (functions/svd_ddnm.py:52-62) composed from the same pieces
+        gen = torch.Generator().manual_seed(3)
+        xt, et, z = (torch.randn(c["x0"].shape, generator=gen).to(dev) for _ in range(3))
+        x0, xn = op.ddnm_step(xt, et, z, c["A"].to(dev), 0.5, 0.6, 0.85, None)
+        want0 = (xt - et * math.sqrt(1 - 0.5)) / math.sqrt(0.5)
+        assert (x0 - want0).abs().max() < 1e-5
+        st = math.sqrt(1 - 0.6)
+        wantn = math.sqrt(0.6) * op.project(x0, c["A"].to(dev)).reshape(x0.shape) + st * 0.85 * z + \
+            st * math.sqrt(1 - 0.85 ** 2) * et
+        assert (xn - wantn).abs().max() < 1e-5
+    R, B = 256, 4
+    torch.manual_seed(11)
+    op = P.CS(3, R, 0.25, dev)  # the reference's own construction: random Gaussian matrix, its right singular vectors
+    x = (torch.rand(B, 3 * R * R) * 2 - 1).to(dev)
+    x0 = torch.randn(B, 3, R, R).to(dev)
+    y = op.A(x)
+    assert y.shape == (B, 3 * 64 * 256)
+    assert (op.A(op.A_pinv(y)) - y).abs().max() < 2e-5
+    p = op.project(x0, y)
+    assert (op.A(p) - y).abs().max() < 5e-5
+    assert (op.project(p, y) - p).abs().max() < 5e-5
+    lhs, rhs = (op.A(x) * y).sum(dim=1), (x * op.At(y)).sum(dim=1)
+    assert ((lhs - rhs).abs() / lhs.abs().clamp_min(1.0)).max() < 1e-3

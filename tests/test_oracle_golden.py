@@ -305,3 +305,20 @@ def test_ddnm_schedule_and_loops(golden_dir):
                                        travel_length=g["travel_length"], travel_repeat=g["travel_repeat"],
                                        noise_fn=lambda like: next(zs))
         assert (x_last - case["x_last"]).abs().max() <= 2e-5 * case["x_last"].abs().max(), key
+
+
+def test_block_cs_and_general_a(golden_dir):
+    """tests/golden/operators3.pt: functions/svd_operators.py CS (with the reproducible Hadamard basis) and GeneralA."""
+    g = load(golden_dir, "operators3.pt")
+    V = O.hadamard_basis(1024, 7)
+    assert torch.equal(V @ V.t(), torch.eye(1024))  # exactly orthogonal in fp32
+    c = g["cs"]
+    op = O.CS(3, 64, 0.25, V)
+    assert torch.equal(op.A(c["x"]), c["A"]) and torch.equal(op.At(c["A"]), c["At"])
+    assert torch.equal(op.A_pinv(c["A"]), c["A_pinv"]) and torch.equal(op.A_pinv_eta(c["A"], 0.1), c["A_pinv_eta"])
+    assert torch.equal(op.project(c["x0"], c["A"]), c["project"])
+    c = g["general"]
+    op = O.GeneralA(c["Amat"].clone())
+    for got, want in ((op.A(c["x"]), c["A"]), (op.At(c["A"]), c["At"]), (op.A_pinv(c["A"]), c["A_pinv"]),
+                      (op.A_pinv_eta(c["A"], 0.1), c["A_pinv_eta"]), (op.project(c["x0"], c["A"]), c["project"])):
+        assert (got - want).abs().max() <= 1e-5 * want.abs().max()  # the SVD is recomputed here

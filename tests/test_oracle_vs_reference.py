@@ -157,6 +157,26 @@ def test_operators(R):
                                b.Lambda_noise(v.clone(), a_t, sy, st_t, eta, e.clone()))
 
 
+def test_block_cs_general_a_denoising(R):
+    """The remaining operator classes of functions/svd_operators.py (:101-208, 442-476), live, with the reference's own
+    random basis."""
+    ref = R.svd_operators
+    B = 2
+    a = ref.CS(3, 64, 0.25, "cpu")
+    pairs = [(a, O.CS(3, 64, 0.25, a.V_small), 3 * 64 * 64)]
+    Am = torch.randn(24, 80)
+    pairs.append((ref.GeneralA(Am.clone()), O.GeneralA(Am.clone()), 80))
+    pairs.append((ref.Denoising(3, 32, "cpu"), O.Denoising(3, 32), 3 * 32 * 32))
+    for a, b, n in pairs:
+        x, x0 = torch.rand(B, n) * 2 - 1, torch.randn(B, n)
+        y = a.A(x.clone())
+        assert torch.equal(y, b.A(x.clone()))
+        assert torch.equal(a.At(y.clone()), b.At(y.clone()))
+        assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
+        assert torch.equal(a.A_pinv_eta(y.clone(), 0.3), b.A_pinv_eta(y.clone(), 0.3))
+        assert torch.equal(x0 - a.A_pinv(a.A(x0.clone()) - y), b.project(x0, y))
+
+
 @pytest.mark.parametrize("name", ["adm_tiny", "adm_alt"])
 def test_adm_networks(R, name):
     """oracle/adm_net.py == src/unet_adm.py (UNetModel forward/encode, SigmaModel), bit for bit."""
