@@ -60,17 +60,54 @@ __device__ __forceinline__ float x0_of(float xt, float et, const Step& s) {
 
 enum { M_LAMBDA = 0, M_NOISE = 1, M_STEP = 2 };
 
+// ---------------------------------------------------------------- vector access helpers
+// V consecutive floats per thread (V = 4: one 128-bit access; V = 1: the fallback for odd sizes / unaligned pointers)
+template <int V> struct Pack { float v[V]; };
+template <int V>
+__device__ __forceinline__ Pack<V> ldv(const float* p) {
+    Pack<V> r;
+    if constexpr (V == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        r.v[0] = t.x, r.v[1] = t.y, r.v[2] = t.z, r.v[3] = t.w;
+    } else if constexpr (V == 2) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        r.v[0] = t.x, r.v[1] = t.y;
+    } else {
+        r.v[0] = __ldg(p);
+    }
+    return r;
+}
+template <int V>
+__device__ __forceinline__ void stv(float* p, const Pack<V>& a) {
+    if constexpr (V == 4) *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    else if constexpr (V == 2) *reinterpret_cast<float2*>(p) = make_float2(a.v[0], a.v[1]);
+    else p[0] = a.v[0];
+}
+template <int V>
+__device__ __forceinline__ void ldiv(const int* p, int* dst) {
+    if constexpr (V == 4) {
+        const int4 t = __ldg(reinterpret_cast<const int4*>(p));
+        dst[0] = t.x, dst[1] = t.y, dst[2] = t.z, dst[3] = t.w;
+    } else {
+        dst[0] = __ldg(p);
+    }
+}
+
 // ---------------------------------------------------------------- colourisation / average-pool SR
 // One thread per needle.  in1 = v | xt, in2 = eps | et (sample stride in2_stride), out1 = result | x_next, out0 = x0_t.
+// RW = contiguous floats per needle row: the r x r patch of SR is read as r row vectors (r = 2, 4), colour planes scalar.
+template <int K> struct NeedleGeom { static constexpr int RW = K == 16 ? 4 : (K == 4 ? 2 : 1); };
+
 template <int K>
 __global__ void __launch_bounds__(128) needle_ddnm_kernel(int mode, const float* __restrict__ in1,
                                                            const float* __restrict__ in2, long long in2_stride,
                                                            const float* __restrict__ z, const float* __restrict__ y,
                                                            float* __restrict__ out1, float* __restrict__ out0, int B, int C,
                                                            int R, int r, int per_ch, float u, float s,
-                                                           const float* __restrict__ Vfull, const Step sc) {
+                                                           const float* __restrict__ Vfull, const Step sc, int vec_ok) {
     constexpr int UN = K <= 16 ? K : 1;  // r = 8 (K = 64) keeps its needles in local memory instead of 256 registers
-    __shared__ float V[K * K];
+    constexpr int RW = NeedleGeom<K>::RW;
+    __shared__ __align__(16) float V[K * K];
     for (int t = threadIdx.x; t < K * K; t += blockDim.x) V[t] = Vfull[t];
     __syncthreads();
     const int yd = R / r;
@@ -91,14 +128,40 @@ __global__ void __launch_bounds__(128) needle_ddnm_kernel(int mode, const float*
     auto off = [&](int k) -> size_t {
         return per_ch ? static_cast<size_t>(k / r) * R + (k % r) : static_cast<size_t>(k) * plane;
     };
+    auto load = [&](const float* p, size_t bs, float* dst) {
+        if (RW > 1 && vec_ok) {
+#pragma unroll
+            for (int rr = 0; rr < (RW > 1 ? RW : 1); ++rr) {
+                const Pack<RW> row = ldv<RW>(p + bs + static_cast<size_t>(rr) * R);
+#pragma unroll
+                for (int cc = 0; cc < RW; ++cc) dst[rr * RW + cc] = row.v[cc];
+            }
+        } else {
+#pragma unroll UN
+            for (int k = 0; k < K; ++k) dst[k] = p[bs + off(k)];
+        }
+    };
+    auto store = [&](float* p, const float* src) {
+        if (RW > 1 && vec_ok) {
+#pragma unroll
+            for (int rr = 0; rr < (RW > 1 ? RW : 1); ++rr) {
+                Pack<RW> row;
+#pragma unroll
+                for (int cc = 0; cc < RW; ++cc) row.v[cc] = src[rr * RW + cc];
+                stv<RW>(p + base + static_cast<size_t>(rr) * R, row);
+            }
+        } else {
+#pragma unroll UN
+            for (int k = 0; k < K; ++k) p[base + off(k)] = src[k];
+        }
+    };
     float lam0, d10, d20, lamN, d1N, d2N;
     ddnm_terms(s, sc.coef, lam0, d10, d20);
     ddnm_terms(0.f, sc.coef, lamN, d1N, d2N);
 
-    float n[K];
+    float n[K], o[K];
     if (mode == M_LAMBDA) {
-#pragma unroll UN
-        for (int k = 0; k < K; ++k) n[k] = in1[base + off(k)];
+        load(in1, base, n);
         float w[K];
 #pragma unroll UN
         for (int kp = 0; kp < K; ++kp) {
@@ -112,23 +175,22 @@ __global__ void __launch_bounds__(128) needle_ddnm_kernel(int mode, const float*
             float acc = 0.f;
 #pragma unroll UN
             for (int kp = 0; kp < K; ++kp) acc = fmaf(V[j * K + kp], w[kp], acc);
-            out1[base + off(j)] = acc;
+            o[j] = acc;
         }
+        store(out1, o);
         return;
     }
     float e[K], zz[K];
+    load(in2, base2, e);
     if (mode == M_NOISE) {
-#pragma unroll UN
-        for (int k = 0; k < K; ++k) zz[k] = in1[base + off(k)], e[k] = in2[base2 + off(k)];
+        load(in1, base, zz);
     } else {
+        load(in1, base, n);
+        load(z, base, zz);
         float dot = 0.f;
 #pragma unroll UN
-        for (int k = 0; k < K; ++k) {
-            e[k] = in2[base2 + off(k)];
-            n[k] = x0_of(in1[base + off(k)], e[k], sc);
-            out0[base + off(k)] = n[k];
-            zz[k] = z[base + off(k)];
-        }
+        for (int k = 0; k < K; ++k) n[k] = x0_of(n[k], e[k], sc);
+        store(out0, n);
 #pragma unroll UN
         for (int k = 0; k < K; ++k) dot = fmaf(V[k * K], n[k], dot);  // v0 = first column of V
         const float meas = u * (s * dot);                              // A x0
@@ -137,130 +199,149 @@ __global__ void __launch_bounds__(128) needle_ddnm_kernel(int mode, const float*
 #pragma unroll UN
             for (int k = 0; k < K; ++k) {
                 const float x0h = n[k] - V[k * K] * t;
-                out1[base + off(k)] =
-                    __fadd_rn(__fadd_rn(__fmul_rn(sc.a, x0h), __fmul_rn(sc.c1, zz[k])), __fmul_rn(sc.c2, e[k]));
+                o[k] = __fadd_rn(__fadd_rn(__fmul_rn(sc.a, x0h), __fmul_rn(sc.c1, zz[k])), __fmul_rn(sc.c2, e[k]));
             }
+            store(out1, o);
             return;
         }
-        // resid = v0 t ; Lambda(resid) = V (lambda o V^T resid)
-        float w[K];
+        // A^+(A x0 - y) = v0 t lies along the first right singular vector, so Lambda (V diag(lambda) V^T) scales it by lambda_0
+        const float tl = __fmul_rn(t, lam0);
 #pragma unroll UN
-        for (int kp = 0; kp < K; ++kp) {
-            float acc = 0.f;
-#pragma unroll UN
-            for (int k = 0; k < K; ++k) acc = fmaf(V[k * K + kp], V[k * K] * t, acc);
-            w[kp] = kp == 0 ? __fmul_rn(acc, lam0) : acc;
-        }
-#pragma unroll UN
-        for (int j = 0; j < K; ++j) {
-            float acc = 0.f;
-#pragma unroll UN
-            for (int kp = 0; kp < K; ++kp) acc = fmaf(V[j * K + kp], w[kp], acc);
-            n[j] = n[j] - acc;  // x0_hat
-        }
+        for (int k = 0; k < K; ++k) n[k] = n[k] - V[k * K] * tl;  // x0_hat
     }
-    // V (d1 o z) + V (d2 o e): channel / patch entry k stands in for component k (:575-581, 698-699)
+    // V (d1 o z + d2 o e): channel / patch entry k stands in for component k (:575-581, 698-699)
+#pragma unroll UN
+    for (int k = 0; k < K; ++k)
+        zz[k] = __fadd_rn(__fmul_rn(zz[k], k == 0 ? d10 : d1N), __fmul_rn(e[k], k == 0 ? d20 : d2N));
 #pragma unroll UN
     for (int j = 0; j < K; ++j) {
-        float a1 = 0.f, a2 = 0.f;
+        float acc = 0.f;
 #pragma unroll UN
-        for (int k = 0; k < K; ++k) {
-            a1 = fmaf(V[j * K + k], __fmul_rn(zz[k], k == 0 ? d10 : d1N), a1);
-            a2 = fmaf(V[j * K + k], __fmul_rn(e[k], k == 0 ? d20 : d2N), a2);
-        }
-        const float nz = __fadd_rn(a1, a2);
-        out1[base + off(j)] = mode == M_NOISE ? nz : __fadd_rn(__fmul_rn(sc.a, n[j]), nz);
+        for (int k = 0; k < K; ++k) acc = fmaf(V[j * K + k], zz[k], acc);
+        o[j] = mode == M_NOISE ? acc : __fadd_rn(__fmul_rn(sc.a, n[j]), acc);
     }
+    store(out1, o);
 }
 
 // ---------------------------------------------------------------- inpainting / denoising (V is a permutation / identity)
-// pos2k == nullptr: Denoising (every entry kept, s = 1, and the class' own scalar rules :464-476)
+// pos2k == nullptr: Denoising (every entry kept, s = 1, and the class' own scalar rules :464-476); otherwise pos2k is the
+// image-order table (nlc_op::idx_c).  V consecutive entries per thread.
+template <int V>
 __global__ void __launch_bounds__(256) mask_ddnm_kernel(int mode, const float* __restrict__ in1,
                                                          const float* __restrict__ in2, long long in2_stride,
                                                          const float* __restrict__ z, const float* __restrict__ y,
-                                                         float* __restrict__ out1, float* __restrict__ out0, int B, int C,
-                                                         int HW, const int* __restrict__ pos2k, int n_kept, const Step sc) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long per_sample = static_cast<long long>(C) * HW;
+                                                         float* __restrict__ out1, float* __restrict__ out0, int B,
+                                                         long long per_sample, const int* __restrict__ pos2k, int n_kept,
+                                                         const Step sc) {
+    const long long iv = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i = iv * V;
     if (i >= per_sample * B) return;
     const long long b = i / per_sample, q = i - b * per_sample;
     const size_t i2 = static_cast<size_t>(b) * (in2_stride ? in2_stride : per_sample) + q;
-    int k;
-    float lam, d1, d2;
+    float lamK, d1K, d2K, lamN, d1N, d2N;
     bool scale_first = false;  // Denoising's `vec * sigma_t * eta` multiplies in that order
+    int ks[V];
     if (pos2k) {
-        const int p = static_cast<int>(q % HW), c = static_cast<int>(q / HW);
-        k = pos2k[p * C + c];
-        ddnm_terms(k >= 0 ? 1.f : 0.f, sc.coef, lam, d1, d2);
+        ldiv<V>(pos2k + q, ks);
+        ddnm_terms(1.f, sc.coef, lamK, d1K, d2K);
+        ddnm_terms(0.f, sc.coef, lamN, d1N, d2N);
     } else {
-        k = static_cast<int>(q);
+#pragma unroll
+        for (int e = 0; e < V; ++e) ks[e] = static_cast<int>(q) + e;
         const Coef& c = sc.coef;
         const float thr = __fmul_rn(c.a, c.sy);
-        lam = c.st < thr ? __fdiv_rn(__fdiv_rn(__fmul_rn(c.st, c.root), c.a), c.sy) : 1.f;
-        d2 = 0.f;
-        if (c.st >= thr) d1 = __fsqrt_rn(__fsub_rn(__fmul_rn(c.st, c.st), __fmul_rn(__fmul_rn(c.a, c.a), c.sy2)));
-        else d1 = 0.f, scale_first = true;
+        lamK = c.st < thr ? __fdiv_rn(__fdiv_rn(__fmul_rn(c.st, c.root), c.a), c.sy) : 1.f;
+        d2K = 0.f;
+        if (c.st >= thr) d1K = __fsqrt_rn(__fsub_rn(__fmul_rn(c.st, c.st), __fmul_rn(__fmul_rn(c.a, c.a), c.sy2)));
+        else d1K = 0.f, scale_first = true;
+        lamN = lamK, d1N = d1K, d2N = d2K;
     }
-    auto noise = [&](float zv, float ev) -> float {
+    auto noise = [&](float zv, float ev, bool kept) -> float {
         if (scale_first) return __fmul_rn(__fmul_rn(zv, sc.coef.st), sc.coef.eta);
-        if (!pos2k) return __fmul_rn(zv, d1);
-        return __fadd_rn(__fmul_rn(zv, d1), __fmul_rn(ev, d2));
+        if (!pos2k) return __fmul_rn(zv, d1K);
+        return __fadd_rn(__fmul_rn(zv, kept ? d1K : d1N), __fmul_rn(ev, kept ? d2K : d2N));
     };
+    const Pack<V> a1 = ldv<V>(in1 + i);
+    Pack<V> o;
     if (mode == M_LAMBDA) {
-        out1[i] = (pos2k || lam != 1.f) ? __fmul_rn(in1[i], lam) : in1[i];
-    } else if (mode == M_NOISE) {
-        out1[i] = noise(in1[i], in2[i2]);
-    } else {
-        const float ev = in2[i2];
-        const float x0 = x0_of(in1[i], ev, sc);
-        out0[i] = x0;
-        const float resid = k >= 0 ? __fsub_rn(x0, y[static_cast<size_t>(b) * n_kept + k]) : 0.f;
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.v[e] = __fmul_rn(a1.v[e], ks[e] >= 0 ? lamK : lamN);
+        stv<V>(out1 + i, o);
+        return;
+    }
+    const Pack<V> a2 = ldv<V>(in2 + i2);
+    if (mode == M_NOISE) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) o.v[e] = noise(a1.v[e], a2.v[e], ks[e] >= 0);
+        stv<V>(out1 + i, o);
+        return;
+    }
+    const Pack<V> zv = ldv<V>(z + i);
+    Pack<V> x0;
+    const float* yb = y + static_cast<size_t>(b) * n_kept;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        x0.v[e] = x0_of(a1.v[e], a2.v[e], sc);
+        const bool kept = ks[e] >= 0;
+        const float resid = kept ? __fsub_rn(x0.v[e], __ldg(yb + ks[e])) : 0.f;
         if (sc.plus) {
-            const float x0h = __fsub_rn(x0, (pos2k || lam != 1.f) ? __fmul_rn(resid, lam) : resid);
-            out1[i] = __fadd_rn(__fmul_rn(sc.a, x0h), noise(z[i], ev));
+            const float x0h = __fsub_rn(x0.v[e], __fmul_rn(resid, kept ? lamK : lamN));
+            o.v[e] = __fadd_rn(__fmul_rn(sc.a, x0h), noise(zv.v[e], a2.v[e], kept));
         } else {
-            const float x0h = __fsub_rn(x0, resid);
-            out1[i] = __fadd_rn(__fadd_rn(__fmul_rn(sc.a, x0h), __fmul_rn(sc.c1, z[i])), __fmul_rn(sc.c2, ev));
+            const float x0h = __fsub_rn(x0.v[e], resid);
+            o.v[e] = __fadd_rn(__fadd_rn(__fmul_rn(sc.a, x0h), __fmul_rn(sc.c1, zv.v[e])), __fmul_rn(sc.c2, a2.v[e]));
         }
     }
+    stv<V>(out0 + i, x0);
+    stv<V>(out1 + i, o);
 }
 
 // ---------------------------------------------------------------- shared elementwise pieces (WH-CS, Deblurring)
+template <int V>
 __global__ void __launch_bounds__(256) x0_kernel(const float* __restrict__ xt, const float* __restrict__ et,
                                                   long long et_stride, float* __restrict__ x0, long long per_sample, int B,
                                                   const Step sc) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * V;
     if (i >= per_sample * B) return;
     const long long b = i / per_sample;
-    x0[i] = x0_of(xt[i], et[static_cast<size_t>(b) * et_stride + (i - b * per_sample)], sc);
+    const Pack<V> x = ldv<V>(xt + i), e = ldv<V>(et + static_cast<size_t>(b) * et_stride + (i - b * per_sample));
+    Pack<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = x0_of(x.v[k], e.v[k], sc);
+    stv<V>(x0 + i, o);
 }
 // out = g1[o] v + g2[o] e with the factors of spectral position o = i % plane:
 //   invperm != nullptr (WH-CS): kept (invperm[o] < m) -> s = 1, else null space;  tab != nullptr (Deblurring): s = tab[o]
 // F != nullptr adds the Lambda'd residual of the step:  -a lambda (F - y) on kept entries (WH-CS only)
+template <int V>
 __global__ void __launch_bounds__(256) mix_kernel(const float* __restrict__ v, const float* __restrict__ e,
                                                    long long e_stride, const float* __restrict__ F,
                                                    const float* __restrict__ y, float* __restrict__ out, int B, int C,
                                                    long long plane, const int* __restrict__ invperm, int m,
                                                    const float* __restrict__ tab, const Step sc) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * V;
     const long long per_sample = static_cast<long long>(C) * plane;
     if (i >= per_sample * B) return;
     const long long b = i / per_sample, q = i - b * per_sample;
     const int o = static_cast<int>(q % plane), c = static_cast<int>(q / plane);
-    float lam, d1, d2;
-    int j = -1;
-    if (invperm) {
-        j = invperm[o];
-        ddnm_terms(j < m ? 1.f : 0.f, sc.coef, lam, d1, d2);
-    } else {
-        ddnm_terms(tab[o], sc.coef, lam, d1, d2);
+    const Pack<V> vv = ldv<V>(v + i), ee = ldv<V>(e + static_cast<size_t>(b) * e_stride + q);
+    Pack<V> ff, ss, res;
+    int js[V];
+    if (invperm) ldiv<V>(invperm + o, js);
+    else ss = ldv<V>(tab + o);
+    if (F) ff = ldv<V>(F + i);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        float lam, d1, d2;
+        ddnm_terms(invperm ? (js[k] < m ? 1.f : 0.f) : ss.v[k], sc.coef, lam, d1, d2);
+        float r = __fadd_rn(__fmul_rn(vv.v[k], d1), __fmul_rn(ee.v[k], d2));
+        if (F && invperm && js[k] < m) {
+            const float resid = ff.v[k] - __ldg(y + static_cast<size_t>(b) * m * C + static_cast<size_t>(js[k]) * C + c);
+            r = fmaf(-sc.a * lam, resid, r);
+        }
+        res.v[k] = r;
     }
-    float r = __fadd_rn(__fmul_rn(v[i], d1), __fmul_rn(e[static_cast<size_t>(b) * e_stride + q], d2));
-    if (F && j >= 0 && j < m) {
-        const float resid = F[i] - y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c];
-        r = fmaf(-sc.a * lam, resid, r);
-    }
-    out[i] = r;
+    stv<V>(out + i, res);
 }
 // WH-CS Lambda in the transform domain: F[o] *= lambda on kept entries
 __global__ void __launch_bounds__(256) whcs_lambda_kernel(float* __restrict__ F, long long n, long long plane,
@@ -270,18 +351,6 @@ __global__ void __launch_bounds__(256) whcs_lambda_kernel(float* __restrict__ F,
     float lam, d1, d2;
     ddnm_terms(invperm[i % plane] < m ? 1.f : 0.f, sc.coef, lam, d1, d2);
     F[i] = __fmul_rn(F[i], lam);
-}
-// T[o] = kept ? F[o] - y : 0  (the spectral residual of the plain DDNM step)
-__global__ void __launch_bounds__(256) whcs_resid_kernel(const float* __restrict__ F, const float* __restrict__ y,
-                                                          float* __restrict__ T, int B, int C, long long plane,
-                                                          const int* __restrict__ invperm, int m) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const long long per_sample = static_cast<long long>(C) * plane;
-    if (i >= per_sample * B) return;
-    const long long b = i / per_sample, q = i - b * per_sample;
-    const int o = static_cast<int>(q % plane), c = static_cast<int>(q / plane);
-    const int j = invperm[o];
-    T[i] = j < m ? F[i] - y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c] : 0.f;
 }
 // Deblurring: per-step factor tables over the m*m spectral positions.  lam[o], and comb[c][o] = -a lambda[o] pinv[c][o]
 __global__ void __launch_bounds__(256) deblur_tables_kernel(const float* __restrict__ lam_s, const float* __restrict__ pinv,
@@ -314,10 +383,22 @@ __global__ void __launch_bounds__(256) assemble_kernel(float* __restrict__ x, co
     x[i] = __fadd_rn(__fadd_rn(__fmul_rn(a, x[i]), __fmul_rn(c1, z[i])),
                      __fmul_rn(c2, e[static_cast<size_t>(b) * e_stride + (i - b * per_sample)]));
 }
+template <int V>
 __global__ void __launch_bounds__(256) renoise_kernel(const float* __restrict__ x0, const float* __restrict__ z,
                                                        long long n, float a, float sig, float* __restrict__ out) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __fadd_rn(__fmul_rn(a, x0[i]), __fmul_rn(z[i], sig));
+    const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * V;
+    if (i >= n) return;
+    const Pack<V> x = ldv<V>(x0 + i), zz = ldv<V>(z + i);
+    Pack<V> o;
+#pragma unroll
+    for (int k = 0; k < V; ++k) o.v[k] = __fadd_rn(__fmul_rn(a, x.v[k]), __fmul_rn(zz.v[k], sig));
+    stv<V>(out + i, o);
+}
+
+static inline bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr,
+                             const void* e = nullptr, const void* f = nullptr) {
+    return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+             reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(f)) & 15) == 0;
 }
 
 template <int K>
@@ -326,8 +407,9 @@ static int launch_needle(nlc_op* op, int mode, const float* in1, const float* in
     const int per_ch = op->task == NLC_OP_SR_AVG, r = per_ch ? op->ratio : 1;
     const long long plane = static_cast<long long>(op->R) * op->R;
     const long long n = per_ch ? static_cast<long long>(B) * op->C * (plane / (r * r)) : static_cast<long long>(B) * plane;
+    const int vec_ok = aligned16(in1, in2, z, out1, out0) && s2 % 4 == 0 && op->R % 4 == 0;
     needle_ddnm_kernel<K><<<blocks_for(n, 128), 128, 0, st>>>(mode, in1, in2, s2, z, y, out1, out0, B, op->C, op->R, r,
-                                                               per_ch, op->u, op->s, op->Vfull, sc);
+                                                               per_ch, op->u, op->s, op->Vfull, sc, vec_ok);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -339,6 +421,9 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
     const long long plane = static_cast<long long>(R) * R;
     const long long per_sample = op->task == NLC_OP_GENERAL ? op->nx : C * plane, total = per_sample * B;
     if (s2 == 0) s2 = per_sample;
+    // 128-bit accesses when every tensor is 16-byte aligned and a sample / a plane is a whole number of float4
+    const bool vec4 = aligned16(in1, in2, z, out1, out0, ws) && per_sample % 4 == 0 && s2 % 4 == 0 && plane % 4 == 0 &&
+                      (op->task != NLC_OP_DENOISE || aligned16(y));
     int rc;
     switch (op->task) {
         case NLC_OP_COLOR:
@@ -355,10 +440,14 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
             }
         case NLC_OP_INPAINT:
         case NLC_OP_DENOISE:
-            mask_ddnm_kernel<<<blocks_for(total), 256, 0, st>>>(
-                mode, in1, in2, s2, z, y, out1, out0, B, C, static_cast<int>(plane),
-                op->task == NLC_OP_INPAINT ? op->idx_b : nullptr,
-                op->task == NLC_OP_INPAINT ? op->n_kept : static_cast<int>(per_sample), sc);
+            if (vec4)
+                mask_ddnm_kernel<4><<<blocks_for(total / 4), 256, 0, st>>>(
+                    mode, in1, in2, s2, z, y, out1, out0, B, per_sample, op->task == NLC_OP_INPAINT ? op->idx_c : nullptr,
+                    op->task == NLC_OP_INPAINT ? op->n_kept : static_cast<int>(per_sample), sc);
+            else
+                mask_ddnm_kernel<1><<<blocks_for(total), 256, 0, st>>>(
+                    mode, in1, in2, s2, z, y, out1, out0, B, per_sample, op->task == NLC_OP_INPAINT ? op->idx_c : nullptr,
+                    op->task == NLC_OP_INPAINT ? op->n_kept : static_cast<int>(per_sample), sc);
             NLC_CHECK_LAUNCH();
             return NLC_OK;
         case NLC_OP_WHCS: {
@@ -373,24 +462,30 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
                 NLC_CHECK_LAUNCH();
                 return fwht2d(op, F, out1, Epilogue(), B, st);
             }
+            const unsigned g4 = blocks_for(total / 4);
             if (mode == M_NOISE) {
-                mix_kernel<<<g, 256, 0, st>>>(in1, in2, s2, nullptr, nullptr, T, B, C, plane, op->idx_a, m, nullptr, sc);
+                if (vec4) mix_kernel<4><<<g4, 256, 0, st>>>(in1, in2, s2, nullptr, nullptr, T, B, C, plane, op->idx_a, m, nullptr, sc);
+                else mix_kernel<1><<<g, 256, 0, st>>>(in1, in2, s2, nullptr, nullptr, T, B, C, plane, op->idx_a, m, nullptr, sc);
                 NLC_CHECK_LAUNCH();
                 return fwht2d(op, T, out1, Epilogue(), B, st);
             }
-            x0_kernel<<<g, 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            if (vec4) x0_kernel<4><<<g4, 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            else x0_kernel<1><<<g, 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
             NLC_CHECK_LAUNCH();
-            if ((rc = fwht2d(op, out0, F, Epilogue(), B, st))) return rc;
             Epilogue e;
             e.base = out0, e.alpha = sc.a;
             if (sc.plus) {  // x_next = a x0 + FWHT(-a lambda (F - y) + d1 z + d2 et)
-                mix_kernel<<<g, 256, 0, st>>>(z, in2, s2, F, y, T, B, C, plane, op->idx_a, m, nullptr, sc);
+                if ((rc = fwht2d(op, out0, F, Epilogue(), B, st))) return rc;
+                if (vec4) mix_kernel<4><<<g4, 256, 0, st>>>(z, in2, s2, F, y, T, B, C, plane, op->idx_a, m, nullptr, sc);
+                else mix_kernel<1><<<g, 256, 0, st>>>(z, in2, s2, F, y, T, B, C, plane, op->idx_a, m, nullptr, sc);
+                NLC_CHECK_LAUNCH();
                 e.beta = 1.f;
-            } else {        // x_next = a x0 - a FWHT(F - y) + c1 z + c2 et
-                whcs_resid_kernel<<<g, 256, 0, st>>>(F, y, T, B, C, plane, op->idx_a, m);
+            } else {        // x_next = a x0 - a FWHT(kept ? F - y : 0) + c1 z + c2 et; the residual rides on the first store
+                Epilogue e1;
+                e1.invperm = op->idx_a, e1.m = m, e1.ymeas = y;
+                if ((rc = fwht2d(op, out0, T, e1, B, st))) return rc;
                 e.beta = -sc.a, e.add1 = z, e.g1 = sc.c1, e.add2 = in2, e.g2 = sc.c2, e.add2_stride = s2;
             }
-            NLC_CHECK_LAUNCH();
             return fwht2d(op, T, out1, e, B, st);
         }
         case NLC_OP_SEPARABLE: {
@@ -414,14 +509,15 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
                 return launch_gemm(st, n, R, R, R, W2, pl, R, 1, op->Vs2, 0, 1, R, out1, nullptr, 1, nullptr, nullptr);
             }
             if (mode == M_NOISE) {  // V_s (d1 o v + d2 o e) V_s2^T
-                mix_kernel<<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, nullptr, nullptr, ADD, B, C, plane, nullptr, 0,
+                mix_kernel<1><<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, nullptr, nullptr, ADD, B, C, plane, nullptr, 0,
                                                               op->lam_s, sc);
                 NLC_CHECK_LAUNCH();
                 if ((rc = launch_gemm(st, n, R, R, R, op->Vs, 0, R, 1, ADD, pl, R, 1, W2, nullptr, 1, nullptr, nullptr)))
                     return rc;
                 return launch_gemm(st, n, R, R, R, W2, pl, R, 1, op->Vs2, 0, 1, R, out1, nullptr, 1, nullptr, nullptr);
             }
-            x0_kernel<<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            if (vec4) x0_kernel<4><<<blocks_for(total / 4), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            else x0_kernel<1><<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
             NLC_CHECK_LAUNCH();
             if ((rc = separable_A(op, out0, B, diff, ws, y, st))) return rc;  // A x0 - y   (uses W0..W2)
             const float* table = op->pinv;
@@ -429,7 +525,7 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
             if (sc.plus) {
                 deblur_tables_kernel<<<blocks_for(mm), 256, 0, st>>>(op->lam_s, op->pinv, C, mm, LAM, COMB, sc);
                 NLC_CHECK_LAUNCH();
-                mix_kernel<<<blocks_for(total), 256, 0, st>>>(z, in2, s2, nullptr, nullptr, ADD, B, C, plane, nullptr, 0,
+                mix_kernel<1><<<blocks_for(total), 256, 0, st>>>(z, in2, s2, nullptr, nullptr, ADD, B, C, plane, nullptr, 0,
                                                               op->lam_s, sc);
                 NLC_CHECK_LAUNCH();
                 table = COMB, add_spec = ADD;
@@ -453,7 +549,8 @@ static int ddnm_apply(nlc_op* op, int mode, const float* in1, const float* in2, 
         case NLC_OP_GENERAL: {  // no closed form kept for these: x0, the library projection, then the x_next assembly
             NLC_REQUIRE(mode == M_STEP && !sc.plus,
                         "DDNM+: this operator class defines no Lambda / Lambda_noise in the reference (CS, GeneralA)");
-            x0_kernel<<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            if (vec4) x0_kernel<4><<<blocks_for(total / 4), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
+            else x0_kernel<1><<<blocks_for(total), 256, 0, st>>>(in1, in2, s2, out0, per_sample, B, sc);
             NLC_CHECK_LAUNCH();
             if ((rc = nlc_op_project(op, out0, y, B, out1, ws, st))) return rc;
             assemble_kernel<<<blocks_for(total), 256, 0, st>>>(out1, z, in2, s2, per_sample, B, sc.a, sc.c1, sc.c2);
@@ -514,8 +611,12 @@ extern "C" int nlc_ddnm_renoise(nlc_ctx* ctx, const float* x0_t, const float* z,
                                 void* stream) {
     NLC_REQUIRE(ctx && x0_t && z && x_next && n >= 0, "nlc_ddnm_renoise: bad argument");
     if (n == 0) return NLC_OK;
-    renoise_kernel<<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0_t, z, n, sqrtf(at_next),
-                                                                               sqrtf(1.0f - at_next), x_next);
+    if (n % 4 == 0 && aligned16(x0_t, z, x_next))
+        renoise_kernel<4><<<blocks_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            x0_t, z, n, sqrtf(at_next), sqrtf(1.0f - at_next), x_next);
+    else
+        renoise_kernel<1><<<blocks_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0_t, z, n, sqrtf(at_next),
+                                                                                      sqrtf(1.0f - at_next), x_next);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

@@ -100,52 +100,252 @@ __global__ void inpaint_back_kernel(const float* __restrict__ x, const float* __
     }
 }
 
-// ---------------------------------------------------------------- Walsh-Hadamard
-// rows: one CTA per image row, R/2 threads, butterflies h = 1 .. R/2 (the reference's first log2(R) stages)
-__global__ void fwht_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int R) {
-    extern __shared__ float row[];
-    const size_t base = static_cast<size_t>(blockIdx.x) * R;
-    for (int i = threadIdx.x; i < R; i += blockDim.x) row[i] = in[base + i];
-    __syncthreads();
-    for (int h = 1; h < R; h <<= 1) {
-        for (int t = threadIdx.x; t < R / 2; t += blockDim.x) {
-            const int i = (t / h) * 2 * h + (t % h);
-            const float a = row[i], b = row[i + h];
-            row[i] = a + b;
-            row[i + h] = a - b;
-        }
-        __syncthreads();
-    }
-    for (int i = threadIdx.x; i < R; i += blockDim.x) out[base + i] = row[i];
+// ---- 128-bit versions of the kernels above for the shapes the sampler uses (R a multiple of 4): same arithmetic per
+// element, four pixels (colour, inpainting) or one r x r patch in row vectors (SR, r = 2 / 4) per thread
+__device__ __forceinline__ float get4(const float4& v, int e) { return e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void set4(float4& v, int e, float f) {
+    if (e == 0) v.x = f; else if (e == 1) v.y = f; else if (e == 2) v.z = f; else v.w = f;
 }
-// columns: CTA = 32 columns x R rows of one plane; stages h = R .. R^2/2 of the flattened transform, then / R.
-// The epilogue (operators.h) folds the projection's final subtraction / the DDNM step's x_{t-1} assembly into the store.
+template <int MODE>
+__global__ void __launch_bounds__(256) color_vec_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
+                                                         float4* __restrict__ out, long long n4, long long plane4, float u,
+                                                         float s, const float* __restrict__ v0) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long b = i / plane4, p4 = i - b * plane4;
+    const float v[3] = {v0[0], v0[1], v0[2]};
+    const size_t base = static_cast<size_t>(b) * 3 * plane4 + p4;
+    float4 xs[3], meas = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 0 || MODE == 3) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xs[c] = __ldg(x + base + c * plane4);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float dot = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) dot = fmaf(v[c], get4(xs[c], e), dot);
+            set4(meas, e, u * (s * dot));
+        }
+        if (MODE == 0) {
+            out[i] = meas;
+            return;
+        }
+    }
+    const float4 yv = __ldg(y + i);
+    float4 t;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float ye = get4(yv, e);
+        set4(t, e, MODE == 1 ? s * (u * ye) : (MODE == 2 ? (u * ye) * (1.0f / s)
+                                                        : (MODE == 4 ? (u * ye) * s : (u * (get4(meas, e) - ye)) * (1.0f / s))));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float4 o;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float w = v[c] * get4(t, e);
+            set4(o, e, MODE == 3 ? get4(xs[c], e) - w : w);
+        }
+        out[base + c * plane4] = o;
+    }
+}
+template <int RW> struct RowVec;
+template <> struct RowVec<2> { typedef float2 type; };
+template <> struct RowVec<4> { typedef float4 type; };
+template <int MODE, int RW>
+__global__ void __launch_bounds__(256) sr_vec_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                                      float* __restrict__ out, long long n_meas, int R, float u, float s,
+                                                      const float* __restrict__ v0) {
+    typedef typename RowVec<RW>::type VT;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_meas) return;
+    const int yd = R / RW;
+    const int j = static_cast<int>(i % yd), ii = static_cast<int>((i / yd) % yd);
+    const long long bc = i / (static_cast<long long>(yd) * yd);
+    const size_t base = (static_cast<size_t>(bc) * R + static_cast<size_t>(ii) * RW) * R + static_cast<size_t>(j) * RW;
+    float xs[RW * RW];
+    float meas = 0.f;
+    if (MODE == 0 || MODE == 3) {
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+            const VT row = __ldg(reinterpret_cast<const VT*>(x + base + static_cast<size_t>(rr) * R));
+            const float* rp = reinterpret_cast<const float*>(&row);
+#pragma unroll
+            for (int cc = 0; cc < RW; ++cc) xs[rr * RW + cc] = rp[cc];
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < RW * RW; ++k) dot = fmaf(v0[k], xs[k], dot);
+        meas = u * (s * dot);
+        if (MODE == 0) {
+            out[i] = meas;
+            return;
+        }
+    }
+    float t;
+    if (MODE == 1) t = s * (u * y[i]);
+    else if (MODE == 2) t = (u * y[i]) * (1.0f / s);
+    else if (MODE == 4) t = (u * y[i]) * s;
+    else t = (u * (meas - y[i])) * (1.0f / s);
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+        VT row;
+        float* rp = reinterpret_cast<float*>(&row);
+#pragma unroll
+        for (int cc = 0; cc < RW; ++cc) {
+            const float w = v0[rr * RW + cc] * t;
+            rp[cc] = MODE == 3 ? xs[rr * RW + cc] - w : w;
+        }
+        *reinterpret_cast<VT*>(out + base + static_cast<size_t>(rr) * R) = row;
+    }
+}
+// inpainting, four consecutive entries of a plane per thread; pos2k in image order (idx_c)
+template <int MODE>
+__global__ void __launch_bounds__(256) inpaint_back_vec_kernel(const float4* __restrict__ x, const float* __restrict__ y,
+                                                                float4* __restrict__ out, long long n4, long long sample4,
+                                                                const int4* __restrict__ pos2k_planar, int n_kept,
+                                                                float f) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long b = i / sample4, q4 = i - b * sample4;
+    const int4 k4 = __ldg(pos2k_planar + q4);
+    const int ks[4] = {k4.x, k4.y, k4.z, k4.w};
+    const float* yb = y + static_cast<size_t>(b) * n_kept;
+    float4 o, xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (MODE == 3) xv = __ldg(x + i);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float xe = get4(xv, e);
+        if (MODE == 3) set4(o, e, ks[e] >= 0 ? xe - (xe - yb[ks[e]]) : xe);
+        else set4(o, e, ks[e] >= 0 ? __fmul_rn(yb[ks[e]], f) : 0.f);
+    }
+    out[i] = o;
+}
+__global__ void __launch_bounds__(256) identity_vec_kernel(const float4* __restrict__ in, const float4* __restrict__ y,
+                                                            float4* __restrict__ out, long long n4, int mode, float f) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = __ldg(in + i);
+    float4 o = v;
+    if (mode == 3) {
+        const float4 w = __ldg(y + i);
+        o = make_float4(__fsub_rn(v.x, __fsub_rn(v.x, w.x)), __fsub_rn(v.y, __fsub_rn(v.y, w.y)),
+                        __fsub_rn(v.z, __fsub_rn(v.z, w.z)), __fsub_rn(v.w, __fsub_rn(v.w, w.w)));
+    } else if (mode == 4) {
+        o = make_float4(__fmul_rn(v.x, f), __fmul_rn(v.y, f), __fmul_rn(v.z, f), __fmul_rn(v.w, f));
+    }
+    out[i] = o;
+}
+
+// ---------------------------------------------------------------- Walsh-Hadamard
+// rows: one warp per image row, E = R/32 contiguous entries per lane (128-bit loads); butterflies h < E in registers,
+// h >= E across lanes by xor-shuffle — ascending h, the reference's stage order (its first log2(R) stages)
+template <int E>
+__global__ void __launch_bounds__(256) fwht_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         long long n_rows) {
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const size_t off = static_cast<size_t>(row) * (32 * E) + lane * E;
+    float v[E];
+    if constexpr (E >= 4) {
+#pragma unroll
+        for (int i = 0; i < E; i += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(in + off + i);
+            v[i] = t.x, v[i + 1] = t.y, v[i + 2] = t.z, v[i + 3] = t.w;
+        }
+    } else if constexpr (E == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(in + off);
+        v[0] = t.x, v[1] = t.y;
+    } else {
+        v[0] = in[off];
+    }
+#pragma unroll
+    for (int h = 1; h < E; h <<= 1)
+#pragma unroll
+        for (int i = 0; i < E; ++i)
+            if (!(i & h)) {
+                const float a = v[i], b = v[i + h];
+                v[i] = a + b, v[i + h] = a - b;
+            }
+#pragma unroll
+    for (int msk = 1; msk < 32; msk <<= 1) {
+        const bool upper = lane & msk;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const float p = __shfl_xor_sync(0xffffffffu, v[i], msk);
+            v[i] = upper ? p - v[i] : v[i] + p;
+        }
+    }
+    if constexpr (E >= 4) {
+#pragma unroll
+        for (int i = 0; i < E; i += 4)
+            *reinterpret_cast<float4*>(out + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else if constexpr (E == 2) {
+        *reinterpret_cast<float2*>(out + off) = make_float2(v[0], v[1]);
+    } else {
+        out[off] = v[0];
+    }
+}
+// columns: CTA = 32 columns x R rows of one plane staged in shared memory ([R][33]: conflict-free both ways); a warp takes
+// one column at a time, lane l holding rows l, l+32, ...: stages h < 32 (rows) by xor-shuffle, h >= 32 in registers —
+// ascending h again (stages R .. R^2/2 of the flattened transform) — then / R.  The epilogue (operators.h) folds the
+// WH-CS gather / residual, the projection's final subtraction and the DDNM step's x_{t-1} assembly into the store.
+template <int E>
 __global__ void __launch_bounds__(256) fwht_cols_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                         const Epilogue e, int R, int C) {
-    extern __shared__ float tile[];  // [R][32]
+                                                         const Epilogue e, int C) {
+    constexpr int R = 32 * E;
+    extern __shared__ float tile[];  // [R][33]
     const int plane = blockIdx.y, c0 = blockIdx.x * 32;
     const size_t pbase = static_cast<size_t>(plane) * R * R;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < R; r += 8) tile[r * 32 + tx] = in[pbase + static_cast<size_t>(r) * R + c0 + tx];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < R; r += 8) tile[r * 33 + lane] = in[pbase + static_cast<size_t>(r) * R + c0 + lane];
     __syncthreads();
-    for (int h = 1; h < R; h <<= 1) {
-        for (int t = ty; t < R / 2; t += 8) {
-            const int i = (t / h) * 2 * h + (t % h);
-            const float a = tile[i * 32 + tx], b = tile[(i + h) * 32 + tx];
-            tile[i * 32 + tx] = a + b;
-            tile[(i + h) * 32 + tx] = a - b;
+    for (int col = warp * 4; col < warp * 4 + 4; ++col) {
+        float v[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = tile[(lane + 32 * i) * 33 + col];
+#pragma unroll
+        for (int msk = 1; msk < 32; msk <<= 1) {
+            const bool upper = lane & msk;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const float p = __shfl_xor_sync(0xffffffffu, v[i], msk);
+                v[i] = upper ? p - v[i] : v[i] + p;
+            }
         }
-        __syncthreads();
+#pragma unroll
+        for (int h = 1; h < E; h <<= 1)
+#pragma unroll
+            for (int i = 0; i < E; ++i)
+                if (!(i & h)) {
+                    const float a = v[i], b = v[i + h];
+                    v[i] = a + b, v[i + h] = a - b;
+                }
+#pragma unroll
+        for (int i = 0; i < E; ++i) tile[(lane + 32 * i) * 33 + col] = v[i];
     }
+    __syncthreads();
     const float fr = static_cast<float>(R);
-    for (int r = ty; r < R; r += 8) {
-        const size_t o = pbase + static_cast<size_t>(r) * R + c0 + tx;
-        float v = tile[r * 32 + tx] / fr;
+    const int b = plane / C, c = plane % C;
+    for (int r = warp; r < R; r += 8) {
+        const size_t o = pbase + static_cast<size_t>(r) * R + c0 + lane;
+        float v = tile[r * 33 + lane] / fr;
+        if (e.invperm) {
+            const int j = e.invperm[r * R + c0 + lane];
+            const size_t yo = (static_cast<size_t>(b) * e.m + j) * C + c;
+            if (e.ygather) {
+                if (j < e.m) e.ygather[yo] = v;
+                continue;
+            }
+            if (e.ymeas) v = j < e.m ? v - e.ymeas[yo] : 0.f;
+        }
         if (e.base) v = e.alpha * e.base[o] + e.beta * v;
         if (e.add1) v += e.g1 * e.add1[o];
         if (e.add2) {
-            const size_t o2 = e.add2_stride ? static_cast<size_t>(plane / C) * e.add2_stride +
-                                                  (static_cast<size_t>(plane % C) * R + r) * R + c0 + tx : o;
+            const size_t o2 = e.add2_stride ? static_cast<size_t>(b) * e.add2_stride +
+                                                  (static_cast<size_t>(c) * R + r) * R + c0 + lane : o;
             v += e.g2 * e.add2[o2];
         }
         out[o] = v;
@@ -344,16 +544,32 @@ static int to_device(T** dst, const T* src, size_t n) {
     return NLC_OK;
 }
 
-int fwht2d(nlc_op* op, const float* in, float* out, const Epilogue& epi, int B, cudaStream_t st) {
-    const int R = op->R, planes = B * op->C;
-    fwht_rows_kernel<<<planes * R, R / 2 > 256 ? 256 : R / 2, R * sizeof(float), st>>>(in, out, R);
+template <int E>
+static int fwht2d_e(const float* in, float* out, const Epilogue& epi, int planes, int C, cudaStream_t st) {
+    constexpr int R = 32 * E;
+    const long long n_rows = static_cast<long long>(planes) * R;
+    fwht_rows_kernel<E><<<blocks_for(n_rows, 8), 256, 0, st>>>(in, out, n_rows);
     NLC_CHECK_LAUNCH();
-    const size_t smem = static_cast<size_t>(R) * 32 * sizeof(float);
-    NLC_CHECK_CUDA(cudaFuncSetAttribute(fwht_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    fwht_cols_kernel<<<dim3(R / 32, planes), 256, smem, st>>>(out, out, epi, R, op->C);
+    const size_t smem = static_cast<size_t>(R) * 33 * sizeof(float);
+    if (smem > 48 * 1024)
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(fwht_cols_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            static_cast<int>(smem)));
+    // a gathering epilogue writes to its own array, the transform itself stays in `out`
+    fwht_cols_kernel<E><<<dim3(R / 32, planes), 256, smem, st>>>(out, out, epi, C);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
+}
+int fwht2d(nlc_op* op, const float* in, float* out, const Epilogue& epi, int B, cudaStream_t st) {
+    const int planes = B * op->C;
+    switch (op->R / 32) {
+        case 1: return fwht2d_e<1>(in, out, epi, planes, op->C, st);
+        case 2: return fwht2d_e<2>(in, out, epi, planes, op->C, st);
+        case 4: return fwht2d_e<4>(in, out, epi, planes, op->C, st);
+        case 8: return fwht2d_e<8>(in, out, epi, planes, op->C, st);
+        case 16: return fwht2d_e<16>(in, out, epi, planes, op->C, st);
+        case 32: return fwht2d_e<32>(in, out, epi, planes, op->C, st);
+        default: return set_error(NLC_EINVAL, "WH-CS: image sizes 32 .. 1024 (powers of two) are built");
+    }
 }
 
 }  // namespace nlc
@@ -380,8 +596,12 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
                 if (pos2k[j] == 0) { pos2k[j] = static_cast<int>(kept.size()); kept.push_back(static_cast<int>(j)); }
             op->n_kept = static_cast<int>(kept.size());
             op->ydim = op->n_kept;
+            std::vector<int> planar(dim + 3, -1);  // image order, padded to a whole int4
+            for (long long p = 0; p < N; ++p)
+                for (int c = 0; c < d->channels; ++c) planar[c * N + p] = pos2k[p * d->channels + c];
             if ((rc = to_device(&op->idx_a, kept.data(), kept.size() ? kept.size() : 1)) ||
-                (rc = to_device(&op->idx_b, pos2k.data(), pos2k.size()))) return rc;
+                (rc = to_device(&op->idx_b, pos2k.data(), pos2k.size())) ||
+                (rc = to_device(&op->idx_c, planar.data(), planar.size()))) return rc;
         } break;
         case NLC_OP_COLOR:
         case NLC_OP_SR_AVG: {
@@ -453,7 +673,7 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
 
 extern "C" void nlc_op_destroy(nlc_op* op) {
     if (!op) return;
-    cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->v0), cudaFree(op->Vfull), cudaFree(op->lam_s);
+    cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->idx_c), cudaFree(op->v0), cudaFree(op->Vfull), cudaFree(op->lam_s);
     cudaFree(op->Us), cudaFree(op->Vs), cudaFree(op->mult), cudaFree(op->pinv);
     if (op->own2) cudaFree(op->Us2), cudaFree(op->Vs2);
     delete op;
@@ -527,13 +747,32 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
             const long long n_meas = per_ch ? static_cast<long long>(B) * C * (N / (r * r)) : static_cast<long long>(B) * N;
             const unsigned g = blocks_for(n_meas);
             // A reads x = in; At / A_pinv read y = in; project reads both
-            if (mode == 0) needle_kernel<0><<<g, 256, 0, st>>>(in, nullptr, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
-            else if (mode == 1) needle_kernel<1><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
-            else if (mode == 2) needle_kernel<2><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
-            else if (mode == 4)
-                needle_kernel<4><<<g, 256, 0, st>>>(nullptr, in, out, B, C, R, r, per_ch, op->u,
-                                                    op->s / (op->s * op->s + static_cast<float>(eta)), op->v0);
-            else needle_kernel<3><<<g, 256, 0, st>>>(in, y, out, B, C, R, r, per_ch, op->u, op->s, op->v0);
+            const float* xin = (mode == 0 || mode == 3) ? in : nullptr;
+            const float* yin = mode == 0 ? nullptr : (mode == 3 ? y : in);
+            const float sv = mode == 4 ? op->s / (op->s * op->s + static_cast<float>(eta)) : op->s;
+            const bool al16 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) |
+                                reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+#define NLC_MODES(KERNEL, ...)                  \
+    switch (mode) {                             \
+        case 0: KERNEL<0 __VA_ARGS__; break;    \
+        case 1: KERNEL<1 __VA_ARGS__; break;    \
+        case 2: KERNEL<2 __VA_ARGS__; break;    \
+        case 3: KERNEL<3 __VA_ARGS__; break;    \
+        default: KERNEL<4 __VA_ARGS__; break;   \
+    }
+            if (!per_ch && C == 3 && N % 4 == 0 && al16) {
+                const long long n4 = n_meas / 4;
+                NLC_MODES(color_vec_kernel, ><<<blocks_for(n4), 256, 0, st>>>(
+                    reinterpret_cast<const float4*>(xin), reinterpret_cast<const float4*>(yin),
+                    reinterpret_cast<float4*>(out), n4, N / 4, op->u, sv, op->v0))
+            } else if (per_ch && r == 4 && al16) {
+                NLC_MODES(sr_vec_kernel, , 4><<<g, 256, 0, st>>>(xin, yin, out, n_meas, R, op->u, sv, op->v0))
+            } else if (per_ch && r == 2 && al16) {
+                NLC_MODES(sr_vec_kernel, , 2><<<g, 256, 0, st>>>(xin, yin, out, n_meas, R, op->u, sv, op->v0))
+            } else {
+                NLC_MODES(needle_kernel, ><<<g, 256, 0, st>>>(xin, yin, out, B, C, R, r, per_ch, op->u, sv, op->v0))
+            }
+#undef NLC_MODES
             NLC_CHECK_LAUNCH();
         } break;
         case NLC_OP_INPAINT: {
@@ -541,13 +780,24 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
                 if (op->n_kept > 0)
                     inpaint_A_kernel<<<blocks_for(static_cast<long long>(B) * op->n_kept), 256, 0, st>>>(
                         in, out, B, C, static_cast<int>(N), op->idx_a, op->n_kept);
-            } else if (mode == 3) {
-                inpaint_back_kernel<3><<<blocks_for(B * C * N), 256, 0, st>>>(in, y, out, B, C, static_cast<int>(N),
-                                                                             op->idx_b, op->n_kept, 1.f);
             } else {
                 const float f = mode == 4 ? 1.0f / (1.0f * 1.0f + static_cast<float>(eta)) : 1.f;
-                inpaint_back_kernel<1><<<blocks_for(B * C * N), 256, 0, st>>>(nullptr, in, out, B, C, static_cast<int>(N),
-                                                                             op->idx_b, op->n_kept, f);
+                const long long tot = static_cast<long long>(B) * C * N;
+                const bool vec = (C * N) % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+                if (vec && mode == 3)
+                    inpaint_back_vec_kernel<3><<<blocks_for(tot / 4), 256, 0, st>>>(
+                        reinterpret_cast<const float4*>(in), y, reinterpret_cast<float4*>(out), tot / 4, C * N / 4,
+                        reinterpret_cast<const int4*>(op->idx_c), op->n_kept, 1.f);
+                else if (vec)
+                    inpaint_back_vec_kernel<1><<<blocks_for(tot / 4), 256, 0, st>>>(
+                        nullptr, in, reinterpret_cast<float4*>(out), tot / 4, C * N / 4,
+                        reinterpret_cast<const int4*>(op->idx_c), op->n_kept, f);
+                else if (mode == 3)
+                    inpaint_back_kernel<3><<<blocks_for(tot), 256, 0, st>>>(in, y, out, B, C, static_cast<int>(N),
+                                                                           op->idx_b, op->n_kept, 1.f);
+                else
+                    inpaint_back_kernel<1><<<blocks_for(tot), 256, 0, st>>>(nullptr, in, out, B, C, static_cast<int>(N),
+                                                                           op->idx_b, op->n_kept, f);
             }
             NLC_CHECK_LAUNCH();
         } break;
@@ -558,14 +808,14 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
             float* T = ws + static_cast<size_t>(B) * C * N;
             const unsigned g = blocks_for(B * C * N);
             int rc;
-            if (mode == 0) {
-                if ((rc = fwht2d(op, in, F, Epilogue(), B, st))) return rc;
-                whcs_gather_kernel<<<g, 256, 0, st>>>(F, out, B, C, static_cast<int>(N), m, op->idx_a);
-                NLC_CHECK_LAUNCH();
+            if (mode == 0) {  // the gather through the permutation rides on the transform's store
+                Epilogue e;
+                e.invperm = op->idx_a, e.m = m, e.ygather = out;
+                if ((rc = fwht2d(op, in, F, e, B, st))) return rc;
             } else if (mode == 3) {
-                if ((rc = fwht2d(op, in, F, Epilogue(), B, st))) return rc;
-                whcs_scatter_kernel<<<g, 256, 0, st>>>(F, y, T, B, C, static_cast<int>(N), m, op->idx_a, 1.f);
-                NLC_CHECK_LAUNCH();
+                Epilogue e1;  // T = kept ? FWHT(x0) - y : 0
+                e1.invperm = op->idx_a, e1.m = m, e1.ymeas = y;
+                if ((rc = fwht2d(op, in, T, e1, B, st))) return rc;
                 Epilogue e;
                 e.base = in, e.alpha = 1.f, e.beta = -1.f;
                 if ((rc = fwht2d(op, T, out, e, B, st))) return rc;  // out = x0 - fwht(T)
@@ -595,8 +845,15 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
         }
         case NLC_OP_DENOISE: {
             NLC_REQUIRE(mode != 3 || y, "nlc_op: y is null");
-            identity_op_kernel<<<blocks_for(B * C * N), 256, 0, st>>>(in, y, out, B * C * N, mode,
-                                                                     1.0f / (1.0f * 1.0f + static_cast<float>(eta)));
+            const long long tot = static_cast<long long>(B) * C * N;
+            const float f = 1.0f / (1.0f * 1.0f + static_cast<float>(eta));
+            if (tot % 4 == 0 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) |
+                                  reinterpret_cast<uintptr_t>(y)) & 15) == 0)
+                identity_vec_kernel<<<blocks_for(tot / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(in),
+                                                                        reinterpret_cast<const float4*>(y),
+                                                                        reinterpret_cast<float4*>(out), tot / 4, mode, f);
+            else
+                identity_op_kernel<<<blocks_for(tot), 256, 0, st>>>(in, y, out, tot, mode, f);
             NLC_CHECK_LAUNCH();
         } break;
         case NLC_OP_BLOCKCS: {

@@ -1,6 +1,6 @@
 """Operator and DDNM-step kernels against the HBM roofline at the benchmark size
-R = 256, batch 64: CUDA-event time per call (20 calls after 5 warm-ups; every call touches 4-6 tensors of 50 MB each, more
-than the 126 MB L2), algorithmic bytes = the tensors a fused implementation has to read and write once, achieved
+R = 256, batch 64: CUDA-event time per call (20 calls after 5 warm-ups, rotating over four sets of input / output tensors
+so that consecutive calls cannot hit in the 126 MB L2), algorithmic bytes = the tensors a fused implementation has to read and write once, achieved
 GB/s against MEASURED_PEAKS.json's copy bandwidth.  Calls are replayed from a CUDA graph (see timeit).
 
     python scripts/op_bench.py [B] [R]
@@ -67,20 +67,30 @@ def main():
         "deblur_gauss": P.Deblurring(O.gauss_kernel(), C, R, dev),
         "denoising": P.Denoising(C, R, dev),
     }
-    xt = torch.randn(B, C, R, R, device=dev)
-    et = torch.randn(B, 2 * C, R, R, device=dev)
-    z = torch.randn(B, C, R, R, device=dev)
+    NBUF = 4  # rotate over four input / output sets (>= 0.5 GB per round) so that nothing is served from the 126 MB L2
+    xts = [torch.randn(B, C, R, R, device=dev) for _ in range(NBUF)]
+    ets = [torch.randn(B, 2 * C, R, R, device=dev) for _ in range(NBUF)]
+    zs = [torch.randn(B, C, R, R, device=dev) for _ in range(NBUF)]
     print("B=%d R=%d  HBM peak %.0f GB/s (MEASURED_PEAKS.json)" % (B, R, peak))
     print("%-22s %-12s %9s %9s %8s %6s" % ("operator", "call", "ms", "alg MB", "GB/s", "frac"))
     for name, op in ops.items():
-        y = op.A(xt.reshape(B, -1))
+        ys = [op.A(xt.reshape(B, -1)) for xt in xts]
         img = 4.0 * B * d / 1e6
         ym = 4.0 * B * op.ydim / 1e6
-        out = torch.empty(B, d, device=dev)
+        outs = [torch.empty(B, d, device=dev) for _ in range(NBUF)]
+        turn = [0]
+
+        def rot(f):
+            def call():
+                k = turn[0] = (turn[0] + 1) % NBUF
+                return f(k)
+            return call
+
         calls = [
-            ("project", lambda: op.project(xt, y, out=out), 2 * img + ym),            # R x0, R y, W x0_hat
-            ("ddnm_step", lambda: op.ddnm_step(xt, et, z, y, 0.5, 0.6, 0.85, None), 5 * img + ym),   # R xt et z y, W x0 x_next
-            ("ddnm+_step", lambda: op.ddnm_step(xt, et, z, y, 0.5, 0.6, 0.85, 0.1), 5 * img + ym),
+            ("project", rot(lambda k: op.project(xts[k], ys[k], out=outs[k])), 2 * img + ym),  # R x0, R y, W x0_hat
+            ("ddnm_step", rot(lambda k: op.ddnm_step(xts[k], ets[k], zs[k], ys[k], 0.5, 0.6, 0.85, None)),
+             5 * img + ym),                                                              # R xt et z y, W x0 x_next
+            ("ddnm+_step", rot(lambda k: op.ddnm_step(xts[k], ets[k], zs[k], ys[k], 0.5, 0.6, 0.85, 0.1)), 5 * img + ym),
         ]
         for cname, fn, mb in calls:
             ms = timeit(fn)
