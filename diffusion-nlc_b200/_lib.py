@@ -76,6 +76,8 @@ _SIGNATURES = {
     "nlc_conv_out_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "nlc_nhwc_head_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nlc_image_metrics": (_I, [_P, _P, _P, _I, _I64, _P, _P, _P, _P]),
+    "nlc_ssim3d_ws": (_SZ, [_I, _I, _I]),
+    "nlc_ssim3d": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P]),
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),

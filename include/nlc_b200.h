@@ -380,6 +380,12 @@ int nlc_l1_diff_rows(nlc_ctx* ctx, const float* a, const float* b, int B, int64_
  * ---------------------------------------------------------------------------------------------- */
 int nlc_image_metrics(nlc_ctx* ctx, const float* x, const float* orig01, int B, int64_t n, float* sample01_out,
                       float* mse_out, float* l1_out, void* stream);
+/* SSIM as the reference evaluates it (image_sample.py:571-582 ssim_fn -> basicsr _ssim_3d, psnr_ssim.py:171-208): both
+ * images [B,3,H,W] in [0,1] are rounded to 0..255, one 11x11x11 Gaussian window (sigma 1.5, replicate padding) runs
+ * over the [H,W,3] volume, ssim_out[b] = mean of the SSIM map.  workspace: nlc_ssim3d_ws(B,H,W) bytes. */
+size_t nlc_ssim3d_ws(int B, int H, int W);
+int nlc_ssim3d(nlc_ctx* ctx, const float* sample01, const float* orig01, int B, int H, int W, void* workspace,
+               float* ssim_out, void* stream);
 
 #ifdef __cplusplus
 }

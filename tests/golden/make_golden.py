@@ -517,6 +517,50 @@ def operators3():
     print("operators3.pt", os.path.getsize(os.path.join(HERE, "operators3.pt")))
 
 
+def basicsr_psnr_ssim():
+    """basicsr.metrics.psnr_ssim of the reference with its unused skimage import stubbed."""
+    import importlib
+    import types
+    refimport.load()
+    for name in ("skimage", "skimage.metrics"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    if not hasattr(sys.modules["skimage.metrics"], "structural_similarity"):
+        sys.modules["skimage.metrics"].structural_similarity = None
+        sys.modules["skimage"].metrics = sys.modules["skimage.metrics"]
+    return importlib.import_module("basicsr.metrics.psnr_ssim")
+
+
+def reference_ssim_fn(PS, sample, orig):
+    """image_sample.py:571-582 on the CPU: basicsr's `_ssim_3d` hard-codes `.cuda()`; those moves are redirected."""
+    orig_t, orig_m = torch.Tensor.cuda, torch.nn.Module.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        sample = torch.round(sample * 255).to(torch.uint8)
+        orig = torch.round(orig * 255).to(torch.uint8)
+        return [float(PS.calculate_ssim(sample[i], orig[i], crop_border=0, test_y_channel=False))
+                for i in range(len(sample))]
+    finally:
+        torch.Tensor.cuda, torch.nn.Module.cuda = orig_t, orig_m
+
+
+def ssim():
+    """SSIM as the reference's evaluation computes it (image_sample.py:571-582 -> basicsr calculate_ssim, ssim3d) for
+    noisy / smooth / identical image pairs at 32 x 32 and a ragged 40 x 52 -> ssim.pt"""
+    PS = basicsr_psnr_ssim()
+    g = torch.Generator().manual_seed(61)
+    gold = {}
+    for name, (H, W) in (("r32", (32, 32)), ("ragged", (40, 52))):
+        smooth = torch.nn.functional.avg_pool2d(torch.rand(4, 3, H + 4, W + 4, generator=g), 5, 1)
+        noisy = (smooth + 0.05 * torch.randn(4, 3, H, W, generator=g)).clamp(0, 1)
+        rnd = torch.rand(4, 3, H, W, generator=g)
+        cases = dict(noisy_vs_smooth=(noisy, smooth), random_vs_smooth=(rnd, smooth), same=(noisy, noisy.clone()))
+        gold[name] = {k: dict(sample=a, orig=b, ssim=torch.tensor(reference_ssim_fn(PS, a, b), dtype=torch.float64))
+                      for k, (a, b) in cases.items()}
+    torch.save(gold, os.path.join(HERE, "ssim.pt"))
+    print("ssim.pt", os.path.getsize(os.path.join(HERE, "ssim.pt")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()[sys.argv[1]]()

@@ -29,3 +29,32 @@ def test_restoration_metrics_match_the_reference_formulas(shape):
         assert torch.allclose(full["const_f"].cpu(), f.cpu(), rtol=1e-6) and torch.allclose(full["const_b"].cpu(), b.cpu(), rtol=1e-6)
         means = M.reduce_means(full)
         assert abs(means["psnr"] - ref["psnr"].double().mean().item()) < 1e-4
+
+
+def test_ssim_against_reference_golden(golden_dir):
+    """nlc_ssim3d against the reference's own ssim_fn values (tests/golden/ssim.pt: image_sample.py:571-582 -> basicsr
+    `_ssim_3d`).  The reference filters in fp32 with an 11^3 window, the kernel separably: 1e-4 absolute on an index in
+    [0, 1]; identical images give exactly 1."""
+    import os
+    from nlc_b200 import metrics as M
+    g = torch.load(os.path.join(golden_dir, "ssim.pt"), weights_only=True)
+    for size in g.values():
+        for name, case in size.items():
+            got = M.ssim_fn(case["sample"].to(dev), case["orig"].to(dev)).cpu().double()
+            assert (got - case["ssim"]).abs().max() < 1e-4, (name, got, case["ssim"])
+            if name == "same":
+                assert torch.equal(got, torch.ones_like(got))
+
+
+def test_ssim_at_256_against_the_oracle():
+    from nlc_b200 import metrics as M
+    gen = torch.Generator().manual_seed(43)
+    B, H = 4, 256
+    orig = torch.nn.functional.avg_pool2d(torch.rand(B, 3, H + 6, H + 6, generator=gen), 7, 1)
+    sample = (orig + 0.04 * torch.randn(B, 3, H, H, generator=gen)).clamp(0, 1)
+    want = OM.ssim3d(sample, orig)
+    got = M.ssim_fn(sample.to(dev), orig.to(dev)).cpu().double()
+    assert (got - want).abs().max() < 1e-4, (got, want)
+    full = M.restoration_metrics((2 * sample - 1).to(dev), orig.to(dev), ssim=True)
+    assert (full["ssim"].cpu().double() - want).abs().max() < 1e-4
+    assert abs(M.reduce_means(full)["ssim"] - want.mean().item()) < 1e-4

@@ -322,3 +322,13 @@ def test_block_cs_and_general_a(golden_dir):
     for got, want in ((op.A(c["x"]), c["A"]), (op.At(c["A"]), c["At"]), (op.A_pinv(c["A"]), c["A_pinv"]),
                       (op.A_pinv_eta(c["A"], 0.1), c["A_pinv_eta"]), (op.project(c["x0"], c["A"]), c["project"])):
         assert (got - want).abs().max() <= 1e-5 * want.abs().max()  # the SVD is recomputed here
+
+
+def test_ssim(golden_dir):
+    """tests/golden/ssim.pt: image_sample.py:571-582 ssim_fn (uint8 rounding + basicsr's 3-D window SSIM) on the reference."""
+    from oracle import metrics as M
+    g = load(golden_dir, "ssim.pt")
+    for size in g.values():
+        for case in size.values():
+            assert torch.equal(M.ssim3d(case["sample"], case["orig"]), case["ssim"])
+    assert float(g["r32"]["same"]["ssim"].min()) == 1.0

@@ -1,6 +1,8 @@
 """Live pin of the oracle (and of the host-side scheduler mirror) against the unmodified reference imported from
 /root/reference.  Skipped where the reference tree is absent (the GPU box); the committed golden vectors cover
 the same ground there."""
+import os
+
 import pytest
 import torch
 
@@ -175,6 +177,19 @@ def test_block_cs_general_a_denoising(R):
         assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
         assert torch.equal(a.A_pinv_eta(y.clone(), 0.3), b.A_pinv_eta(y.clone(), 0.3))
         assert torch.equal(x0 - a.A_pinv(a.A(x0.clone()) - y), b.project(x0, y))
+
+
+def test_ssim(R):
+    """oracle/metrics.ssim3d against the unmodified basicsr code behind image_sample.py:571-582, live, random sizes."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as MG
+    from oracle import metrics as M
+    PS = MG.basicsr_psnr_ssim()
+    for H, W in ((32, 32), (17, 45), (64, 64)):
+        a, b = torch.rand(2, 3, H, W), torch.rand(2, 3, H, W)
+        b = 0.7 * a + 0.3 * b
+        assert M.ssim3d(a, b).tolist() == MG.reference_ssim_fn(PS, a, b)
 
 
 @pytest.mark.parametrize("name", ["adm_tiny", "adm_alt"])
