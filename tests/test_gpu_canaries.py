@@ -100,3 +100,76 @@ def test_conv_out_head_linear_metrics_and_resampled_residual():
                     resid_mode=mode)
         torch.cuda.synchronize()
         assert intact(fbuf, f.numel()) and (f != SENT).all()
+
+
+@pytest.mark.parametrize("name", ["inpainting", "colorization", "sr2", "sr4", "whcs", "deblur", "denoising", "cs"])
+def test_operator_and_ddnm_kernels_stay_inside_their_buffers(name):
+    """The 128-bit operator kernels, the warp-shuffle FWHT with its fused epilogues, block CS, the fused DDNM / DDNM+ step,
+    SSIM: outputs and the workspace sit between guard bands, called through the C ABI with odd batch sizes."""
+    import ctypes as C
+    from nlc_b200 import _lib, svd_operators as P
+    from oracle import operators as O
+    R, Ch, B = 64, 3, 3
+    gen = torch.Generator().manual_seed(5)
+    mask = (torch.rand(R, R, generator=gen) > 0.3).float()
+    mr = torch.nonzero(mask.reshape(-1) == 0).long().reshape(-1) * 3
+    missing = torch.cat([mr, mr + 1, mr + 2])
+    op = {"inpainting": lambda: P.Inpainting(Ch, R, missing, dev), "colorization": lambda: P.Colorization(R, dev),
+          "sr2": lambda: P.SuperResolution(Ch, R, 2, dev), "sr4": lambda: P.SuperResolution(Ch, R, 4, dev),
+          "whcs": lambda: P.WalshHadamardCS(Ch, R, 4, torch.randperm(R * R, generator=gen), dev),
+          "deblur": lambda: P.Deblurring(O.gauss_kernel(), Ch, R, dev), "denoising": lambda: P.Denoising(Ch, R, dev),
+          "cs": lambda: P.CS(Ch, R, 0.25, dev, V_small=O.hadamard_basis(1024, 3))}[name]()
+    L, st = _lib.lib(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d = Ch * R * R
+    nws = max(int(L.nlc_op_ws(op._h, B)), 16)
+    wbuf, ws = guarded((nws,), torch.uint8)
+    wsp = C.c_void_p(ws.data_ptr())
+    x = torch.randn(B, d, device=dev)
+    ybuf, y = guarded((B, op.ydim))
+    _lib.check(L.nlc_op_A(op._h, x.data_ptr(), B, y.data_ptr(), wsp, st))
+    outs = []
+    for fn, src in ((L.nlc_op_At, y), (L.nlc_op_Apinv, y)):
+        buf, o = guarded((B, d))
+        _lib.check(fn(op._h, src.data_ptr(), B, o.data_ptr(), wsp, st))
+        outs.append((buf, o))
+    buf, o = guarded((B, d))
+    _lib.check(L.nlc_op_Apinv_eta(op._h, y.data_ptr(), B, 0.1, o.data_ptr(), wsp, st))
+    outs.append((buf, o))
+    buf, o = guarded((B, d))
+    _lib.check(L.nlc_op_project(op._h, x.data_ptr(), y.data_ptr(), B, o.data_ptr(), wsp, st))
+    outs.append((buf, o))
+    et, z = torch.randn(B, 2 * d, device=dev), torch.randn(B, d, device=dev)
+    plus_modes = (0,) if name == "cs" else (0, 1)
+    for plus in plus_modes:
+        b0, x0 = guarded((B, d))
+        b1, xn = guarded((B, d))
+        _lib.check(L.nlc_ddnm_step(op._h, x.data_ptr(), et.data_ptr(), 2 * d, z.data_ptr(), y.data_ptr(), B, 0.5, 0.6,
+                                   0.85, 0.1, plus, x0.data_ptr(), xn.data_ptr(), wsp, st))
+        outs += [(b0, x0), (b1, xn)]
+    if name != "cs":
+        coef = _lib.DdnmCoef(a=0.8, sigma_t=0.3, sigma_y=0.2, eta=0.85)
+        for two in (False, True):
+            buf, o = guarded((B, d))
+            if two:
+                _lib.check(L.nlc_op_lambda_noise(op._h, x.data_ptr(), z.data_ptr(), B, C.byref(coef), o.data_ptr(), wsp, st))
+            else:
+                _lib.check(L.nlc_op_lambda(op._h, x.data_ptr(), B, C.byref(coef), o.data_ptr(), wsp, st))
+            outs.append((buf, o))
+    torch.cuda.synchronize()
+    assert intact(ybuf, y.numel()) and intact(wbuf, nws) and (y != SENT).all()
+    for buf, o in outs:
+        assert intact(buf, o.numel()) and torch.isfinite(o).all() and (o != SENT).all()
+
+
+def test_ssim_stays_inside_its_buffers():
+    import ctypes as C
+    from nlc_b200 import _lib
+    L, st = _lib.lib(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (B, H, W) in ((3, 40, 52), (2, 16, 32), (1, 7, 5)):
+        a, b = torch.rand(B, 3, H, W, device=dev), torch.rand(B, 3, H, W, device=dev)
+        nws = int(L.nlc_ssim3d_ws(B, H, W))
+        wbuf, ws = guarded((nws,), torch.uint8)
+        obuf, out = guarded((B,))
+        _lib.check(L.nlc_ssim3d(_lib.ctx(0), a.data_ptr(), b.data_ptr(), B, H, W, C.c_void_p(ws.data_ptr()), out.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert intact(wbuf, nws) and intact(obuf, B) and ((out > -1) & (out <= 1)).all()
