@@ -1,0 +1,116 @@
+"""Checkpoint ingestion: the three file formats the reference's drivers read, turned into the plain
+`state_dict` the nlc_b200 network classes take (`load_state_dict` keeps the reference's key names).
+
+* guided-diffusion / ADM `.pt`: a plain state dict (image_sample.py:757-771 via src/dist_util.py:57-77, which only adds an
+  MPI broadcast around `torch.load`).
+* DDIM `.ckpt`: a list `[model_state, optimizer_state, epoch, step, ema_state]` written from an `nn.DataParallel` model;
+  the reference loads element 0 and then overwrites every trainable parameter with the EMA copy in the last element
+  (run_image_experiment.py:195-209).
+* EDM network pickles: `pickle.load(f)['ema']` is an `EDMPrecond` whose `.model` is the SongUNet
+  (edm_image_sample.py:152-156).  Those pickles embed the defining module's SOURCE and re-execute it on load
+  (torch_utils/persistence.py); here they are read with a restricted unpickler that never executes it: persistent objects
+  come back as inert records of their `__dict__`, from which the parameter / buffer tree is walked.
+"""
+import collections
+import io
+import pickle
+
+import torch
+
+
+def load_state_dict(path, **kwargs):
+    """src/dist_util.py:57-77 without the MPI broadcast (one process per GPU reads its own copy)."""
+    kwargs.setdefault("map_location", "cpu")
+    with open(path, "rb") as f:
+        return torch.load(io.BytesIO(f.read()), **kwargs)
+
+
+def _strip_module(sd):
+    return collections.OrderedDict((k[7:] if k.startswith("module.") else k, v) for k, v in sd.items())
+
+
+def eps_state_dict(ckpt, trainable=None):
+    """The state dict the reference ends up with after run_image_experiment.py:195-209: a plain dict is returned as is; for
+    a DDIM list checkpoint the DataParallel prefix is dropped and the EMA values replace the parameters (`trainable`:
+    optional set of names to restrict the overwrite to, the reference's `requires_grad` filter; buffers are never in the EMA
+    dict)."""
+    if not isinstance(ckpt, (list, tuple)):
+        return ckpt
+    sd = _strip_module(ckpt[0])
+    ema = _strip_module(ckpt[-1])
+    for name, value in ema.items():
+        if name in sd and (trainable is None or name in trainable):
+            sd[name] = value.detach().clone() if torch.is_tensor(value) else value
+    return sd
+
+
+def load_eps_model(model, ckpt_file):
+    """`model.load_state_dict` from a `.pt` / `.ckpt` file, EMA weights applied (run_image_experiment.py:190-212)."""
+    return model.load_state_dict(eps_state_dict(load_state_dict(ckpt_file, weights_only=False)))
+
+
+# ------------------------------------------------------------------------------------------------ EDM pickles
+class _Record:
+    """What a persistent object (torch_utils.persistence) is read back as: its class name and its `__dict__`."""
+
+    def __init__(self, meta):
+        self.class_name = meta.get("class_name")
+        self.state = meta.get("state") or {}
+
+    def __getattr__(self, name):  # obj.model, obj.sigma_data ... as on the live object
+        state = self.__dict__.get("state", {})
+        if name in state:
+            return state[name]
+        if name in state.get("_modules", {}):
+            return state["_modules"][name]
+        raise AttributeError(name)
+
+
+class _AttrDict(dict):
+    __getattr__ = dict.get
+
+
+class _RestrictedUnpickler(pickle.Unpickler):
+    _ALLOWED_PREFIXES = ("torch", "collections", "numpy", "builtins", "_codecs")
+
+    def find_class(self, module, name):
+        if module == "torch_utils.persistence" and name == "_reconstruct_persistent_obj":
+            return _Record
+        if module.startswith("dnnlib") and name == "EasyDict":
+            return _AttrDict
+        if module.split(".")[0] in self._ALLOWED_PREFIXES:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError("refusing to import %s.%s from a checkpoint" % (module, name))
+
+
+def _module_state(obj):
+    return obj.state if isinstance(obj, _Record) else obj.__dict__
+
+
+def module_state_dict(obj, prefix=""):
+    """`nn.Module.state_dict()` of a module tree read back as records: parameters, persistent buffers, sub-modules."""
+    st = _module_state(obj)
+    sd = collections.OrderedDict()
+    for name, p in (st.get("_parameters") or {}).items():
+        if p is not None:
+            sd[prefix + name] = p.detach()
+    skip = st.get("_non_persistent_buffers_set") or set()
+    for name, b in (st.get("_buffers") or {}).items():
+        if b is not None and name not in skip:
+            sd[prefix + name] = b
+    for name, sub in (st.get("_modules") or {}).items():
+        if sub is not None:
+            sd.update(module_state_dict(sub, prefix + name + "."))
+    return sd
+
+
+def edm_state_dict(path_or_file, key="ema"):
+    """State dict of the SongUNet inside an EDM network pickle (edm_image_sample.py:152-156:
+    `pickle.load(f)['ema'].model.state_dict()`), without executing the source code the pickle carries."""
+    if hasattr(path_or_file, "read"):
+        data = _RestrictedUnpickler(path_or_file).load()
+    else:
+        with open(path_or_file, "rb") as f:
+            data = _RestrictedUnpickler(f).load()
+    net = data[key]
+    return module_state_dict(net.model)

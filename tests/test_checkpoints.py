@@ -1,0 +1,104 @@
+"""Checkpoint ingestion (CPU): the DDIM list-with-EMA format (run_image_experiment.py:195-209) and EDM
+network pickles (edm_image_sample.py:152-156) against what the reference's own loading code produces."""
+import io
+import pickle
+import sys
+import types
+
+import pytest
+import torch
+
+import nlc_b200  # noqa: F401
+from nlc_b200 import checkpoints as CK
+
+
+class _Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv = torch.nn.Conv2d(3, 4, 3)
+        self.bn = torch.nn.BatchNorm2d(4)
+        self.frozen = torch.nn.Linear(2, 2)
+        for p in self.frozen.parameters():
+            p.requires_grad = False
+
+
+def test_ddim_list_checkpoint_with_ema(tmp_path):
+    torch.manual_seed(0)
+    net = torch.nn.DataParallel(_Net())
+    ema = {n: torch.randn_like(p) for n, p in net.module.named_parameters() if p.requires_grad}
+    path = tmp_path / "model.ckpt"
+    torch.save([net.state_dict(), {"opt": 1}, 3, 1234, ema], path)
+    # what run_image_experiment.py:195-209 does
+    ref = torch.nn.DataParallel(_Net())
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
+    ref.load_state_dict(ckpt[0], strict=True)
+    ref = ref.module
+    for name, param in ref.named_parameters():
+        if param.requires_grad:
+            param.data.copy_(ckpt[-1][name].data)
+    trainable = {n for n, p in _Net().named_parameters() if p.requires_grad}
+    got = CK.eps_state_dict(CK.load_state_dict(str(path), weights_only=False), trainable=trainable)
+    want = ref.state_dict()
+    assert list(got) == list(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    plain = {"a": torch.ones(2)}
+    assert CK.eps_state_dict(plain) is plain
+
+
+def _fake_persistence():
+    """A stand-in for the vendored torch_utils.persistence: objects pickle as (_reconstruct_persistent_obj, (meta,))."""
+    mod = types.ModuleType("torch_utils.persistence")
+
+    def _reconstruct_persistent_obj(meta):
+        raise AssertionError("the checkpoint reader must not execute the pickle's own reconstruction code")
+
+    _reconstruct_persistent_obj.__module__ = "torch_utils.persistence"
+    _reconstruct_persistent_obj.__qualname__ = "_reconstruct_persistent_obj"
+    mod._reconstruct_persistent_obj = _reconstruct_persistent_obj
+    pkg = types.ModuleType("torch_utils")
+    pkg.persistence = mod
+    return pkg, mod
+
+
+def test_edm_pickle_without_executing_its_source():
+    pkg, mod = _fake_persistence()
+    sys.modules["torch_utils"], sys.modules["torch_utils.persistence"] = pkg, mod
+
+    class Persistent:
+        def __init__(self, class_name, state):
+            self.meta = dict(type="class", version=6, module_src="raise SystemExit('executed!')", class_name=class_name,
+                             state=state)
+
+        def __reduce__(self):
+            return (mod._reconstruct_persistent_obj, (self.meta,))
+
+    def module_state(params=None, buffers=None, modules=None, **extra):
+        st = dict(training=False, _parameters=dict(params or {}), _buffers=dict(buffers or {}),
+                  _non_persistent_buffers_set=set(), _modules=dict(modules or {}))
+        st.update(extra)
+        return st
+
+    torch.manual_seed(1)
+    w, b, rf = torch.nn.Parameter(torch.randn(4, 3, 3, 3)), torch.nn.Parameter(torch.randn(4)), torch.ones(2, 2)
+    conv = Persistent("Conv2d", module_state(params=dict(weight=w, bias=b), buffers=dict(resample_filter=rf)))
+    lin = Persistent("Linear", module_state(params=dict(weight=torch.nn.Parameter(torch.randn(5, 4)), bias=None)))
+    enc = torch.nn.ModuleDict()  # a real torch container between persistent objects, as in SongUNet.enc
+    enc.__dict__["_modules"]["32x32_conv"] = conv
+    unet = Persistent("SongUNet", module_state(modules=dict(map_layer0=lin, enc=enc), img_resolution=32))
+    precond = Persistent("EDMPrecond", module_state(modules=dict(model=unet), sigma_data=0.5))
+    try:
+        blob = pickle.dumps(dict(ema=precond, loss_fn=None))
+    finally:
+        del sys.modules["torch_utils"], sys.modules["torch_utils.persistence"]
+    sd = CK.edm_state_dict(io.BytesIO(blob))
+    assert list(sd) == ["map_layer0.weight", "enc.32x32_conv.weight", "enc.32x32_conv.bias", "enc.32x32_conv.resample_filter"]
+    assert torch.equal(sd["enc.32x32_conv.weight"], w) and torch.equal(sd["enc.32x32_conv.resample_filter"], rf)
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("true",))
+
+    with pytest.raises(pickle.UnpicklingError):
+        CK.edm_state_dict(io.BytesIO(pickle.dumps(dict(ema=Evil()))))
