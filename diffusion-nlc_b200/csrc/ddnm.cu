@@ -15,6 +15,7 @@
 //   Deblurring                       per-step factor tables over the R x R spectral positions + the separable GEMM chain
 // All HBM-bound fp32.
 #include <math.h>
+#include <string.h>
 
 #include "operators.h"
 
@@ -94,22 +95,97 @@ __device__ __forceinline__ void ldiv(const int* p, int* dst) {
 }
 
 // ---------------------------------------------------------------- colourisation / average-pool SR
+// One needle = the K entries one measurement is taken from (a pixel's channels / an r x r patch).  V_small (K x K) comes
+// in as a kernel argument for K <= 16, so its entries are constant-bank operands of the FMAs (no load instruction at all);
+// r = 8 (K = 64) stages it in shared memory.
+template <int K> struct NeedleGeom { static constexpr int RW = K == 16 ? 4 : (K == 4 ? 2 : 1); };
+template <int K> struct VMat { float v[K <= 16 ? K * K : 1]; };
+struct NeedleTerms { float lam0, d10, d20, d1N, d2N; };
+
+// in: n = v | x_t, e = eps | e_t, zz = - | z, yv = measurement.  out: o = result | x_next; n is overwritten by x0_t (M_STEP)
+template <int K, typename VT>
+__device__ __forceinline__ void needle_math(int mode, float* n, const float* e, float* zz, float yv, const VT& V, float u,
+                                            float s, const Step& sc, const NeedleTerms& T, float* o) {
+    constexpr int UN = K <= 16 ? K : 1;  // K = 64 keeps its needles in local memory instead of 256 registers
+    if (mode == M_LAMBDA) {
+        float w[K];
+#pragma unroll UN
+        for (int kp = 0; kp < K; ++kp) {
+            float acc = 0.f;
+#pragma unroll UN
+            for (int k = 0; k < K; ++k) acc = fmaf(V[k * K + kp], n[k], acc);  // V^T n
+            w[kp] = kp == 0 ? __fmul_rn(acc, T.lam0) : acc;
+        }
+#pragma unroll UN
+        for (int j = 0; j < K; ++j) {
+            float acc = 0.f;
+#pragma unroll UN
+            for (int kp = 0; kp < K; ++kp) acc = fmaf(V[j * K + kp], w[kp], acc);
+            o[j] = acc;
+        }
+        return;
+    }
+    if (mode == M_NOISE) {
+#pragma unroll UN
+        for (int k = 0; k < K; ++k) zz[k] = n[k];
+    } else {
+        float dot = 0.f;
+#pragma unroll UN
+        for (int k = 0; k < K; ++k) n[k] = x0_of(n[k], e[k], sc);
+#pragma unroll UN
+        for (int k = 0; k < K; ++k) dot = fmaf(V[k * K], n[k], dot);  // v0 = first column of V
+        const float meas = u * (s * dot);                              // A x0
+        const float t = (u * (meas - yv)) * (1.0f / s);                // spectral A^+(A x0 - y)
+        if (!sc.plus) {
+#pragma unroll UN
+            for (int k = 0; k < K; ++k) {
+                const float x0h = n[k] - V[k * K] * t;
+                o[k] = __fadd_rn(__fadd_rn(__fmul_rn(sc.a, x0h), __fmul_rn(sc.c1, zz[k])), __fmul_rn(sc.c2, e[k]));
+            }
+            return;
+        }
+        // A^+(A x0 - y) = v0 t lies along the first right singular vector, so Lambda (V diag(lambda) V^T) scales it by lambda_0
+        const float tl = __fmul_rn(t, T.lam0);
+#pragma unroll UN
+        for (int k = 0; k < K; ++k) o[k] = n[k] - V[k * K] * tl;  // x0_hat
+    }
+    // V (d1 o z + d2 o e): channel / patch entry k stands in for component k (:575-581, 698-699)
+#pragma unroll UN
+    for (int k = 0; k < K; ++k)
+        zz[k] = __fadd_rn(__fmul_rn(zz[k], k == 0 ? T.d10 : T.d1N), __fmul_rn(e[k], k == 0 ? T.d20 : T.d2N));
+#pragma unroll UN
+    for (int j = 0; j < K; ++j) {
+        float acc = 0.f;
+#pragma unroll UN
+        for (int k = 0; k < K; ++k) acc = fmaf(V[j * K + k], zz[k], acc);
+        o[j] = mode == M_NOISE ? acc : __fadd_rn(__fmul_rn(sc.a, o[j]), acc);
+    }
+}
+__device__ __forceinline__ NeedleTerms needle_terms(float s, const Step& sc) {
+    NeedleTerms T;
+    float lamN;
+    ddnm_terms(s, sc.coef, T.lam0, T.d10, T.d20);
+    ddnm_terms(0.f, sc.coef, lamN, T.d1N, T.d2N);
+    return T;
+}
+
 // One thread per needle.  in1 = v | xt, in2 = eps | et (sample stride in2_stride), out1 = result | x_next, out0 = x0_t.
 // RW = contiguous floats per needle row: the r x r patch of SR is read as r row vectors (r = 2, 4), colour planes scalar.
-template <int K> struct NeedleGeom { static constexpr int RW = K == 16 ? 4 : (K == 4 ? 2 : 1); };
-
 template <int K>
 __global__ void __launch_bounds__(128) needle_ddnm_kernel(int mode, const float* __restrict__ in1,
                                                            const float* __restrict__ in2, long long in2_stride,
                                                            const float* __restrict__ z, const float* __restrict__ y,
                                                            float* __restrict__ out1, float* __restrict__ out0, int B, int C,
                                                            int R, int r, int per_ch, float u, float s,
+                                                           const __grid_constant__ VMat<K> Vc,
                                                            const float* __restrict__ Vfull, const Step sc, int vec_ok) {
-    constexpr int UN = K <= 16 ? K : 1;  // r = 8 (K = 64) keeps its needles in local memory instead of 256 registers
+    constexpr int UN = K <= 16 ? K : 1;
     constexpr int RW = NeedleGeom<K>::RW;
-    __shared__ __align__(16) float V[K * K];
-    for (int t = threadIdx.x; t < K * K; t += blockDim.x) V[t] = Vfull[t];
-    __syncthreads();
+    __shared__ __align__(16) float Vs[K <= 16 ? 1 : K * K];
+    if constexpr (K > 16) {
+        for (int t = threadIdx.x; t < K * K; t += blockDim.x) Vs[t] = Vfull[t];
+        __syncthreads();
+    }
     const int yd = R / r;
     const long long plane = static_cast<long long>(R) * R;
     const long long per_sample = per_ch ? static_cast<long long>(C) * yd * yd : plane;
@@ -155,72 +231,51 @@ __global__ void __launch_bounds__(128) needle_ddnm_kernel(int mode, const float*
             for (int k = 0; k < K; ++k) p[base + off(k)] = src[k];
         }
     };
-    float lam0, d10, d20, lamN, d1N, d2N;
-    ddnm_terms(s, sc.coef, lam0, d10, d20);
-    ddnm_terms(0.f, sc.coef, lamN, d1N, d2N);
-
-    float n[K], o[K];
-    if (mode == M_LAMBDA) {
-        load(in1, base, n);
-        float w[K];
-#pragma unroll UN
-        for (int kp = 0; kp < K; ++kp) {
-            float acc = 0.f;
-#pragma unroll UN
-            for (int k = 0; k < K; ++k) acc = fmaf(V[k * K + kp], n[k], acc);  // V^T n
-            w[kp] = kp == 0 ? __fmul_rn(acc, lam0) : acc;
-        }
-#pragma unroll UN
-        for (int j = 0; j < K; ++j) {
-            float acc = 0.f;
-#pragma unroll UN
-            for (int kp = 0; kp < K; ++kp) acc = fmaf(V[j * K + kp], w[kp], acc);
-            o[j] = acc;
-        }
-        store(out1, o);
-        return;
-    }
-    float e[K], zz[K];
-    load(in2, base2, e);
-    if (mode == M_NOISE) {
-        load(in1, base, zz);
-    } else {
-        load(in1, base, n);
-        load(z, base, zz);
-        float dot = 0.f;
-#pragma unroll UN
-        for (int k = 0; k < K; ++k) n[k] = x0_of(n[k], e[k], sc);
-        store(out0, n);
-#pragma unroll UN
-        for (int k = 0; k < K; ++k) dot = fmaf(V[k * K], n[k], dot);  // v0 = first column of V
-        const float meas = u * (s * dot);                              // A x0
-        const float t = (u * (meas - y[i])) * (1.0f / s);              // spectral A^+(A x0 - y)
-        if (!sc.plus) {
-#pragma unroll UN
-            for (int k = 0; k < K; ++k) {
-                const float x0h = n[k] - V[k * K] * t;
-                o[k] = __fadd_rn(__fadd_rn(__fmul_rn(sc.a, x0h), __fmul_rn(sc.c1, zz[k])), __fmul_rn(sc.c2, e[k]));
-            }
-            store(out1, o);
-            return;
-        }
-        // A^+(A x0 - y) = v0 t lies along the first right singular vector, so Lambda (V diag(lambda) V^T) scales it by lambda_0
-        const float tl = __fmul_rn(t, lam0);
-#pragma unroll UN
-        for (int k = 0; k < K; ++k) n[k] = n[k] - V[k * K] * tl;  // x0_hat
-    }
-    // V (d1 o z + d2 o e): channel / patch entry k stands in for component k (:575-581, 698-699)
-#pragma unroll UN
-    for (int k = 0; k < K; ++k)
-        zz[k] = __fadd_rn(__fmul_rn(zz[k], k == 0 ? d10 : d1N), __fmul_rn(e[k], k == 0 ? d20 : d2N));
-#pragma unroll UN
-    for (int j = 0; j < K; ++j) {
-        float acc = 0.f;
-#pragma unroll UN
-        for (int k = 0; k < K; ++k) acc = fmaf(V[j * K + k], zz[k], acc);
-        o[j] = mode == M_NOISE ? acc : __fadd_rn(__fmul_rn(sc.a, n[j]), acc);
-    }
+    const NeedleTerms T = needle_terms(s, sc);
+    float n[K], e[K], zz[K], o[K];
+    load(in1, base, n);
+    if (mode != M_LAMBDA) load(in2, base2, e);
+    if (mode == M_STEP) load(z, base, zz);
+    const float yv = mode == M_STEP ? y[i] : 0.f;
+    if constexpr (K <= 16) needle_math<K>(mode, n, e, zz, yv, Vc.v, u, s, sc, T, o);
+    else needle_math<K>(mode, n, e, zz, yv, Vs, u, s, sc, T, o);
+    if (mode == M_STEP) store(out0, n);
     store(out1, o);
+}
+// colourisation, four adjacent pixels per thread: every plane moves as 128-bit vectors
+__global__ void __launch_bounds__(256) color_ddnm_vec_kernel(int mode, const float* __restrict__ in1,
+                                                              const float* __restrict__ in2, long long in2_stride,
+                                                              const float* __restrict__ z, const float* __restrict__ y,
+                                                              float* __restrict__ out1, float* __restrict__ out0,
+                                                              long long n4, long long plane, float u, float s,
+                                                              const __grid_constant__ VMat<3> Vc, const Step sc) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const long long b = (i * 4) / plane, p = i * 4 - b * plane;
+    const size_t base = static_cast<size_t>(b) * 3 * plane + p, base2 = static_cast<size_t>(b) * in2_stride + p;
+    const NeedleTerms T = needle_terms(s, sc);
+    Pack<4> a1[3], a2[3], zv[3], yv, x0[3], o[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        a1[c] = ldv<4>(in1 + base + c * plane);
+        if (mode != M_LAMBDA) a2[c] = ldv<4>(in2 + base2 + c * plane);
+        if (mode == M_STEP) zv[c] = ldv<4>(z + base + c * plane);
+    }
+    if (mode == M_STEP) yv = ldv<4>(y + b * plane + p);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float n[3], e[3], zz[3], oo[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) n[c] = a1[c].v[k], e[c] = a2[c].v[k], zz[c] = zv[c].v[k];
+        needle_math<3>(mode, n, e, zz, yv.v[k], Vc.v, u, s, sc, T, oo);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x0[c].v[k] = n[c], o[c].v[k] = oo[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        if (mode == M_STEP) stv<4>(out0 + base + c * plane, x0[c]);
+        stv<4>(out1 + base + c * plane, o[c]);
+    }
 }
 
 // ---------------------------------------------------------------- inpainting / denoising (V is a permutation / identity)
@@ -408,8 +463,18 @@ static int launch_needle(nlc_op* op, int mode, const float* in1, const float* in
     const long long plane = static_cast<long long>(op->R) * op->R;
     const long long n = per_ch ? static_cast<long long>(B) * op->C * (plane / (r * r)) : static_cast<long long>(B) * plane;
     const int vec_ok = aligned16(in1, in2, z, out1, out0) && s2 % 4 == 0 && op->R % 4 == 0;
+    VMat<K> Vc;
+    if (K <= 16) memcpy(Vc.v, op->Vfull_host, sizeof(float) * K * K);
+    if constexpr (K == 3) {
+        if (!per_ch && vec_ok && plane % 4 == 0 && aligned16(y)) {
+            color_ddnm_vec_kernel<<<blocks_for(n / 4), 256, 0, st>>>(mode, in1, in2, s2, z, y, out1, out0, n / 4, plane,
+                                                                     op->u, op->s, Vc, sc);
+            NLC_CHECK_LAUNCH();
+            return NLC_OK;
+        }
+    }
     needle_ddnm_kernel<K><<<blocks_for(n, 128), 128, 0, st>>>(mode, in1, in2, s2, z, y, out1, out0, B, op->C, op->R, r,
-                                                               per_ch, op->u, op->s, op->Vfull, sc, vec_ok);
+                                                               per_ch, op->u, op->s, Vc, op->Vfull, sc, vec_ok);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

@@ -16,6 +16,7 @@
 //   GeneralA (:173-208)     dense U, s, V of an arbitrary small A: two fp32 GEMMs around a per-column scale
 //   Denoising (:442-476)    A = I
 // All kernels are HBM-bound fp32 (the separable pair adds eight small fp32 GEMMs per image-channel).
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -614,6 +615,8 @@ extern "C" int nlc_op_create(nlc_ctx* ctx, const nlc_op_desc* d, nlc_op** out) {
             if ((rc = to_device(&op->v0, v0.data(), K)) ||
                 (rc = to_device(&op->Vfull, d->V_small_host, static_cast<size_t>(K) * K))) return rc;
             op->K = K;
+            op->Vfull_host = static_cast<float*>(malloc(sizeof(float) * K * K));
+            memcpy(op->Vfull_host, d->V_small_host, sizeof(float) * K * K);
             op->ydim = d->task == NLC_OP_COLOR ? N : d->channels * (N / (d->ratio * d->ratio));
         } break;
         case NLC_OP_WHCS: {
@@ -676,6 +679,7 @@ extern "C" void nlc_op_destroy(nlc_op* op) {
     cudaFree(op->idx_a), cudaFree(op->idx_b), cudaFree(op->idx_c), cudaFree(op->v0), cudaFree(op->Vfull), cudaFree(op->lam_s);
     cudaFree(op->Us), cudaFree(op->Vs), cudaFree(op->mult), cudaFree(op->pinv);
     if (op->own2) cudaFree(op->Us2), cudaFree(op->Vs2);
+    free(op->Vfull_host);
     delete op;
 }
 

@@ -14,6 +14,7 @@ struct nlc_op {
     float u, s;
     float* v0;    // COLOR: 3 ; SR_AVG: r*r
     float* Vfull; // COLOR / SR_AVG: the whole K x K V_small, row-major (Lambda / Lambda_noise rotate with it)
+    float* Vfull_host;  // the same on the host (handed to the kernels by value for K <= 16)
     int K;        // needle length: 3 (colour) or r*r
     float *Us, *Vs, *mult, *pinv;  // SEPARABLE (left factors; also right factors unless Us2 / Vs2 are set)
     float *Us2, *Vs2;              // SEPARABLE: right factors (== Us / Vs for one-kernel operators)
