@@ -333,23 +333,7 @@ __global__ void __launch_bounds__(256) fwht_cols_kernel(const float* __restrict_
     for (int r = warp; r < R; r += 8) {
         const size_t o = pbase + static_cast<size_t>(r) * R + c0 + lane;
         float v = tile[r * 33 + lane] / fr;
-        if (e.invperm) {
-            const int j = e.invperm[r * R + c0 + lane];
-            const size_t yo = (static_cast<size_t>(b) * e.m + j) * C + c;
-            if (e.ygather) {
-                if (j < e.m) e.ygather[yo] = v;
-                continue;
-            }
-            if (e.ymeas) v = j < e.m ? v - e.ymeas[yo] : 0.f;
-        }
-        if (e.base) v = e.alpha * e.base[o] + e.beta * v;
-        if (e.add1) v += e.g1 * e.add1[o];
-        if (e.add2) {
-            const size_t o2 = e.add2_stride ? static_cast<size_t>(b) * e.add2_stride +
-                                                  (static_cast<size_t>(c) * R + r) * R + c0 + lane : o;
-            v += e.g2 * e.add2[o2];
-        }
-        out[o] = v;
+        if (fwht_epilogue(e, v, b, c, C, R, r, c0 + lane, o)) out[o] = v;
     }
 }
 // y[b][j*C + c] = F[b][c][perm[j]], j < m  (gather through invperm: thread per spectral entry q)
@@ -562,6 +546,14 @@ static int fwht2d_e(const float* in, float* out, const Epilogue& epi, int planes
 }
 int fwht2d(nlc_op* op, const float* in, float* out, const Epilogue& epi, int B, cudaStream_t st) {
     const int planes = B * op->C;
+    // NLC_FWHT_CLUSTER=1: the one-kernel cluster / DSMEM transform (fwht_cluster.cu).  Bit-identical, half the HBM traffic,
+    // but measured 2x slower than the two streaming kernels below (profiles/r01m_fwht_cluster_experiment.md), so opt-in.
+    const char* env = getenv("NLC_FWHT_CLUSTER");
+    const bool use_cluster = env && env[0] == '1';
+    if (use_cluster) {
+        const int rc = fwht2d_cluster(in, out, epi, planes, op->C, op->R, st);
+        if (rc != 1) return rc;
+    }
     switch (op->R / 32) {
         case 1: return fwht2d_e<1>(in, out, epi, planes, op->C, st);
         case 2: return fwht2d_e<2>(in, out, epi, planes, op->C, st);

@@ -44,6 +44,35 @@ struct Epilogue {
     float* ygather = nullptr;
 };
 
+#ifdef __CUDACC__
+// Shared by the two FWHT implementations: what happens to transform value `v` of plane (b, c), entry (r, col), flat index
+// o.  Returns false when nothing is to be stored at o (the gather wrote elsewhere).
+__device__ __forceinline__ bool fwht_epilogue(const Epilogue& e, float& v, int b, int c, int C, int R, int r, int col,
+                                              size_t o) {
+    if (e.invperm) {
+        const int j = e.invperm[r * R + col];
+        const size_t yo = (static_cast<size_t>(b) * e.m + j) * C + c;
+        if (e.ygather) {
+            if (j < e.m) e.ygather[yo] = v;
+            return false;
+        }
+        if (e.ymeas) v = j < e.m ? v - e.ymeas[yo] : 0.f;
+    }
+    if (e.base) v = e.alpha * e.base[o] + e.beta * v;
+    if (e.add1) v += e.g1 * e.add1[o];
+    if (e.add2) {
+        const size_t o2 = e.add2_stride ? static_cast<size_t>(b) * e.add2_stride + (static_cast<size_t>(c) * R + r) * R + col : o;
+        v += e.g2 * e.add2[o2];
+    }
+    return true;
+}
+#endif
+
+// One-kernel 2-D FWHT for R = 64 .. 512 (fwht_cluster.cu): a thread-block cluster holds one plane in distributed shared
+// memory.  Returns NLC_OK, or 1 when the size is not covered (the caller falls back to the two-kernel transform).
+// Experimental (opt-in with NLC_FWHT_CLUSTER=1): correct and bit-identical, but slower than the two-kernel path.
+int fwht2d_cluster(const float* in, float* out, const Epilogue& epi, int planes, int C, int R, cudaStream_t st);
+
 // orthonormal 2-D fast Walsh-Hadamard transform of B*C planes (the reference's 1-D FWHT over R^2 entries)
 int fwht2d(nlc_op* op, const float* in, float* out, const Epilogue& epi, int B, cudaStream_t st);
 

@@ -130,3 +130,42 @@ def test_block_cs_and_general_a(golden_dir):
     assert (op.project(p, y) - p).abs().max() < 5e-5
     lhs, rhs = (op.A(x) * y).sum(dim=1), (x * op.At(y)).sum(dim=1)
     assert ((lhs - rhs).abs() / lhs.abs().clamp_min(1.0)).max() < 1e-3
+
+
+@pytest.mark.parametrize("R", [64, 128, 256, 512])
+def test_cluster_fwht_equals_two_kernel_fwht(R):
+    """The one-kernel transform (thread-block cluster, the plane in distributed shared memory; fwht_cluster.cu) runs the
+    same butterflies in the same stage order as the two-kernel one: results are bit-identical, for every entry point
+    that goes through it; at R = 128 both are also checked against the oracle's spectral restatement."""
+    from nlc_b200 import svd_operators as P
+    gen = torch.Generator().manual_seed(R)
+    B, C = 3, 3
+    perm = torch.randperm(R * R, generator=gen)
+    op = P.WalshHadamardCS(C, R, 4, perm, dev)
+    x = (torch.rand(B, C * R * R, generator=gen) * 2 - 1).to(dev)
+    x0 = torch.randn(B, C, R, R, generator=gen).to(dev)
+    et, z = torch.randn(B, 2 * C, R, R, generator=gen).to(dev), torch.randn(B, C, R, R, generator=gen).to(dev)
+
+    def run():
+        y = op.A(x)
+        return [y, op.At(y), op.project(x0, y), op.Lambda(x, 0.8, 0.2, 0.1, 0.85), op.Lambda_noise(x, 0.8, 0.2, 0.3, 0.85, x0),
+                *op.ddnm_step(x0, et, z, y, 0.5, 0.6, 0.85, None), *op.ddnm_step(x0, et, z, y, 0.5, 0.6, 0.85, 0.1)]
+
+    old = os.environ.get("NLC_FWHT_CLUSTER")
+    try:
+        os.environ["NLC_FWHT_CLUSTER"] = "1"
+        a = run()
+        os.environ["NLC_FWHT_CLUSTER"] = "0"
+        b = run()
+    finally:
+        if old is None:
+            os.environ.pop("NLC_FWHT_CLUSTER", None)
+        else:
+            os.environ["NLC_FWHT_CLUSTER"] = old
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    if R == 128:
+        orc = O.WalshHadamardCS(C, R, 4, perm)
+        y = orc.A(x.cpu())
+        assert (a[0].cpu() - y).abs().max() < 2e-6
+        assert (a[2].cpu() - orc.project(x0.cpu(), y)).abs().max() < 1e-5
