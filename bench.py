@@ -58,6 +58,13 @@ WORKLOADS = {
                  label="c5: ADM-256 UNet + sigma-model, DDNM Walsh-Hadamard CS x4 (svd projection), ddim_simple_orig eta "
                        "0.85, dynamic clip, %d steps, NLC pred",
                  metric="DDIM+NLC images/sec (ADM-256, DDNM WH-CS x4)"),
+    # the DDNM+ sampler of functions/svd_ddnm.py (noisy measurements, one UNet forward per
+    # step, no sigma-model) on the c4 network and operator
+    "c4p": dict(name="adm256", arch="adm", loop="ddnm_plus", R=256, steps=10, batch=32, gflop_per_nfe=2239.67, eta=0.85,
+                sigma_y=0.1, constraint=("sr_averagepooling", 4.0),
+                label="c4+: ADM-256 UNet, DDNM+ SR x4 with measurement noise 0.1 (functions/svd_ddnm.py "
+                      "ddnm_plus_diffusion, eta 0.85), %d steps",
+                metric="DDNM+ images/sec (ADM-256, SR x4, noisy measurements)"),
 }
 CFG = dict(WORKLOADS["c2"])
 ADM_KEYS = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
@@ -128,6 +135,23 @@ def cpu_port_rate(n_steps, batch, threads):
             dt = time.perf_counter() - t0
         nfe = 2 * n_steps - 1
         return batch / (dt / nfe * CFG["nfe_per_pass"]), dt
+    if CFG.get("loop") == "ddnm_plus":
+        # `n_steps` reverse steps (one network call each) of the oracle's DDNM+ loop at `batch`
+        from oracle import adm_net, ddnm, operators as O
+        cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
+        cfg.pop("sigma")
+        sd = weights.adm_unet_state_dict(**cfg, seed=3)
+        R = CFG["R"]
+        op = O.SuperResolution(3, R, int(CFG["constraint"][1]))
+        g = torch.Generator().manual_seed(0)
+        y = op.A(torch.rand(batch, 3 * R * R, generator=g) * 2 - 1)
+        x = torch.randn(batch, 3, R, R, generator=g)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            ddnm.run(x, lambda z, t: adm_net.unet_forward(sd, z, t, cfg), torch.linspace(1e-4, 2e-2, 1000), CFG["eta"], op,
+                     y, CFG["sigma_y"], T_sampling=n_steps, noise_fn=lambda like: torch.randn(like.shape, generator=g))
+            dt = time.perf_counter() - t0
+        return batch / (dt / n_steps * CFG["steps"]), dt
     if CFG["arch"] == "adm":
         from oracle import adm_net
         cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
@@ -281,7 +305,37 @@ def main():
         ops.STATS.conv_timer = conv_samples if (ind + 1) % every == every // 2 and hook.active else None
 
     hook.active = False
-    if CFG["arch"] == "edm":
+    if CFG.get("loop") == "ddnm_plus":
+        import types
+        from nlc_b200 import svd_ddnm
+        task, scale = CFG["constraint"]
+        A_funcs = CF.svd_constraint(task, fn_scale=scale, device=dev, image_size=R, channels=3)
+        x_true = torch.rand(shape, generator=g_dev, device=dev) * 2 - 1
+        y = A_funcs.A(x_true)
+        y = y + CFG["sigma_y"] * torch.randn(y.shape, generator=g_dev, device=dev)
+        y_bytes = y.numel() * 4
+        betas = torch.linspace(1e-4, 2e-2, 1000, device=dev)
+        ddnm_cfg = types.SimpleNamespace(
+            diffusion=types.SimpleNamespace(num_diffusion_timesteps=1000),
+            time_travel=types.SimpleNamespace(T_sampling=CFG["steps"], travel_length=1, travel_repeat=1))
+        lat_dev = torch.randn(shape, generator=g_dev, device=dev)
+        out_dtype, x_scale = torch.float32, 1.0
+        calls = [0]
+
+        def net(x, t):
+            hook(calls[0], None)
+            calls[0] += 1
+            return model(x, t)
+
+        if world > 1:
+            gathered = [torch.empty(shape, device=dev) for _ in range(world)]
+
+        def sample(x_in, to_cpu, with_hook):
+            calls[0] = 0
+            xs, x0s = svd_ddnm.ddnm_plus_diffusion(x_in, net if with_hook else model, betas, CFG["eta"], A_funcs, y,
+                                                   CFG["sigma_y"], config=ddnm_cfg, to_cpu=to_cpu)
+            return x0s[0]
+    elif CFG["arch"] == "edm":
         from nlc_b200.experiments import EDMImageExperiment
         exp = EDMImageExperiment(model, None, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev,
                                  num_timesteps=CFG["steps"])

@@ -10,7 +10,7 @@ on the device instead of bouncing to the CPU after every step (`xs.append(xt_nex
 last `x_t` and `x0_t` are returned by the reference, so only those are kept.
 
 `noise_fn(like)` (default `torch.randn_like`, i.e. the device generator exactly as in the reference) lets a test feed
-recorded draws.
+recorded draws; `to_cpu=False` returns the device tensors (the reference always moves the results to the host).
 """
 import ctypes as C
 
@@ -58,7 +58,7 @@ def _alpha_table(b):
     return (1 - beta).cumprod(dim=0).float().cpu()
 
 
-def _loop(x, model, b, eta, A_funcs, y, sigma_y, cls_fn, classes, config, noise_fn):
+def _loop(x, model, b, eta, A_funcs, y, sigma_y, cls_fn, classes, config, noise_fn, to_cpu=True):
     skip = config.diffusion.num_diffusion_timesteps // config.time_travel.T_sampling
     times = get_schedule_jump(config.time_travel.T_sampling, config.time_travel.travel_length,
                               config.time_travel.travel_repeat)
@@ -91,15 +91,18 @@ def _loop(x, model, b, eta, A_funcs, y, sigma_y, cls_fn, classes, config, noise_
                 _lib.check(lib.nlc_ddnm_renoise(ctx, x0_t.data_ptr(), z.data_ptr(), x0_t.numel(), at_next, out.data_ptr(),
                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)))
                 xt = out
+    if not to_cpu:  # sharded runs all-gather the device tensors
+        return [xt], [x0_t]
     return [xt.to("cpu")], [x0_t.to("cpu")]
 
 
-def ddnm_diffusion(x, model, b, eta, A_funcs, y, cls_fn=None, classes=None, config=None, noise_fn=torch.randn_like):
+def ddnm_diffusion(x, model, b, eta, A_funcs, y, cls_fn=None, classes=None, config=None, noise_fn=torch.randn_like,
+                   to_cpu=True):
     """functions/svd_ddnm.py:19-78."""
-    return _loop(x, model, b, eta, A_funcs, y, None, cls_fn, classes, config, noise_fn)
+    return _loop(x, model, b, eta, A_funcs, y, None, cls_fn, classes, config, noise_fn, to_cpu)
 
 
 def ddnm_plus_diffusion(x, model, b, eta, A_funcs, y, sigma_y, cls_fn=None, classes=None, config=None,
-                        noise_fn=torch.randn_like):
+                        noise_fn=torch.randn_like, to_cpu=True):
     """functions/svd_ddnm.py:80-145."""
-    return _loop(x, model, b, eta, A_funcs, y, float(sigma_y), cls_fn, classes, config, noise_fn)
+    return _loop(x, model, b, eta, A_funcs, y, float(sigma_y), cls_fn, classes, config, noise_fn, to_cpu)

@@ -9,7 +9,7 @@ python __graft_entry__.py smoke > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; 
 python bench.py > $O/${TAG}_bench_c2.json 2> $O/${TAG}_bench_c2.err; echo "bench c2 rc=$?"; cat $O/${TAG}_bench_c2.json
 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_reference.json 2> $O/${TAG}_bench_reference.err; echo "ref rc=$?"
 cat $O/${TAG}_bench_reference.json
-for w in c3 c4 c5 c5cs; do
+for w in c3 c4 c4p c5 c5cs; do
   python bench.py --workload $w --steps 2 --warmup 3 > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err; echo "bench $w rc=$?"
   cat $O/${TAG}_bench_$w.json; tail -2 $O/${TAG}_bench_$w.err
 done
