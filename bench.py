@@ -466,7 +466,10 @@ def main():
                 "peak_source": peak_src,
                 # dram__bytes_read+write of one launch of the step's top shape (3x3 conv 128->128 at 64x64, batch 256:
                 # 1.074 GB algorithmic) from the ncu --set full capture in profiles/r01_ncu_conv_tc_summary.md
-                "traffic": 1.021e9 if CFG["name"] == "c2" and B == 256 else None,
+                # ADM-256 at batch 32: the dominant 3x3 conv 256->256 at 256x256 moved 1.353 GB read + 2.136 GB written
+                # against 3.22 GB algorithmic (profiles/r01k_ncu_adm_kernels.md)
+                "traffic": 1.021e9 if CFG["name"] == "c2" and B == 256 else (
+                    3.489e9 if CFG["name"] == "adm256" and B == 32 else None),
                 "launches_sampled": len(conv_samples),
                 # share of the step spent in the conv kernel, from the sampled timesteps
                 "conv_share_of_step": (conv_ms / sampled_timesteps) / (ms_per_step / CFG["steps"]) if conv_ms > 0 else None,
