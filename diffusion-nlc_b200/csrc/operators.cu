@@ -429,6 +429,75 @@ __global__ void __launch_bounds__(256) sgemm_strided_kernel(const GemmArgs g) {
     }
 }
 
+// The same GEMM for the sizes the 256 x 256 operators produce (M, N >= 128): 128 x 128 x 16 tiles, 8 x 8 outputs per thread
+// read from shared memory as float4, the next K slab prefetched into registers while the current one is multiplied.
+__device__ __forceinline__ void gemm_epilogue(const GemmArgs& g, float v, int b, size_t cb, int i, int j) {
+    const size_t o = static_cast<size_t>(i) * g.N + j;
+    if (g.mult) v *= g.mult[static_cast<size_t>(b % g.nch) * g.M * g.N + o];
+    if (g.sub) v -= g.sub[cb + o];
+    if (g.base) v = g.alpha * g.base[cb + o] + g.beta * v;
+    if (g.add) v += g.add[cb + o];
+    g.Cm[cb + o] = v;
+}
+__global__ void __launch_bounds__(256, 2) sgemm_strided128_kernel(const GemmArgs g) {
+    __shared__ __align__(16) float As[16][128 + 4];  // +4: the k-major fill of a unit-K operand would hit one bank 16 times
+    __shared__ __align__(16) float Bs[16][128 + 4];
+    const int b = blockIdx.z, i0 = blockIdx.y * 128, j0 = blockIdx.x * 128;
+    const float* A = g.A + static_cast<long long>(b) * g.sab;
+    const float* Bm = g.Bm + static_cast<long long>(b) * g.sbb;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // this thread's 8 + 8 elements of a slab, element q at (i, k) = (ai0 + q*ais, ak0 + q*aks): the unit-stride index varies
+    // fastest across threads (t = tid + 256 q; unit-K operand: k = t & 15, i = t >> 4; otherwise i = t & 127, k = t >> 7)
+    const bool akf = g.sak == 1, bkf = g.sbk == 1;
+    const int tid = threadIdx.x;
+    const int ai0 = akf ? tid >> 4 : tid & 127, ais = akf ? 16 : 0, ak0 = akf ? tid & 15 : tid >> 7, aks = akf ? 0 : 2;
+    const int bj0 = bkf ? tid >> 4 : tid & 127, bjs = bkf ? 16 : 0, bk0 = bkf ? tid & 15 : tid >> 7, bks = bkf ? 0 : 2;
+    const float* Ap = A + static_cast<long long>(i0 + ai0) * g.sai + static_cast<long long>(ak0) * g.sak;
+    const float* Bp = Bm + static_cast<long long>(bk0) * g.sbk + static_cast<long long>(j0 + bj0) * g.sbj;
+    const long long aq = ais * g.sai + aks * g.sak, bq = bks * g.sbk + bjs * g.sbj;  // element q -> q + 1
+    float ra[8], rb[8];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            ra[q] = (i0 + ai0 + q * ais < g.M && k0 + ak0 + q * aks < g.K) ? Ap[k0 * g.sak + q * aq] : 0.f;
+            rb[q] = (j0 + bj0 + q * bjs < g.N && k0 + bk0 + q * bks < g.K) ? Bp[k0 * g.sbk + q * bq] : 0.f;
+        }
+    };
+    float acc[8][8] = {};
+    fetch(0);
+    for (int k0 = 0; k0 < g.K; k0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) As[ak0 + q * aks][ai0 + q * ais] = ra[q], Bs[bk0 + q * bks][bj0 + q * bjs] = rb[q];
+        __syncthreads();
+        if (k0 + 16 < g.K) fetch(k0 + 16);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a[r], bb[c], acc[r][c]);
+        }
+        __syncthreads();
+    }
+    const size_t cb = static_cast<size_t>(b) * g.M * g.N;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const int i = i0 + (r < 4 ? ty * 4 + r : 64 + ty * 4 + r - 4);
+        if (i >= g.M) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int j = j0 + (c < 4 ? tx * 4 + c : 64 + tx * 4 + c - 4);
+            if (j < g.N) gemm_epilogue(g, acc[r][c], b, cb, i, j);
+        }
+    }
+}
+
 __global__ void l1_diff_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n,
                                     float* __restrict__ out) {
     __shared__ float red[32];
@@ -477,8 +546,11 @@ int launch_gemm(cudaStream_t st, int batch, int M, int N, int K, const float* A,
                 long long sak, const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm, const float* mult,
                 int nch, const float* sub, const float* base, float alpha, float beta, const float* add) {
     GemmArgs g{A, Bm, mult, sub, base, add, alpha, beta, Cm, sab, sai, sak, sbb, sbk, sbj, M, N, K, nch};
-    dim3 grid((N + 63) / 64, (M + 63) / 64, batch);
-    sgemm_strided_kernel<<<grid, 256, 0, st>>>(g);
+    if (M >= 128 && N >= 128) {
+        sgemm_strided128_kernel<<<dim3((N + 127) / 128, (M + 127) / 128, batch), 256, 0, st>>>(g);
+    } else {
+        sgemm_strided_kernel<<<dim3((N + 63) / 64, (M + 63) / 64, batch), 256, 0, st>>>(g);
+    }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
