@@ -1,0 +1,175 @@
+"""Host-side mirror of the evaluation drivers of the reference's image_sample.py: `evaluate_constraint` (:608-710),
+`evaluate_unconstraint` (:522-569), `ssim_fn` (:571-582), `analyze_log` (:584-606) and the module-level
+`projection_loop` (:431-519), with the same arguments and the same result dictionary keys.
+
+What changes underneath: the sampling loops are the nlc_b200 ones (`ExperimentDiffusion.denoise_loop / projection_loop`),
+and the per-batch metrics (MSE, PSNR, SSIM, constraint residuals) are computed from the device tensors by libnlc_b200
+kernels (`metrics.restoration_metrics`) instead of the reference's CPU / numpy / per-image cuDNN round trip.  Batches are
+dealt round-robin to the ranks of a sharded run (`rank`, `world`), metric means are all-reduced at the end; with one
+process the numbers are the reference's.  PNG output is kept (optional: `images_dir=None` skips it and the reference's
+resume-by-existing-files logic); FID needs InceptionV3 and is taken from `experiment.fid_fn` when the caller provides
+one, else reported as None."""
+import math
+import os
+from functools import partial
+from time import time
+
+import numpy as np
+import torch
+
+from . import metrics as M
+
+
+def ssim_fn(sample, orig):
+    """image_sample.py:571-582: per-image SSIM (uint8 rounding, basicsr 3-D window) as a Python list."""
+    return M.ssim_fn(sample, orig).cpu().tolist()
+
+
+def projection_loop(self, *args, **kwargs):
+    """image_sample.py:431-519 takes the experiment as `self`; the implementation lives on the experiment class."""
+    return self.projection_loop(*args, **kwargs)
+
+
+def _save_batch(sample01, images_dir, rank, i):
+    if images_dir is None:
+        return
+    from torchvision.utils import save_image
+    for j, img in enumerate(sample01):
+        save_image(img, os.path.join(images_dir, f"{rank:02}-{i:05}-{j:03}.png"))
+
+
+def _already_done(images_dir, rank, i, batch_size):
+    if images_dir is None:
+        return False
+    return all(os.path.exists(os.path.join(images_dir, f"{rank:02}-{i:05}-{j:03}.png")) for j in range(batch_size))
+
+
+def _fid(experiment, images_dir):
+    fn = getattr(experiment, "fid_fn", None)
+    return fn(images_dir) if (fn is not None and images_dir is not None) else None
+
+
+def evaluate_unconstraint(experiment, n_samples, images_dir, norm_init_noise=False, style="base", sampling="denoise",
+                          norm_eps=False, refine_prior_sigma=False, sigma_estimate_rate=(1, 0, 0), max_T=None,
+                          sigma_pred_threshold=1000, new_eta=None, recal_sigma_prev=False, return_log=False,
+                          res_pkl_path="", rank=0, world=1):
+    """image_sample.py:522-569.  Returns (log_dict, return_lists); `log_dict['samples']` additionally holds this rank's
+    images in [0, 1] on the device (the reference only writes them to disk)."""
+    batch_size = experiment.batch_size
+    n_batches = math.ceil(n_samples / batch_size)
+    shape = (batch_size,) + tuple(experiment.data_shape)
+    gen = experiment.new_gen()
+    return_lists, kept = [], []
+    for i in range(rank, n_batches, world):
+        if _already_done(images_dir, rank, i, batch_size):
+            continue
+        if sampling == "project":
+            sample, return_list = experiment.projection_loop(
+                shape=shape, gen=gen, norm_init_noise=norm_init_noise, style=style, constrain_fn=None, norm_eps=norm_eps,
+                refine_prior_sigma=refine_prior_sigma, xT=None, return_log=return_log, chunk_size=1,
+                sigma_estimate_rate=sigma_estimate_rate, constrain_loss=None, max_T=max_T, stop_condition=0.0,
+                sigma_pred_threshold=sigma_pred_threshold, new_eta=new_eta, recal_sigma_prev=recal_sigma_prev,
+                to_cpu=False)
+        else:
+            sample, return_list = experiment.denoise_loop(
+                shape=shape, gen=gen, norm_init_noise=norm_init_noise, style=style, constrain_fn=None, norm_eps=norm_eps,
+                refine_prior_sigma=refine_prior_sigma, return_log=return_log, chunk_size=1,
+                sigma_pred_threshold=sigma_pred_threshold, new_eta=new_eta, to_cpu=False)
+        return_lists.append(return_list)
+        if return_log and res_pkl_path:
+            import joblib
+            joblib.dump(return_lists, res_pkl_path)
+        sample = sample.add(1).div(2).clamp(0, 1)
+        _save_batch(sample, images_dir, rank, i)
+        kept.append(sample)
+    log_dict = {"fid": _fid(experiment, images_dir), "samples": torch.cat(kept) if kept else None}
+    return log_dict, return_lists
+
+
+def analyze_log(return_list, x_orig, y, constrain_loss):
+    """image_sample.py:584-606: PSNR / SSIM / constraint loss of x_t, x0 before and after the projection, per step."""
+    z_list, eps_list, x0_prec_list, x0_postc_list = return_list[:4]
+    keys = ["zt", "z0_prec", "z0_postc"]
+    res = {k: {"psnr": [], "ssim": [], "const": []} for k in keys}
+    dev = y.device
+    x_orig = x_orig.to(dev)
+    for kk in range(len(eps_list)):
+        for key, sample in zip(keys, (z_list[kk], x0_prec_list[kk], x0_postc_list[kk])):
+            m = M.restoration_metrics(sample.to(dev), x_orig, ssim=True, return_image=True)
+            mse = m["mse"].mean()  # equal image sizes: the mean of per-image means is the batch mean (:595)
+            const, _ = constrain_loss(2 * m["image"] - 1.0, y)
+            res[key]["psnr"].append((10 * torch.log10(1 / mse)).item())
+            res[key]["ssim"].append(float(m["ssim"].mean()))
+            res[key]["const"].append(float(torch.mean(const)))
+    return res
+
+
+@torch.no_grad()
+def evaluate_constraint(experiment, data_loader, Constraint, images_dir, n_samples=-1, transform_dir=None,
+                        norm_init_noise=False, style="base", sampling="denoise", norm_eps=False,
+                        refine_prior_sigma=False, prior_xt=False, sigma_estimate_rate=(1, 0, 0), return_log=False,
+                        max_T=None, sigma_pred_threshold=1000, new_eta=None, recal_sigma_prev=False, rank=0, world=1):
+    """image_sample.py:608-710: restore every batch of `data_loader` (ground truth in [0, 1]) under `Constraint`, score it.
+    Returns (log_dict, return_list) with the reference's keys (`mse`, `psner` [sic], `ssim`, `const_f_loss`,
+    `const_b_loss`, `const_orig_loss`, `fid`, `full_log`, `full_results`); the means are over all ranks' samples."""
+    device = experiment.device
+    gen = experiment.new_gen()
+    lists = {k: [] for k in ("mse", "psnr", "ssim", "const_f", "const_b", "const_orig")}
+    full_results, return_list = [], None
+    for i, (x_orig, _classes) in enumerate(data_loader):
+        if i % world != rank:
+            continue
+        batch_size = x_orig.shape[0]
+        x_orig = x_orig.to(device)
+        batch_x = 2 * x_orig - 1.0
+        if _already_done(images_dir, rank, i, batch_size):
+            continue
+        y = Constraint.transform(batch_x)
+        Apy = None
+        if transform_dir is not None or prior_xt:
+            Apy = Constraint.inv_transform(y)
+        if transform_dir is not None:
+            from torchvision.utils import save_image
+            sample_apy = Apy.add(1).div(2).clamp(0, 1)
+            for j in range(len(Apy)):
+                save_image(sample_apy[j], os.path.join(transform_dir, f"Apy_{rank:02}-{i:05}-{j:03}.png"))
+                save_image(x_orig[j], os.path.join(transform_dir, f"orig_{rank:02}-{i:05}-{j:03}.png"))
+        shape = (batch_size,) + tuple(experiment.data_shape)
+        constraint_fn = partial(Constraint.constraint_fn, y=y, lambda_t=Constraint.lr)
+        constrain_loss = partial(Constraint.loss, y=y)
+        xT = Apy + experiment.scheduler.sampling_sigmas[0] * torch.randn_like(Apy) if prior_xt else None
+        t1 = time()
+        if sampling == "project":
+            sample, return_list = experiment.projection_loop(
+                shape=shape, gen=gen, norm_init_noise=norm_init_noise, style=style, constrain_fn=constraint_fn,
+                norm_eps=norm_eps, refine_prior_sigma=refine_prior_sigma, xT=xT, return_log=return_log, chunk_size=1,
+                sigma_estimate_rate=sigma_estimate_rate, constrain_loss=constrain_loss, max_T=max_T, stop_condition=0.0,
+                sigma_pred_threshold=sigma_pred_threshold, new_eta=new_eta, recal_sigma_prev=recal_sigma_prev,
+                to_cpu=False)
+        else:
+            sample, return_list = experiment.denoise_loop(
+                shape=shape, gen=gen, norm_init_noise=norm_init_noise, style=style, constrain_fn=constraint_fn,
+                norm_eps=norm_eps, refine_prior_sigma=refine_prior_sigma, xT=xT, return_log=return_log, chunk_size=1,
+                constrain_loss=constrain_loss, sigma_pred_threshold=sigma_pred_threshold, new_eta=new_eta, to_cpu=False)
+        elapsed = time() - t1
+        m = M.restoration_metrics(sample.to(device), x_orig, constraint=Constraint, y=y, return_image=True, ssim=True)
+        _save_batch(m["image"], images_dir, rank, i)
+        for k in lists:
+            lists[k] += m[k].cpu().tolist()
+        print(f"done batches:{i}/{len(data_loader)}, time:{elapsed:.2f}  psnr:{np.mean(lists['psnr'])}, "
+              f"ssim:{np.mean(lists['ssim'])}, cost:{np.mean(lists['const_f'])}")
+        if return_log:
+            full_results.append(analyze_log(return_list, x_orig, y, Constraint.loss))
+        if n_samples > 0 and (i + 1) * batch_size > n_samples:
+            break
+    # global means over the samples of all ranks (one all-reduce of the sums and the count)
+    means = M.reduce_means({k: torch.tensor(v, dtype=torch.float64, device=device) for k, v in lists.items()},
+                           keys=tuple(lists))
+    log_dict = {"mse": means["mse"], "psner": means["psnr"], "ssim": means["ssim"], "const_f_loss": means["const_f"],
+                "const_b_loss": means["const_b"], "const_orig_loss": means["const_orig"],
+                "fid": _fid(experiment, images_dir),
+                "full_log": {"psnr": lists["psnr"], "mse": lists["mse"], "ssim": lists["ssim"],
+                             "const_forward": lists["const_f"], "const_backward": lists["const_b"],
+                             "const_orig_loss": lists["const_orig"]},
+                "full_results": full_results}
+    return log_dict, return_list

@@ -96,6 +96,21 @@ def main():
             ms = timeit(fn)
             gbs = mb / ms
             print("%-22s %-12s %9.3f %9.1f %8.0f %6.2f" % (name, cname, ms, mb, gbs, gbs / peak))
+    # evaluation metrics of a finished batch: two images in, per-image scalars out
+    from nlc_b200 import metrics as M
+    origs = [torch.rand(B, C, R, R, device=dev) for _ in range(NBUF)]
+    samps = [(o + 0.05 * torch.randn_like(o)).clamp(0, 1) for o in origs]
+    turn = [0]
+
+    def nxt():
+        turn[0] = (turn[0] + 1) % NBUF
+        return turn[0]
+
+    img = 4.0 * B * d / 1e6
+    for cname, fn in (("ssim_fn", lambda k: M.ssim_fn(samps[k], origs[k])),
+                      ("mse/psnr/l1", lambda k: M.restoration_metrics(xts[k], origs[k]))):
+        ms = timeit(lambda: fn(nxt()))
+        print("%-22s %-12s %9.3f %9.1f %8.0f %6.2f" % ("metrics", cname, ms, 2 * img, 2 * img / ms, 2 * img / ms / peak))
 
 
 if __name__ == "__main__":
