@@ -291,7 +291,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line there
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
