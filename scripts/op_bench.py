@@ -112,6 +112,22 @@ def main():
         ms = timeit(lambda: fn(nxt()))
         print("%-22s %-12s %9.3f %9.1f %8.0f %6.2f" % ("metrics", cname, ms, 2 * img, 2 * img / ms, 2 * img / ms / peak))
 
+    # optimizer + EMA update of the sigma-model training step: 61.4 M parameters = the ADM-256 sigma-model
+    import ctypes as Ct
+    from nlc_b200 import _lib
+    n = 61_400_000 // 4 * 4
+    bufs = [torch.randn(n, device=dev) for _ in range(2)] + [torch.zeros(n, device=dev) for _ in range(2)] + \
+        [torch.randn(n, device=dev)]
+    L = _lib.lib()
+
+    def adam():
+        _lib.check(L.nlc_adamw_ema_step(_lib.ctx(0), bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(),
+                                        bufs[3].data_ptr(), bufs[4].data_ptr(), n, 1e-4, 0.9, 0.999, 1e-8, 0.01, 3, 0.999, 1.0,
+                                        Ct.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    ms = timeit(adam)
+    mb = 9 * 4.0 * n / 1e6  # p, g, m, v, ema read; p, m, v, ema written
+    print("%-22s %-12s %9.3f %9.1f %8.0f %6.2f" % ("training", "adamw+ema", ms, mb, mb / ms, mb / ms / peak))
 
 if __name__ == "__main__":
     main()

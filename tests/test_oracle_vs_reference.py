@@ -3,6 +3,7 @@
 the same ground there."""
 import os
 
+import numpy as np
 import pytest
 import torch
 
@@ -177,6 +178,23 @@ def test_block_cs_general_a_denoising(R):
         assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
         assert torch.equal(a.A_pinv_eta(y.clone(), 0.3), b.A_pinv_eta(y.clone(), 0.3))
         assert torch.equal(x0 - a.A_pinv(a.A(x0.clone()) - y), b.project(x0, y))
+
+
+def test_training_batch_preparation(R):
+    """oracle/training.prepare_batch against the reference's own lines (src/experiments.py:666-669 with its
+    Scheduler.diffusion and vector_norm), live."""
+    from oracle import training as OT
+    sch = R.schedulers.get_sampler("ddim", 1000, 10)
+    B, shape = 4, (4, 3, 16, 16)
+    x0, noise, extra = torch.rand(shape) * 2 - 1, torch.randn(shape), torch.randn(shape)
+    eta1, eta2 = 0.05 + torch.rand(B, 1, 1, 1) * 0.2, 0.1 + torch.rand(B, 1, 1, 1)
+    t = torch.randint(0, 1000, (B,))
+    noise_delta = eta1 * noise + eta1 * eta2 * extra
+    new_noise = noise + noise_delta
+    dist_real = R.utils.vector_norm(new_noise) / np.sqrt(3 * 16 * 16)
+    noisy_x, _ = sch.diffusion(x0, t, new_noise)
+    got_x, got_d, got_n = OT.prepare_batch(x0, t, noise, extra, eta1, eta2, sch.alphas_cumprod)
+    assert torch.equal(got_x, noisy_x) and torch.equal(got_d, dist_real) and torch.equal(got_n, new_noise)
 
 
 def test_ssim(R):
