@@ -76,7 +76,7 @@ _SIGNATURES = {
     "nlc_conv_out_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "nlc_nhwc_head_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "nlc_image_metrics": (_I, [_P, _P, _P, _I, _I64, _P, _P, _P, _P]),
-    "nlc_train_prepare": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I64, _P, _P, _P, _P]),
+    "nlc_train_prepare": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I64, _P, _P, _P, _P]),
     "nlc_adamw_ema_step": (_I, [_P, _P, _P, _P, _P, _P, _I64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                 _I64, C.c_double, C.c_double, _P]),
     "nlc_ssim3d_ws": (_SZ, [_I, _I, _I]),

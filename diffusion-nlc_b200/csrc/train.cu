@@ -3,6 +3,7 @@
 //   nlc_train_prepare    the perturbed-noise batch of :661-669 in one pass per sample:
 //                          new_noise = noise + eta1 noise + (eta1 eta2) extra,  dist_real = ||new_noise||_2 / sqrt(d),
 //                          noisy_x = x0 sqrt(alpha_bar_t) + new_noise sqrt(1 - alpha_bar_t)      (src/schedulers.py:323-329)
+//                        and its EDM variant of :996-1001 (new_noise = noise + eta1 (noise + eta2 extra), x0 + sigma new_noise)
 //                        (the reference: 9 elementwise launches and a norm over [B, d])
 //   nlc_adamw_ema_step   torch.optim.AdamW's update (decoupled weight decay, bias-corrected moments) of :692 and the EMA
 //                        of the master parameters (:233-236) fused into ONE pass over a flat fp32 parameter buffer, with the
@@ -19,7 +20,7 @@ namespace nlc {
 __global__ void __launch_bounds__(1024) train_prepare_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                                                               const float* __restrict__ extra,
                                                               const float* __restrict__ eta1, const float* __restrict__ eta2,
-                                                              const float* __restrict__ alpha_bar, long long d,
+                                                              const float* __restrict__ alpha_bar, int edm, long long d,
                                                               float inv_sqrt_d, float* __restrict__ noisy_x,
                                                               float* __restrict__ new_noise_out,
                                                               float* __restrict__ dist_real) {
@@ -27,14 +28,18 @@ __global__ void __launch_bounds__(1024) train_prepare_kernel(const float* __rest
     const int b = blockIdx.x;
     const size_t base = static_cast<size_t>(b) * d;
     const float e1 = eta1[b], e12 = __fmul_rn(eta1[b], eta2[b]);
-    const float ab = alpha_bar[b];
-    const float sa = sqrtf(ab), sn = sqrtf(__fsub_rn(1.0f, ab));
+    const float e2 = eta2[b];
+    const float ab = alpha_bar[b];  // alpha_bar_t, or sigma for the EDM step
+    const float sa = edm ? 1.0f : sqrtf(ab), sn = edm ? ab : sqrtf(__fsub_rn(1.0f, ab));
     float acc = 0.f;
     auto one = [&](float xv, float nv, float ev, float& nn) -> float {
-        // noise + (eta1 * noise + (eta1 * eta2) * extra)   (src/experiments.py:666-667)
-        nn = __fadd_rn(nv, __fadd_rn(__fmul_rn(e1, nv), __fmul_rn(e12, ev)));
+        // DDIM: noise + (eta1 * noise + (eta1 * eta2) * extra)   (src/experiments.py:666-667)
+        // EDM:  noise + eta1 * (noise + eta2 * extra)            (:998-999)
+        nn = edm ? __fadd_rn(nv, __fmul_rn(e1, __fadd_rn(nv, __fmul_rn(e2, ev))))
+                 : __fadd_rn(nv, __fadd_rn(__fmul_rn(e1, nv), __fmul_rn(e12, ev)));
         acc = fmaf(nn, nn, acc);
-        return __fadd_rn(__fmul_rn(xv, sa), __fmul_rn(nn, sn));
+        // x0 sqrt(ab) + new_noise sqrt(1 - ab)  |  x0 + sigma new_noise   (:1001)
+        return edm ? __fadd_rn(xv, __fmul_rn(sn, nn)) : __fadd_rn(__fmul_rn(xv, sa), __fmul_rn(nn, sn));
     };
     if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(noise) |
                           reinterpret_cast<uintptr_t>(extra) | reinterpret_cast<uintptr_t>(noisy_x) |
@@ -124,12 +129,12 @@ __global__ void __launch_bounds__(256) adamw_ema_kernel(float* __restrict__ p, c
 using namespace nlc;
 
 extern "C" int nlc_train_prepare(nlc_ctx* ctx, const float* x0, const float* noise, const float* extra, const float* eta1,
-                                 const float* eta2, const float* alpha_bar, int B, int64_t d, float* noisy_x,
+                                 const float* eta2, const float* alpha_bar, int edm, int B, int64_t d, float* noisy_x,
                                  float* new_noise_out, float* dist_real, void* stream) {
     NLC_REQUIRE(ctx && x0 && noise && extra && eta1 && eta2 && alpha_bar && noisy_x && dist_real && B >= 1 && d >= 1,
                 "nlc_train_prepare: bad argument");
     train_prepare_kernel<<<B, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
-        x0, noise, extra, eta1, eta2, alpha_bar, d, static_cast<float>(1.0 / sqrt(static_cast<double>(d))), noisy_x,
+        x0, noise, extra, eta1, eta2, alpha_bar, edm, d, static_cast<float>(1.0 / sqrt(static_cast<double>(d))), noisy_x,
         new_noise_out, dist_real);
     NLC_CHECK_LAUNCH();
     return NLC_OK;

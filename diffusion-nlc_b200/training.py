@@ -19,7 +19,13 @@ from . import _lib, parallel
 from .svd_operators import _stream
 
 
-def prepare_batch(x0, t, noise, extra, eta1, eta2, alphas_cumprod, return_noise=False):
+def prepare_batch_edm(x0, sigma, noise, extra, eta1, eta2, return_noise=False):
+    """The EDM experiment's variant (src/experiments.py:996-1001): new_noise = noise + eta1 (noise + eta2 extra),
+    noisy_img = x0 + sigma new_noise, with per-sample sigma [B] (or [B,1,1,1])."""
+    return prepare_batch(x0, None, noise, extra, eta1, eta2, None, return_noise=return_noise, sigma=sigma)
+
+
+def prepare_batch(x0, t, noise, extra, eta1, eta2, alphas_cumprod, return_noise=False, sigma=None):
     """src/experiments.py:661-669 in one kernel.  x0, noise, extra: [B, ...] on the device; t: [B] long; eta1, eta2: [B]
     (or [B,1,1,1]) perturbation factors (`eta1_fn`, `eta2_fn`, :228-231); alphas_cumprod: the scheduler's table.
     Returns (noisy_x, dist_real[, new_noise]): the network input and the regression target ||new_noise|| / sqrt(d)."""
@@ -29,13 +35,14 @@ def prepare_batch(x0, t, noise, extra, eta1, eta2, alphas_cumprod, return_noise=
     f = lambda v: v.to(dev, torch.float32).contiguous()
     x0c, nc, ec = f(x0), f(noise), f(extra)
     e1, e2 = f(eta1).reshape(B), f(eta2).reshape(B)
-    ab = f(alphas_cumprod.to(dev)[t.to(dev).long()]).reshape(B)
+    ab = f(sigma).reshape(B) if sigma is not None else f(alphas_cumprod.to(dev)[t.to(dev).long()]).reshape(B)
     noisy = torch.empty_like(x0c)
     new_noise = torch.empty_like(x0c) if return_noise else None
     dist_real = torch.empty(B, device=dev)
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
     _lib.check(_lib.lib().nlc_train_prepare(_lib.ctx(idx), x0c.data_ptr(), nc.data_ptr(), ec.data_ptr(), e1.data_ptr(),
-                                            e2.data_ptr(), ab.data_ptr(), B, d, noisy.data_ptr(),
+                                            e2.data_ptr(), ab.data_ptr(), 0 if sigma is None else 1, B, d,
+                                            noisy.data_ptr(),
                                             C.c_void_p(new_noise.data_ptr()) if return_noise else None,
                                             dist_real.data_ptr(), _stream()))
     shape = (B,) + (1,) * (x0.dim() - 1)

@@ -391,12 +391,14 @@ int nlc_ssim3d(nlc_ctx* ctx, const float* sample01, const float* orig01, int B, 
  * SURVEY section 8(f) rank 3, first slice — the sigma-model training step (src/experiments.py:654-694) around the
  * sigma-model's own forward / backward: batch preparation and the optimizer + EMA update.
  * ---------------------------------------------------------------------------------------------- */
-/* new_noise = noise + eta1 noise + (eta1 eta2) extra;  dist_real[b] = ||new_noise[b]||_2 / sqrt(d);
- * noisy_x = x0 sqrt(alpha_bar[b]) + new_noise sqrt(1 - alpha_bar[b])   (:661-669, src/schedulers.py:323-329).
+/* edm = 0: new_noise = noise + eta1 noise + (eta1 eta2) extra;  dist_real[b] = ||new_noise[b]||_2 / sqrt(d);
+ *          noisy_x = x0 sqrt(alpha_bar[b]) + new_noise sqrt(1 - alpha_bar[b])   (:661-669, src/schedulers.py:323-329).
+ * edm = 1: new_noise = noise + eta1 (noise + eta2 extra);  noisy_x = x0 + sigma[b] new_noise, sigma passed as `alpha_bar`
+ *          (the EDM experiment's step, :996-1001).
  * x0, noise, extra, noisy_x, new_noise_out (nullable): [B, d]; eta1, eta2, alpha_bar, dist_real: [B]. */
 int nlc_train_prepare(nlc_ctx* ctx, const float* x0, const float* noise, const float* extra, const float* eta1,
-                      const float* eta2, const float* alpha_bar, int B, int64_t d, float* noisy_x, float* new_noise_out,
-                      float* dist_real, void* stream);
+                      const float* eta2, const float* alpha_bar, int edm, int B, int64_t d, float* noisy_x,
+                      float* new_noise_out, float* dist_real, void* stream);
 /* One torch.optim.AdamW step (:144, :692) on a flat fp32 buffer followed by the EMA of the parameters (:233-236; ema may be
  * NULL): grads are multiplied by grad_scale first (1 / world_size after a sum all-reduce).  step counts from 1. */
 int nlc_adamw_ema_step(nlc_ctx* ctx, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema,

@@ -22,6 +22,15 @@ def prepare_batch(x0, t, noise, extra, eta1, eta2, alphas_cumprod):
     return noisy_x, dist_real, new_noise
 
 
+def prepare_batch_edm(x0, sigma, noise, extra, eta1, eta2):
+    """-> (noisy_img, dist_real, new_noise): src/experiments.py:998-1001."""
+    noise_delta = eta1 * (noise + eta2 * extra)
+    new_noise = noise + noise_delta
+    dims = tuple(range(1, x0.dim()))
+    dist_real = torch.linalg.vector_norm(new_noise, dim=dims, keepdim=True) / np.sqrt(x0[0].numel())
+    return x0 + sigma * new_noise, dist_real, new_noise
+
+
 class AdamWEma:
     """torch.optim.AdamW + the EMA copy of the parameters, as set_optimizers / update_ema use them."""
 

@@ -173,3 +173,31 @@ def test_ssim_stays_inside_its_buffers():
         _lib.check(L.nlc_ssim3d(_lib.ctx(0), a.data_ptr(), b.data_ptr(), B, H, W, C.c_void_p(ws.data_ptr()), out.data_ptr(), st))
         torch.cuda.synchronize()
         assert intact(wbuf, nws) and intact(obuf, B) and ((out > -1) & (out <= 1)).all()
+
+
+def test_training_kernels_stay_inside_their_buffers():
+    import ctypes as C
+    from nlc_b200 import _lib
+    L, st = _lib.lib(), C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (B, d) in ((3, 3 * 16 * 16), (2, 1001)):
+        x0, noise, extra = (torch.randn(B, d, device=dev) for _ in range(3))
+        eta1, eta2, ab = torch.rand(B, device=dev), torch.rand(B, device=dev), torch.rand(B, device=dev) * 0.9 + 0.05
+        b1, noisy = guarded((B, d))
+        b2, nn = guarded((B, d))
+        b3, dist = guarded((B,))
+        _lib.check(L.nlc_train_prepare(_lib.ctx(0), x0.data_ptr(), noise.data_ptr(), extra.data_ptr(), eta1.data_ptr(),
+                                       eta2.data_ptr(), ab.data_ptr(), B % 2, B, d, noisy.data_ptr(),
+                                       C.c_void_p(nn.data_ptr()), dist.data_ptr(), st))
+        torch.cuda.synchronize()
+        assert intact(b1, B * d) and intact(b2, B * d) and intact(b3, B) and torch.isfinite(noisy).all() and (dist > 0).all()
+    for n in (4096, 4099):
+        bufs = [guarded((n,)) for _ in range(4)]
+        for _, v in bufs:
+            v.copy_(torch.randn(n, device=dev).abs())
+        g = torch.randn(n, device=dev)
+        _lib.check(L.nlc_adamw_ema_step(_lib.ctx(0), bufs[0][1].data_ptr(), g.data_ptr(), bufs[1][1].data_ptr(),
+                                        bufs[2][1].data_ptr(), bufs[3][1].data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 0.01, 1, 0.99,
+                                        1.0, st))
+        torch.cuda.synchronize()
+        for buf, v in bufs:
+            assert intact(buf, n) and torch.isfinite(v).all()

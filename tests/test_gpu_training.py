@@ -30,6 +30,14 @@ def test_prepare_batch(shape):
     assert (got_n.cpu() - want_n).abs().max() <= 1e-6 * want_n.abs().max()
     assert (got_x.cpu() - want_x).abs().max() <= 1e-6 * want_x.abs().max()
     assert ((got_d.cpu() - want_d).abs() / want_d).max() < 2e-6
+    # the EDM experiment's variant (src/experiments.py:996-1001)
+    sigma = (torch.randn(sh, generator=g) * 1.2 - 1.2).exp()
+    want_x, want_d, want_n = OT.prepare_batch_edm(x0, sigma, noise, extra, eta1, eta2)
+    got_x, got_d, got_n = T.prepare_batch_edm(x0.to(dev), sigma.to(dev), noise.to(dev), extra.to(dev), eta1.to(dev),
+                                              eta2.to(dev), return_noise=True)
+    assert (got_n.cpu() - want_n).abs().max() <= 1e-6 * want_n.abs().max()
+    assert (got_x.cpu() - want_x).abs().max() <= 1e-6 * want_x.abs().max()
+    assert ((got_d.cpu() - want_d).abs() / want_d).max() < 2e-6
 
 
 @pytest.mark.parametrize("n", [4096, 10007])
