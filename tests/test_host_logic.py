@@ -98,6 +98,17 @@ def _worker(rank, ws, port, q):
     ok = ok and abs(float(loss) - float(full.abs().sum())) < 1e-3 and bool(nan) and float(tmax) == 10 + ws - 1
     sums = parallel.reduce_metric_sums(torch.tensor([float(hi - lo), 1.0]))
     ok = ok and sums.tolist() == [float(B), float(ws)]
+    # evaluation metrics of a sharded run (image_sample.evaluate_constraint): global means over uneven shards, incl. a rank
+    # whose shard is empty for one key set
+    from nlc_b200 import metrics
+    vals = {"mse": torch.arange(lo, hi, dtype=torch.float64), "ssim": torch.arange(lo, hi, dtype=torch.float64) * 2,
+            "psnr": torch.ones(hi - lo, dtype=torch.float64)}
+    means = metrics.reduce_means(vals, keys=("mse", "psnr", "ssim"))
+    ok = ok and abs(means["mse"] - (B - 1) / 2) < 1e-12 and abs(means["ssim"] - (B - 1)) < 1e-12 and means["psnr"] == 1.0
+    # round-robin dealing of batches to ranks, as the evaluation drivers do it
+    dealt = [i for i in range(7) if i % ws == rank]
+    counts = parallel.reduce_metric_sums(torch.tensor([float(len(dealt))]))
+    ok = ok and counts.item() == 7.0
     q.put((rank, ok))
     dist.destroy_process_group()
 
