@@ -336,32 +336,18 @@ __global__ void __launch_bounds__(256) fwht_cols_kernel(const float* __restrict_
         if (fwht_epilogue(e, v, b, c, C, R, r, c0 + lane, o)) out[o] = v;
     }
 }
-// y[b][j*C + c] = F[b][c][perm[j]], j < m  (gather through invperm: thread per spectral entry q)
-__global__ void whcs_gather_kernel(const float* __restrict__ F, float* __restrict__ y, int B, int C, int N, int m,
-                                   const int* __restrict__ invperm) {
+// temp[b][c][q] = invperm[q] < m ? f * y[b][invperm[q]*C + c] : 0: the measurement scattered back to its spectral positions
+// (A^T, A^+ with f = 1, A_pinv_eta with f = 1 / (1 + eta)); the forward gather and the projection's residual ride on the
+// transform's epilogue instead (fwht_epilogue)
+__global__ void whcs_scatter_kernel(const float* __restrict__ y, float* __restrict__ temp, int B, int C, int N, int m,
+                                    const int* __restrict__ invperm, float f) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(B) * C * N) return;
     const int q = static_cast<int>(i % N);
     const int c = static_cast<int>((i / N) % C);
     const int b = static_cast<int>(i / (static_cast<long long>(N) * C));
     const int j = invperm[q];
-    if (j < m) y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c] = F[i];
-}
-// temp[b][c][q] = j < m ? (F ? F[b][c][q] - y : y)[b][j*C+c] : 0
-__global__ void whcs_scatter_kernel(const float* __restrict__ F, const float* __restrict__ y, float* __restrict__ temp,
-                                    int B, int C, int N, int m, const int* __restrict__ invperm, float f) {
-    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= static_cast<long long>(B) * C * N) return;
-    const int q = static_cast<int>(i % N);
-    const int c = static_cast<int>((i / N) % C);
-    const int b = static_cast<int>(i / (static_cast<long long>(N) * C));
-    const int j = invperm[q];
-    float v = 0.f;
-    if (j < m) {
-        const float yv = y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c];
-        v = F ? F[i] - yv : __fmul_rn(yv, f);  // f = 1 (At, A^+) or 1 / (1 + eta)
-    }
-    temp[i] = v;
+    temp[i] = j < m ? __fmul_rn(y[static_cast<size_t>(b) * m * C + static_cast<size_t>(j) * C + c], f) : 0.f;
 }
 
 // ---------------------------------------------------------------- strided batched fp32 GEMM (separable operators)
@@ -889,7 +875,7 @@ static int op_apply(nlc_op* op, int mode, const float* in, const float* y, int B
                 if ((rc = fwht2d(op, T, out, e, B, st))) return rc;  // out = x0 - fwht(T)
             } else {
                 const float f = mode == 4 ? 1.0f / (1.0f * 1.0f + static_cast<float>(eta)) : 1.f;
-                whcs_scatter_kernel<<<g, 256, 0, st>>>(nullptr, in, T, B, C, static_cast<int>(N), m, op->idx_a, f);
+                whcs_scatter_kernel<<<g, 256, 0, st>>>(in, T, B, C, static_cast<int>(N), m, op->idx_a, f);
                 NLC_CHECK_LAUNCH();
                 if ((rc = fwht2d(op, T, out, Epilogue(), B, st))) return rc;
             }
