@@ -65,6 +65,7 @@ struct ConvKParams {
     void* out_op;
     int ld_out_op;
     int out_head_split;
+    int out_up;      // 0, or 1 + 2a + b: output pixel (n,ho,wo) is written at (n, 2ho+a, 2wo+b) of a [B,2Ho,2Wo,.] tensor
     int w_batched;
     int f16;         // 16-bit operands are fp16 (kind::f16 with the f16 format bits), not bf16
     float* stats;    // GroupNorm partials of the fp32 output: [pixel/32][stats_nblk][2] = (mean, M2) over 32 px x 4 ch
@@ -415,6 +416,23 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
             const size_t pix0 = p.out_head_split ? static_cast<size_t>(n0) * p.Wo + wo0
                                                  : (static_cast<size_t>(n0) * p.Ho + ho0) * p.Wo + wo0;
             const int hs_off = p.out_head_split * ho0;
+            // sub-pixel placement (one phase of a nearest-x2 upsample + 3x3 conv computed at the LOW resolution)
+            const int up_a = (p.out_up - 1) >> 1, up_b = (p.out_up - 1) & 1;
+            auto opix = [&](int r) -> size_t {
+                const size_t q = pix0 + r;
+                if (!p.out_up) return q;
+                const size_t wo = q & (static_cast<size_t>(p.Wo) - 1);
+                const size_t ho = (q >> p.log2_wo) & (static_cast<size_t>(p.Ho) - 1);
+                const size_t nn = q >> (p.log2_wo + p.log2_ho);
+                return ((nn * 2 * p.Ho + 2 * ho + up_a) * 2 * p.Wo) + 2 * wo + up_b;
+            };
+            // GroupNorm partial block of this warp's 32 pixels: in output order, or (placement) sample-major, phase, block
+            size_t stat_blk = (pix0 + lane) >> 5;
+            if (p.out_up) {
+                const size_t hw = static_cast<size_t>(p.Ho) * p.Wo;
+                const size_t nn = pix0 >> (p.log2_wo + p.log2_ho);
+                stat_blk = nn * (4 * hw >> 5) + static_cast<size_t>(p.out_up - 1) * (hw >> 5) + ((pix0 & (hw - 1)) >> 5);
+            }
 
             // Residual rows of the chunk about to be processed are fetched one chunk ahead (mode 0): the first chunk's
             // loads are issued before the accumulator wait, every later chunk's while the previous one is being stored.
@@ -557,7 +575,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
                 }
                 if (p.stats && vmask == 0xffffffffu)  // (the odd tail tile of a CTA pair is entirely out of range)
-                    gn_partials(f, lane, p.stats + (((pix0 + lane) >> 5) * p.stats_nblk + (col0 >> 2)) * 2);
+                    gn_partials(f, lane, p.stats + (stat_blk * p.stats_nblk + (col0 >> 2)) * 2);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     *reinterpret_cast<float4*>(stg + lane * 32 + ((i ^ (lane & 7)) << 2)) =
@@ -568,7 +586,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 4 + sub_r4;
                         if ((vmask >> r) & 1)
-                            reinterpret_cast<float4*>(p.out_f32 + (pix0 + r) * p.ld_out_f32 + ocol0)[sub_c4] =
+                            reinterpret_cast<float4*>(p.out_f32 + opix(r) * p.ld_out_f32 + ocol0)[sub_c4] =
                                 *reinterpret_cast<const float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2));
                     }
                 }
@@ -579,7 +597,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                             const int r = it * 4 + sub_r4;
                             if ((vmask >> r) & 1) {
                                 const float4 t = *reinterpret_cast<const float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2));
-                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + (pix0 + r) * p.ld_out_op +
+                                reinterpret_cast<float4*>(static_cast<float*>(p.out_op) + opix(r) * p.ld_out_op +
                                                           ocol0)[sub_c4] =
                                     X3 ? t : make_float4(round_tf32(t.x), round_tf32(t.y), round_tf32(t.z),
                                                          round_tf32(t.w));
@@ -595,7 +613,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                                 const float4 b =
                                     *reinterpret_cast<const float4*>(stg + r * 32 + (((2 * sub_c8 + 1) ^ (r & 7)) << 2));
                                 reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_op) +
-                                                         (pix0 + r) * p.ld_out_op + ocol0)[sub_c8] =
+                                                         opix(r) * p.ld_out_op + ocol0)[sub_c8] =
                                     make_uint4(pack_op16x2(a.x, a.y, p.f16), pack_op16x2(a.z, a.w, p.f16),
                                                pack_op16x2(b.x, b.y, p.f16), pack_op16x2(b.z, b.w, p.f16));
                             }
@@ -792,6 +810,11 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     }
     p.out_head_split = d->out_head_split;
     NLC_REQUIRE(d->out_head_split % 8 == 0, "nlc_conv_tc: out_head_split must be a multiple of 8");
+    NLC_REQUIRE(d->out_up >= 0 && d->out_up <= 4 &&
+                    (d->out_up == 0 || (is_pow2(d->Ho) && is_pow2(d->Wo) && !d->out_head_split && !d->resid &&
+                                        (d->Ho * d->Wo) % 32 == 0)),
+                "nlc_conv_tc: out_up (sub-pixel placement) needs power-of-two extents, a dense output and no residual");
+    p.out_up = d->out_up;
     if (d->stats) {
         NLC_REQUIRE(p.BN == 1 && d->out_head_split == 0 && d->stats_nblk >= d->Cout / 4 &&
                         (reinterpret_cast<uintptr_t>(d->stats) & 7) == 0,

@@ -127,13 +127,40 @@ def pack_conv_weight(w, op_dtype, extra=None):
     return round_tf32_(k.clone())
 
 
+# "nearest-neighbour x2 upsample, then 3x3 conv (padding 1)" at the low resolution: output pixel (2i+a, 2j+b) only sees the
+# low-resolution rows {i-1, i} (a = 0) or {i, i+1} (a = 1), with the kernel rows that land on the same source row summed
+_UP_ROWS = {0: ((-1, (0,)), (0, (1, 2))), 1: ((0, (0, 1)), (1, (2,)))}  # phase -> ((source offset, kernel rows), ...)
+
+
+def upsample_phase_weights(w, op_dtype):
+    """torch [Cout,Cin,3,3] -> {(a, b): packed [Cout, 4*Cin]} for the four sub-pixel phases (taps in `upsample_phase_taps`
+    order).  The sums are taken in fp32 before the operand rounding."""
+    w = w.detach().float()
+    out = {}
+    for a in (0, 1):
+        for b in (0, 1):
+            k = torch.zeros(w.shape[0], w.shape[1], 2, 2, dtype=torch.float32, device=w.device)
+            for i, (_, rows) in enumerate(_UP_ROWS[a]):
+                for j, (_, cols) in enumerate(_UP_ROWS[b]):
+                    for kh in rows:
+                        for kw in cols:
+                            k[:, :, i, j] += w[:, :, kh, kw]
+            out[(a, b)] = pack_conv_weight(k, op_dtype)
+    return out
+
+
+def upsample_phase_taps(src, c0, nch, a, b):
+    """The four K segments (source offsets) of phase (a, b), in the order `upsample_phase_weights` packs them."""
+    return [(src, dh, dw, c0, nch) for dh, _ in _UP_ROWS[a] for dw, _ in _UP_ROWS[b]]
+
+
 def taps3x3(src, c0, nch, pad=1):
     """Nine K segments of a 3x3 convolution over channels [c0,c0+nch) of source `src`."""
     return [(src, kh - pad, kw - pad, c0, nch) for kh in range(3) for kw in range(3)]
 
 
 def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, rowvec=None, resid=None,
-            out_scale=1.0, out_f32=None, out_op=None, stats=False, resid_mode=0):
+            out_scale=1.0, out_f32=None, out_op=None, stats=False, resid_mode=0, out_up=None):
     """Tensor-core implicit GEMM (nlc_conv_tc). srcs: list[Act]; segs: list of (src, dh, dw, c0, nch);
     resid/out_f32/out_op: Act or None; rowvec: [B, Cout] fp32 tensor."""
     d = _lib.ConvDesc()
@@ -154,6 +181,8 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.resid, d.ld_resid = resid.ptr, resid.ld
         d.resid_mode = resid_mode  # 1 / 2: the residual is at half / double resolution (nearest x2 / 2x2 average)
     d.out_scale = out_scale
+    if out_up is not None:  # (a, b): this launch is one phase of "nearest x2, then 3x3" computed at the low resolution
+        d.out_up = 1 + 2 * out_up[0] + out_up[1]
     if out_f32 is not None:
         d.out_f32, d.ld_out_f32 = out_f32.ptr, out_f32.ld
     if out_op is not None:
@@ -170,6 +199,10 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
     if timer is not None or optimer is not None:
         e1.record()
         flops = 2.0 * B * Ho * Wo * Cout * sum(sg[4] for sg in segs)
+        if out_up is not None:
+            # a sub-pixel phase executes 4 of the 9 taps' multiplies of the "upsample, then 3x3" it computes: the bench counts
+            # the ALGORITHMIC work of the layer (2 * pixels * Cout * 9 Cin), as for every other launch
+            flops *= 9.0 / 4.0
         if timer is not None:
             timer.append((flops, e0, e1))
         if optimer is not None:

@@ -9,12 +9,13 @@ everything is NHWC; the fused entry points used by the sampler (`forward_scaled`
 fold the per-sample input scale into conv_in.
 """
 import math
+import os
 
 import torch
 
 from . import ops
 from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
-                     emit_groupnorm, run)
+                     emit_groupnorm, emit_upsample_conv3x3, run, upsample_conv_eligible)
 from .ops import Act
 
 GN_EPS = 1e-6  # Normalize(), src/unet_ddim.py:54-55
@@ -161,6 +162,7 @@ class UNetModel:
             if i_level != 0:
                 p = "up.%d.upsample.conv." % i_level
                 lvl["up"] = (eng.pack3x3(sd[p + "weight"]), eng.dev32(sd[p + "bias"]))
+                lvl["up_phase"] = ops.upsample_phase_weights(sd[p + "weight"].to(eng.device), eng.op_dtype)
             self.up.append(lvl)
         self.no_w, self.no_b = eng.dev32(sd["norm_out.weight"]), eng.dev32(sd["norm_out.bias"])
         self.cout_w, self.cout_b = eng.dev32(sd["conv_out.weight"]), eng.dev32(sd["conv_out.bias"])
@@ -324,11 +326,18 @@ class UNetModel:
             if lvl["up"] is not None:
                 # Upsample: nearest x2 then 3x3 conv (src/unet_ddim.py:69-74); the replicated operand is
                 # materialised once in the operand dtype
-                upo = eng.act_op("up.rep", B, 2 * res, 2 * res, cur.C)
                 src32 = cur.f32
-                dec.add(lambda src32=src32, upo=upo: ops.resample(src32, 1, None, upo, dt))
-                res *= 2
-                emit_conv3x3(dec, upo, lvl["up"][0], lvl["up"][1], cur.C, head_feat(k))
+                if upsample_conv_eligible(res, res) and os.environ.get("NLC_UPCONV", "1") != "0":
+                    # ... computed at the low resolution instead: four sub-pixel phase convs (engine.emit_upsample_conv3x3)
+                    lowo = eng.act_op("up.low", B, res, res, cur.C)
+                    dec.add(lambda src32=src32, lowo=lowo: ops.resample(src32, 0, None, lowo, dt))
+                    res *= 2
+                    emit_upsample_conv3x3(dec, lowo, lvl["up_phase"], lvl["up"][1], cur.C, head_feat(k))
+                else:
+                    upo = eng.act_op("up.rep", B, 2 * res, 2 * res, cur.C)
+                    dec.add(lambda src32=src32, upo=upo: ops.resample(src32, 1, None, upo, dt))
+                    res *= 2
+                    emit_conv3x3(dec, upo, lvl["up"][0], lvl["up"][1], cur.C, head_feat(k))
         a = eng.act_op("rb.a1", B, R, R, cur.C)
         emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
         emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])

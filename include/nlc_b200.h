@@ -112,6 +112,11 @@ typedef struct {
                            2: resid is [B,2Ho,2Wo,.] and its 2x2 average is added (sum of the window, then * 0.25).
                            Folds ADM's x_upd (src/unet_adm.py:236-243, Upsample / Downsample without conv of the
                            skip path, :81-140) into the conv that consumes it.                                   */
+    int out_up;         /* 0: dense output; 1 + 2a + b (a, b in {0,1}): output pixel (n,ho,wo) is written at
+                           (n, 2ho+a, 2wo+b) of a [B,2Ho,2Wo,.] tensor (and its GroupNorm partials into that tensor's
+                           block range).  With the four phase-combined 2x2 tap sets of a 3x3 kernel this computes
+                           "nearest-neighbour x2 upsample, then 3x3 conv" (src/unet_ddim.py:58-74) at the LOW
+                           resolution: 16 instead of 36 multiplies per output and no replicated operand in HBM. */
 } nlc_conv_desc;
 
 int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);

@@ -419,3 +419,53 @@ def test_conv_tc_resampled_residual(dev, mode, shape):
     assert torch.equal(a.t, b.t)
     ref = F.conv2d(x, w, padding=1) + full.permute(0, 3, 1, 2)
     assert _rel(b.t.permute(0, 3, 1, 2), ref) < 5e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 128, 128), (3, 32, 32, 256, 256), (1, 16, 8, 64, 128)])
+def test_upsample_conv_as_four_subpixel_phases(dev, prec, tol, shape):
+    """"nearest x2, then 3x3 conv" (src/unet_ddim.py:58-74) computed at the low resolution: four phase convolutions with the
+    summed 2x2 tap sets, each writing its quarter of the output in place (nlc_conv_desc.out_up) and the matching GroupNorm
+    partials.  Reference: F.conv2d on the upsampled tensor with the phase weights' own rounding folded out (the phase sums
+    are rounded to the operand dtype once, so the comparison uses them)."""
+    from nlc_b200 import ops
+    B, H, W, Cin, Cout = shape
+    dt = _dt(prec)
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(11)
+    x = _rnd(torch.randn(B, Cin, H, W, generator=g).to(dev), dt)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev)
+    b = (torch.randn(Cout, generator=g) + 3.0).to(dev)
+    # reference with exactly the weights the kernel sees: per phase, the rounded 2x2 sums
+    ref = torch.zeros(B, Cout, 2 * H, 2 * W, device=dev)
+    packs = ops.upsample_phase_weights(w, dt)
+    for (a, bb), pk in packs.items():
+        k = pk.float().reshape(Cout, 2, 2, Cin).permute(0, 3, 1, 2)  # [Cout, Cin, 2, 2]
+        offs_r = [d for d, _ in ops._UP_ROWS[a]]
+        offs_c = [d for d, _ in ops._UP_ROWS[bb]]
+        xp = F.pad(x, (1, 1, 1, 1))
+        acc = b[None, :, None, None].expand(B, Cout, H, W).clone()
+        for i, dh in enumerate(offs_r):
+            for j, dw in enumerate(offs_c):
+                acc = acc + torch.einsum("oc,nchw->nohw", k[:, :, i, j], xp[:, :, 1 + dh:1 + dh + H, 1 + dw:1 + dw + W])
+        ref[:, :, a::2, bb::2] = acc
+    # ... which is the upsample + 3x3 conv up to the rounding of the summed weights
+    full = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, b, padding=1)
+    assert _rel(ref, full) < (2e-2 if prec == "bf16" else 2e-3)
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(tdt))
+    buf = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), device=dev)
+    st = ops.GnStats(torch.zeros(B * 4 * H * W // 32, Cout // 4, 2, device=dev))
+    o32 = ops.Act(buf, 0, Cout, st)
+    oop = ops.Act(torch.zeros(B, 2 * H, 2 * W, Cout, device=dev, dtype=tdt))
+    for (a, bb), pk in packs.items():
+        ops.conv_tc([xa], ops.upsample_phase_taps(0, 0, Cin, a, bb), pk, Cout, B, H, W, dt, bias=b, out_f32=o32, out_op=oop,
+                    stats=True, out_up=(a, bb))
+    torch.cuda.synchronize()
+    assert _rel(buf.permute(0, 3, 1, 2), ref) < 5e-5
+    assert _rel(oop.t.float().permute(0, 3, 1, 2), ref) < (8e-3 if prec == "bf16" else 1e-3)
+    gam, bet = torch.randn(Cout, generator=g).to(dev), torch.randn(Cout, generator=g).to(dev)
+    want = F.silu(F.group_norm(buf.permute(0, 3, 1, 2), 32, gam, bet, eps=1e-5))
+    y = ops.Act(torch.zeros(B, 2 * H, 2 * W, Cout, device=dev, dtype=tdt))
+    ws = torch.zeros(ops.groupnorm_ws(B, 4 * H * W, Cout, 32), device=dev)
+    ops.groupnorm(o32, 32, 1e-5, gam, bet, y, dt, ws, silu=True, use_stats=True)
+    assert _rel(y.t.float().permute(0, 3, 1, 2), want) < tol
