@@ -19,7 +19,7 @@ import torch
 
 from . import ops
 from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
-                     emit_groupnorm, run)
+                     emit_groupnorm, emit_upsample_conv3x3, run, upsample_conv_eligible)
 from .ops import Act
 
 GN_EPS = 1e-6
@@ -54,6 +54,8 @@ class _BlockW:
         _check_filter(sd, p + "skip.resample_filter")
         self.n0w, self.n0b = eng.dev32(g("norm0.weight")), eng.dev32(g("norm0.bias"))
         self.w0, self.b0 = eng.pack3x3(w0), eng.dev32(g("conv0.bias"))
+        # up blocks: conv0 runs at the low resolution as four sub-pixel phases (engine.emit_upsample_conv3x3)
+        self.w0_phase = ops.upsample_phase_weights(w0.to(eng.device), eng.op_dtype) if (up and with_emb) else None
         if with_emb:  # PureUNetBlock never applies norm1 (src/edm_networks.py:940-944)
             self.n1w, self.n1b = eng.dev32(g("norm1.weight")), eng.dev32(g("norm1.bias"))
         b1 = g("conv1.bias").float()
@@ -96,9 +98,14 @@ def _emit_block(pc, w, x, dest, emb=None):
         # activated tensor, written directly by the GroupNorm apply pass; the skip branch resamples x itself
         mode = 1 if w.up else 2
         src32 = x.f32
+        up_low = w.up and w.with_emb and upsample_conv_eligible(H, W)
+        if up_low:  # the activated tensor stays at the low resolution; conv0 computes conv(upsample(a0)) from it
+            a0 = eng.act_op("ub.a0", B, H, W, w.cin)
+            emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True)
         H, W = (2 * H, 2 * W) if w.up else (H // 2, W // 2)
-        a0 = eng.act_op("ub.a0r", B, H, W, w.cin)
-        emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True, resample=mode)
+        if not up_low:
+            a0 = eng.act_op("ub.a0r", B, H, W, w.cin)
+            emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True, resample=mode)
         xs = eng.act_op("ub.xs", B, H, W, w.cin)
         pc.add(lambda: ops.resample(src32, mode, None, xs, dt), "resample")
         skip_src = xs
@@ -108,7 +115,10 @@ def _emit_block(pc, w, x, dest, emb=None):
         res_dest = Feat(f32=eng.act_f32("ub.y", B, H, W, w.cout))
     if w.with_emb:
         h = eng.act_f32("ub.h", B, H, W, w.cout)
-        emit_conv3x3(pc, a0, w.w0, w.b0, w.cout, Feat(f32=h), rowvec=rowvec)
+        if (w.up or w.down) and up_low:
+            emit_upsample_conv3x3(pc, a0, w.w0_phase, w.b0, w.cout, Feat(f32=h), rowvec=rowvec)
+        else:
+            emit_conv3x3(pc, a0, w.w0, w.b0, w.cout, Feat(f32=h), rowvec=rowvec)
         a1 = eng.act_op("ub.a1", B, H, W, w.cout)
         emit_groupnorm(pc, h, w.n1w, w.n1b, _groups(w.cout), GN_EPS, a1, silu=True)
     else:

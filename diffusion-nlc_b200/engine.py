@@ -208,7 +208,7 @@ def emit_conv3x3(pc, src_op, w_packed, bias, Cout, dest, rowvec=None, resid=None
            "conv3x3 %dx%d %d->%d s%d B%d%s" % (Ho, Wo, src_op.C, Cout, stride, B, " +1x1" if extra_src is not None else ""))
 
 
-def emit_upsample_conv3x3(pc, src_op, phase_w, bias, Cout, dest):
+def emit_upsample_conv3x3(pc, src_op, phase_w, bias, Cout, dest, rowvec=None):
     """Upsample(with_conv) = nearest x2 followed by a 3x3 conv (src/unet_ddim.py:58-74), computed on the LOW-resolution
     operand `src_op` as four sub-pixel phase convolutions with 2x2 taps each (ops.upsample_phase_weights) that write
     their quarter of `dest` (2H x 2W) in place (nlc_conv_desc.out_up): 16 instead of 36 multiplies per output and no
@@ -220,13 +220,16 @@ def emit_upsample_conv3x3(pc, src_op, phase_w, bias, Cout, dest):
         for b in (0, 1):
             segs = ops.upsample_phase_taps(0, 0, src_op.C, a, b)
             pc.add(lambda segs=segs, w=phase_w[(a, b)], ab=(a, b): ops.conv_tc(
-                [src_op], segs, w, Cout, B, H, W, dt, bias=bias, out_f32=dest.f32, out_op=dest.op, stats=st, out_up=ab),
+                [src_op], segs, w, Cout, B, H, W, dt, bias=bias, rowvec=rowvec, out_f32=dest.f32, out_op=dest.op, stats=st,
+                out_up=ab),
                 "upconv3x3 phase %d%d %dx%d %d->%d B%d" % (a, b, H, W, src_op.C, Cout, B))
 
 
 def upsample_conv_eligible(H, W):
-    """The low-resolution conv must tile inside one image and write whole GroupNorm partial blocks."""
-    return H * W >= 128 and (H & (H - 1)) == 0 and (W & (W - 1)) == 0
+    """The low-resolution conv must tile inside one image and write whole GroupNorm partial blocks (NLC_UPCONV=0 keeps
+    the replicated-operand path for A/B measurements)."""
+    import os
+    return (H * W >= 128 and (H & (H - 1)) == 0 and (W & (W - 1)) == 0 and os.environ.get("NLC_UPCONV", "1") != "0")
 
 
 def emit_conv_in(pc, x_nchw, in_scale_fn, w_packed, bias, Cout, dest, w_f32=None):

@@ -327,7 +327,7 @@ class UNetModel:
                 # Upsample: nearest x2 then 3x3 conv (src/unet_ddim.py:69-74); the replicated operand is
                 # materialised once in the operand dtype
                 src32 = cur.f32
-                if upsample_conv_eligible(res, res) and os.environ.get("NLC_UPCONV", "1") != "0":
+                if upsample_conv_eligible(res, res):
                     # ... computed at the low resolution instead: four sub-pixel phase convs (engine.emit_upsample_conv3x3)
                     lowo = eng.act_op("up.low", B, res, res, cur.C)
                     dec.add(lambda src32=src32, lowo=lowo: ops.resample(src32, 0, None, lowo, dt))
