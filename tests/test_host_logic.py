@@ -124,3 +124,28 @@ def test_world_size_2_sharding_over_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_upsample_phase_weights_reproduce_upsample_then_conv():
+    """ops.upsample_phase_weights / upsample_phase_taps: the four sub-pixel phase kernels (summed rows / columns of a 3x3
+    kernel over two source rows / columns) are "nearest x2, then 3x3 conv with padding 1" (src/unet_ddim.py:58-74), checked
+    against torch on the CPU with the packed weights exactly as the kernels receive them (fp32 container)."""
+    import torch.nn.functional as F
+    from nlc_b200 import ops
+    from nlc_b200._lib import NLC_F32X3
+    g = torch.Generator().manual_seed(5)
+    B, Cin, Cout, H, W = 2, 8, 12, 6, 10
+    w, x = torch.randn(Cout, Cin, 3, 3, generator=g), torch.randn(B, Cin, H, W, generator=g)
+    want = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    got = torch.zeros_like(want)
+    packs = ops.upsample_phase_weights(w, NLC_F32X3)  # plain fp32 packing: [Cout, tap, Cin]
+    xp = F.pad(x, (1, 1, 1, 1))
+    for (a, b), pk in packs.items():
+        k = pk.reshape(Cout, 4, Cin)
+        taps = ops.upsample_phase_taps(0, 0, Cin, a, b)
+        assert [t[3:] for t in taps] == [(0, Cin)] * 4 and len(taps) == 4
+        acc = 0
+        for i, (_, dh, dw, _, _) in enumerate(taps):
+            acc = acc + torch.einsum("oc,nchw->nohw", k[:, i], xp[:, :, 1 + dh:1 + dh + H, 1 + dw:1 + dw + W])
+        got[:, :, a::2, b::2] = acc
+    assert (got - want).abs().max() < 1e-5 * want.abs().max()
