@@ -290,10 +290,22 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; the contract is ONE JSON line there
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION and =WARN; the contract is ONE JSON line there.
+        # Quieten those two levels and, whatever the level, send everything NCCL prints while the communicator comes up
+        # (eager init with device_id + one barrier) to stderr.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     B, R = CFG["batch"], CFG["R"]
     model, sigma_model = build_models(args.precision, dev)
