@@ -149,3 +149,24 @@ def test_upsample_phase_weights_reproduce_upsample_then_conv():
             acc = acc + torch.einsum("oc,nchw->nohw", k[:, i], xp[:, :, 1 + dh:1 + dh + H, 1 + dw:1 + dw + W])
         got[:, :, a::2, b::2] = acc
     assert (got - want).abs().max() < 1e-5 * want.abs().max()
+
+
+def test_ddnm_schedule_and_factory_helpers_without_a_gpu():
+    """Host logic of the SURVEY 8f modules that needs no device: the RePaint time-travel schedule equals the oracle's (and the
+    reference's own checks hold), channel-multiplier defaults of the factories (src/script_util.py:158-172), file-resume
+    helper of the evaluation drivers."""
+    from nlc_b200 import image_sample as IS, script_util as SU, svd_ddnm as SD
+    from oracle import ddnm as OD
+    for T, length, repeat in ((4, 2, 2), (10, 3, 3), (100, 1, 1), (25, 10, 2), (20, 5, 1)):
+        ts = SD.get_schedule_jump(T, length, repeat)
+        assert ts == OD.schedule_jump(T, length, repeat)
+        assert ts[0] == T - 1 and ts[-1] == -1 and all(abs(a - b) == 1 for a, b in zip(ts[:-1], ts[1:]))
+        # every index with budget is revisited (repeat - 1) more times
+        assert ts.count(0) == (repeat if length < T else 1)
+    assert SU._channel_mult("", 256) == (1, 1, 2, 2, 4, 4) and SU._channel_mult("", 32) == (1, 2, 2, 2)
+    assert SU._channel_mult("1,2,3", 64) == (1, 2, 3) and SU._channel_mult((1, 2), 64) == (1, 2)
+    with pytest.raises(ValueError):
+        SU._channel_mult("", 48)
+    assert IS._already_done(None, 0, 0, 4) is False
+    a = SD.compute_alpha(torch.linspace(1e-4, 2e-2, 1000), torch.tensor([0, 499, -1]))
+    assert a.shape == (3, 1, 1, 1) and float(a[2]) == 1.0 and float(a[0]) == float(1 - torch.tensor(1e-4))
