@@ -192,6 +192,13 @@ def cpu_port_rate(n_steps, batch, threads):
     return batch / (dt / n_steps * CFG["steps"]), dt
 
 
+def _unit():
+    """What one sampled CPU step is, for the `sample` text."""
+    if CFG.get("loop") == "ddnm_plus":
+        return "DDNM+ reverse steps (one network call each)"
+    return "Heun steps" if CFG["arch"] == "edm" else "NLC timesteps"
+
+
 def _select(args):
     CFG.clear()
     CFG.update(WORKLOADS[args.workload])
@@ -221,8 +228,8 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": CFG["label"], "per_gpu_batch": CFG["batch"]},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": "each step = %d NLC timesteps at batch %d of the workload on the oracle port "
-                                   "(torch fp32, %d threads, %.1f s per step), extrapolated linearly to %d timesteps"
+                         "sample": ("each step = %d " + _unit() + " at batch %d of the workload on the oracle port "
+                                    "(torch fp32, %d threads, %.1f s per step), extrapolated linearly to %d timesteps")
                                    % (n_steps, batch, threads, sum(d for _, d in per_step) / len(per_step),
                                       CFG["steps"])},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -496,8 +503,8 @@ def main():
         n_steps, batch = CPU_SAMPLE[CFG["arch"]]
         rate, dt = cpu_port_rate(n_steps, batch, threads)
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": "%d NLC timesteps at batch %d of the workload on the oracle port (torch fp32, %d threads, "
-                         "%.1f s), extrapolated linearly to %d timesteps" % (n_steps, batch, threads, dt, CFG["steps"])}
+               "sample": ("%d " + _unit() + " at batch %d of the workload on the oracle port (torch fp32, %d threads, "
+                          "%.1f s), extrapolated linearly to %d timesteps") % (n_steps, batch, threads, dt, CFG["steps"])}
 
     line = {
         "metric": CFG["metric"], "value": value, "unit": "images/s",
