@@ -135,9 +135,11 @@ def unet_forward(sd, x, t, return_feat=False):
     return (out, feat) if return_feat else out
 
 
-def sigma_forward(sd, feat):
+def sigma_forward(sd, feat, training=False):
     """SigmaModel, src/unet_ddim.py:493-529: per block [pad if odd] -> PureResnetBlock -> (AttnBlock in block 0)
-    -> Downsample; Flatten -> Linear -> BatchNorm1d (eval) -> GELU -> Linear -> [B,1,1,1]."""
+    -> Downsample; Flatten -> Linear -> BatchNorm1d (eval) -> GELU -> Linear -> [B,1,1,1].
+    training=True: BatchNorm1d normalises with the batch statistics (`sigma_model.train()`, src/experiments.py:643;
+    dropout is taken as 0, the running statistics are not updated here) — the forward the training step differentiates."""
     h = feat
     idx = 0
     n_layers = _count(sd, "down_layer") if any(k.startswith("down_layer.") for k in sd) else 0
@@ -156,8 +158,11 @@ def sigma_forward(sd, feat):
         idx += 1
     h = h.flatten(1)
     h = F.linear(h, sd["fc_layer.1.weight"], sd["fc_layer.1.bias"])
-    h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
-                     sd["fc_layer.2.bias"], training=False, eps=1e-5)
+    if training:
+        h = F.batch_norm(h, None, None, sd["fc_layer.2.weight"], sd["fc_layer.2.bias"], training=True, eps=1e-5)
+    else:
+        h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
+                         sd["fc_layer.2.bias"], training=False, eps=1e-5)
     h = F.gelu(h)
     out = F.linear(h, sd["final_mlp.weight"], sd["final_mlp.bias"])
     return out[:, :, None, None]

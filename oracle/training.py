@@ -4,7 +4,9 @@
 Only tests/ may import this.  The batch preparation follows :661-669 and `Scheduler.diffusion` (src/schedulers.py:323-329)
 and is pinned live against the reference's scheduler in tests/test_oracle_vs_reference.py; the optimizer side IS
 `torch.optim.AdamW` (:144) and `update_ema` (:233-236, src/nn_util.py:55-65), which the reference calls directly, so the
-oracle calls the same torch classes.
+oracle calls the same torch classes.  The sigma-model's train-mode forward (batch-statistics BatchNorm) is
+oracle/ddim_net.sigma_forward(training=True); tests/golden/train_step_tiny.pt pins a whole reference iteration (loss,
+gradients, updated parameters, EMA) against it.
 """
 import numpy as np
 import torch

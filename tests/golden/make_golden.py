@@ -561,6 +561,48 @@ def ssim():
     print("ssim.pt", os.path.getsize(os.path.join(HERE, "ssim.pt")))
 
 
+def train_step():
+    """One sigma-model training iteration of the reference (src/experiments.py:683-694) on its own modules: the DDIM
+    SigmaModel (src/unet_ddim.py:493-529, dropout 0) in train() mode on recorded encoder features, MSE against a target
+    noise level, backward, torch.optim.AdamW step and the EMA update -> train_step_tiny.pt (loss, every parameter's gradient,
+    the updated parameters and EMA copy).  The targets for a native backward pass."""
+    import copy
+    R = refimport.load()
+    torch.set_num_threads(4)
+    cfg = weights.CONFIGS["tiny"]
+    ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+    net = R.unet_ddim.SigmaModel(dropout=0.0, **cfg["sigma"])
+    net.load_state_dict(ssd)
+    net.train()
+    g = torch.Generator().manual_seed(71)
+    feat = torch.load(os.path.join(HERE, "nets_tiny.pt"), weights_only=True)["feat"]
+    feat = torch.cat([feat, feat.flip(0) * 0.7 + 0.1 * torch.randn(feat.shape, generator=g)])  # batch 4 for BatchNorm
+    dist_real = (1.0 + 0.2 * torch.randn(feat.shape[0], 1, 1, 1, generator=g))
+    optim = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=0.01)
+    ema = copy.deepcopy(list(net.parameters()))
+    dist_hat = net(feat) + 1
+    loss = torch.nn.MSELoss()(dist_real, dist_hat)
+    optim.zero_grad()
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in net.named_parameters()}
+    optim.step()
+    R.experiments  # (update_ema is src/nn_util.py:55-65: targ.mul_(rate).add_(src, alpha=1-rate))
+    for targ, src in zip(ema, net.parameters()):
+        targ.detach().mul_(0.999).add_(src.detach(), alpha=1 - 0.999)
+    # the sigma-model has 3.9 M parameters: every tensor is stored as (L2 norm, sum, first 32 entries), the small head
+    # layers in full
+    def digest(t):
+        t = t.detach().double().reshape(-1)
+        return dict(norm=t.norm().clone(), sum=t.sum().clone(), head=t[:32].clone(), full=t.float().clone() if t.numel() <= 4096 else None)
+
+    gold = dict(feat=feat, dist_real=dist_real, dist_hat=dist_hat.detach(), loss=loss.detach(),
+                grads={n: digest(v) for n, v in grads.items()},
+                new_params={n: digest(p) for n, p in net.named_parameters()},
+                ema={n: digest(e) for (n, _), e in zip(net.named_parameters(), ema)})
+    torch.save(gold, os.path.join(HERE, "train_step_tiny.pt"))
+    print("train_step_tiny.pt", os.path.getsize(os.path.join(HERE, "train_step_tiny.pt")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         globals()[sys.argv[1]]()

@@ -332,3 +332,39 @@ def test_ssim(golden_dir):
         for case in size.values():
             assert torch.equal(M.ssim3d(case["sample"], case["orig"]), case["ssim"])
     assert float(g["r32"]["same"]["ssim"].min()) == 1.0
+
+
+def test_sigma_model_training_iteration(golden_dir):
+    """tests/golden/train_step_tiny.pt: one training iteration of the reference's DDIM SigmaModel in train() mode
+    (src/experiments.py:683-694): the oracle's functional forward with batch-statistics BatchNorm reproduces the loss, and
+    autograd through it every parameter gradient, the AdamW update and the EMA copy (digests: L2 norm, sum, first entries;
+    small tensors in full).  These are the targets a native backward pass has to hit."""
+    from oracle import training as OT
+    g = load(golden_dir, "train_step_tiny.pt")
+    cfg = weights.CONFIGS["tiny"]
+    ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+    names = [n for n in g["grads"]]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    sd = dict(ssd)
+    sd.update(params)
+    dist_hat = ddim_net.sigma_forward(sd, g["feat"], training=True) + 1
+    assert (dist_hat.detach() - g["dist_hat"]).abs().max() <= 2e-6 * g["dist_hat"].abs().max()
+    loss = torch.nn.functional.mse_loss(dist_hat, g["dist_real"])
+    assert abs(loss.item() - g["loss"].item()) <= 2e-6 * abs(g["loss"].item())
+    opt = OT.AdamWEma([params[n] for n in names], lr=1e-3, weight_decay=0.01, ema_rate=0.999)
+    loss.backward()
+
+    def check(t, ref, tol, what):
+        t = t.detach().double().reshape(-1)
+        scale = max(float(ref["norm"]), 1e-12)
+        assert abs(float(t.norm()) - float(ref["norm"])) <= tol * scale, what
+        assert (t[:32] - ref["head"]).abs().max() <= tol * max(float(ref["head"].abs().max()), scale / t.numel() ** 0.5), what
+        if ref["full"] is not None:
+            assert (t.float() - ref["full"]).abs().max() <= tol * max(float(ref["full"].abs().max()), 1e-12), what
+
+    for n in names:
+        check(params[n].grad, g["grads"][n], 2e-4, ("grad", n))
+    opt.step()
+    for n, e in zip(names, opt.ema):
+        check(params[n], g["new_params"][n], 1e-5, ("param", n))
+        check(e, g["ema"][n], 1e-5, ("ema", n))
