@@ -197,6 +197,34 @@ def test_training_batch_preparation(R):
     assert torch.equal(got_x, noisy_x) and torch.equal(got_d, dist_real) and torch.equal(got_n, new_noise)
 
 
+def test_operator_edge_cases(R):
+    """Degenerate instances the reference accepts: nothing / everything missing, ratio 1, a rank-deficient general matrix
+    (zero-guarded pseudo-inverse), batch 1."""
+    ref = R.svd_operators
+    Rr, C = 32, 3
+    n = C * Rr * Rr
+    none, every = torch.zeros(0, dtype=torch.long), torch.arange(n)
+    Am = torch.randn(10, 40)
+    Am[7] = Am[2]  # rank 9: one singular value falls under the 1e-3 threshold
+    pairs = [
+        (ref.Inpainting(C, Rr, none, "cpu"), O.Inpainting(C, Rr, none), n),
+        (ref.Inpainting(C, Rr, every, "cpu"), O.Inpainting(C, Rr, every), n),
+        (ref.WalshHadamardCS(C, Rr, 1, torch.randperm(Rr * Rr), "cpu"), None, n),
+        (ref.SuperResolution(C, Rr, 1, "cpu"), O.SuperResolution(C, Rr, 1), n),
+        (ref.GeneralA(Am.clone()), O.GeneralA(Am.clone()), 40),
+    ]
+    pairs[2] = (pairs[2][0], O.WalshHadamardCS(C, Rr, 1, pairs[2][0].perm), n)
+    for B in (1, 3):
+        for a, b, d in pairs:
+            x, x0 = torch.rand(B, d) * 2 - 1, torch.randn(B, d)
+            y = a.A(x.clone())
+            assert y.shape == b.A(x.clone()).shape and torch.equal(y, b.A(x.clone()))
+            assert torch.equal(a.At(y.clone()), b.At(y.clone()))
+            assert torch.equal(a.A_pinv(y.clone()), b.A_pinv(y.clone()))
+            assert torch.equal(x0 - a.A_pinv(a.A(x0.clone()) - y), b.project(x0, y))
+    assert pairs[1][0].A(torch.zeros(2, n)).shape == (2, 0)  # everything missing: an empty measurement
+
+
 def test_ssim(R):
     """oracle/metrics.ssim3d against the unmodified basicsr code behind image_sample.py:571-582, live, random sizes."""
     import sys
