@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nlc_b200  # noqa: E402,F401
 from nlc_b200 import svd_operators as P  # noqa: E402
-from oracle import operators as O  # noqa: E402  (blur kernel construction helpers only)
+from nlc_b200.constraint_functions import _gauss_kernel  # noqa: E402
 
 
 def timeit(fn, n=20, warm=5):
@@ -64,7 +64,7 @@ def main():
         "sr_averagepooling x4": P.SuperResolution(C, R, 4, dev),
         "inpainting box": P.Inpainting(C, R, missing, dev),
         "cs_walshhadamard x4": P.WalshHadamardCS(C, R, 4, torch.randperm(R * R, generator=gen), dev),
-        "deblur_gauss": P.Deblurring(O.gauss_kernel(), C, R, dev),
+        "deblur_gauss": P.Deblurring(_gauss_kernel(5, 10), C, R, dev),
         "denoising": P.Denoising(C, R, dev),
     }
     NBUF = 4  # rotate over four input / output sets (>= 0.5 GB per round) so that nothing is served from the 126 MB L2
