@@ -238,9 +238,9 @@ def run_reference(args):
 
 
 def build_models(precision, dev):
-    """The workload's UNet + sigma-model executors with seeded synthetic weights (oracle/weights.py only provides the
-    state_dicts; no oracle arithmetic runs on this arm)."""
-    from oracle import weights
+    """The workload's UNet + sigma-model executors with seeded synthetic weights (nlc_b200.synthetic_weights: random-init
+    state_dicts of the named architectures; nothing under oracle/ is imported on this arm)."""
+    from nlc_b200 import synthetic_weights as weights
     if CFG["arch"] == "edm":
         from nlc_b200.edm_networks import SigmaModel, SongUNet
         cfg = dict(weights.EDM_CONFIGS[CFG["name"]])
