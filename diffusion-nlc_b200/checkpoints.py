@@ -9,7 +9,8 @@
 * EDM network pickles: `pickle.load(f)['ema']` is an `EDMPrecond` whose `.model` is the SongUNet
   (edm_image_sample.py:152-156).  Those pickles embed the defining module's SOURCE and re-execute it on load
   (torch_utils/persistence.py); here they are read with a restricted unpickler that never executes it: persistent objects
-  come back as inert records of their `__dict__`, from which the parameter / buffer tree is walked.
+  come back as inert records of their `__dict__`, from which the parameter / buffer tree is walked; ordinary classes of
+  the training code (`src.*`, `training.*`) come back as inert stand-ins in the same way.
 """
 import collections
 import io
@@ -71,16 +72,49 @@ class _AttrDict(dict):
 
 
 class _RestrictedUnpickler(pickle.Unpickler):
-    _ALLOWED_PREFIXES = ("torch", "collections", "numpy", "builtins", "_codecs")
+    # what a pickled module tree needs to come back as data: tensor / storage rebuild helpers, containers, plain builtins
+    _ALLOWED_MODULES = ("torch._utils", "torch.storage", "torch.nn.parameter", "torch.nn.modules.container", "torch._tensor",
+                        "numpy.core.multiarray", "numpy._core.multiarray")
+    _ALLOWED_NAMES = {
+        "collections": {"OrderedDict"},
+        "builtins": {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "complex", "bytes", "bytearray",
+                     "str", "slice", "range", "object"},
+        "copyreg": {"_reconstructor"},
+        "_codecs": {"encode"},
+        "numpy": {"ndarray", "dtype"},
+        "torch": {"Size", "device", "Tensor", "FloatStorage", "HalfStorage", "BFloat16Storage", "DoubleStorage", "LongStorage",
+                  "IntStorage", "BoolStorage", "ByteStorage", "UntypedStorage", "float32", "float16", "bfloat16", "float64",
+                  "int64", "int32", "bool", "uint8"},
+    }
+    # model-code namespaces: classes from these are NOT imported; they come back as inert stand-ins that only hold the
+    # pickled __dict__ (a plain nn.Module of the training code, e.g. this repository's own non-persistent
+    # src.edm_networks.SongUNet inside a persistent EDMPrecond)
+    _MODEL_PREFIXES = ("src", "training", "torch_utils", "dnnlib")
 
     def find_class(self, module, name):
         if module == "torch_utils.persistence" and name == "_reconstruct_persistent_obj":
             return _Record
         if module.startswith("dnnlib") and name == "EasyDict":
             return _AttrDict
-        if module.split(".")[0] in self._ALLOWED_PREFIXES:
+        if module == "torch.storage" and name == "_load_from_bytes":
+            return _load_storage_from_bytes  # torch's own helper would torch.load() the blob with the full unpickler
+        if module in self._ALLOWED_MODULES or name in self._ALLOWED_NAMES.get(module, ()):
             return super().find_class(module, name)
+        if module.split(".")[0] in self._MODEL_PREFIXES:
+            return type(str(name), (_Inert,), {"__module__": "nlc_b200.checkpoints.stub." + module})
         raise pickle.UnpicklingError("refusing to import %s.%s from a checkpoint" % (module, name))
+
+
+def _load_storage_from_bytes(b):
+    """torch.storage._load_from_bytes with the weights-only unpickler (storages of plain tensors need nothing else)."""
+    return torch.load(io.BytesIO(b), weights_only=True)
+
+
+class _Inert:
+    """Stand-in for a class of the training code: holds whatever state the pickle sets, runs nothing."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"_state": state})
 
 
 def _module_state(obj):

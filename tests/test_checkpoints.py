@@ -102,3 +102,30 @@ def test_edm_pickle_without_executing_its_source():
 
     with pytest.raises(pickle.UnpicklingError):
         CK.edm_state_dict(io.BytesIO(pickle.dumps(dict(ema=Evil()))))
+
+
+def test_edm_pickle_written_by_the_reference_itself():
+    """A network pickle produced with the reference's own classes and its vendored torch_utils.persistence (a persistent
+    EDMPrecond around the module's plain SongUNet, persistent layers inside): the reader returns exactly
+    `pickle.load(f)['ema'].model.state_dict()` (edm_image_sample.py:152-156) without importing src.* or running the
+    embedded source."""
+    import importlib
+    sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    import refimport
+    if not refimport.available():
+        pytest.skip("reference tree not present")
+    refimport.load()
+    EN = importlib.import_module("src.edm_networks")
+    torch.manual_seed(0)
+    net = EN.EDMPrecond(img_resolution=16, img_channels=3, model_type="SongUNet", model_channels=32, channel_mult=[1, 2],
+                        num_blocks=1, attn_resolutions=[8])
+    blob = pickle.dumps(dict(ema=net, loss_fn=None))
+    want = net.model.state_dict()
+    got = CK.edm_state_dict(io.BytesIO(blob))
+    assert list(got) == list(want) and all(torch.equal(got[k], want[k]) for k in want)
+    for hostile in ((__import__("os").system, ("true",)), (eval, ("1+1",)), (torch.hub.load, ("x", "y"))):
+        class Evil:
+            def __reduce__(self, _h=hostile):
+                return _h
+        with pytest.raises(pickle.UnpicklingError):
+            CK.edm_state_dict(io.BytesIO(pickle.dumps(dict(ema=Evil()))))
