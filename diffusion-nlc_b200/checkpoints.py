@@ -45,9 +45,17 @@ def eps_state_dict(ckpt, trainable=None):
     return sd
 
 
-def load_eps_model(model, ckpt_file):
-    """`model.load_state_dict` from a `.pt` / `.ckpt` file, EMA weights applied (run_image_experiment.py:190-212)."""
-    return model.load_state_dict(eps_state_dict(load_state_dict(ckpt_file, weights_only=False)))
+def load_eps_model(model, ckpt_file, trust_pickle=False):
+    """`model.load_state_dict` from a `.pt` / `.ckpt` file, EMA weights applied (run_image_experiment.py:190-212).
+    The file is read with torch's weights-only loader (tensors, containers and plain scalars - all these formats hold);
+    `trust_pickle=True` is the explicit opt-in to the full unpickler for a checkpoint that carries other objects."""
+    try:
+        ckpt = load_state_dict(ckpt_file, weights_only=True)
+    except pickle.UnpicklingError:
+        if not trust_pickle:
+            raise
+        ckpt = load_state_dict(ckpt_file, weights_only=False)
+    return model.load_state_dict(eps_state_dict(ckpt))
 
 
 # ------------------------------------------------------------------------------------------------ EDM pickles
@@ -72,9 +80,8 @@ class _AttrDict(dict):
 
 
 class _RestrictedUnpickler(pickle.Unpickler):
-    # what a pickled module tree needs to come back as data: tensor / storage rebuild helpers, containers, plain builtins
-    _ALLOWED_MODULES = ("torch._utils", "torch.storage", "torch.nn.parameter", "torch.nn.modules.container", "torch._tensor",
-                        "numpy.core.multiarray", "numpy._core.multiarray")
+    # what a pickled module tree needs to come back as data: EXACT (module, name) pairs only - a whole-module allow-list
+    # would hand out helpers such as torch._utils._import_dotted_name, which resolves any callable by name
     _ALLOWED_NAMES = {
         "collections": {"OrderedDict"},
         "builtins": {"set", "frozenset", "dict", "list", "tuple", "int", "float", "bool", "complex", "bytes", "bytearray",
@@ -82,10 +89,17 @@ class _RestrictedUnpickler(pickle.Unpickler):
         "copyreg": {"_reconstructor"},
         "_codecs": {"encode"},
         "numpy": {"ndarray", "dtype"},
+        "numpy.core.multiarray": {"_reconstruct", "scalar"},
+        "numpy._core.multiarray": {"_reconstruct", "scalar"},
+        "torch._utils": {"_rebuild_tensor", "_rebuild_tensor_v2", "_rebuild_parameter", "_rebuild_parameter_with_state"},
+        "torch._tensor": {"_rebuild_from_type_v2"},
+        "torch.nn.parameter": {"Parameter"},
         "torch": {"Size", "device", "Tensor", "FloatStorage", "HalfStorage", "BFloat16Storage", "DoubleStorage", "LongStorage",
                   "IntStorage", "BoolStorage", "ByteStorage", "UntypedStorage", "float32", "float16", "bfloat16", "float64",
                   "int64", "int32", "bool", "uint8"},
     }
+    # torch.nn container / layer classes of a pickled module tree are never instantiated: inert stand-ins, like the
+    # training code's own classes
     # model-code namespaces: classes from these are NOT imported; they come back as inert stand-ins that only hold the
     # pickled __dict__ (a plain nn.Module of the training code, e.g. this repository's own non-persistent
     # src.edm_networks.SongUNet inside a persistent EDMPrecond)
@@ -98,9 +112,11 @@ class _RestrictedUnpickler(pickle.Unpickler):
             return _AttrDict
         if module == "torch.storage" and name == "_load_from_bytes":
             return _load_storage_from_bytes  # torch's own helper would torch.load() the blob with the full unpickler
-        if module in self._ALLOWED_MODULES or name in self._ALLOWED_NAMES.get(module, ()):
+        if "." in name:  # protocol-4 dotted attribute paths ("sys.modules", "os.system" ...) are never needed
+            raise pickle.UnpicklingError("refusing the dotted name %s.%s from a checkpoint" % (module, name))
+        if name in self._ALLOWED_NAMES.get(module, ()):
             return super().find_class(module, name)
-        if module.split(".")[0] in self._MODEL_PREFIXES:
+        if module.split(".")[0] in self._MODEL_PREFIXES or module.startswith("torch.nn.modules."):
             return type(str(name), (_Inert,), {"__module__": "nlc_b200.checkpoints.stub." + module})
         raise pickle.UnpicklingError("refusing to import %s.%s from a checkpoint" % (module, name))
 

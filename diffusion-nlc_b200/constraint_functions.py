@@ -129,10 +129,12 @@ class Constraint_Function:
     def loss(self, x, y):
         """(||A x - y||_1, ||inv_transform(y) - x||_1) per sample, on the CPU like the reference."""
         y_hat = self.transform(x)
-        key = (y.data_ptr(), tuple(y.shape))
-        if self._xhat_cache is None or self._xhat_cache[0] != key:
-            self._xhat_cache = (key, self.inv_transform(y))  # y is fixed for a whole batch
-        x_hat = self._xhat_cache[1]
+        # y is fixed for a whole batch: A^+ y is cached against the tensor OBJECT (held, so its address cannot be reused
+        # by another measurement) and its in-place version counter (a refilled buffer invalidates the entry)
+        c = self._xhat_cache
+        if c is None or c[0] is not y or c[1] != y._version:
+            c = self._xhat_cache = (y, y._version, self.inv_transform(y))
+        x_hat = c[2]
         fwd = ops_svd.l1_diff_rows(y_hat, y.reshape(y.shape[0], -1))
         bwd = ops_svd.l1_diff_rows(x_hat, x)
         return fwd.cpu(), bwd.cpu()

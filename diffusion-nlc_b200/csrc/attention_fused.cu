@@ -305,13 +305,14 @@ using namespace nlc;
 template <int DH>
 static int launch_fused(nlc_ctx* ctx, const FaParams& p) {
     using Cfg = FaCfg<DH>;
-    static bool configured = false;
-    if (!configured) {
+    NLC_REQUIRE_DEVICE(ctx);
+    static PerDeviceFlag configured;
+    if (!configured[ctx->device]) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
         // two CTAs per SM need the whole 228 KB as shared memory (the default carveout only guarantees one)
         NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_fused_kernel<DH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                             cudaSharedmemCarveoutMaxShared));
-        configured = true;
+        configured[ctx->device] = true;
     }
     const int slots = Cfg::kCtasPerSm * ctx->sm_count;
     attn_fused_kernel<DH><<<p.n_tiles < slots ? p.n_tiles : slots, kFaThreads, Cfg::kSmem, p.stream>>>(p);

@@ -44,7 +44,25 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: one flag per (kernel instantiation, device),
+// not one per process, so a second context on another GPU configures its own copy of the function.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool& operator[](int dev) { return done[dev & 63]; }
+};
+
 }  // namespace nlc
+
+// The entry points that configure / launch kernels with opt-in shared memory run on the CURRENT device: it must be the
+// context's (one nlc_ctx per (process, device); the caller selects the device, as torch.cuda.set_device does).
+#define NLC_REQUIRE_DEVICE(ctx)                                                                                   \
+    do {                                                                                                          \
+        int _cur = -1;                                                                                            \
+        NLC_CHECK_CUDA(cudaGetDevice(&_cur));                                                                     \
+        if (_cur != (ctx)->device)                                                                                \
+            return nlc::set_error(NLC_EINVAL, "%s: the current CUDA device is %d but the context belongs to %d", \
+                                  __func__, _cur, (ctx)->device);                                                 \
+    } while (0)
 
 struct nlc_ctx {
     int device;

@@ -646,14 +646,14 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
 template <int BLOCK_N, int MODE, bool CTA2>
-static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream) {
+static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream, int device) {
     using Cfg = ConvCfg<BLOCK_N, CTA2, MODE == 2>;
     constexpr int kLaunchThreads = MODE == 2 ? kThreadsX3 : kThreads;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceFlag configured;
+    if (!configured[device]) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, CTA2>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        configured = true;
+        configured[device] = true;
     }
     if (CTA2) {
         cudaLaunchConfig_t cfg;
@@ -679,6 +679,7 @@ using namespace nlc;
 extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && d, "nlc_conv_tc: null argument");
+    NLC_REQUIRE_DEVICE(ctx);
     NLC_REQUIRE(dtype_valid(d->dtype), "nlc_conv_tc: dtype must be NLC_BF16, NLC_F16, NLC_F32 or NLC_F32X3");
     const bool x3 = d->dtype == NLC_F32X3;
     const bool tf32 = !dtype_is16(d->dtype);  // fp32 containers
@@ -835,23 +836,23 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     if (pair) {
         const int pairs = p.num_tiles < ctx->sm_count / 2 ? p.num_tiles : ctx->sm_count / 2;
         if (tf32) {
-            if (block_n == 256) return launch_conv<256, 1, true>(p, 2 * pairs, stream);
-            return launch_conv<128, 1, true>(p, 2 * pairs, stream);
+            if (block_n == 256) return launch_conv<256, 1, true>(p, 2 * pairs, stream, ctx->device);
+            return launch_conv<128, 1, true>(p, 2 * pairs, stream, ctx->device);
         }
-        if (block_n == 256) return launch_conv<256, 0, true>(p, 2 * pairs, stream);
-        return launch_conv<128, 0, true>(p, 2 * pairs, stream);
+        if (block_n == 256) return launch_conv<256, 0, true>(p, 2 * pairs, stream, ctx->device);
+        return launch_conv<128, 0, true>(p, 2 * pairs, stream, ctx->device);
     }
     const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
     if (x3) {
-        if (block_n == 128) return launch_conv<128, 2, false>(p, grid, stream);
-        return launch_conv<64, 2, false>(p, grid, stream);
+        if (block_n == 128) return launch_conv<128, 2, false>(p, grid, stream, ctx->device);
+        return launch_conv<64, 2, false>(p, grid, stream, ctx->device);
     }
     if (tf32) {
-        if (block_n == 256) return launch_conv<256, 1, false>(p, grid, stream);
-        if (block_n == 128) return launch_conv<128, 1, false>(p, grid, stream);
-        return launch_conv<64, 1, false>(p, grid, stream);
+        if (block_n == 256) return launch_conv<256, 1, false>(p, grid, stream, ctx->device);
+        if (block_n == 128) return launch_conv<128, 1, false>(p, grid, stream, ctx->device);
+        return launch_conv<64, 1, false>(p, grid, stream, ctx->device);
     }
-    if (block_n == 256) return launch_conv<256, 0, false>(p, grid, stream);
-    if (block_n == 128) return launch_conv<128, 0, false>(p, grid, stream);
-    return launch_conv<64, 0, false>(p, grid, stream);
+    if (block_n == 256) return launch_conv<256, 0, false>(p, grid, stream, ctx->device);
+    if (block_n == 128) return launch_conv<128, 0, false>(p, grid, stream, ctx->device);
+    return launch_conv<64, 0, false>(p, grid, stream, ctx->device);
 }

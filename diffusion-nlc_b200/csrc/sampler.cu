@@ -493,11 +493,12 @@ extern "C" int nlc_dynamic_threshold(nlc_ctx* ctx, float* x, int B, int d, doubl
     const float lo = floorf(rank);
     const int rank_lo = static_cast<int>(lo), rank_hi = static_cast<int>(ceilf(rank));
     const size_t smem = static_cast<size_t>(kSelCopies) * kSelBins * sizeof(uint32_t);
-    static bool configured = false;
-    if (!configured) {
+    NLC_REQUIRE_DEVICE(ctx);
+    static nlc::PerDeviceFlag configured;
+    if (!configured[ctx->device]) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(dynamic_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-        configured = true;
+        configured[ctx->device] = true;
     }
     dynamic_threshold_kernel<<<B, 1024, smem, stream>>>(x, d, rank_lo, rank_hi, rank - lo, max_value, s_out);
     NLC_CHECK_LAUNCH();

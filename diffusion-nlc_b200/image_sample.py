@@ -49,6 +49,51 @@ def _fid(experiment, images_dir):
     return fn(images_dir) if (fn is not None and images_dir is not None) else None
 
 
+class BatchStreams:
+    """Noise streams of a run whose batches are dealt round-robin to `world` ranks.
+
+    The un-sharded reference draws everything from two sequential streams: x_T of batch i is the i-th draw of the CPU
+    generator `experiment.new_gen()` (src/experiments.py:260-271) and every step's z comes from the device's default
+    generator (src/schedulers.py:438...).  A rank that simply started both streams at their beginning would hand its
+    first batch the noise of batch 0 - every rank the same images.  Here each rank REPLAYS the global streams and
+    discards the draws that belong to batches it does not own (the policy of parallel.sharded_noise), so - with every
+    rank seeded alike, as torch.manual_seed / torch.cuda.manual_seed_all(seed) do - the union of the shards is the
+    un-sharded run, sample for sample.  (A NaN early exit, which shortens one batch's draws, is not replayed.)"""
+
+    def __init__(self, experiment, shape, rank=0, world=1, device_draws_per_batch=0, host_draws_per_batch=1):
+        self.shape, self.rank, self.world = tuple(shape), rank, world
+        self.device = experiment.device
+        self.gen = experiment.new_gen()
+        self.n_dev, self.n_host = device_draws_per_batch, host_draws_per_batch
+        self.next_batch = 0
+
+    def advance_to(self, i):
+        """Discard the draws of batches [next_batch, i); returns the CPU generator positioned at batch i."""
+        for _ in range(self.next_batch, i):
+            for _ in range(self.n_host):
+                torch.randn(self.shape, generator=self.gen)
+            for _ in range(self.n_dev):
+                torch.randn(self.shape, device=self.device)
+        self.next_batch = i + 1
+        return self.gen
+
+
+def device_draws_per_batch(experiment, sampling="denoise", max_T=None, new_eta=None):
+    """How many torch.randn_like(x0) calls one batch makes on the device generator (Scheduler.pred_xprev draws iff the
+    scheduler is a DDPM kind or eta > 0; `new_eta` replaces eta for the last step, src/experiments.py:347-348)."""
+    sch = experiment.scheduler
+    steps = len(sch.timesteps_host) - 1 if hasattr(sch, "timesteps_host") else len(sch.timesteps) - 1
+    if sampling == "project" and max_T is not None:
+        steps = max_T
+    always = sch.kind in ("ddpm", "ddpm_orig")
+    n = steps if (always or float(sch.eta) > 0) else 0
+    if new_eta is not None and not always:
+        last = 1 if float(new_eta) > 0 else 0
+        first = steps - 1 if float(sch.eta) > 0 else 0
+        n = first + last
+    return n
+
+
 def evaluate_unconstraint(experiment, n_samples, images_dir, norm_init_noise=False, style="base", sampling="denoise",
                           norm_eps=False, refine_prior_sigma=False, sigma_estimate_rate=(1, 0, 0), max_T=None,
                           sigma_pred_threshold=1000, new_eta=None, recal_sigma_prev=False, return_log=False,
@@ -58,11 +103,13 @@ def evaluate_unconstraint(experiment, n_samples, images_dir, norm_init_noise=Fal
     batch_size = experiment.batch_size
     n_batches = math.ceil(n_samples / batch_size)
     shape = (batch_size,) + tuple(experiment.data_shape)
-    gen = experiment.new_gen()
+    streams = BatchStreams(experiment, shape, rank, world,
+                           device_draws_per_batch(experiment, sampling, max_T, new_eta))
     return_lists, kept = [], []
     for i in range(rank, n_batches, world):
         if _already_done(images_dir, rank, i, batch_size):
             continue
+        gen = streams.advance_to(i)
         if sampling == "project":
             sample, return_list = experiment.projection_loop(
                 shape=shape, gen=gen, norm_init_noise=norm_init_noise, style=style, constrain_fn=None, norm_eps=norm_eps,
@@ -113,13 +160,19 @@ def evaluate_constraint(experiment, data_loader, Constraint, images_dir, n_sampl
     Returns (log_dict, return_list) with the reference's keys (`mse`, `psner` [sic], `ssim`, `const_f_loss`,
     `const_b_loss`, `const_orig_loss`, `fid`, `full_log`, `full_results`); the means are over all ranks' samples."""
     device = experiment.device
-    gen = experiment.new_gen()
+    streams = None
     lists = {k: [] for k in ("mse", "psnr", "ssim", "const_f", "const_b", "const_orig")}
     full_results, return_list = [], None
     for i, (x_orig, _classes) in enumerate(data_loader):
         if i % world != rank:
             continue
         batch_size = x_orig.shape[0]
+        if streams is None:
+            # x_T is one CPU draw per batch, or (prior_xt) one more device draw; then the per-step draws
+            n_dev = device_draws_per_batch(experiment, sampling, max_T, new_eta) + (1 if prior_xt else 0)
+            streams = BatchStreams(experiment, (batch_size,) + tuple(experiment.data_shape), rank, world, n_dev,
+                                   host_draws_per_batch=0 if prior_xt else 1)
+        gen = streams.advance_to(i)
         x_orig = x_orig.to(device)
         batch_x = 2 * x_orig - 1.0
         if _already_done(images_dir, rank, i, batch_size):

@@ -222,6 +222,10 @@ class Scheduler:
         beta_t = (s_t ** 2 - s_p ** 2) / (s_t ** 2 + 1)
         a_t, a_p = 1 / (s_t ** 2 + 1), 1 / (s_p ** 2 + 1)
         self.min_var_coef = beta_t * (1 - a_p) / (1 - a_t)
+        if self.device.type != "cpu":
+            # a schedule set after .to(device): refresh the host / device snapshots the loops and pred_xprev read
+            # (timesteps_host, sigma_table, slopes_table, min_var_coef_host), which .to() takes
+            self.to(self.device)
 
     # ---------------------------------------------------------------- per-step device work
     def get_eps_logvar(self, sigma_t, sigma_prev, learned_logvar=None):

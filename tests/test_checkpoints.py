@@ -129,3 +129,43 @@ def test_edm_pickle_written_by_the_reference_itself():
                 return _h
         with pytest.raises(pickle.UnpicklingError):
             CK.edm_state_dict(io.BytesIO(pickle.dumps(dict(ema=Evil()))))
+
+
+def test_restricted_unpickler_refuses_helper_and_dotted_name_bypasses():
+    """The allow-list is exact (module, name) pairs: torch._utils._import_dotted_name (which resolves ANY callable by
+    name) and protocol-4 dotted attribute paths must be refused, not resolved."""
+    import torch._utils
+
+    class ViaHelper:
+        def __reduce__(self):
+            return (torch._utils._import_dotted_name, ("os.getcwd",))
+
+    with pytest.raises(pickle.UnpicklingError):
+        CK.edm_state_dict(io.BytesIO(pickle.dumps(dict(ema=ViaHelper()))))
+    # protocol 4 STACK_GLOBAL with a dotted name: ('torch._utils', 'sys.modules')
+    payload = (b"\x80\x04" + b"\x8c\x0ctorch._utils" + b"\x8c\x0bsys.modules" + b"\x93" + b".")
+    with pytest.raises(pickle.UnpicklingError):
+        CK._RestrictedUnpickler(io.BytesIO(payload)).load()
+    for mod, name in (("torch._utils", "_import_dotted_name"), ("torch.storage", "_load_from_bytes_evil"),
+                      ("torch._tensor", "Tensor"), ("numpy.core.multiarray", "frombuffer")):
+        with pytest.raises(pickle.UnpicklingError):
+            CK._RestrictedUnpickler(io.BytesIO(b"")).find_class(mod, name)
+
+
+def test_load_eps_model_uses_the_weights_only_loader(tmp_path):
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("1+1",))
+
+    class Sink:
+        def load_state_dict(self, sd):
+            self.sd = sd
+            return self
+
+    good = tmp_path / "good.pt"
+    torch.save({"w": torch.arange(4.0)}, good)
+    assert torch.equal(CK.load_eps_model(Sink(), str(good)).sd["w"], torch.arange(4.0))
+    bad = tmp_path / "bad.pt"
+    torch.save({"w": Evil()}, bad)
+    with pytest.raises(pickle.UnpicklingError):
+        CK.load_eps_model(Sink(), str(bad))

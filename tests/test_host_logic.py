@@ -170,3 +170,40 @@ def test_ddnm_schedule_and_factory_helpers_without_a_gpu():
     assert IS._already_done(None, 0, 0, 4) is False
     a = SD.compute_alpha(torch.linspace(1e-4, 2e-2, 1000), torch.tensor([0, 499, -1]))
     assert a.shape == (3, 1, 1, 1) and float(a[2]) == 1.0 and float(a[0]) == float(1 - torch.tensor(1e-4))
+
+
+def test_batch_streams_shards_reproduce_the_unsharded_noise():
+    """image_sample.BatchStreams: with batches dealt round-robin to 2 ranks, each rank replays the global x_T stream (CPU
+    generator) and the per-step device stream and discards the draws of the batches it does not own, so the union of the
+    shards equals the un-sharded run (and no two ranks start from the same noise)."""
+    import types
+    from nlc_b200 import image_sample as IS
+    shape, n_batches, n_steps = (3, 2, 4, 4), 5, 3
+
+    def run(rank, world):
+        exp = types.SimpleNamespace(device=torch.device("cpu"), new_gen=lambda: torch.manual_seed(11))
+        st = IS.BatchStreams(exp, shape, rank, world, device_draws_per_batch=n_steps)
+        out = {}
+        for i in range(rank, n_batches, world):
+            gen = st.advance_to(i)
+            xT = torch.randn(shape, generator=gen)
+            # (device == cpu here: the "device" default generator is the same global one manual_seed() returned, which is
+            #  exactly the un-sharded reference's situation on a CPU run)
+            zs = [torch.randn(shape) for _ in range(n_steps)]
+            out[i] = (xT, zs)
+        return out
+
+    whole = run(0, 1)
+    parts = {**run(0, 2), **run(1, 2)}
+    assert sorted(parts) == sorted(whole) == list(range(n_batches))
+    for i in whole:
+        assert torch.equal(parts[i][0], whole[i][0])
+        assert all(torch.equal(a, b) for a, b in zip(parts[i][1], whole[i][1]))
+    assert not torch.equal(whole[0][0], whole[1][0])
+    sch = types.SimpleNamespace(timesteps_host=torch.arange(11), kind="ddim_simple_orig", eta=0.85)
+    exp = types.SimpleNamespace(scheduler=sch)
+    assert IS.device_draws_per_batch(exp) == 10
+    sch.eta = 0.0
+    assert IS.device_draws_per_batch(exp) == 0 and IS.device_draws_per_batch(exp, new_eta=0.5) == 1
+    sch.kind = "ddpm"
+    assert IS.device_draws_per_batch(exp, sampling="project", max_T=4) == 4
