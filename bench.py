@@ -12,6 +12,17 @@ batch (= 200 UNet-encoder + 100 decoder + 100 sigma-model evaluations per image)
   roofline: tcgen05 implicit-GEMM conv kernel, algorithmic FLOPs / CUDA-event time of sampled launches
   cpu_baseline: the oracle port (torch fp32, all host cores) on a bounded sample of the same workload
 
+The default run's ONE JSON line also carries (sub-records, each measured by the same timing code):
+  adm256 : the north-star target config c5 (ADM-256 + colourisation, batch 64 per GPU, 10 timesteps per pass): value,
+           ms_per_timestep, roofline, e2e - so the driver's 1->8 scaling run measures the target config too
+  tf32   : c2 in the tf32 operand mode (what cuDNN does for the reference's default GPU run)
+  strong : (N > 1) c2 with the GLOBAL batch 256 sharded over the N GPUs (configs[1]'s wording), exact batch-global
+           decisions via the per-step all-reduce
+  kernel_to_beat : the reference's networks through PyTorch eager / cuDNN (TF32 convolutions, its default GPU path) on
+           the same GPU, one NLC timestep at the workload's batch (the oracle's functional networks moved to the GPU;
+           baseline leg only, rank 0)
+`--no-extras` keeps only the headline record.
+
 `--impl reference` times the oracle port (the reference is pure Python and cannot travel to the GPU box) on the
 host cores for the same config.  N>1: one process per GPU under torchrun, batch sharded, NCCL all-gather of the
 finished images each pass; value = all ranks' images / max-over-ranks device time.
@@ -69,6 +80,7 @@ WORKLOADS = {
 CFG = dict(WORKLOADS["c2"])
 ADM_KEYS = ("image_size", "model_channels", "out_channels", "num_res_blocks", "attention_resolutions", "channel_mult",
             "num_heads", "num_head_channels", "use_scale_shift_norm", "resblock_updown", "use_new_attention_order")
+HEADLINE_PRECISION = "bf16"  # the operand mode of the driver's line (the mode that meets the 45 dB gate)
 CPU_SAMPLE = {"ddim": (6, 32), "adm": (1, 2), "edm": (3, 16)}  # (timesteps, batch) of the bounded CPU sample: ~10-20 s of host work
 
 
@@ -270,63 +282,98 @@ def build_models(precision, dev):
     return model, sigma_model
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="nlc", choices=["nlc", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "tf32", "fp32"])
-    ap.add_argument("--timesteps", type=int, default=0, help="sampling steps per pass (default: the workload's)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    _select(args)
-    if args.impl == "reference":
-        return run_reference(args)
+PROFILE_TRAFFIC = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
-    import torch.distributed as dist
+
+def measured_traffic(workload, batch, precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the workload's dominant conv_tc shape, from the
+    committed ncu --set full summary (profiles/ncu_traffic.json, written by scripts/ncu_summary.py from the .ncu-rep of the
+    final binary); None when no capture exists for this (workload, batch, precision)."""
+    try:
+        with open(PROFILE_TRAFFIC) as f:
+            t = json.load(f)
+        e = t.get("%s|%d|%s" % (workload, batch, precision))
+        return (e["dram_bytes"], e.get("source")) if e else (None, None)
+    except Exception:
+        return None, None
+
+
+class DistCtx:
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION and =WARN; the contract is ONE JSON line
+            # there.  Quieten those two levels and, whatever the level, send everything NCCL prints while the
+            # communicator comes up (eager init with device_id + one barrier) to stderr.
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+                os.environ["NCCL_DEBUG"] = "NONE"
+            sys.stdout.flush()
+            saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved_stdout, 1)
+                os.close(saved_stdout)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = torch.tensor([v], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def measure(dc, precision, steps, warmup, use_graph=True, do_e2e=True, exact_global=False, scaling="weak"):
+    """Time the workload selected in CFG on this rank's GPU: `warmup` untimed passes, then exactly `steps` passes between
+    barrier + synchronize, CUDA events on the launching stream, max over ranks.  Returns the record's fields."""
     from nlc_b200 import constraint_functions as CF, ops
     from nlc_b200.experiments import ImageExperiment
     from nlc_b200.schedulers import get_sampler
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION and =WARN; the contract is ONE JSON line there.
-        # Quieten those two levels and, whatever the level, send everything NCCL prints while the communicator comes up
-        # (eager init with device_id + one barrier) to stderr.
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            os.environ["NCCL_DEBUG"] = "NONE"
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
-
+    import gc
+    gc.collect()  # (the previous measurement's networks and plans: tens of GB of device buffers)
+    torch.cuda.empty_cache()
+    dist, world, rank, dev = dc.dist, dc.world, dc.rank, dc.dev
     B, R = CFG["batch"], CFG["R"]
-    model, sigma_model = build_models(args.precision, dev)
+    model, sigma_model = build_models(precision, dev)
     shape = (B, 3, R, R)
     g_dev = torch.Generator(device=dev).manual_seed(99 + rank)
     y_bytes = 0
     gathered = None
     conv_samples = []
     every = 10 if CFG["steps"] >= 20 else 2  # conv kernels are timed on every 10th (2nd) timestep of the timed passes
+    state = dict(active=False)
 
-    def hook(ind, _):
-        ops.STATS.conv_timer = conv_samples if (ind + 1) % every == every // 2 and hook.active else None
+    def sampled(ind):
+        return ind % every == every // 2
 
-    hook.active = False
+    def hook(ind, _):  # EDM / DDNM+ loops: arm the per-launch timer for the next step
+        ops.STATS.conv_timer = conv_samples if sampled(ind + 1) and state["active"] else None
+
+    def graph_skip(ind):  # denoise_loop: the sampled timesteps run eagerly with the per-launch timer, the rest replay
+        on = sampled(ind) and state["active"]
+        ops.STATS.conv_timer = conv_samples if on else None
+        return on
+
+    def step_done(ind, _):
+        ops.STATS.conv_timer = None
+
+    graphed = False
     if CFG.get("loop") == "ddnm_plus":
         import types
         from nlc_b200 import svd_ddnm
@@ -345,7 +392,7 @@ def main():
         calls = [0]
 
         def net(x, t):
-            hook(calls[0], None)
+            hook(calls[0] - 1, None)
             calls[0] += 1
             return model(x, t)
 
@@ -370,9 +417,11 @@ def main():
             gathered = [torch.empty(shape, device=dev, dtype=torch.float64) for _ in range(world)]
 
         def sample(x_in, to_cpu, with_hook):
-            out = exp.edm_sampler(shape, latents=x_in, step_hook=hook if with_hook else None, **edm_kw)
+            out = exp.edm_sampler(shape, latents=x_in, step_hook=(lambda i, d: hook(i, d)) if with_hook else None,
+                                  **edm_kw)
             return out.cpu() if to_cpu else out
     else:
+        graphed = use_graph
         sch = get_sampler(CFG["sampler"], 1000, CFG["steps"], start_sigma=CFG["start_sigma"], eta=CFG["eta"],
                           sampler_var=CFG["sampler_var"]).to(dev)
         exp = ImageExperiment(model, sch, batch_size=B, data_shape=(3, R, R), seed=1234 + rank, device=dev)
@@ -380,7 +429,8 @@ def main():
         exp.set_norm_maxmin(CFG["norm_min"], CFG["norm_max"])
         exp.set_clip_fn(CFG["clip"])
         loop_kw = dict(style=CFG["style"], norm_eps=CFG["norm_eps"], refine_prior_sigma=CFG["refine"], return_log=False,
-                       chunk_size=1, sigma_pred_threshold=CFG["sigma_pred_threshold"])
+                       chunk_size=1, sigma_pred_threshold=CFG["sigma_pred_threshold"], graph=use_graph,
+                       exact_global=exact_global and world > 1)
         if CFG["constraint"] is not None:
             # DDNM restoration: synthetic ground truth x ~ U(-1,1), measurement y = A x, projection + loss every step
             # (image_sample.py:636-665); the CS permutation is drawn once on the CPU with a fixed seed
@@ -400,8 +450,9 @@ def main():
             gathered = [torch.empty(shape, device=dev) for _ in range(world)]
 
         def sample(x_in, to_cpu, with_hook):
-            out, _ = exp.denoise_loop(shape=shape, xT=x_in, to_cpu=to_cpu, step_hook=hook if with_hook else None,
-                                      **loop_kw)
+            out, _ = exp.denoise_loop(shape=shape, xT=x_in, to_cpu=to_cpu,
+                                      graph_skip=graph_skip if with_hook else None,
+                                      step_hook=step_done if with_hook else None, **loop_kw)
             return out
 
     def one_pass_device():
@@ -410,70 +461,56 @@ def main():
             dist.all_gather(gathered, out.contiguous())
         return out
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---------------------------------------------------------------- device-resident timing
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(warmup, 1)):
         one_pass_device()
-    barrier()
-    clocks = ClockSampler(local)
+    dc.barrier()
+    clocks = ClockSampler(dc.local)
     clocks.start()
     ops.STATS.launches = 0
-    hook.active = True
+    ops.STATS.graph_replays = 0
+    state["active"] = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         one_pass_device()
     e1.record()
-    barrier()
-    hook.active = False
+    dc.barrier()
+    state["active"] = False
     ops.STATS.conv_timer = None
-    launches = ops.STATS.launches
+    launches, replays = ops.STATS.launches, ops.STATS.graph_replays
     clocks.stop_flag = True
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        tms = torch.tensor([ms], device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-    ms_per_step = ms / args.steps
+    ms = dc.max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms / steps
     value = B * world / (ms_per_step / 1000.0)
 
     # ---------------------------------------------------------------- end-to-end through the public API
-    pinned = torch.empty(shape, dtype=torch.float32).pin_memory()
-    gen = torch.Generator().manual_seed(4321 + rank)
+    e2e = None
+    if do_e2e:
+        pinned = torch.empty(shape, dtype=torch.float32).pin_memory()
+        gen = torch.Generator().manual_seed(4321 + rank)
 
-    def one_pass_e2e():
-        # the reference draws the initial noise on the host side (src/experiments.py:268; per-sample generators for EDM):
-        # pinned staging, H2D, the whole sampling loop through the public API, D2H of the finished images
-        torch.randn(shape, generator=gen, out=pinned)
-        x = pinned.to(dev, non_blocking=True)
-        if x_scale != 1.0:
-            x = x * x_scale
-        return sample(x, True, False)
+        def one_pass_e2e():
+            # the reference draws the initial noise on the host side (src/experiments.py:268; per-sample generators for
+            # EDM): pinned staging, H2D, the whole sampling loop through the public API, D2H of the finished images
+            torch.randn(shape, generator=gen, out=pinned)
+            x = pinned.to(dev, non_blocking=True)
+            if x_scale != 1.0:
+                x = x * x_scale
+            return sample(x, True, False)
 
-    one_pass_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 3))
-    for _ in range(n_e2e):
         one_pass_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    if world > 1:
-        te = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_s = float(te.item())
-    e2e_value = B * world / e2e_s
-    nbytes = B * 3 * R * R * 4
-    out_bytes = B * 3 * R * R * (8 if out_dtype == torch.float64 else 4)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        dc.barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(steps, 3))
+        for _ in range(n_e2e):
+            one_pass_e2e()
+        dc.barrier()
+        e2e_s = dc.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        nbytes = B * 3 * R * R * 4
+        out_bytes = B * 3 * R * R * (8 if out_dtype == torch.float64 else 4)
+        e2e = {"value": B * world / e2e_s, "unit": "images/s", "h2d_bytes_per_step": nbytes + y_bytes,
+               "d2h_bytes_per_step": out_bytes}
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
     tf_peak, hbm_peak, peak_src = peaks()
@@ -482,21 +519,174 @@ def main():
     achieved = conv_fl / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
     nfe_per_pass = CFG.get("nfe_per_pass", CFG["steps"])
     nfe_flops = CFG["gflop_per_nfe"] * 1e9 * B * nfe_per_pass
-    sampled_timesteps = max(1, args.steps * sum(1 for i in range(CFG["steps"]) if (i + 1) % every == every // 2))
-    roofline = {"bound": "tensor", "kernel": "nlc::conv_tc_kernel (tcgen05 implicit GEMM, %s)" % args.precision,
+    sampled_timesteps = max(1, steps * sum(1 for i in range(CFG["steps"]) if sampled(i)))
+    traffic, traffic_src = measured_traffic(CFG["name"], B, precision)
+    roofline = {"bound": "tensor", "kernel": "nlc::conv_tc_kernel (tcgen05 implicit GEMM, %s)" % precision,
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                 "peak_source": peak_src,
-                # dram__bytes_read+write of one launch of the step's top shape (3x3 conv 128->128 at 64x64, batch 256:
-                # 1.074 GB algorithmic) from the ncu --set full capture in profiles/r01_ncu_conv_tc_summary.md
-                # ADM-256 at batch 32: the dominant 3x3 conv 256->256 at 256x256 moved 1.353 GB read + 2.136 GB written
-                # against 3.22 GB algorithmic (profiles/r01k_ncu_adm_kernels.md)
-                "traffic": 1.021e9 if CFG["name"] == "c2" and B == 256 else (
-                    3.489e9 if CFG["name"] == "adm256" and B == 32 else None),
+                # dram__bytes_read + dram__bytes_write of one launch of the step's dominant conv shape, read from the
+                # committed ncu --set full summary of the final binary (None: no capture for this batch / mode)
+                "traffic": traffic, "traffic_source": traffic_src,
                 "launches_sampled": len(conv_samples),
-                # share of the step spent in the conv kernel, from the sampled timesteps
+                # share of the step spent in the conv kernel, from the sampled (eagerly launched) timesteps
                 "conv_share_of_step": (conv_ms / sampled_timesteps) / (ms_per_step / CFG["steps"]) if conv_ms > 0 else None,
-                "whole_step_tflops": nfe_flops / (ms_per_step / 1000.0) / 1e12}
+                "whole_step_tflops": nfe_flops / (ms_per_step / 1000.0) / 1e12,
+                "whole_step_frac": nfe_flops / (ms_per_step / 1000.0) / 1e12 / tf_peak}
+    rec = {
+        "metric": CFG["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": precision, "data": "synthetic",
+        "config": {"workload": CFG["label"], "per_gpu_batch": B, "global_batch": B * world,
+                   "step": "one full %d-timestep sampling pass of one batch" % CFG["steps"],
+                   "l2": "activations per pass (GBs) exceed the 126 MB L2; no explicit flush",
+                   "parallelism": "dp%d (batch sharded, NCCL all-gather of finished images%s)" % (
+                       world, "; per-step all-reduce of the batch-global loop decisions" if exact_global and world > 1 else ""),
+                   "cuda_graph": bool(graphed)},
+        "nfe_per_s": value * nfe_per_pass,
+        "ms_per_timestep": ms_per_step / CFG["steps"],
+        "clocks": clocks.summary(),
+        "e2e": e2e,
+        "gpu_launches": launches,
+        "graph_replays": replays,
+        "roofline": roofline,
+    }
+    del model, sigma_model
+    torch.cuda.empty_cache()
+    return rec
 
+
+def kernel_to_beat(dev, reps=3):
+    """The reference's networks through PyTorch eager / cuDNN on this GPU (its own GPU path: fp32 tensors, TF32 allowed for
+    convolutions): one NLC timestep = UNet encode + sigma-model + UNet forward at the workload's batch, via the oracle's
+    functional networks (pinned torch.equal to the reference on the CPU) moved to the device.  Baseline leg only."""
+    from oracle import weights
+    torch.backends.cudnn.benchmark = True
+    torch.backends.cudnn.allow_tf32 = True
+    B, R = CFG["batch"], CFG["R"]
+    if CFG["arch"] == "adm":
+        from oracle import adm_net
+        B = min(B, 16)  # torch eager needs 161 GB at batch 32 (profiles/r01g_torch_eager_baseline.log)
+        cfg = dict(weights.ADM_CONFIGS[CFG["name"]])
+        sg = cfg.pop("sigma")
+        sd = {k: v.to(dev) for k, v in weights.adm_unet_state_dict(**cfg, seed=3).items()}
+        ssd = {k: v.to(dev) for k, v in weights.adm_sigma_state_dict(**sg, seed=4).items()}
+        enc, fwd = (lambda x, t: adm_net.unet_encode(sd, x, t, cfg)), (lambda x, t: adm_net.unet_forward(sd, x, t, cfg))
+        sig = lambda f: adm_net.sigma_forward(ssd, f, cfg)
+    elif CFG["arch"] == "ddim":
+        from oracle import ddim_net
+        cfg = weights.CONFIGS[CFG["name"]]
+        sd = {k: v.to(dev) for k, v in weights.ddim_unet_state_dict(**cfg["unet"], seed=3).items()}
+        ssd = {k: v.to(dev) for k, v in weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4).items()}
+        enc, fwd = (lambda x, t: ddim_net.unet_encode(sd, x, t)), (lambda x, t: ddim_net.unet_forward(sd, x, t))
+        sig = lambda f: ddim_net.sigma_forward(ssd, f)
+    else:
+        return None
+    x = torch.randn(B, 3, R, R, device=dev)
+    t = torch.full((B,), 500.0, device=dev)
+
+    def step():
+        r = sig(enc(x, t))
+        return fwd(x * (1 + r).reshape(-1, 1, 1, 1), t)
+
+    out = {}
+    for mode, ctx in (("tf32", None), ("fp16_autocast", torch.autocast("cuda", dtype=torch.float16))):
+        with torch.no_grad():
+            if ctx is not None:
+                ctx.__enter__()
+            try:
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+            finally:
+                if ctx is not None:
+                    ctx.__exit__(None, None, None)
+        ms = e0.elapsed_time(e1) / reps
+        out[mode] = {"ms_per_timestep": ms, "value": B / (ms / 1000.0 * CFG["steps"]), "unit": "images/s"}
+    out["batch"] = B
+    out["what"] = ("torch %s eager + cuDNN on this GPU, the reference's networks (oracle functional form): encode + "
+                   "sigma-model + forward per NLC timestep, x %d timesteps; tf32 = the reference's default GPU path, "
+                   "fp16_autocast = torch.autocast(float16), not a reference mode" % (torch.__version__, CFG["steps"]))
+    del sd, ssd
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nlc", choices=["nlc", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
+    ap.add_argument("--precision", default=HEADLINE_PRECISION, choices=["bf16", "fp16", "tf32", "fp32"])
+    ap.add_argument("--timesteps", type=int, default=0, help="sampling steps per pass (default: the workload's)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: the workload's batch is the GLOBAL batch, sharded over the GPUs")
+    ap.add_argument("--no-graph", action="store_true", help="launch every timestep eagerly (no CUDA-graph replay)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline record only (no adm256 / tf32 / strong / "
+                                                             "kernel_to_beat sub-records)")
+    args = ap.parse_args()
+    _select(args)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    dc = DistCtx()
+    if args.scaling == "strong":
+        assert CFG["batch"] % dc.world == 0, "the global batch must divide over the GPUs"
+        CFG["batch"] //= dc.world
+    line = measure(dc, args.precision, args.steps, args.warmup, use_graph=not args.no_graph,
+                   exact_global=args.scaling == "strong", scaling=args.scaling)
+    extras = args.workload == "c2" and not args.no_extras and not args.batch and not args.timesteps \
+        and args.scaling == "weak"
+    if extras:
+        # tf32 operand mode of the same workload (one timed pass)
+        sub = measure(dc, "tf32", 1, 1, use_graph=not args.no_graph, do_e2e=False)
+        line["tf32"] = {k: sub[k] for k in ("value", "unit", "ms_per_timestep", "dtype")}
+        line["tf32"]["roofline_frac_of_bf16_peak"] = sub["roofline"]["frac"]
+        if dc.world > 1:
+            # configs[1] as worded: global batch 256 sharded over the GPUs (strong scaling), exact batch-global decisions
+            CFG["batch"] = WORKLOADS["c2"]["batch"] // dc.world
+            sub = measure(dc, args.precision, 2, 2, use_graph=not args.no_graph, do_e2e=False, exact_global=True,
+                          scaling="strong")
+            line["strong"] = {k: sub[k] for k in ("value", "unit", "ms_per_timestep", "dtype", "scaling", "gpu_launches",
+                                                  "graph_replays")}
+            line["strong"]["per_gpu_batch"], line["strong"]["global_batch"] = CFG["batch"], WORKLOADS["c2"]["batch"]
+            # ... and the same sharded run launched eagerly: what the CUDA graph buys at 32 images per GPU
+            sub = measure(dc, args.precision, 1, 1, use_graph=False, do_e2e=False, exact_global=True, scaling="strong")
+            line["strong"]["eager_value"] = sub["value"]
+        # the north-star target config: ADM-256, batch 64 per GPU (c5), weak scaling
+        CFG.clear()
+        CFG.update(WORKLOADS["c5"])
+        CFG["label"] = CFG["label"] % CFG["steps"]
+        sub = measure(dc, args.precision, 2, 2, use_graph=not args.no_graph)
+        line["adm256"] = {k: sub[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "ms_per_timestep", "dtype",
+                                              "scaling", "config", "e2e", "roofline", "gpu_launches", "graph_replays",
+                                              "nfe_per_s", "clocks")}
+        CFG.clear()
+        CFG.update(WORKLOADS["c2"])
+        CFG["label"] = CFG["label"] % CFG["steps"]
+
+    if dc.rank != 0:
+        if dc.world > 1:
+            dc.dist.destroy_process_group()
+        return
+    if dc.world > 1:
+        dc.dist.destroy_process_group()  # the baseline legs below are rank 0's alone
+
+    if not args.no_extras:
+        try:
+            with torch.no_grad():
+                line["kernel_to_beat"] = kernel_to_beat(dc.dev)
+        except Exception as e:  # a baseline leg must never cost the headline line
+            line["kernel_to_beat"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     cpu = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -505,27 +695,8 @@ def main():
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                "sample": ("%d " + _unit() + " at batch %d of the workload on the oracle port (torch fp32, %d threads, "
                           "%.1f s), extrapolated linearly to %d timesteps") % (n_steps, batch, threads, dt, CFG["steps"])}
-
-    line = {
-        "metric": CFG["metric"], "value": value, "unit": "images/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-        "config": {"workload": CFG["label"], "per_gpu_batch": B, "global_batch": B * world,
-                   "step": "one full %d-timestep sampling pass of one batch" % CFG["steps"],
-                   "l2": "activations per pass (GBs) exceed the 126 MB L2; no explicit flush",
-                   "parallelism": "dp%d (batch sharded, NCCL all-gather of finished images)" % world},
-        "nfe_per_s": value * nfe_per_pass,
-        "ms_per_timestep": ms_per_step / CFG["steps"],
-        "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes + y_bytes,
-                "d2h_bytes_per_step": out_bytes},
-        "gpu_launches": launches,
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-    }
+    line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -99,6 +99,7 @@ _SIGNATURES = {
     "nlc_normalize_rows": (_I, [_P, _P, _I, _I, _P]),
     "nlc_pred_xstart": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "nlc_pred_xprev": (_I, [_P, _I, C.c_double, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _I, _I, _I, _P, _P, _P]),
+    "nlc_best_update": (_I, [_P, _P, _F, _P, _P, _P, _P, _I64, _P]),
     "nlc_edm_prepare": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "nlc_edm_eps": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "nlc_edm_mix": (_I, [_P, _P, _P, _P, _P, _P, _P, C.c_double, C.c_double, _I, _I, _P, _P, _P]),

@@ -128,6 +128,12 @@ class Constraint_Function:
 
     def loss(self, x, y):
         """(||A x - y||_1, ||inv_transform(y) - x||_1) per sample, on the CPU like the reference."""
+        fwd, bwd = self.loss_device(x, y)
+        return fwd.cpu(), bwd.cpu()
+
+    def loss_device(self, x, y):
+        """The same two per-sample losses left on the device: no host read, so a loop that tracks its best x0 with
+        nlc_best_update can be captured in a CUDA graph (ExperimentDiffusion.denoise_loop, `constrain_loss_device`)."""
         y_hat = self.transform(x)
         # y is fixed for a whole batch: A^+ y is cached against the tensor OBJECT (held, so its address cannot be reused
         # by another measurement) and its in-place version counter (a refilled buffer invalidates the entry)
@@ -137,7 +143,7 @@ class Constraint_Function:
         x_hat = c[2]
         fwd = ops_svd.l1_diff_rows(y_hat, y.reshape(y.shape[0], -1))
         bwd = ops_svd.l1_diff_rows(x_hat, x)
-        return fwd.cpu(), bwd.cpu()
+        return fwd, bwd
 
 
 def get_constraint_function(constraint, constraint_scale=4.0, device="cuda", image_size=256, channels=3,

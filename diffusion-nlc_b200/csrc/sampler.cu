@@ -520,3 +520,48 @@ extern "C" int nlc_sigma_estimate(nlc_ctx* ctx, const float* norms, float* last_
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
+
+
+// ----------------------------------------------------------------------------------------------------------------
+// Best-x0 bookkeeping of the DDIM-family loop on the device (src/experiments.py:371-376: `const_val = mean(const);
+// if const_val < best_val: best_x0 = x0.clone(); best_val = const_val`).  The reference decides on the host, which costs
+// one device->host read per step and keeps the step out of a CUDA graph; here the comparison and the conditional copy
+// are two stream-ordered kernels.
+namespace nlc {
+
+__global__ void best_decide_kernel(const float* __restrict__ loss_sum, float inv_count, float* __restrict__ best_val,
+                                   int* __restrict__ flag) {
+    const float v = __fmul_rn(*loss_sum, inv_count);
+    const int better = v < *best_val;  // (a NaN mean is never better, as in the reference's host comparison)
+    *flag = better;
+    if (better) *best_val = v;
+}
+
+__global__ void __launch_bounds__(256) copy_if_kernel(const int* __restrict__ flag, const float4* __restrict__ src,
+                                                      float4* __restrict__ dst, size_t n4) {
+    if (*flag == 0) return;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+}
+
+}  // namespace nlc
+
+extern "C" int nlc_best_update(nlc_ctx* ctx, const float* loss_sum, float inv_count, float* best_val, int* flag,
+                               const float* x0, float* best_x0, int64_t n, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    NLC_REQUIRE(ctx && loss_sum && best_val && flag && x0 && best_x0 && n > 0 && n % 4 == 0,
+                "nlc_best_update: null argument or n %% 4 != 0");
+    NLC_REQUIRE(((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(best_x0)) & 15) == 0,
+                "nlc_best_update: x0 / best_x0 must be 16-byte aligned");
+    nlc::best_decide_kernel<<<1, 1, 0, stream>>>(loss_sum, inv_count, best_val, flag);
+    NLC_CHECK_LAUNCH();
+    const size_t n4 = static_cast<size_t>(n) / 4;
+    size_t blocks = (n4 + 255) / 256;
+    const size_t cap = static_cast<size_t>(ctx->sm_count) * 8;
+    if (blocks > cap) blocks = cap;
+    nlc::copy_if_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        flag, reinterpret_cast<const float4*>(x0), reinterpret_cast<float4*>(best_x0), n4);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}

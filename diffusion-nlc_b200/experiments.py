@@ -15,6 +15,7 @@ Differences from the reference, all host-side and documented in DESIGN.md:
   * `return_log=True` returns the same lists but costs the same device->host copies as in the reference.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -37,6 +38,19 @@ class _Work:
         self.x0 = f(B, *shape)
         self.xa, self.xb = f(B, *shape), f(B, *shape)
         self.nan_flag = torch.zeros(1, device=device, dtype=torch.int32)
+        self._shape, self._device = (B,) + tuple(shape), device
+        self._graph_bufs = None
+
+    def graph_bufs(self):
+        """Fixed-address inputs of a captured step: (sigma_t, sigma_prev) of the step, its noise draw, and the device-side
+        best-x0 bookkeeping (value, flag, image)."""
+        if self._graph_bufs is None:
+            import types
+            f = lambda *s: torch.empty(*s, device=self._device, dtype=torch.float32)
+            self._graph_bufs = types.SimpleNamespace(
+                step_sig=f(2), noise=f(*self._shape), best_val=f(1), best_x0=f(*self._shape), loss_sum=f(1),
+                flag=torch.zeros(1, device=self._device, dtype=torch.int32))
+        return self._graph_bufs
 
 
 class ExperimentDiffusion:
@@ -61,6 +75,13 @@ class ExperimentDiffusion:
         self.sigma_model = None
         self.norm_min, self.norm_max = 0.0, 1.0
         self.nan_check_every = 16
+        # replay the timestep from a CUDA graph in denoise_loop (NLC_GRAPH=0 disables; see denoise_loop)
+        self.cuda_graph = os.environ.get("NLC_GRAPH", "1") != "0"
+        # instrumentation for parity studies: `time_source(step) -> (t, t_hat)` ([B] float tensors or None) replaces the
+        # step's two discrete time lookups t = searchsorted(sigma) (src/experiments.py:410,427) by given values, so a
+        # free-running trajectory can be compared with the reference's without its time-bucket decisions diverging
+        self.time_source = None
+        self._step = 0
         self.gen = self.new_gen()
         self._work = {}
 
@@ -142,11 +163,16 @@ class ExperimentDiffusion:
                 w.t.copy_(t.reshape(-1).to(torch.float32).clamp_(0.0, 1000.0))
         sigma_cur, t_cur, scale_cur = w.sigma, w.t, w.scale
         sp_cur = sp_in
+        forced = self.time_source(self._step) if self.time_source is not None else (None, None)
+        if forced[0] is not None and refine_prior_sigma:
+            w.t.copy_(forced[0].reshape(-1))
         if "pred" in style:
             feat = self.model.encode_scaled(xt, t_cur, scale_cur)
             r = self.sigma_model.forward_nhwc(feat)
             ops.sigma_correct(r, sigma_cur, sp_in, style == "pred", sch.sigma_table, w.sigma_hat, w.sigma_prev_hat,
                               w.t_hat, w.scale_hat, slopes=sch.slopes_table)
+            if forced[1] is not None:
+                w.t_hat.copy_(forced[1].reshape(-1))
             sigma_cur, t_cur, scale_cur = w.sigma_hat, w.t_hat, w.scale_hat
             sp_cur = w.sigma_prev_hat
         elif refine_prior_sigma and sp_in.numel() == 1:
@@ -270,15 +296,42 @@ class ExperimentDiffusion:
         return result, [z_list, eps_list, x0_prec_list, x0_postc_list, sigma_list, const_loss_list]
 
     # ---------------------------------------------------------------- L1: the DDIM-family loop
+    @staticmethod
+    def _device_loss(constrain_loss):
+        """The device-resident twin of a `partial(Constraint_Function.loss, y=y)` (its `loss_device`), or None."""
+        fn, kw = constrain_loss, {}
+        if hasattr(fn, "func") and hasattr(fn, "keywords"):
+            fn, kw = constrain_loss.func, dict(constrain_loss.keywords)
+            if constrain_loss.args:
+                return None
+        owner = getattr(fn, "__self__", None)
+        if owner is not None and getattr(fn, "__name__", "") == "loss" and hasattr(owner, "loss_device"):
+            from functools import partial
+            return partial(owner.loss_device, **kw)
+        return None
+
     @torch.no_grad()
     def denoise_loop(self, shape, gen=None, norm_init_noise=False, style="base", constrain_fn=None, norm_eps=False,
                      refine_prior_sigma=False, xT=None, return_log=True, chunk_size=2, sigma_pred_threshold=1000,
                      new_eta=None, constrain_loss=None, return_best=True, free_const_steps=-1, noise_fn=None,
-                     step_hook=None, to_cpu=True):
+                     step_hook=None, to_cpu=True, graph=None, graph_skip=None, constrain_loss_device=None,
+                     exact_global=False):
         """src/experiments.py:329-397.  `noise_fn(ind, like)` (optional) supplies the per-step noise instead of
         torch.randn_like (used by parity tests and by sharded runs that must reproduce the un-sharded stream);
         `step_hook(ind, dict)` (optional) observes per-step device tensors without copying them; `to_cpu=False`
-        leaves the result on the device (the reference always returns a CPU tensor)."""
+        leaves the result on the device (the reference always returns a CPU tensor).
+
+        `graph=True` (default: the experiment's `cuda_graph` attribute) replays the timestep from a CUDA graph: the
+        ~300 kernel launches of one NLC step (refine -> encode -> sigma-model -> forward -> update [-> projection ->
+        loss -> best-x0]) are captured once per loop call and style, and every later step costs three host calls (the
+        step's two noise levels copied into a fixed buffer, the noise draw, the replay).  The arithmetic and the order of
+        the random draws are those of the eager loop; the best-x0 decision moves to the device (nlc_best_update), which
+        needs the device-resident twin of `constrain_loss` (`constrain_loss_device`, found automatically for
+        Constraint_Function.loss).  Steps whose host scalars change (the 'base' steps above sigma_pred_threshold, a
+        `new_eta` last step, steps without `refine_prior_sigma`, steps `graph_skip(ind)` excludes) run eagerly;
+        `step_hook` sees the eager steps only.
+        `exact_global=True` (sharded runs): the mean constraint loss behind the best-x0 choice and the NaN flag are
+        all-reduced over the ranks, so every shard decides as the un-sharded reference does."""
         sch = self.scheduler
         sch.reset_state()
         sig = sch.sampling_sigmas
@@ -299,8 +352,108 @@ class ExperimentDiffusion:
         ts_host = sch.timesteps_host.tolist()
         best_val, best_x0 = 10000, xt
         x0 = xt
+        world = 1
+        if exact_global:
+            import torch.distributed as dist
+            world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        use_graph = getattr(self, "cuda_graph", False) if graph is None else bool(graph)
+        if self.time_source is not None or (step_hook is not None and graph_skip is None):
+            use_graph = False  # (a forced time changes from step to step; a hook without `graph_skip` wants every step)
+        loss_dev = constrain_loss_device
+        if constrain_loss is not None and loss_dev is None and (use_graph or world > 1):
+            loss_dev = self._device_loss(constrain_loss)
+        # the device-side loop variant: fixed step buffers + device best-x0 tracking (graph replays and, for exactness
+        # under sharding, the all-reduced loss); needs no per-step host read of the loss
+        dev_mode = (use_graph or world > 1) and not return_log and (constrain_loss is None or loss_dev is not None)
+        use_graph = use_graph and dev_mode and xt.is_cuda
+        if dev_mode:
+            gb = w.graph_bufs()
+            gb.best_val.fill_(10000.0)
+            gb.best_x0.copy_(xt)
+            needs_noise = sch.kind in ("ddpm", "ddpm_orig") or float(sch.eta) > 0 or (new_eta is not None and new_eta > 0)
+            graphs, warmed = {}, set()
+            out_ref = {}
+
+            def body(ind, t, sigma_t, sigma_prev, cur_style, cur_refine, apply_con, noise):
+                eps, eps_logvar, s_t, s_p = self.get_denoise_vector(
+                    xt, t, sigma_t, sigma_prev, cur_style, norm_eps, refine_prior_sigma=cur_refine, chunk_size=chunk_size)
+                x0_hat = self._pred_xstart_clipped(xt, eps, s_t, w.x0)
+                x0_ = constrain_fn(x0_hat) if apply_con else x0_hat
+                sch.pred_xprev(x0=x0_, eps=eps, sigma_t=s_t, sigma_prev=s_p, xt=xt, log_variance=eps_logvar,
+                               noise=noise, out=nxt, nan_flag=w.nan_flag)
+                if loss_dev is not None:
+                    const, _ = loss_dev(x0_.clamp(-1, 1))
+                    torch.sum(const, dim=0, keepdim=True, out=gb.loss_sum)
+                    if world > 1:
+                        import torch.distributed as dist
+                        dist.all_reduce(gb.loss_sum)
+                    ops.best_update(gb.loss_sum, B * world, gb.best_val, gb.flag, x0_, gb.best_x0)
+                xt.copy_(nxt)
+                out_ref["x0"] = x0_
+                return dict(xt=xt, eps=eps, x0_hat=x0_hat, x0=x0_, x_prev=nxt, sigma_t=s_t, sigma_prev=s_p)
+
+            for ind in range(len(ts_host) - 1):
+                t = ts_host[ind]
+                self._step = ind
+                last_eta = ind == steps - 1 and new_eta is not None
+                if last_eta:
+                    sch.eta = new_eta
+                cur_style, cur_refine = style, refine_prior_sigma
+                if t > sigma_pred_threshold:
+                    cur_style, cur_refine = "base", False
+                apply_con = constrain_fn is not None and (free_const_steps <= 0 or ind <= free_const_steps)
+                gb.step_sig.copy_(sig[ind:ind + 2], non_blocking=True)
+                noise = None
+                if needs_noise and (sch.kind in ("ddpm", "ddpm_orig") or float(sch.eta) > 0):
+                    if noise_fn is not None:
+                        gb.noise.copy_(noise_fn(ind, xt))
+                    else:
+                        gb.noise.normal_()  # the draw torch.randn_like(x0) makes, on the same generator
+                    noise = gb.noise
+                key = (cur_style, apply_con, noise is not None)
+                capturable = (use_graph and cur_refine and not last_eta
+                              and (graph_skip is None or not graph_skip(ind)))
+                if capturable and key in warmed:
+                    g = graphs.get(key)
+                    if g is None:
+                        n0 = ops.STATS.launches
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g):
+                            body(ind, t, gb.step_sig[0:1], gb.step_sig[1:2], cur_style, cur_refine, apply_con, noise)
+                        g.n_launches = ops.STATS.launches - n0
+                        g.x0 = out_ref["x0"]  # (lives in the graph's memory pool: every replay refreshes it)
+                        ops.STATS.launches = n0
+                        graphs[key] = g
+                    g.replay()
+                    out_ref["x0"] = g.x0
+                    ops.STATS.launches += g.n_launches
+                    ops.STATS.graph_replays += 1
+                    sch.i += 1
+                else:
+                    rec = body(ind, t, gb.step_sig[0:1], gb.step_sig[1:2], cur_style, cur_refine, apply_con, noise)
+                    if cur_refine:
+                        warmed.add(key)
+                    if step_hook is not None:
+                        step_hook(ind, rec)
+                if (ind + 1) % self.nan_check_every == 0:
+                    if world > 1:
+                        import torch.distributed as dist
+                        flag = w.nan_flag.clone()
+                        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                    else:
+                        flag = w.nan_flag
+                    if int(flag.item()) != 0:
+                        break
+            x0 = out_ref.get("x0", xt)
+            best_x0 = gb.best_x0 if loss_dev is not None else x0
+            result = (best_x0 if return_best else x0).clone()
+            graphs.clear()
+            result = result.cpu() if to_cpu else result
+            return result, [z_list, eps_list, x0_prec_list, x0_postc_list, const_loss_list]
+
         for ind in range(len(ts_host) - 1):
             t = ts_host[ind]
+            self._step = ind
             if ind == steps - 1 and new_eta is not None:
                 sch.eta = new_eta
             sigma_t, sigma_prev = sig[ind:ind + 1], sig[ind + 1:ind + 2]

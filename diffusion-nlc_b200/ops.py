@@ -15,6 +15,7 @@ class _Stats:
     `conv_timer` is a list, every nlc_conv_tc launch is bracketed by CUDA events on the launching stream and
     (flops, start, stop) is appended."""
     launches = 0
+    graph_replays = 0  # CUDA-graph replays of a captured timestep (each adds the captured launch count to `launches`)
     conv_timer = None
     op_timer = None  # list -> every wrapper below appends (name, start_event, stop_event, flops)
 
@@ -427,6 +428,14 @@ def pred_xprev(sched, eta, x0, eps, xt, noise, learned_v, logvar_mode, min_var_c
         float(min_var_coef), _p(sigma), sigma.numel(), _p(sigma_prev), sigma_prev.numel(), B, d, _p(x_prev),
         _p(nan_flag), _stream()))
     STATS.launches += 1
+
+
+@_timed("best_update")
+def best_update(loss_sum, count, best_val, flag, x0, best_x0):
+    """Device-side `if mean(const) < best_val: best_x0 = x0.clone(); best_val = mean` (nlc_best_update)."""
+    _lib.check(_lib.lib().nlc_best_update(_ctx(x0), _p(loss_sum), 1.0 / float(count), _p(best_val), _p(flag), _p(x0),
+                                          _p(best_x0), x0.numel(), _stream()))
+    STATS.launches += 2
 
 
 # ---------------------------------------------------------------------------------------------- EDM sampler (fp64 state)

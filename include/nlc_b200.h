@@ -261,6 +261,12 @@ int nlc_pred_xprev(nlc_ctx* ctx, int sched, double eta, const float* x0, const f
                    const float* sigma, int n_sigma, const float* sigma_prev, int n_prev, int B, int d,
                    float* x_prev, int* nan_flag, void* stream);
 
+/* Best-x0 bookkeeping of the loop on the device (src/experiments.py:371-376): v = *loss_sum * inv_count (the batch-mean
+ * constraint loss; loss_sum may already be all-reduced over the ranks of a sharded run); if v < *best_val then
+ * *best_val = v and best_x0 <- x0 (n floats).  `flag` is one int of scratch.  No host read: the step stays graph-able. */
+int nlc_best_update(nlc_ctx* ctx, const float* loss_sum, float inv_count, float* best_val, int* flag, const float* x0,
+                    float* best_x0, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * L3 / D2 — EDM Heun sampler (src/experiments.py:777-843, 847-918).  The sample x is float64, the network runs in
  * float32.  Per-sample reductions come back as NLC_EDM_PARTS partial sums per sample (fixed order).

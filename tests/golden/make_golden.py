@@ -88,13 +88,29 @@ def main():
             return out
 
         sch.pred_xprev = spy
+        # the two discrete time lookups of every step, observed (src/experiments.py:410,427)
+        t_first, t_second = [], []
+        orig_enc, orig_pred = exp.encode_xt, exp.pred_xt
+
+        def enc_spy(xt, t, sigma=None, batch_t=True, _o=orig_enc, _l=t_first):
+            _l.append(torch.as_tensor(t).reshape(-1).float().expand(B).clone())
+            return _o(xt, t, sigma=sigma, batch_t=batch_t)
+
+        def pred_spy(xt, t, sigma=None, batch_t=True, _o=orig_pred, _l=t_second):
+            _l.append(torch.as_tensor(t).reshape(-1).float().expand(B).clone())
+            return _o(xt, t, sigma=sigma, batch_t=batch_t)
+
+        exp.encode_xt, exp.pred_xt = enc_spy, pred_spy
         final, logs = exp.denoise_loop(shape=shape, gen=exp.new_gen(5), style="pred", norm_eps=True,
                                        refine_prior_sigma=True, return_log=True, chunk_size=1)
         loops["%s|%s|%s" % (kind, eta, var)] = dict(
+            t_first=torch.stack(t_first), t_hat=torch.stack(t_second),
             z=z, noises=noises, final=final, eps=logs[1], x0_hat=logs[2], x0=logs[3],
             xt=rec["xt"], sigma_t=rec["sigma_t"], sigma_prev=rec["sigma_prev"], x_prev=rec["x_prev"],
             timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone())
     torch.save(loops, os.path.join(HERE, "denoise_loop_tiny.pt"))
+    if os.environ.get("NLC_GOLDEN_STOP_AFTER_LOOPS") == "1":  # (regenerate the first three fixtures only)
+        return
 
     # ---- operators
     ref = R.svd_operators
@@ -601,6 +617,169 @@ def train_step():
                 ema={n: digest(e) for (n, _), e in zip(net.named_parameters(), ema)})
     torch.save(gold, os.path.join(HERE, "train_step_tiny.pt"))
     print("train_step_tiny.pt", os.path.getsize(os.path.join(HERE, "train_step_tiny.pt")))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Benchmark architectures (BASELINE.json configs c2, c3, c4/c5): the unmodified reference at its REAL sizes.
+C2_SNAPSHOTS = (0, 3, 10, 25, 50, 75, 90, 99)  # steps whose tensors are stored for teacher-forced checks
+
+
+def _checksum(t):
+    """Position-weighted float64 digest: pins a tensor that the test regenerates from its seed instead of loading."""
+    v = t.double().reshape(-1)
+    return torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, dtype=torch.float64)).sum() / v.numel()])
+
+
+def loop_c2():
+    """Config c2 on the unmodified reference: CelebA-64 unet_ddim + sigma-model, ddim_simple_orig eta 0.85, 100 steps
+    from sigma 100, style pred + norm_eps + refine, clamp clip, norm_min -2 / norm_max 110 (bench.py's c2), batch 4.
+    Stored: the final image, every step's corrected sigmas and times, full tensors at C2_SNAPSHOTS.  The initial and
+    per-step noise is NOT stored (100 x 196 KB): the test redraws it from seed 5 and checks the digests  -> loop_c2_100.pt"""
+    R = refimport.load()
+    torch.set_num_threads(8)
+    cfg = weights.CONFIGS["c2"]
+    u, sg = cfg["unet"], cfg["sigma"]
+    net = R.unet_ddim.UNetModel(**u).eval()
+    net.load_state_dict(weights.ddim_unet_state_dict(**u, seed=3))
+    snet = R.unet_ddim.SigmaModel(dim=sg["dim"], channels=sg["channels"], n_blocks=sg["n_blocks"]).eval()
+    snet.load_state_dict(weights.ddim_sigma_state_dict(**sg, seed=4))
+    B, side, steps = 4, u["image_size"], 100
+    shape = (B, 3, side, side)
+    sch = R.schedulers.get_sampler("ddim_simple_orig", 1000, steps, start_sigma=100, eta=0.85)
+    exp = R.experiments.ImageExperiment(net, sch, batch_size=B, data_shape=shape[1:], seed=5, device="cpu")
+    exp.set_model(net, snet, learn_epsvar=False)
+    exp.set_norm_maxmin(-2.0, 110.0)
+    exp.set_clip_fn("clamp")
+    torch.manual_seed(5)
+    z = torch.randn(shape)
+    noises = [torch.randn(shape) for _ in range(len(sch.timesteps) - 1)]
+    rec = dict(sigma_t=[], sigma_prev=[], snap={})
+    orig = sch.pred_xprev
+
+    def spy(*a, _orig=orig, **k):
+        out = _orig(*a, **k)
+        i = len(rec["sigma_t"])
+        rec["sigma_t"].append(torch.as_tensor(k["sigma_t"]).reshape(-1).clone())
+        rec["sigma_prev"].append(torch.as_tensor(k["sigma_prev"]).reshape(-1).clone())
+        if i in C2_SNAPSHOTS:
+            rec["snap"][i] = dict(xt=k["xt"].clone(), eps=k["eps"].clone(), x0=k["x0"].clone(), x_prev=out.clone())
+        return out
+
+    sch.pred_xprev = spy
+    # the two time lookups of every step (observed, not modified): t of the refined sigma for the encode pass, t_hat of
+    # the corrected sigma for the forward pass (src/experiments.py:410,427)
+    t_first, t_second = [], []
+    orig_enc, orig_pred = exp.encode_xt, exp.pred_xt
+
+    def enc_spy(xt, t, sigma=None, batch_t=True):
+        t_first.append(torch.as_tensor(t).reshape(-1).float().expand(B).clone())
+        return orig_enc(xt, t, sigma=sigma, batch_t=batch_t)
+
+    def pred_spy(xt, t, sigma=None, batch_t=True):
+        t_second.append(torch.as_tensor(t).reshape(-1).float().expand(B).clone())
+        return orig_pred(xt, t, sigma=sigma, batch_t=batch_t)
+
+    exp.encode_xt, exp.pred_xt = enc_spy, pred_spy
+    final, _ = exp.denoise_loop(shape=shape, gen=exp.new_gen(5), style="pred", norm_eps=True, refine_prior_sigma=True,
+                                return_log=False, chunk_size=1, sigma_pred_threshold=960)
+    sig_hat = torch.stack([v.expand(B) for v in rec["sigma_t"]])  # [steps, B] (scalar on the 'base' steps)
+    t_hat = torch.searchsorted(sch.sigmas, sig_hat.contiguous())  # the time bucket each corrected sigma falls in
+    assert len(t_first) == steps and len(t_second) == steps and torch.equal(torch.stack(t_second).long(), t_hat)
+    torch.save(dict(final=final, t_first=torch.stack(t_first), z_digest=_checksum(z), noise_digest=torch.stack([_checksum(n) for n in noises]),
+                    sigma_t=sig_hat, sigma_prev=torch.stack([v.expand(B) for v in rec["sigma_prev"]]), t_hat=t_hat,
+                    snap=rec["snap"], timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone(),
+                    table=sch.sigmas.clone()), os.path.join(HERE, "loop_c2_100.pt"))
+
+
+def nets_bench():
+    """Network outputs of the unmodified reference at the c3 (EDM SongUNet-64) and c4/c5 (ADM-256) architectures
+    -> nets_bench.pt"""
+    torch.set_num_threads(8)
+    gold = {}
+    cfg, sg, sd, ssd, net, snet = edm_reference_modules("edm64")
+    Rr = cfg["img_resolution"]
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 3, Rr, Rr, generator=g)
+    c_noise = torch.tensor([0.73, -1.1])
+    with torch.no_grad():
+        out, feat = net(x, c_noise, None), net.encode(x, c_noise, None)
+        r = snet(feat)
+    gold["edm64"] = dict(x=x, c_noise=c_noise, out=out, feat=feat, r=r)
+    del net, snet, sd, ssd
+    cfg, sg, sd, ssd, net, snet = adm_reference_modules("adm256")
+    del sd, ssd
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(1, 3, cfg["image_size"], cfg["image_size"], generator=g)
+    t = torch.tensor([412.0])
+    with torch.no_grad():
+        out, feat = net(x, t), net.encode(x, t)
+        r = snet(feat)
+    gold["adm256"] = dict(x=x, t=t, out=out, feat=feat, r=r)
+    torch.save(gold, os.path.join(HERE, "nets_bench.pt"))
+
+
+def steps_adm256():
+    """Configs c4 / c5 on the unmodified reference at 256 x 256: the DDNM-constrained NLC loop (ADM-256 with the learned
+    variance head, ddim_simple_orig eta 0.85, dynamic clip, svd projection) for SR x4 (c4) and colourisation (c5),
+    batch 1, a 2-step schedule from sigma 20 (3 loop iterations incl. the final one to sigma 0), every pred_xprev call
+    observed  -> steps_adm256.pt"""
+    from functools import partial
+    R = refimport.load()
+    IS = image_sample_module()
+    torch.set_num_threads(8)
+    cfg, sg, sd, ssd, net, snet = adm_reference_modules("adm256")
+    del sd, ssd
+    side, B, C = cfg["image_size"], 1, 3
+    shape = (B, C, side, side)
+    ref = R.svd_operators
+    gold = {}
+    for task, scale in (("sr_averagepooling", 4), ("colorization", 1)):
+        A_funcs = ref.SuperResolution(C, side, scale, "cpu") if task == "sr_averagepooling" else ref.Colorization(side, "cpu")
+        A, Ap = A_funcs.A, A_funcs.A_pinv
+
+        def affine_svd(x0_t, y, lambda_t, A, Ap):  # image_sample.py:376-379
+            return x0_t - Ap(A(x0_t.reshape(x0_t.size(0), -1)) - y.reshape(y.size(0), -1)).reshape(*x0_t.size())
+
+        con = IS.Constraint_Function(task, A, Ap, partial(affine_svd, A=A, Ap=Ap), proj="svd", channels=C,
+                                     image_size=side, lr=1.0)
+        g = torch.Generator().manual_seed(32)
+        x_true = torch.rand(shape, generator=g) * 2 - 1
+        y = con.transform(x_true)
+        sch = R.schedulers.get_sampler("ddim_simple_orig", 1000, 2, start_sigma=20.0, eta=0.85, sampler_var="learned")
+        exp = R.experiments.ImageExperiment(net, sch, batch_size=B, data_shape=shape[1:], seed=5, device="cpu")
+        exp.set_model(net, snet, learn_epsvar=True)
+        exp.set_norm_maxmin(-2.0, 110.0)
+        exp.set_clip_fn("dynamic")
+        torch.manual_seed(5)
+        z = torch.randn(shape)
+        noises = [torch.randn(shape) for _ in range(len(sch.timesteps) - 1)]
+        rec = dict(sigma_t=[], sigma_prev=[], x_prev=[], x0=[])
+        orig = sch.pred_xprev
+
+        def spy(*a, _orig=orig, _rec=rec, **k):
+            out = _orig(*a, **k)
+            _rec["x0"].append(k["x0"].clone())
+            _rec["sigma_t"].append(torch.as_tensor(k["sigma_t"]).reshape(-1).clone())
+            _rec["sigma_prev"].append(torch.as_tensor(k["sigma_prev"]).reshape(-1).clone())
+            _rec["x_prev"].append(out.clone())
+            return out
+
+        sch.pred_xprev = spy
+        final, logs = exp.denoise_loop(shape=shape, gen=exp.new_gen(5), style="pred",
+                                       constrain_fn=partial(con.constraint_fn, y=y, lambda_t=con.lr), norm_eps=True,
+                                       refine_prior_sigma=True, return_log=True, chunk_size=1,
+                                       constrain_loss=partial(con.loss, y=y), sigma_pred_threshold=960)
+        gold["%s|%d" % (task, scale)] = dict(
+            y=y, x_true_digest=_checksum(x_true), z_digest=_checksum(z),
+            noise_digest=torch.stack([_checksum(n) for n in noises]), final=final, const=logs[4],
+            timesteps=sch.timesteps.clone(), sigmas=sch.sampling_sigmas.clone(), **rec)
+    torch.save(gold, os.path.join(HERE, "steps_adm256.pt"))
+
+
+def bench_arch():
+    loop_c2()
+    nets_bench()
+    steps_adm256()
 
 
 if __name__ == "__main__":

@@ -86,23 +86,33 @@ def test_teacher_forced_steps_against_reference_dumps(golden_loops, prec, key):
         assert _l2rel(xpr.cpu(), case["x_prev"][i]) < 1e-5, (key, i)
 
 
-@pytest.mark.parametrize("prec,min_psnr", [("tf32", 40.0), ("bf16", 30.0), ("fp16", 40.0)])
-def test_free_running_trajectory_psnr(golden_loops, prec, min_psnr):
-    """(The unconstrained loop with random-init weights is bimodal: ~70 dB when no sample's t_hat = searchsorted(sigma_hat)
-    lands in a neighbouring time bucket, ~41 dB when one of the 12 sample-steps does, which for sigma_hat errors of a few
-    1e-4 is a coin flip decided by last-bit details; the thresholds are set below the lower mode.)
-    ddim_simple_orig (the driver default, image_sample.py:56,65) re-derives eps from the clipped x0 each step and
-    is contractive even for random-init weights; deterministic DDIM is not and is gated by the
-    teacher-forced test only."""
+@pytest.mark.parametrize("prec,min_sync,min_free", [("tf32", 45.0, 40.0), ("bf16", 45.0, 30.0), ("fp16", 45.0, 40.0)])
+def test_free_running_trajectory_psnr(golden_loops, prec, min_sync, min_free):
+    """Final-image PSNR of the free-running loop, two gates (see tests/test_gpu_bench_arch.py for the same at the c2 size):
+    `min_sync` with the reference's own time buckets (both discrete lookups t = searchsorted(sigma) of every step taken from
+    the recorded reference run through `time_source`, everything else free-running) - the north-star's >= 45 dB, decided by
+    arithmetic precision alone; `min_free` entirely free, where the result is bimodal: ~70 dB when none of the 12 sample-steps
+    lands in a neighbouring time bucket, ~41 dB when one does, which for sigma_hat errors of a few 1e-4 against ~1 % buckets
+    is decided by last-bit details.  ddim_simple_orig (the driver default, image_sample.py:56,65) re-derives eps from the
+    clipped x0 each step; deterministic DDIM with random-init weights diverges after a flip and is gated teacher-forced
+    only."""
     case = golden_loops["ddim_simple_orig|0.85|none"]
     exp, sch = _setup(prec, "ddim_simple_orig", 0.85, "none")
     xT = (case["z"] / (1 / (case["sigmas"][0] ** 2 + 1)).sqrt()).to(dev)
-    out, logs = exp.denoise_loop(shape=tuple(xT.shape), xT=xT, style="pred", norm_eps=True, refine_prior_sigma=True,
-                                 return_log=True, noise_fn=lambda i, like: case["noises"][i].to(dev))
-    assert out.device.type == "cpu" and len(logs[1]) == len(case["eps"])
-    mse = torch.mean((out - case["final"]) ** 2).item()
-    psnr = 10 * torch.log10(torch.tensor(4.0 / max(mse, 1e-20))).item()
-    assert psnr >= min_psnr, psnr
+    res = {}
+    for name in ("sync", "free"):
+        if name == "sync":
+            exp.time_source = lambda i: (case["t_first"][i].to(dev), case["t_hat"][i].to(dev))
+        out, logs = exp.denoise_loop(shape=tuple(xT.shape), xT=xT, style="pred", norm_eps=True, refine_prior_sigma=True,
+                                     return_log=True, noise_fn=lambda i, like: case["noises"][i].to(dev))
+        exp.time_source = None
+        assert out.device.type == "cpu" and len(logs[1]) == len(case["eps"])
+        mse = torch.mean((out - case["final"]) ** 2).item()
+        res[name] = 10 * torch.log10(torch.tensor(4.0 / max(mse, 1e-20))).item()
+    print("\ntiny loop %s: PSNR %.1f dB with the reference's time buckets, %.1f dB entirely free" % (
+        prec, res["sync"], res["free"]))
+    assert res["sync"] >= min_sync, res
+    assert res["free"] >= min_free, res
 
 
 def test_loop_properties_at_benchmark_shape():

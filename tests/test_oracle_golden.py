@@ -368,3 +368,80 @@ def test_sigma_model_training_iteration(golden_dir):
     for n, e in zip(names, opt.ema):
         check(params[n], g["new_params"][n], 1e-5, ("param", n))
         check(e, g["ema"][n], 1e-5, ("ema", n))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Benchmark architectures (tests/golden/make_golden.py bench_arch): the oracle at the REAL c2 / c3 / c4-c5 sizes
+def _digest(t):
+    v = t.double().reshape(-1)
+    return torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, dtype=torch.float64)).sum() / v.numel()])
+
+
+def same_digest(t, want):
+    """(float64 sums over ~1e5 values differ in the last bits between machines: compared to 1e-9 relative)"""
+    return torch.allclose(_digest(t) if t.dim() != 1 or t.numel() != 2 else t, want, rtol=1e-9, atol=1e-9)
+
+
+def bench_noise(shape, n, seed=5):
+    """The reference's draws for a loop seeded with `seed` (x_T first, then one per step), regenerated instead of stored."""
+    torch.manual_seed(seed)
+    z = torch.randn(shape)
+    return z, [torch.randn(shape) for _ in range(n)]
+
+
+def test_c2_loop_snapshots_at_the_benchmark_architecture(golden_dir):
+    """tests/golden/loop_c2_100.pt (config c2: CelebA-64 unet_ddim, 100 steps, batch 4): the regenerated noise matches the
+    recorded digests, and the oracle's NLC step reproduces the reference's sigma_hat / eps / x_{t-1} bit for bit on the
+    reference's own x_t at three of the stored steps (the whole 100-step loop is ~90 s of CPU and is left to the GPU)."""
+    g = load(golden_dir, "loop_c2_100.pt")
+    shape = (4, 3, 64, 64)
+    z, noises = bench_noise(shape, 100)
+    assert same_digest(z, g["z_digest"])
+    assert all(same_digest(n, d) for n, d in zip(noises, g["noise_digest"]))
+    cfg = weights.CONFIGS["c2"]
+    sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
+    ssd = weights.ddim_sigma_state_dict(**cfg["sigma"], seed=4)
+    tab = S.Tables()
+    ts, sig, mvc = tab.ddim_schedule(100.0, None, 100)
+    assert torch.equal(ts, g["timesteps"]) and torch.equal(sig, g["sigmas"]) and torch.equal(tab.sigmas, g["table"])
+    assert torch.equal(torch.searchsorted(tab.sigmas, g["sigma_t"].contiguous()), g["t_hat"])
+    d = 3 * 64 * 64
+    fwd = lambda z_, t: ddim_net.unet_forward(sd, z_, t)
+    enc = lambda z_, t: ddim_net.unet_encode(sd, z_, t)
+    sgf = lambda f: ddim_net.sigma_forward(ssd, f)
+    for i in (0, 25, 99):
+        sn = g["snap"][i]
+        log = []
+        with torch.no_grad():
+            S.denoise_loop(tab, ts[i:i + 2].tolist(), sig[i:i + 2], mvc, fwd, enc, sgf, sn["xt"], kind="ddim_simple_orig",
+                           eta=0.85, style="pred", norm_eps=True, refine=True, norm_min=-2.0 / d ** 0.5,
+                           norm_max=110.0 / d ** 0.5, noises=[noises[i]], sigma_pred_threshold=960, log=log)
+        st = log[0]
+        assert torch.equal(st["sigma_t"], g["sigma_t"][i]) and torch.equal(st["sigma_prev"], g["sigma_prev"][i]), i
+        assert torch.equal(st["eps"], sn["eps"]) and torch.equal(st["x0"], sn["x0"]), i
+        assert torch.equal(st["x_prev"], sn["x_prev"]), i
+
+
+def test_networks_at_the_benchmark_architectures(golden_dir):
+    """tests/golden/nets_bench.pt: EDM SongUNet-64 (c3) and ADM-256 (c4/c5) outputs of the unmodified reference."""
+    from oracle import adm_net, edm_net
+    g = load(golden_dir, "nets_bench.pt")
+    cfg = dict(weights.EDM_CONFIGS["edm64"])
+    sg = cfg.pop("sigma")
+    sd, ssd = weights.edm_unet_state_dict(**cfg, seed=3), weights.edm_sigma_state_dict(**sg, seed=4)
+    e = g["edm64"]
+    with torch.no_grad():
+        out, feat = edm_net.unet_forward(sd, e["x"], e["c_noise"], cfg, return_feat=True)
+        r = edm_net.sigma_forward(ssd, feat)
+    assert torch.equal(out, e["out"]) and torch.equal(feat, e["feat"]) and torch.equal(r, e["r"])
+    del sd, ssd
+    cfg = dict(weights.ADM_CONFIGS["adm256"])
+    sg = cfg.pop("sigma")
+    sd, ssd = weights.adm_unet_state_dict(**cfg, seed=3), weights.adm_sigma_state_dict(**sg, seed=4)
+    a = g["adm256"]
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        out, feat = adm_net.unet_forward(sd, a["x"], a["t"], cfg, return_feat=True)
+        r = adm_net.sigma_forward(ssd, feat, cfg)
+    torch.set_num_threads(4)
+    assert torch.equal(out, a["out"]) and torch.equal(feat, a["feat"]) and torch.equal(r, a["r"])
