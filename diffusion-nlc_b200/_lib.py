@@ -71,6 +71,7 @@ _SIGNATURES = {
     "nlc_create": (_P, [_I]),
     "nlc_destroy": (None, [_P]),
     "nlc_sm_count": (_I, [_P]),
+    "nlc_ctx_set": (_I, [_P, C.c_char_p, _I]),
     "nlc_conv_tc": (_I, [_P, C.POINTER(ConvDesc), _P]),
     "nlc_conv_in_nchw": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _I, _I, _P]),
     "nlc_im2col_in": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _I, _P]),
@@ -82,7 +83,7 @@ _SIGNATURES = {
                                 _I64, C.c_double, C.c_double, _P]),
     "nlc_ssim3d_ws": (_SZ, [_I, _I, _I]),
     "nlc_ssim3d": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
-    "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P]),
+    "nlc_groupnorm": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P]),
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "nlc_resample_op": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

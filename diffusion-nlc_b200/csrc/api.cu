@@ -55,11 +55,26 @@ nlc_ctx* nlc_create(int device) {
     ctx->encode_tiled = reinterpret_cast<nlc::encode_tiled_fn>(fn);
     const char* e = getenv("NLC_CTA_PAIRS");
     ctx->use_cta_pairs = !(e && e[0] == '0');
+    e = getenv("NLC_SLAB");
+    ctx->use_slab = e ? atoi(e) : 1;
     return ctx;
 }
 
 void nlc_destroy(nlc_ctx* ctx) { delete ctx; }
 
 int nlc_sm_count(nlc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int nlc_ctx_set(nlc_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return nlc::set_error(NLC_EINVAL, "nlc_ctx_set: null argument");
+    if (!strcmp(key, "cta_pairs")) {
+        ctx->use_cta_pairs = value != 0;
+    } else if (!strcmp(key, "slab")) {
+        if (value < 0 || value > 2) return nlc::set_error(NLC_EINVAL, "nlc_ctx_set: slab must be 0, 1 or 2");
+        ctx->use_slab = value;
+    } else {
+        return nlc::set_error(NLC_EINVAL, "nlc_ctx_set: unknown key '%s'", key);
+    }
+    return NLC_OK;
+}
 
 }  // extern "C"

@@ -25,52 +25,9 @@
 // A_lo.W_lo term is ~2^-22 relative).  Because the tensor core's own accumulation truncates, every K chunk gets a
 // fresh TMEM accumulator and the epilogue warps sum the chunks in registers.  This is the accuracy mode behind the
 // <=1e-4 per-step parity tests.
-#include "common.h"
-#include "ptx.cuh"
+#include "conv_common.cuh"
 
 namespace nlc {
-
-constexpr int kBlockM = 128;
-constexpr int kChunkBytes = 128;                      // one swizzle row = one K chunk
-constexpr int kAStageBytes = kBlockM * kChunkBytes;   // 16 KB
-constexpr int kEpiWarps = 8;                       // two per TMEM lane quarter: they split the column chunks
-constexpr int kThreads = 64 + 32 * kEpiWarps + 32;  // warp 0 TMA (A tiles), warp 1 MMA, warps 2.. epilogue, last warp TMA (W tiles)
-constexpr int kSplitWarps = 4;                     // MODE 2 only: warps 2+kEpiWarps.. split fp32 stages into hi/lo
-constexpr int kThreadsX3 = 64 + 32 * kEpiWarps + 32 * kSplitWarps;  // (one producer warp; the split warps follow the epilogue)
-
-struct ConvSegDev {
-    int map, dh, dw, c0, nchunk;
-};
-
-struct ConvKParams {
-    CUtensorMap mapA[NLC_MAX_SRC];
-    CUtensorMap mapB;
-    int B, Ho, Wo, stride;
-    int BW, BH, BN;
-    int tiles_w, tiles_h, tiles_n;
-    int num_m_tiles, num_n_tiles, num_tiles;
-    int num_m_units;  // M tiles (1-CTA kernel) or M tile pairs (CTA-pair kernel); num_tiles = num_m_units * num_n_tiles
-    int Cout, nseg, total_chunks;
-    ConvSegDev seg[NLC_MAX_SEG];
-    const float* bias;
-    const float* rowvec;
-    int ld_rowvec;
-    const float* resid;
-    int ld_resid;
-    int resid_mode;            // 0 same size, 1 nearest x2 of a half-size tensor, 2 2x2 average of a double-size tensor
-    int log2_wo, log2_ho;      // (power-of-two extents: pixel index -> (n, ho, wo) by shifts)
-    float out_scale;
-    float* out_f32;
-    int ld_out_f32;
-    void* out_op;
-    int ld_out_op;
-    int out_head_split;
-    int out_up;      // 0, or 1 + 2a + b: output pixel (n,ho,wo) is written at (n, 2ho+a, 2wo+b) of a [B,2Ho,2Wo,.] tensor
-    int w_batched;
-    int f16;         // 16-bit operands are fp16 (kind::f16 with the f16 format bits), not bf16
-    float* stats;    // GroupNorm partials of the fp32 output: [pixel/32][stats_nblk][2] = (mean, M2) over 32 px x 4 ch
-    int stats_nblk;
-};
 
 // CTA2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128
 // rows of A and one half of the B tile, so the weights cross L2->SM once per pair.
@@ -88,57 +45,6 @@ struct ConvCfg {
     static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: alignment slack
 };
-
-// GroupNorm statistics of the tile the epilogue holds in registers, so that the consumer's GroupNorm never re-reads
-// the tensor for them.  One warp = 32 consecutive pixels, f[] = 32 consecutive channels of this lane's pixel.
-// For each of the 8 four-channel blocks the warp writes (mean, M2) over its 32 x 4 values: per-lane two-pass
-// moments of the 4 channels, shifted by lane 0's block mean (a bf16-rounded pivot: any value near the mean removes
-// the cancellation), then a transposing butterfly that reduces the 16 running sums in 16 shuffles.
-__device__ __forceinline__ void gn_partials(const float (&f)[32], int lane, float* __restrict__ dst) {
-    float m[8], v[16];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        m[j] = 0.25f * ((f[4 * j] + f[4 * j + 1]) + (f[4 * j + 2] + f[4 * j + 3]));
-        const float a = f[4 * j] - m[j], b = f[4 * j + 1] - m[j], c = f[4 * j + 2] - m[j], d = f[4 * j + 3] - m[j];
-        v[8 + j] = (a * a + b * b) + (c * c + d * d);
-    }
-    float pv[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint32_t pk = __shfl_sync(0xffffffffu, pack_bf16x2(m[2 * i], m[2 * i + 1]), 0);
-        pv[2 * i] = __uint_as_float(pk << 16);
-        pv[2 * i + 1] = __uint_as_float(pk & 0xffff0000u);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float dm = m[j] - pv[j];
-        v[j] = dm;
-        v[8 + j] += 4.0f * dm * dm;
-    }
-    // lanes end up holding: bit4 -> {sum of (m - p), sum of squares}, bits 3..1 -> block j
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-    float w8[8], w4[4], w2[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        w8[i] = (h16 ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, h16 ? v[i] : v[i + 8], 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        w4[i] = (h8 ? w8[i + 4] : w8[i]) + __shfl_xor_sync(0xffffffffu, h8 ? w8[i] : w8[i + 4], 8);
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-        w2[i] = (h4 ? w4[i + 2] : w4[i]) + __shfl_xor_sync(0xffffffffu, h4 ? w4[i] : w4[i + 2], 4);
-    float z = (h2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? w2[0] : w2[1], 2);
-    z += __shfl_xor_sync(0xffffffffu, z, 1);
-    const float s2 = __shfl_xor_sync(0xffffffffu, z, 16);
-    if ((lane & 17) == 0) {  // bit4 == 0 (holds s1), bit0 == 0 (one of the two duplicates)
-        const float p4a = h8 ? pv[4] : pv[0], p4b = h8 ? pv[5] : pv[1], p4c = h8 ? pv[6] : pv[2], p4d = h8 ? pv[7] : pv[3];
-        const float p2a = h4 ? p4c : p4a, p2b = h4 ? p4d : p4b;
-        const float piv = h2 ? p2b : p2a;
-        const int j = (lane >> 1) & 7;
-        // mean = p + s1/32;  M2 = sum (x-p)^2 - 128 (mean-p)^2 = s2 - s1^2/8
-        *reinterpret_cast<float2*>(dst + 2 * j) = make_float2(piv + z * (1.0f / 32.0f), fmaxf(s2 - z * z * 0.125f, 0.0f));
-    }
-}
 
 template <int BLOCK_N, int MODE, bool CTA2>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
@@ -470,7 +376,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     }
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[acc]);
+                    if (lane == 0) mbar_arrive_relaxed(&tempty[acc]);
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
@@ -626,7 +532,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CTA2) mbar_arrive_remote(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
+                    if (CTA2) mbar_arrive_remote_relaxed(&tempty[acc], 0); else mbar_arrive_relaxed(&tempty[acc]);
                 }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
@@ -644,6 +550,10 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 }
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+// conv_slab.cu
+bool conv_slab_eligible(const nlc_ctx* ctx, const nlc_conv_desc* d, int chunk);
+int launch_conv_slab(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p, int chunk, bool tf32, cudaStream_t stream);
 
 template <int BLOCK_N, int MODE, bool CTA2>
 static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream, int device) {
@@ -739,6 +649,9 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
             }
         }
     }
+    // 3x3 stride-1 layers of small images: the halo-slab kernel (conv_slab.cu; CTA pairs, 128-wide accumulators)
+    const bool slab = conv_slab_eligible(ctx, d, chunk);
+    if (slab) block_n = 128, pair = true;
     p.num_n_tiles = d->Cout / block_n;
     p.num_m_units = pair ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles;
     p.num_tiles = p.num_m_units * p.num_n_tiles;
@@ -761,6 +674,10 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.f16 = d->dtype == NLC_F16;
     for (int s = 0; s < d->nsrc; ++s) {
         const nlc_operand& o = d->src[s];
+        NLC_REQUIRE(o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && (static_cast<size_t>(o.ld) * esz) % 16 == 0,
+                    "nlc_conv_tc: source %d must be 16-byte aligned (ptr and row pitch)", s);
+        NLC_REQUIRE(o.B == d->B, "nlc_conv_tc: source %d batch %d != %d", s, o.B, d->B);
+        if (slab) continue;  // (launch_conv_slab encodes the slab boxes)
         NLC_REQUIRE(o.ptr && (reinterpret_cast<uintptr_t>(o.ptr) & 15) == 0 && (static_cast<size_t>(o.ld) * esz) % 16 == 0,
                     "nlc_conv_tc: source %d must be 16-byte aligned (ptr and row pitch)", s);
         NLC_REQUIRE(o.B == d->B, "nlc_conv_tc: source %d batch %d != %d", s, o.B, d->B);
@@ -833,6 +750,7 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;
 
+    if (slab) return launch_conv_slab(ctx, d, p, chunk, tf32, stream);
     if (pair) {
         const int pairs = p.num_tiles < ctx->sm_count / 2 ? p.num_tiles : ctx->sm_count / 2;
         if (tf32) {

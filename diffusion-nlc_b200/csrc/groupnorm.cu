@@ -212,7 +212,25 @@ __device__ __forceinline__ void gn_act8(const float4 v0, const float4 v1, const 
 // grid (chunks, B); dynamic smem 2*C floats: y = act(x*ca[c] + cb[c]).  Four independent 32-byte loads in flight
 // per thread.
 constexpr int kGnUnrollMax = 8;
-template <bool TF32, int MODE>
+// X16: the input is a 16-bit tensor in the operand dtype (the activation between a ResBlock's two convolutions, which in the
+// 16-bit modes is written by the first conv's epilogue in the operand dtype only, its statistics coming from the fp32
+// accumulators): 16-byte loads of 8 channels instead of two 16-byte fp32 loads (MODE 0 only).
+__device__ __forceinline__ void unpack_op16x8(uint4 u, int f16, float4& a, float4& b) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (f16) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+            f[2 * k] = t.x, f[2 * k + 1] = t.y;
+        } else {
+            f[2 * k] = __uint_as_float(w[k] << 16), f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+    }
+    a = make_float4(f[0], f[1], f[2], f[3]), b = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+template <bool TF32, int MODE, bool X16 = false>
 __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
     gn_apply_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C, int groups,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
@@ -275,6 +293,9 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                         v[u][2 * q] = __ldg(reinterpret_cast<const float4*>(xq));
                         v[u][2 * q + 1] = __ldg(reinterpret_cast<const float4*>(xq + 4));
                     }
+                } else if (X16) {
+                    const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + (img_in + pix) * ld_x + c;
+                    unpack_op16x8(__ldg(reinterpret_cast<const uint4*>(xp)), rnd, v[u][0], v[u][1]);
                 } else {
                     const float* xp = x + (img_in + pix) * ld_x + c;
                     v[u][0] = __ldg(reinterpret_cast<const float4*>(xp));
@@ -405,7 +426,7 @@ static int pick_chunks(int B, int HW, int sm_count, int min_rows) {
     return chunks;
 }
 
-template <bool TF32, int MODE>
+template <bool TF32, int MODE, bool X16 = false>
 static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, int groups, const float* gamma,
                         const float* beta, const float* scale, const float* shift, int ld_ss, int do_silu,
                         const float* mr, void* y, int ld_y, int sm_count, int rnd, cudaStream_t stream) {
@@ -419,7 +440,7 @@ static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, in
     const int per = static_cast<int>((items + chunks - 1) / chunks);
     chunks = (items + per - 1) / per;
     const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
-    gn_apply_kernel<TF32, MODE><<<dim3(static_cast<unsigned>(chunks), B), kGnThreads, smem, stream>>>(
+    gn_apply_kernel<TF32, MODE, X16><<<dim3(static_cast<unsigned>(chunks), B), kGnThreads, smem, stream>>>(
         x, ld_x, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y, ld_y, per, rnd);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
@@ -434,12 +455,15 @@ extern "C" size_t nlc_groupnorm_ws(int B, int HW, int C, int groups) {
     return static_cast<size_t>(B) * kGnMaxChunks * groups * 3 + static_cast<size_t>(B) * groups * 2;
 }
 
-extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int groups, float eps,
+extern "C" int nlc_groupnorm(nlc_ctx* ctx, const void* x_, int x_is_op, int ld_x, int B, int H, int W, int C, int groups, float eps,
                              const float* gamma, const float* beta, const float* scale, const float* shift,
                              int ld_ss, int do_silu, const float* stats, int stats_nblk, int resample, void* y_op,
                              int ld_y, int op_dtype, float* workspace, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const float* x = static_cast<const float*>(x_);
     NLC_REQUIRE(ctx && x && y_op && workspace, "nlc_groupnorm: null argument");
+    NLC_REQUIRE(!x_is_op || (dtype_is16(op_dtype) && stats && resample == 0 && ld_x % 8 == 0),
+                "nlc_groupnorm: an operand-dtype input needs a 16-bit mode, conv-epilogue statistics and no resampling");
     NLC_REQUIRE(groups >= 1 && groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0 && C % 8 == 0,
                 "nlc_groupnorm: C=%d groups=%d unsupported (channels per group must be a multiple of 4)", C, groups);
     NLC_REQUIRE(ld_x % 4 == 0 && ld_y % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -493,6 +517,9 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int 
         if (resample == 1) NLC_GN_APPLY(true, 1);
         NLC_GN_APPLY(true, 2);
     }
+    if (x_is_op)
+        return launch_apply<false, 0, true>(x, ld_x, B, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y_op,
+                                            ld_y, ctx->sm_count, rnd, stream);
     if (resample == 0) NLC_GN_APPLY(false, 0);
     if (resample == 1) NLC_GN_APPLY(false, 1);
     NLC_GN_APPLY(false, 2);

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
+from .engine import (Engine, Feat, PlanCtx, h_feat, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
                      emit_groupnorm, emit_upsample_conv3x3, run, upsample_conv_eligible)
 from .ops import Act
 
@@ -45,11 +45,17 @@ def _check_filter(sd, key):
 class _BlockW:
     """UNetBlock / PureUNetBlock weights (src/edm_networks.py:148-205, 912-955)."""
 
-    def __init__(self, eng, sd, p, up=False, down=False, with_emb=True):
+    def __init__(self, eng, sd, p, up=False, down=False, with_emb=True, adaptive=False, head_ch=None, skip_scale=SKIP_SCALE,
+                 eps=GN_EPS):
+        """`adaptive`, `head_ch`, `skip_scale`, `eps`: the UNetBlock options in which DhariwalUNet differs from the DDPM++
+        network (adaptive scale/shift, 64-channel heads, skip_scale 1, eps 1e-5; src/edm_networks.py:427-428)."""
         g = lambda k: _g(sd, p + k)
         w0 = g("conv0.weight")
         self.cin, self.cout = w0.shape[1], w0.shape[0]
         self.up, self.down, self.with_emb = up, down, with_emb
+        self.adaptive, self.skip_scale, self.eps = adaptive, float(skip_scale), eps
+        self.heads = 1 if head_ch is None else self.cout // head_ch
+        self.resid_mode = 0
         _check_filter(sd, p + "conv0.resample_filter")
         _check_filter(sd, p + "skip.resample_filter")
         self.n0w, self.n0b = eng.dev32(g("norm0.weight")), eng.dev32(g("norm0.bias"))
@@ -64,12 +70,16 @@ class _BlockW:
             self.w1 = eng.pack3x3(g("conv1.weight"), extra=g("skip.weight"))
             b1 = b1 + g("skip.bias").float()
         else:
-            if up or down:
-                raise NotImplementedError("resample_proj=False skip (kernel 0) is not built by the factory")
+            # a same-width resampling block without resample_proj has a weight-less skip (Conv2d(kernel=0), :172-176): the
+            # residual is x itself, nearest x2 / 2x2 averaged - read at its own resolution by the second conv's epilogue
+            self.resid_mode = 1 if up else (2 if down else 0)
             self.w1 = eng.pack3x3(g("conv1.weight"))
         self.b1 = eng.dev32(b1)
         self.aff_w = g("affine.weight") if with_emb else None
-        self.aff_b = g("affine.bias") if with_emb else None
+        self.aff_b = g("affine.bias").float().cpu() if with_emb else None
+        if with_emb and not adaptive:
+            # (the conv0 bias rides on the per-sample affine row: one vector instead of two in the conv epilogue)
+            self.aff_b = self.aff_b + g("conv0.bias").float().cpu()
         self.emb_off = 0
         self.attn = (p + "qkv.weight") in sd
         if self.attn:
@@ -92,7 +102,7 @@ def _emit_block(pc, w, x, dest, emb=None):
     skip_src = x.op
     if not (w.up or w.down):
         a0 = eng.act_op("ub.a0", B, H, W, w.cin)
-        emit_groupnorm(pc, x.f32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True)
+        emit_groupnorm(pc, x.f32, w.n0w, w.n0b, _groups(w.cin), w.eps, a0, silu=True)
     else:
         # Conv2d(up/down) with the [1,1] filter (src/edm_networks.py:85-93): nearest x2 / 2x2 average of the
         # activated tensor, written directly by the GroupNorm apply pass; the skip branch resamples x itself
@@ -101,48 +111,62 @@ def _emit_block(pc, w, x, dest, emb=None):
         up_low = w.up and w.with_emb and upsample_conv_eligible(H, W)
         if up_low:  # the activated tensor stays at the low resolution; conv0 computes conv(upsample(a0)) from it
             a0 = eng.act_op("ub.a0", B, H, W, w.cin)
-            emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True)
+            emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), w.eps, a0, silu=True)
         H, W = (2 * H, 2 * W) if w.up else (H // 2, W // 2)
         if not up_low:
             a0 = eng.act_op("ub.a0r", B, H, W, w.cin)
-            emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), GN_EPS, a0, silu=True, resample=mode)
-        xs = eng.act_op("ub.xs", B, H, W, w.cin)
-        pc.add(lambda: ops.resample(src32, mode, None, xs, dt), "resample")
-        skip_src = xs
-    rowvec = emb[:, w.emb_off:w.emb_off + w.cout] if (emb is not None and w.with_emb) else None
+            emit_groupnorm(pc, src32, w.n0w, w.n0b, _groups(w.cin), w.eps, a0, silu=True, resample=mode)
+        skip_src = None
+        if w.fused_skip:  # (a weight-less skip reads x at its own resolution in the second conv's epilogue instead)
+            xs = eng.act_op("ub.xs", B, H, W, w.cin)
+            pc.add(lambda: ops.resample(src32, mode, None, xs, dt), "resample")
+            skip_src = xs
+    rowvec = scale = shift = None
+    if emb is not None and w.with_emb:
+        if w.adaptive:  # scale, shift = params.chunk(2): silu(shift + norm1(x) * (scale + 1)), :189-191
+            scale = emb[:, w.emb_off:w.emb_off + w.cout]
+            shift = emb[:, w.emb_off + w.cout:w.emb_off + 2 * w.cout]
+        else:
+            rowvec = emb[:, w.emb_off:w.emb_off + w.cout]
     res_dest = dest
     if w.attn:
         res_dest = Feat(f32=eng.act_f32("ub.y", B, H, W, w.cout))
     if w.with_emb:
-        h = eng.act_f32("ub.h", B, H, W, w.cout)
+        h = eng.act_h("ub.h", B, H, W, w.cout)
         if (w.up or w.down) and up_low:
-            emit_upsample_conv3x3(pc, a0, w.w0_phase, w.b0, w.cout, Feat(f32=h), rowvec=rowvec)
+            emit_upsample_conv3x3(pc, a0, w.w0_phase, w.b0 if rowvec is None else None, w.cout, h_feat(h), rowvec=rowvec)
         else:
-            emit_conv3x3(pc, a0, w.w0, w.b0, w.cout, Feat(f32=h), rowvec=rowvec)
+            emit_conv3x3(pc, a0, w.w0, w.b0 if rowvec is None else None, w.cout, h_feat(h), rowvec=rowvec)
         a1 = eng.act_op("ub.a1", B, H, W, w.cout)
-        emit_groupnorm(pc, h, w.n1w, w.n1b, _groups(w.cout), GN_EPS, a1, silu=True)
+        emit_groupnorm(pc, h, w.n1w, w.n1b, _groups(w.cout), w.eps, a1, silu=True, scale=scale, shift=shift)
     else:
         a1 = eng.act_op("ub.a1", B, H, W, w.cout)
         emit_conv3x3(pc, a0, w.w0, w.b0, w.cout, Feat(op=a1))
     if w.fused_skip:
         assert skip_src is not None, "block with a 1x1 skip needs the operand copy of its input"
-        emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, extra_src=skip_src, out_scale=SKIP_SCALE)
+        emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, extra_src=skip_src, out_scale=w.skip_scale)
     else:
-        emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, resid=x.f32, out_scale=SKIP_SCALE)
+        emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, resid=x.f32, out_scale=w.skip_scale, resid_mode=w.resid_mode)
     if w.attn:
         C = w.cout
         y = res_dest
         a2 = eng.act_op("ub.a2", B, H, W, C)
-        emit_groupnorm(pc, y.f32, w.n2w, w.n2b, _groups(C), GN_EPS, a2, silu=False)
+        emit_groupnorm(pc, y.f32, w.n2w, w.n2b, _groups(C), w.eps, a2, silu=False)
         qkv = eng.act_op("ub.qkv", B, H, W, 3 * C)
         emit_conv1x1(pc, a2, w.wqkv, w.bqkv, 3 * C, Feat(op=qkv))
         o = eng.act_op("ub.o", B, H, W, C)
-        emit_attention(pc, qkv, 0, C, 2 * C, 0, 1, C, float(1.0 / math.sqrt(C)), o)
-        emit_conv1x1(pc, o, w.wproj, w.bproj, C, dest, resid=y.f32, out_scale=SKIP_SCALE)
+        dh = C // w.heads  # rows regrouped as [q | k | v] x [head][channel]; weights softmax(q . k / sqrt(dh)), :124-127
+        emit_attention(pc, qkv, 0, C, 2 * C, dh if w.heads > 1 else 0, w.heads, dh, float(1.0 / math.sqrt(dh)), o)
+        emit_conv1x1(pc, o, w.wproj, w.bproj, C, dest, resid=y.f32, out_scale=w.skip_scale)
 
 
 class SongUNet:
     """Drop-in for src/edm_networks.py:732 `SongUNet` (inference, unconditional DDPM++ configuration)."""
+    # what DhariwalUNet (below) changes
+    _BLOCK_KW = {}
+    _EMB_ENDPOINT, _EMB_COS_FIRST = True, False  # PositionalEmbedding(endpoint=True) + the sin/cos swap of :838
+    _OUT_NORM, _OUT_CONV = "dec.%dx%d_aux_norm", "dec.%dx%d_aux_conv"
+    _OUT_EPS = GN_EPS
 
     def __init__(self, img_resolution, in_channels, out_channels, label_dim=0, augment_dim=0, model_channels=128,
                  channel_mult=(1, 2, 2, 2), channel_mult_emb=4, num_blocks=4, attn_resolutions=(16,), dropout=0.10,
@@ -167,9 +191,10 @@ class SongUNet:
         self.m0w, self.m0b = eng.dev32(sd["map_layer0.weight"]), eng.dev32(sd["map_layer0.bias"])
         self.m1w, self.m1b = eng.dev32(sd["map_layer1.weight"]), eng.dev32(sd["map_layer1.bias"])
         half = mc // 2
-        # PositionalEmbedding(endpoint=True) (src/edm_networks.py:220-224); the sin/cos swap of :838 -> sin || cos
-        freqs = torch.arange(start=0, end=half, dtype=torch.float32) / (half - 1)
+        # PositionalEmbedding (src/edm_networks.py:220-224); SongUNet: endpoint=True and the sin/cos swap of :838 -> sin || cos
+        freqs = torch.arange(start=0, end=half, dtype=torch.float32) / (half - (1 if self._EMB_ENDPOINT else 0))
         self.freqs = ((1 / 10000) ** freqs).to(eng.device)
+        kw = self._BLOCK_KW
         p = "enc.%dx%d_conv." % (R, R)
         self.cin_w, self.cin_b = eng.dev32(sd[p + "weight"]), eng.dev32(sd[p + "bias"])
         self.cin_wp = ops.pack_conv_in_weight(self.cin_w, eng.op_dtype)
@@ -178,21 +203,22 @@ class SongUNet:
         for level in range(L):
             res = R >> level
             if level > 0:
-                self.enc.append((res, _BlockW(eng, sd, "enc.%dx%d_down." % (res, res), down=True)))
+                self.enc.append((res, _BlockW(eng, sd, "enc.%dx%d_down." % (res, res), down=True, **kw)))
             for idx in range(self.num_blocks):
-                self.enc.append((res, _BlockW(eng, sd, "enc.%dx%d_block%d." % (res, res, idx))))
+                self.enc.append((res, _BlockW(eng, sd, "enc.%dx%d_block%d." % (res, res, idx), **kw)))
         for level in reversed(range(L)):
             res = R >> level
             if level == L - 1:
-                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_in0." % (res, res)), False))
-                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_in1." % (res, res)), False))
+                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_in0." % (res, res), **kw), False))
+                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_in1." % (res, res), **kw), False))
             else:
-                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_up." % (res, res), up=True), False))
+                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_up." % (res, res), up=True, **kw), False))
             for idx in range(self.num_blocks + 1):
-                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_block%d." % (res, res, idx)), True))
-        p = "dec.%dx%d_aux_" % (R, R)
-        self.no_w, self.no_b = eng.dev32(sd[p + "norm.weight"]), eng.dev32(sd[p + "norm.bias"])
-        self.cout_w, self.cout_b = eng.dev32(sd[p + "conv.weight"]), eng.dev32(sd[p + "conv.bias"])
+                self.dec.append((res, _BlockW(eng, sd, "dec.%dx%d_block%d." % (res, res, idx), **kw), True))
+        pn, pc_ = (self._OUT_NORM % (R, R) if "%" in self._OUT_NORM else self._OUT_NORM,
+                   self._OUT_CONV % (R, R) if "%" in self._OUT_CONV else self._OUT_CONV)
+        self.no_w, self.no_b = eng.dev32(sd[pn + ".weight"]), eng.dev32(sd[pn + ".bias"])
+        self.cout_w, self.cout_b = eng.dev32(sd[pc_ + ".weight"]), eng.dev32(sd[pc_ + ".bias"])
         self.cout_packed = (ops.pack_conv_out_weight(self.cout_w, self.cout_b, eng.op_dtype)
                             if eng.chunk == 64 and self.cout_w.shape[0] <= 8 else None)
         order = [b for _, b in self.enc]
@@ -203,7 +229,7 @@ class SongUNet:
             if i == n_enc:
                 self.emb_enc = off
             b.emb_off = off
-            off += b.cout
+            off += b.aff_w.shape[0]  # cout, or 2 * cout with adaptive scale/shift
         self.emb_total = off
         self.aw = eng.dev32(torch.cat([b.aff_w for b in order], dim=0))
         self.ab = eng.dev32(torch.cat([b.aff_b for b in order], dim=0))
@@ -275,7 +301,7 @@ class SongUNet:
         enc = PlanCtx(eng, B)
         P["emb_n"], P["use_scale"] = [self.emb_enc], [False]
         x_in, in_scale = P["x"], P["in_scale"]
-        enc.add(lambda: ops.timestep_embedding(P["t"], self.freqs, False, P["emb_sin"]), "embedding")
+        enc.add(lambda: ops.timestep_embedding(P["t"], self.freqs, self._EMB_COS_FIRST, P["emb_sin"]), "embedding")
         enc.add(lambda: ops.linear(P["emb_sin"], self.m0w, self.m0b, P["emb_h"], act_out=1), "map_layer0")
         enc.add(lambda: ops.linear(P["emb_h"], self.m1w, self.m1b, P["emb"], act_out=1), "map_layer1")
         enc.add(lambda: ops.linear(P["emb"], self.aw[:P["emb_n"][0]], self.ab[:P["emb_n"][0]],
@@ -316,7 +342,7 @@ class SongUNet:
             _emit_block(dec, w, x, dest, aff)
             cur = dest
         a = eng.act_op("ub.a0", B, R, R, cur.C)
-        emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, _groups(cur.C), GN_EPS, a, silu=True)
+        emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, _groups(cur.C), self._OUT_EPS, a, silu=True)
         emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         m = max(enc._gn_ws_floats, dec._gn_ws_floats)
         enc._gn_ws_floats = dec._gn_ws_floats = m
@@ -363,6 +389,40 @@ class SongUNet:
 
     def to(self, *a, **k):
         return self
+
+
+class DhariwalUNet(SongUNet):
+    """Drop-in for src/edm_networks.py:406 `DhariwalUNet` (inference, unconditional): the ADM architecture of the EDM code
+    base - the same encoder / decoder skeleton as SongUNet with adaptive scale/shift blocks, 64-channel attention heads at
+    every listed resolution, skip_scale 1, GroupNorm eps 1e-5, weight-less skips in the resampling blocks, the plain
+    cos || sin embedding and `out_norm` / `out_conv`.  Like the reference class it has no `encode`: NLC 'pred*' styles need
+    SongUNet; this is the base-style EDM model of BASELINE config 3."""
+    _BLOCK_KW = dict(adaptive=True, head_ch=64, skip_scale=1.0, eps=1e-5)
+    _EMB_ENDPOINT, _EMB_COS_FIRST = False, True
+    _OUT_NORM, _OUT_CONV = "out_norm", "out_conv"
+    _OUT_EPS = 1e-5
+
+    def __init__(self, img_resolution, in_channels, out_channels, label_dim=0, augment_dim=0, model_channels=192,
+                 channel_mult=(1, 2, 3, 4), channel_mult_emb=4, num_blocks=3, attn_resolutions=(32, 16, 8), dropout=0.10,
+                 label_dropout=0, precision="bf16", device="cuda", **kwargs):
+        for m in channel_mult:
+            if (model_channels * m // 32) % 4 != 0 and model_channels * m >= 128:
+                raise NotImplementedError("DhariwalUNet: %d channels give %d per GroupNorm group; the GroupNorm kernels take "
+                                          "multiples of 4 (model_channels 128 / 256 work, 192 does not)"
+                                          % (model_channels * m, model_channels * m // 32))
+        super().__init__(img_resolution, in_channels, out_channels, label_dim=label_dim, augment_dim=augment_dim,
+                         model_channels=model_channels, channel_mult=channel_mult, channel_mult_emb=channel_mult_emb,
+                         num_blocks=num_blocks, attn_resolutions=attn_resolutions, precision=precision, device=device)
+
+    @classmethod
+    def from_reference(cls, m, precision="bf16", device="cuda"):
+        raise NotImplementedError("construct DhariwalUNet with the reference's constructor arguments and load_state_dict()")
+
+    def encode_scaled(self, x, noise_labels, in_scale=None):
+        raise AttributeError("DhariwalUNet has no encode (src/edm_networks.py:406-502): use the 'base' styles")
+
+    def encode(self, *a, **k):
+        raise AttributeError("DhariwalUNet has no encode (src/edm_networks.py:406-502): use the 'base' styles")
 
 
 class SigmaModel:

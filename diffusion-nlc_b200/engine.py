@@ -54,6 +54,11 @@ class Engine:
         self._sizing = None
         # GroupNorm statistics from the producing conv's epilogue (NLC_FUSE_GN_STATS=0 restores the separate pass)
         self.fuse_gn_stats = os.environ.get("NLC_FUSE_GN_STATS", "1") != "0"
+        # 16-bit tensor between a ResBlock's two convolutions (act_h): on in the fp16 mode, whose rounding (2^-11) is far
+        # below the mode's own error budget; off in bf16 (2^-8 on the GroupNorm input costs ~1 dB of the 45 dB gate);
+        # NLC_H16=0|1 overrides
+        h16 = os.environ.get("NLC_H16")
+        self.h16 = (self.op_dtype == NLC_F16) if h16 is None else (h16 != "0" and self.op_dtype in (NLC_BF16, NLC_F16))
 
     # ------------------------------------------------------------------ buffers
     def plan_two_pass(self, build):
@@ -108,6 +113,19 @@ class Engine:
             if self._sizing is None:
                 a.stats = GnStats(st)
         return a
+
+    def act_h(self, tag, B, H, W, C):
+        """The activation between a ResBlock's two convolutions: it only feeds a GroupNorm.  In the 16-bit modes with the
+        statistics taken from the producing conv's fp32 accumulators it is kept in the OPERAND dtype only (`h16`): the conv
+        epilogue writes 2 instead of 4 bytes per element and the GroupNorm apply pass reads 2 instead of 4 - the kernels are
+        bound by bytes through L2 / HBM, not by the tensor pipe.  Otherwise fp32 as before."""
+        if self.h16 and self.fuse_gn_stats and GnStats.eligible(B, H, W, C):
+            a = Act(self.scratch(tag + ".16", (B, H, W, C), self.op_torch))
+            st = self.scratch(tag + ".stats", (B * H * W // 32, C // 4, 2), torch.float32)
+            if self._sizing is None:
+                a.stats = GnStats(st)
+            return a
+        return self.act_f32(tag, B, H, W, C)
 
     def with_stats(self, act):
         """Attach the stats holder of a plan-lifetime (named) fp32 buffer to a view of it."""
@@ -174,15 +192,23 @@ def emit_groupnorm(pc, x32, gamma, beta, groups, eps, y_op, silu=True, scale=Non
     ws = pc.gn_ws(x32.B, x32.H * x32.W, x32.C, groups)
     dt = pc.eng.op_dtype
     fused = x32.stats is not None and x32.stats.covers(x32.c0, x32.C)
+    assert pc.eng._sizing is not None or x32.dtype == torch.float32 or (fused and not resample), \
+        "a 16-bit GroupNorm input needs fused statistics"
     pc.add(lambda: ops.groupnorm(x32, groups, eps, gamma, beta, y_op, dt, ws(), silu=silu, scale=scale, shift=shift,
                                  use_stats=fused, resample=resample),
-           "groupnorm %dx%dx%d B%d%s%s" % (x32.H, x32.W, x32.C, x32.B, " fused-stats" if fused else "",
-                                          (" up2", " pool2")[resample - 1] if resample else ""))
+           "groupnorm %dx%dx%d B%d%s%s%s" % (x32.H, x32.W, x32.C, x32.B, " fused-stats" if fused else "",
+                                            (" up2", " pool2")[resample - 1] if resample else "",
+                                            " x16" if x32.dtype != torch.float32 else ""))
+
+
+def h_feat(h):
+    """Feat around an `Engine.act_h` activation (operand dtype only, or fp32 only)."""
+    return Feat(f32=h) if h.dtype == torch.float32 else Feat(op=h)
 
 
 def _want_stats(dest, Cout):
     """True when the conv writing `dest` should also write GroupNorm partials (and records the coverage)."""
-    a = dest.f32
+    a = dest.f32 if dest.f32 is not None else dest.op
     if a is None or a.stats is None or Cout % 4 != 0 or a.c0 % 4 != 0:
         return False
     a.stats.covered.append((a.c0, a.c0 + Cout))

@@ -188,9 +188,11 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.out_f32, d.ld_out_f32 = out_f32.ptr, out_f32.ld
     if out_op is not None:
         d.out_op, d.ld_out_op = out_op.ptr, out_op.ld
-    if stats:  # GroupNorm partials of the fp32 output, at its channel offset inside the buffer's stats tensor
-        st = out_f32.stats.t
-        d.stats, d.stats_nblk = st.data_ptr() + (out_f32.c0 // 4) * 8, st.shape[1]
+    if stats:  # GroupNorm partials of the output (taken from the fp32 accumulators), at its channel offset inside the
+        # buffer's stats tensor; the holder hangs on the fp32 output, or on the operand copy when that is the only one
+        holder = out_f32 if (out_f32 is not None and out_f32.stats is not None) else out_op
+        st = holder.stats.t
+        d.stats, d.stats_nblk = st.data_ptr() + (holder.c0 // 4) * 8, st.shape[1]
     timer, optimer = STATS.conv_timer, STATS.op_timer
     if timer is not None or optimer is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -282,16 +284,18 @@ def groupnorm_ws(B, HW, C, groups):
                                                          " rs%d" % k["resample"] if k.get("resample") else ""))
 def groupnorm(x, groups, eps, gamma, beta, y_op, op_dtype, ws, silu=True, scale=None, shift=None, use_stats=False,
               resample=0):
-    """GroupNorm (+scale/shift, +SiLU) of fp32 NHWC `x` (Act) into operand `y_op` (Act).  use_stats: merge the
-    partials the producing convolutions wrote (x.stats) instead of a statistics pass; resample 1/2: write the
-    activated tensor nearest-x2 upsampled / 2x2 average pooled."""
+    """GroupNorm (+scale/shift, +SiLU) of NHWC `x` (Act: fp32, or the 16-bit operand dtype with use_stats) into operand
+    `y_op` (Act).  use_stats: merge the partials the producing convolutions wrote (x.stats) instead of a statistics pass;
+    resample 1/2: write the activated tensor nearest-x2 upsampled / 2x2 average pooled."""
+    x_is_op = 0 if x.dtype == torch.float32 else 1
+    assert not x_is_op or (use_stats and x.dtype == OP_DTYPES[op_dtype]), "16-bit GroupNorm input needs fused statistics"
     ld_ss = scale.stride(0) if scale is not None else 0
     st_ptr, st_nblk = None, 0
     if use_stats:
         st = x.stats.t
         st_ptr, st_nblk = C.c_void_p(st.data_ptr() + (x.c0 // 4) * 8), st.shape[1]
     _lib.check(_lib.lib().nlc_groupnorm(
-        _ctx(x.t), C.c_void_p(x.ptr), x.ld, x.B, x.H, x.W, x.C, groups, eps, _p(gamma), _p(beta), _p(scale),
+        _ctx(x.t), C.c_void_p(x.ptr), x_is_op, x.ld, x.B, x.H, x.W, x.C, groups, eps, _p(gamma), _p(beta), _p(scale),
         _p(shift), ld_ss, 1 if silu else 0, st_ptr, st_nblk, resample, C.c_void_p(y_op.ptr), y_op.ld, op_dtype, _p(ws),
         _stream()))
     small = not use_stats and not resample and x.H * x.W * ((x.C // groups) // 4) <= 1024  # one fused launch

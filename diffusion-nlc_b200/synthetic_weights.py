@@ -322,6 +322,61 @@ def edm_unet_state_dict(img_resolution, in_channels, out_channels, model_channel
     return I.sd
 
 
+def _dhariwal_block(I, p, cin, cout, emb_ch, attention=False, up=False, down=False):
+    I.norm(p + "norm0", cin)
+    I.conv(p + "conv0", cin, cout, 3)
+    if up or down:
+        I.sd[p + "conv0.resample_filter"] = torch.full((1, 1, 2, 2), 0.25)
+    I.linear(p + "affine", emb_ch, 2 * cout, gain=0.5)  # adaptive_scale: [scale | shift]
+    I.norm(p + "norm1", cout)
+    I.conv(p + "conv1", cout, cout, 3, gain=0.5)  # init_zero in the reference: re-drawn
+    if cin != cout:
+        I.conv(p + "skip", cin, cout, 1)
+    if up or down:  # (a same-width resampling block has a weight-less skip that only carries the filter buffer)
+        I.sd[p + "skip.resample_filter"] = torch.full((1, 1, 2, 2), 0.25)
+    if attention:
+        I.norm(p + "norm2", cout)
+        I.conv(p + "qkv", cout, 3 * cout, 1)
+        I.conv(p + "proj", cout, cout, 1, gain=0.5)
+
+
+def dhariwal_unet_state_dict(img_resolution, in_channels, out_channels, model_channels, channel_mult, num_blocks,
+                             attn_resolutions, channel_mult_emb=4, seed=0, **_):
+    """Same keys/shapes as src.edm_networks.DhariwalUNet(...).state_dict() (unconditional: label_dim = augment_dim = 0)."""
+    I = _Init(seed)
+    emb = model_channels * channel_mult_emb
+    I.linear("map_layer0", model_channels, emb)
+    I.linear("map_layer1", emb, emb)
+    cout = in_channels
+    skips = []
+    for level, mult in enumerate(channel_mult):
+        res = img_resolution >> level
+        if level == 0:
+            cin, cout = cout, model_channels * mult
+            I.conv("enc.%dx%d_conv" % (res, res), cin, cout, 3)
+        else:
+            _dhariwal_block(I, "enc.%dx%d_down." % (res, res), cout, cout, emb, down=True)
+        skips.append(cout)
+        for idx in range(num_blocks):
+            cin, cout = cout, model_channels * mult
+            _dhariwal_block(I, "enc.%dx%d_block%d." % (res, res, idx), cin, cout, emb, attention=res in attn_resolutions)
+            skips.append(cout)
+    L = len(channel_mult)
+    for level, mult in reversed(list(enumerate(channel_mult))):
+        res = img_resolution >> level
+        if level == L - 1:
+            _dhariwal_block(I, "dec.%dx%d_in0." % (res, res), cout, cout, emb, attention=True)
+            _dhariwal_block(I, "dec.%dx%d_in1." % (res, res), cout, cout, emb)
+        else:
+            _dhariwal_block(I, "dec.%dx%d_up." % (res, res), cout, cout, emb, up=True)
+        for idx in range(num_blocks + 1):
+            cin, cout = cout + skips.pop(), model_channels * mult
+            _dhariwal_block(I, "dec.%dx%d_block%d." % (res, res, idx), cin, cout, emb, attention=res in attn_resolutions)
+    I.norm("out_norm", cout)
+    I.conv("out_conv", cout, out_channels, 3, gain=0.5)
+    return I.sd
+
+
 def edm_sigma_state_dict(dim, channels, n_blocks, seed=1, fc_dim=128):
     """Same keys/shapes as src.edm_networks.SigmaModel(dim, channels, n_blocks).state_dict()."""
     I = _Init(seed)
@@ -345,6 +400,15 @@ def edm_sigma_state_dict(dim, channels, n_blocks, seed=1, fc_dim=128):
     return I.sd
 
 
+DHARIWAL_CONFIGS = {
+    # the ADM architecture of the EDM code base at 64x64 with 128-wide levels (the ImageNet-64 checkpoint's 192-wide levels
+    # give 6 / 18 channels per GroupNorm group, which the GroupNorm kernels do not take: multiples of 4 only)
+    "dhariwal64": dict(img_resolution=64, in_channels=3, out_channels=3, model_channels=128, channel_mult=(1, 2, 3, 4),
+                       num_blocks=3, attn_resolutions=(32, 16, 8)),
+    # two levels, one block per level, for unit tests
+    "dhariwal_tiny": dict(img_resolution=16, in_channels=3, out_channels=3, model_channels=128, channel_mult=(1, 2),
+                          num_blocks=1, attn_resolutions=(8,)),
+}
 EDM_CONFIGS = {
     # c3: EDM ffhq-64 DDPM++
     "edm64": dict(img_resolution=64, in_channels=3, out_channels=3, model_channels=128, channel_mult=(1, 2, 2, 2),

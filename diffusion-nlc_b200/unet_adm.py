@@ -19,7 +19,7 @@ import math
 import torch
 
 from . import ops
-from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
+from .engine import (Engine, Feat, PlanCtx, h_feat, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
                      emit_groupnorm, run)
 from .ops import Act
 
@@ -97,7 +97,7 @@ def _emit_resblock(pc, w, x, dest, emb=None):
         a1 = eng.act_op("rb.a1r", B, H, W, w.cin)
         emit_groupnorm(pc, src32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True, resample=mode)
         resid_mode = mode
-    h = eng.act_f32("rb.h", B, H, W, w.cout)
+    h = eng.act_h("rb.h", B, H, W, w.cout)
     rowvec = scale = shift = None
     if emb is not None and w.emb_w is not None:
         if w.scale_shift:
@@ -105,7 +105,7 @@ def _emit_resblock(pc, w, x, dest, emb=None):
             shift = emb[:, w.emb_off + w.cout:w.emb_off + 2 * w.cout]
         else:
             rowvec = emb[:, w.emb_off:w.emb_off + w.cout]
-    emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, Feat(f32=h), rowvec=rowvec)
+    emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, h_feat(h), rowvec=rowvec)
     a2 = eng.act_op("rb.a2", B, H, W, w.cout)
     emit_groupnorm(pc, h, w.n2w, w.n2b, GROUPS, GN_EPS, a2, silu=True, scale=scale, shift=shift)
     if w.fused_skip:

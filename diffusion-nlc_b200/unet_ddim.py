@@ -14,7 +14,7 @@ import os
 import torch
 
 from . import ops
-from .engine import (Engine, Feat, PlanCtx, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
+from .engine import (Engine, Feat, PlanCtx, h_feat, emit_attention, emit_conv1x1, emit_conv3x3, emit_conv_in, emit_conv_out,
                      emit_groupnorm, emit_upsample_conv3x3, run, upsample_conv_eligible)
 from .ops import Act
 
@@ -38,6 +38,9 @@ class _ResBlockW:
         self.n1w, self.n1b = eng.dev32(g("norm1.weight")), eng.dev32(g("norm1.bias"))
         self.n2w, self.n2b = eng.dev32(g("norm2.weight")), eng.dev32(g("norm2.bias"))
         self.w1, self.b1 = eng.pack3x3(g("conv1.weight")), eng.dev32(g("conv1.bias"))
+        # with a time embedding the conv1 bias rides on the per-sample temb row (UNetModel.load_state_dict adds it to the
+        # fused temb_proj bias): one vector instead of two in the conv epilogue
+        self.b1_host = g("conv1.bias").float().cpu() if with_temb else None
         self.shortcut = None
         b2 = g("conv2.bias").float()
         if prefix + "nin_shortcut.weight" in sd:
@@ -73,8 +76,8 @@ def _emit_resblock(pc, wts, x, dest, rowvec=None):
     B, H, W = x.B, x.H, x.W
     a1 = eng.act_op("rb.a1", B, H, W, wts.cin)
     emit_groupnorm(pc, x.f32, wts.n1w, wts.n1b, GROUPS, GN_EPS, a1, silu=True)
-    h = eng.act_f32("rb.h", B, H, W, wts.cout)
-    emit_conv3x3(pc, a1, wts.w1, wts.b1, wts.cout, Feat(f32=h), rowvec=rowvec)
+    h = eng.act_h("rb.h", B, H, W, wts.cout)
+    emit_conv3x3(pc, a1, wts.w1, wts.b1 if rowvec is None else None, wts.cout, h_feat(h), rowvec=rowvec)
     a2 = eng.act_op("rb.a2", B, H, W, wts.cout)
     emit_groupnorm(pc, h, wts.n2w, wts.n2b, GROUPS, GN_EPS, a2, silu=True)
     if wts.shortcut == "nin":
@@ -179,7 +182,7 @@ class UNetModel:
         self.temb_total = off
         self.temb_enc = self.mid1.temb_off + self.mid1.cout
         self.tpw = eng.dev32(torch.cat([b.temb_w for b in order], dim=0))
-        self.tpb = eng.dev32(torch.cat([b.temb_b for b in order], dim=0))
+        self.tpb = eng.dev32(torch.cat([b.temb_b.float().cpu() + b.b1_host for b in order], dim=0))
         self._loaded = True
         self._plans = {}
         return self

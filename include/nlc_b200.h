@@ -46,6 +46,10 @@ int nlc_abi_version(void);
 nlc_ctx* nlc_create(int device);
 void nlc_destroy(nlc_ctx* ctx);
 int nlc_sm_count(nlc_ctx* ctx);
+/* Kernel-selection switches of a context (defaults from the environment: NLC_CTA_PAIRS, NLC_SLAB):
+ *   "cta_pairs" 0|1  tcgen05 cta_group::2 convolution kernels;
+ *   "slab" 0|1|2     halo-slab 3x3 kernel: off / layers with 128 output channels / every eligible layer. */
+int nlc_ctx_set(nlc_ctx* ctx, const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * N1/N2/N3 building blocks — replace torch.nn.Conv2d / GroupNorm / attention launches inside
@@ -150,8 +154,11 @@ int nlc_nhwc_head_to_nchw(nlc_ctx* ctx, const float* x, int ld, int B, int H, in
  * `stats` != NULL: the statistics pass is skipped; the per-(32 pixel, 4 channel) partials the producing
  * nlc_conv_tc wrote are merged instead (x is then read exactly once).  `resample` applies ADM's resblock_updown
  * h_upd (src/unet_adm.py:236-243) / the EDM block's conv0 resampling (src/edm_networks.py:85-93) to the activated
- * tensor while it is written: y is [B,2H,2W,C] (1) or [B,H/2,W/2,C] (2). */
-int nlc_groupnorm(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int groups, float eps,
+ * tensor while it is written: y is [B,2H,2W,C] (1) or [B,H/2,W/2,C] (2).
+ * `x_is_op` != 0: x is a 16-bit tensor in the operand dtype instead of fp32 (the tensor between a ResBlock's two
+ * convolutions, which the 16-bit modes keep in the operand dtype only; needs `stats`, whose partials the producing conv took
+ * from its fp32 accumulators, and resample == 0): 4 instead of 6 bytes moved per element. */
+int nlc_groupnorm(nlc_ctx* ctx, const void* x, int x_is_op, int ld_x, int B, int H, int W, int C, int groups, float eps,
                   const float* gamma, const float* beta, const float* scale, const float* shift, int ld_ss,
                   int silu, const float* stats /* nullable: partials written by nlc_conv_tc */, int stats_nblk,
                   int resample /* 0 none, 1 nearest x2, 2 avgpool 2x2 of the activated tensor */, void* y_op,

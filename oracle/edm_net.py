@@ -11,6 +11,10 @@ min(32, C//4)), :124-130 (AttentionOp), :148-205 (UNetBlock), :212-225 (Position
 forward / encode), :912-955 (PureUNetBlock), :958-1022 (Downsample, SigmaModel).
 Covers the configuration the factory builds (src/script_util.py:222-270): embedding 'positional', encoder /
 decoder 'standard', adaptive_scale False, resample_proj True, num_heads 1, skip_scale sqrt(0.5), eps 1e-6.
+
+`dhariwal_forward` restates `DhariwalUNet.forward` (src/edm_networks.py:406-502, the ADM architecture inside the EDM code
+base: adaptive scale/shift, 64-channel heads, skip_scale 1, eps 1e-5, weight-less resampling skips, cos||sin embedding);
+it has no `encode`, so it serves the 'base' styles only.  Pinned by tests/golden/nets_dhariwal.pt and live.
 """
 import math
 
@@ -166,3 +170,59 @@ def sigma_forward(sd, feat):
     h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
                      sd["fc_layer.2.bias"], training=False, eps=1e-5)
     return F.linear(F.silu(h), sd["final_mlp.weight"], sd["final_mlp.bias"])[:, :, None, None]
+
+
+# ------------------------------------------------------------------------------------------------ DhariwalUNet
+def dhariwal_block(sd, p, x, emb, up=False, down=False):
+    """UNetBlock.forward with the DhariwalUNet settings (src/edm_networks.py:186-205 with adaptive_scale True, skip_scale 1,
+    eps 1e-5, channels_per_head 64, resample_proj False: a block that only resamples has a weight-less skip)."""
+    orig = x
+    x = _conv(sd, p + "conv0", F.silu(_gn(sd, p + "norm0", x, eps=1e-5)), up=up, down=down)
+    params = F.linear(emb, sd[p + "affine.weight"]).add_(sd[p + "affine.bias"]).unsqueeze(2).unsqueeze(3)
+    scale, shift = params.chunk(chunks=2, dim=1)
+    x = F.silu(torch.addcmul(shift, _gn(sd, p + "norm1", x, eps=1e-5), scale + 1))
+    x = _conv(sd, p + "conv1", x)
+    has_skip = (p + "skip.weight") in sd or (p + "skip.resample_filter") in sd
+    x = x.add_(_conv(sd, p + "skip", orig, up=up, down=down) if has_skip else orig)
+    x = x * 1
+    if p + "qkv.weight" in sd:
+        B, C = x.shape[:2]
+        heads = C // 64
+        q, k, v = _conv(sd, p + "qkv", _gn(sd, p + "norm2", x, eps=1e-5)).reshape(B * heads, C // heads, 3, -1).unbind(2)
+        w = torch.einsum("ncq,nck->nqk", q.to(torch.float32), (k / np.sqrt(k.shape[1])).to(torch.float32)).softmax(dim=2)
+        a = torch.einsum("nqk,nck->ncq", w, v)
+        x = _conv(sd, p + "proj", a.reshape(*x.shape)).add_(x)
+        x = x * 1
+    return x
+
+
+def dhariwal_embedding(sd, noise_labels, model_channels):
+    """PositionalEmbedding(endpoint=False), cos || sin, two SiLU-activated Linear layers (:475-486)."""
+    half = model_channels // 2
+    freqs = torch.arange(start=0, end=half, dtype=torch.float32)
+    freqs = freqs / half
+    freqs = (1 / 10000) ** freqs
+    x = noise_labels.ger(freqs.to(noise_labels.dtype))
+    emb = torch.cat([x.cos(), x.sin()], dim=1)
+    emb = F.silu(F.linear(emb, sd["map_layer0.weight"]).add_(sd["map_layer0.bias"]))
+    emb = F.linear(emb, sd["map_layer1.weight"]).add_(sd["map_layer1.bias"])
+    return F.silu(emb)
+
+
+def dhariwal_forward(sd, x, noise_labels, cfg):
+    """DhariwalUNet.forward (src/edm_networks.py:475-502), unconditional (label_dim = augment_dim = 0)."""
+    emb = dhariwal_embedding(sd, noise_labels, cfg["model_channels"])
+    skips = []
+    for name in _enc_names(cfg):
+        p = "enc.%s." % name
+        if name.endswith("_conv"):
+            x = _conv(sd, p[:-1], x)
+        else:
+            x = dhariwal_block(sd, p, x, emb, down=name.endswith("_down"))
+        skips.append(x)
+    for name in _dec_names(cfg):
+        p = "dec.%s." % name
+        if x.shape[1] != sd[p + "conv0.weight"].shape[1]:
+            x = torch.cat([x, skips.pop()], dim=1)
+        x = dhariwal_block(sd, p, x, emb, up=name.endswith("_up"))
+    return _conv(sd, "out_conv", F.silu(_gn(sd, "out_norm", x, eps=1e-5)))

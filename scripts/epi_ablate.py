@@ -37,7 +37,11 @@ def run(B, H, Cin, Cout, name, **kw):
     print("%-34s %-28s %.3f ms %7.1f TFLOP/s" % ("%dx%d %d->%d B%d" % (H, H, Cin, Cout, B), name, ms, fl / ms / 1e9))
 
 
-for shape in ((256, 64, 128, 128), (32, 256, 256, 256), (256, 32, 256, 256)):
+from nlc_b200 import _lib  # noqa: E402
+if len(sys.argv) > 1:  # slab mode: 0 off, 1 Cout == 128, 2 every eligible layer
+    _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"slab", int(sys.argv[1])))
+    print("slab mode", sys.argv[1])
+for shape in ((256, 64, 128, 128), (32, 256, 256, 256), (256, 32, 256, 256), (256, 64, 256, 128), (64, 64, 512, 512)):
     run(*shape, "op only", f32=False, op=True)
     run(*shape, "f32 only")
     run(*shape, "f32+bias+rowvec", bias=True, rowvec=True)

@@ -776,6 +776,26 @@ def steps_adm256():
     torch.save(gold, os.path.join(HERE, "steps_adm256.pt"))
 
 
+def dhariwal():
+    """DhariwalUNet (src/edm_networks.py:406-502) outputs of the unmodified reference: a two-level test shape and the
+    64 x 64 four-level shape  -> nets_dhariwal.pt"""
+    import importlib
+    refimport.load()
+    EN = importlib.import_module("src.edm_networks")
+    torch.set_num_threads(8)
+    gold = {}
+    for name in ("dhariwal_tiny", "dhariwal64"):
+        cfg = dict(weights.DHARIWAL_CONFIGS[name])
+        net = EN.DhariwalUNet(**{k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}).eval()
+        net.load_state_dict(weights.dhariwal_unet_state_dict(**cfg, seed=3))
+        g = torch.Generator().manual_seed(16)
+        x = torch.randn(2, 3, cfg["img_resolution"], cfg["img_resolution"], generator=g)
+        c_noise = torch.tensor([0.4, -0.9])
+        with torch.no_grad():
+            gold[name] = dict(x=x, c_noise=c_noise, out=net(x, c_noise, None))
+    torch.save(gold, os.path.join(HERE, "nets_dhariwal.pt"))
+
+
 def bench_arch():
     loop_c2()
     nets_bench()

@@ -167,6 +167,21 @@ def test_edm64_network(nets_gold, prec):
     assert (s(g["feat"].to(dev)).cpu() - g["r"]).abs().max() < tol
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fp16", "bf16"])
+@pytest.mark.parametrize("name", ["dhariwal_tiny", "dhariwal64"])
+def test_dhariwal_unet(golden_dir, prec, name):
+    """DhariwalUNet (src/edm_networks.py:406-502: adaptive scale/shift, 64-channel heads at 32 / 16 / 8, weight-less
+    resampling skips) against the unmodified reference, at a two-level shape and at 64 x 64 with four levels."""
+    from nlc_b200.edm_networks import DhariwalUNet
+    cfg = dict(weights.DHARIWAL_CONFIGS[name])
+    g = torch.load(os.path.join(golden_dir, "nets_dhariwal.pt"), weights_only=True)[name]
+    m = DhariwalUNet(precision=prec, device=dev, **cfg).load_state_dict(weights.dhariwal_unet_state_dict(**cfg, seed=3))
+    out = m(g["x"].to(dev), g["c_noise"].to(dev), None)
+    assert _maxrel(out.cpu(), g["out"]) < NET_TOL[prec]
+    with pytest.raises(AttributeError):
+        m.encode(g["x"].to(dev), g["c_noise"].to(dev), None)
+
+
 def _adm_models(prec):
     from nlc_b200.unet_adm import SigmaModel, UNetModel
     cfg = dict(weights.ADM_CONFIGS["adm256"])

@@ -74,6 +74,72 @@ def test_conv_tc_matches_torch(dev, prec, case):
     assert _rel(oop.t.float().permute(0, 3, 1, 2), ref) < (8e-3 if prec == "bf16" else 1e-3)
 
 
+SLAB_CASES = [
+    # B, H, W, Cin, Cout, extra 1x1 channels
+    (3, 64, 64, 128, 128, 0),    # the c2 / c3 shape
+    (2, 64, 64, 256, 128, 0),    # concat input, 12 slabs per unit
+    (3, 16, 16, 128, 128, 0),    # one super tile per image, odd count: the pair's second CTA runs past the end
+    (2, 32, 32, 128, 256, 0),    # two n tiles
+    (2, 64, 64, 128, 128, 192),  # fused 1x1 shortcut over a second tensor (ResBlock with nin_shortcut)
+    (1, 32, 64, 64, 128, 64),    # H != W
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "tf32", "fp16"])
+@pytest.mark.parametrize("case", SLAB_CASES)
+def test_conv_slab_matches_torch(dev, prec, case):
+    """The halo-slab kernel (conv_slab.cu: one slab per channel chunk and horizontal tap feeds the three vertical taps of two
+    M tiles) against torch, forced on for every eligible layer, with the full epilogue (bias, per-sample row, residual, scale,
+    GroupNorm partials, fp32 + operand outputs); and against the tap-per-tile kernel on the same inputs (same products,
+    different summation order)."""
+    from nlc_b200 import _lib, ops
+    B, H, W, Cin, Cout, Cx = case
+    dt = _dt(prec)
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(23)
+    x = _rnd(torch.randn(B, Cin, H, W, generator=g).to(dev), dt)
+    w = _rnd((torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev), dt)
+    b = torch.randn(Cout, generator=g).to(dev)
+    rowvec = torch.randn(B, Cout, generator=g).to(dev)
+    resid = torch.randn(B, H, W, Cout, generator=g).to(dev)
+    ref = F.conv2d(x, w, b, padding=1)
+    srcs = [ops.Act(x.permute(0, 2, 3, 1).contiguous().to(tdt))]
+    segs = ops.taps3x3(0, 0, Cin)
+    extra = None
+    if Cx:
+        wide = _rnd(torch.randn(B, Cx + 64, H, W, generator=g).to(dev), dt)  # the shortcut reads channels [64, 64 + Cx)
+        wx = _rnd((torch.randn(Cout, Cx, 1, 1, generator=g) / Cx ** 0.5).to(dev), dt)
+        ref = ref + F.conv2d(wide[:, 64:], wx)
+        srcs.append(ops.Act(wide.permute(0, 2, 3, 1).contiguous().to(tdt)))
+        segs = segs + [(1, 0, 0, 64, Cx)]
+        extra = wx
+    ref = (ref + rowvec[:, :, None, None] + resid.permute(0, 3, 1, 2)) * 0.5
+    wp = ops.pack_conv_weight(w, dt, extra)
+    outs = {}
+    ctx = _lib.ctx(0)
+    try:
+        for mode in (2, 0):
+            _lib.check(_lib.lib().nlc_ctx_set(ctx, b"slab", mode))
+            st = ops.GnStats(torch.zeros(B * H * W // 32, Cout // 4, 2, device=dev))
+            o32 = ops.Act(torch.full((B, H, W, Cout), float("nan"), device=dev), 0, Cout, st)
+            oop = ops.Act(torch.zeros(B, H, W, Cout, device=dev, dtype=tdt))
+            ops.conv_tc(srcs, segs, wp, Cout, B, H, W, dt, bias=b, rowvec=rowvec, resid=ops.Act(resid), out_scale=0.5,
+                        out_f32=o32, out_op=oop, stats=True)
+            torch.cuda.synchronize()
+            outs[mode] = (o32.t.clone(), oop.t.float().clone(), st.t.clone())
+    finally:
+        _lib.check(_lib.lib().nlc_ctx_set(ctx, b"slab", 1))
+    o32, oop, stats = outs[2]
+    assert _rel(o32.permute(0, 3, 1, 2), ref) < 5e-5
+    assert _rel(oop.permute(0, 3, 1, 2), ref) < (8e-3 if prec == "bf16" else 1e-3)
+    assert _rel(o32, outs[0][0]) < 2e-5
+    # GroupNorm partials: (mean, M2) per 32 pixels x 4 channels
+    blocks = o32.reshape(B * H * W // 32, 32, Cout // 4, 4).permute(0, 2, 1, 3).reshape(-1, Cout // 4, 128).double()
+    assert (stats[:, :, 0].double() - blocks.mean(2)).abs().max() < 1e-4 * blocks.abs().max()
+    m2 = ((blocks - blocks.mean(2, keepdim=True)) ** 2).sum(2)
+    assert ((stats[:, :, 1].double() - m2).abs() / m2.clamp_min(1e-3)).max() < 1e-3
+
+
 @pytest.mark.parametrize("prec", ["bf16", "tf32"])
 def test_conv_tc_fused_shortcut_and_channel_slices(dev, prec):
     """3x3 over one source + 1x1 shortcut over a channel slice of a wider buffer, one accumulator."""
@@ -281,6 +347,43 @@ def test_groupnorm_from_conv_epilogue_statistics(dev, prec, tol, shape):
     assert ((mr[:, :, 1].double() - (xg.var(2, unbiased=False) + 1e-5).rsqrt()) / mr[:, :, 1].double()).abs().max() < 2e-4
 
 
+@pytest.mark.parametrize("prec,tol", [("bf16", 1.2e-2), ("fp16", 1.5e-3)])
+@pytest.mark.parametrize("shape", [(3, 64, 64, 128, 128), (1, 256, 128, 64, 256), (2, 16, 16, 128, 384)])
+def test_groupnorm_of_a_16bit_activation_with_epilogue_statistics(dev, prec, tol, shape):
+    """The tensor between a ResBlock's two convolutions in the 16-bit modes (Engine.act_h): the conv writes it in the operand
+    dtype ONLY, its GroupNorm partials come from the fp32 accumulators, and nlc_groupnorm(x_is_op=1) reads the 16-bit
+    tensor.  Against F.group_norm (+ per-sample scale/shift, SiLU) of the fp32 conv output: the statistics are those of the
+    unrounded tensor (1e-4), the activated output carries one extra operand rounding of its input."""
+    from nlc_b200 import ops
+    B, H, W, Cin, Cout = shape
+    dt = _dt(prec)
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(19)
+    x = _rnd(torch.randn(B, Cin, H, W, generator=g).to(dev), dt)
+    w1 = _rnd((torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5).to(dev), dt)
+    b1 = (torch.randn(Cout, generator=g) + 3.0).to(dev)
+    rv = torch.randn(B, Cout, generator=g).to(dev)
+    ref_h = F.conv2d(x, w1, b1, padding=1) + rv[:, :, None, None]
+    xa = ops.Act(x.permute(0, 2, 3, 1).contiguous().to(tdt))
+    st = ops.GnStats(torch.zeros(B * H * W // 32, Cout // 4, 2, device=dev))
+    h16 = ops.Act(torch.zeros(B, H, W, Cout, device=dev, dtype=tdt), 0, Cout, st)
+    ops.conv_tc([xa], ops.taps3x3(0, 0, Cin), ops.pack_conv_weight(w1, dt), Cout, B, H, W, dt, bias=b1, rowvec=rv,
+                out_op=h16, stats=True)
+    assert _rel(h16.t.float().permute(0, 3, 1, 2), ref_h) < (5e-3 if prec == "bf16" else 6e-4)
+    gam, bet = torch.randn(Cout, generator=g).to(dev), torch.randn(Cout, generator=g).to(dev)
+    sc, sh = (0.3 * torch.randn(B, Cout, generator=g)).to(dev), torch.randn(B, Cout, generator=g).to(dev)
+    ref = F.group_norm(ref_h, 32, gam, bet, eps=1e-5) * (1 + sc[:, :, None, None]) + sh[:, :, None, None]
+    ref = F.silu(ref)
+    y = ops.Act(torch.zeros(B, H, W, Cout, device=dev, dtype=tdt))
+    ws = torch.zeros(ops.groupnorm_ws(B, H * W, Cout, 32), device=dev)
+    ops.groupnorm(h16, 32, 1e-5, gam, bet, y, dt, ws, silu=True, scale=sc, shift=sh, use_stats=True)
+    assert _rel(y.t.float().permute(0, 3, 1, 2), ref) < tol
+    mr = ws[B * 64 * 32 * 3:].view(B, 32, 2)
+    xg = ref_h.reshape(B, 32, -1).double()
+    assert (mr[:, :, 0].double() - xg.mean(2)).abs().max() < 1e-4 * xg.abs().max()
+    assert ((mr[:, :, 1].double() - (xg.var(2, unbiased=False) + 1e-5).rsqrt()) / mr[:, :, 1].double()).abs().max() < 2e-4
+
+
 @pytest.mark.parametrize("prec,tol", [("bf16", 6e-3), ("tf32", 8e-4), ("fp16", 8e-4)])
 @pytest.mark.parametrize("mode", [1, 2])
 def test_groupnorm_with_fused_resample(dev, prec, tol, mode):
@@ -399,10 +502,13 @@ def test_conv_tc_pair_kernel_fused_shortcut_wide_rows(dev):
 def test_conv_tc_resampled_residual(dev, mode, shape):
     """nlc_conv_desc.resid_mode: the residual is read at half (1: nearest x2) / double (2: 2x2 average) resolution by
     the epilogue, bit-identical to adding the separately resampled tensor (ADM resblock_updown x_upd)."""
-    from nlc_b200 import ops
+    from nlc_b200 import _lib, ops
     from nlc_b200._lib import NLC_BF16
     B, H, W = shape
     C = 128
+    # (both launches on the tap-per-tile kernel: the halo-slab kernel, which takes the plain-residual one at these sizes, sums
+    #  the same products in another order)
+    _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"slab", 0))
     g = torch.Generator().manual_seed(31)
     x = _rnd(torch.randn(B, C, H, W, generator=g).to(dev), NLC_BF16)
     w = _rnd((torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(dev), NLC_BF16)
@@ -416,6 +522,7 @@ def test_conv_tc_resampled_residual(dev, mode, shape):
     ops.conv_tc([xa], ops.taps3x3(0, 0, C), wp, C, B, H, W, NLC_BF16, resid=ops.Act(full), out_f32=a)
     ops.conv_tc([xa], ops.taps3x3(0, 0, C), wp, C, B, H, W, NLC_BF16, resid=ops.Act(resid), out_f32=b, resid_mode=mode)
     torch.cuda.synchronize()
+    _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"slab", 1))
     assert torch.equal(a.t, b.t)
     ref = F.conv2d(x, w, padding=1) + full.permute(0, 3, 1, 2)
     assert _rel(b.t.permute(0, 3, 1, 2), ref) < 5e-5

@@ -445,3 +445,15 @@ def test_networks_at_the_benchmark_architectures(golden_dir):
         r = adm_net.sigma_forward(ssd, feat, cfg)
     torch.set_num_threads(4)
     assert torch.equal(out, a["out"]) and torch.equal(feat, a["feat"]) and torch.equal(r, a["r"])
+
+
+@pytest.mark.parametrize("name", ["dhariwal_tiny", "dhariwal64"])
+def test_dhariwal_unet(golden_dir, name):
+    """tests/golden/nets_dhariwal.pt: DhariwalUNet.forward of the unmodified reference (src/edm_networks.py:406-502)."""
+    from oracle import edm_net
+    cfg = dict(weights.DHARIWAL_CONFIGS[name])
+    sd = weights.dhariwal_unet_state_dict(**cfg, seed=3)
+    g = load(golden_dir, "nets_dhariwal.pt")[name]
+    with torch.no_grad():
+        out = edm_net.dhariwal_forward(sd, g["x"], g["c_noise"], cfg)
+    assert torch.equal(out, g["out"])
