@@ -295,7 +295,10 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                     }
                 } else if (X16) {
                     const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + (img_in + pix) * ld_x + c;
-                    unpack_op16x8(__ldg(reinterpret_cast<const uint4*>(xp)), rnd, v[u][0], v[u][1]);
+                    // (raw bits only: unpacking here would make every load wait for its own data before the next issues)
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xp));
+                    v[u][0] = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
+                                          __uint_as_float(raw.w));
                 } else {
                     const float* xp = x + (img_in + pix) * ld_x + c;
                     v[u][0] = __ldg(reinterpret_cast<const float4*>(xp));
@@ -318,6 +321,10 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                     for (int k = 0; k < 8; ++k) f[k] = ((t[0][k] + t[1][k]) + (t[2][k] + t[3][k])) * 0.25f;
                     gn_store8<TF32>(y, (static_cast<size_t>(n) * npix + pix) * ld_y + c, f, rnd);
                 } else {
+                    if (X16)
+                        unpack_op16x8(make_uint4(__float_as_uint(v[u][0].x), __float_as_uint(v[u][0].y),
+                                                 __float_as_uint(v[u][0].z), __float_as_uint(v[u][0].w)),
+                                      rnd, v[u][0], v[u][1]);
                     gn_act8(v[u][0], v[u][1], ca + c, cb + c, do_silu, f);
                     if (MODE == 0) {
                         gn_store8<TF32>(y, (img_in + pix) * ld_y + c, f, rnd);

@@ -12,8 +12,9 @@ from nlc_b200._lib import NLC_BF16
 dev = torch.device("cuda:0")
 shapes = [tuple(int(v) for v in sys.argv[1:5])] if len(sys.argv) >= 5 else [(32, 256, 256, 256), (32, 128, 128, 256),
                                                                            (256, 64, 64, 128), (256, 32, 32, 256)]
-for B, H, W, C in shapes:
-    x = ops.Act(torch.randn(B, H, W, C, device=dev), 0, C, ops.GnStats(torch.rand(B * H * W // 32, C // 4, 2, device=dev)))
+for B, H, W, C, in16 in [s + (i,) for s in shapes for i in (False, True)]:
+    xt = torch.randn(B, H, W, C, device=dev)
+    x = ops.Act(xt.to(torch.bfloat16) if in16 else xt, 0, C, ops.GnStats(torch.rand(B * H * W // 32, C // 4, 2, device=dev)))
     x.stats.covered.append((0, C))
     y = ops.Act(torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16))
     gam, bet = torch.randn(C, device=dev), torch.randn(C, device=dev)
@@ -29,5 +30,6 @@ for B, H, W, C in shapes:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
-    gb = B * H * W * C * 6 / 1e9
-    print("GN apply (+finalize) B%d %dx%d C%d: %.3f ms  %.0f GB/s" % (B, H, W, C, ms, gb / ms * 1e3))
+    gb = B * H * W * C * (4 if in16 else 6) / 1e9
+    print("GN apply (+finalize) B%d %dx%d C%d %s input: %.3f ms  %.0f GB/s" % (B, H, W, C, "16-bit" if in16 else "fp32", ms,
+                                                                              gb / ms * 1e3))
