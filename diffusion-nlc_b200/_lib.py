@@ -41,7 +41,7 @@ class ConvDesc(C.Structure):
         ("resid", C.c_void_p), ("ld_resid", C.c_int), ("out_scale", C.c_float),
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int), ("out_op", C.c_void_p), ("ld_out_op", C.c_int),
         ("out_head_split", C.c_int), ("stats", C.c_void_p), ("stats_nblk", C.c_int), ("resid_mode", C.c_int),
-        ("out_up", C.c_int),
+        ("out_up", C.c_int), ("resid_is_op", C.c_int),
     ]
 
 

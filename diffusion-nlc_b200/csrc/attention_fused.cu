@@ -141,60 +141,63 @@ __global__ void __launch_bounds__(kFaThreads, FaCfg<DH>::kCtasPerSm) attn_fused_
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the pipeline in uniform control flow; one elected lane issues the tcgen05 instructions, whose
+        // operands then stay in uniform registers (ptx.cuh: elect_one_sync).  With 64-key S blocks an MMA is 32 tensor
+        // clocks: the ~17-instruction per-MMA issue sequence of a `lane == 0` loop was the bound of this kernel.
+        {
             const uint32_t idesc_s = umma_idesc(p.f16 ? 0 : 1, kFaBlock, kFaKeys);  // 128 queries x 64 keys
             const uint32_t idesc_o = umma_idesc(p.f16 ? 0 : 1, kFaBlock, DH);       // 128 queries x DH channels
             const uint32_t q_addr = smem_u32(sQ);
             uint32_t kv_it = 0, s_it = 0, p_it = 0, tile_it = 0;
-            // S block `s_it` = Q K^T of the K tile in ring slot `kv_it`
-            auto issue_s = [&](uint32_t kv, uint32_t si) {
+            // S block `si` = Q K^T of the K tile in ring slot `kv`; then the commits named by the flags (same elected lane)
+            auto issue_s = [&](uint32_t kv, uint32_t si, bool free_kv, bool free_q) {
                 const int st = kv % kFaStages;
                 const int sb = si & 1;
                 mbar_wait(&s_empty[sb], ((si >> 1) & 1) ^ 1);
                 mbar_wait(&kv_full[st], (kv / kFaStages) & 1);
                 tc_fence_after_sync();
                 const uint32_t k_addr = smem_u32(sKV + st * kFaStageBytes);
+                if (elect_one_sync()) {
 #pragma unroll
-                for (int c = 0; c < Cfg::kChunks; ++c) {
-                    const uint64_t qdesc = umma_desc_sw128(q_addr + c * kFaTileBytes);
-                    const uint64_t kdesc = umma_desc_sw128(k_addr + c * Cfg::kKChunkBytes);
+                    for (int c = 0; c < Cfg::kChunks; ++c) {
+                        const uint64_t qdesc = umma_desc_sw128(q_addr + c * kFaTileBytes);
+                        const uint64_t kdesc = umma_desc_sw128(k_addr + c * Cfg::kKChunkBytes);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(tmem_base + sb * kFaKeys, qdesc + 2 * k, kdesc + 2 * k, idesc_s, (c | k) != 0);
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base + sb * kFaKeys, qdesc + 2 * k, kdesc + 2 * k, idesc_s, (c | k) != 0);
+                    }
+                    if (free_kv) umma_commit(&kv_empty[st]);
+                    umma_commit(&s_full[sb]);
+                    if (free_q) umma_commit(q_empty);
                 }
+                __syncwarp();
             };
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_it) {
                 mbar_wait(q_full, tile_it & 1);
                 tc_fence_after_sync();
                 // pass 1: logits only (row maxima)
-                for (int kb = 0; kb < nkb; ++kb, ++kv_it, ++s_it) {
-                    issue_s(kv_it, s_it);
-                    umma_commit(&kv_empty[kv_it % kFaStages]);
-                    umma_commit(&s_full[s_it & 1]);
-                }
-                // pass 2: S(kb+1) is issued before P(kb) is awaited, so Q K^T overlaps the softmax of the previous block
-                issue_s(kv_it, s_it);
-                umma_commit(&s_full[s_it & 1]);
+                for (int kb = 0; kb < nkb; ++kb, ++kv_it, ++s_it) issue_s(kv_it, s_it, true, false);
+                // pass 2: S(kb+1) is issued before P(kb) is awaited, so Q K^T overlaps the softmax of the previous block;
+                // after the last Q K^T of the tile has been issued Q may be overwritten once it is done (q_empty)
+                issue_s(kv_it, s_it, false, nkb == 1);
                 mbar_wait(o_empty, (tile_it & 1) ^ 1);  // the previous tile's O has been read out of TMEM
                 for (int kb = 0; kb < nkb; ++kb, ++p_it) {
-                    if (kb + 1 < nkb) {
-                        issue_s(kv_it + kb + 1, s_it + kb + 1);
-                        umma_commit(&s_full[(s_it + kb + 1) & 1]);
-                    } else {
-                        umma_commit(q_empty);  // every Q K^T of this tile has been issued: Q may be overwritten once done
-                    }
+                    if (kb + 1 < nkb) issue_s(kv_it + kb + 1, s_it + kb + 1, false, kb + 2 == nkb);
                     const int pb = p_it & 1;
                     const int st = (kv_it + kb) % kFaStages;
                     mbar_wait(&p_full[pb], (p_it >> 1) & 1);
                     tc_fence_after_sync();
                     const uint64_t pdesc = umma_desc_sw128(smem_u32(sP + pb * kFaPBytes));
                     const uint64_t vdesc = umma_desc_sw128(smem_u32(sKV + st * kFaStageBytes + Cfg::kKBytes));
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (kb | k) != 0);
-                    umma_commit(&kv_empty[st]);
-                    umma_commit(&p_empty[pb]);
+                        for (int k = 0; k < 4; ++k) umma_bf16(tmem_o, pdesc + 2 * k, vdesc + 2 * k, idesc_o, (kb | k) != 0);
+                        umma_commit(&kv_empty[st]);
+                        umma_commit(&p_empty[pb]);
+                        if (kb + 1 == nkb) umma_commit(o_full);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(o_full);
                 kv_it += nkb;
                 s_it += nkb;
             }

@@ -33,6 +33,7 @@ struct ConvKParams {
     int ld_rowvec;
     const float* resid;
     int ld_resid;
+    int resid16;               // the residual is a 16-bit operand-dtype tensor (bf16, or fp16 with f16 set)
     int resid_mode;            // 0 same size, 1 nearest x2 of a half-size tensor, 2 2x2 average of a double-size tensor
     int log2_wo, log2_ho;      // (power-of-two extents: pixel index -> (n, ho, wo) by shifts)
     float out_scale;

@@ -44,6 +44,8 @@ struct SlabParams {
     int num_units;        // pair units x n tiles
     int num_pair_units;
     int nstep;
+    int nstep3;           // the first nstep3 slabs carry three vertical taps (3x3 part), the rest one (fused 1x1 shortcut): the
+                          // MMA issuer takes the tap count from here - a kernel parameter, i.e. provably warp-uniform
     const SlabStep* steps;  // device array [nstep]
 };
 
@@ -138,7 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (the pair's leader)
-        if (lane == 0 && rank == 0) {
+        // whole warp in uniform control flow, one elected lane issues (conv_tc.cu / ptx.cuh: elect_one_sync)
+        if (rank == 0) {
             const uint32_t idesc = umma_idesc(TF32 ? 2 : (p.f16 ? 0 : 1), 2 * kBlockM, kSlabN);
             int ss = 0, ws = 0, acc = 0;
             uint32_t sphase = 0, wphase = 0, acc_phase = 0;
@@ -147,38 +150,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                 mbar_wait(&tempty[acc], acc_phase ^ 1);
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + acc * (kSlabG * kSlabN);
-                bool first = true;
                 for (int i = 0; i < sp.nstep; ++i) {
-                    const SlabStep st = sp.steps[i];
+                    const int ntap = i < sp.nstep3 ? 3 : 1;
                     mbar_wait(&s_full[ss], sphase);
                     tc_fence_after_sync();
                     const uint32_t sa = slab0 + ss * sp.slab_bytes;
-                    for (int t = 0; t < st.ntap; ++t) {
+                    for (int t = 0; t < ntap; ++t) {
                         // a 3-tap slab carries dh = -1, 0, +1 at slab rows +0, +1, +2; a 1-tap slab (1x1 shortcut) the centre
-                        const int dhi = st.ntap == 3 ? t : 1;
+                        const int dhi = ntap == 3 ? t : 1;
                         mbar_wait(&w_full[ws], wphase);
                         tc_fence_after_sync();
                         const uint64_t bdesc = umma_desc_sw128(wt0 + ws * kSlabWBytes);
+                        const uint32_t first = (i | t) == 0 ? 0u : 1u;
+                        if (elect_one_sync()) {
 #pragma unroll
-                        for (int g = 0; g < kSlabG; ++g) {
-                            const uint64_t adesc = umma_desc_sw128(sa + (g * p.BH + dhi) * sp.row_bytes);
+                            for (int g = 0; g < kSlabG; ++g) {
+                                const uint64_t adesc = umma_desc_sw128(sa + (g * p.BH + dhi) * sp.row_bytes);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const uint32_t accum = (first && k == 0) ? 0u : 1u;
-                                if (TF32)
-                                    umma_tf32_pair(d_tmem + g * kSlabN, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-                                else
-                                    umma_bf16_pair(d_tmem + g * kSlabN, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint32_t accum = k == 0 ? first : 1u;
+                                    if (TF32)
+                                        umma_tf32_pair(d_tmem + g * kSlabN, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                    else
+                                        umma_bf16_pair(d_tmem + g * kSlabN, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                }
                             }
+                            umma_commit_pair(&w_empty[ws]);
                         }
-                        first = false;
-                        umma_commit_pair(&w_empty[ws]);
+                        __syncwarp();
                         if (++ws == kSlabWStages) ws = 0, wphase ^= 1;
                     }
-                    umma_commit_pair(&s_empty[ss]);
+                    if (elect_one_sync()) umma_commit_pair(&s_empty[ss]);
+                    __syncwarp();
                     if (++ss == kSlabStages) ss = 0, sphase ^= 1;
                 }
-                umma_commit_pair(&tfull[acc]);
+                if (elect_one_sync()) umma_commit_pair(&tfull[acc]);
+                __syncwarp();
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1;
             }
@@ -215,6 +222,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                     tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * kSlabG + g) * kSlabN;
                 float4 rpre[8];
                 auto prefetch_resid = [&](int c_next) {
+                    if (p.resid16) {  // (16-bit residual stream: four 16-byte loads of 8 channels, as in conv_tc.cu)
+                        const __nv_bfloat16* rp =
+                            reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix0 * p.ld_resid + n_tile * kSlabN + c_next;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int r = it * 8 + sub_r8;
+                            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                            if (valid) t = __ldg(reinterpret_cast<const uint4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c8);
+                            rpre[it] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
+                        }
+                        return;
+                    }
                     const float* rp = p.resid + pix0 * p.ld_resid + n_tile * kSlabN + c_next;
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
@@ -231,10 +250,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                     tmem_ld_32x32b_x32(taddr + c, v);
                     const int col0 = n_tile * kSlabN + c;
                     if (p.resid) {
+                        if (p.resid16) {
 #pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int r = it * 4 + sub_r4;
-                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = rpre[it];
+                            for (int it = 0; it < 4; ++it) {
+                                const int r = it * 8 + sub_r8;
+                                float4 a, b;
+                                unpack_op16x8(make_uint4(__float_as_uint(rpre[it].x), __float_as_uint(rpre[it].y),
+                                                         __float_as_uint(rpre[it].z), __float_as_uint(rpre[it].w)),
+                                              p.f16, a, b);
+                                *reinterpret_cast<float4*>(stg + r * 32 + (((2 * sub_c8) ^ (r & 7)) << 2)) = a;
+                                *reinterpret_cast<float4*>(stg + r * 32 + (((2 * sub_c8 + 1) ^ (r & 7)) << 2)) = b;
+                            }
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int r = it * 4 + sub_r4;
+                                *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = rpre[it];
+                            }
                         }
                         if (c + 32 * (kEpiWarps / 4) < kSlabN) prefetch_resid(c + 32 * (kEpiWarps / 4));
                         __syncwarp();
@@ -454,6 +486,7 @@ int launch_conv_slab(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p, int c
     sp.steps = step_table(steps, n, ctx->device, stream, &rc);
     if (rc != NLC_OK) return rc;
     sp.nstep = n;
+    sp.nstep3 = 3 * (cin / chunk);
     sp.k = p;
 
     static PerDeviceFlag configured[2];

@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0 && rank == 0) {  // the pair's leader issues for both CTAs
+        // The whole warp walks the pipeline (waits, stage / accumulator bookkeeping) in uniform control flow and one
+        // elected lane issues the tcgen05 instructions (see elect_one_sync); the pair's leader CTA issues for both CTAs.
+        if (rank == 0) {
             // operand format bits: tf32, or for the 16-bit modes bf16 / fp16 (same kind::f16 instruction)
             const uint32_t idesc = umma_idesc(TF32 ? 2 : (p.f16 ? 0 : 1), CTA2 ? 2 * kBlockM : kBlockM, BLOCK_N);
             int stage = 0;
@@ -171,14 +173,17 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                         const uint64_t ahi = umma_desc_sw128(sa), bhi = umma_desc_sw128(sa + kAStageBytes);
                         const uint64_t alo = umma_desc_sw128(sa + Cfg::kLoadBytes);
                         const uint64_t blo = umma_desc_sw128(sa + Cfg::kLoadBytes + kAStageBytes);
+                        if (elect_one_sync()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, k != 0);
+                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, alo + 2 * k, bhi + 2 * k, idesc, k != 0);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1);
+                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ahi + 2 * k, blo + 2 * k, idesc, 1);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
-                        umma_commit(&empty[stage]);
-                        umma_commit(&tfull[acc]);
+                            for (int k = 0; k < 4; ++k) umma_tf32(d_tmem, ahi + 2 * k, bhi + 2 * k, idesc, 1);
+                            umma_commit(&empty[stage]);
+                            umma_commit(&tfull[acc]);
+                        }
+                        __syncwarp();
                         if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1;
@@ -188,40 +193,46 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     }
                 }
             } else {
-            for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
-                mbar_wait(&tempty[acc], acc_phase ^ 1);
-                tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kc = 0; kc < p.total_chunks; ++kc) {
-                    mbar_wait(&full[stage], phase);
+                for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+                    mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after_sync();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-                    const uint64_t adesc = umma_desc_sw128(sa);
-                    const uint64_t bdesc = umma_desc_sw128(sa + kAStageBytes);
+                    const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                    for (int kc = 0; kc < p.total_chunks; ++kc) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after_sync();
+                        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+                        const uint64_t adesc = umma_desc_sw128(sa);
+                        const uint64_t bdesc = umma_desc_sw128(sa + kAStageBytes);
+                        if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 4 x 32 B K-steps inside the 128 B swizzle row
-                        if (CTA2) {
-                            if (TF32)
-                                umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-                            else
-                                umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-                        } else if (TF32) {
-                            umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
-                        } else {
-                            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                            for (int k = 0; k < 4; ++k) {  // 4 x 32 B K-steps inside the 128 B swizzle row
+                                if (CTA2) {
+                                    if (TF32)
+                                        umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                    else
+                                        umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                } else if (TF32) {
+                                    umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                } else {
+                                    umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                }
+                            }
+                            // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+                            if (CTA2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+                        }
+                        __syncwarp();
+                        if (++stage == kStages) {
+                            stage = 0;
+                            phase ^= 1;
                         }
                     }
-                    // smem slot reusable (in both CTAs of a pair) once these MMAs retire
-                    if (CTA2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1;
+                    if (elect_one_sync()) {  // accumulator -> epilogue(s)
+                        if (CTA2) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);
                     }
+                    __syncwarp();
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
                 }
-                if (CTA2) umma_commit_pair(&tfull[acc]); else umma_commit(&tfull[acc]);  // accumulator -> epilogue(s)
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
-            }
             }
         }
     } else if (!X3 && warp == 2 + kEpiWarps) {
@@ -342,9 +353,23 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 
             // Residual rows of the chunk about to be processed are fetched one chunk ahead (mode 0): the first chunk's
             // loads are issued before the accumulator wait, every later chunk's while the previous one is being stored.
+            // (a 16-bit residual - nlc_conv_desc.resid_is_op - comes as four 16-byte loads of 8 channels per lane, 8 rows x 4
+            // chunks per instruction, instead of eight fp32 ones)
             float4 rpre[8];
             const bool pre = p.resid != nullptr && p.resid_mode == 0;
+            const __nv_bfloat16* resid16 = reinterpret_cast<const __nv_bfloat16*>(p.resid);
             auto prefetch_resid = [&](int c_next) {
+                if (p.resid16) {
+                    const __nv_bfloat16* rp = resid16 + pix0 * p.ld_resid + n_tile * BLOCK_N + c_next;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = it * 8 + sub_r8;
+                        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                        if ((vmask >> r) & 1) t = __ldg(reinterpret_cast<const uint4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c8);
+                        rpre[it] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
+                    }
+                    return;
+                }
                 const float* rp = p.resid + pix0 * p.ld_resid + n_tile * BLOCK_N + c_next;
 #pragma unroll
                 for (int it = 0; it < 8; ++it) {
@@ -395,12 +420,53 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     // (one loop per mode, so that the eight loads of a lane stay back to back: with the mode test inside
                     // the loop the compiler serialised them and the residual layers lost 25 %)
                     if (p.resid_mode == 0) {
+                        if (p.resid16) {
 #pragma unroll
-                        for (int it = 0; it < 8; ++it) {
-                            const int r = it * 4 + sub_r4;
-                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = rpre[it];
+                            for (int it = 0; it < 4; ++it) {
+                                const int r = it * 8 + sub_r8;
+                                float4 a, b;
+                                unpack_op16x8(make_uint4(__float_as_uint(rpre[it].x), __float_as_uint(rpre[it].y),
+                                                         __float_as_uint(rpre[it].z), __float_as_uint(rpre[it].w)),
+                                              p.f16, a, b);
+                                *reinterpret_cast<float4*>(stg + r * 32 + (((2 * sub_c8) ^ (r & 7)) << 2)) = a;
+                                *reinterpret_cast<float4*>(stg + r * 32 + (((2 * sub_c8 + 1) ^ (r & 7)) << 2)) = b;
+                            }
+                        } else {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                const int r = it * 4 + sub_r4;
+                                *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = rpre[it];
+                            }
                         }
                         if (c + 32 * (kEpiWarps / 4) < BLOCK_N) prefetch_resid(c + 32 * (kEpiWarps / 4));
+                    } else if (p.resid16) {
+                        // resampled skip path on a 16-bit residual: 8-byte loads of 4 channels (mode 1: the half-resolution
+                        // pixel; mode 2: the 2x2 window of the double-resolution tensor, summed in fp32, then * 0.25)
+#pragma unroll 2
+                        for (int it = 0; it < 8; ++it) {
+                            const int r = it * 4 + sub_r4;
+                            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if ((vmask >> r) & 1) {
+                                const size_t q = pix0 + r;
+                                const size_t wo = q & (static_cast<size_t>(p.Wo) - 1);
+                                const size_t ho = (q >> p.log2_wo) & (static_cast<size_t>(p.Ho) - 1);
+                                const size_t nn = q >> (p.log2_wo + p.log2_ho);
+                                if (p.resid_mode == 1) {
+                                    const size_t src = (nn * (p.Ho >> 1) + (ho >> 1)) * (p.Wo >> 1) + (wo >> 1);
+                                    t = unpack_op16x4(__ldg(reinterpret_cast<const uint2*>(resid16 + src * p.ld_resid + col0) + sub_c4), p.f16);
+                                } else {
+                                    const size_t w2 = 2 * static_cast<size_t>(p.Wo);
+                                    const __nv_bfloat16* s0 = resid16 + ((nn * 2 * p.Ho + 2 * ho) * w2 + 2 * wo) * p.ld_resid + col0;
+                                    const float4 a = unpack_op16x4(__ldg(reinterpret_cast<const uint2*>(s0) + sub_c4), p.f16);
+                                    const float4 b = unpack_op16x4(__ldg(reinterpret_cast<const uint2*>(s0 + p.ld_resid) + sub_c4), p.f16);
+                                    const float4 d = unpack_op16x4(__ldg(reinterpret_cast<const uint2*>(s0 + w2 * p.ld_resid) + sub_c4), p.f16);
+                                    const float4 e = unpack_op16x4(__ldg(reinterpret_cast<const uint2*>(s0 + (w2 + 1) * p.ld_resid) + sub_c4), p.f16);
+                                    t = make_float4(((a.x + b.x) + (d.x + e.x)) * 0.25f, ((a.y + b.y) + (d.y + e.y)) * 0.25f,
+                                                    ((a.z + b.z) + (d.z + e.z)) * 0.25f, ((a.w + b.w) + (d.w + e.w)) * 0.25f);
+                                }
+                            }
+                            *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = t;
+                        }
                     } else if (p.resid_mode == 1) {
                         // resampled skip path: the residual lives at half resolution (nearest x2)
 #pragma unroll
@@ -598,7 +664,10 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     NLC_REQUIRE(d->nsrc >= 1 && d->nsrc <= NLC_MAX_SRC, "nlc_conv_tc: nsrc %d out of range", d->nsrc);
     NLC_REQUIRE(d->nseg >= 1 && d->nseg <= NLC_MAX_SEG, "nlc_conv_tc: nseg %d out of range", d->nseg);
     NLC_REQUIRE(d->stride == 1 || d->stride == 2, "nlc_conv_tc: stride %d unsupported", d->stride);
-    NLC_REQUIRE(is_pow2(d->Ho) && is_pow2(d->Wo), "nlc_conv_tc: output %dx%d must be powers of two", d->Ho, d->Wo);
+    // (rows of >= 128 pixels tile as BH = 1: Ho is then a plain count - e.g. the three 64-channel heads of a 192-channel
+    // attention block in the unfused path - and only the modes that index pixels by shifts need a power of two)
+    NLC_REQUIRE(is_pow2(d->Wo) && (is_pow2(d->Ho) || (d->Wo >= kBlockM && !d->out_up && d->resid_mode == 0)),
+                "nlc_conv_tc: output %dx%d must be powers of two", d->Ho, d->Wo);
     NLC_REQUIRE(d->B >= 1 && d->Cout % 64 == 0, "nlc_conv_tc: Cout %d must be a multiple of 64", d->Cout);
     NLC_REQUIRE(d->out_f32 || d->out_op, "nlc_conv_tc: no output requested");
     NLC_REQUIRE(!d->out_f32 || (d->ld_out_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(d->out_f32) & 15) == 0),
@@ -607,6 +676,8 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
                 "nlc_conv_tc: out_op must be 16-byte aligned");
     NLC_REQUIRE(!d->resid || (d->ld_resid % 4 == 0 && (reinterpret_cast<uintptr_t>(d->resid) & 15) == 0),
                 "nlc_conv_tc: resid must be 16-byte aligned with ld %% 4 == 0");
+    NLC_REQUIRE(!d->resid_is_op || (d->resid && dtype_is16(d->dtype) && d->ld_resid % 8 == 0),
+                "nlc_conv_tc: resid_is_op needs a residual, a 16-bit operand mode and ld_resid %% 8 == 0");
     NLC_REQUIRE(!d->rowvec || (d->ld_rowvec % 4 == 0 && (reinterpret_cast<uintptr_t>(d->rowvec) & 15) == 0),
                 "nlc_conv_tc: rowvec must be 16-byte aligned with ld %% 4 == 0");
     NLC_REQUIRE(!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0, "nlc_conv_tc: bias must be 16-byte aligned");
@@ -747,7 +818,8 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     for (p.log2_wo = 0; (1 << p.log2_wo) < d->Wo; ++p.log2_wo) {}
     for (p.log2_ho = 0; (1 << p.log2_ho) < d->Ho; ++p.log2_ho) {}
     p.bias = d->bias, p.rowvec = d->rowvec, p.ld_rowvec = d->ld_rowvec;
-    p.resid = d->resid, p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
+    p.resid = static_cast<const float*>(d->resid), p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
+    p.resid16 = d->resid_is_op != 0;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;
 
     if (slab) return launch_conv_slab(ctx, d, p, chunk, tf32, stream);

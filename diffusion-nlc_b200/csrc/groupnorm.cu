@@ -214,22 +214,8 @@ __device__ __forceinline__ void gn_act8(const float4 v0, const float4 v1, const 
 constexpr int kGnUnrollMax = 8;
 // X16: the input is a 16-bit tensor in the operand dtype (the activation between a ResBlock's two convolutions, which in the
 // 16-bit modes is written by the first conv's epilogue in the operand dtype only, its statistics coming from the fp32
-// accumulators): 16-byte loads of 8 channels instead of two 16-byte fp32 loads (MODE 0 only).
-__device__ __forceinline__ void unpack_op16x8(uint4 u, int f16, float4& a, float4& b) {
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    float f[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (f16) {
-            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
-            f[2 * k] = t.x, f[2 * k + 1] = t.y;
-        } else {
-            f[2 * k] = __uint_as_float(w[k] << 16), f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
-        }
-    }
-    a = make_float4(f[0], f[1], f[2], f[3]), b = make_float4(f[4], f[5], f[6], f[7]);
-}
-
+// accumulators; in the 16-bit-activation plans every GroupNorm input at a level with >= 128 pixels): 16-byte loads of 8
+// channels instead of two 16-byte fp32 loads.
 template <bool TF32, int MODE, bool X16 = false>
 __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
     gn_apply_kernel(const float* __restrict__ x, int ld_x, int H, int W, int C, int groups,
@@ -289,9 +275,17 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                     const float* xp = x + (img_in + static_cast<size_t>(2 * ho) * W + 2 * wo) * ld_x + c;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const float* xq = xp + (static_cast<size_t>(q >> 1) * W + (q & 1)) * ld_x;
-                        v[u][2 * q] = __ldg(reinterpret_cast<const float4*>(xq));
-                        v[u][2 * q + 1] = __ldg(reinterpret_cast<const float4*>(xq + 4));
+                        if (X16) {
+                            const __nv_bfloat16* xq = reinterpret_cast<const __nv_bfloat16*>(x) +
+                                (img_in + static_cast<size_t>(2 * ho + (q >> 1)) * W + 2 * wo + (q & 1)) * ld_x + c;
+                            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xq));
+                            v[u][q] = make_float4(__uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z),
+                                                  __uint_as_float(raw.w));
+                        } else {
+                            const float* xq = xp + (static_cast<size_t>(q >> 1) * W + (q & 1)) * ld_x;
+                            v[u][2 * q] = __ldg(reinterpret_cast<const float4*>(xq));
+                            v[u][2 * q + 1] = __ldg(reinterpret_cast<const float4*>(xq + 4));
+                        }
                     }
                 } else if (X16) {
                     const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + (img_in + pix) * ld_x + c;
@@ -316,7 +310,16 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                 if (MODE == 2) {
                     float t[4][8];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) gn_act8(v[u][2 * q], v[u][2 * q + 1], ca + c, cb + c, do_silu, t[q]);
+                    for (int q = 0; q < 4; ++q) {
+                        float4 lo, hi;
+                        if (X16)
+                            unpack_op16x8(make_uint4(__float_as_uint(v[u][q].x), __float_as_uint(v[u][q].y),
+                                                     __float_as_uint(v[u][q].z), __float_as_uint(v[u][q].w)),
+                                          rnd, lo, hi);
+                        else
+                            lo = v[u][2 * q], hi = v[u][2 * q + 1];
+                        gn_act8(lo, hi, ca + c, cb + c, do_silu, t[q]);
+                    }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[k] = ((t[0][k] + t[1][k]) + (t[2][k] + t[3][k])) * 0.25f;
                     gn_store8<TF32>(y, (static_cast<size_t>(n) * npix + pix) * ld_y + c, f, rnd);
@@ -342,6 +345,121 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
             if (cc[u] >= C) cc[u] -= C, ++pp[u];
         }
     }
+}
+
+// ---------------------------------------------------------------- apply, 16-bit output, same resolution: the lean kernel
+// ncu on the generic kernel above (16-bit input, 64x64x128, batch 256; profiles/r02j_ncu_gn.md): 168 warp instructions per
+// 8-channel item - per-item index arithmetic, coefficient loads from shared memory, predication of eight unrolled items - at
+// 25 % occupancy: issue slots 57 % busy, no eligible warp 43 % of the cycles, DRAM at 42 % of peak.  Here a thread owns ONE
+// 8-channel block for its whole pixel range, so the 16 affine coefficients (statistics, gamma / beta, optional per-sample
+// scale / shift, and for SiLU the pre-multiplied -log2(e) copies) live in registers, a pixel step is one pointer
+// increment, and U loads are in flight per thread: ~65 instructions per item (48 of them the SiLU), 4 CTAs per SM.
+// grid (chunks, B), block = C/8 * rows threads (rows = 256 / (C/8) pixels per pass).
+template <bool X16, bool SILU, int U>
+__global__ void __launch_bounds__(256, 4)
+    gn_apply_lean_kernel(const void* __restrict__ x_, int ld_x, int HW, int C, int groups, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ scale, const float* __restrict__ shift,
+                         int ld_ss, const float* __restrict__ mr, __nv_bfloat16* __restrict__ y, int ld_y,
+                         int pix_per_chunk, int f16) {
+    const int C8 = C >> 3;
+    const int n = blockIdx.y;
+    const int cblk = static_cast<int>(threadIdx.x) % C8, prow = static_cast<int>(threadIdx.x) / C8;
+    const int rows = static_cast<int>(blockDim.x) / C8;
+    const int c0 = cblk << 3;
+    const int cpg = C / groups;
+    float a[8], b[8], a2[8], b2[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k, g = c / cpg;
+        const float mean = __ldg(mr + (n * groups + g) * 2), rstd = __ldg(mr + (n * groups + g) * 2 + 1);
+        float ak = rstd * (gamma ? __ldg(gamma + c) : 1.f);
+        float bk = (beta ? __ldg(beta + c) : 0.f) - mean * ak;
+        if (scale) {
+            const float sc = 1.f + __ldg(scale + static_cast<size_t>(n) * ld_ss + c);
+            ak *= sc;
+            bk = bk * sc + __ldg(shift + static_cast<size_t>(n) * ld_ss + c);
+        }
+        a[k] = ak, b[k] = bk;
+        a2[k] = ak * -1.4426950408889634f, b2[k] = bk * -1.4426950408889634f;  // exp(-v) = 2^(x a2 + b2)
+    }
+    const int p0 = blockIdx.x * pix_per_chunk;
+    int p1 = p0 + pix_per_chunk;
+    if (p1 > HW) p1 = HW;
+    const size_t img = static_cast<size_t>(n) * HW;
+    const size_t step_x = static_cast<size_t>(rows) * ld_x, step_y = static_cast<size_t>(rows) * ld_y;
+    const __nv_bfloat16* x16 = static_cast<const __nv_bfloat16*>(x_) + (img + p0 + prow) * ld_x + c0;
+    const float* x32 = static_cast<const float*>(x_) + (img + p0 + prow) * ld_x + c0;
+    __nv_bfloat16* yp = y + (img + p0 + prow) * ld_y + c0;
+    for (int p = p0 + prow; p < p1; p += rows * U) {
+        uint4 raw[U][X16 ? 1 : 2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p + u * rows < p1) {
+                if (X16) {
+                    raw[u][0] = __ldg(reinterpret_cast<const uint4*>(x16 + u * step_x));
+                } else {
+                    raw[u][0] = __ldg(reinterpret_cast<const uint4*>(x32 + u * step_x));
+                    raw[u][X16 ? 0 : 1] = __ldg(reinterpret_cast<const uint4*>(x32 + u * step_x) + 1);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p + u * rows < p1) {
+                float v[8];
+                if (X16) {
+                    float4 lo, hi;
+                    unpack_op16x8(raw[u][0], f16, lo, hi);
+                    v[0] = lo.x, v[1] = lo.y, v[2] = lo.z, v[3] = lo.w, v[4] = hi.x, v[5] = hi.y, v[6] = hi.z, v[7] = hi.w;
+                } else {
+                    const uint4 q0 = raw[u][0], q1 = raw[u][X16 ? 0 : 1];
+                    v[0] = __uint_as_float(q0.x), v[1] = __uint_as_float(q0.y), v[2] = __uint_as_float(q0.z);
+                    v[3] = __uint_as_float(q0.w), v[4] = __uint_as_float(q1.x), v[5] = __uint_as_float(q1.y);
+                    v[6] = __uint_as_float(q1.z), v[7] = __uint_as_float(q1.w);
+                }
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    f[k] = fmaf(v[k], a[k], b[k]);
+                    if (SILU) f[k] = __fdividef(f[k], 1.0f + fast_exp2(fmaf(v[k], a2[k], b2[k])));
+                }
+                *reinterpret_cast<uint4*>(yp + u * step_y) =
+                    make_uint4(pack_op16x2(f[0], f[1], f16), pack_op16x2(f[2], f[3], f16), pack_op16x2(f[4], f[5], f16),
+                               pack_op16x2(f[6], f[7], f16));
+            }
+        }
+        x16 += U * step_x, x32 += U * step_x, yp += U * step_y;
+    }
+}
+
+// (returns false when the shape is not served: more than 256 channel blocks, i.e. C > 2048)
+static bool launch_apply_lean(const void* x, int x_is_op, int ld_x, int B, int HW, int C, int groups, const float* gamma,
+                              const float* beta, const float* scale, const float* shift, int ld_ss, int do_silu,
+                              const float* mr, void* y, int ld_y, int sm_count, int f16, cudaStream_t stream) {
+    constexpr int U = 4;
+    const int C8 = C / 8;
+    if (C8 > 256) return false;
+    const int rows = 256 / C8;
+    const int threads = rows * C8;
+    long long chunks = (16LL * sm_count + B - 1) / B;
+    const long long max_chunks = (HW + rows * U - 1) / (rows * U);
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    int per = static_cast<int>((HW + chunks - 1) / chunks);
+    per = (per + rows - 1) / rows * rows;
+    chunks = (HW + per - 1) / per;
+    const dim3 grid(static_cast<unsigned>(chunks), B);
+    __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y);
+#define NLC_GN_LEAN(X, S)                                                                                              \
+    gn_apply_lean_kernel<X, S, U><<<grid, threads, 0, stream>>>(x, ld_x, HW, C, groups, gamma, beta, scale, shift, ld_ss, mr, yo, \
+                                                                ld_y, per, f16)
+    if (x_is_op) {
+        if (do_silu) NLC_GN_LEAN(true, true); else NLC_GN_LEAN(true, false);
+    } else {
+        if (do_silu) NLC_GN_LEAN(false, true); else NLC_GN_LEAN(false, false);
+    }
+#undef NLC_GN_LEAN
+    return true;
 }
 
 // ---------------------------------------------------------------- small images: statistics + apply in one kernel
@@ -469,8 +587,8 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const void* x_, int x_is_op, int ld_x
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const float* x = static_cast<const float*>(x_);
     NLC_REQUIRE(ctx && x && y_op && workspace, "nlc_groupnorm: null argument");
-    NLC_REQUIRE(!x_is_op || (dtype_is16(op_dtype) && stats && resample == 0 && ld_x % 8 == 0),
-                "nlc_groupnorm: an operand-dtype input needs a 16-bit mode, conv-epilogue statistics and no resampling");
+    NLC_REQUIRE(!x_is_op || (dtype_is16(op_dtype) && stats && ld_x % 8 == 0),
+                "nlc_groupnorm: an operand-dtype input needs a 16-bit mode and conv-epilogue statistics");
     NLC_REQUIRE(groups >= 1 && groups <= 64 && C % groups == 0 && (C / groups) % 4 == 0 && C % 8 == 0,
                 "nlc_groupnorm: C=%d groups=%d unsupported (channels per group must be a multiple of 4)", C, groups);
     NLC_REQUIRE(ld_x % 4 == 0 && ld_y % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -524,9 +642,20 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const void* x_, int x_is_op, int ld_x
         if (resample == 1) NLC_GN_APPLY(true, 1);
         NLC_GN_APPLY(true, 2);
     }
-    if (x_is_op)
-        return launch_apply<false, 0, true>(x, ld_x, B, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y_op,
-                                            ld_y, ctx->sm_count, rnd, stream);
+    if (resample == 0 && launch_apply_lean(x, x_is_op, ld_x, B, HW, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr,
+                                           y_op, ld_y, ctx->sm_count, rnd, stream)) {
+        NLC_CHECK_LAUNCH();
+        return NLC_OK;
+    }
+#define NLC_GN_APPLY16(M)                                                                                                \
+    return launch_apply<false, M, true>(x, ld_x, B, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y_op, ld_y, \
+                                        ctx->sm_count, rnd, stream)
+    if (x_is_op) {
+        if (resample == 0) NLC_GN_APPLY16(0);
+        if (resample == 1) NLC_GN_APPLY16(1);
+        NLC_GN_APPLY16(2);
+    }
+#undef NLC_GN_APPLY16
     if (resample == 0) NLC_GN_APPLY(false, 0);
     if (resample == 1) NLC_GN_APPLY(false, 1);
     NLC_GN_APPLY(false, 2);

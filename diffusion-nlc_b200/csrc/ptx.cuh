@@ -61,6 +61,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One lane of the (converged) warp, the same one every time (PTX: the election is deterministic for a given member mask).
+// tcgen05.mma / tcgen05.commit execute once per warp on the uniform datapath: issued under elect.sync from UNIFORM control
+// flow their operands stay in uniform registers and the instructions go out back to back; issued from a `lane == 0` branch
+// that encloses the whole pipeline loop, every operand is "divergent" to the compiler and each MMA costs a ~17-instruction
+// elect / broadcast / retry sequence (profiles/r02k_ncu_epi_notes.md: the issuing thread, not the tensor pipe, bounded the
+// N = 128 tiles).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -277,6 +295,19 @@ __device__ __forceinline__ uint32_t pack_op16x2(float a, float b, int f16) {
         return *reinterpret_cast<uint32_t*>(&t);
     }
     return pack_bf16x2(a, b);
+}
+// ... and back: one packed 16-bit pair -> two floats; four pairs (8 channels, one 16-byte load) -> two float4.
+__device__ __forceinline__ float2 unpack_op16x2(uint32_t w, int f16) {
+    if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ float4 unpack_op16x4(uint2 u, int f16) {
+    const float2 a = unpack_op16x2(u.x, f16), b = unpack_op16x2(u.y, f16);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void unpack_op16x8(uint4 u, int f16, float4& a, float4& b) {
+    a = unpack_op16x4(make_uint2(u.x, u.y), f16);
+    b = unpack_op16x4(make_uint2(u.z, u.w), f16);
 }
 // fp32 -> tf32 (round to nearest, ties away), returned as fp32 bits with the low 13 mantissa bits cleared.
 __device__ __forceinline__ float round_tf32(float x) {

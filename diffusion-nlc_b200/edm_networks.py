@@ -102,12 +102,12 @@ def _emit_block(pc, w, x, dest, emb=None):
     skip_src = x.op
     if not (w.up or w.down):
         a0 = eng.act_op("ub.a0", B, H, W, w.cin)
-        emit_groupnorm(pc, x.f32, w.n0w, w.n0b, _groups(w.cin), w.eps, a0, silu=True)
+        emit_groupnorm(pc, x.res, w.n0w, w.n0b, _groups(w.cin), w.eps, a0, silu=True)
     else:
         # Conv2d(up/down) with the [1,1] filter (src/edm_networks.py:85-93): nearest x2 / 2x2 average of the
         # activated tensor, written directly by the GroupNorm apply pass; the skip branch resamples x itself
         mode = 1 if w.up else 2
-        src32 = x.f32
+        src32 = x.res
         up_low = w.up and w.with_emb and upsample_conv_eligible(H, W)
         if up_low:  # the activated tensor stays at the low resolution; conv0 computes conv(upsample(a0)) from it
             a0 = eng.act_op("ub.a0", B, H, W, w.cin)
@@ -119,7 +119,10 @@ def _emit_block(pc, w, x, dest, emb=None):
         skip_src = None
         if w.fused_skip:  # (a weight-less skip reads x at its own resolution in the second conv's epilogue instead)
             xs = eng.act_op("ub.xs", B, H, W, w.cin)
-            pc.add(lambda: ops.resample(src32, mode, None, xs, dt), "resample")
+            if src32.dtype == torch.float32:
+                pc.add(lambda: ops.resample(src32, mode, None, xs, dt), "resample")
+            else:  # 16-bit residual stream
+                pc.add(lambda: ops.resample_op(src32, mode, xs, dt), "resample")
             skip_src = xs
     rowvec = scale = shift = None
     if emb is not None and w.with_emb:
@@ -130,7 +133,7 @@ def _emit_block(pc, w, x, dest, emb=None):
             rowvec = emb[:, w.emb_off:w.emb_off + w.cout]
     res_dest = dest
     if w.attn:
-        res_dest = Feat(f32=eng.act_f32("ub.y", B, H, W, w.cout))
+        res_dest = eng.stream_feat("ub.y", B, H, W, w.cout)
     if w.with_emb:
         h = eng.act_h("ub.h", B, H, W, w.cout)
         if (w.up or w.down) and up_low:
@@ -146,18 +149,18 @@ def _emit_block(pc, w, x, dest, emb=None):
         assert skip_src is not None, "block with a 1x1 skip needs the operand copy of its input"
         emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, extra_src=skip_src, out_scale=w.skip_scale)
     else:
-        emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, resid=x.f32, out_scale=w.skip_scale, resid_mode=w.resid_mode)
+        emit_conv3x3(pc, a1, w.w1, w.b1, w.cout, res_dest, resid=x.res, out_scale=w.skip_scale, resid_mode=w.resid_mode)
     if w.attn:
         C = w.cout
         y = res_dest
         a2 = eng.act_op("ub.a2", B, H, W, C)
-        emit_groupnorm(pc, y.f32, w.n2w, w.n2b, _groups(C), w.eps, a2, silu=False)
+        emit_groupnorm(pc, y.res, w.n2w, w.n2b, _groups(C), w.eps, a2, silu=False)
         qkv = eng.act_op("ub.qkv", B, H, W, 3 * C)
         emit_conv1x1(pc, a2, w.wqkv, w.bqkv, 3 * C, Feat(op=qkv))
         o = eng.act_op("ub.o", B, H, W, C)
         dh = C // w.heads  # rows regrouped as [q | k | v] x [head][channel]; weights softmax(q . k / sqrt(dh)), :124-127
         emit_attention(pc, qkv, 0, C, 2 * C, dh if w.heads > 1 else 0, w.heads, dh, float(1.0 / math.sqrt(dh)), o)
-        emit_conv1x1(pc, o, w.wproj, w.bproj, C, dest, resid=y.f32, out_scale=w.skip_scale)
+        emit_conv1x1(pc, o, w.wproj, w.bproj, C, dest, resid=y.res, out_scale=w.skip_scale)
 
 
 class SongUNet:
@@ -286,16 +289,15 @@ class SongUNet:
         for b, k in zip(consumers, reversed(range(n_skips))):
             c_h = b.cin - skip_ch[k]
             r = skip_res[k]
-            cat[k] = (eng.named("cat32.%d" % k, (B, r, r, b.cin), f32), eng.named("cat16.%d" % k, (B, r, r, b.cin), opt),
-                      c_h)
+            cat[k] = eng.cat_buffers(k, B, r, r, b.cin) + (c_h,)
 
         def skip_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(eng.with_stats(Act(c32, c1, skip_ch[k])), Act(c16, c1, skip_ch[k]))
+            return eng.cat_view(c32, c16, c1, skip_ch[k])
 
         def head_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(eng.with_stats(Act(c32, 0, c1)), Act(c16, 0, c1))
+            return eng.cat_view(c32, c16, 0, c1)
 
         aff = P["aff"]
         enc = PlanCtx(eng, B)
@@ -310,14 +312,19 @@ class SongUNet:
         emit_conv_in(enc, x_in, lambda: in_scale if P["use_scale"][0] else None, self.cin_wp, self.cin_b,
                      self.cin_w.shape[0], d0, w_f32=self.cin_w)
         cur = d0
+        feat32 = Act(eng.named("feat", (B, skip_res[-1], skip_res[-1], skip_ch[-1]), f32))
         for k, (res, w) in enumerate(self.enc, start=1):
             dest = skip_feat(k)
+            if k == n_skips - 1 and dest.f32 is None:
+                # 16-bit residual stream at the last level: the block writes the fp32 feature tensor itself, next to the
+                # operand copy in the concat buffer
+                dest = Feat(f32=feat32, op=dest.op)
             _emit_block(enc, w, cur, dest, aff)
             cur = dest
         last_skip = cur
-        feat32 = Act(eng.named("feat", (B, skip_res[-1], skip_res[-1], skip_ch[-1]), f32))
-        src32 = last_skip.f32
-        enc.add(lambda: ops.resample(src32, 0, feat32, None, dt), "feat copy")
+        if last_skip.f32 is not feat32:
+            src32 = last_skip.f32
+            enc.add(lambda: ops.resample(src32, 0, feat32, None, dt), "feat copy")
         P["feat"] = feat32.t
 
         dec = PlanCtx(eng, B)
@@ -327,22 +334,21 @@ class SongUNet:
         for i, (res, w, is_cat) in enumerate(self.dec):
             if is_cat:
                 c32, c16, _ = cat[k]
-                x = Feat(eng.with_stats(Act(c32)), Act(c16))
+                x = eng.cat_view(c32, c16)
                 k -= 1
             else:
                 x = cur
             nxt = self.dec[i + 1] if i + 1 < len(self.dec) else None
             if nxt is None:
-                dest = Feat(f32=eng.act_f32("dec.out", B, R, R, w.cout))
+                dest = eng.stream_feat("dec.out", B, R, R, w.cout)
             elif nxt[2]:
                 dest = head_feat(k)
             else:  # next block takes this output alone (in1 after in0, or an up block)
-                dest = Feat(f32=eng.act_f32("dec.t%d" % (i % 2), B, res, res, w.cout),
-                            op=eng.act_op("dec.t%d" % (i % 2), B, res, res, w.cout))
+                dest = eng.stream_feat("dec.t%d" % (i % 2), B, res, res, w.cout, need_op=True)
             _emit_block(dec, w, x, dest, aff)
             cur = dest
         a = eng.act_op("ub.a0", B, R, R, cur.C)
-        emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, _groups(cur.C), self._OUT_EPS, a, silu=True)
+        emit_groupnorm(dec, cur.res, self.no_w, self.no_b, _groups(cur.C), self._OUT_EPS, a, silu=True)
         emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         m = max(enc._gn_ws_floats, dec._gn_ws_floats)
         enc._gn_ws_floats = dec._gn_ws_floats = m

@@ -33,6 +33,9 @@ class Feat:
     def any(self):
         return self.f32 if self.f32 is not None else self.op
 
+    # what a GroupNorm or a residual add reads: the fp32 tensor, or - 16-bit-activation plans (Engine.r16) - the operand copy
+    res = any
+
     B = property(lambda s: s.any.B)
     H = property(lambda s: s.any.H)
     W = property(lambda s: s.any.W)
@@ -59,6 +62,13 @@ class Engine:
         # NLC_H16=0|1 overrides
         h16 = os.environ.get("NLC_H16")
         self.h16 = (self.op_dtype == NLC_F16) if h16 is None else (h16 != "0" and self.op_dtype in (NLC_BF16, NLC_F16))
+        # 16-bit RESIDUAL STREAM (`stream_feat`): at the levels whose GroupNorm statistics come from the conv epilogues
+        # (>= 128 pixels per image) every activation - block outputs, skip / concat buffers, the residual operand of the
+        # second conv - exists in the operand dtype only.  The convolutions are bound by bytes and by the board power cap, not
+        # by the tensor pipe (profiles/r02h_power_probe.log): a ResBlock moves 18 instead of 26-32 bytes per element.  On in
+        # the fp16 mode (2^-11 per rounding, the same the operand copies already carry); NLC_R16=0|1 overrides.
+        r16 = os.environ.get("NLC_R16")
+        self.r16 = self.h16 and self.fuse_gn_stats and ((self.op_dtype == NLC_F16) if r16 is None else r16 != "0")
 
     # ------------------------------------------------------------------ buffers
     def plan_two_pass(self, build):
@@ -127,10 +137,38 @@ class Engine:
             return a
         return self.act_f32(tag, B, H, W, C)
 
+    def level16(self, B, H, W, C):
+        """True when the activations of this shape live in the operand dtype only (16-bit residual stream)."""
+        return self.r16 and GnStats.eligible(B, H, W, C)
+
+    def stream_feat(self, tag, B, H, W, C, need_op=False):
+        """A block output on the residual stream: fp32 scratch (+ an operand copy when a conv reads it raw), or - 16-bit
+        residual stream - one operand-dtype scratch with its GroupNorm statistics holder."""
+        if self.level16(B, H, W, C):
+            a = Act(self.scratch(tag + ".16", (B, H, W, C), self.op_torch))
+            st = self.scratch(tag + ".stats", (B * H * W // 32, C // 4, 2), torch.float32)
+            if self._sizing is None:
+                a.stats = GnStats(st)
+            return Feat(op=a)
+        return Feat(f32=self.act_f32(tag, B, H, W, C), op=self.act_op(tag + ".op", B, H, W, C) if need_op else None)
+
+    def cat_buffers(self, k, B, H, W, C):
+        """The concat buffer of skip k: (fp32, operand) named tensors; the fp32 one is None on the 16-bit residual stream."""
+        c16 = self.named("cat16.%d" % k, (B, H, W, C), self.op_torch)
+        if self.level16(B, H, W, C):
+            return None, c16
+        return self.named("cat32.%d" % k, (B, H, W, C), torch.float32), c16
+
+    def cat_view(self, c32, c16, c0=0, C=None):
+        """Feat over channels [c0, c0+C) of a concat buffer pair (statistics holder on the tensor a GroupNorm will read)."""
+        if c32 is None:
+            return Feat(op=self.with_stats(Act(c16, c0, C)))
+        return Feat(self.with_stats(Act(c32, c0, C)), Act(c16, c0, C))
+
     def with_stats(self, act):
-        """Attach the stats holder of a plan-lifetime (named) fp32 buffer to a view of it."""
+        """Attach the stats holder of a plan-lifetime (named) buffer to a view of it."""
         t = act.t
-        if self._sizing is not None or not self.fuse_gn_stats or t.dtype != torch.float32:
+        if self._sizing is not None or not self.fuse_gn_stats:
             return act
         B, H, W, C = t.shape
         if not GnStats.eligible(B, H, W, C):
@@ -192,7 +230,7 @@ def emit_groupnorm(pc, x32, gamma, beta, groups, eps, y_op, silu=True, scale=Non
     ws = pc.gn_ws(x32.B, x32.H * x32.W, x32.C, groups)
     dt = pc.eng.op_dtype
     fused = x32.stats is not None and x32.stats.covers(x32.c0, x32.C)
-    assert pc.eng._sizing is not None or x32.dtype == torch.float32 or (fused and not resample), \
+    assert pc.eng._sizing is not None or x32.dtype == torch.float32 or fused, \
         "a 16-bit GroupNorm input needs fused statistics"
     pc.add(lambda: ops.groupnorm(x32, groups, eps, gamma, beta, y_op, dt, ws(), silu=silu, scale=scale, shift=shift,
                                  use_stats=fused, resample=resample),
@@ -208,7 +246,7 @@ def h_feat(h):
 
 def _want_stats(dest, Cout):
     """True when the conv writing `dest` should also write GroupNorm partials (and records the coverage)."""
-    a = dest.f32 if dest.f32 is not None else dest.op
+    a = dest.f32 if (dest.f32 is not None and (dest.f32.stats is not None or dest.op is None)) else dest.op
     if a is None or a.stats is None or Cout % 4 != 0 or a.c0 % 4 != 0:
         return False
     a.stats.covered.append((a.c0, a.c0 + Cout))

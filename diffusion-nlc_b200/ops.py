@@ -180,6 +180,8 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         d.rowvec, d.ld_rowvec = rowvec.data_ptr(), rowvec.stride(0)
     if resid is not None:
         d.resid, d.ld_resid = resid.ptr, resid.ld
+        d.resid_is_op = 0 if resid.dtype == torch.float32 else 1  # (16-bit residual stream: the operand dtype)
+        assert not d.resid_is_op or resid.dtype == OP_DTYPES[op_dtype], "a 16-bit residual must be in the operand dtype"
         d.resid_mode = resid_mode  # 1 / 2: the residual is at half / double resolution (nearest x2 / 2x2 average)
     d.out_scale = out_scale
     if out_up is not None:  # (a, b): this launch is one phase of "nearest x2, then 3x3" computed at the low resolution

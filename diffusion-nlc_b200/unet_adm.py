@@ -83,16 +83,16 @@ def _emit_resblock(pc, w, x, dest, emb=None):
     eng = pc.eng
     dt = eng.op_dtype
     B, H, W = x.B, x.H, x.W
-    resid, resid_mode = x.f32, 0
+    resid, resid_mode = x.res, 0
     if w.updown is None:
         a1 = eng.act_op("rb.a1", B, H, W, w.cin)
-        emit_groupnorm(pc, x.f32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True)
+        emit_groupnorm(pc, x.res, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True)
     else:
         # h_upd / x_upd (src/unet_adm.py:236-243): the activated tensor is written already resampled by the
         # GroupNorm apply pass; x_upd is never materialised: the second conv's epilogue reads x at its own resolution
         # (nearest x2 / 2x2 average, nlc_conv_desc.resid_mode)
         mode = 1 if w.updown == "up" else 2
-        src32 = x.f32
+        src32 = x.res
         H, W = (2 * H, 2 * W) if mode == 1 else (H // 2, W // 2)
         a1 = eng.act_op("rb.a1r", B, H, W, w.cin)
         emit_groupnorm(pc, src32, w.n1w, w.n1b, GROUPS, GN_EPS, a1, silu=True, resample=mode)
@@ -119,7 +119,7 @@ def _emit_attnblock(pc, w, x, dest):
     eng = pc.eng
     B, H, W, C = x.B, x.H, x.W, w.C
     a = eng.act_op("at.a", B, H, W, C)
-    emit_groupnorm(pc, x.f32, w.nw, w.nb, GROUPS, GN_EPS, a, silu=False)
+    emit_groupnorm(pc, x.res, w.nw, w.nb, GROUPS, GN_EPS, a, silu=False)
     qkv = eng.act_op("at.qkv", B, H, W, 3 * C)
     emit_conv1x1(pc, a, w.wqkv, w.bqkv, 3 * C, Feat(op=qkv))
     o = eng.act_op("at.o", B, H, W, C)
@@ -128,7 +128,7 @@ def _emit_attnblock(pc, w, x, dest):
         emit_attention(pc, qkv, 0, C, 2 * C, w.dh, w.heads, w.dh, scale, o)
     else:  # legacy: [head] x [q | k | v][ch]
         emit_attention(pc, qkv, 0, w.dh, 2 * w.dh, 3 * w.dh, w.heads, w.dh, scale, o)
-    emit_conv1x1(pc, o, w.wproj, w.bproj, C, dest, resid=x.f32)
+    emit_conv1x1(pc, o, w.wproj, w.bproj, C, dest, resid=x.res)
 
 
 class UNetModel:
@@ -274,17 +274,20 @@ class UNetModel:
                     H, W = 2 * H, 2 * W
                 elif w.updown == "down":
                     H, W = H // 2, W // 2
-                out = dest if last else Feat(f32=eng.act_f32("blk.o%d" % li, B, H, W, w.cout))
+                out = dest if last else eng.stream_feat("blk.o%d" % li, B, H, W, w.cout)
                 _emit_resblock(pc, w, cur, out, emb)
             elif kind == "attn":
-                out = dest if last else Feat(f32=eng.act_f32("blk.o%d" % li, B, cur.H, cur.W, w.C))
+                out = dest if last else eng.stream_feat("blk.o%d" % li, B, cur.H, cur.W, w.C)
                 _emit_attnblock(pc, w, cur, out)
             elif kind == "down":  # Downsample(use_conv): 3x3 stride 2 pad 1
                 assert last
-                src = eng.act_op("rs.src", B, cur.H, cur.W, cur.C)
-                c32 = cur.f32
                 dt = eng.op_dtype
-                pc.add(lambda c32=c32, src=src: ops.resample(c32, 0, None, src, dt))
+                if cur.op is not None:
+                    src = cur.op
+                else:
+                    src = eng.act_op("rs.src", B, cur.H, cur.W, cur.C)
+                    c32 = cur.f32
+                    pc.add(lambda c32=c32, src=src: ops.resample(c32, 0, None, src, dt))
                 emit_conv3x3(pc, src, w[0], w[1], cur.C, dest, stride=2, pad=1)
                 out = dest
             else:  # Upsample(use_conv): nearest x2 then 3x3
@@ -292,7 +295,10 @@ class UNetModel:
                 src = eng.act_op("rs.src", B, 2 * cur.H, 2 * cur.W, cur.C)
                 c32 = cur.f32
                 dt = eng.op_dtype
-                pc.add(lambda c32=c32, src=src: ops.resample(c32, 1, None, src, dt))
+                if c32 is None:
+                    pc.add(lambda c16=cur.op, src=src: ops.resample_op(c16, 1, src, dt))
+                else:
+                    pc.add(lambda c32=c32, src=src: ops.resample(c32, 1, None, src, dt))
                 emit_conv3x3(pc, src, w[0], w[1], cur.C, dest)
                 out = dest
             cur = out
@@ -330,21 +336,20 @@ class UNetModel:
         c_h = self.mid_ch
         for ob, k in zip(self.output_blocks, reversed(range(n_skips))):
             c_skip, rk = self.skip_ch[k], res_list[k]
-            cat[k] = (eng.named("cat32.%d" % k, (B, rk, rk, c_h + c_skip), f32),
-                      eng.named("cat16.%d" % k, (B, rk, rk, c_h + c_skip), opt), c_h)
+            cat[k] = eng.cat_buffers(k, B, rk, rk, c_h + c_skip) + (c_h,)
             c_h = [l for l in ob if l[0] == "res"][-1][1].cout
 
         def skip_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(eng.with_stats(Act(c32, c1, self.skip_ch[k])), Act(c16, c1, self.skip_ch[k]))
+            return eng.cat_view(c32, c16, c1, self.skip_ch[k])
 
         def head_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(eng.with_stats(Act(c32, 0, c1)), Act(c16, 0, c1))
+            return eng.cat_view(c32, c16, 0, c1)
 
         def cat_feat(k):
             c32, c16, _ = cat[k]
-            return Feat(eng.with_stats(Act(c32)), Act(c16))
+            return eng.cat_view(c32, c16)
 
         emb = P["emb"]
         enc = PlanCtx(eng, B)
@@ -372,9 +377,14 @@ class UNetModel:
         mid = PlanCtx(eng, B)
         mid._gn_ws_floats, mid._attn_ws_bytes = enc._gn_ws_floats, enc._attn_ws_bytes
         # write the middle output into the concat head (fp32 + operand); the feature tensor is a dense copy
-        self._emit_block(mid, self.middle, cur, mid_out, emb, B)
-        src32 = mid_out.f32
-        mid.add(lambda: ops.resample(src32, 0, feat32, None, dt))
+        if mid_out.f32 is None:
+            # 16-bit residual stream at the middle resolution: the last conv writes the fp32 feature tensor itself next to
+            # the operand copy in the concat head
+            self._emit_block(mid, self.middle, cur, Feat(f32=feat32, op=mid_out.op), emb, B)
+        else:
+            self._emit_block(mid, self.middle, cur, mid_out, emb, B)
+            src32 = mid_out.f32
+            mid.add(lambda: ops.resample(src32, 0, feat32, None, dt))
         P["feat_mid"] = feat32.t
 
         dec = PlanCtx(eng, B)
@@ -386,11 +396,11 @@ class UNetModel:
             if k > 0:
                 dest = head_feat(k - 1)
             else:
-                dest = Feat(f32=eng.act_f32("up.out", B, R, R, [l for l in ob if l[0] == "res"][-1][1].cout))
+                dest = eng.stream_feat("up.out", B, R, R, [l for l in ob if l[0] == "res"][-1][1].cout)
             cur = self._emit_block(dec, ob, x, dest, emb, B)
             k -= 1
         a = eng.act_op("rb.a1", B, R, R, cur.C)
-        emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
+        emit_groupnorm(dec, cur.res, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
         emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         m = max(enc._gn_ws_floats, mid._gn_ws_floats, dec._gn_ws_floats)
         enc._gn_ws_floats = mid._gn_ws_floats = dec._gn_ws_floats = m
@@ -426,7 +436,7 @@ class UNetModel:
         P["emb_n"][0] = self.emb_enc
         run(P["enc"])
         if self.feat_layer == 0:
-            return P["feat_src"].f32.dense().contiguous()
+            return P["feat_src"].res.dense().float().contiguous()
         run(P["mid"])
         return P["feat_mid"]
 
@@ -441,7 +451,7 @@ class UNetModel:
     def forward_and_encode(self, x, t, y=None):
         out = self.forward_scaled(x, t).clone()
         P = self._plan(x.shape[0])
-        feat = P["feat_src"].f32.dense() if self.feat_layer == 0 else P["feat_mid"]
+        feat = P["feat_src"].res.dense().float() if self.feat_layer == 0 else P["feat_mid"]
         return out, feat.clone().permute(0, 3, 1, 2)
 
     def convert_to_fp16(self):

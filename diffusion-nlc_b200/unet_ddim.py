@@ -75,7 +75,7 @@ def _emit_resblock(pc, wts, x, dest, rowvec=None):
     eng = pc.eng
     B, H, W = x.B, x.H, x.W
     a1 = eng.act_op("rb.a1", B, H, W, wts.cin)
-    emit_groupnorm(pc, x.f32, wts.n1w, wts.n1b, GROUPS, GN_EPS, a1, silu=True)
+    emit_groupnorm(pc, x.res, wts.n1w, wts.n1b, GROUPS, GN_EPS, a1, silu=True)
     h = eng.act_h("rb.h", B, H, W, wts.cout)
     emit_conv3x3(pc, a1, wts.w1, wts.b1 if rowvec is None else None, wts.cout, h_feat(h), rowvec=rowvec)
     a2 = eng.act_op("rb.a2", B, H, W, wts.cout)
@@ -84,19 +84,19 @@ def _emit_resblock(pc, wts, x, dest, rowvec=None):
         assert x.op is not None, "a block with a 1x1 shortcut needs the operand copy of its input"
         emit_conv3x3(pc, a2, wts.w2, wts.b2, wts.cout, dest, extra_src=x.op)
     else:
-        emit_conv3x3(pc, a2, wts.w2, wts.b2, wts.cout, dest, resid=x.f32)
+        emit_conv3x3(pc, a2, wts.w2, wts.b2, wts.cout, dest, resid=x.res)
 
 
 def _emit_attnblock(pc, wts, x, dest):
     eng = pc.eng
     B, H, W, C = x.B, x.H, x.W, wts.C
     a = eng.act_op("at.a", B, H, W, C)
-    emit_groupnorm(pc, x.f32, wts.nw, wts.nb, GROUPS, GN_EPS, a, silu=False)
+    emit_groupnorm(pc, x.res, wts.nw, wts.nb, GROUPS, GN_EPS, a, silu=False)
     qkv = eng.act_op("at.qkv", B, H, W, 3 * C)
     emit_conv1x1(pc, a, wts.wqkv, wts.bqkv, 3 * C, Feat(op=qkv))
     o = eng.act_op("at.o", B, H, W, C)
     emit_attention(pc, qkv, 0, C, 2 * C, 0, 1, C, float(int(C) ** (-0.5)), o)
-    emit_conv1x1(pc, o, wts.wproj, wts.bproj, C, dest, resid=x.f32)
+    emit_conv1x1(pc, o, wts.wproj, wts.bproj, C, dest, resid=x.res)
 
 
 def _emit_downsample(pc, w, b, x, dest):
@@ -235,23 +235,21 @@ class UNetModel:
         for i_level in reversed(range(self.num_resolutions)):
             for i_block in range(self.num_res_blocks + 1):
                 c_skip, r = hs_shapes[k]
-                cat[k] = (eng.named("cat32.%d" % k, (B, r, r, c_h + c_skip), f32),
-                          eng.named("cat16.%d" % k, (B, r, r, c_h + c_skip), opt), c_h)
+                cat[k] = eng.cat_buffers(k, B, r, r, c_h + c_skip) + (c_h,)
                 c_h = self.up[i_level]["block"][i_block].cout
                 k -= 1
 
         def skip_feat(k):
             c32, c16, c1 = cat[k]
-            c_skip = hs_shapes[k][0]
-            return Feat(eng.with_stats(Act(c32, c1, c_skip)), Act(c16, c1, c_skip))
+            return eng.cat_view(c32, c16, c1, hs_shapes[k][0])
 
         def head_feat(k):
             c32, c16, c1 = cat[k]
-            return Feat(eng.with_stats(Act(c32, 0, c1)), Act(c16, 0, c1))
+            return eng.cat_view(c32, c16, 0, c1)
 
         def cat_feat(k):
             c32, c16, _ = cat[k]
-            return Feat(eng.with_stats(Act(c32)), Act(c16))
+            return eng.cat_view(c32, c16)
 
         # ---- encoder (shared by forward and encode)
         enc = PlanCtx(eng, B)
@@ -279,7 +277,7 @@ class UNetModel:
                 dest = skip_feat(k)
                 rv = tp[:, wts.temb_off:wts.temb_off + wts.cout]
                 if lvl["attn"]:
-                    tmp = Feat(f32=eng.act_f32("blk.out", B, res, res, wts.cout))
+                    tmp = eng.stream_feat("blk.out", B, res, res, wts.cout)
                     _emit_resblock(enc, wts, cur, tmp, rowvec=rv)
                     _emit_attnblock(enc, lvl["attn"][i_block], tmp, dest)
                 else:
@@ -293,7 +291,7 @@ class UNetModel:
                 res //= 2
         n_skips = k
         rmid = res
-        m1 = Feat(f32=eng.act_f32("mid.1", B, rmid, rmid, c_mid))
+        m1 = eng.stream_feat("mid.1", B, rmid, rmid, c_mid)
         _emit_resblock(enc, self.mid1, cur, m1, rowvec=tp[:, self.mid1.temb_off:self.mid1.temb_off + c_mid])
         feat = Feat(f32=Act(eng.named("feat", (B, rmid, rmid, c_mid), f32)))
         _emit_attnblock(enc, self.mid_attn, m1, feat)
@@ -314,12 +312,12 @@ class UNetModel:
                 last_in_level = i_block == self.num_res_blocks
                 last = last_in_level and i_level == 0
                 if last or last_in_level:
-                    dest = Feat(f32=eng.act_f32("up.out", B, res, res, wts.cout))
+                    dest = eng.stream_feat("up.out", B, res, res, wts.cout)
                 else:
                     dest = head_feat(k - 1)
                 rv = tp[:, wts.temb_off:wts.temb_off + wts.cout]
                 if lvl["attn"]:
-                    tmp = Feat(f32=eng.act_f32("blk.out", B, res, res, wts.cout))
+                    tmp = eng.stream_feat("blk.out", B, res, res, wts.cout)
                     _emit_resblock(dec, wts, x, tmp, rowvec=rv)
                     _emit_attnblock(dec, lvl["attn"][i_block], tmp, dest)
                 else:
@@ -329,20 +327,26 @@ class UNetModel:
             if lvl["up"] is not None:
                 # Upsample: nearest x2 then 3x3 conv (src/unet_ddim.py:69-74); the replicated operand is
                 # materialised once in the operand dtype
-                src32 = cur.f32
+                src32 = cur.f32  # (None on the 16-bit residual stream: the block output already is the operand)
                 if upsample_conv_eligible(res, res):
                     # ... computed at the low resolution instead: four sub-pixel phase convs (engine.emit_upsample_conv3x3)
-                    lowo = eng.act_op("up.low", B, res, res, cur.C)
-                    dec.add(lambda src32=src32, lowo=lowo: ops.resample(src32, 0, None, lowo, dt))
+                    if src32 is None:
+                        lowo = cur.op
+                    else:
+                        lowo = eng.act_op("up.low", B, res, res, cur.C)
+                        dec.add(lambda src32=src32, lowo=lowo: ops.resample(src32, 0, None, lowo, dt))
                     res *= 2
                     emit_upsample_conv3x3(dec, lowo, lvl["up_phase"], lvl["up"][1], cur.C, head_feat(k))
                 else:
                     upo = eng.act_op("up.rep", B, 2 * res, 2 * res, cur.C)
-                    dec.add(lambda src32=src32, upo=upo: ops.resample(src32, 1, None, upo, dt))
+                    if src32 is None:
+                        dec.add(lambda src=cur.op, upo=upo: ops.resample_op(src, 1, upo, dt))
+                    else:
+                        dec.add(lambda src32=src32, upo=upo: ops.resample(src32, 1, None, upo, dt))
                     res *= 2
                     emit_conv3x3(dec, upo, lvl["up"][0], lvl["up"][1], cur.C, head_feat(k))
         a = eng.act_op("rb.a1", B, R, R, cur.C)
-        emit_groupnorm(dec, cur.f32, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
+        emit_groupnorm(dec, cur.res, self.no_w, self.no_b, GROUPS, GN_EPS, a, silu=True)
         emit_conv_out(dec, a, self.cout_w, self.cout_b, self.cout_packed, P["out"])
         enc._gn_ws_floats = dec._gn_ws_floats = max(enc._gn_ws_floats, dec._gn_ws_floats)
         enc._attn_ws_bytes = dec._attn_ws_bytes = max(enc._attn_ws_bytes, dec._attn_ws_bytes)

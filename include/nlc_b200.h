@@ -98,7 +98,7 @@ typedef struct {
     const float* bias;   /* [Cout] or NULL                          */
     const float* rowvec; /* [B, ld_rowvec] per-sample add or NULL   */
     int ld_rowvec;
-    const float* resid; /* NHWC fp32 [B,Ho,Wo,ld_resid] or NULL    */
+    const void* resid;  /* NHWC fp32 [B,Ho,Wo,ld_resid] (operand dtype with resid_is_op) or NULL */
     int ld_resid;
     float out_scale;
     float* out_f32; /* NHWC fp32 or NULL                       */
@@ -121,6 +121,9 @@ typedef struct {
                            block range).  With the four phase-combined 2x2 tap sets of a 3x3 kernel this computes
                            "nearest-neighbour x2 upsample, then 3x3 conv" (src/unet_ddim.py:58-74) at the LOW
                            resolution: 16 instead of 36 multiplies per output and no replicated operand in HBM. */
+    int resid_is_op;    /* 1: `resid` points at a tensor in the 16-bit OPERAND dtype (NLC_BF16 / NLC_F16 modes only; ld_resid
+                           in elements, a multiple of 8) instead of fp32: the residual stream of the 16-bit-activation
+                           plans, read 2 instead of 4 bytes per element.  All three resid_modes. */
 } nlc_conv_desc;
 
 int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);

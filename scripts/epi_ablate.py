@@ -18,9 +18,12 @@ def run(B, H, Cin, Cout, name, **kw):
     bias = torch.randn(Cout, device=dev) if kw.get("bias") else None
     rowvec = torch.randn(B, Cout, device=dev) if kw.get("rowvec") else None
     resid = ops.Act(torch.randn(B, H, H, Cout, device=dev)) if kw.get("resid") else None
+    if kw.get("resid16"):  # 16-bit residual stream (nlc_conv_desc.resid_is_op)
+        resid = ops.Act(torch.randn(B, H, H, Cout, device=dev).to(torch.bfloat16))
     st = ops.GnStats(torch.zeros(B * H * H // 32, Cout // 4, 2, device=dev)) if kw.get("stats") else None
     o32 = ops.Act(torch.empty(B, H, H, Cout, device=dev), 0, Cout, st) if kw.get("f32", True) else None
-    o16 = ops.Act(torch.empty(B, H, H, Cout, device=dev, dtype=torch.bfloat16)) if kw.get("op") else None
+    o16 = ops.Act(torch.empty(B, H, H, Cout, device=dev, dtype=torch.bfloat16), 0, Cout, st if o32 is None else None) \
+        if kw.get("op") else None
     f = lambda: ops.conv_tc([x], ops.taps3x3(0, 0, Cin), w, Cout, B, H, H, NLC_BF16, bias=bias, rowvec=rowvec, resid=resid,
                             out_f32=o32, out_op=o16, stats=st is not None)
     for _ in range(3):
@@ -48,3 +51,5 @@ for shape in ((256, 64, 128, 128), (32, 256, 256, 256), (256, 32, 256, 256), (25
     run(*shape, "f32+bias+rowvec+stats", bias=True, rowvec=True, stats=True)
     run(*shape, "f32+bias+resid", bias=True, resid=True)
     run(*shape, "f32+op+bias+resid+stats", bias=True, resid=True, stats=True, op=True)
+    run(*shape, "op+bias+rowvec+stats", f32=False, op=True, bias=True, rowvec=True, stats=True)
+    run(*shape, "op+bias+resid16+stats", f32=False, op=True, bias=True, resid16=True, stats=True)
