@@ -41,7 +41,7 @@ class ConvDesc(C.Structure):
         ("resid", C.c_void_p), ("ld_resid", C.c_int), ("out_scale", C.c_float),
         ("out_f32", C.c_void_p), ("ld_out_f32", C.c_int), ("out_op", C.c_void_p), ("ld_out_op", C.c_int),
         ("out_head_split", C.c_int), ("stats", C.c_void_p), ("stats_nblk", C.c_int), ("resid_mode", C.c_int),
-        ("out_up", C.c_int), ("resid_is_op", C.c_int),
+        ("out_up", C.c_int), ("resid_is_op", C.c_int), ("act", C.c_int),
     ]
 
 
@@ -87,6 +87,11 @@ _SIGNATURES = {
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "nlc_resample_op": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "nlc_fid_preprocess": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "nlc_im2col_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I64, _P]),
+    "nlc_pool2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "nlc_global_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "nlc_cov_accumulate": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "nlc_attention": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P]),
     "nlc_attention_ws": (_SZ, [_I, _I, _I, _I, _I]),
     "nlc_linear": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _I, _P, _I, _P]),

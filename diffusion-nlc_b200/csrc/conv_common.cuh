@@ -42,6 +42,7 @@ struct ConvKParams {
     void* out_op;
     int ld_out_op;
     int out_head_split;
+    int act;         // 1: ReLU applied last
     int out_up;      // 0, or 1 + 2a + b: output pixel (n,ho,wo) is written at (n, 2ho+a, 2wo+b) of a [B,2Ho,2Wo,.] tensor
     int w_batched;
     int f16;         // 16-bit operands are fp16 (kind::f16 with the f16 format bits), not bf16

@@ -211,39 +211,44 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
             const int hb = s - n * sp.sb_per_img;
             const bool valid = n < p.B;
             const uint32_t vmask = valid ? 0xffffffffu : 0u;
+            // Residual rows are fetched one column chunk ahead, across the M tiles of the unit: the first chunk's loads are
+            // issued before the accumulator wait, every later one while the previous chunk is being stored (an exposed
+            // first-chunk fetch is a DRAM round trip per tile: the top epilogue stall in profiles/r02k_ncu_epi_notes.md).
+            auto pix0_of = [&](int g) -> size_t {
+                return (static_cast<size_t>(n) * p.Ho + (hb * kSlabG + g) * p.BH + bh0) * p.Wo + bw0;
+            };
+            float4 rpre[8];
+            auto prefetch_resid = [&](size_t pix_base, int c_next) {
+                if (p.resid16) {  // (16-bit residual stream: four 16-byte loads of 8 channels, as in conv_tc.cu)
+                    const __nv_bfloat16* rp =
+                        reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix_base * p.ld_resid + n_tile * kSlabN + c_next;
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const int r = it * 8 + sub_r8;
+                        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+                        if (valid) t = __ldg(reinterpret_cast<const uint4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c8);
+                        rpre[it] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
+                    }
+                    return;
+                }
+                const float* rp = p.resid + pix_base * p.ld_resid + n_tile * kSlabN + c_next;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + sub_r4;
+                    rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid)
+                        rpre[it] = __ldg(reinterpret_cast<const float4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c4);
+                }
+            };
+            if (p.resid) prefetch_resid(pix0_of(0), 32 * half);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after_sync();
 #pragma unroll 1
             for (int g = 0; g < kSlabG; ++g) {
-                const int ho0 = (hb * kSlabG + g) * p.BH + bh0;
-                const size_t pix0 = (static_cast<size_t>(n) * p.Ho + ho0) * p.Wo + bw0;
+                const size_t pix0 = pix0_of(g);
                 const size_t stat_blk = pix0 >> 5;
                 const uint32_t taddr =
                     tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * kSlabG + g) * kSlabN;
-                float4 rpre[8];
-                auto prefetch_resid = [&](int c_next) {
-                    if (p.resid16) {  // (16-bit residual stream: four 16-byte loads of 8 channels, as in conv_tc.cu)
-                        const __nv_bfloat16* rp =
-                            reinterpret_cast<const __nv_bfloat16*>(p.resid) + pix0 * p.ld_resid + n_tile * kSlabN + c_next;
-#pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const int r = it * 8 + sub_r8;
-                            uint4 t = make_uint4(0u, 0u, 0u, 0u);
-                            if (valid) t = __ldg(reinterpret_cast<const uint4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c8);
-                            rpre[it] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
-                        }
-                        return;
-                    }
-                    const float* rp = p.resid + pix0 * p.ld_resid + n_tile * kSlabN + c_next;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int r = it * 4 + sub_r4;
-                        rpre[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid)
-                            rpre[it] = __ldg(reinterpret_cast<const float4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c4);
-                    }
-                };
-                if (p.resid) prefetch_resid(32 * half);
 #pragma unroll 1
                 for (int c = 32 * half; c < kSlabN; c += 32 * (kEpiWarps / 4)) {
                     uint32_t v[32];
@@ -268,7 +273,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                                 *reinterpret_cast<float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2)) = rpre[it];
                             }
                         }
-                        if (c + 32 * (kEpiWarps / 4) < kSlabN) prefetch_resid(c + 32 * (kEpiWarps / 4));
+                        if (c + 32 * (kEpiWarps / 4) < kSlabN)
+                            prefetch_resid(pix0, c + 32 * (kEpiWarps / 4));
+                        else if (g + 1 < kSlabG)
+                            prefetch_resid(pix0_of(g + 1), 32 * half);
                         __syncwarp();
                     }
                     float f[32];
@@ -403,7 +411,7 @@ static const SlabStep* step_table(const SlabStep* steps, int n, int device, cuda
 
 bool conv_slab_eligible(const nlc_ctx* ctx, const nlc_conv_desc* d, int chunk) {
     if (!ctx->use_slab || d->dtype == NLC_F32X3 || d->stride != 1 || d->nseg < 9 || d->wbatched.ptr) return false;
-    if (d->out_up || d->out_head_split || d->resid_mode != 0) return false;
+    if (d->out_up || d->out_head_split || d->resid_mode != 0 || d->act) return false;
     if (d->Cout % kSlabN != 0 || (ctx->use_slab == 1 && d->Cout != kSlabN)) return false;
     const int W = d->Wo, H = d->Ho;
     if (W != 16 && W != 32 && W != 64) return false;

@@ -546,6 +546,10 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
                 }
+                if (p.act) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                }
                 if (p.stats && vmask == 0xffffffffu)  // (the odd tail tile of a CTA pair is entirely out of range)
                     gn_partials(f, lane, p.stats + (stat_blk * p.stats_nblk + (col0 >> 2)) * 2);
 #pragma unroll
@@ -820,6 +824,8 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.bias = d->bias, p.rowvec = d->rowvec, p.ld_rowvec = d->ld_rowvec;
     p.resid = static_cast<const float*>(d->resid), p.ld_resid = d->ld_resid, p.out_scale = d->out_scale;
     p.resid16 = d->resid_is_op != 0;
+    NLC_REQUIRE(d->act == 0 || d->act == 1, "nlc_conv_tc: act must be 0 (none) or 1 (ReLU)");
+    p.act = d->act;
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;
 
     if (slab) return launch_conv_slab(ctx, d, p, chunk, tf32, stream);

@@ -7,8 +7,8 @@ and the per-batch metrics (MSE, PSNR, SSIM, constraint residuals) are computed f
 kernels (`metrics.restoration_metrics`) instead of the reference's CPU / numpy / per-image cuDNN round trip.  Batches are
 dealt round-robin to the ranks of a sharded run (`rank`, `world`), metric means are all-reduced at the end; with one
 process the numbers are the reference's.  PNG output is kept (optional: `images_dir=None` skips it and the reference's
-resume-by-existing-files logic); FID needs InceptionV3 and is taken from `experiment.fid_fn` when the caller provides
-one, else reported as None."""
+resume-by-existing-files logic); FID statistics are accumulated on the device (nlc_b200.fid) when the experiment has been
+given a target with `fid.fid_helper`, else taken from a caller-supplied `experiment.fid_fn`, else reported as None."""
 import math
 import os
 from functools import partial
@@ -44,9 +44,27 @@ def _already_done(images_dir, rank, i, batch_size):
     return all(os.path.exists(os.path.join(images_dir, f"{rank:02}-{i:05}-{j:03}.png")) for j in range(batch_size))
 
 
-def _fid(experiment, images_dir):
-    fn = getattr(experiment, "fid_fn", None)
-    return fn(images_dir) if (fn is not None and images_dir is not None) else None
+class _Fid:
+    """FID of a driver run.  With `fid.fid_helper(experiment, fid_target, inception)` the InceptionV3 statistics are
+    accumulated on the device batch by batch from the sampler outputs (through the 8-bit image round trip the reference's
+    PNG files go through) and all-reduced over the ranks at the end; an `experiment.fid_fn` supplied by the caller instead
+    is called on `images_dir` as the reference does (src/experiments.py:220-226); without either the FID is None."""
+
+    def __init__(self, experiment, images_dir):
+        self.experiment, self.images_dir = experiment, images_dir
+        make = getattr(experiment, "fid_stats", None)
+        self.stats = make() if make is not None else None
+
+    def update(self, sample_pm1):
+        if self.stats is not None:
+            net = self.experiment.fid_inception
+            self.stats.update(net.features_of_samples(sample_pm1.to(net.device, torch.float32)))
+
+    def value(self):
+        if self.stats is not None:
+            return self.experiment.fid_of(self.stats)
+        fn = getattr(self.experiment, "fid_fn", None)
+        return fn(self.images_dir) if (fn is not None and self.images_dir is not None) else None
 
 
 class BatchStreams:
@@ -106,6 +124,7 @@ def evaluate_unconstraint(experiment, n_samples, images_dir, norm_init_noise=Fal
     streams = BatchStreams(experiment, shape, rank, world,
                            device_draws_per_batch(experiment, sampling, max_T, new_eta))
     return_lists, kept = [], []
+    fid = _Fid(experiment, images_dir)
     for i in range(rank, n_batches, world):
         if _already_done(images_dir, rank, i, batch_size):
             continue
@@ -126,10 +145,11 @@ def evaluate_unconstraint(experiment, n_samples, images_dir, norm_init_noise=Fal
         if return_log and res_pkl_path:
             import joblib
             joblib.dump(return_lists, res_pkl_path)
+        fid.update(sample)
         sample = sample.add(1).div(2).clamp(0, 1)
         _save_batch(sample, images_dir, rank, i)
         kept.append(sample)
-    log_dict = {"fid": _fid(experiment, images_dir), "samples": torch.cat(kept) if kept else None}
+    log_dict = {"fid": fid.value(), "samples": torch.cat(kept) if kept else None}
     return log_dict, return_lists
 
 
@@ -163,6 +183,7 @@ def evaluate_constraint(experiment, data_loader, Constraint, images_dir, n_sampl
     streams = None
     lists = {k: [] for k in ("mse", "psnr", "ssim", "const_f", "const_b", "const_orig")}
     full_results, return_list = [], None
+    fid = _Fid(experiment, images_dir)
     for i, (x_orig, _classes) in enumerate(data_loader):
         if i % world != rank:
             continue
@@ -206,6 +227,7 @@ def evaluate_constraint(experiment, data_loader, Constraint, images_dir, n_sampl
                 constrain_loss=constrain_loss, sigma_pred_threshold=sigma_pred_threshold, new_eta=new_eta, to_cpu=False)
         elapsed = time() - t1
         m = M.restoration_metrics(sample.to(device), x_orig, constraint=Constraint, y=y, return_image=True, ssim=True)
+        fid.update(sample)
         _save_batch(m["image"], images_dir, rank, i)
         for k in lists:
             lists[k] += m[k].cpu().tolist()
@@ -220,7 +242,7 @@ def evaluate_constraint(experiment, data_loader, Constraint, images_dir, n_sampl
                            keys=tuple(lists))
     log_dict = {"mse": means["mse"], "psner": means["psnr"], "ssim": means["ssim"], "const_f_loss": means["const_f"],
                 "const_b_loss": means["const_b"], "const_orig_loss": means["const_orig"],
-                "fid": _fid(experiment, images_dir),
+                "fid": fid.value(),
                 "full_log": {"psnr": lists["psnr"], "mse": lists["mse"], "ssim": lists["ssim"],
                              "const_forward": lists["const_f"], "const_backward": lists["const_b"],
                              "const_orig_loss": lists["const_orig"]},

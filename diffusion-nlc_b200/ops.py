@@ -161,7 +161,7 @@ def taps3x3(src, c0, nch, pad=1):
 
 
 def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, rowvec=None, resid=None,
-            out_scale=1.0, out_f32=None, out_op=None, stats=False, resid_mode=0, out_up=None):
+            out_scale=1.0, out_f32=None, out_op=None, stats=False, resid_mode=0, out_up=None, relu=False):
     """Tensor-core implicit GEMM (nlc_conv_tc). srcs: list[Act]; segs: list of (src, dh, dw, c0, nch);
     resid/out_f32/out_op: Act or None; rowvec: [B, Cout] fp32 tensor."""
     d = _lib.ConvDesc()
@@ -184,6 +184,7 @@ def conv_tc(srcs, segs, weight, Cout, B, Ho, Wo, op_dtype, stride=1, bias=None, 
         assert not d.resid_is_op or resid.dtype == OP_DTYPES[op_dtype], "a 16-bit residual must be in the operand dtype"
         d.resid_mode = resid_mode  # 1 / 2: the residual is at half / double resolution (nearest x2 / 2x2 average)
     d.out_scale = out_scale
+    d.act = 1 if relu else 0
     if out_up is not None:  # (a, b): this launch is one phase of "nearest x2, then 3x3" computed at the low resolution
         d.out_up = 1 + 2 * out_up[0] + out_up[1]
     if out_f32 is not None:
@@ -473,4 +474,41 @@ def edm_axpy(x_hat, e, den, eps_scale, mul, coef, x_next):
     B, d = x_hat.shape[0], x_hat[0].numel()
     _lib.check(_lib.lib().nlc_edm_axpy(_ctx(x_hat), _p(x_hat), _p(e), _p(den), float(eps_scale or 0.0), _p(mul),
                                        _p(coef), B, d, _p(x_next), _stream()))
+    STATS.launches += 1
+
+
+# ---------------------------------------------------------------------- FID statistics (fid.py)
+def fid_preprocess(x_nchw, from_pm1, quantize, resize, normalize, R_out, y_map, op_dtype):
+    """[B,3,H,W] fp32 -> NHWC operand matrix of `y_map` (fid._Map): PNG round trip, bilinear 299, 2x - 1 (nlc_fid_preprocess)."""
+    B, _, H, W = x_nchw.shape
+    _lib.check(_lib.lib().nlc_fid_preprocess(_ctx(x_nchw), _p(x_nchw), B, H, W, int(from_pm1), int(quantize), int(resize),
+                                             int(normalize), R_out, C.c_void_p(y_map.ptr), y_map.ld, op_dtype, _stream()))
+    STATS.launches += 1
+
+
+def im2col_nhwc(x_map, kh, kw, stride, pad, patches, op_dtype):
+    """Feature map -> zero-padded patch matrix [M_pad, K_pad] (nlc_im2col_nhwc)."""
+    _lib.check(_lib.lib().nlc_im2col_nhwc(_ctx(patches), C.c_void_p(x_map.ptr), op_dtype, x_map.ld, x_map.B, x_map.H, x_map.W,
+                                          x_map.C, kh, kw, stride[0], stride[1], pad[0], pad[1], _p(patches), patches.shape[1],
+                                          patches.shape[0], _stream()))
+    STATS.launches += 1
+
+
+def pool2d(x_map, stride, pad, mode, y_map, op_dtype):
+    """3x3 max (mode 0) / average without padding count (mode 1) pooling between feature maps (nlc_pool2d)."""
+    _lib.check(_lib.lib().nlc_pool2d(_ctx(x_map.t), C.c_void_p(x_map.ptr), op_dtype, x_map.ld, x_map.B, x_map.H, x_map.W,
+                                     x_map.C, stride, pad, mode, C.c_void_p(y_map.ptr), y_map.ld, _stream()))
+    STATS.launches += 1
+
+
+def global_avgpool(x_map, y, op_dtype):
+    _lib.check(_lib.lib().nlc_global_avgpool(_ctx(x_map.t), C.c_void_p(x_map.ptr), op_dtype, x_map.ld, x_map.B,
+                                             x_map.H * x_map.W, x_map.C, _p(y), _stream()))
+    STATS.launches += 1
+
+
+def cov_accumulate(feats, sum64, outer64):
+    """sum += sum_b f[b], outer += f^T f in fp64 (nlc_cov_accumulate)."""
+    _lib.check(_lib.lib().nlc_cov_accumulate(_ctx(feats), _p(feats), feats.shape[0], feats.shape[1], _p(sum64), _p(outer64),
+                                             _stream()))
     STATS.launches += 1

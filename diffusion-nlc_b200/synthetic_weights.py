@@ -417,3 +417,48 @@ EDM_CONFIGS = {
     "edm_tiny": dict(img_resolution=16, in_channels=3, out_channels=3, model_channels=128, channel_mult=(1, 2),
                      num_blocks=1, attn_resolutions=(8,), sigma=dict(dim=8, channels=256, n_blocks=2)),
 }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# FID InceptionV3 (pytorch_fid's pt_inception-2015-12-05 weights are a state_dict in torchvision's Inception3 layout; they
+# cannot be fetched here, so the FID tests and the oracle use this seeded stand-in with the same keys and shapes).
+def fid_inception_layers():
+    """(name, cin, cout, kh, kw) of every BasicConv2d of the FID Inception trunk (torchvision Inception3 up to Mixed_7c)."""
+    L = [("Conv2d_1a_3x3", 3, 32, 3, 3), ("Conv2d_2a_3x3", 32, 32, 3, 3), ("Conv2d_2b_3x3", 32, 64, 3, 3),
+         ("Conv2d_3b_1x1", 64, 80, 1, 1), ("Conv2d_4a_3x3", 80, 192, 3, 3)]
+    for n, cin, pf in (("Mixed_5b", 192, 32), ("Mixed_5c", 256, 64), ("Mixed_5d", 288, 64)):
+        L += [(n + ".branch1x1", cin, 64, 1, 1), (n + ".branch5x5_1", cin, 48, 1, 1), (n + ".branch5x5_2", 48, 64, 5, 5),
+              (n + ".branch3x3dbl_1", cin, 64, 1, 1), (n + ".branch3x3dbl_2", 64, 96, 3, 3),
+              (n + ".branch3x3dbl_3", 96, 96, 3, 3), (n + ".branch_pool", cin, pf, 1, 1)]
+    L += [("Mixed_6a.branch3x3", 288, 384, 3, 3), ("Mixed_6a.branch3x3dbl_1", 288, 64, 1, 1),
+          ("Mixed_6a.branch3x3dbl_2", 64, 96, 3, 3), ("Mixed_6a.branch3x3dbl_3", 96, 96, 3, 3)]
+    for n, c7 in (("Mixed_6b", 128), ("Mixed_6c", 160), ("Mixed_6d", 160), ("Mixed_6e", 192)):
+        L += [(n + ".branch1x1", 768, 192, 1, 1), (n + ".branch7x7_1", 768, c7, 1, 1), (n + ".branch7x7_2", c7, c7, 1, 7),
+              (n + ".branch7x7_3", c7, 192, 7, 1), (n + ".branch7x7dbl_1", 768, c7, 1, 1),
+              (n + ".branch7x7dbl_2", c7, c7, 7, 1), (n + ".branch7x7dbl_3", c7, c7, 1, 7),
+              (n + ".branch7x7dbl_4", c7, c7, 7, 1), (n + ".branch7x7dbl_5", c7, 192, 1, 7),
+              (n + ".branch_pool", 768, 192, 1, 1)]
+    L += [("Mixed_7a.branch3x3_1", 768, 192, 1, 1), ("Mixed_7a.branch3x3_2", 192, 320, 3, 3),
+          ("Mixed_7a.branch7x7x3_1", 768, 192, 1, 1), ("Mixed_7a.branch7x7x3_2", 192, 192, 1, 7),
+          ("Mixed_7a.branch7x7x3_3", 192, 192, 7, 1), ("Mixed_7a.branch7x7x3_4", 192, 192, 3, 3)]
+    for n, cin in (("Mixed_7b", 1280), ("Mixed_7c", 2048)):
+        L += [(n + ".branch1x1", cin, 320, 1, 1), (n + ".branch3x3_1", cin, 384, 1, 1),
+              (n + ".branch3x3_2a", 384, 384, 1, 3), (n + ".branch3x3_2b", 384, 384, 3, 1),
+              (n + ".branch3x3dbl_1", cin, 448, 1, 1), (n + ".branch3x3dbl_2", 448, 384, 3, 3),
+              (n + ".branch3x3dbl_3a", 384, 384, 1, 3), (n + ".branch3x3dbl_3b", 384, 384, 3, 1),
+              (n + ".branch_pool", cin, 192, 1, 1)]
+    return L
+
+
+def fid_inception_state_dict(seed=1):
+    """Seeded weights in the layout of pytorch_fid's FID Inception (conv.weight + bn.{weight,bias,running_mean,running_var});
+    He-scaled so that activations stay O(1) through the 94 layers, non-trivial BatchNorm statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, cin, cout, kh, kw in fid_inception_layers():
+        sd[name + ".conv.weight"] = torch.randn(cout, cin, kh, kw, generator=g) * (2.0 / (cin * kh * kw)) ** 0.5
+        sd[name + ".bn.weight"] = 1.0 + 0.2 * (torch.rand(cout, generator=g) - 0.5)
+        sd[name + ".bn.bias"] = 0.1 * torch.randn(cout, generator=g)
+        sd[name + ".bn.running_mean"] = 0.1 * torch.randn(cout, generator=g)
+        sd[name + ".bn.running_var"] = 0.5 + torch.rand(cout, generator=g)
+    return sd

@@ -124,6 +124,8 @@ typedef struct {
     int resid_is_op;    /* 1: `resid` points at a tensor in the 16-bit OPERAND dtype (NLC_BF16 / NLC_F16 modes only; ld_resid
                            in elements, a multiple of 8) instead of fp32: the residual stream of the 16-bit-activation
                            plans, read 2 instead of 4 bytes per element.  All three resid_modes. */
+    int act;            /* activation applied last (after bias / row / residual / out_scale): 0 none, 1 ReLU (the
+                           BasicConv2d blocks of the FID InceptionV3, whose BatchNorm is folded into weight and bias) */
 } nlc_conv_desc;
 
 int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream);
@@ -172,6 +174,28 @@ size_t nlc_groupnorm_ws(int B, int HW, int C, int groups);
  * src/unet_ddim.py:69-74) or 2x2 average pooled (src/unet_adm.py:134-140). mode: 0 copy, 1 up2, 2 avgpool2 */
 int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int mode, float* y_f32,
                  int ld_y_f32, void* y_op, int ld_y_op, int op_dtype, void* stream);
+
+/* ---- FID statistics on the device.  The reference goes through the third-party pytorch_fid package
+ * after writing every sample as a PNG (src/experiments.py:210-226 fid_helper -> compute_statistics_of_path /
+ * calculate_frechet_distance; image_sample.py:566,703; result_evaluater.py:24-27).  The InceptionV3 convolutions are
+ * nlc_conv_tc GEMMs over patch matrices (BatchNorm folded, ReLU = nlc_conv_desc.act); these are the pieces around them. */
+/* x [B,3,H,W] fp32 -> y NHWC [B,R_out,R_out,ld_y] operand dtype (3 channels written).  from_pm1: x is a sample in [-1,1],
+ * mapped add(1).div(2).clamp(0,1) (image_sample.py:560); quantize: the 8-bit PNG round trip (save_image: x*255+0.5, clamp,
+ * truncate; ToTensor: /255); resize: bilinear to R_out x R_out, align_corners = False (pytorch_fid InceptionV3
+ * resize_input); normalize: 2x - 1 (normalize_input). */
+int nlc_fid_preprocess(nlc_ctx* ctx, const float* x_nchw, int B, int H, int W, int from_pm1, int quantize, int resize,
+                       int normalize, int R_out, void* y_op, int ld_y, int op_dtype, void* stream);
+/* NHWC [B,H,W,ld_x] (C channels used) -> patch matrix [M_pad, K_pad], row m = (n, ho, wo), column (kh*KW + kw)*C + c; rows
+ * >= B*Ho*Wo and columns >= KH*KW*C are zero.  Ho = (H + 2 PH - KH) / SH + 1 (torch.nn.Conv2d arithmetic). */
+int nlc_im2col_nhwc(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int H, int W, int C, int KH, int KW,
+                    int SH, int SW, int PH, int PW, void* out, int K_pad, long long M_pad, void* stream);
+/* 3x3 pooling on NHWC operand tensors: mode 0 max_pool2d, 1 avg_pool2d(count_include_pad=False); stride 1|2, pad 0|1. */
+int nlc_pool2d(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int H, int W, int C, int stride, int pad,
+               int mode, void* y_op, int ld_y, void* stream);
+/* adaptive_avg_pool2d(1,1): [B, HW, ld_x] operand -> fp32 [B, C] */
+int nlc_global_avgpool(nlc_ctx* ctx, const void* x_op, int op_dtype, int ld_x, int B, int HW, int C, float* y, void* stream);
+/* FID statistics: sum[D] += sum_b f[b,:], outer[D,D] += f^T f, both fp64 (mu = sum/N, Sigma = (outer - N mu mu^T)/(N-1)) */
+int nlc_cov_accumulate(nlc_ctx* ctx, const float* feats, int B, int D, double* sum, double* outer, void* stream);
 
 /* Same resampling on a tensor that is already in the operand dtype (ADM's resblock_updown pools / upsamples the
  * activated tensor GN+SiLU(x) before the block's first conv, src/unet_adm.py:236-243). mode: 1 up2, 2 avgpool2 */

@@ -132,7 +132,10 @@ def frechet_distance(mu1, sigma1, mu2, sigma2, eps=1e-6):
     sigma1, sigma2 = np.atleast_2d(sigma1), np.atleast_2d(sigma2)
     assert mu1.shape == mu2.shape and sigma1.shape == sigma2.shape
     diff = mu1 - mu2
-    covmean, _ = linalg.sqrtm(sigma1.dot(sigma2), disp=False)
+    try:  # (pytorch_fid calls sqrtm(..., disp=False) -> (matrix, error estimate); SciPy >= 1.16 dropped the argument)
+        covmean, _ = linalg.sqrtm(sigma1.dot(sigma2), disp=False)
+    except TypeError:
+        covmean = linalg.sqrtm(sigma1.dot(sigma2))
     if not np.isfinite(covmean).all():
         offset = np.eye(sigma1.shape[0]) * eps
         covmean = linalg.sqrtm((sigma1 + offset).dot(sigma2 + offset))

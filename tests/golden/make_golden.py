@@ -796,6 +796,22 @@ def dhariwal():
     torch.save(gold, os.path.join(HERE, "nets_dhariwal.pt"))
 
 
+def fid():
+    """FID Inception features of a seeded batch, computed with torchvision's own Inception3 modules carrying pytorch_fid's
+    pooling patches (oracle.fid.torchvision_fid_inception; pytorch_fid itself is not available) -> fid_tiny.pt"""
+    from oracle import fid as OF
+    torch.set_num_threads(8)
+    sd = weights.fid_inception_state_dict(seed=7)
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(2, 3, 48, 48, generator=g)
+    samples = torch.randn(2, 3, 64, 64, generator=g) * 0.6  # sampler outputs: some values outside [-1, 1]
+    net = OF.torchvision_fid_inception(sd)
+    with torch.no_grad():
+        feats = net(x)
+        feats_s = net(OF.png_round_trip((samples + 1) / 2))
+    torch.save(dict(x=x, samples=samples, features=feats, features_of_samples=feats_s), os.path.join(HERE, "fid_tiny.pt"))
+
+
 def bench_arch():
     loop_c2()
     nets_bench()

@@ -109,6 +109,19 @@ def _worker(rank, ws, port, q):
     dealt = [i for i in range(7) if i % ws == rank]
     counts = parallel.reduce_metric_sums(torch.tensor([float(len(dealt))]))
     ok = ok and counts.item() == 7.0
+    # FID statistics of a sharded run (fid.FidStatistics.all_reduce / finalize): each rank holds the fp64 partial sums of its
+    # own features (filled directly here: the accumulation kernel needs the GPU); the reduced result is np.mean / np.cov of
+    # the union
+    from nlc_b200 import fid
+    import numpy as np
+    feats = np.random.default_rng(11).normal(size=(10, 6))
+    mine = torch.from_numpy(feats[rank::ws])
+    st = fid.FidStatistics(dims=6, device="cpu")
+    st.sum += mine.sum(0)
+    st.outer += mine.T @ mine
+    st.count = mine.shape[0]
+    mu, sigma = st.all_reduce().finalize()
+    ok = ok and st.count == 10 and np.allclose(mu, feats.mean(0)) and np.allclose(sigma, np.cov(feats, rowvar=False))
     q.put((rank, ok))
     dist.destroy_process_group()
 
