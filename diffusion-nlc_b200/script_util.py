@@ -50,13 +50,12 @@ def create_simple_sigma_eps_model(config, precision="bf16", device="cuda"):
     num_res_blocks, attn_resolutions, dropout, in_channels, resamp_with_conv, sigma_block, sigma_dropout},
     config.data.image_size."""
     m = config.model
-    if getattr(m, "feat_layer", 0) != 0:
-        raise NotImplementedError("feat_layer != 0 of src/unet_simple.py is not built for the DDIM UNet")
     mult = tuple(m.ch_mult)
     eps_model = unet_ddim.UNetModel(
         image_size=config.data.image_size, in_channels=m.in_channels, model_channels=m.ch, out_channels=m.out_ch,
         num_res_blocks=m.num_res_blocks, attention_resolutions=tuple(m.attn_resolutions), dropout=m.dropout,
-        channel_mult=mult, conv_resample=getattr(m, "resamp_with_conv", True), precision=precision, device=device)
+        channel_mult=mult, conv_resample=getattr(m, "resamp_with_conv", True),
+        feat_layer=int(getattr(m, "feat_layer", 0) != 0), precision=precision, device=device)
     inp_channels = int(m.ch * mult[-1])
     inp_dim = int(config.data.image_size * 0.5 ** (len(mult) - 1))
     sigma_model = unet_ddim.SigmaModel(dim=inp_dim, channels=inp_channels, n_blocks=m.sigma_block, out_dim=1,

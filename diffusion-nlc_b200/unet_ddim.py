@@ -109,7 +109,12 @@ class UNetModel:
     """Drop-in for src/unet_ddim.py:214 `UNetModel` (inference only)."""
 
     def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
-                 dropout=0.0, channel_mult=(1, 2, 4, 8), conv_resample=True, precision="bf16", device="cuda"):
+                 dropout=0.0, channel_mult=(1, 2, 4, 8), conv_resample=True, feat_layer=0, precision="bf16", device="cuda"):
+        # feat_layer: which middle-block tensor `encode` returns - 0: after mid.attn_1 (src/unet_ddim.py:365-393 and
+        # src/unet_simple.py:371-372), 1: after mid.block_2 (src/unet_simple.py:373-375,402-407: `config.model.feat_layer`)
+        if feat_layer not in (0, 1):
+            raise ValueError("feat_layer must be 0 or 1")
+        self.feat_layer = feat_layer
         if not conv_resample:
             raise NotImplementedError("conv_resample=False (avg-pool / bare upsample) is not used by the reference "
                                       "factories (src/script_util.py:209-219)")
@@ -180,7 +185,7 @@ class UNetModel:
             b.temb_off = off
             off += b.cout
         self.temb_total = off
-        self.temb_enc = self.mid1.temb_off + self.mid1.cout
+        self.temb_enc = (self.mid2 if self.feat_layer else self.mid1).temb_off + (self.mid2 if self.feat_layer else self.mid1).cout
         self.tpw = eng.dev32(torch.cat([b.temb_w for b in order], dim=0))
         self.tpb = eng.dev32(torch.cat([b.temb_b.float().cpu() + b.b1_host for b in order], dim=0))
         self._loaded = True
@@ -189,13 +194,12 @@ class UNetModel:
 
     @classmethod
     def from_reference(cls, ref_module, precision="bf16", device="cuda"):
-        """Build from an instance of the reference's src.unet_ddim.UNetModel (or src.unet_simple.Model with
-        feat_layer 0)."""
+        """Build from an instance of the reference's src.unet_ddim.UNetModel or src.unet_simple.Model (either feat_layer)."""
         m = ref_module
         attn_res = sorted({m.resolution // (2 ** i) for i, lvl in enumerate(m.down) if len(lvl.attn) > 0})
         ch_mult = tuple(lvl.block[-1].out_channels // m.ch for lvl in m.down)
         self = cls(m.resolution, m.in_channels, m.ch, m.conv_out.out_channels, m.num_res_blocks, attn_res,
-                   channel_mult=ch_mult, precision=precision, device=device)
+                   channel_mult=ch_mult, feat_layer=int(getattr(m, "feat_layer", 0) != 0), precision=precision, device=device)
         return self.load_state_dict(m.state_dict())
 
     # ------------------------------------------------------------------ plan
@@ -294,15 +298,29 @@ class UNetModel:
         m1 = eng.stream_feat("mid.1", B, rmid, rmid, c_mid)
         _emit_resblock(enc, self.mid1, cur, m1, rowvec=tp[:, self.mid1.temb_off:self.mid1.temb_off + c_mid])
         feat = Feat(f32=Act(eng.named("feat", (B, rmid, rmid, c_mid), f32)))
-        _emit_attnblock(enc, self.mid_attn, m1, feat)
         P["feat"] = feat.f32.t
+        k = n_skips
+        rv2 = tp[:, self.mid2.temb_off:self.mid2.temb_off + c_mid]
+        dec = PlanCtx(eng, B)
+        if self.feat_layer == 0:
+            _emit_attnblock(enc, self.mid_attn, m1, feat)
+        else:
+            # the feature is mid.block_2's output, which is also the decoder's first head: the block belongs to the encoder
+            # pass; it writes the head slice of the first concat buffer and (fp32) the feature tensor
+            ma = eng.stream_feat("mid.a", B, rmid, rmid, c_mid)
+            _emit_attnblock(enc, self.mid_attn, m1, ma)
+            head = head_feat(k)
+            if head.f32 is None:
+                _emit_resblock(enc, self.mid2, ma, Feat(f32=feat.f32, op=head.op), rowvec=rv2)
+            else:
+                _emit_resblock(enc, self.mid2, ma, head, rowvec=rv2)
+                h32, f32t = head.f32, feat.f32
+                enc.add(lambda: ops.resample(h32, 0, f32t, None, dt), "feat copy")
 
         # ---- decoder
-        dec = PlanCtx(eng, B)
         dec._gn_ws_floats, dec._attn_ws_bytes = enc._gn_ws_floats, enc._attn_ws_bytes
-        k = n_skips
-        _emit_resblock(dec, self.mid2, feat, head_feat(k),
-                       rowvec=tp[:, self.mid2.temb_off:self.mid2.temb_off + c_mid])
+        if self.feat_layer == 0:
+            _emit_resblock(dec, self.mid2, feat, head_feat(k), rowvec=rv2)
         res = rmid
         for i_level in reversed(range(self.num_resolutions)):
             lvl = self.up[i_level]

@@ -113,15 +113,19 @@ def _encoder(sd, x, t):
     return h, hs, temb
 
 
-def unet_encode(sd, x, t):
-    """src/unet_ddim.py:365-393."""
-    return _encoder(sd, x, t)[0]
+def unet_encode(sd, x, t, feat_layer=0):
+    """src/unet_ddim.py:365-393; feat_layer 1 (src/unet_simple.py:373-375): the feature is mid.block_2's output."""
+    h, _, temb = _encoder(sd, x, t)
+    return h if feat_layer == 0 else resnet_block(sd, "mid.block_2.", h, temb)
 
 
-def unet_forward(sd, x, t, return_feat=False):
-    """src/unet_ddim.py:323-363 (and forward_and_encode :395-436 when return_feat)."""
+def unet_forward(sd, x, t, return_feat=False, feat_layer=0):
+    """src/unet_ddim.py:323-363 (and forward_and_encode :395-436 when return_feat; src/unet_simple.py:399-407 for
+    feat_layer 1)."""
     feat, hs, temb = _encoder(sd, x, t)
     h = resnet_block(sd, "mid.block_2.", feat, temb)
+    if feat_layer != 0:
+        feat = h
     for lv in reversed(range(_levels(sd, "up"))):
         n_blocks = _count(sd, "up.%d.block" % lv)
         has_attn = _count(sd, "up.%d.attn" % lv) > 0

@@ -796,6 +796,31 @@ def dhariwal():
     torch.save(gold, os.path.join(HERE, "nets_dhariwal.pt"))
 
 
+def simple_feat_layer():
+    """src/unet_simple.py Model(config) with config.model.feat_layer = 1 (the DDIM UNet the factory builds): encode /
+    forward_and_encode of the unmodified reference on the tiny architecture -> nets_simple_fl1.pt"""
+    import importlib
+    import types
+    refimport.load()
+    US = importlib.import_module("src.unet_simple")
+    u = weights.CONFIGS["tiny"]["unet"]
+    cfg = types.SimpleNamespace(
+        model=types.SimpleNamespace(ch=u["model_channels"], out_ch=u["out_channels"], ch_mult=list(u["channel_mult"]),
+                                    num_res_blocks=u["num_res_blocks"], attn_resolutions=list(u["attention_resolutions"]),
+                                    dropout=0.0, in_channels=u["in_channels"], resamp_with_conv=True, type="simple",
+                                    feat_layer=1),
+        data=types.SimpleNamespace(image_size=u["image_size"]),
+        diffusion=types.SimpleNamespace(num_diffusion_timesteps=1000))
+    net = US.Model(cfg).eval()
+    net.load_state_dict(weights.ddim_unet_state_dict(**u, seed=3))
+    x = torch.randn(2, 3, u["image_size"], u["image_size"], generator=torch.Generator().manual_seed(8))
+    t = torch.tensor([640.0, 12.0])
+    with torch.no_grad():
+        out, feat = net.forward_and_encode(x, t)
+        assert torch.equal(feat, net.encode(x, t))
+    torch.save(dict(x=x, t=t, out=out, feat=feat), os.path.join(HERE, "nets_simple_fl1.pt"))
+
+
 def fid():
     """FID Inception features of a seeded batch, computed with torchvision's own Inception3 modules carrying pytorch_fid's
     pooling patches (oracle.fid.torchvision_fid_inception; pytorch_fid itself is not available) -> fid_tiny.pt"""

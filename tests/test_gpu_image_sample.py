@@ -91,3 +91,30 @@ def test_evaluate_unconstraint(golden):
     assert s.shape == (6, 3) + tuple(exp.data_shape[-2:]) and s.min() >= 0 and s.max() <= 1 and log["fid"] is None
     logp, _ = IS.evaluate_unconstraint(exp, 2, None, sampling="project", sigma_estimate_rate=(0.5, 0.2, 0.2, 0.1), **KW)
     assert logp["samples"].shape[0] == 2 and torch.isfinite(logp["samples"]).all()
+
+
+def test_evaluate_unconstraint_reports_the_device_fid(golden):
+    """With fid.fid_helper the driver accumulates the InceptionV3 statistics of its own samples on the device; the reported
+    FID is the Frechet distance between the target and those statistics (a 64-feature head keeps the host sqrtm small)."""
+    import numpy as np
+    from nlc_b200 import fid, image_sample as IS
+    from oracle import fid as OF, weights
+    exp = _setup("fp32", golden, "colorization|1")[0]
+    sd = weights.fid_inception_state_dict(seed=7)
+    net = fid.InceptionV3(precision="fp32", device=dev).load_state_dict(sd)
+    seen = []
+    orig = net.features_of_samples
+    net.features_of_samples = lambda x: seen.append(orig(x)) or seen[-1]
+    target = (np.zeros(2048), np.eye(2048))
+    fid.fid_helper(exp, target, net)
+    exp.fid_of = lambda st: ("stats", st.count) + st.finalize()  # (skip the 2048 x 2048 host sqrtm: return the statistics)
+    log, _ = IS.evaluate_unconstraint(exp, 5, None, **KW)
+    tag, count, mu, sigma = log["fid"]
+    feats = torch.cat(seen).cpu().numpy()
+    assert tag == "stats" and count == log["samples"].shape[0] == feats.shape[0]
+    m, s = OF.statistics(feats)
+    assert np.abs(mu - m).max() < 1e-9 and np.abs(sigma - s).max() < 1e-9
+    # the features are those of the images the driver returned, through the 8-bit round trip
+    with torch.no_grad():
+        want = OF.inception_features(sd, OF.png_round_trip(log["samples"].cpu()))
+    assert ((torch.from_numpy(feats) - want).abs().max() / want.abs().max()).item() < 1e-3

@@ -61,6 +61,33 @@ def test_benchmark_architectures_vs_oracle(name, B, prec):
     assert (s(f).cpu() - r_ref).abs().max() < (1e-2 if prec == "bf16" else 2e-3)
 
 
+@pytest.mark.parametrize("prec", ["fp32", "tf32", "fp16", "bf16"])
+def test_feat_layer_1_of_the_factory_unet(golden_dir, prec):
+    """`feat_layer != 0` of src/unet_simple.py (the DDIM UNet create_simple_sigma_eps_model builds): encode returns the
+    tensor after mid.block_2, which is also the decoder's first head.  Golden from the unmodified reference
+    (tests/golden/nets_simple_fl1.pt) and the oracle on the c1 architecture; forward is unchanged by the switch."""
+    from nlc_b200.unet_ddim import UNetModel
+    tol = dict(TOL, fp32=1e-4)[prec]
+    g = torch.load(os.path.join(golden_dir, "nets_simple_fl1.pt"), weights_only=True)
+    cfg = weights.CONFIGS["tiny"]["unet"]
+    sd = weights.ddim_unet_state_dict(**cfg, seed=3)
+    m = UNetModel(**cfg, feat_layer=1, precision=prec, device=dev).load_state_dict(sd)
+    x, t = g["x"].to(dev), g["t"].to(dev)
+    assert _rel(m.encode(x, t).cpu(), g["feat"]) < tol
+    out, feat = m.forward_and_encode(x, t)
+    assert _rel(out.cpu(), g["out"]) < tol and _rel(feat.cpu(), g["feat"]) < tol
+    cfg = weights.CONFIGS["c1"]["unet"]
+    sd = weights.ddim_unet_state_dict(**cfg, seed=3)
+    m = UNetModel(**cfg, feat_layer=1, precision=prec, device=dev).load_state_dict(sd)
+    x = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(6))
+    t = torch.tensor([999.0, 250.0, 3.0])
+    with torch.no_grad():
+        ref, rfeat = ddim_net.unet_forward(sd, x, t, return_feat=True, feat_layer=1)
+    out, feat = m.forward_and_encode(x.to(dev), t.to(dev))
+    assert _rel(out.cpu(), ref) < tol and _rel(feat.cpu(), rfeat) < tol
+    assert _rel(m.encode(x.to(dev), t.to(dev)).cpu(), rfeat) < tol
+
+
 def test_input_scale_folding_and_batch_independence():
     """forward_scaled(x, t, scale) == forward(x*scale, t); rows do not interact (the property batch sharding rests
     on): a batch of 6 equals two batches of 3.  Tolerance 2e-3: a last-bit difference in fp32 (scale applied after

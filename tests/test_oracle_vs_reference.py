@@ -52,6 +52,39 @@ def test_state_dict_layout_and_networks(R, name):
         assert torch.equal(snet(f), ddim_net.sigma_forward(ssd, f))
 
 
+def _simple_config(u, feat_layer):
+    """The YAML-shaped config object src/unet_simple.py `Model(config)` reads (the store/config/*.yml files are absent)."""
+    import types
+    return types.SimpleNamespace(
+        model=types.SimpleNamespace(ch=u["model_channels"], out_ch=u["out_channels"], ch_mult=list(u["channel_mult"]),
+                                    num_res_blocks=u["num_res_blocks"], attn_resolutions=list(u["attention_resolutions"]),
+                                    dropout=0.0, in_channels=u["in_channels"], resamp_with_conv=True, type="simple",
+                                    feat_layer=feat_layer),
+        data=types.SimpleNamespace(image_size=u["image_size"]),
+        diffusion=types.SimpleNamespace(num_diffusion_timesteps=1000))
+
+
+@pytest.mark.parametrize("feat_layer", [0, 1])
+def test_unet_simple_feat_layer(R, feat_layer):
+    """src/unet_simple.py `Model(config)` - the DDIM UNet the factory create_simple_sigma_eps_model actually builds
+    (src/script_util.py:209-219) - has the state_dict of src/unet_ddim.py's UNetModel and a `feat_layer` switch: 0 returns
+    the tensor after mid.attn_1, anything else the one after mid.block_2 (:371-375, :402-407)."""
+    import importlib
+    US = importlib.import_module("src.unet_simple")
+    u = weights.CONFIGS["tiny"]["unet"]
+    sd = weights.ddim_unet_state_dict(**u, seed=3)
+    net = US.Model(_simple_config(u, feat_layer)).eval()
+    assert set(net.state_dict()) == set(sd)
+    net.load_state_dict(sd)
+    x = torch.randn(2, 3, u["image_size"], u["image_size"], generator=torch.Generator().manual_seed(8))
+    t = torch.tensor([640.0, 12.0])
+    with torch.no_grad():
+        assert torch.equal(net.encode(x, t), ddim_net.unet_encode(sd, x, t, feat_layer=feat_layer))
+        out, feat = net.forward_and_encode(x, t)
+        o2, f2 = ddim_net.unet_forward(sd, x, t, return_feat=True, feat_layer=feat_layer)
+        assert torch.equal(out, o2) and torch.equal(feat, f2) and torch.equal(net(x, t), o2)
+
+
 def test_c2_layout(R):
     cfg = weights.CONFIGS["c2"]
     sd = weights.ddim_unet_state_dict(**cfg["unet"], seed=3)
