@@ -87,6 +87,18 @@ _SIGNATURES = {
     "nlc_groupnorm_ws": (_SZ, [_I, _I, _I, _I]),
     "nlc_resample": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _I, _P]),
     "nlc_resample_op": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "nlc_sgemm": (_I, [_P, _I, _I, _I, _I, _P, _I64, _I64, _I64, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "nlc_unfold3x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "nlc_fold3x3": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _F, _P]),
+    "nlc_gn_train_fwd": (_I, [_P, _P, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P, _P]),
+    "nlc_gn_train_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P, _P, _P]),
+    "nlc_softmax_rows": (_I, [_P, _P, _P, _I, _I, _F, _P, _P]),
+    "nlc_bias_add": (_I, [_P, _P, _P, _I64, _I, _P]),
+    "nlc_colsum": (_I, [_P, _P, _I64, _I, _P, _P]),
+    "nlc_axpby": (_I, [_P, _F, _P, _F, _P, _P, _I64, _P]),
+    "nlc_permute_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
+    "nlc_bn1d_gelu_train": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nlc_head_loss": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "nlc_fid_preprocess": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "nlc_im2col_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I64, _P]),
     "nlc_pool2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

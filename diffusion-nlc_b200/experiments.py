@@ -77,6 +77,7 @@ class ExperimentDiffusion:
         self.nan_check_every = 16
         # replay the timestep from a CUDA graph in denoise_loop (NLC_GRAPH=0 disables; see denoise_loop)
         self.cuda_graph = os.environ.get("NLC_GRAPH", "1") != "0"
+        self._graph_cache = {}  # captured timesteps, kept across denoise_loop calls (see _graph_signature)
         # instrumentation for parity studies: `time_source(step) -> (t, t_hat)` ([B] float tensors or None) replaces the
         # step's two discrete time lookups t = searchsorted(sigma) (src/experiments.py:410,427) by given values, so a
         # free-running trajectory can be compared with the reference's without its time-bucket decisions diverging
@@ -310,6 +311,32 @@ class ExperimentDiffusion:
             return partial(owner.loss_device, **kw)
         return None
 
+    @staticmethod
+    def _callable_signature(fn):
+        """Identity of a `partial(Constraint_Function.method, y=y, ...)` for the graph cache: the bound object, the method and
+        every keyword - tensors by (address, shape, dtype): a captured step reads them through their fixed addresses."""
+        if fn is None:
+            return None
+        func, kw = (fn.func, fn.keywords) if hasattr(fn, "func") and hasattr(fn, "keywords") else (fn, {})
+        if getattr(fn, "args", ()):
+            return ("opaque", id(fn))
+        items = tuple((k, (v.data_ptr(), tuple(v.shape), str(v.dtype)) if torch.is_tensor(v) else v) for k, v in sorted(kw.items()))
+        return (id(getattr(func, "__self__", None)), getattr(func, "__name__", repr(func)), items)
+
+    def _graph_signature(self, B, key, norm_eps, chunk_size, constrain_fn, loss_dev, world):
+        """Everything a captured timestep bakes in besides device buffers with fixed addresses (the workspace of batch size B,
+        the networks' plan buffers, the scheduler tables): the host scalars that become kernel arguments and the identities of
+        the objects whose buffers it reads.  A cached graph is replayed only under an identical signature."""
+        sch = self.scheduler
+        return (B, key, bool(norm_eps), id(self.model), id(self.sigma_model), id(sch), sch.kind, float(sch.eta),
+                getattr(sch, "sampler_var", None), self.clip_mode, float(self.norm_min), float(self.norm_max),
+                bool(self.learn_epsvar), self.time_shift, self._callable_signature(constrain_fn),
+                self._callable_signature(loss_dev), world, torch.cuda.current_stream().cuda_stream)
+
+    def clear_graphs(self):
+        """Drop the captured timesteps (they pin their private memory pools)."""
+        self._graph_cache.clear()
+
     @torch.no_grad()
     def denoise_loop(self, shape, gen=None, norm_init_noise=False, style="base", constrain_fn=None, norm_eps=False,
                      refine_prior_sigma=False, xT=None, return_log=True, chunk_size=2, sigma_pred_threshold=1000,
@@ -371,7 +398,12 @@ class ExperimentDiffusion:
             gb.best_val.fill_(10000.0)
             gb.best_x0.copy_(xt)
             needs_noise = sch.kind in ("ddpm", "ddpm_orig") or float(sch.eta) > 0 or (new_eta is not None and new_eta > 0)
-            graphs, warmed = {}, set()
+            # Captured timesteps live on the experiment across calls: re-capturing every pass costs a graph instantiation and,
+            # when the old graph is destroyed, the cudaFree / cudaMalloc round trip of its private memory pool - 0.2 s per
+            # pass, 10-20 % of a c2 pass (profiles/r02p_graph_cache.md)
+            graphs, warmed = self._graph_cache, set()
+            while len(graphs) > 8:
+                graphs.pop(next(iter(graphs)))
             out_ref = {}
 
             def body(ind, t, sigma_t, sigma_prev, cur_style, cur_refine, apply_con, noise):
@@ -413,8 +445,10 @@ class ExperimentDiffusion:
                 key = (cur_style, apply_con, noise is not None)
                 capturable = (use_graph and cur_refine and not last_eta
                               and (graph_skip is None or not graph_skip(ind)))
-                if capturable and key in warmed:
-                    g = graphs.get(key)
+                gkey = self._graph_signature(B, key, norm_eps, chunk_size, constrain_fn if apply_con else None, loss_dev,
+                                             world) if capturable else None
+                if capturable and (key in warmed or gkey in graphs):
+                    g = graphs.get(gkey)
                     if g is None:
                         n0 = ops.STATS.launches
                         g = torch.cuda.CUDAGraph()
@@ -423,7 +457,7 @@ class ExperimentDiffusion:
                         g.n_launches = ops.STATS.launches - n0
                         g.x0 = out_ref["x0"]  # (lives in the graph's memory pool: every replay refreshes it)
                         ops.STATS.launches = n0
-                        graphs[key] = g
+                        graphs[gkey] = g
                     g.replay()
                     out_ref["x0"] = g.x0
                     ops.STATS.launches += g.n_launches
@@ -447,7 +481,6 @@ class ExperimentDiffusion:
             x0 = out_ref.get("x0", xt)
             best_x0 = gb.best_x0 if loss_dev is not None else x0
             result = (best_x0 if return_best else x0).clone()
-            graphs.clear()
             result = result.cpu() if to_cpu else result
             return result, [z_list, eps_list, x0_prec_list, x0_postc_list, const_loss_list]
 

@@ -118,3 +118,313 @@ def train_step(model, trainer, scheduler, batch_x, t, noise, extra, eta1, eta2, 
     loss.backward()
     trainer.step()
     return loss.detach()
+
+
+# ======================================================================================================================
+# Second slice: the sigma-model's own forward and backward pass, natively (csrc/sigma_train.cu).
+class _Flat:
+    """Named fp32 tensors as views of one flat buffer, every tensor 16-byte aligned (the layout SigmaTrainer uses)."""
+
+    def __init__(self, shapes, device):
+        self.names = list(shapes)
+        sizes = [((int(torch.Size(shapes[n]).numel()) + 3) // 4) * 4 for n in self.names]
+        self.flat = torch.zeros(sum(sizes), device=device)
+        self.views, off = {}, 0
+        for n, sz in zip(self.names, sizes):
+            self.views[n] = self.flat[off:off + torch.Size(shapes[n]).numel()].view(shapes[n])
+            off += sz
+
+    def __getitem__(self, n):
+        return self.views[n]
+
+
+class NativeSigmaModel:
+    """The DDIM-family sigma-model (src/unet_ddim.py:493-529: per block PureResnetBlock [-> AttnBlock in block 0] ->
+    Downsample; Flatten -> Linear -> BatchNorm1d -> GELU -> Linear) with a native training-mode forward AND backward pass:
+    `loss_and_grad(feat, dist_real)` is `dist_hat = model(feat) + 1; loss = loss_fn(dist_real, dist_hat); loss.backward()`
+    of src/experiments.py:688-691 without autograd.  Parameters and gradients live in flat fp32 buffers in the reference's
+    parameter layout (`params[name]`, `grads[name]`), which `step()` updates with the fused AdamW + EMA kernel (gradients
+    all-reduced over the ranks first).  fp32 throughout; activations NHWC; every contraction is `nlc_sgemm`.
+    `dropout` > 0 draws its masks with torch on the device (statistically the reference's nn.Dropout, not its stream)."""
+
+    GROUPS, GN_EPS, BN_EPS, BN_MOMENTUM = 32, 1e-6, 1e-5, 0.1
+
+    def __init__(self, dim=4, channels=64, n_blocks=2, out_dim=1, dropout=0.1, loss="l2", device="cuda"):
+        if out_dim != 1:
+            raise NotImplementedError("out_dim != 1 is not used by the reference")
+        if dim % (2 ** n_blocks) != 0:
+            raise NotImplementedError("feature sizes that need the reference's ConstantPad2d (odd sizes) are not built")
+        if loss not in ("l2", "l1"):
+            raise NotImplementedError("loss_sigma '%s': MSELoss ('l2') and L1Loss ('l1') are built" % loss)
+        self.dim, self.C, self.n_blocks, self.p_drop = dim, channels, n_blocks, float(dropout)
+        self.loss_kind = 0 if loss == "l2" else 1
+        self.device = torch.device(device)
+        self._lib, self._bufs = _lib.lib(), {}
+        self._ctx = _lib.ctx(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.training = True
+
+    # ------------------------------------------------------------------ parameters
+    def load_state_dict(self, sd, strict=True):
+        sd = {k: v.detach() for k, v in sd.items()}
+        buffers = ("running_mean", "running_var", "num_batches_tracked")
+        shapes = {k: tuple(v.shape) for k, v in sd.items() if not k.endswith(buffers)}
+        self.params, self.grads = _Flat(shapes, self.device), _Flat(shapes, self.device)
+        for k in shapes:
+            self.params[k].copy_(sd[k].to(self.device, torch.float32))
+        self.run_mean = sd["fc_layer.2.running_mean"].to(self.device, torch.float32).clone()
+        self.run_var = sd["fc_layer.2.running_var"].to(self.device, torch.float32).clone()
+        self.num_batches_tracked = int(sd.get("fc_layer.2.num_batches_tracked", 0))
+        # module slots: block i owns (pad/identity, resblock, [attn], downsample)
+        self.blocks, idx = [], 0
+        for i in range(self.n_blocks):
+            idx += 1
+            blk = {"res": "down_layer.%d." % idx}
+            idx += 1
+            if i == 0:
+                blk["attn"] = "down_layer.%d." % idx
+                idx += 1
+            blk["down"] = "down_layer.%d." % idx
+            idx += 1
+            self.blocks.append(blk)
+        need = [self.blocks[0]["res"] + "conv1.weight", self.blocks[0]["attn"] + "q.weight", "fc_layer.1.weight", "final_mlp.weight"]
+        missing = [k for k in need if k not in shapes]
+        if missing:
+            raise KeyError("sigma-model state_dict lacks %s" % missing)
+        self.fc_dim = shapes["fc_layer.1.weight"][0]
+        self.exp_avg = torch.zeros_like(self.params.flat)
+        self.exp_avg_sq = torch.zeros_like(self.params.flat)
+        self.ema = self.params.flat.clone()
+        self.steps = 0
+        return self
+
+    def state_dict(self):
+        sd = {k: self.params[k].clone() for k in self.params.names}
+        sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"] = self.run_mean.clone(), self.run_var.clone()
+        sd["fc_layer.2.num_batches_tracked"] = torch.tensor(self.num_batches_tracked)
+        return sd
+
+    def ema_state_dict(self):
+        off, out = 0, {}
+        for k in self.params.names:
+            n = self.params[k].numel()
+            out[k] = self.ema[off:off + n].view_as(self.params[k]).clone()
+            off += (n + 3) // 4 * 4
+        return out
+
+    # ------------------------------------------------------------------ plumbing
+    def _buf(self, tag, *shape):
+        key = (tag,) + tuple(shape)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(*shape, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _mm(self, batch, M, N, K, A, sa, B, sb, out, add=None):
+        """out[b] = A[b] B[b] (+ add[b]); sa = (batch, row, k) strides of A, sb = (batch, k, column) strides of B."""
+        _lib.check(self._lib.nlc_sgemm(self._ctx, batch, M, N, K, A.data_ptr(), sa[0], sa[1], sa[2], B.data_ptr(), sb[0], sb[1],
+                                       sb[2], out.data_ptr(), C.c_void_p(add.data_ptr()) if add is not None else None, _stream()))
+
+    def _linear(self, x, rows, cin, w, b, out):
+        """out[rows, cout] = x[rows, cin] w[cout, cin]^T + b"""
+        cout = w.shape[0]
+        self._mm(1, rows, cout, cin, x, (0, cin, 1), w, (0, 1, cin), out)
+        _lib.check(self._lib.nlc_bias_add(self._ctx, out.data_ptr(), b.data_ptr(), rows, cout, _stream()))
+
+    def _linear_bwd(self, x, dy, rows, cin, w, dw, db, dx, add=None):
+        """dw[cout, cin] = dy^T x; db = column sums of dy; dx[rows, cin] = dy w (+ add)"""
+        cout = w.shape[0]
+        self._mm(1, cout, cin, rows, dy, (0, 1, cout), x, (0, cin, 1), dw)
+        _lib.check(self._lib.nlc_colsum(self._ctx, dy.data_ptr(), rows, cout, db.data_ptr(), _stream()))
+        if dx is not None:
+            self._mm(1, rows, cin, cout, dy, (0, cout, 1), w, (0, cin, 1), dx, add=add)
+
+    def _gn(self, x, B, HW, name, act, y, stats):
+        _lib.check(self._lib.nlc_gn_train_fwd(self._ctx, x.data_ptr(), B, HW, self.C, self.GROUPS, self.GN_EPS,
+                                              self.params[name + ".weight"].data_ptr(), self.params[name + ".bias"].data_ptr(), act,
+                                              y.data_ptr(), stats.data_ptr(), _stream()))
+
+    def _gn_bwd(self, x, dy, B, HW, name, act, stats, dx, accumulate):
+        _lib.check(self._lib.nlc_gn_train_bwd(self._ctx, x.data_ptr(), dy.data_ptr(), B, HW, self.C, self.GROUPS,
+                                              self.params[name + ".weight"].data_ptr(), self.params[name + ".bias"].data_ptr(), act,
+                                              stats.data_ptr(), dx.data_ptr(), 1 if accumulate else 0,
+                                              self.grads[name + ".weight"].data_ptr(), self.grads[name + ".bias"].data_ptr(),
+                                              _stream()))
+
+    def _conv3(self, x, B, H, W, name, down, tag):
+        """3x3 conv through its patch matrix; returns (y [B*Ho*Wo, C], patches)."""
+        Cc = self.C
+        Ho, Wo = (H // 2, W // 2) if down else (H, W)
+        M = B * Ho * Wo
+        P = self._buf(tag + ".P", M, 9 * Cc)
+        _lib.check(self._lib.nlc_unfold3x3(self._ctx, x.data_ptr(), B, H, W, Cc, down, P.data_ptr(), _stream()))
+        y = self._buf(tag + ".y", M, Cc)
+        self._linear(P, M, 9 * Cc, self.params[name + ".weight"].view(Cc, 9 * Cc), self.params[name + ".bias"], y)
+        return y, P
+
+    def _conv3_bwd(self, dy, P, B, H, W, name, down, dx, beta, tag):
+        Cc = self.C
+        Ho, Wo = (H // 2, W // 2) if down else (H, W)
+        M = B * Ho * Wo
+        dP = self._buf(tag + ".dP", M, 9 * Cc)
+        self._linear_bwd(P, dy, M, 9 * Cc, self.params[name + ".weight"].view(Cc, 9 * Cc),
+                         self.grads[name + ".weight"].view(Cc, 9 * Cc), self.grads[name + ".bias"], dP)
+        _lib.check(self._lib.nlc_fold3x3(self._ctx, dP.data_ptr(), B, H, W, Cc, down, dx.data_ptr(), beta, _stream()))
+
+    def _axpby(self, a, x, b, y, out):
+        _lib.check(self._lib.nlc_axpby(self._ctx, a, x.data_ptr(), b, C.c_void_p(y.data_ptr()) if y is not None else None,
+                                       out.data_ptr(), out.numel(), _stream()))
+
+    # ------------------------------------------------------------------ forward + backward
+    def loss_and_grad(self, feat, dist_real, nhwc=False):
+        """feat: encoder feature [B, C, dim, dim] (the reference's layout) or NHWC [B, dim, dim, C] with nhwc=True;
+        dist_real: [B] (or [B,1,1,1]) targets.  Training-mode forward, loss, backward: fills `grads`, updates the BatchNorm
+        running statistics, returns (loss [1], dist_hat [B]) on the device."""
+        L, ctx, Cc = self._lib, self._ctx, self.C
+        B, dim = feat.shape[0], self.dim
+        feat = feat.to(self.device, torch.float32).contiguous()
+        target = dist_real.to(self.device, torch.float32).reshape(B).contiguous()
+        self.grads.flat.zero_()
+        x = self._buf("in", B * dim * dim, Cc)
+        if nhwc:
+            x.copy_(feat.reshape(B * dim * dim, Cc))
+        else:
+            _lib.check(L.nlc_permute_nhwc(ctx, feat.data_ptr(), B, dim * dim, Cc, 0, x.data_ptr(), _stream()))
+        saved, H = [], dim
+        for bi, blk in enumerate(self.blocks):
+            M, HW, r = B * H * H, H * H, blk["res"]
+            t = "b%d" % bi
+            a1, st1 = self._buf(t + ".a1", M, Cc), self._buf(t + ".st1", B * self.GROUPS * 2)
+            self._gn(x, B, HW, r + "norm1", 1, a1, st1)
+            c1, P1 = self._conv3(a1, B, H, H, r + "conv1", 0, t + ".c1")
+            a2, st2 = self._buf(t + ".a2", M, Cc), self._buf(t + ".st2", B * self.GROUPS * 2)
+            self._gn(c1, B, HW, r + "norm2", 1, a2, st2)
+            mask = None
+            if self.training and self.p_drop > 0:
+                mask = (torch.rand(M, Cc, device=self.device) >= self.p_drop).float() / (1.0 - self.p_drop)
+                a2.mul_(mask)
+            c2, P2 = self._conv3(a2, B, H, H, r + "conv2", 0, t + ".c2")
+            y = self._buf(t + ".y", M, Cc)
+            self._axpby(1.0, x, 1.0, c2, y)
+            rec = dict(x=x, st1=st1, P1=P1, c1=c1, st2=st2, P2=P2, mask=mask, H=H)
+            z = y
+            if "attn" in blk:
+                a = blk["attn"]
+                n, stn = self._buf(t + ".n", M, Cc), self._buf(t + ".stn", B * self.GROUPS * 2)
+                self._gn(y, B, HW, a + "norm", 0, n, stn)
+                q, k, v = (self._buf(t + "." + nm, M, Cc) for nm in "qkv")
+                for nm, dst in (("q", q), ("k", k), ("v", v)):
+                    self._linear(n, M, Cc, self.params[a + nm + ".weight"].view(Cc, Cc), self.params[a + nm + ".bias"], dst)
+                S, Pm = self._buf(t + ".S", B, HW, HW), self._buf(t + ".Pm", B, HW, HW)
+                self._mm(B, HW, HW, Cc, q, (HW * Cc, Cc, 1), k, (HW * Cc, 1, Cc), S)
+                scale = float(int(Cc) ** (-0.5))
+                _lib.check(L.nlc_softmax_rows(ctx, S.data_ptr(), None, B * HW, HW, scale, Pm.data_ptr(), _stream()))
+                O = self._buf(t + ".O", M, Cc)
+                self._mm(B, HW, Cc, HW, Pm, (HW * HW, HW, 1), v, (HW * Cc, Cc, 1), O)
+                pr = self._buf(t + ".pr", M, Cc)
+                self._linear(O, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc), self.params[a + "proj_out.bias"], pr)
+                z = self._buf(t + ".z", M, Cc)
+                self._axpby(1.0, y, 1.0, pr, z)
+                rec.update(y=y, n=n, stn=stn, q=q, k=k, v=v, Pm=Pm, O=O, scale=scale)
+            d, Pd = self._conv3(z, B, H, H, blk["down"] + "conv", 1, t + ".d")
+            rec.update(Pd=Pd)
+            saved.append(rec)
+            x, H = d, H // 2
+        HWf, hidden = H * H, Cc * H * H
+        hflat = self._buf("hflat", B, hidden)
+        _lib.check(L.nlc_permute_nhwc(ctx, x.data_ptr(), B, HWf, Cc, 1, hflat.data_ptr(), _stream()))
+        F1 = self.fc_dim
+        f1, g, stb = self._buf("f1", B, F1), self._buf("g", B, F1), self._buf("stb", F1 * 2)
+        self._linear(hflat, B, hidden, self.params["fc_layer.1.weight"], self.params["fc_layer.1.bias"], f1)
+        _lib.check(L.nlc_bn1d_gelu_train(ctx, f1.data_ptr(), None, B, F1, self.BN_EPS, self.BN_MOMENTUM,
+                                         self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
+                                         self.run_mean.data_ptr(), self.run_var.data_ptr(), stb.data_ptr(), g.data_ptr(), None,
+                                         None, _stream()))
+        self.num_batches_tracked += 1
+        r = self._buf("r", B, 1)
+        self._linear(g, B, F1, self.params["final_mlp.weight"], self.params["final_mlp.bias"], r)
+        dist_hat, loss, dr = self._buf("dist_hat", B), self._buf("loss", 1), self._buf("dr", B, 1)
+        _lib.check(L.nlc_head_loss(ctx, r.data_ptr(), target.data_ptr(), B, self.loss_kind, dist_hat.data_ptr(), loss.data_ptr(),
+                                   dr.data_ptr(), _stream()))
+        # ---------------------------------------------------------------- backward
+        dg = self._buf("dg", B, F1)
+        self._linear_bwd(g, dr, B, F1, self.params["final_mlp.weight"], self.grads["final_mlp.weight"],
+                         self.grads["final_mlp.bias"], dg)
+        df1 = self._buf("df1", B, F1)
+        _lib.check(L.nlc_bn1d_gelu_train(ctx, f1.data_ptr(), dg.data_ptr(), B, F1, self.BN_EPS, self.BN_MOMENTUM,
+                                         self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
+                                         None, None, stb.data_ptr(), df1.data_ptr(), self.grads["fc_layer.2.weight"].data_ptr(),
+                                         self.grads["fc_layer.2.bias"].data_ptr(), _stream()))
+        dh = self._buf("dh", B, hidden)
+        self._linear_bwd(hflat, df1, B, hidden, self.params["fc_layer.1.weight"], self.grads["fc_layer.1.weight"],
+                         self.grads["fc_layer.1.bias"], dh)
+        dx = self._buf("dlast", B * HWf, Cc)
+        _lib.check(L.nlc_permute_nhwc(ctx, dh.data_ptr(), B, HWf, Cc, 0, dx.data_ptr(), _stream()))
+        for bi in reversed(range(len(self.blocks))):
+            blk, rec, t = self.blocks[bi], saved[bi], "b%d" % bi
+            H = rec["H"]
+            M, HW, r = B * H * H, H * H, blk["res"]
+            dz = self._buf(t + ".dz", M, Cc)
+            self._conv3_bwd(dx, rec["Pd"], B, H, H, blk["down"] + "conv", 1, dz, 0.0, t + ".d")
+            dy = dz
+            if "attn" in blk:
+                a, Pm, scale = blk["attn"], rec["Pm"], rec["scale"]
+                dO = self._buf(t + ".dO", M, Cc)
+                self._linear_bwd(rec["O"], dz, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc),
+                                 self.grads[a + "proj_out.weight"].view(Cc, Cc), self.grads[a + "proj_out.bias"], dO)
+                dPm, dS = self._buf(t + ".dPm", B, HW, HW), self._buf(t + ".dS", B, HW, HW)
+                self._mm(B, HW, HW, Cc, dO, (HW * Cc, Cc, 1), rec["v"], (HW * Cc, 1, Cc), dPm)
+                dv, dq, dk = (self._buf(t + ".d" + nm, M, Cc) for nm in "vqk")
+                self._mm(B, HW, Cc, HW, Pm, (HW * HW, 1, HW), dO, (HW * Cc, Cc, 1), dv)
+                _lib.check(L.nlc_softmax_rows(ctx, Pm.data_ptr(), dPm.data_ptr(), B * HW, HW, scale, dS.data_ptr(), _stream()))
+                self._mm(B, HW, Cc, HW, dS, (HW * HW, HW, 1), rec["k"], (HW * Cc, Cc, 1), dq)
+                self._mm(B, HW, Cc, HW, dS, (HW * HW, 1, HW), rec["q"], (HW * Cc, Cc, 1), dk)
+                dn = self._buf(t + ".dn", M, Cc)
+                first = True
+                for nm, dsrc in (("q", dq), ("k", dk), ("v", dv)):
+                    self._linear_bwd(rec["n"], dsrc, M, Cc, self.params[a + nm + ".weight"].view(Cc, Cc),
+                                     self.grads[a + nm + ".weight"].view(Cc, Cc), self.grads[a + nm + ".bias"], dn,
+                                     add=None if first else dn)
+                    first = False
+                dy = self._buf(t + ".dy", M, Cc)
+                dy.copy_(dz)
+                self._gn_bwd(rec["y"], dn, B, HW, a + "norm", 0, rec["stn"], dy, True)
+            # ResBlock: y = x + conv2(drop(swish(gn2(conv1(swish(gn1(x)))))))
+            da2 = self._buf(t + ".da2", M, Cc)
+            self._conv3_bwd(dy, rec["P2"], B, H, H, r + "conv2", 0, da2, 0.0, t + ".c2")
+            if rec["mask"] is not None:
+                da2.mul_(rec["mask"])
+            dc1 = self._buf(t + ".dc1", M, Cc)
+            self._gn_bwd(rec["c1"], da2, B, HW, r + "norm2", 1, rec["st2"], dc1, False)
+            da1 = self._buf(t + ".da1", M, Cc)
+            self._conv3_bwd(dc1, rec["P1"], B, H, H, r + "conv1", 0, da1, 0.0, t + ".c1")
+            dxin = self._buf(t + ".dx", M, Cc)
+            dxin.copy_(dy)
+            self._gn_bwd(rec["x"], da1, B, HW, r + "norm1", 1, rec["st1"], dxin, True)
+            dx = dxin
+        return loss, dist_hat
+
+    # ------------------------------------------------------------------ optimizer
+    def step(self, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, ema_rate=0.999):
+        """All-reduce the gradients over the ranks (mean), AdamW + EMA in one fused pass (nlc_adamw_ema_step)."""
+        rank, world = parallel.world()
+        if world > 1:
+            torch.distributed.all_reduce(self.grads.flat, op=torch.distributed.ReduceOp.SUM)
+        self.steps += 1
+        _lib.check(self._lib.nlc_adamw_ema_step(
+            self._ctx, self.params.flat.data_ptr(), self.grads.flat.data_ptr(), self.exp_avg.data_ptr(),
+            self.exp_avg_sq.data_ptr(), self.ema.data_ptr(), self.params.flat.numel(), lr, betas[0], betas[1], eps, weight_decay,
+            self.steps, ema_rate, 1.0 / world, _stream()))
+
+
+def train_step_native(model, sigma, scheduler, batch_x, t, noise, extra, eta1, eta2, lr, weight_decay=0.0, microbatch=None,
+                      **adam):
+    """One iteration of src/experiments.py:654-694 with nothing left to autograd: batch preparation kernel, frozen-UNet
+    `encode_scaled` on the tensor-core engine, `NativeSigmaModel.loss_and_grad`, fused AdamW + EMA.  Returns the loss."""
+    noisy_x, dist_real = prepare_batch(batch_x, t, noise, extra, eta1, eta2, scheduler.alphas_cumprod)
+    B = noisy_x.shape[0]
+    mb = microbatch or B
+    feats = [model.encode_scaled(noisy_x[i:i + mb], t[i:i + mb].to(noisy_x.device)).clone() for i in range(0, B, mb)]
+    loss, _ = sigma.loss_and_grad(torch.cat(feats), dist_real, nhwc=True)
+    sigma.step(lr, weight_decay=weight_decay, **adam)
+    return loss

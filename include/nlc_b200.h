@@ -175,6 +175,42 @@ size_t nlc_groupnorm_ws(int B, int HW, int C, int groups);
 int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, int C, int mode, float* y_f32,
                  int ld_y_f32, void* y_op, int ld_y_op, int op_dtype, void* stream);
 
+/* ---- The sigma-model's own forward / backward of the training step (src/experiments.py:683-691 leaves
+ * it to autograd over src/unet_ddim.py:439-529).  Activations are NHWC fp32 matrices [B*H*W, C]; every contraction is nlc_sgemm,
+ * the functions below are what sits between the GEMMs (csrc/sigma_train.cu; host side: nlc_b200/training.py NativeSigmaModel). */
+/* C[b] = A[b] B[b] (+ add[b]): strided batched fp32 GEMM on the CUDA cores.  A element (i,k) at A + b*sab + i*sai + k*sak, B
+ * element (k,j) at Bm + b*sbb + k*sbk + j*sbj, C[b] row-major [M,N] contiguous; `add` (same layout as C) or NULL. */
+int nlc_sgemm(nlc_ctx* ctx, int batch, int M, int N, int K, const float* A, long long sab, long long sai, long long sak,
+              const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm, const float* add, void* stream);
+/* x [B,H,W,C] -> patches [B*Ho*Wo, C*9] with column c*9 + kh*3 + kw (torch's weight.view(Cout, Cin*9) multiplies them);
+ * down 0: stride 1, zero padding 1; down 1: the reference's Downsample, F.pad(x,(0,1,0,1)) then stride 2 (src/unet_ddim.py:89-94).
+ * nlc_fold3x3 is the adjoint: dx = beta*dx + sum of the patch gradients that read each pixel. */
+int nlc_unfold3x3(nlc_ctx* ctx, const float* x, int B, int H, int W, int C, int down, float* patches, void* stream);
+int nlc_fold3x3(nlc_ctx* ctx, const float* d_patches, int B, int H, int W, int C, int down, float* dx, float beta, void* stream);
+/* GroupNorm(groups, eps) [+ swish when act = 1] in training: forward saves stats [B*groups][2] = (mean, rstd); backward writes
+ * (or, accumulate != 0, adds to) dx and ATOMICALLY accumulates dgamma / dbeta (zero them first). */
+int nlc_gn_train_fwd(nlc_ctx* ctx, const float* x, int B, int HW, int C, int groups, float eps, const float* gamma,
+                     const float* beta, int act, float* y, float* stats, void* stream);
+int nlc_gn_train_bwd(nlc_ctx* ctx, const float* x, const float* dy, int B, int HW, int C, int groups, const float* gamma,
+                     const float* beta, int act, const float* stats, float* dx, int accumulate, float* dgamma, float* dbeta,
+                     void* stream);
+/* dp == NULL: out = softmax(scale * s) over rows of length T; dp != NULL: s holds the probabilities p and
+ * out = scale * p * (dp - sum_j dp_j p_j), the gradient with respect to the unscaled logits. */
+int nlc_softmax_rows(nlc_ctx* ctx, const float* s, const float* dp, int rows, int T, float scale, float* out, void* stream);
+int nlc_bias_add(nlc_ctx* ctx, float* y, const float* bias, long long rows, int C, void* stream);      /* y[r,c] += bias[c] */
+int nlc_colsum(nlc_ctx* ctx, const float* x, long long rows, int C, float* out, void* stream);         /* out[c] = sum_r x[r,c] */
+int nlc_axpby(nlc_ctx* ctx, float a, const float* x, float b, const float* y /* or NULL */, float* out, long long n, void* stream);
+int nlc_permute_nhwc(nlc_ctx* ctx, const float* x, int B, int HW, int C, int to_nchw, float* y, void* stream);
+/* BatchNorm1d(F) in training mode followed by GELU(erf) on x [B,F]: dy == NULL forward (out = gelu(bn(x)), stats [F][2] =
+ * (batch mean, rstd) saved, running statistics updated with `momentum` and the unbiased variance when run_mean != NULL);
+ * dy != NULL backward (out = dx, dgamma[F], dbeta[F] written). */
+int nlc_bn1d_gelu_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int F, float eps, float momentum,
+                        const float* gamma, const float* beta, float* run_mean, float* run_var, float* stats, float* out,
+                        float* dgamma, float* dbeta, void* stream);
+/* dist_hat = r + 1 (src/experiments.py:689); loss = MSELoss (kind 0) | L1Loss (kind 1), mean reduction; dr = d loss / d r */
+int nlc_head_loss(nlc_ctx* ctx, const float* r, const float* target, int B, int kind, float* dist_hat, float* loss, float* dr,
+                  void* stream);
+
 /* ---- FID statistics on the device.  The reference goes through the third-party pytorch_fid package
  * after writing every sample as a PNG (src/experiments.py:210-226 fid_helper -> compute_statistics_of_path /
  * calculate_frechet_distance; image_sample.py:566,703; result_evaluater.py:24-27).  The InceptionV3 convolutions are

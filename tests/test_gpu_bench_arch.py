@@ -160,6 +160,21 @@ def test_c2_graph_replay_equals_eager_loop(c2_gold):
                                   return_log=False, sigma_pred_threshold=960, graph=graph, to_cpu=False)
         outs.append(out.clone())
     assert torch.equal(outs[0], outs[1])
+    # the captured timestep is kept on the experiment: a second call (other start, other noise) replays it from its first
+    # capturable step and still equals the eager loop; a changed host scalar (eta) is a different signature
+    assert len(exp._graph_cache) == 1
+    xT2 = xT.flip(0) * 0.9
+    for eta in (0.85, 0.5):
+        sch.eta = eta
+        outs = []
+        for graph in (False, True):
+            torch.cuda.manual_seed(12)
+            out, _ = exp.denoise_loop(shape=(4, 3, 64, 64), xT=xT2, style="pred", norm_eps=True, refine_prior_sigma=True,
+                                      return_log=False, sigma_pred_threshold=960, graph=graph, to_cpu=False)
+            outs.append(out.clone())
+        assert torch.equal(outs[0], outs[1]), eta
+    assert len(exp._graph_cache) == 2
+    exp.clear_graphs()
 
 
 # ------------------------------------------------------------------------------------------------------ networks
