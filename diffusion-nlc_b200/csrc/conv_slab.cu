@@ -241,6 +241,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                 }
             };
             if (p.resid) prefetch_resid(pix0_of(0), 32 * half);
+            // ... and the residual block of the NEXT unit is pulled into L2 now (its register fetches then cost an L2 hit,
+            // not a DRAM round trip per column chunk: profiles/r02r_ncu_summary.md, K 1152 with / without residual)
+            if (p.resid && unit + unit_step < sp.num_units) {
+                int nt2;
+                const int s2 = super_of(unit + unit_step, nt2);
+                const int n2 = s2 / sp.sb_per_img, hb2 = s2 - n2 * sp.sb_per_img;
+                if (n2 < p.B) {
+                    const int esz = p.resid16 ? 2 : 4;
+                    const int lines = (kSlabN * esz) >> 7;  // 128-byte lines per row of this unit's column range
+                    const char* base = reinterpret_cast<const char*>(p.resid) + static_cast<size_t>(nt2) * kSlabN * esz;
+                    for (int g = 0; g < kSlabG; ++g) {
+                        const size_t px = (static_cast<size_t>(n2) * p.Ho + (hb2 * kSlabG + g) * p.BH + bh0) * p.Wo + bw0;
+                        for (int i = lane + 32 * half; i < 32 * lines; i += 32 * (kEpiWarps / 4))
+                            prefetch_l2(base + (px + i / lines) * static_cast<size_t>(p.ld_resid) * esz + ((i % lines) << 7));
+                    }
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after_sync();
 #pragma unroll 1

@@ -379,6 +379,24 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 }
             };
             if (pre) prefetch_resid(32 * half);
+            // ... and the residual block of the NEXT tile of this CTA is pulled into L2 now, a whole tile ahead (conv_slab.cu)
+            if (pre && !p.out_head_split && unit + unit_step < p.num_tiles) {
+                const int u2 = unit + unit_step;
+                const int nt2 = u2 / p.num_m_units;
+                const int mt2 = CTA2 ? 2 * (u2 - nt2 * p.num_m_units) + static_cast<int>(rank) : u2 - nt2 * p.num_m_units;
+                const int tn2 = mt2 / tiles_per_img;
+                const int rem2 = mt2 - tn2 * tiles_per_img;
+                const int th2 = rem2 / p.tiles_w, tw2 = rem2 - th2 * p.tiles_w;
+                const int n2 = tn2 * p.BN + bn0;
+                if (n2 < p.B) {
+                    const size_t px = (static_cast<size_t>(n2) * p.Ho + th2 * p.BH + bh0) * p.Wo + tw2 * p.BW + bw0;
+                    const int esz = p.resid16 ? 2 : 4;
+                    const int lines = (BLOCK_N * esz) >> 7;
+                    const char* base = reinterpret_cast<const char*>(p.resid) + static_cast<size_t>(nt2) * BLOCK_N * esz;
+                    for (int i = lane + 32 * half; i < 32 * lines; i += 32 * (kEpiWarps / 4))
+                        prefetch_l2(base + (px + i / lines) * static_cast<size_t>(p.ld_resid) * esz + ((i % lines) << 7));
+                }
+            }
             // X3: the K chunks arrive one accumulator at a time and are summed here, in registers (round to nearest)
             constexpr int kNJ = X3 ? BLOCK_N / (32 * (kEpiWarps / 4)) : 1;  // column chunks owned by this warp
             float accr[kNJ][32];

@@ -543,6 +543,76 @@ __global__ void __launch_bounds__(kGnSmallThreads)
     }
 }
 
+// The same with one WARP per (sample, group) for <= 1024 values per group (the 4x4 / 8x8 levels of the c2 / c3 networks):
+// shuffle reductions only, eight groups per CTA.  The block version above spends its time in per-CTA overhead there
+// (8192 CTAs of 256 values each: 21 us per launch in profiles/r02r_launches_c2_summary.md, 4.4 % of a c2 step).
+template <bool TF32>
+__global__ void __launch_bounds__(256)
+    gn_small_warp_kernel(const float* __restrict__ x, int ld_x, int HW, int C, int groups, int n_pairs, float eps,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
+                         const float* __restrict__ shift, int ld_ss, int do_silu, void* __restrict__ y, int ld_y, int rnd) {
+    const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (pair >= n_pairs) return;
+    const int lane = threadIdx.x & 31;
+    const int n = pair / groups, g = pair - n * groups;
+    const int cpg = C / groups, cpg4 = cpg >> 2;
+    const int total4 = HW * cpg4;
+    const float* xb = x + static_cast<size_t>(n) * HW * ld_x + g * cpg;
+    float4 v[kGnSmallVec];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < kGnSmallVec; ++u) {
+        const int i = lane + u * 32;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total4) {
+            const int pix = i / cpg4, c4 = i - pix * cpg4;
+            v[u] = __ldg(reinterpret_cast<const float4*>(xb + static_cast<size_t>(pix) * ld_x + 4 * c4));
+            s += (v[u].x + v[u].y) + (v[u].z + v[u].w);
+        }
+    }
+    const float cnt = static_cast<float>(total4) * 4.0f;
+    const float mean = warp_sum(s) / cnt;
+    float m2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < kGnSmallVec; ++u) {
+        if (lane + u * 32 < total4) {
+            const float a = v[u].x - mean, b = v[u].y - mean, c = v[u].z - mean, d = v[u].w - mean;
+            m2 += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(m2) / cnt + eps);
+#pragma unroll
+    for (int u = 0; u < kGnSmallVec; ++u) {
+        const int i = lane + u * 32;
+        if (i < total4) {
+            const int pix = i / cpg4, c4 = i - pix * cpg4;
+            const int c = g * cpg + 4 * c4;
+            const float in[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+            float f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a = rstd * (gamma ? gamma[c + k] : 1.f);
+                float b = (beta ? beta[c + k] : 0.f) - mean * a;
+                if (scale) {
+                    const float sc = 1.f + scale[static_cast<size_t>(n) * ld_ss + c + k];
+                    a *= sc;
+                    b = b * sc + shift[static_cast<size_t>(n) * ld_ss + c + k];
+                }
+                f[k] = fmaf(in[k], a, b);
+                if (do_silu) f[k] = silu(f[k]);
+            }
+            const size_t off = (static_cast<size_t>(n) * HW + pix) * ld_y + c;
+            if (TF32) {
+                *reinterpret_cast<float4*>(static_cast<float*>(y) + off) =
+                    make_float4(op_f32(f[0], rnd), op_f32(f[1], rnd), op_f32(f[2], rnd), op_f32(f[3], rnd));
+            } else {
+                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + off) =
+                    make_uint2(pack_op16x2(f[0], f[1], rnd), pack_op16x2(f[2], f[3], rnd));
+            }
+        }
+    }
+}
+
 static int pick_chunks(int B, int HW, int sm_count, int min_rows) {
     int chunks = 1;
     while (chunks < kGnMaxChunks && HW % (chunks * 2) == 0 && HW / (chunks * 2) >= min_rows &&
@@ -603,6 +673,17 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const void* x_, int x_is_op, int ld_x
     const int HW = H * W;
     float* mr = workspace + static_cast<size_t>(B) * kGnMaxChunks * groups * 3;  // [B][groups][2]
 
+    if (!stats && resample == 0 && HW * ((C / groups) / 4) <= 32 * kGnSmallVec) {  // <= 1024 values per group: a warp each
+        const int n_pairs = B * groups;
+        if (!dtype_is16(op_dtype))
+            gn_small_warp_kernel<true><<<(n_pairs + 7) / 8, 256, 0, stream>>>(x, ld_x, HW, C, groups, n_pairs, eps, gamma, beta, scale,
+                                                                              shift, ld_ss, do_silu, y_op, ld_y, rnd);
+        else
+            gn_small_warp_kernel<false><<<(n_pairs + 7) / 8, 256, 0, stream>>>(x, ld_x, HW, C, groups, n_pairs, eps, gamma, beta,
+                                                                               scale, shift, ld_ss, do_silu, y_op, ld_y, rnd);
+        NLC_CHECK_LAUNCH();
+        return NLC_OK;
+    }
     if (!stats && resample == 0 && HW * ((C / groups) / 4) <= kGnSmallThreads * kGnSmallVec) {
         if (!dtype_is16(op_dtype))
             gn_small_kernel<true><<<dim3(groups, B), kGnSmallThreads, 0, stream>>>(

@@ -79,6 +79,11 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// Pull one 128-byte line into L2 (no register, no dependency): the epilogues use it for the residual rows of the NEXT tile.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -120,11 +120,12 @@ def test_train_step_end_to_end():
 
 # ------------------------------------------------------------------------------------------------------------------------
 # The sigma-model's own forward / backward, natively (training.NativeSigmaModel, csrc/sigma_train.cu)
-def _check_digest(t, ref, tol, what):
-    """(the key bias of an attention block has an exactly zero gradient - softmax is invariant to a per-query constant - and
-    both sides hold ~1e-9 of round-off there: the scale has an absolute floor)"""
+def _check_digest(t, ref, tol, what, floor=0.0):
+    """`floor`: absolute per-tensor scale below which a tensor is round-off.  Several gradients of this network are EXACTLY
+    zero in exact arithmetic - the key bias of an attention block (softmax ignores a per-query constant), every bias in
+    front of the training-mode BatchNorm (which subtracts the batch mean) - and hold ~1e-8 of noise on both sides."""
     t = t.detach().double().reshape(-1).cpu()
-    scale = max(float(ref["norm"]), 1e-4)
+    scale = max(float(ref["norm"]), floor)
     assert abs(float(t.norm()) - float(ref["norm"])) <= tol * scale, what
     assert (t[:32] - ref["head"]).abs().max() <= tol * max(float(ref["head"].abs().max()), scale / t.numel() ** 0.5), what
     if ref["full"] is not None:
@@ -146,11 +147,19 @@ def test_native_sigma_model_training_iteration_matches_the_reference(golden_dir)
     assert (dist_hat.cpu() - g["dist_hat"].reshape(-1)).abs().max() <= 1e-5 * g["dist_hat"].abs().max()
     assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
     assert set(m.grads.names) == set(g["grads"])
+    gmax = max(float(v["norm"]) for v in g["grads"].values())
     for n in m.grads.names:
-        _check_digest(m.grads[n], g["grads"][n], 2e-4, ("grad", n))
+        _check_digest(m.grads[n], g["grads"][n], 2e-4, ("grad", n), floor=1e-3 * gmax)
     m.step(1e-3, weight_decay=0.01, ema_rate=0.999)
     ema = m.ema_state_dict()
+    lr = 1e-3
     for n in m.params.names:
+        if float(g["grads"][n]["norm"]) < 1e-3 * gmax:
+            # an exactly-zero gradient is round-off on both sides, and AdamW turns round-off into a full +-lr step per entry
+            # (m / sqrt(v) = +-1): such a tensor may differ from the reference's by up to 2 lr per entry, and no more
+            ref = g["new_params"][n]
+            assert ref["full"] is not None and (m.params[n].cpu().reshape(-1) - ref["full"]).abs().max() <= 2.01 * lr, n
+            continue
         _check_digest(m.params[n], g["new_params"][n], 1e-5, ("param", n))
         _check_digest(ema[n], g["ema"][n], 1e-5, ("ema", n))
     # BatchNorm running statistics moved towards the batch statistics (momentum 0.1), exactly as torch does
@@ -202,6 +211,7 @@ def test_native_sigma_model_gradients_against_autograd(name, B, loss):
     got, dh = m.loss_and_grad(feat.permute(0, 2, 3, 1).contiguous().to(dev), target.to(dev), nhwc=True)
     assert abs(got.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
     assert (dh.cpu() - dist_hat.detach().reshape(-1)).abs().max() <= 1e-5
+    gmax = max(float(params[n].grad.norm()) for n in names)
     for n in names:
         a, b = m.grads[n].cpu().double(), params[n].grad.double()
-        assert (a - b).norm() <= 3e-4 * b.norm() + 1e-7, (n, float((a - b).norm()), float(b.norm()))
+        assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
