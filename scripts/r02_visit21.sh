@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out; mkdir -p $O
+timeout 1500 python -m pytest tests/test_gpu_ops.py tests/test_gpu_nets.py tests/test_gpu_adm.py tests/test_gpu_edm.py tests/test_gpu_bench_arch.py tests/test_gpu_constrained.py tests/test_gpu_canaries.py tests/test_gpu_fid.py -q > $O/r02u_pytest.log 2>&1; echo "pytest rc=$?"; grep -n "passed\|failed\|FAILED" $O/r02u_pytest.log | tail -8
+timeout 300 python scripts/epi_ablate.py 1 > $O/r02u_epi_ablate.log 2>&1; echo "epi rc=$?"; head -17 $O/r02u_epi_ablate.log
+timeout 600 python scripts/step_profile.py c2 256 fp16 > $O/r02u_step_c2_fp16.log 2>&1; head -30 $O/r02u_step_c2_fp16.log
+timeout 600 python scripts/step_profile.py adm256 16 fp16 > $O/r02u_step_adm_fp16.log 2>&1; head -12 $O/r02u_step_adm_fp16.log
