@@ -77,6 +77,28 @@ __global__ void __launch_bounds__(256) transpose_heads_kernel(const T* __restric
     for (int r = ty; r < 32; r += 8) dst[static_cast<size_t>(c0 + r) * Tn + t0 + tx] = tile[tx][r];
 }
 
+// 16-bit elements: 64 x 64 tiles moved as 32-bit pairs, so that every global access instruction of a warp covers a full
+// 128-byte line on both sides (the 32 x 32 version above moves 64-byte half lines: 1.6 TB/s in
+// profiles/r02r_launches_c2_summary.md).  Needs Tn % 64 == 0 and dh % 64 == 0.
+__global__ void __launch_bounds__(256) transpose_heads16_kernel(const uint16_t* __restrict__ v, int ld, int head_stride, int Tn,
+                                                                 int heads, int dh, uint16_t* __restrict__ vt) {
+    __shared__ uint16_t tile[64][64 + 2];
+    const int bh = blockIdx.z, b = bh / heads, h = bh - b * heads;
+    const uint16_t* src = v + static_cast<size_t>(b) * Tn * ld + static_cast<size_t>(h) * head_stride;
+    uint16_t* dst = vt + static_cast<size_t>(bh) * dh * Tn;
+    const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 64; r += 8) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(src + static_cast<size_t>(t0 + r) * ld + c0 + 2 * tx);
+        tile[r][2 * tx] = static_cast<uint16_t>(w & 0xffffu), tile[r][2 * tx + 1] = static_cast<uint16_t>(w >> 16);
+    }
+    __syncthreads();
+    for (int r = ty; r < 64; r += 8) {
+        const uint32_t w = static_cast<uint32_t>(tile[2 * tx][r]) | (static_cast<uint32_t>(tile[2 * tx + 1][r]) << 16);
+        *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(c0 + r) * Tn + t0 + 2 * tx) = w;
+    }
+}
+
 // ---------------------------------------------------------------- small-T fused attention
 // one CTA per (image, head); K and V rows live in shared memory as fp32 with an odd pitch.
 template <typename T>
@@ -229,6 +251,9 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
         if (f32c)
             transpose_heads_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(q8 + v_off * esz), ld,
                                                                     head_stride, T, heads, dh, static_cast<float*>(VT));
+        else if (T % 64 == 0 && dh % 64 == 0 && ld % 2 == 0 && v_off % 2 == 0 && head_stride % 2 == 0)
+            transpose_heads16_kernel<<<dim3(T / 64, dh / 64, static_cast<unsigned>(bh)), 256, 0, stream>>>(
+                reinterpret_cast<const uint16_t*>(q8 + v_off * esz), ld, head_stride, T, heads, dh, static_cast<uint16_t*>(VT));
         else
             transpose_heads_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
                 reinterpret_cast<const __nv_bfloat16*>(q8 + v_off * esz), ld, head_stride, T, heads, dh,

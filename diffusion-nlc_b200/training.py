@@ -162,6 +162,10 @@ class NativeSigmaModel:
         self._lib, self._bufs = _lib.lib(), {}
         self._ctx = _lib.ctx(self.device.index if self.device.index is not None else torch.cuda.current_device())
         self.training = True
+        import os
+        self.use_tc = os.environ.get("NLC_TRAIN_TC", "1") != "0"
+        self.use_graph = os.environ.get("NLC_GRAPH", "1") != "0"
+        self._static = {}
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, sd, strict=True):
@@ -195,6 +199,7 @@ class NativeSigmaModel:
         self.exp_avg_sq = torch.zeros_like(self.params.flat)
         self.ema = self.params.flat.clone()
         self.steps = 0
+        self._static = {}  # (captured passes point at the previous parameter buffers)
         return self
 
     def state_dict(self):
@@ -225,19 +230,53 @@ class NativeSigmaModel:
         _lib.check(self._lib.nlc_sgemm(self._ctx, batch, M, N, K, A.data_ptr(), sa[0], sa[1], sa[2], B.data_ptr(), sb[0], sb[1],
                                        sb[2], out.data_ptr(), C.c_void_p(add.data_ptr()) if add is not None else None, _stream()))
 
+    # The large contractions (the 3x3 convolutions' forward / data-gradient / weight-gradient GEMMs: 98 % of the sigma-model's
+    # FLOPs) go to the tensor cores in the fp32-accurate mode of nlc_conv_tc (NLC_F32X3: three tf32 split products, per-chunk
+    # accumulators): out[M, N] = A[M, K] Bt[N, K]^T with both operands K-major, M % 128 == 0, N % 64 == 0, K % 32 == 0.  The
+    # CUDA-core nlc_sgemm serves the rest (attention products, the head, shapes that do not tile) - and everything when
+    # NLC_TRAIN_TC=0.
+    TC_MIN_FLOP = 1 << 28
+
+    def _tc_ok(self, M, N, K):
+        return self.use_tc and M % 128 == 0 and N % 64 == 0 and K % 32 == 0 and 2 * M * N * K >= self.TC_MIN_FLOP
+
+    def _mm_tc(self, M, N, K, A, Bt, out, bias=None):
+        """out[M, N] = A[M, K] Bt[N, K]^T (+ bias[N]) on tcgen05, fp32-accurate (A, Bt, out contiguous fp32)."""
+        from . import ops
+        from ._lib import NLC_F32X3
+        ops.conv_tc([ops.Act(A.view(1, M // 128, 128, K))], [(0, 0, 0, 0, K)], Bt, N, 1, M // 128, 128, NLC_F32X3, bias=bias,
+                    out_f32=ops.Act(out.view(1, M // 128, 128, N)))
+
+    def _transpose(self, x, rows, cols, tag):
+        """[rows, cols] -> [cols, rows] (contiguous fp32 scratch)."""
+        y = self._buf(tag, cols, rows)
+        _lib.check(self._lib.nlc_permute_nhwc(self._ctx, x.data_ptr(), 1, rows, cols, 1, y.data_ptr(), _stream()))
+        return y
+
     def _linear(self, x, rows, cin, w, b, out):
         """out[rows, cout] = x[rows, cin] w[cout, cin]^T + b"""
         cout = w.shape[0]
+        if self._tc_ok(rows, cout, cin):
+            return self._mm_tc(rows, cout, cin, x, w, out, bias=b)
         self._mm(1, rows, cout, cin, x, (0, cin, 1), w, (0, 1, cin), out)
         _lib.check(self._lib.nlc_bias_add(self._ctx, out.data_ptr(), b.data_ptr(), rows, cout, _stream()))
 
     def _linear_bwd(self, x, dy, rows, cin, w, dw, db, dx, add=None):
         """dw[cout, cin] = dy^T x; db = column sums of dy; dx[rows, cin] = dy w (+ add)"""
         cout = w.shape[0]
-        self._mm(1, cout, cin, rows, dy, (0, 1, cout), x, (0, cin, 1), dw)
         _lib.check(self._lib.nlc_colsum(self._ctx, dy.data_ptr(), rows, cout, db.data_ptr(), _stream()))
+        if self._tc_ok(cout, cin, rows):
+            dyt = self._transpose(dy, rows, cout, "tc.dyt")     # [cout, rows]
+            xt = self._transpose(x, rows, cin, "tc.xt")         # [cin, rows]
+            self._mm_tc(cout, cin, rows, dyt, xt, dw)
+        else:
+            self._mm(1, cout, cin, rows, dy, (0, 1, cout), x, (0, cin, 1), dw)
         if dx is not None:
-            self._mm(1, rows, cin, cout, dy, (0, cout, 1), w, (0, cin, 1), dx, add=add)
+            if self._tc_ok(rows, cin, cout) and add is None:
+                wt = self._transpose(w, cout, cin, "tc.wt")     # [cin, cout]
+                self._mm_tc(rows, cin, cout, dy, wt, dx)
+            else:
+                self._mm(1, rows, cin, cout, dy, (0, cout, 1), w, (0, cin, 1), dx, add=add)
 
     def _gn(self, x, B, HW, name, act, y, stats):
         _lib.check(self._lib.nlc_gn_train_fwd(self._ctx, x.data_ptr(), B, HW, self.C, self.GROUPS, self.GN_EPS,
@@ -279,11 +318,35 @@ class NativeSigmaModel:
     def loss_and_grad(self, feat, dist_real, nhwc=False):
         """feat: encoder feature [B, C, dim, dim] (the reference's layout) or NHWC [B, dim, dim, C] with nhwc=True;
         dist_real: [B] (or [B,1,1,1]) targets.  Training-mode forward, loss, backward: fills `grads`, updates the BatchNorm
-        running statistics, returns (loss [1], dist_hat [B]) on the device."""
+        running statistics, returns (loss [1], dist_hat [B]) on the device (plan buffers: valid until the next call).
+        The ~130 launches of the pass are captured in a CUDA graph after the first call at a batch size (NLC_GRAPH=0:
+        always eager) - at 4x4 .. 8x8 pixels the pass is launch-bound otherwise."""
+        B = feat.shape[0]
+        key = (B, bool(nhwc))
+        st = self._static.get(key)
+        if st is None:
+            st = dict(feat=torch.empty(tuple(feat.shape), device=self.device), target=torch.empty(B, device=self.device),
+                      graph=None)
+            self._static[key] = st
+        st["feat"].copy_(feat)
+        st["target"].copy_(dist_real.reshape(B))
+        if st["graph"] is not None:
+            st["graph"].replay()
+        else:
+            out = self._loss_and_grad(st["feat"], st["target"], nhwc)
+            st["out"] = out
+            if self.use_graph and self.device.type == "cuda":
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    st["out"] = self._loss_and_grad(st["feat"], st["target"], nhwc)
+                st["graph"] = g
+        self.num_batches_tracked += 1
+        return st["out"]
+
+    def _loss_and_grad(self, feat, target, nhwc):
         L, ctx, Cc = self._lib, self._ctx, self.C
         B, dim = feat.shape[0], self.dim
-        feat = feat.to(self.device, torch.float32).contiguous()
-        target = dist_real.to(self.device, torch.float32).reshape(B).contiguous()
         self.grads.flat.zero_()
         x = self._buf("in", B * dim * dim, Cc)
         if nhwc:
@@ -340,7 +403,6 @@ class NativeSigmaModel:
                                          self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
                                          self.run_mean.data_ptr(), self.run_var.data_ptr(), stb.data_ptr(), g.data_ptr(), None,
                                          None, _stream()))
-        self.num_batches_tracked += 1
         r = self._buf("r", B, 1)
         self._linear(g, B, F1, self.params["final_mlp.weight"], self.params["final_mlp.bias"], r)
         dist_hat, loss, dr = self._buf("dist_hat", B), self._buf("loss", 1), self._buf("dr", B, 1)
