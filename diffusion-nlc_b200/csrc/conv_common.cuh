@@ -21,6 +21,8 @@ struct ConvSegDev {
 struct ConvKParams {
     CUtensorMap mapA[NLC_MAX_SRC];
     CUtensorMap mapB;
+    CUtensorMap mapOut;  // tma_epi: the 16-bit output as (channel, wo, ho, n), box = 32 channels x one warp's 32 pixels
+    CUtensorMap mapRes;  // tma_epi with a residual: the 16-bit residual tensor, same box
     int B, Ho, Wo, stride;
     int BW, BH, BN;
     int tiles_w, tiles_h, tiles_n;
@@ -46,9 +48,26 @@ struct ConvKParams {
     int out_up;      // 0, or 1 + 2a + b: output pixel (n,ho,wo) is written at (n, 2ho+a, 2wo+b) of a [B,2Ho,2Wo,.] tensor
     int w_batched;
     int f16;         // 16-bit operands are fp16 (kind::f16 with the f16 format bits), not bf16
+    int tma_epi;     // 16-bit epilogue through TMA (epi_tma_* below): output by tensor store, residual block by tensor load
     float* stats;    // GroupNorm partials of the fp32 output: [pixel/32][stats_nblk][2] = (mean, M2) over 32 px x 4 ch
     int stats_nblk;
 };
+
+// ---- 16-bit epilogue through TMA (ConvKParams.tma_epi).  A warp's 32 pixels x 32 channels are one box of the output's
+// tensor map (the M tile's brick order IS the box's traversal order), 64 bytes per pixel, staged in shared memory as
+// [32][64 B] with SWIZZLE_64B (16-byte chunk j of row r at chunk j ^ ((r >> 1) & 3): lanes 0..7 cover all eight 16-byte bank
+// groups, so the row-per-lane 128-bit accesses are conflict-free).  Against the LSU path (fp32 staging block: 8 STS + 8 LDS
+// + 4 STG per chunk, and 4 LDG + 8 STS + 8 LDS for a residual) a chunk costs 4 STS + one tensor store, and 4 LDS + one
+// tensor load for the residual; rows of an image past the batch are clipped / zero-filled by the TMA unit.
+constexpr int kEpiTmaBlockBytes = 32 * 64;
+__device__ __forceinline__ uint32_t epi_swz64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+
+// box of one epilogue warp (32 consecutive rows of the (BN, BH, BW) brick) in (wo, ho, n)
+inline void epi_tma_box(int BW, int BH, int* bw, int* bh, int* bn) {
+    *bw = BW < 32 ? BW : 32;
+    *bh = BH < 32 / *bw ? BH : 32 / *bw;
+    *bn = 32 / (*bw * *bh);
+}
 
 // GroupNorm statistics of the tile the epilogue holds in registers, so that the consumer's GroupNorm never re-reads
 // the tensor for them.  One warp = 32 consecutive pixels, f[] = 32 consecutive channels of this lane's pixel.

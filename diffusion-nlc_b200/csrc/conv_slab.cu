@@ -20,12 +20,15 @@
 
 namespace nlc {
 
+int epi_tma_setup(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p);  // conv_tc.cu
+
 constexpr int kSlabN = 128;          // accumulator width (output channels per unit)
 constexpr int kSlabG = 2;            // M tiles per CTA
 constexpr int kSlabStages = 3;       // slab ring
 constexpr int kSlabWStages = 6;      // weight-tile ring
 constexpr int kSlabWBytes = (kSlabN / 2) * kChunkBytes;  // this CTA's half of a weight tile: 8 KB
-constexpr int kSlabBarBytes = 256;
+constexpr int kSlabBarBytes = 512;    // 22 mbarriers, the TMEM slot, kEpiWarps residual-block barriers (tma_epi); 512: the
+                                      // staging blocks behind it stay aligned for SWIZZLE_64B tensor loads / stores
 constexpr int kSlabEpiBytes = kEpiWarps * 32 * 32 * 4;
 constexpr int kSlabTmemCols = 2 * kSlabG * kSlabN;  // 512
 constexpr int kSlabMaxSteps = 64;    // slabs per unit: 3 per 64-channel chunk (+ 1 per chunk of a fused 1x1 shortcut)
@@ -49,8 +52,9 @@ struct SlabParams {
     const SlabStep* steps;  // device array [nstep]
 };
 
-template <int MODE>
+template <int MODE, int TEPI = 0>
 __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_constant__ SlabParams sp) {
+    static_assert(TEPI == 0 || MODE == 0, "the 16-bit-only epilogues (1 TMA, 2 256-bit accesses) serve the 16-bit operand modes");
     constexpr bool TF32 = MODE != 0;
     const ConvKParams& p = sp.k;
     const uint32_t rank = cluster_ctarank();
@@ -69,6 +73,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
     uint64_t* tfull = w_empty + kSlabWStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rbar = tempty + 4;  // [kEpiWarps]
     float* stg_base = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kSlabBarBytes);
 
     const int warp = threadIdx.x >> 5;
@@ -82,6 +87,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
         for (int s = 0; s < kSlabStages; ++s) mbar_init(&s_full[s], 1), mbar_init(&s_empty[s], 1);
         for (int s = 0; s < kSlabWStages; ++s) mbar_init(&w_full[s], 1), mbar_init(&w_empty[s], 1);
         for (int a = 0; a < 2; ++a) mbar_init(&tfull[a], 1), mbar_init(&tempty[a], 2 * kEpiWarps);
+        for (int w = 0; w < kEpiWarps; ++w) mbar_init(&rbar[w], 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc_pair<kSlabTmemCols>(tmem_slot);
@@ -195,6 +201,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         float* stg = stg_base + (warp - 2) * 1024;
+        uint8_t* ostg = reinterpret_cast<uint8_t*>(stg);     // tma_epi (conv_common.cuh): 16-bit output block ...
+        uint8_t* rstg = ostg + kEpiTmaBlockBytes;            // ... and 16-bit residual block of this warp
+        uint64_t* my_rbar = &rbar[warp - 2];
+        uint32_t rphase = 0;
+        constexpr bool tma_epi = TEPI == 1;
         const int brick = p.BW * p.BH;  // = 128: one M tile is BH whole image rows
         const int row0 = quad * 32;
         const int bh0 = row0 / p.BW;
@@ -240,7 +251,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                         rpre[it] = __ldg(reinterpret_cast<const float4*>(rp + static_cast<size_t>(r) * p.ld_resid) + sub_c4);
                 }
             };
-            if (p.resid) prefetch_resid(pix0_of(0), 32 * half);
+            const int ho_u = hb * kSlabG * p.BH + bh0;  // first image row of this warp's pixels in M tile 0 of the unit
+            if (p.resid && TEPI == 0) prefetch_resid(pix0_of(0), 32 * half);
+            // TEPI 2: the lane's own 64 residual bytes of the next chunk, two 256-bit loads
+            uint32_t rq[2][8];
+            auto fetch_resid256 = [&](size_t pix_base, int c_next) {
+                if (valid) {
+                    const __nv_bfloat16* rrow = reinterpret_cast<const __nv_bfloat16*>(p.resid) +
+                                                (pix_base + lane) * p.ld_resid + n_tile * kSlabN + c_next;
+                    ldg256(rrow, rq[0]);
+                    ldg256(rrow + 16, rq[1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rq[0][i] = rq[1][i] = 0u;
+                }
+            };
+            if (TEPI == 2 && p.resid) fetch_resid256(pix0_of(0), 32 * half);
+            if (p.resid && tma_epi && lane == 0) {
+                mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                tma_load_4d(rstg, &p.mapRes, my_rbar, n_tile * kSlabN + 32 * half, bw0, ho_u, n);
+            }
             // ... and the residual block of the NEXT unit is pulled into L2 now (its register fetches then cost an L2 hit,
             // not a DRAM round trip per column chunk: profiles/r02r_ncu_summary.md, K 1152 with / without residual)
             if (p.resid && unit + unit_step < sp.num_units) {
@@ -266,6 +296,103 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                 const size_t stat_blk = pix0 >> 5;
                 const uint32_t taddr =
                     tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (acc * kSlabG + g) * kSlabN;
+                if constexpr (TEPI != 0) {
+                    const int ho_g = ho_u + g * p.BH;
+#pragma unroll 1
+                    for (int c = 32 * half; c < kSlabN; c += 32 * (kEpiWarps / 4)) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + c, v);
+                        const int col0 = n_tile * kSlabN + c;
+                        uint4 rr[4];
+                        if (p.resid) {
+                            if constexpr (TEPI == 1) {
+                                mbar_wait(my_rbar, rphase);
+                                rphase ^= 1;
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rstg + epi_swz64(lane, j));
+                                __syncwarp();
+                                if (lane == 0) {  // next block: the next column chunk, or the first one of the unit's next M tile
+                                    if (c + 32 * (kEpiWarps / 4) < kSlabN) {
+                                        mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                                        tma_load_4d(rstg, &p.mapRes, my_rbar, col0 + 32 * (kEpiWarps / 4), bw0, ho_g, n);
+                                    } else if (g + 1 < kSlabG) {
+                                        mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                                        tma_load_4d(rstg, &p.mapRes, my_rbar, n_tile * kSlabN + 32 * half, bw0, ho_g + p.BH, n);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    rr[j] = make_uint4(rq[j >> 1][4 * (j & 1)], rq[j >> 1][4 * (j & 1) + 1],
+                                                       rq[j >> 1][4 * (j & 1) + 2], rq[j >> 1][4 * (j & 1) + 3]);
+                                if (c + 32 * (kEpiWarps / 4) < kSlabN)
+                                    fetch_resid256(pix0, c + 32 * (kEpiWarps / 4));
+                                else if (g + 1 < kSlabG)
+                                    fetch_resid256(pix0_of(g + 1), 32 * half);
+                            }
+                        }
+                        tmem_ld_wait();
+                        float f[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                        if (p.bias) {
+                            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 t = __ldg(b4 + i);
+                                f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                            }
+                        }
+                        if (p.rowvec && valid) {
+                            const float4* b4 =
+                                reinterpret_cast<const float4*>(p.rowvec + static_cast<size_t>(n) * p.ld_rowvec + col0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 t = __ldg(b4 + i);
+                                f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                            }
+                        }
+                        if (p.resid) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 a, b;
+                                unpack_op16x8(rr[j], p.f16, a, b);
+                                f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += a.z, f[8 * j + 3] += a.w;
+                                f[8 * j + 4] += b.x, f[8 * j + 5] += b.y, f[8 * j + 6] += b.z, f[8 * j + 7] += b.w;
+                            }
+                        }
+                        if (p.out_scale != 1.0f) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
+                        }
+                        if (p.stats && valid) gn_partials(f, lane, p.stats + (stat_blk * p.stats_nblk + (col0 >> 2)) * 2);
+                        if constexpr (TEPI == 1) {
+                            if (lane == 0) bulk_wait_group_read0();  // the previous tensor store has read the staging block
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<uint4*>(ostg + epi_swz64(lane, j)) = make_uint4(
+                                    pack_op16x2(f[8 * j], f[8 * j + 1], p.f16), pack_op16x2(f[8 * j + 2], f[8 * j + 3], p.f16),
+                                    pack_op16x2(f[8 * j + 4], f[8 * j + 5], p.f16), pack_op16x2(f[8 * j + 6], f[8 * j + 7], p.f16));
+                            fence_proxy_async_smem();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_4d(&p.mapOut, ostg, col0, bw0, ho_g, n);
+                                bulk_commit_group();
+                            }
+                        } else if (valid) {
+                            __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out_op) + (pix0 + lane) * p.ld_out_op + col0;
+#pragma unroll
+                            for (int h2 = 0; h2 < 2; ++h2) {
+                                uint32_t w8[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) w8[i] = pack_op16x2(f[16 * h2 + 2 * i], f[16 * h2 + 2 * i + 1], p.f16);
+                                stg256(orow + 16 * h2, w8);
+                            }
+                        }
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int c = 32 * half; c < kSlabN; c += 32 * (kEpiWarps / 4)) {
                     uint32_t v[32];
@@ -383,6 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
+        if (TEPI == 1 && lane == 0) bulk_wait_group0();  // this warp's tensor stores are complete before the CTA retires
     }
 
     tc_fence_before_sync();
@@ -512,13 +640,17 @@ int launch_conv_slab(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p, int c
     if (rc != NLC_OK) return rc;
     sp.nstep = n;
     sp.nstep3 = 3 * (cin / chunk);
+    rc = epi_tma_setup(ctx, d, p);  // (the geometry above is final: BW = W, BH = 128 / W, BN = 1)
+    if (rc != NLC_OK) return rc;
     sp.k = p;
 
-    static PerDeviceFlag configured[2];
-    auto kern = tf32 ? conv_slab_kernel<1> : conv_slab_kernel<0>;
-    if (!configured[tf32 ? 1 : 0][ctx->device]) {
+    static PerDeviceFlag configured[4];
+    const int which = tf32 ? 1 : (p.tma_epi ? 1 + p.tma_epi : 0);
+    auto kern = tf32 ? conv_slab_kernel<1>
+                     : (p.tma_epi == 1 ? conv_slab_kernel<0, 1> : (p.tma_epi == 2 ? conv_slab_kernel<0, 2> : conv_slab_kernel<0>));
+    if (!configured[which][ctx->device]) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        configured[tf32 ? 1 : 0][ctx->device] = true;
+        configured[which][ctx->device] = true;
     }
     const int pairs = sp.num_units < ctx->sm_count / 2 ? sp.num_units : ctx->sm_count / 2;
     cudaLaunchConfig_t cfg;

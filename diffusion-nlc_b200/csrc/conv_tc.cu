@@ -41,14 +41,19 @@ struct ConvCfg {
         X3 ? (BLOCK_N == 128 ? 3 : 4)
            : (CTA2 ? (BLOCK_N == 256 ? 6 : 8) : ((BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8)));
     static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: power of two >= 32
-    static constexpr int kBarBytes = ((3 * kStages + 4) * 8 + 16 + 127) / 128 * 128;
+    // mbarriers (ring, accumulators), TMEM slot, one residual-block barrier per epilogue warp (tma_epi); rounded to 512 so
+    // that the epilogue staging blocks behind it are aligned for SWIZZLE_64B tensor loads / stores
+    static constexpr int kBarBytes = ((3 * kStages + 4) * 8 + 16 + 8 * kEpiWarps + 511) / 512 * 512;
     static constexpr int kEpiBytes = kEpiWarps * 32 * 32 * 4;  // one 32x32 fp32 staging block per epilogue warp
     static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024: alignment slack
 };
 
-template <int BLOCK_N, int MODE, bool CTA2>
+// TEPI: the 16-bit-only epilogues (conv_common.cuh; ConvKParams.tma_epi launches): 1 = through TMA, 2 = 256-bit global
+// accesses straight from / to registers - separate instantiations, so that no epilogue carries another's registers
+template <int BLOCK_N, int MODE, bool CTA2, int TEPI = 0>
 __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
     conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+    static_assert(TEPI == 0 || MODE == 0, "the 16-bit-only epilogues serve the 16-bit operand modes");
     constexpr bool TF32 = MODE != 0;  // fp32 containers, kind::tf32
     constexpr bool X3 = MODE == 2;    // unrounded fp32 operands, split in shared memory, three MMAs per K step
     static_assert(!(X3 && CTA2) && !(X3 && BLOCK_N == 256), "the fp32 mode runs on the 1-CTA kernel with N <= 128");
@@ -70,6 +75,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
     uint64_t* tfull = bars + 3 * kStages;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* rbar = tempty + 4;  // [kEpiWarps] (tma_epi: a warp's residual block has landed)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -88,6 +94,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], CTA2 ? 2 * kEpiWarps : kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
         }
+        for (int w = 0; w < kEpiWarps; ++w) mbar_init(&rbar[w], 1);
         fence_mbar_init();
     }
     if (warp == 2) {
@@ -304,6 +311,11 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
         const int half = (warp - 2) >> 2;  // the two warps of a lane quarter take alternate 32-column chunks
         float* stg = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kBarBytes) + (warp - 2) * 1024;
+        // tma_epi: the same 4 KB as a 16-bit output block and a 16-bit residual block ([32][64 B], SWIZZLE_64B)
+        uint8_t* ostg = reinterpret_cast<uint8_t*>(stg);
+        uint8_t* rstg = ostg + kEpiTmaBlockBytes;
+        uint64_t* my_rbar = &rbar[warp - 2];
+        uint32_t rphase = 0;
         const int brick = p.BW * p.BH;
         const int row = quad * 32 + lane;
         const int bn = row / brick;
@@ -356,7 +368,8 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
             // (a 16-bit residual - nlc_conv_desc.resid_is_op - comes as four 16-byte loads of 8 channels per lane, 8 rows x 4
             // chunks per instruction, instead of eight fp32 ones)
             float4 rpre[8];
-            const bool pre = p.resid != nullptr && p.resid_mode == 0;
+            constexpr bool tma_epi = TEPI == 1;  // (host: 16-bit output only, dense placement, 16-bit residual or none)
+            const bool pre = p.resid != nullptr && p.resid_mode == 0 && TEPI == 0;
             const __nv_bfloat16* resid16 = reinterpret_cast<const __nv_bfloat16*>(p.resid);
             auto prefetch_resid = [&](int c_next) {
                 if (p.resid16) {
@@ -379,8 +392,25 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 }
             };
             if (pre) prefetch_resid(32 * half);
+            if (tma_epi && p.resid && lane == 0) {  // first residual block of the tile: a tensor load, before the accumulator wait
+                mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                tma_load_4d(rstg, &p.mapRes, my_rbar, n_tile * BLOCK_N + 32 * half, wo0, ho0, n0);
+            }
+            // TEPI 2: the lane's own 64 residual bytes of the next chunk, two 256-bit loads
+            uint32_t rq[2][8];
+            const __nv_bfloat16* rrow = resid16 + (pix0 + lane) * p.ld_resid + n_tile * BLOCK_N;
+            auto fetch_resid256 = [&](int c_next) {
+                if (valid) {
+                    ldg256(rrow + c_next, rq[0]);
+                    ldg256(rrow + c_next + 16, rq[1]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) rq[0][i] = rq[1][i] = 0u;
+                }
+            };
+            if (TEPI == 2 && p.resid) fetch_resid256(32 * half);
             // ... and the residual block of the NEXT tile of this CTA is pulled into L2 now, a whole tile ahead (conv_slab.cu)
-            if (pre && !p.out_head_split && unit + unit_step < p.num_tiles) {
+            if (p.resid != nullptr && p.resid_mode == 0 && !p.out_head_split && unit + unit_step < p.num_tiles) {
                 const int u2 = unit + unit_step;
                 const int nt2 = u2 / p.num_m_units;
                 const int mt2 = CTA2 ? 2 * (u2 - nt2 * p.num_m_units) + static_cast<int>(rank) : u2 - nt2 * p.num_m_units;
@@ -428,6 +458,100 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 tc_fence_after_sync();
             }
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * BLOCK_N;
+            if constexpr (TEPI != 0) {
+#pragma unroll 1
+                for (int c = 32 * half; c < BLOCK_N; c += 32 * (kEpiWarps / 4)) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c, v);
+                    const int col0 = n_tile * BLOCK_N + c;
+                    uint4 rr[4];
+                    if (p.resid) {
+                        if constexpr (TEPI == 1) {
+                            // this chunk's residual block has landed: own row -> registers, then the next block's load
+                            mbar_wait(my_rbar, rphase);
+                            rphase ^= 1;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rstg + epi_swz64(lane, j));
+                            __syncwarp();
+                            if (c + 32 * (kEpiWarps / 4) < BLOCK_N && lane == 0) {
+                                mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                                tma_load_4d(rstg, &p.mapRes, my_rbar, col0 + 32 * (kEpiWarps / 4), wo0, ho0, n0);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                rr[j] = make_uint4(rq[j >> 1][4 * (j & 1)], rq[j >> 1][4 * (j & 1) + 1], rq[j >> 1][4 * (j & 1) + 2],
+                                                   rq[j >> 1][4 * (j & 1) + 3]);
+                            if (c + 32 * (kEpiWarps / 4) < BLOCK_N) fetch_resid256(c + 32 * (kEpiWarps / 4));
+                        }
+                    }
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (p.bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldg(b4 + i);
+                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (p.rowvec && valid) {
+                        const float4* b4 =
+                            reinterpret_cast<const float4*>(p.rowvec + static_cast<size_t>(n) * p.ld_rowvec + col0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldg(b4 + i);
+                            f[4 * i] += t.x, f[4 * i + 1] += t.y, f[4 * i + 2] += t.z, f[4 * i + 3] += t.w;
+                        }
+                    }
+                    if (p.resid) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 a, b;
+                            unpack_op16x8(rr[j], p.f16, a, b);
+                            f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += a.z, f[8 * j + 3] += a.w;
+                            f[8 * j + 4] += b.x, f[8 * j + 5] += b.y, f[8 * j + 6] += b.z, f[8 * j + 7] += b.w;
+                        }
+                    }
+                    if (p.out_scale != 1.0f) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] *= p.out_scale;
+                    }
+                    if (p.act) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+                    }
+                    if (p.stats && vmask == 0xffffffffu)
+                        gn_partials(f, lane, p.stats + (stat_blk * p.stats_nblk + (col0 >> 2)) * 2);
+                    if constexpr (TEPI == 1) {
+                        // the previous chunk's tensor store has finished READING the staging block before it is rewritten
+                        if (lane == 0) bulk_wait_group_read0();
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(ostg + epi_swz64(lane, j)) =
+                                make_uint4(pack_op16x2(f[8 * j], f[8 * j + 1], p.f16), pack_op16x2(f[8 * j + 2], f[8 * j + 3], p.f16),
+                                           pack_op16x2(f[8 * j + 4], f[8 * j + 5], p.f16), pack_op16x2(f[8 * j + 6], f[8 * j + 7], p.f16));
+                        fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA unit's async-proxy read
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&p.mapOut, ostg, col0, wo0, ho0, n0);
+                            bulk_commit_group();
+                        }
+                    } else if (valid) {
+                        __nv_bfloat16* orow = static_cast<__nv_bfloat16*>(p.out_op) + (pix0 + lane) * p.ld_out_op + col0;
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            uint32_t w8[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) w8[i] = pack_op16x2(f[16 * h2 + 2 * i], f[16 * h2 + 2 * i + 1], p.f16);
+                            stg256(orow + 16 * h2, w8);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 32 * half; c < BLOCK_N; c += 32 * (kEpiWarps / 4)) {
                 uint32_t v[32];
@@ -616,6 +740,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 }
                 __syncwarp();
             }
+            }
             if (!X3) {
                 tc_fence_before_sync();
                 __syncwarp();
@@ -626,6 +751,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 if (acc == 0) acc_phase ^= 1;
             }
         }
+        if (TEPI == 1 && lane == 0) bulk_wait_group0();  // this warp's tensor stores are complete before the CTA retires
     }
 
     tc_fence_before_sync();
@@ -639,17 +765,55 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
 
+// Decide whether a launch takes the TMA epilogue and encode its output / residual tensor maps.  Called once the tile
+// geometry (BW, BH, BN) is final: by nlc_conv_tc for the tap-per-tile kernel, by launch_conv_slab for the slab kernel.
+int epi_tma_setup(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p) {
+    p.tma_epi = 0;
+    if (!ctx->use_tma_epi || !dtype_is16(d->dtype) || !d->out_op || d->out_f32 || d->out_up || d->out_head_split) return NLC_OK;
+    if (d->resid && (!d->resid_is_op || d->resid_mode != 0)) return NLC_OK;
+    if (!is_pow2(d->Wo) || !is_pow2(d->Ho) || d->Cout % 32 != 0) return NLC_OK;
+    int bw, bh, bn;
+    epi_tma_box(p.BW, p.BH, &bw, &bh, &bn);
+    for (int which = 0; which < (d->resid ? 2 : 1); ++which) {
+        const void* base = which ? d->resid : d->out_op;
+        const cuuint64_t ld = which ? d->ld_resid : d->ld_out_op;
+        if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return NLC_OK;
+        cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->B};
+        cuuint64_t gstr[3] = {ld * 2, ld * 2 * d->Wo, ld * 2 * d->Wo * d->Ho};
+        cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = ctx->encode_tiled(which ? &p.mapRes : &p.mapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                                       const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(%s) failed with %d", which ? "residual" : "output",
+                    (int)r);
+    }
+    if (!d->resid) p.mapRes = p.mapOut;
+    p.tma_epi = 1;
+    if (ctx->use_tma_epi == 2) {  // 256-bit accesses: every pixel row of the output (and residual) slice on a 32-byte boundary
+        const bool ok = (reinterpret_cast<uintptr_t>(d->out_op) & 31) == 0 && (d->ld_out_op * 2) % 32 == 0 &&
+                        (!d->resid || ((reinterpret_cast<uintptr_t>(d->resid) & 31) == 0 && (d->ld_resid * 2) % 32 == 0));
+        if (ok) p.tma_epi = 2;
+    }
+    return NLC_OK;
+}
+
 // conv_slab.cu
 bool conv_slab_eligible(const nlc_ctx* ctx, const nlc_conv_desc* d, int chunk);
 int launch_conv_slab(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p, int chunk, bool tf32, cudaStream_t stream);
 
-template <int BLOCK_N, int MODE, bool CTA2>
+template <int BLOCK_N, int MODE, bool CTA2, int TEPI = 0>
 static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream, int device) {
     using Cfg = ConvCfg<BLOCK_N, CTA2, MODE == 2>;
     constexpr int kLaunchThreads = MODE == 2 ? kThreadsX3 : kThreads;
+    if constexpr (MODE == 0 && TEPI == 0) {
+        if (p.tma_epi == 1) return launch_conv<BLOCK_N, MODE, CTA2, 1>(p, grid, stream, device);
+        if (p.tma_epi == 2) return launch_conv<BLOCK_N, MODE, CTA2, 2>(p, grid, stream, device);
+    }
     static PerDeviceFlag configured;
     if (!configured[device]) {
-        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, CTA2>,
+        NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, CTA2, TEPI>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
         configured[device] = true;
     }
@@ -662,9 +826,9 @@ static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream, int 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, CTA2>, p));
+        NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, CTA2, TEPI>, p));
     } else {
-        conv_tc_kernel<BLOCK_N, MODE, CTA2><<<grid, kLaunchThreads, Cfg::kSmemBytes, stream>>>(p);
+        conv_tc_kernel<BLOCK_N, MODE, CTA2, TEPI><<<grid, kLaunchThreads, Cfg::kSmemBytes, stream>>>(p);
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
@@ -847,6 +1011,10 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     p.out_f32 = d->out_f32, p.ld_out_f32 = d->ld_out_f32, p.out_op = d->out_op, p.ld_out_op = d->ld_out_op;
 
     if (slab) return launch_conv_slab(ctx, d, p, chunk, tf32, stream);
+    {
+        const int rc = epi_tma_setup(ctx, d, p);
+        if (rc != NLC_OK) return rc;
+    }
     if (pair) {
         const int pairs = p.num_tiles < ctx->sm_count / 2 ? p.num_tiles : ctx->sm_count / 2;
         if (tf32) {

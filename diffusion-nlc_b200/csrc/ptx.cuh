@@ -121,6 +121,33 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// TMA store of a shared-memory box (written by generic-proxy stores + fence_proxy_async_smem) to global memory; completion
+// is tracked per thread in bulk async-groups: commit after issuing, wait_group.read before the staging block is rewritten,
+// wait_group 0 before the kernel ends.  Out-of-range parts of the box are clipped.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+            reinterpret_cast<uint64_t>(m)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): a lane moves one full 32-byte sector, so a warp whose lanes sit in 32
+// different pixel rows still issues whole-sector requests (the 128-bit version of the same pattern is 32 half sectors).
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster (the two SMs of a TPC) execute one tcgen05.mma together: M = 256 (128 rows per CTA), each
 // CTA supplies its own A rows and one half of the B tile, so the B operand crosses L2->SM once per pair.

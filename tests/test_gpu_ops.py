@@ -576,3 +576,75 @@ def test_upsample_conv_as_four_subpixel_phases(dev, prec, tol, shape):
     ws = torch.zeros(ops.groupnorm_ws(B, 4 * H * W, Cout, 32), device=dev)
     ops.groupnorm(o32, 32, 1e-5, gam, bet, y, dt, ws, silu=True, use_stats=True)
     assert _rel(y.t.float().permute(0, 3, 1, 2), want) < tol
+
+
+TMA_EPI_CASES = [
+    # B, H, W, Cin, Cout, k, stride, residual, stats, channel-slice output
+    (3, 64, 64, 128, 128, 3, 1, True, True, False),    # slab kernel (W = 64: box 32 x 1)
+    (3, 16, 16, 128, 128, 3, 1, True, True, False),    # slab kernel, W = 16 (box 16 x 2), odd super-tile count
+    (2, 32, 32, 128, 256, 3, 1, False, True, True),    # slab kernel, two n tiles, output = channel slice of a wider buffer
+    (5, 4, 4, 256, 512, 3, 1, True, False, False),     # 8 images per M tile, ragged batch: rows past the batch are clipped
+    (6, 8, 8, 256, 256, 3, 2, False, False, False),    # stride 2, two images per tile
+    (3, 32, 32, 256, 768, 1, 1, False, False, False),  # qkv-shaped 1x1, N = 256 tiles
+    (1, 256, 256, 64, 64, 3, 1, True, True, False),    # 128-pixel rows, N = 64
+    (2, 2, 2, 512, 512, 3, 1, True, False, False),     # 32 images per tile
+    (130, 1, 1, 256, 128, 1, 1, False, False, False),  # 1x1 spatial
+    (9, 64, 64, 64, 128, 1, 1, True, True, False),     # CTA-pair kernel with an odd tile count
+]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", TMA_EPI_CASES)
+def test_conv_tma_epilogue_equals_lsu_epilogue(dev, prec, case):
+    """The 16-bit-only convolution epilogues - through TMA (ConvKParams.tma_epi 1: residual block by tensor load, output block
+    by tensor store, SWIZZLE_64B staging) and with 256-bit global accesses from / to registers (2) - against the staged
+    load/store-unit epilogue on the same launch: identical arithmetic in the same
+    order, so outputs and GroupNorm partials must be BIT-equal; and nothing outside the output's channel slice / batch is
+    touched (canary bands)."""
+    from nlc_b200 import _lib, ops
+    B, H, W, Cin, Cout, k, stride, with_resid, with_stats, sliced = case
+    dt = _dt(prec)
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(77)
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x = torch.randn(B, H, W, Cin, generator=g).to(dev).to(tdt)
+    w = _rnd((torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev), dt)
+    b = torch.randn(Cout, generator=g).to(dev)
+    rowvec = torch.randn(B, Cout, generator=g).to(dev)
+    resid = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev).to(tdt) if with_resid else None
+    segs = [(0, kh - pad, kw - pad, 0, Cin) for kh in range(k) for kw in range(k)]
+    wp = ops.pack_conv_weight(w, dt)
+    ctx = _lib.ctx(0)
+    outs = {}
+    try:
+        for mode in (1, 2, 0):
+            _lib.check(_lib.lib().nlc_ctx_set(ctx, b"tma_epi", mode))
+            can_stats = with_stats and Ho * Wo >= 128
+            st = ops.GnStats(torch.zeros(B * Ho * Wo // 32, (Cout + (64 if sliced else 0)) // 4, 2, device=dev)) if can_stats else None
+            if sliced:  # the launch owns channels [32, 32 + Cout) of a buffer with 64 more; one extra image of canary behind
+                buf = torch.full((B + 1, Ho, Wo, Cout + 64), 7.0, device=dev, dtype=tdt)
+                oop = ops.Act(buf[:B], 32, Cout, st)
+            else:
+                buf = torch.full((B + 1, Ho, Wo, Cout), 7.0, device=dev, dtype=tdt)
+                oop = ops.Act(buf[:B], 0, Cout, st)
+            ops.conv_tc([ops.Act(x)], segs, wp, Cout, B, Ho, Wo, dt, stride=stride, bias=b, rowvec=rowvec,
+                        resid=ops.Act(resid) if with_resid else None, out_scale=0.5, out_op=oop, stats=can_stats)
+            torch.cuda.synchronize()
+            outs[mode] = (buf.clone(), st.t.clone() if can_stats else None)
+    finally:
+        _lib.check(_lib.lib().nlc_ctx_set(ctx, b"tma_epi", 1))
+    for mode in (1, 2):  # 1: TMA; 2: 256-bit global accesses straight from / to registers
+        assert torch.equal(outs[mode][0].view(torch.int16), outs[0][0].view(torch.int16))
+        if outs[mode][1] is not None:
+            assert torch.equal(outs[mode][1], outs[0][1])
+    buf = outs[1][0].float()
+    assert torch.all(buf[B] == 7.0)
+    if sliced:
+        assert torch.all(buf[..., :32] == 7.0) and torch.all(buf[..., 32 + Cout:] == 7.0)
+    xr = x.float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xr, w, b, stride=stride, padding=pad) + rowvec[:, :, None, None]
+    if with_resid:
+        ref = ref + resid.float().permute(0, 3, 1, 2)
+    got = buf[:B, ..., 32:32 + Cout] if sliced else buf[:B]
+    assert _rel(got.permute(0, 3, 1, 2), ref * 0.5) < (8e-3 if prec == "bf16" else 1e-3)
