@@ -57,6 +57,8 @@ nlc_ctx* nlc_create(int device) {
     ctx->use_cta_pairs = !(e && e[0] == '0');
     e = getenv("NLC_SLAB");
     ctx->use_slab = e ? atoi(e) : 1;
+    e = getenv("NLC_ATTN_ONEPASS");
+    ctx->attn_onepass = !(e && e[0] == '0');
     e = getenv("NLC_TMA_EPI");
     ctx->use_tma_epi = e ? atoi(e) : 1;
     return ctx;
@@ -73,6 +75,8 @@ int nlc_ctx_set(nlc_ctx* ctx, const char* key, int value) {
     } else if (!strcmp(key, "slab")) {
         if (value < 0 || value > 2) return nlc::set_error(NLC_EINVAL, "nlc_ctx_set: slab must be 0, 1 or 2");
         ctx->use_slab = value;
+    } else if (!strcmp(key, "attn_onepass")) {
+        ctx->attn_onepass = value != 0;
     } else if (!strcmp(key, "tma_epi")) {
         if (value < 0 || value > 2) return nlc::set_error(NLC_EINVAL, "nlc_ctx_set: tma_epi must be 0, 1 or 2");
         ctx->use_tma_epi = value;

@@ -253,6 +253,45 @@ def test_attention(dev, prec, tol, case):
     assert _rel(out.t.float().view(B, T, C), ref) < tol
 
 
+@pytest.mark.parametrize("prec,tol", [("bf16", 1.2e-2), ("fp16", 2e-3)])
+@pytest.mark.parametrize("case", [(2, 1024, 4, 64), (3, 256, 1, 256), (2, 64, 2, 64), (1, 512, 2, 256)])
+def test_attention_online_softmax_rescales(dev, prec, tol, case):
+    """One-pass fused attention (attn_fused1_kernel) on logits whose magnitude GROWS along the keys (key s scaled by a ramp
+    0.2 -> 9), so that the running reference of most rows moves several times and the accumulator in TMEM is rescaled; both
+    kernels (one pass / two passes) against torch's fp32 softmax on the same 16-bit inputs."""
+    from nlc_b200 import _lib, ops
+    B, T, heads, dh = case
+    dt = _dt(prec)
+    C = heads * dh
+    tdt = ops.OP_DTYPES[dt]
+    g = torch.Generator().manual_seed(11)
+    q = torch.randn(B, T, heads, dh, generator=g)
+    k = torch.randn(B, T, heads, dh, generator=g) * torch.linspace(0.2, 9.0, T).view(1, T, 1, 1)
+    v = torch.randn(B, T, heads, dh, generator=g)
+    qkv = torch.cat([q.reshape(B, T, C), k.reshape(B, T, C), v.reshape(B, T, C)], dim=2).to(dev).to(tdt)
+    f = qkv.float()
+    q, k, v = [f[:, :, i * C:(i + 1) * C].view(B, T, heads, dh) for i in range(3)]
+    scale = dh ** -0.5
+    logits = torch.einsum("bthd,bshd->bhts", q, k) * scale
+    # the premise of the test: block maxima (64 keys) of a typical row climb by far more than the 2^8 rescale threshold
+    blk = logits.view(B, heads, T, T // 64, 64).amax(-1) * 1.4426950408889634
+    if T > 64:
+        assert ((blk.cummax(-1).values[..., -1] - blk[..., 0]) > 16).float().mean() > 0.5
+    ref = torch.einsum("bhts,bshd->bthd", torch.softmax(logits, dim=-1), v).reshape(B, T, C)
+    side = 1 << ((T.bit_length() - 1) // 2)
+    ws = torch.zeros(max(ops.attention_ws(dt, B, T, heads, dh), 16), device=dev, dtype=torch.uint8)
+    ctx = _lib.ctx(0)
+    try:
+        for mode in (1, 0):
+            _lib.check(_lib.lib().nlc_ctx_set(ctx, b"attn_onepass", mode))
+            out = ops.Act(torch.zeros(B, side, T // side, C, device=dev, dtype=tdt))
+            ops.attention(ops.Act(qkv.view(B, side, T // side, 3 * C)), dt, 0, C, 2 * C, dh, heads, dh, scale, out, ws)
+            torch.cuda.synchronize()
+            assert _rel(out.t.float().view(B, T, C), ref) < tol, "mode %d" % mode
+    finally:
+        _lib.check(_lib.lib().nlc_ctx_set(ctx, b"attn_onepass", 1))
+
+
 def test_linear_and_embedding(dev):
     from nlc_b200 import ops
     g = torch.Generator().manual_seed(6)
