@@ -17,6 +17,14 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("NLC_PDL");  // opt-in: measured neutral inside the CUDA-graph replay
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 }  // namespace nlc
 
 extern "C" {

@@ -33,6 +33,8 @@ __device__ __forceinline__ __half from_f32<__half>(float v, int) { return __floa
 template <typename OutT>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ S, OutT* __restrict__ P,
                                                             long long rows, int T, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -66,6 +68,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_heads_kernel(const T* __restrict__ v, int ld, int head_stride,
                                                                int Tn, int heads, int dh, T* __restrict__ vt) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ T tile[32][33];
     const int bh = blockIdx.z, b = bh / heads, h = bh - b * heads;
     const T* src = v + static_cast<size_t>(b) * Tn * ld + static_cast<size_t>(h) * head_stride;
@@ -82,6 +86,8 @@ __global__ void __launch_bounds__(256) transpose_heads_kernel(const T* __restric
 // profiles/r02r_launches_c2_summary.md).  Needs Tn % 64 == 0 and dh % 64 == 0.
 __global__ void __launch_bounds__(256) transpose_heads16_kernel(const uint16_t* __restrict__ v, int ld, int head_stride, int Tn,
                                                                  int heads, int dh, uint16_t* __restrict__ vt) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ uint16_t tile[64][64 + 2];
     const int bh = blockIdx.z, b = bh / heads, h = bh - b * heads;
     const uint16_t* src = v + static_cast<size_t>(b) * Tn * ld + static_cast<size_t>(h) * head_stride;
@@ -105,6 +111,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     attn_small_kernel(const T* __restrict__ qkv, int ld, int q_off, int k_off, int v_off, int head_stride, int Tn,
                       int heads, int dh, float scale, T* __restrict__ out, int ld_out, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ float sm[];
     const int pitch = dh + 1;
     float* sk = sm;
@@ -215,19 +223,19 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
         if (f32c) {
             NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 227 * 1024));
-            attn_small_kernel<float><<<B * heads, 256, smem, stream>>>(static_cast<const float*>(qkv), ld, q_off, k_off,
+            launch_pdl((attn_small_kernel<float>), dim3(B * heads), dim3(256), smem, stream, static_cast<const float*>(qkv), ld, q_off, k_off,
                                                                        v_off, head_stride, T, heads, dh, scale,
                                                                        static_cast<float*>(out_op), ld_out, rnd);
         } else if (f16) {
             NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 227 * 1024));
-            attn_small_kernel<__half><<<B * heads, 256, smem, stream>>>(static_cast<const __half*>(qkv), ld, q_off, k_off,
+            launch_pdl((attn_small_kernel<__half>), dim3(B * heads), dim3(256), smem, stream, static_cast<const __half*>(qkv), ld, q_off, k_off,
                                                                        v_off, head_stride, T, heads, dh, scale,
                                                                        static_cast<__half*>(out_op), ld_out, rnd);
         } else {
             NLC_CHECK_CUDA(cudaFuncSetAttribute(attn_small_kernel<__nv_bfloat16>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attn_small_kernel<__nv_bfloat16><<<B * heads, 256, smem, stream>>>(
+            launch_pdl((attn_small_kernel<__nv_bfloat16>), dim3(B * heads), dim3(256), smem, stream, 
                 static_cast<const __nv_bfloat16*>(qkv), ld, q_off, k_off, v_off, head_stride, T, heads, dh, scale,
                 static_cast<__nv_bfloat16*>(out_op), ld_out, rnd);
         }
@@ -249,13 +257,13 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
     {
         dim3 grid(T / 32, dh / 32, static_cast<unsigned>(bh));
         if (f32c)
-            transpose_heads_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(q8 + v_off * esz), ld,
+            launch_pdl((transpose_heads_kernel<float>), dim3(grid), dim3(256), 0, stream, reinterpret_cast<const float*>(q8 + v_off * esz), ld,
                                                                     head_stride, T, heads, dh, static_cast<float*>(VT));
         else if (T % 64 == 0 && dh % 64 == 0 && ld % 2 == 0 && v_off % 2 == 0 && head_stride % 2 == 0)
-            transpose_heads16_kernel<<<dim3(T / 64, dh / 64, static_cast<unsigned>(bh)), 256, 0, stream>>>(
+            launch_pdl((transpose_heads16_kernel), dim3(dim3(T / 64, dh / 64, static_cast<unsigned>(bh))), dim3(256), 0, stream, 
                 reinterpret_cast<const uint16_t*>(q8 + v_off * esz), ld, head_stride, T, heads, dh, static_cast<uint16_t*>(VT));
         else
-            transpose_heads_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+            launch_pdl((transpose_heads_kernel<__nv_bfloat16>), dim3(grid), dim3(256), 0, stream, 
                 reinterpret_cast<const __nv_bfloat16*>(q8 + v_off * esz), ld, head_stride, T, heads, dh,
                 static_cast<__nv_bfloat16*>(VT));
         NLC_CHECK_LAUNCH();
@@ -285,11 +293,11 @@ extern "C" int nlc_attention(nlc_ctx* ctx, const void* qkv, int op_dtype, int ld
         const long long rows = static_cast<long long>(bh) * T;
         const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
         if (f32c)
-            softmax_rows_kernel<float><<<grid, 256, 0, stream>>>(S, static_cast<float*>(P), rows, T, rnd);
+            launch_pdl((softmax_rows_kernel<float>), dim3(grid), dim3(256), 0, stream, S, static_cast<float*>(P), rows, T, rnd);
         else if (f16)
-            softmax_rows_kernel<__half><<<grid, 256, 0, stream>>>(S, static_cast<__half*>(P), rows, T, rnd);
+            launch_pdl((softmax_rows_kernel<__half>), dim3(grid), dim3(256), 0, stream, S, static_cast<__half*>(P), rows, T, rnd);
         else
-            softmax_rows_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(S, static_cast<__nv_bfloat16*>(P), rows, T, rnd);
+            launch_pdl((softmax_rows_kernel<__nv_bfloat16>), dim3(grid), dim3(256), 0, stream, S, static_cast<__nv_bfloat16*>(P), rows, T, rnd);
         NLC_CHECK_LAUNCH();
     }
     // O = P V, heads merged back into [B, T, heads*dh]

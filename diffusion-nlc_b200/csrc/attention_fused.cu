@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(kFaThreads, FaCfg<DH>::kCtasPerSm) attn_fused_
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 2 * kFaKeys;
     const int nkb = p.n_kblk;
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): the set-up above overlapped the previous kernel's tail
+    pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -368,6 +370,8 @@ __global__ void __launch_bounds__(kFaThreads, FaCfg<DH>::kCtasPerSm) attn_fused1
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_o = tmem_base + 2 * kFaKeys;
     const int nkb = p.n_kblk;
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): the set-up above overlapped the previous kernel's tail
+    pdl_trigger();
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer: Q once per tile, (K, V^T) once per key block
@@ -578,9 +582,9 @@ static int launch_fused(nlc_ctx* ctx, const FaParams& p) {
     const int slots = Cfg::kCtasPerSm * ctx->sm_count;
     const int grid = p.n_tiles < slots ? p.n_tiles : slots;
     if (ctx->attn_onepass)
-        attn_fused1_kernel<DH><<<grid, kFaThreads, Cfg::kSmem, p.stream>>>(p);
+        launch_pdl((attn_fused1_kernel<DH>), dim3(grid), dim3(kFaThreads), Cfg::kSmem, p.stream, p);
     else
-        attn_fused_kernel<DH><<<grid, kFaThreads, Cfg::kSmem, p.stream>>>(p);
+        launch_pdl((attn_fused_kernel<DH>), dim3(grid), dim3(kFaThreads), Cfg::kSmem, p.stream, p);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/nlc_b200.h"
 
@@ -50,6 +51,22 @@ struct PerDeviceFlag {
     bool done[64] = {};
     bool& operator[](int dev) { return done[dev & 63]; }
 };
+
+// Launch with programmatic stream serialization (ptx.cuh: pdl_wait / pdl_trigger; the kernel MUST call pdl_wait() before it
+// touches global memory).  Inside a captured CUDA graph the attribute becomes a programmatic dependency edge.  Opt-in
+// (NLC_PDL=1): by default the same kernels are launched in ordinary stream order, where pdl_wait() is a no-op.
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);
+}
 
 }  // namespace nlc
 

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256)
     conv_in_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, int B, int Cin, int H, int W,
                    const float* __restrict__ wt, const float* __restrict__ bias, int Cout, float* __restrict__ yf,
                    int ld_yf, void* __restrict__ yo, int ld_yo, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ float sw[];  // [9*Cin][Cout]
     const int K = 9 * Cin;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
@@ -88,6 +90,8 @@ template <bool TF32>
 __global__ void __launch_bounds__(256)
     im2col_in_kernel(const float* __restrict__ x, const float* __restrict__ in_scale, int B, int Cin, int H, int W,
                      void* __restrict__ patches, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     constexpr int KP = TF32 ? 32 : 64;
     const long long npix = static_cast<long long>(B) * H * W;
     for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
@@ -157,6 +161,8 @@ template <typename T, int COUT>
 __global__ void __launch_bounds__(256)
     conv_out_kernel(const T* __restrict__ x, int ld_x, int B, int Cin, int H, int W, const float* __restrict__ wt,
                     const float* __restrict__ bias, float* __restrict__ out) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ float sw[];  // [9][COUT][Cin]
     for (int i = threadIdx.x; i < COUT * Cin * 9; i += blockDim.x) {
         const int co = i / (Cin * 9), r = i - co * Cin * 9;
@@ -233,7 +239,7 @@ static int launch_conv_out(nlc_ctx* ctx, const T* x, int ld_x, int B, int Cin, i
     case N:                                                                                                      \
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_out_kernel<T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                             static_cast<int>(smem)));                                            \
-        conv_out_kernel<T, N><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(x, ld_x, B, Cin, H, W, wt,    \
+        launch_pdl((conv_out_kernel<T, N>), dim3(static_cast<unsigned>(blocks)), dim3(256), smem, stream, x, ld_x, B, Cin, H, W, wt,    \
                                                                                     bias, out);                  \
         break;
     switch (Cout) {
@@ -271,12 +277,12 @@ extern "C" int nlc_conv_in_nchw(nlc_ctx* ctx, const float* x_nchw, const float* 
     if (!dtype_is16(op_dtype)) {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-        conv_in_kernel<true><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
+        launch_pdl((conv_in_kernel<true>), dim3(static_cast<unsigned>(blocks)), dim3(256), smem, stream, 
             x_nchw, in_scale, B, Cin, H, W, weight, bias, Cout, out_f32, ld_out_f32, out_op, ld_out_op, rnd);
     } else {
         NLC_CHECK_CUDA(cudaFuncSetAttribute(conv_in_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             static_cast<int>(smem)));
-        conv_in_kernel<false><<<static_cast<unsigned>(blocks), 256, smem, stream>>>(
+        launch_pdl((conv_in_kernel<false>), dim3(static_cast<unsigned>(blocks)), dim3(256), smem, stream, 
             x_nchw, in_scale, B, Cin, H, W, weight, bias, Cout, out_f32, ld_out_f32, out_op, ld_out_op, rnd);
     }
     NLC_CHECK_LAUNCH();
@@ -314,9 +320,9 @@ extern "C" int nlc_im2col_in(nlc_ctx* ctx, const float* x_nchw, const float* in_
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
     if (!dtype_is16(op_dtype))
-        im2col_in_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
+        launch_pdl((im2col_in_kernel<true>), dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
     else
-        im2col_in_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
+        launch_pdl((im2col_in_kernel<false>), dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, x_nchw, in_scale, B, Cin, H, W, patches_op, rnd);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
     cluster_sync_all();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();  // (programmatic dependent launch, conv_tc.cu)
+    pdl_trigger();
 
     // CTA `rank` of pair unit u owns super tile 2u + rank = (image, block of G*BH rows)
     auto super_of = [&](int unit, int& n_tile) {
@@ -657,10 +659,12 @@ int launch_conv_slab(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p, int c
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs), cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
     NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, sp));
     NLC_CHECK_LAUNCH();
     return NLC_OK;

@@ -105,6 +105,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
     if (CTA2) cluster_sync_all();  // the peer's barriers are initialised before anything remote touches them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    // (programmatic dependent launch: everything above overlapped the previous kernel's tail; nothing below may)
+    pdl_wait();
+    pdl_trigger();
 
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
@@ -822,13 +825,16 @@ static int launch_conv(const ConvKParams& p, int grid, cudaStream_t stream, int 
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kLaunchThreads);
         cfg.dynamicSmemBytes = Cfg::kSmemBytes, cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr, cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
         NLC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, CTA2, TEPI>, p));
     } else {
-        conv_tc_kernel<BLOCK_N, MODE, CTA2, TEPI><<<grid, kLaunchThreads, Cfg::kSmemBytes, stream>>>(p);
+        NLC_CHECK_CUDA(launch_pdl((conv_tc_kernel<BLOCK_N, MODE, CTA2, TEPI>), dim3(grid), dim3(kLaunchThreads), Cfg::kSmemBytes,
+                                  stream, p));
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;

@@ -43,6 +43,8 @@ __device__ __forceinline__ Wf wf_of4(float4 v) {
 // grid (nchunks, B); dynamic smem: entries * sizeof(Wf)
 __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __restrict__ x, int ld_x, int HW, int C,
                                                                int groups, int rows_per_chunk, float* __restrict__ ws) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     extern __shared__ float gn_smem[];
     Wf* part = reinterpret_cast<Wf*>(gn_smem);
     const int C4 = C >> 2;
@@ -83,6 +85,8 @@ __global__ void __launch_bounds__(kGnThreads) gn_stats_kernel(const float* __res
 // (a) from the Welford partials of gn_stats_kernel; grid (B), one thread per group
 __global__ void gn_finalize_welford_kernel(const float* __restrict__ ws, int stat_chunks, int groups, float eps,
                                            float* __restrict__ mr) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const int n = blockIdx.x;
     for (int g = threadIdx.x; g < groups; g += blockDim.x) {
         Wf acc = {0.f, 0.f, 0.f};
@@ -117,6 +121,8 @@ __device__ __forceinline__ float gn_block_sum(float v, float* red) {
 __global__ void __launch_bounds__(kGnThreads)
     gn_finalize_blocks_kernel(const float* __restrict__ stats, int stats_nblk, int n_rowgroups, int blocks_per_group,
                               float eps, float* __restrict__ mr) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ float red[kGnThreads / 32];
     const int g = blockIdx.x, n = blockIdx.y;
     const float2* base = reinterpret_cast<const float2*>(stats) + static_cast<size_t>(n) * n_rowgroups * stats_nblk +
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(kGnThreads)
 __global__ void __launch_bounds__(256)
     gn_finalize_blocks_warp_kernel(const float* __restrict__ stats, int stats_nblk, int n_rowgroups, int blocks_per_group,
                                    int groups, int n_pairs, float eps, float* __restrict__ mr) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (pair >= n_pairs) return;
     const int lane = threadIdx.x & 31;
@@ -222,6 +230,8 @@ __global__ void __launch_bounds__(kGnThreads, MODE == 2 ? 1 : 2)
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                     const float* __restrict__ shift, int ld_ss, int do_silu, const float* __restrict__ mr,
                     void* __restrict__ y, int ld_y, int items_per_chunk, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     constexpr int kGnUnroll = MODE == 2 ? 2 : kGnUnrollMax;  // MODE 2 items are four times as wide
     extern __shared__ __align__(16) float gn_smem[];
     float* ca = gn_smem;
@@ -361,6 +371,8 @@ __global__ void __launch_bounds__(256, 4)
                          const float* __restrict__ beta, const float* __restrict__ scale, const float* __restrict__ shift,
                          int ld_ss, const float* __restrict__ mr, __nv_bfloat16* __restrict__ y, int ld_y,
                          int pix_per_chunk, int f16) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const int C8 = C >> 3;
     const int n = blockIdx.y;
     const int cblk = static_cast<int>(threadIdx.x) % C8, prow = static_cast<int>(threadIdx.x) / C8;
@@ -451,7 +463,7 @@ static bool launch_apply_lean(const void* x, int x_is_op, int ld_x, int B, int H
     const dim3 grid(static_cast<unsigned>(chunks), B);
     __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y);
 #define NLC_GN_LEAN(X, S)                                                                                              \
-    gn_apply_lean_kernel<X, S, U><<<grid, threads, 0, stream>>>(x, ld_x, HW, C, groups, gamma, beta, scale, shift, ld_ss, mr, yo, \
+    launch_pdl((gn_apply_lean_kernel<X, S, U>), dim3(grid), dim3(threads), 0, stream, x, ld_x, HW, C, groups, gamma, beta, scale, shift, ld_ss, mr, yo, \
                                                                 ld_y, per, f16)
     if (x_is_op) {
         if (do_silu) NLC_GN_LEAN(true, true); else NLC_GN_LEAN(true, false);
@@ -473,6 +485,8 @@ __global__ void __launch_bounds__(kGnSmallThreads)
     gn_small_kernel(const float* __restrict__ x, int ld_x, int HW, int C, int groups, float eps,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                     const float* __restrict__ shift, int ld_ss, int do_silu, void* __restrict__ y, int ld_y, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ float red[kGnSmallThreads / 32];
     const int g = blockIdx.x, n = blockIdx.y;
     const int cpg = C / groups, cpg4 = cpg >> 2;
@@ -551,6 +565,8 @@ __global__ void __launch_bounds__(256)
     gn_small_warp_kernel(const float* __restrict__ x, int ld_x, int HW, int C, int groups, int n_pairs, float eps,
                          const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ scale,
                          const float* __restrict__ shift, int ld_ss, int do_silu, void* __restrict__ y, int ld_y, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const int pair = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (pair >= n_pairs) return;
     const int lane = threadIdx.x & 31;
@@ -635,7 +651,7 @@ static int launch_apply(const float* x, int ld_x, int B, int H, int W, int C, in
     const int per = static_cast<int>((items + chunks - 1) / chunks);
     chunks = (items + per - 1) / per;
     const size_t smem = static_cast<size_t>(2) * C * sizeof(float);
-    gn_apply_kernel<TF32, MODE, X16><<<dim3(static_cast<unsigned>(chunks), B), kGnThreads, smem, stream>>>(
+    launch_pdl((gn_apply_kernel<TF32, MODE, X16>), dim3(dim3(static_cast<unsigned>(chunks), B)), dim3(kGnThreads), smem, stream, 
         x, ld_x, H, W, C, groups, gamma, beta, scale, shift, ld_ss, do_silu, mr, y, ld_y, per, rnd);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
@@ -676,20 +692,20 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const void* x_, int x_is_op, int ld_x
     if (!stats && resample == 0 && HW * ((C / groups) / 4) <= 32 * kGnSmallVec) {  // <= 1024 values per group: a warp each
         const int n_pairs = B * groups;
         if (!dtype_is16(op_dtype))
-            gn_small_warp_kernel<true><<<(n_pairs + 7) / 8, 256, 0, stream>>>(x, ld_x, HW, C, groups, n_pairs, eps, gamma, beta, scale,
+            launch_pdl((gn_small_warp_kernel<true>), dim3((n_pairs + 7) / 8), dim3(256), 0, stream, x, ld_x, HW, C, groups, n_pairs, eps, gamma, beta, scale,
                                                                               shift, ld_ss, do_silu, y_op, ld_y, rnd);
         else
-            gn_small_warp_kernel<false><<<(n_pairs + 7) / 8, 256, 0, stream>>>(x, ld_x, HW, C, groups, n_pairs, eps, gamma, beta,
+            launch_pdl((gn_small_warp_kernel<false>), dim3((n_pairs + 7) / 8), dim3(256), 0, stream, x, ld_x, HW, C, groups, n_pairs, eps, gamma, beta,
                                                                                scale, shift, ld_ss, do_silu, y_op, ld_y, rnd);
         NLC_CHECK_LAUNCH();
         return NLC_OK;
     }
     if (!stats && resample == 0 && HW * ((C / groups) / 4) <= kGnSmallThreads * kGnSmallVec) {
         if (!dtype_is16(op_dtype))
-            gn_small_kernel<true><<<dim3(groups, B), kGnSmallThreads, 0, stream>>>(
+            launch_pdl((gn_small_kernel<true>), dim3(dim3(groups, B)), dim3(kGnSmallThreads), 0, stream, 
                 x, ld_x, HW, C, groups, eps, gamma, beta, scale, shift, ld_ss, do_silu, y_op, ld_y, rnd);
         else
-            gn_small_kernel<false><<<dim3(groups, B), kGnSmallThreads, 0, stream>>>(
+            launch_pdl((gn_small_kernel<false>), dim3(dim3(groups, B)), dim3(kGnSmallThreads), 0, stream, 
                 x, ld_x, HW, C, groups, eps, gamma, beta, scale, shift, ld_ss, do_silu, y_op, ld_y, rnd);
         NLC_CHECK_LAUNCH();
         return NLC_OK;
@@ -699,20 +715,20 @@ extern "C" int nlc_groupnorm(nlc_ctx* ctx, const void* x_, int x_is_op, int ld_x
                     "nlc_groupnorm: conv-epilogue partials need H*W %% 32 == 0 and an 8-byte aligned buffer");
         const int bpg = (C / groups) / 4;
         if ((HW / 32) * bpg <= 512)
-            gn_finalize_blocks_warp_kernel<<<(B * groups + 7) / 8, 256, 0, stream>>>(stats, stats_nblk, HW / 32, bpg,
+            launch_pdl((gn_finalize_blocks_warp_kernel), dim3((B * groups + 7) / 8), dim3(256), 0, stream, stats, stats_nblk, HW / 32, bpg,
                                                                                       groups, B * groups, eps, mr);
         else
-            gn_finalize_blocks_kernel<<<dim3(groups, B), kGnThreads, 0, stream>>>(stats, stats_nblk, HW / 32, bpg, eps, mr);
+            launch_pdl((gn_finalize_blocks_kernel), dim3(dim3(groups, B)), dim3(kGnThreads), 0, stream, stats, stats_nblk, HW / 32, bpg, eps, mr);
         NLC_CHECK_LAUNCH();
     } else {
         const int stat_chunks = pick_chunks(B, HW, ctx->sm_count, 1);
         const int C4 = C / 4;
         const int row_lanes = C4 >= kGnThreads ? 1 : kGnThreads / C4;
         const size_t smem_stats = static_cast<size_t>(row_lanes) * C4 * sizeof(Wf);
-        gn_stats_kernel<<<dim3(stat_chunks, B), kGnThreads, smem_stats, stream>>>(x, ld_x, HW, C, groups,
+        launch_pdl((gn_stats_kernel), dim3(dim3(stat_chunks, B)), dim3(kGnThreads), smem_stats, stream, x, ld_x, HW, C, groups,
                                                                                    HW / stat_chunks, workspace);
         NLC_CHECK_LAUNCH();
-        gn_finalize_welford_kernel<<<B, 64, 0, stream>>>(workspace, stat_chunks, groups, eps, mr);
+        launch_pdl((gn_finalize_welford_kernel), dim3(B), dim3(64), 0, stream, workspace, stat_chunks, groups, eps, mr);
         NLC_CHECK_LAUNCH();
     }
 #define NLC_GN_APPLY(T, M)                                                                                        \

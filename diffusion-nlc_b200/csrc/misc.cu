@@ -31,6 +31,8 @@ template <int MODE, bool TF32, typename TIN>
 __global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x, int ld_x, int H, int W, int C,
                                                         float* __restrict__ yf, int ld_yf, void* __restrict__ yo,
                                                         int ld_yo, long long total4, int rnd) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const int Ho = MODE == 1 ? 2 * H : (MODE == 2 ? H / 2 : H);
     const int Wo = MODE == 1 ? 2 * W : (MODE == 2 ? W / 2 : W);
     const int C4 = C >> 2;
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x
 // (output of the tensor-core conv_out, whose 3 | 6 real channels sit in a 64-channel padded tile)
 __global__ void __launch_bounds__(256) nhwc_head_to_nchw_kernel(const float* __restrict__ x, int ld, long long npix,
                                                                  int HW, int C, float* __restrict__ out) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     for (long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pix < npix;
          pix += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long n = pix / HW;
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(256) nhwc_head_to_nchw_kernel(const float* __r
 // ---------------------------------------------------------------- timestep embedding
 __global__ void temb_kernel(const float* __restrict__ t, int B, const float* __restrict__ freqs, int half,
                             int cos_first, float* __restrict__ out, int ld) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half) return;
     const int b = i / half, k = i - b * half;
@@ -118,6 +124,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ld_x, int B, int K,
                                                       const float* __restrict__ Wt, const float* __restrict__ bias,
                                                       int N, int act_in, int act_out, float* __restrict__ y, int ld_y) {
+    pdl_wait();  // programmatic dependent launch (ptx.cuh): nothing above touches global memory
+    pdl_trigger();
     __shared__ float xs[kLinBK][kLinBM + 1];
     __shared__ float ws[kLinBK][kLinBN + 1];
     const int b0 = blockIdx.y * kLinBM, n0 = blockIdx.x * kLinBN;
@@ -216,7 +224,7 @@ extern "C" int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H
     const bool tf32 = !dtype_is16(op_dtype);
     const int rnd = dtype_fmt(op_dtype);
 #define NLC_RS(M, T)                                                                                          \
-    resample_kernel<M, T, float><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld_x, H, W, C, y_f32,      \
+    launch_pdl((resample_kernel<M, T, float>), dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, x, ld_x, H, W, C, y_f32,      \
                                                                                     ld_y_f32, y_op, ld_y_op, total4, rnd)
     if (mode == 0) {
         if (tf32) NLC_RS(0, true); else NLC_RS(0, false);
@@ -246,20 +254,20 @@ extern "C" int nlc_resample_op(nlc_ctx* ctx, const void* x_op, int op_dtype, int
     const int rnd = dtype_fmt(op_dtype);
     if (!dtype_is16(op_dtype)) {
         const float* x = static_cast<const float*>(x_op);
-        if (mode == 1) resample_kernel<1, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
-        else resample_kernel<2, true, float><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+        if (mode == 1) launch_pdl((resample_kernel<1, true, float>), dim3(g), dim3(256), 0, stream, x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+        else launch_pdl((resample_kernel<2, true, float>), dim3(g), dim3(256), 0, stream, x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     } else if (op_dtype == NLC_F16) {
         const __half* x = static_cast<const __half*>(x_op);
         if (mode == 1)
-            resample_kernel<1, false, __half><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+            launch_pdl((resample_kernel<1, false, __half>), dim3(g), dim3(256), 0, stream, x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
         else
-            resample_kernel<2, false, __half><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+            launch_pdl((resample_kernel<2, false, __half>), dim3(g), dim3(256), 0, stream, x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     } else {
         const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(x_op);
         if (mode == 1)
-            resample_kernel<1, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+            launch_pdl((resample_kernel<1, false, __nv_bfloat16>), dim3(g), dim3(256), 0, stream, x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
         else
-            resample_kernel<2, false, __nv_bfloat16><<<g, 256, 0, stream>>>(x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
+            launch_pdl((resample_kernel<2, false, __nv_bfloat16>), dim3(g), dim3(256), 0, stream, x, ld_x, H, W, C, nullptr, 0, y_op, ld_y, total4, rnd);
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
@@ -275,7 +283,7 @@ extern "C" int nlc_nhwc_head_to_nchw(nlc_ctx* ctx, const float* x, int ld, int B
     long long blocks = (npix + 255) / 256;
     const long long cap = static_cast<long long>(ctx->sm_count) * 16;
     if (blocks > cap) blocks = cap;
-    nhwc_head_to_nchw_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, ld, npix, H * W, C, out_nchw);
+    launch_pdl((nhwc_head_to_nchw_kernel), dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, x, ld, npix, H * W, C, out_nchw);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -285,7 +293,7 @@ extern "C" int nlc_timestep_embedding(nlc_ctx* ctx, const float* t, int B, const
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     NLC_REQUIRE(ctx && t && freqs && out && half > 0 && ld_out >= 2 * half, "nlc_timestep_embedding: bad argument");
     const int total = B * half;
-    temb_kernel<<<(total + 255) / 256, 256, 0, stream>>>(t, B, freqs, half, cos_first, out, ld_out);
+    launch_pdl((temb_kernel), dim3((total + 255) / 256), dim3(256), 0, stream, t, B, freqs, half, cos_first, out, ld_out);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }
@@ -298,9 +306,9 @@ extern "C" int nlc_linear(nlc_ctx* ctx, const float* x, int ld_x, int B, int K, 
     const bool vec = K % 4 == 0 && ld_x % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                      (reinterpret_cast<uintptr_t>(W) & 15) == 0;
     if (vec)
-        linear_kernel<true><<<grid, 256, 0, stream>>>(x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
+        launch_pdl((linear_kernel<true>), dim3(grid), dim3(256), 0, stream, x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
     else
-        linear_kernel<false><<<grid, 256, 0, stream>>>(x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
+        launch_pdl((linear_kernel<false>), dim3(grid), dim3(256), 0, stream, x, ld_x, B, K, W, bias, N, act_in, act_out, y, ld_y);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

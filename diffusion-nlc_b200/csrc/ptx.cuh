@@ -84,6 +84,14 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization (common.h: launch_pdl) may be scheduled while
+// the previous kernel of the stream is still running: pdl_wait() blocks until that kernel has completed and its writes are
+// visible (a no-op for an ordinary launch) and must precede every global-memory access; pdl_trigger() lets the NEXT
+// kernel's CTAs be scheduled as soon as SM resources free up (they block in their own pdl_wait()).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
