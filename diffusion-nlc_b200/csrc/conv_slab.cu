@@ -312,16 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                                 rphase ^= 1;
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rstg + epi_swz64(lane, j));
-                                __syncwarp();
-                                if (lane == 0) {  // next block: the next column chunk, or the first one of the unit's next M tile
-                                    if (c + 32 * (kEpiWarps / 4) < kSlabN) {
-                                        mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
-                                        tma_load_4d(rstg, &p.mapRes, my_rbar, col0 + 32 * (kEpiWarps / 4), bw0, ho_g, n);
-                                    } else if (g + 1 < kSlabG) {
-                                        mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
-                                        tma_load_4d(rstg, &p.mapRes, my_rbar, n_tile * kSlabN + 32 * half, bw0, ho_g + p.BH, n);
-                                    }
-                                }
+                                // (the next block's tensor load is issued below, after these values have been consumed)
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j)
@@ -361,6 +352,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_slab_kernel(const __grid_con
                                 unpack_op16x8(rr[j], p.f16, a, b);
                                 f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += a.z, f[8 * j + 3] += a.w;
                                 f[8 * j + 4] += b.x, f[8 * j + 5] += b.y, f[8 * j + 6] += b.z, f[8 * j + 7] += b.w;
+                            }
+                            if constexpr (TEPI == 1) {
+                                // the residual values have been consumed (their LDS have returned): the block goes back to the
+                                // TMA unit (conv_tc.cu) - next: the next column chunk, or the first one of the unit's next M tile
+                                fence_proxy_async_smem();
+                                __syncwarp();
+                                if (lane == 0) {
+                                    if (c + 32 * (kEpiWarps / 4) < kSlabN) {
+                                        mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                                        tma_load_4d(rstg, &p.mapRes, my_rbar, col0 + 32 * (kEpiWarps / 4), bw0, ho_g, n);
+                                    } else if (g + 1 < kSlabG) {
+                                        mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                                        tma_load_4d(rstg, &p.mapRes, my_rbar, n_tile * kSlabN + 32 * half, bw0, ho_g + p.BH, n);
+                                    }
+                                }
                             }
                         }
                         if (p.out_scale != 1.0f) {

@@ -475,11 +475,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                             rphase ^= 1;
 #pragma unroll
                             for (int j = 0; j < 4; ++j) rr[j] = *reinterpret_cast<const uint4*>(rstg + epi_swz64(lane, j));
-                            __syncwarp();
-                            if (c + 32 * (kEpiWarps / 4) < BLOCK_N && lane == 0) {
-                                mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
-                                tma_load_4d(rstg, &p.mapRes, my_rbar, col0 + 32 * (kEpiWarps / 4), wo0, ho0, n0);
-                            }
+                            // (the block is handed back to the TMA unit further down, once these loads have RETURNED)
                         } else {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
@@ -516,6 +512,19 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                             unpack_op16x8(rr[j], p.f16, a, b);
                             f[8 * j] += a.x, f[8 * j + 1] += a.y, f[8 * j + 2] += a.z, f[8 * j + 3] += a.w;
                             f[8 * j + 4] += b.x, f[8 * j + 5] += b.y, f[8 * j + 6] += b.z, f[8 * j + 7] += b.w;
+                        }
+                        if constexpr (TEPI == 1) {
+                            // Every lane has CONSUMED its residual values, so its shared-memory loads have returned: only now
+                            // may the TMA unit overwrite the block with the next one.  (Issuing the next load right after the
+                            // loads were issued left a window - a warp barrier does not wait for outstanding LDS, and under
+                            // the MMA's operand traffic an LDS can outlast the tensor load of an L2-resident block: one image
+                            // in ~50 forward passes of ADM-256 came out different, scripts/repro_check.py.)
+                            fence_proxy_async_smem();  // generic-proxy reads of the block -> before the async-proxy write of the next
+                            __syncwarp();
+                            if (c + 32 * (kEpiWarps / 4) < BLOCK_N && lane == 0) {
+                                mbar_expect_tx(my_rbar, kEpiTmaBlockBytes);
+                                tma_load_4d(rstg, &p.mapRes, my_rbar, col0 + 32 * (kEpiWarps / 4), wo0, ho0, n0);
+                            }
                         }
                     }
                     if (p.out_scale != 1.0f) {
@@ -767,6 +776,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
 }
 
 static bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+bool conv_slab_eligible(const nlc_ctx* ctx, const nlc_conv_desc* d, int chunk);  // conv_slab.cu
 
 // Decide whether a launch takes the TMA epilogue and encode its output / residual tensor maps.  Called once the tile
 // geometry (BW, BH, BN) is final: by nlc_conv_tc for the tap-per-tile kernel, by launch_conv_slab for the slab kernel.
@@ -774,6 +784,12 @@ int epi_tma_setup(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p) {
     p.tma_epi = 0;
     if (!ctx->use_tma_epi || !dtype_is16(d->dtype) || !d->out_op || d->out_f32 || d->out_up || d->out_head_split) return NLC_OK;
     if (d->resid && (!d->resid_is_op || d->resid_mode != 0)) return NLC_OK;
+    {
+        static const int mask = [] { const char* e = getenv("NLC_TMA_EPI_MASK"); return e ? atoi(e) : 15; }();  // debugging
+        if (!(mask & (d->resid ? 2 : 1))) return NLC_OK;
+        const bool is_slab = conv_slab_eligible(ctx, d, 64);
+        if (!(mask & (is_slab ? 4 : 8))) return NLC_OK;
+    }
     if (!is_pow2(d->Wo) || !is_pow2(d->Ho) || d->Cout % 32 != 0) return NLC_OK;
     int bw, bh, bn;
     epi_tma_box(p.BW, p.BH, &bw, &bh, &bn);

@@ -43,8 +43,10 @@ def test_adm256_forward_is_finite_and_batch_independent(adm256, prec):
     sc = torch.tensor([0.05, 0.3, 0.9], device=dev)
     full = m.forward_scaled(x, t, sc).clone()
     assert full.shape == (3, 6, 256, 256) and torch.isfinite(full).all()
-    again = m.forward_scaled(x, t, sc).clone()
-    assert torch.equal(full, again)  # same plan, same launches: bit-reproducible
+    for _ in range(12):  # same plan, same launches: bit-reproducible (twelve repeats: a shared-memory hand-off race between the
+        # epilogue's residual loads and the next tensor load once showed up as one different image in ~50 passes)
+        again = m.forward_scaled(x, t, sc).clone()
+        assert torch.equal(full, again)
     a = m.forward_scaled(x[:2].contiguous(), t[:2], sc[:2]).clone()
     b = m.forward_scaled(x[2:].contiguous(), t[2:], sc[2:]).clone()
     parts = torch.cat([a, b])
