@@ -801,9 +801,13 @@ int epi_tma_setup(nlc_ctx* ctx, const nlc_conv_desc* d, ConvKParams& p) {
         cuuint64_t gstr[3] = {ld * 2, ld * 2 * d->Wo, ld * 2 * d->Wo * d->Ho};
         cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
         cuuint32_t estr[4] = {1, 1, 1, 1};
+        // (L2 promotion: the residual's 64-byte rows are fetched as whole 128-byte lines - the other half belongs to the
+        // neighbouring warp's block; none for the output map.  Measured: DRAM bytes and step time are the same either way,
+        // profiles/r02zk_dram_c5_promo?.csv)
         CUresult r = ctx->encode_tiled(which ? &p.mapRes : &p.mapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                                        const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                       CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                       CU_TENSOR_MAP_SWIZZLE_64B,
+                                       which ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         NLC_REQUIRE(r == CUDA_SUCCESS, "nlc_conv_tc: cuTensorMapEncodeTiled(%s) failed with %d", which ? "residual" : "output",
                     (int)r);
