@@ -26,7 +26,8 @@ namespace nlc {
 
 // ---------------------------------------------------------------- patches
 // x [B,H,W,C] -> P [B*Ho*Wo, C*9], column c*9 + (kh*3 + kw): torch's weight.view(Cout, Cin*9) is the GEMM's right operand.
-// down = 0: stride 1, zero padding 1;  down = 1: F.pad(x, (0,1,0,1)) then stride 2, no padding (src/unet_ddim.py:89-94).
+// down = 0: stride 1, zero padding 1;  down = 1: F.pad(x, (0,1,0,1)) then stride 2, no padding (src/unet_ddim.py:89-94);
+// down = 2: stride 2, zero padding 1 (guided-diffusion Downsample, src/unet_adm.py:143-166: the ADM sigma-model).
 __global__ void unfold3x3_kernel(const float* __restrict__ x, int B, int H, int W, int C, int down, int Ho, int Wo,
                                  float* __restrict__ P) {
     const long long total = static_cast<long long>(B) * Ho * Wo * C * 9;
@@ -37,7 +38,8 @@ __global__ void unfold3x3_kernel(const float* __restrict__ x, int B, int H, int 
         const long long m = i / (9LL * C);
         const int wo = static_cast<int>(m % Wo), ho = static_cast<int>((m / Wo) % Ho), n = static_cast<int>(m / (Wo * Ho));
         const int kh = tap / 3, kw = tap - kh * 3;
-        const int h = down ? 2 * ho + kh : ho + kh - 1, w = down ? 2 * wo + kw : wo + kw - 1;
+        const int off = down == 1 ? 0 : 1;  // rows 2 ho + kh (down 1), 2 ho + kh - 1 (down 2), ho + kh - 1 (stride 1)
+        const int h = (down ? 2 * ho : ho) + kh - off, w = (down ? 2 * wo : wo) + kw - off;
         float v = 0.f;
         if (h >= 0 && h < H && w >= 0 && w < W) v = x[((static_cast<size_t>(n) * H + h) * W + w) * C + c];
         P[i] = v;
@@ -56,8 +58,9 @@ __global__ void fold3x3_kernel(const float* __restrict__ dP, int B, int H, int W
         for (int kh = 0; kh < 3; ++kh) {
             int ho;
             if (down) {
-                if ((h - kh) < 0 || ((h - kh) & 1)) continue;
-                ho = (h - kh) >> 1;
+                const int q = h - kh + (down == 2 ? 1 : 0);  // 2 ho = h - kh (+ 1 with padding 1)
+                if (q < 0 || (q & 1)) continue;
+                ho = q >> 1;
             } else {
                 ho = h - kh + 1;
             }
@@ -65,8 +68,9 @@ __global__ void fold3x3_kernel(const float* __restrict__ dP, int B, int H, int W
             for (int kw = 0; kw < 3; ++kw) {
                 int wo;
                 if (down) {
-                    if ((w - kw) < 0 || ((w - kw) & 1)) continue;
-                    wo = (w - kw) >> 1;
+                    const int q = w - kw + (down == 2 ? 1 : 0);
+                    if (q < 0 || (q & 1)) continue;
+                    wo = q >> 1;
                 } else {
                     wo = w - kw + 1;
                 }
@@ -335,8 +339,8 @@ extern "C" int nlc_sgemm(nlc_ctx* ctx, int batch, int M, int N, int K, const flo
 
 extern "C" int nlc_unfold3x3(nlc_ctx* ctx, const float* x, int B, int H, int W, int C, int down, float* P, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    NLC_REQUIRE(ctx && x && P && (down == 0 || down == 1), "nlc_unfold3x3: bad arguments");
-    const int Ho = down ? (H + 1 - 3) / 2 + 1 : H, Wo = down ? (W + 1 - 3) / 2 + 1 : W;
+    NLC_REQUIRE(ctx && x && P && down >= 0 && down <= 2, "nlc_unfold3x3: bad arguments");
+    const int Ho = down ? (H + down - 3) / 2 + 1 : H, Wo = down ? (W + down - 3) / 2 + 1 : W;
     unfold3x3_kernel<<<grid1d(static_cast<long long>(B) * Ho * Wo * C * 9, ctx->sm_count), 256, 0, st>>>(x, B, H, W, C, down, Ho,
                                                                                                        Wo, P);
     NLC_CHECK_LAUNCH();
@@ -346,8 +350,8 @@ extern "C" int nlc_unfold3x3(nlc_ctx* ctx, const float* x, int B, int H, int W, 
 extern "C" int nlc_fold3x3(nlc_ctx* ctx, const float* dP, int B, int H, int W, int C, int down, float* dx, float beta,
                            void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    NLC_REQUIRE(ctx && dP && dx && (down == 0 || down == 1), "nlc_fold3x3: bad arguments");
-    const int Ho = down ? (H + 1 - 3) / 2 + 1 : H, Wo = down ? (W + 1 - 3) / 2 + 1 : W;
+    NLC_REQUIRE(ctx && dP && dx && down >= 0 && down <= 2, "nlc_fold3x3: bad arguments");
+    const int Ho = down ? (H + down - 3) / 2 + 1 : H, Wo = down ? (W + down - 3) / 2 + 1 : W;
     fold3x3_kernel<<<grid1d(static_cast<long long>(B) * H * W * C, ctx->sm_count), 256, 0, st>>>(dP, B, H, W, C, down, Ho, Wo, dx,
                                                                                                  beta);
     NLC_CHECK_LAUNCH();

@@ -1,17 +1,20 @@
-"""First slice of the sigma-model training step (src/experiments.py:632-700) on libnlc_b200.
+"""The sigma-model training step (src/experiments.py:632-700) on libnlc_b200.
 
 One iteration of the reference: perturb the noise and diffuse the batch (:658-669), run the FROZEN UNet's `encode` under
 no-grad (:673-682; 99 % of the step's FLOPs), sigma-model forward, loss against the true noise level, backward (:683-691),
 AdamW on the master parameters and an EMA copy (:692-694).  Built natively here: the batch preparation (`nlc_train_prepare`,
-one pass), the encoder (the sampling path's engine, any of the three network classes) and the optimizer + EMA update
-(`nlc_adamw_ema_step`, one pass over a flat buffer).  NOT built: the sigma-model's own forward / backward — it stays an
-ordinary `torch.nn.Module` under autograd (pass the reference's module, or any module with the same signature).
+one pass), the encoder (the sampling path's engine, any of the three network classes), the optimizer + EMA update
+(`nlc_adamw_ema_step`, one pass over a flat buffer) and - `NativeSigmaModel` / `train_step_native` - the sigma-model's own
+training-mode forward and backward for the DDIM family (src/unet_ddim.py:493-529) and the ADM family
+(src/unet_adm.py:1029-1083).  `SigmaTrainer` / `train_step` keep the first slice: any `torch.nn.Module` sigma-model under
+autograd (the EDM family's, or the reference's own modules) between the native preparation, encoder and optimizer.
 
 Data parallelism: the reference wraps the sigma-model in DDP but runs forward and backward under `no_sync()` (:683-687), so
 its ranks never average their gradients.  `SigmaTrainer.step` all-reduces the flat gradient buffer over NCCL (one
 collective per step, folded mean) before the update, which is what the DDP wrapper was meant to do.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -140,7 +143,9 @@ class _Flat:
 
 class NativeSigmaModel:
     """The DDIM-family sigma-model (src/unet_ddim.py:493-529: per block PureResnetBlock [-> AttnBlock in block 0] ->
-    Downsample; Flatten -> Linear -> BatchNorm1d -> GELU -> Linear) with a native training-mode forward AND backward pass:
+    Downsample; Flatten -> Linear -> BatchNorm1d -> GELU -> Linear) or, with family="adm", the ADM-family one
+    (src/unet_adm.py:1029-1083: PureResNetBlock, multi-head AttentionBlock, stride-2 Downsample; the c4 / c5 sigma-model is
+    dim 8, 1024 channels, 16 heads) with a native training-mode forward AND backward pass:
     `loss_and_grad(feat, dist_real)` is `dist_hat = model(feat) + 1; loss = loss_fn(dist_real, dist_hat); loss.backward()`
     of src/experiments.py:688-691 without autograd.  Parameters and gradients live in flat fp32 buffers in the reference's
     parameter layout (`params[name]`, `grads[name]`), which `step()` updates with the fused AdamW + EMA kernel (gradients
@@ -149,7 +154,23 @@ class NativeSigmaModel:
 
     GROUPS, GN_EPS, BN_EPS, BN_MOMENTUM = 32, 1e-6, 1e-5, 0.1
 
-    def __init__(self, dim=4, channels=64, n_blocks=2, out_dim=1, dropout=0.1, loss="l2", device="cuda"):
+    def __init__(self, dim=4, channels=64, n_blocks=2, out_dim=1, dropout=0.1, loss="l2", device="cuda", family="ddim",
+                 num_heads=1, num_head_channels=-1, use_new_attention_order=False):
+        """family "ddim": src/unet_ddim.py:493-529 (single-head AttnBlock with separate q / k / v convolutions, GroupNorm eps
+        1e-6, Downsample = pad (0,1,0,1) + stride 2).  family "adm": src/unet_adm.py:1029-1083 (PureResNetBlock with
+        in_layers / out_layers, AttentionBlock with one qkv projection and `num_heads` / `num_head_channels` heads in the
+        legacy or the new channel order, GroupNorm32 eps 1e-5, Downsample = stride 2 with padding 1)."""
+        if family not in ("ddim", "adm"):
+            raise NotImplementedError("sigma-model family '%s': 'ddim' and 'adm' have a native backward" % family)
+        self.family = family
+        if family == "adm":
+            self.GN_EPS = 1e-5
+            self.heads = channels // num_head_channels if num_head_channels != -1 else num_heads
+            assert channels % self.heads == 0
+        else:
+            self.heads = 1
+        self.new_order = bool(use_new_attention_order)
+        self.down_mode = 1 if family == "ddim" else 2
         if out_dim != 1:
             raise NotImplementedError("out_dim != 1 is not used by the reference")
         if dim % (2 ** n_blocks) != 0:
@@ -180,17 +201,21 @@ class NativeSigmaModel:
         self.num_batches_tracked = int(sd.get("fc_layer.2.num_batches_tracked", 0))
         # module slots: block i owns (pad/identity, resblock, [attn], downsample)
         self.blocks, idx = [], 0
+        adm = self.family == "adm"
         for i in range(self.n_blocks):
             idx += 1
-            blk = {"res": "down_layer.%d." % idx}
+            r = "down_layer.%d." % idx
+            blk = {"norm1": r + ("in_layers.0" if adm else "norm1"), "conv1": r + ("in_layers.2" if adm else "conv1"),
+                   "norm2": r + ("out_layers.0" if adm else "norm2"), "conv2": r + ("out_layers.3" if adm else "conv2")}
             idx += 1
             if i == 0:
                 blk["attn"] = "down_layer.%d." % idx
                 idx += 1
-            blk["down"] = "down_layer.%d." % idx
+            blk["down"] = "down_layer.%d." % idx + ("op" if adm else "conv")
             idx += 1
             self.blocks.append(blk)
-        need = [self.blocks[0]["res"] + "conv1.weight", self.blocks[0]["attn"] + "q.weight", "fc_layer.1.weight", "final_mlp.weight"]
+        need = [self.blocks[0]["conv1"] + ".weight", self.blocks[0]["attn"] + ("qkv.weight" if adm else "q.weight"),
+                "fc_layer.1.weight", "final_mlp.weight"]
         missing = [k for k in need if k not in shapes]
         if missing:
             raise KeyError("sigma-model state_dict lacks %s" % missing)
@@ -310,6 +335,13 @@ class NativeSigmaModel:
                          self.grads[name + ".weight"].view(Cc, 9 * Cc), self.grads[name + ".bias"], dP)
         _lib.check(self._lib.nlc_fold3x3(self._ctx, dP.data_ptr(), B, H, W, Cc, down, dx.data_ptr(), beta, _stream()))
 
+    def _head_view(self, qkv, B, HW, nh, ch, which):
+        """[B, T, heads, ch] view of q (0) / k (1) / v (2) inside a [B*T, 3C] projection: legacy order = per head
+        [q | k | v] (src/unet_adm.py:340-345), new order = [q | k | v] x [head] (:373-377)."""
+        if self.new_order:
+            return qkv.view(B, HW, 3, nh, ch)[:, :, which]
+        return qkv.view(B, HW, nh, 3, ch)[:, :, :, which]
+
     def _axpby(self, a, x, b, y, out):
         _lib.check(self._lib.nlc_axpby(self._ctx, a, x.data_ptr(), b, C.c_void_p(y.data_ptr()) if y is not None else None,
                                        out.data_ptr(), out.numel(), _stream()))
@@ -355,23 +387,48 @@ class NativeSigmaModel:
             _lib.check(L.nlc_permute_nhwc(ctx, feat.data_ptr(), B, dim * dim, Cc, 0, x.data_ptr(), _stream()))
         saved, H = [], dim
         for bi, blk in enumerate(self.blocks):
-            M, HW, r = B * H * H, H * H, blk["res"]
+            M, HW = B * H * H, H * H
             t = "b%d" % bi
             a1, st1 = self._buf(t + ".a1", M, Cc), self._buf(t + ".st1", B * self.GROUPS * 2)
-            self._gn(x, B, HW, r + "norm1", 1, a1, st1)
-            c1, P1 = self._conv3(a1, B, H, H, r + "conv1", 0, t + ".c1")
+            self._gn(x, B, HW, blk["norm1"], 1, a1, st1)
+            c1, P1 = self._conv3(a1, B, H, H, blk["conv1"], 0, t + ".c1")
             a2, st2 = self._buf(t + ".a2", M, Cc), self._buf(t + ".st2", B * self.GROUPS * 2)
-            self._gn(c1, B, HW, r + "norm2", 1, a2, st2)
+            self._gn(c1, B, HW, blk["norm2"], 1, a2, st2)
             mask = None
             if self.training and self.p_drop > 0:
                 mask = (torch.rand(M, Cc, device=self.device) >= self.p_drop).float() / (1.0 - self.p_drop)
                 a2.mul_(mask)
-            c2, P2 = self._conv3(a2, B, H, H, r + "conv2", 0, t + ".c2")
+            c2, P2 = self._conv3(a2, B, H, H, blk["conv2"], 0, t + ".c2")
             y = self._buf(t + ".y", M, Cc)
             self._axpby(1.0, x, 1.0, c2, y)
             rec = dict(x=x, st1=st1, P1=P1, c1=c1, st2=st2, P2=P2, mask=mask, H=H)
             z = y
-            if "attn" in blk:
+            if "attn" in blk and self.family == "adm":
+                # AttentionBlock (src/unet_adm.py:299-305): one qkv projection, `heads` heads of ch channels; the heads
+                # are regrouped into [B * heads, T, ch] operands (torch copies: data movement only) around the batched GEMMs
+                a, nh = blk["attn"], self.heads
+                ch = Cc // nh
+                n, stn = self._buf(t + ".n", M, Cc), self._buf(t + ".stn", B * self.GROUPS * 2)
+                self._gn(y, B, HW, a + "norm", 0, n, stn)
+                qkv = self._buf(t + ".qkv", M, 3 * Cc)
+                self._linear(n, M, Cc, self.params[a + "qkv.weight"].view(3 * Cc, Cc), self.params[a + "qkv.bias"], qkv)
+                q, k, v = (self._buf(t + "." + nm + "h", B * nh, HW, ch) for nm in "qkv")
+                for i, dst in enumerate((q, k, v)):
+                    dst.view(B, nh, HW, ch).copy_(self._head_view(qkv, B, HW, nh, ch, i).permute(0, 2, 1, 3))
+                S, Pm = self._buf(t + ".S", B * nh, HW, HW), self._buf(t + ".Pm", B * nh, HW, HW)
+                self._mm(B * nh, HW, HW, ch, q, (HW * ch, ch, 1), k, (HW * ch, 1, ch), S)
+                scale = float(1.0 / math.sqrt(ch))  # (q ch^-1/4) . (k ch^-1/4), src/unet_adm.py:346-349
+                _lib.check(L.nlc_softmax_rows(ctx, S.data_ptr(), None, B * nh * HW, HW, scale, Pm.data_ptr(), _stream()))
+                Oh = self._buf(t + ".Oh", B * nh, HW, ch)
+                self._mm(B * nh, HW, ch, HW, Pm, (HW * HW, HW, 1), v, (HW * ch, ch, 1), Oh)
+                O = self._buf(t + ".O", M, Cc)
+                O.view(B, HW, nh, ch).copy_(Oh.view(B, nh, HW, ch).permute(0, 2, 1, 3))
+                pr = self._buf(t + ".pr", M, Cc)
+                self._linear(O, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc), self.params[a + "proj_out.bias"], pr)
+                z = self._buf(t + ".z", M, Cc)
+                self._axpby(1.0, y, 1.0, pr, z)
+                rec.update(y=y, n=n, stn=stn, q=q, k=k, v=v, Pm=Pm, O=O, scale=scale)
+            elif "attn" in blk:
                 a = blk["attn"]
                 n, stn = self._buf(t + ".n", M, Cc), self._buf(t + ".stn", B * self.GROUPS * 2)
                 self._gn(y, B, HW, a + "norm", 0, n, stn)
@@ -389,7 +446,7 @@ class NativeSigmaModel:
                 z = self._buf(t + ".z", M, Cc)
                 self._axpby(1.0, y, 1.0, pr, z)
                 rec.update(y=y, n=n, stn=stn, q=q, k=k, v=v, Pm=Pm, O=O, scale=scale)
-            d, Pd = self._conv3(z, B, H, H, blk["down"] + "conv", 1, t + ".d")
+            d, Pd = self._conv3(z, B, H, H, blk["down"], self.down_mode, t + ".d")
             rec.update(Pd=Pd)
             saved.append(rec)
             x, H = d, H // 2
@@ -425,11 +482,35 @@ class NativeSigmaModel:
         for bi in reversed(range(len(self.blocks))):
             blk, rec, t = self.blocks[bi], saved[bi], "b%d" % bi
             H = rec["H"]
-            M, HW, r = B * H * H, H * H, blk["res"]
+            M, HW = B * H * H, H * H
             dz = self._buf(t + ".dz", M, Cc)
-            self._conv3_bwd(dx, rec["Pd"], B, H, H, blk["down"] + "conv", 1, dz, 0.0, t + ".d")
+            self._conv3_bwd(dx, rec["Pd"], B, H, H, blk["down"], self.down_mode, dz, 0.0, t + ".d")
             dy = dz
-            if "attn" in blk:
+            if "attn" in blk and self.family == "adm":
+                a, Pm, scale, nh = blk["attn"], rec["Pm"], rec["scale"], self.heads
+                ch = Cc // nh
+                dO = self._buf(t + ".dO", M, Cc)
+                self._linear_bwd(rec["O"], dz, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc),
+                                 self.grads[a + "proj_out.weight"].view(Cc, Cc), self.grads[a + "proj_out.bias"], dO)
+                dOh = self._buf(t + ".dOh", B * nh, HW, ch)
+                dOh.view(B, nh, HW, ch).copy_(dO.view(B, HW, nh, ch).permute(0, 2, 1, 3))
+                dPm, dS = self._buf(t + ".dPm", B * nh, HW, HW), self._buf(t + ".dS", B * nh, HW, HW)
+                self._mm(B * nh, HW, HW, ch, dOh, (HW * ch, ch, 1), rec["v"], (HW * ch, 1, ch), dPm)
+                dv, dq, dk = (self._buf(t + ".d" + nm + "h", B * nh, HW, ch) for nm in "vqk")
+                self._mm(B * nh, HW, ch, HW, Pm, (HW * HW, 1, HW), dOh, (HW * ch, ch, 1), dv)
+                _lib.check(L.nlc_softmax_rows(ctx, Pm.data_ptr(), dPm.data_ptr(), B * nh * HW, HW, scale, dS.data_ptr(), _stream()))
+                self._mm(B * nh, HW, ch, HW, dS, (HW * HW, HW, 1), rec["k"], (HW * ch, ch, 1), dq)
+                self._mm(B * nh, HW, ch, HW, dS, (HW * HW, 1, HW), rec["q"], (HW * ch, ch, 1), dk)
+                dqkv = self._buf(t + ".dqkv", M, 3 * Cc)
+                for i, src in enumerate((dq, dk, dv)):
+                    self._head_view(dqkv, B, HW, nh, ch, i).copy_(src.view(B, nh, HW, ch).permute(0, 2, 1, 3))
+                dn = self._buf(t + ".dn", M, Cc)
+                self._linear_bwd(rec["n"], dqkv, M, Cc, self.params[a + "qkv.weight"].view(3 * Cc, Cc),
+                                 self.grads[a + "qkv.weight"].view(3 * Cc, Cc), self.grads[a + "qkv.bias"], dn)
+                dy = self._buf(t + ".dy", M, Cc)
+                dy.copy_(dz)
+                self._gn_bwd(rec["y"], dn, B, HW, a + "norm", 0, rec["stn"], dy, True)
+            elif "attn" in blk:
                 a, Pm, scale = blk["attn"], rec["Pm"], rec["scale"]
                 dO = self._buf(t + ".dO", M, Cc)
                 self._linear_bwd(rec["O"], dz, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc),
@@ -453,16 +534,16 @@ class NativeSigmaModel:
                 self._gn_bwd(rec["y"], dn, B, HW, a + "norm", 0, rec["stn"], dy, True)
             # ResBlock: y = x + conv2(drop(swish(gn2(conv1(swish(gn1(x)))))))
             da2 = self._buf(t + ".da2", M, Cc)
-            self._conv3_bwd(dy, rec["P2"], B, H, H, r + "conv2", 0, da2, 0.0, t + ".c2")
+            self._conv3_bwd(dy, rec["P2"], B, H, H, blk["conv2"], 0, da2, 0.0, t + ".c2")
             if rec["mask"] is not None:
                 da2.mul_(rec["mask"])
             dc1 = self._buf(t + ".dc1", M, Cc)
-            self._gn_bwd(rec["c1"], da2, B, HW, r + "norm2", 1, rec["st2"], dc1, False)
+            self._gn_bwd(rec["c1"], da2, B, HW, blk["norm2"], 1, rec["st2"], dc1, False)
             da1 = self._buf(t + ".da1", M, Cc)
-            self._conv3_bwd(dc1, rec["P1"], B, H, H, r + "conv1", 0, da1, 0.0, t + ".c1")
+            self._conv3_bwd(dc1, rec["P1"], B, H, H, blk["conv1"], 0, da1, 0.0, t + ".c1")
             dxin = self._buf(t + ".dx", M, Cc)
             dxin.copy_(dy)
-            self._gn_bwd(rec["x"], da1, B, HW, r + "norm1", 1, rec["st1"], dxin, True)
+            self._gn_bwd(rec["x"], da1, B, HW, blk["norm1"], 1, rec["st1"], dxin, True)
             dx = dxin
         return loss, dist_hat
 

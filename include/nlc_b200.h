@@ -187,7 +187,8 @@ int nlc_resample(nlc_ctx* ctx, const float* x, int ld_x, int B, int H, int W, in
 int nlc_sgemm(nlc_ctx* ctx, int batch, int M, int N, int K, const float* A, long long sab, long long sai, long long sak,
               const float* Bm, long long sbb, long long sbk, long long sbj, float* Cm, const float* add, void* stream);
 /* x [B,H,W,C] -> patches [B*Ho*Wo, C*9] with column c*9 + kh*3 + kw (torch's weight.view(Cout, Cin*9) multiplies them);
- * down 0: stride 1, zero padding 1; down 1: the reference's Downsample, F.pad(x,(0,1,0,1)) then stride 2 (src/unet_ddim.py:89-94).
+ * down 0: stride 1, zero padding 1; down 1: the reference's Downsample, F.pad(x,(0,1,0,1)) then stride 2 (src/unet_ddim.py:89-94);
+ * down 2: stride 2, zero padding 1 (guided-diffusion Downsample of the ADM sigma-model, src/unet_adm.py:143-166).
  * nlc_fold3x3 is the adjoint: dx = beta*dx + sum of the patch gradients that read each pixel. */
 int nlc_unfold3x3(nlc_ctx* ctx, const float* x, int B, int H, int W, int C, int down, float* patches, void* stream);
 int nlc_fold3x3(nlc_ctx* ctx, const float* d_patches, int B, int H, int W, int C, int down, float* dx, float beta, void* stream);

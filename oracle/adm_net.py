@@ -164,8 +164,9 @@ def unet_forward(sd, x, t, cfg, return_feat=False):
     return (out, feat) if return_feat else out
 
 
-def sigma_forward(sd, feat, cfg):
-    """src/unet_adm.py:1029-1083."""
+def sigma_forward(sd, feat, cfg, training=False):
+    """src/unet_adm.py:1029-1083.  training=True: BatchNorm1d with batch statistics (the module in train mode, dropout 0) -
+    the forward the native backward pass of nlc_b200.training.NativeSigmaModel(family="adm") is checked against."""
     h = feat
     max_idx = max(int(k.split(".")[1]) for k in sd if k.startswith("down_layer."))
     for idx in range(max_idx + 1):
@@ -179,6 +180,9 @@ def sigma_forward(sd, feat, cfg):
         elif p + "op.weight" in sd:
             h = _conv(sd, p + "op", h, stride=2)
     h = F.linear(h.flatten(1), sd["fc_layer.1.weight"], sd["fc_layer.1.bias"])
-    h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
-                     sd["fc_layer.2.bias"], training=False, eps=1e-5)
+    if training:
+        h = F.batch_norm(h, None, None, sd["fc_layer.2.weight"], sd["fc_layer.2.bias"], training=True, eps=1e-5)
+    else:
+        h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
+                         sd["fc_layer.2.bias"], training=False, eps=1e-5)
     return F.linear(F.gelu(h), sd["final_mlp.weight"], sd["final_mlp.bias"])[:, :, None, None]

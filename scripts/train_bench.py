@@ -11,17 +11,29 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from nlc_b200 import training as T
-from oracle import ddim_net, weights
+from oracle import adm_net, ddim_net, weights
 
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-for name in ("c2", "c1"):
-    cfg = weights.CONFIGS[name]["sigma"]
-    ssd = weights.ddim_sigma_state_dict(**cfg, seed=4)
+for name in ("c2", "c1", "adm256"):  # adm256: the c4 / c5 sigma-model (dim 8, 1024 channels, 16 heads; ADM family)
+    if name.startswith("adm"):
+        acfg = dict(weights.ADM_CONFIGS[name])
+        cfg = acfg.pop("sigma")
+        ssd = weights.adm_sigma_state_dict(**cfg, seed=4)
+        extra = dict(family="adm", num_heads=acfg["num_heads"], num_head_channels=acfg["num_head_channels"],
+                     use_new_attention_order=acfg["use_new_attention_order"])
+        fwd = lambda sd_, f_: adm_net.sigma_forward(sd_, f_, acfg, training=True)
+        Bn = min(B, 64)
+    else:
+        cfg = weights.CONFIGS[name]["sigma"]
+        ssd = weights.ddim_sigma_state_dict(**cfg, seed=4)
+        extra = {}
+        fwd = lambda sd_, f_: ddim_net.sigma_forward(sd_, f_, training=True)
+        Bn = B
     g = torch.Generator().manual_seed(1)
-    feat = torch.randn(B, cfg["dim"], cfg["dim"], cfg["channels"], generator=g).to(dev)  # NHWC, as the engine hands it over
-    target = (1 + 0.3 * torch.randn(B, generator=g)).to(dev)
-    m = T.NativeSigmaModel(**cfg, dropout=0.0, loss="l2", device=dev).load_state_dict(ssd)
+    feat = torch.randn(Bn, cfg["dim"], cfg["dim"], cfg["channels"], generator=g).to(dev)  # NHWC, as the engine hands it over
+    target = (1 + 0.3 * torch.randn(Bn, generator=g)).to(dev)
+    m = T.NativeSigmaModel(**cfg, dropout=0.0, loss="l2", device=dev, **extra).load_state_dict(ssd)
 
     def native():
         m.loss_and_grad(feat, target, nhwc=True)
@@ -39,7 +51,7 @@ for name in ("c2", "c1"):
 
     def autograd():
         opt.zero_grad(set_to_none=True)
-        loss = torch.nn.functional.mse_loss(ddim_net.sigma_forward(sd, feat_nchw, training=True).reshape(-1) + 1, target)
+        loss = torch.nn.functional.mse_loss(fwd(sd, feat_nchw).reshape(-1) + 1, target)
         loss.backward()
         opt.step()
         for e, p in zip(ema, params.values()):
@@ -59,4 +71,4 @@ for name in ("c2", "c1"):
 
     tn, ta = timed(native), timed(autograd)
     print("%s sigma-model (dim %d, %d channels), batch %d: native fwd+bwd+AdamW/EMA %.2f ms, torch autograd (cuDNN, TF32 allowed) "
-          "+ torch.optim.AdamW + EMA loop %.2f ms" % (name, cfg["dim"], cfg["channels"], B, tn, ta), flush=True)
+          "+ torch.optim.AdamW + EMA loop %.2f ms" % (name, cfg["dim"], cfg["channels"], Bn, tn, ta), flush=True)

@@ -217,6 +217,46 @@ def test_native_sigma_model_gradients_against_autograd(name, B, loss):
         assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
 
 
+@pytest.mark.parametrize("name,B,loss", [("adm_tiny", 4, "l2"), ("adm_alt", 6, "l1")])
+def test_native_adm_sigma_model_gradients_against_autograd(name, B, loss):
+    """The ADM-family sigma-model (src/unet_adm.py:1029-1083: PureResNetBlock, multi-head AttentionBlock in the legacy /
+    new channel order, stride-2 padding-1 Downsample, GroupNorm32 eps 1e-5) trained natively: loss, dist_hat, every
+    gradient and the BatchNorm running statistics against torch autograd through the oracle's train-mode forward (which
+    tests/test_oracle_vs_reference.py pins to the reference's own module in train mode)."""
+    from nlc_b200 import training as T
+    from oracle import adm_net
+    cfg = dict(weights.ADM_CONFIGS[name])
+    sg = cfg.pop("sigma")
+    ssd = weights.adm_sigma_state_dict(**sg, seed=9)
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(B, sg["channels"], sg["dim"], sg["dim"], generator=g)
+    target = 1.0 + 0.3 * torch.randn(B, 1, 1, 1, generator=g)
+    names = [k for k in ssd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    sd = dict(ssd)
+    sd.update(params)
+    dist_hat = adm_net.sigma_forward(sd, feat, cfg, training=True) + 1
+    ref_loss = (torch.nn.functional.mse_loss if loss == "l2" else torch.nn.functional.l1_loss)(dist_hat, target)
+    ref_loss.backward()
+    m = T.NativeSigmaModel(**sg, dropout=0.0, loss=loss, device=dev, family="adm", num_heads=cfg["num_heads"],
+                           num_head_channels=cfg["num_head_channels"],
+                           use_new_attention_order=cfg["use_new_attention_order"]).load_state_dict(ssd)
+    got, dh = m.loss_and_grad(feat.permute(0, 2, 3, 1).contiguous().to(dev), target.to(dev), nhwc=True)
+    assert abs(got.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert (dh.cpu() - dist_hat.detach().reshape(-1)).abs().max() <= 1e-5
+    gmax = max(float(params[n].grad.norm()) for n in names)
+    for n in names:
+        a, b = m.grads[n].cpu().double(), params[n].grad.double()
+        assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
+    # the captured replay of the pass gives the same gradients; one optimizer step runs
+    ref_grads = m.grads.flat.clone()
+    m.loss_and_grad(feat.permute(0, 2, 3, 1).contiguous().to(dev), target.to(dev), nhwc=True)
+    assert (m.grads.flat - ref_grads).norm() <= 1e-5 * ref_grads.norm()
+    before = m.params.flat.clone()
+    m.step(1e-3, weight_decay=0.01)
+    assert torch.isfinite(m.params.flat).all() and (m.params.flat - before).abs().max() > 0
+
+
 def test_native_sigma_model_graph_replay_and_dropout():
     """The captured pass (second and later calls at a batch size) equals the eager one; with dropout the pass runs, the masks
     of forward and backward agree (the loss decreases along -grad), and load_state_dict drops the captured graphs."""

@@ -288,6 +288,34 @@ def test_adm_networks(R, name):
         assert torch.equal(snet(f), adm_net.sigma_forward(ssd, f, cfg))
 
 
+@pytest.mark.parametrize("name", ["adm_tiny", "adm_alt"])
+def test_adm_sigma_model_train_mode_and_gradients(R, name):
+    """The oracle's TRAIN-mode ADM sigma-model forward (batch-statistics BatchNorm1d; dropout 0) and its autograd gradients
+    against the reference's own module in train mode: the target nlc_b200.training.NativeSigmaModel(family="adm") is held to
+    on the GPU (tests/test_gpu_training.py)."""
+    from oracle import adm_net
+    cfg, sg, sd, ssd, net, snet = _make_golden().adm_reference_modules(name)
+    g = torch.Generator().manual_seed(6)
+    feat = torch.randn(5, sg["channels"], sg["dim"], sg["dim"], generator=g)
+    target = 1.0 + 0.3 * torch.randn(5, 1, 1, 1, generator=g)
+    snet.train()
+    for mod in snet.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    ref = torch.nn.functional.mse_loss(snet(feat) + 1, target)
+    ref.backward()
+    names = [k for k, _ in snet.named_parameters()]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    mine = dict(ssd)
+    mine.update(params)
+    loss = torch.nn.functional.mse_loss(adm_net.sigma_forward(mine, feat, cfg, training=True) + 1, target)
+    loss.backward()
+    assert torch.allclose(loss, ref, rtol=1e-6, atol=0)
+    gmax = max(float(p.grad.norm()) for p in snet.parameters())
+    for n, p_ref in snet.named_parameters():
+        assert (params[n].grad - p_ref.grad).norm() <= 1e-5 * p_ref.grad.norm() + 1e-7 * gmax, n
+
+
 def test_adm256_layout(R):
     """Key names / shapes of the c4/c5 architecture (no forward: 553 M parameters)."""
     import importlib
