@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128) bn1d_train_fwd_kernel(const float* __rest
                                                              float momentum, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ run_mean,
                                                              float* __restrict__ run_var, float* __restrict__ stats,
-                                                             float* __restrict__ y) {
+                                                             float* __restrict__ y, int act) {
     __shared__ float red[8];
     const int f = blockIdx.x;
     float s = 0.f;
@@ -265,15 +265,22 @@ __global__ void __launch_bounds__(128) bn1d_train_fwd_kernel(const float* __rest
     }
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float z = (x[static_cast<size_t>(b) * F + f] - mean) * rstd * gamma[f] + beta[f];
-        y[static_cast<size_t>(b) * F + f] = 0.5f * z * (1.0f + erff(z * 0.70710678118654752f));
+        // act 0: GELU(erf) (the DDIM / ADM sigma-models), 1: SiLU (the EDM sigma-model, src/edm_networks.py:1006-1010)
+        y[static_cast<size_t>(b) * F + f] = act == 0 ? 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)) : z / (1.0f + expf(-z));
     }
+}
+// derivative of the head's activation at z
+__device__ __forceinline__ float head_act_grad(float z, int act) {
+    if (act == 0) return 0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z);
+    const float sg = 1.0f / (1.0f + expf(-z));
+    return sg * (1.0f + z * (1.0f - sg));
 }
 // dy: gradient wrt gelu output -> dx, dgamma[f], dbeta[f]
 __global__ void __launch_bounds__(128) bn1d_train_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B,
                                                              int F, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, const float* __restrict__ stats,
                                                              float* __restrict__ dx, float* __restrict__ dgamma,
-                                                             float* __restrict__ dbeta) {
+                                                             float* __restrict__ dbeta, int act) {
     __shared__ float red[8];
     const int f = blockIdx.x;
     const float mean = stats[2 * f], rstd = stats[2 * f + 1], g = gamma[f], bt = beta[f];
@@ -281,9 +288,8 @@ __global__ void __launch_bounds__(128) bn1d_train_bwd_kernel(const float* __rest
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float xh = (x[static_cast<size_t>(b) * F + f] - mean) * rstd;
         const float z = xh * g + bt;
-        // gelu'(z) = Phi(z) + z phi(z)
-        const float dz = dy[static_cast<size_t>(b) * F + f] *
-                         (0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z));
+        // gelu'(z) = Phi(z) + z phi(z);  silu'(z) = s (1 + z (1 - s))
+        const float dz = dy[static_cast<size_t>(b) * F + f] * head_act_grad(z, act);
         sg += dz * xh, sb += dz;
     }
     sg = block_sum_256(sg, red), sb = block_sum_256(sb, red);
@@ -291,8 +297,7 @@ __global__ void __launch_bounds__(128) bn1d_train_bwd_kernel(const float* __rest
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float xh = (x[static_cast<size_t>(b) * F + f] - mean) * rstd;
         const float z = xh * g + bt;
-        const float dz = dy[static_cast<size_t>(b) * F + f] *
-                         (0.5f * (1.0f + erff(z * 0.70710678118654752f)) + z * 0.3989422804014327f * expf(-0.5f * z * z));
+        const float dz = dy[static_cast<size_t>(b) * F + f] * head_act_grad(z, act);
         dx[static_cast<size_t>(b) * F + f] = rstd * g * (dz - sb / static_cast<float>(B) - xh * sg / static_cast<float>(B));
     }
 }
@@ -421,19 +426,27 @@ extern "C" int nlc_permute_nhwc(nlc_ctx* ctx, const float* x, int B, int HW, int
     return NLC_OK;
 }
 
-extern "C" int nlc_bn1d_gelu_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int F, float eps, float momentum,
-                                   const float* gamma, const float* beta, float* run_mean, float* run_var, float* stats,
-                                   float* out, float* dgamma, float* dbeta, void* stream_) {
-    NLC_REQUIRE(ctx && x && gamma && beta && stats && out && B >= 1 && F >= 1, "nlc_bn1d_gelu_train: bad arguments");
+extern "C" int nlc_bn1d_act_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int F, float eps, float momentum, int act,
+                                  const float* gamma, const float* beta, float* run_mean, float* run_var, float* stats,
+                                  float* out, float* dgamma, float* dbeta, void* stream_) {
+    NLC_REQUIRE(ctx && x && gamma && beta && stats && out && B >= 1 && F >= 1 && (act == 0 || act == 1),
+                "nlc_bn1d_act_train: bad arguments (act 0 = GELU, 1 = SiLU)");
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (dy) {
-        NLC_REQUIRE(dgamma && dbeta, "nlc_bn1d_gelu_train: backward needs dgamma / dbeta");
-        bn1d_train_bwd_kernel<<<F, 128, 0, st>>>(x, dy, B, F, gamma, beta, stats, out, dgamma, dbeta);
+        NLC_REQUIRE(dgamma && dbeta, "nlc_bn1d_act_train: backward needs dgamma / dbeta");
+        bn1d_train_bwd_kernel<<<F, 128, 0, st>>>(x, dy, B, F, gamma, beta, stats, out, dgamma, dbeta, act);
     } else {
-        bn1d_train_fwd_kernel<<<F, 128, 0, st>>>(x, B, F, eps, momentum, gamma, beta, run_mean, run_var, stats, out);
+        bn1d_train_fwd_kernel<<<F, 128, 0, st>>>(x, B, F, eps, momentum, gamma, beta, run_mean, run_var, stats, out, act);
     }
     NLC_CHECK_LAUNCH();
     return NLC_OK;
+}
+
+extern "C" int nlc_bn1d_gelu_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int F, float eps, float momentum,
+                                   const float* gamma, const float* beta, float* run_mean, float* run_var, float* stats,
+                                   float* out, float* dgamma, float* dbeta, void* stream_) {
+    return nlc_bn1d_act_train(ctx, x, dy, B, F, eps, momentum, 0, gamma, beta, run_mean, run_var, stats, out, dgamma, dbeta,
+                              stream_);
 }
 
 extern "C" int nlc_head_loss(nlc_ctx* ctx, const float* r, const float* target, int B, int kind, float* dist_hat, float* loss,

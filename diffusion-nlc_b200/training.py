@@ -5,9 +5,10 @@ no-grad (:673-682; 99 % of the step's FLOPs), sigma-model forward, loss against 
 AdamW on the master parameters and an EMA copy (:692-694).  Built natively here: the batch preparation (`nlc_train_prepare`,
 one pass), the encoder (the sampling path's engine, any of the three network classes), the optimizer + EMA update
 (`nlc_adamw_ema_step`, one pass over a flat buffer) and - `NativeSigmaModel` / `train_step_native` - the sigma-model's own
-training-mode forward and backward for the DDIM family (src/unet_ddim.py:493-529) and the ADM family
-(src/unet_adm.py:1029-1083).  `SigmaTrainer` / `train_step` keep the first slice: any `torch.nn.Module` sigma-model under
-autograd (the EDM family's, or the reference's own modules) between the native preparation, encoder and optimizer.
+training-mode forward and backward for all three families: DDIM (src/unet_ddim.py:493-529), ADM
+(src/unet_adm.py:1029-1083) and EDM (src/edm_networks.py:979-1022).  `SigmaTrainer` / `train_step` keep the first slice: any
+`torch.nn.Module` sigma-model under autograd (e.g. the reference's own modules) between the native preparation, encoder and
+optimizer.
 
 Data parallelism: the reference wraps the sigma-model in DDP but runs forward and backward under `no_sync()` (:683-687), so
 its ranks never average their gradients.  `SigmaTrainer.step` all-reduces the flat gradient buffer over NCCL (one
@@ -145,7 +146,9 @@ class NativeSigmaModel:
     """The DDIM-family sigma-model (src/unet_ddim.py:493-529: per block PureResnetBlock [-> AttnBlock in block 0] ->
     Downsample; Flatten -> Linear -> BatchNorm1d -> GELU -> Linear) or, with family="adm", the ADM-family one
     (src/unet_adm.py:1029-1083: PureResNetBlock, multi-head AttentionBlock, stride-2 Downsample; the c4 / c5 sigma-model is
-    dim 8, 1024 channels, 16 heads) with a native training-mode forward AND backward pass:
+    dim 8, 1024 channels, 16 heads), or with family="edm" the EDM one (src/edm_networks.py:979-1022: PureUNetBlock with
+    skip_scale, attention in the even blocks, SiLU head; c3: dim 8, 256 channels) with a native training-mode forward AND
+    backward pass:
     `loss_and_grad(feat, dist_real)` is `dist_hat = model(feat) + 1; loss = loss_fn(dist_real, dist_hat); loss.backward()`
     of src/experiments.py:688-691 without autograd.  Parameters and gradients live in flat fp32 buffers in the reference's
     parameter layout (`params[name]`, `grads[name]`), which `step()` updates with the fused AdamW + EMA kernel (gradients
@@ -159,18 +162,26 @@ class NativeSigmaModel:
         """family "ddim": src/unet_ddim.py:493-529 (single-head AttnBlock with separate q / k / v convolutions, GroupNorm eps
         1e-6, Downsample = pad (0,1,0,1) + stride 2).  family "adm": src/unet_adm.py:1029-1083 (PureResNetBlock with
         in_layers / out_layers, AttentionBlock with one qkv projection and `num_heads` / `num_head_channels` heads in the
-        legacy or the new channel order, GroupNorm32 eps 1e-5, Downsample = stride 2 with padding 1)."""
-        if family not in ("ddim", "adm"):
-            raise NotImplementedError("sigma-model family '%s': 'ddim' and 'adm' have a native backward" % family)
+        legacy or the new channel order, GroupNorm32 eps 1e-5, Downsample = stride 2 with padding 1).  family "edm":
+        src/edm_networks.py:979-1022 (see below; parameters that the reference's forward never applies - `norm1` of a
+        PureUNetBlock - keep a zero gradient, where torch's optimizer skips a parameter without gradient: with weight decay the
+        fused AdamW shrinks them, which changes nothing the model computes)."""
+        if family not in ("ddim", "adm", "edm"):
+            raise NotImplementedError("sigma-model family '%s': 'ddim', 'adm' and 'edm' have a native backward" % family)
         self.family = family
+        self.heads, self.res_scale, self.head_act = 1, 1.0, 0
         if family == "adm":
             self.GN_EPS = 1e-5
             self.heads = channels // num_head_channels if num_head_channels != -1 else num_heads
             assert channels % self.heads == 0
-        else:
-            self.heads = 1
+        elif family == "edm":
+            # src/edm_networks.py:979-1022: PureUNetBlock (conv0 feeds conv1 directly; skip_scale sqrt(0.5) after the residual
+            # add and after the attention add; one head; GroupNorm with min(32, C / 4) groups, eps 1e-6), attention in the
+            # blocks with an even index, the DDIM-style Downsample, and SiLU instead of GELU in the head
+            self.GROUPS = min(32, channels // 4)
+            self.res_scale, self.head_act = math.sqrt(0.5), 1
         self.new_order = bool(use_new_attention_order)
-        self.down_mode = 1 if family == "ddim" else 2
+        self.down_mode = 2 if family == "adm" else 1
         if out_dim != 1:
             raise NotImplementedError("out_dim != 1 is not used by the reference")
         if dim % (2 ** n_blocks) != 0:
@@ -201,20 +212,26 @@ class NativeSigmaModel:
         self.num_batches_tracked = int(sd.get("fc_layer.2.num_batches_tracked", 0))
         # module slots: block i owns (pad/identity, resblock, [attn], downsample)
         self.blocks, idx = [], 0
-        adm = self.family == "adm"
+        adm, edm = self.family == "adm", self.family == "edm"
         for i in range(self.n_blocks):
             idx += 1
             r = "down_layer.%d." % idx
-            blk = {"norm1": r + ("in_layers.0" if adm else "norm1"), "conv1": r + ("in_layers.2" if adm else "conv1"),
-                   "norm2": r + ("out_layers.0" if adm else "norm2"), "conv2": r + ("out_layers.3" if adm else "conv2")}
-            idx += 1
-            if i == 0:
-                blk["attn"] = "down_layer.%d." % idx
+            if edm:  # one module: ResBlock part + (even blocks) attention part
+                blk = {"norm1": r + "norm0", "conv1": r + "conv0", "conv2": r + "conv1"}
+                if i % 2 == 0:
+                    blk["attn"] = r
                 idx += 1
+            else:
+                blk = {"norm1": r + ("in_layers.0" if adm else "norm1"), "conv1": r + ("in_layers.2" if adm else "conv1"),
+                       "norm2": r + ("out_layers.0" if adm else "norm2"), "conv2": r + ("out_layers.3" if adm else "conv2")}
+                idx += 1
+                if i == 0:
+                    blk["attn"] = "down_layer.%d." % idx
+                    idx += 1
             blk["down"] = "down_layer.%d." % idx + ("op" if adm else "conv")
             idx += 1
             self.blocks.append(blk)
-        need = [self.blocks[0]["conv1"] + ".weight", self.blocks[0]["attn"] + ("qkv.weight" if adm else "q.weight"),
+        need = [self.blocks[0]["conv1"] + ".weight", self.blocks[0]["attn"] + ("q.weight" if self.family == "ddim" else "qkv.weight"),
                 "fc_layer.1.weight", "final_mlp.weight"]
         missing = [k for k in need if k not in shapes]
         if missing:
@@ -338,6 +355,8 @@ class NativeSigmaModel:
     def _head_view(self, qkv, B, HW, nh, ch, which):
         """[B, T, heads, ch] view of q (0) / k (1) / v (2) inside a [B*T, 3C] projection: legacy order = per head
         [q | k | v] (src/unet_adm.py:340-345), new order = [q | k | v] x [head] (:373-377)."""
+        if self.family == "edm":  # reshape(B * heads, ch, 3, T).unbind(2): channel = (head * ch + c) * 3 + which
+            return qkv.view(B, HW, nh, ch, 3)[..., which]
         if self.new_order:
             return qkv.view(B, HW, 3, nh, ch)[:, :, which]
         return qkv.view(B, HW, nh, 3, ch)[:, :, :, which]
@@ -392,24 +411,30 @@ class NativeSigmaModel:
             a1, st1 = self._buf(t + ".a1", M, Cc), self._buf(t + ".st1", B * self.GROUPS * 2)
             self._gn(x, B, HW, blk["norm1"], 1, a1, st1)
             c1, P1 = self._conv3(a1, B, H, H, blk["conv1"], 0, t + ".c1")
-            a2, st2 = self._buf(t + ".a2", M, Cc), self._buf(t + ".st2", B * self.GROUPS * 2)
-            self._gn(c1, B, HW, blk["norm2"], 1, a2, st2)
+            rs = self.res_scale
+            if self.family == "edm":  # PureUNetBlock: conv1(dropout(conv0(silu(norm0 x)))), no second normalisation
+                a2, st2 = c1, None
+            else:
+                a2, st2 = self._buf(t + ".a2", M, Cc), self._buf(t + ".st2", B * self.GROUPS * 2)
+                self._gn(c1, B, HW, blk["norm2"], 1, a2, st2)
             mask = None
             if self.training and self.p_drop > 0:
                 mask = (torch.rand(M, Cc, device=self.device) >= self.p_drop).float() / (1.0 - self.p_drop)
                 a2.mul_(mask)
             c2, P2 = self._conv3(a2, B, H, H, blk["conv2"], 0, t + ".c2")
             y = self._buf(t + ".y", M, Cc)
-            self._axpby(1.0, x, 1.0, c2, y)
+            self._axpby(rs, x, rs, c2, y)  # (x + h) * skip_scale; skip_scale = 1 outside the EDM family
             rec = dict(x=x, st1=st1, P1=P1, c1=c1, st2=st2, P2=P2, mask=mask, H=H)
             z = y
-            if "attn" in blk and self.family == "adm":
-                # AttentionBlock (src/unet_adm.py:299-305): one qkv projection, `heads` heads of ch channels; the heads
-                # are regrouped into [B * heads, T, ch] operands (torch copies: data movement only) around the batched GEMMs
+            if "attn" in blk and self.family != "ddim":
+                # AttentionBlock (src/unet_adm.py:299-305) / the attention half of a PureUNetBlock (src/edm_networks.py:
+                # 948-954): one qkv projection, `heads` heads of ch channels; the heads are regrouped into [B * heads, T, ch]
+                # operands (torch copies: data movement only) around the batched GEMMs
                 a, nh = blk["attn"], self.heads
                 ch = Cc // nh
+                anorm, aproj = (a + "norm2", a + "proj") if self.family == "edm" else (a + "norm", a + "proj_out")
                 n, stn = self._buf(t + ".n", M, Cc), self._buf(t + ".stn", B * self.GROUPS * 2)
-                self._gn(y, B, HW, a + "norm", 0, n, stn)
+                self._gn(y, B, HW, anorm, 0, n, stn)
                 qkv = self._buf(t + ".qkv", M, 3 * Cc)
                 self._linear(n, M, Cc, self.params[a + "qkv.weight"].view(3 * Cc, Cc), self.params[a + "qkv.bias"], qkv)
                 q, k, v = (self._buf(t + "." + nm + "h", B * nh, HW, ch) for nm in "qkv")
@@ -424,9 +449,9 @@ class NativeSigmaModel:
                 O = self._buf(t + ".O", M, Cc)
                 O.view(B, HW, nh, ch).copy_(Oh.view(B, nh, HW, ch).permute(0, 2, 1, 3))
                 pr = self._buf(t + ".pr", M, Cc)
-                self._linear(O, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc), self.params[a + "proj_out.bias"], pr)
+                self._linear(O, M, Cc, self.params[aproj + ".weight"].view(Cc, Cc), self.params[aproj + ".bias"], pr)
                 z = self._buf(t + ".z", M, Cc)
-                self._axpby(1.0, y, 1.0, pr, z)
+                self._axpby(rs, y, rs, pr, z)
                 rec.update(y=y, n=n, stn=stn, q=q, k=k, v=v, Pm=Pm, O=O, scale=scale)
             elif "attn" in blk:
                 a = blk["attn"]
@@ -456,10 +481,10 @@ class NativeSigmaModel:
         F1 = self.fc_dim
         f1, g, stb = self._buf("f1", B, F1), self._buf("g", B, F1), self._buf("stb", F1 * 2)
         self._linear(hflat, B, hidden, self.params["fc_layer.1.weight"], self.params["fc_layer.1.bias"], f1)
-        _lib.check(L.nlc_bn1d_gelu_train(ctx, f1.data_ptr(), None, B, F1, self.BN_EPS, self.BN_MOMENTUM,
-                                         self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
-                                         self.run_mean.data_ptr(), self.run_var.data_ptr(), stb.data_ptr(), g.data_ptr(), None,
-                                         None, _stream()))
+        _lib.check(L.nlc_bn1d_act_train(ctx, f1.data_ptr(), None, B, F1, self.BN_EPS, self.BN_MOMENTUM, self.head_act,
+                                        self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
+                                        self.run_mean.data_ptr(), self.run_var.data_ptr(), stb.data_ptr(), g.data_ptr(), None,
+                                        None, _stream()))
         r = self._buf("r", B, 1)
         self._linear(g, B, F1, self.params["final_mlp.weight"], self.params["final_mlp.bias"], r)
         dist_hat, loss, dr = self._buf("dist_hat", B), self._buf("loss", 1), self._buf("dr", B, 1)
@@ -470,10 +495,10 @@ class NativeSigmaModel:
         self._linear_bwd(g, dr, B, F1, self.params["final_mlp.weight"], self.grads["final_mlp.weight"],
                          self.grads["final_mlp.bias"], dg)
         df1 = self._buf("df1", B, F1)
-        _lib.check(L.nlc_bn1d_gelu_train(ctx, f1.data_ptr(), dg.data_ptr(), B, F1, self.BN_EPS, self.BN_MOMENTUM,
-                                         self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
-                                         None, None, stb.data_ptr(), df1.data_ptr(), self.grads["fc_layer.2.weight"].data_ptr(),
-                                         self.grads["fc_layer.2.bias"].data_ptr(), _stream()))
+        _lib.check(L.nlc_bn1d_act_train(ctx, f1.data_ptr(), dg.data_ptr(), B, F1, self.BN_EPS, self.BN_MOMENTUM, self.head_act,
+                                        self.params["fc_layer.2.weight"].data_ptr(), self.params["fc_layer.2.bias"].data_ptr(),
+                                        None, None, stb.data_ptr(), df1.data_ptr(), self.grads["fc_layer.2.weight"].data_ptr(),
+                                        self.grads["fc_layer.2.bias"].data_ptr(), _stream()))
         dh = self._buf("dh", B, hidden)
         self._linear_bwd(hflat, df1, B, hidden, self.params["fc_layer.1.weight"], self.grads["fc_layer.1.weight"],
                          self.grads["fc_layer.1.bias"], dh)
@@ -486,12 +511,18 @@ class NativeSigmaModel:
             dz = self._buf(t + ".dz", M, Cc)
             self._conv3_bwd(dx, rec["Pd"], B, H, H, blk["down"], self.down_mode, dz, 0.0, t + ".d")
             dy = dz
-            if "attn" in blk and self.family == "adm":
+            rs = self.res_scale
+            if "attn" in blk and self.family != "ddim":
                 a, Pm, scale, nh = blk["attn"], rec["Pm"], rec["scale"], self.heads
                 ch = Cc // nh
+                anorm, aproj = (a + "norm2", a + "proj") if self.family == "edm" else (a + "norm", a + "proj_out")
+                if rs != 1.0:  # z = (y + proj) * skip_scale
+                    dzs = self._buf(t + ".dzs", M, Cc)
+                    self._axpby(rs, dz, 0.0, None, dzs)
+                    dz = dzs
                 dO = self._buf(t + ".dO", M, Cc)
-                self._linear_bwd(rec["O"], dz, M, Cc, self.params[a + "proj_out.weight"].view(Cc, Cc),
-                                 self.grads[a + "proj_out.weight"].view(Cc, Cc), self.grads[a + "proj_out.bias"], dO)
+                self._linear_bwd(rec["O"], dz, M, Cc, self.params[aproj + ".weight"].view(Cc, Cc),
+                                 self.grads[aproj + ".weight"].view(Cc, Cc), self.grads[aproj + ".bias"], dO)
                 dOh = self._buf(t + ".dOh", B * nh, HW, ch)
                 dOh.view(B, nh, HW, ch).copy_(dO.view(B, HW, nh, ch).permute(0, 2, 1, 3))
                 dPm, dS = self._buf(t + ".dPm", B * nh, HW, HW), self._buf(t + ".dS", B * nh, HW, HW)
@@ -509,7 +540,7 @@ class NativeSigmaModel:
                                  self.grads[a + "qkv.weight"].view(3 * Cc, Cc), self.grads[a + "qkv.bias"], dn)
                 dy = self._buf(t + ".dy", M, Cc)
                 dy.copy_(dz)
-                self._gn_bwd(rec["y"], dn, B, HW, a + "norm", 0, rec["stn"], dy, True)
+                self._gn_bwd(rec["y"], dn, B, HW, anorm, 0, rec["stn"], dy, True)
             elif "attn" in blk:
                 a, Pm, scale = blk["attn"], rec["Pm"], rec["scale"]
                 dO = self._buf(t + ".dO", M, Cc)
@@ -533,12 +564,19 @@ class NativeSigmaModel:
                 dy.copy_(dz)
                 self._gn_bwd(rec["y"], dn, B, HW, a + "norm", 0, rec["stn"], dy, True)
             # ResBlock: y = x + conv2(drop(swish(gn2(conv1(swish(gn1(x)))))))
+            if rs != 1.0:  # y = (x + conv2(...)) * skip_scale: both branches see skip_scale * dy
+                dys = self._buf(t + ".dys", M, Cc)
+                self._axpby(rs, dy, 0.0, None, dys)
+                dy = dys
             da2 = self._buf(t + ".da2", M, Cc)
             self._conv3_bwd(dy, rec["P2"], B, H, H, blk["conv2"], 0, da2, 0.0, t + ".c2")
             if rec["mask"] is not None:
                 da2.mul_(rec["mask"])
-            dc1 = self._buf(t + ".dc1", M, Cc)
-            self._gn_bwd(rec["c1"], da2, B, HW, blk["norm2"], 1, rec["st2"], dc1, False)
+            if self.family == "edm":
+                dc1 = da2
+            else:
+                dc1 = self._buf(t + ".dc1", M, Cc)
+                self._gn_bwd(rec["c1"], da2, B, HW, blk["norm2"], 1, rec["st2"], dc1, False)
             da1 = self._buf(t + ".da1", M, Cc)
             self._conv3_bwd(dc1, rec["P1"], B, H, H, blk["conv1"], 0, da1, 0.0, t + ".c1")
             dxin = self._buf(t + ".dx", M, Cc)

@@ -212,6 +212,10 @@ int nlc_permute_nhwc(nlc_ctx* ctx, const float* x, int B, int HW, int C, int to_
 int nlc_bn1d_gelu_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int F, float eps, float momentum,
                         const float* gamma, const float* beta, float* run_mean, float* run_var, float* stats, float* out,
                         float* dgamma, float* dbeta, void* stream);
+/* The same with the activation chosen: act 0 = GELU(erf), 1 = SiLU (the head of the EDM sigma-model, src/edm_networks.py:1006-1010). */
+int nlc_bn1d_act_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int F, float eps, float momentum, int act,
+                       const float* gamma, const float* beta, float* run_mean, float* run_var, float* stats, float* out,
+                       float* dgamma, float* dbeta, void* stream);
 /* dist_hat = r + 1 (src/experiments.py:689); loss = MSELoss (kind 0) | L1Loss (kind 1), mean reduction; dr = d loss / d r */
 int nlc_head_loss(nlc_ctx* ctx, const float* r, const float* target, int B, int kind, float* dist_hat, float* loss, float* dr,
                   void* stream);

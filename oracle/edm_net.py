@@ -154,8 +154,9 @@ def unet_forward(sd, x, noise_labels, cfg, return_feat=False):
     return (out, feat) if return_feat else out
 
 
-def sigma_forward(sd, feat):
-    """SigmaModel.forward (src/edm_networks.py:1014-1022)."""
+def sigma_forward(sd, feat, training=False):
+    """SigmaModel.forward (src/edm_networks.py:1014-1022).  training=True: BatchNorm1d with batch statistics (the module in
+    train mode with dropout 0): the forward nlc_b200.training.NativeSigmaModel(family="edm") is differentiated against."""
     h = feat
     max_idx = max(int(k.split(".")[1]) for k in sd if k.startswith("down_layer."))
     for idx in range(max_idx + 1):
@@ -167,8 +168,11 @@ def sigma_forward(sd, feat):
         elif p + "conv.weight" in sd:
             h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[p + "conv.weight"], sd[p + "conv.bias"], stride=2)
     h = F.linear(h.flatten(1), sd["fc_layer.1.weight"], sd["fc_layer.1.bias"])
-    h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
-                     sd["fc_layer.2.bias"], training=False, eps=1e-5)
+    if training:
+        h = F.batch_norm(h, None, None, sd["fc_layer.2.weight"], sd["fc_layer.2.bias"], training=True, eps=1e-5)
+    else:
+        h = F.batch_norm(h, sd["fc_layer.2.running_mean"], sd["fc_layer.2.running_var"], sd["fc_layer.2.weight"],
+                         sd["fc_layer.2.bias"], training=False, eps=1e-5)
     return F.linear(F.silu(h), sd["final_mlp.weight"], sd["final_mlp.bias"])[:, :, None, None]
 
 

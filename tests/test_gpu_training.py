@@ -257,6 +257,40 @@ def test_native_adm_sigma_model_gradients_against_autograd(name, B, loss):
     assert torch.isfinite(m.params.flat).all() and (m.params.flat - before).abs().max() > 0
 
 
+@pytest.mark.parametrize("name,B,loss", [("edm_tiny", 6, "l2"), ("edm64", 4, "l1")])
+def test_native_edm_sigma_model_gradients_against_autograd(name, B, loss):
+    """The EDM-family sigma-model (src/edm_networks.py:979-1022: PureUNetBlock - conv0 feeds conv1 directly, skip_scale
+    sqrt(0.5) after both adds, single-head attention with the interleaved qkv layout in the even blocks - the DDIM-style
+    Downsample and a SiLU head) trained natively: loss, dist_hat and every gradient against autograd through the oracle's
+    train-mode forward (pinned to the reference's module on the CPU); the never-applied norm1 gets a zero gradient."""
+    from nlc_b200 import training as T
+    from oracle import edm_net
+    sg = dict(weights.EDM_CONFIGS[name])["sigma"]
+    ssd = weights.edm_sigma_state_dict(**sg, seed=9)
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(B, sg["channels"], sg["dim"], sg["dim"], generator=g)
+    target = 1.0 + 0.3 * torch.randn(B, 1, 1, 1, generator=g)
+    names = [k for k in ssd if not k.endswith(("running_mean", "running_var", "num_batches_tracked", "resample_filter"))]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    sd = dict(ssd)
+    sd.update(params)
+    dist_hat = edm_net.sigma_forward(sd, feat.clone(), training=True) + 1
+    ref_loss = (torch.nn.functional.mse_loss if loss == "l2" else torch.nn.functional.l1_loss)(dist_hat, target)
+    ref_loss.backward()
+    m = T.NativeSigmaModel(**sg, dropout=0.0, loss=loss, device=dev, family="edm").load_state_dict(ssd)
+    got, dh = m.loss_and_grad(feat.permute(0, 2, 3, 1).contiguous().to(dev), target.to(dev), nhwc=True)
+    assert abs(got.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item())
+    assert (dh.cpu() - dist_hat.detach().reshape(-1)).abs().max() <= 1e-5
+    gmax = max(float(params[n].grad.norm()) for n in names if params[n].grad is not None)
+    for n in names:
+        a = m.grads[n].cpu().double()
+        if params[n].grad is None:  # norm1 of a PureUNetBlock: defined, never applied
+            assert "norm1" in n and float(a.abs().max()) == 0.0, n
+            continue
+        b = params[n].grad.double()
+        assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
+
+
 def test_native_sigma_model_graph_replay_and_dropout():
     """The captured pass (second and later calls at a batch size) equals the eager one; with dropout the pass runs, the masks
     of forward and backward agree (the loss decreases along -grad), and load_state_dict drops the captured graphs."""

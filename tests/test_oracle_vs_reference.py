@@ -316,6 +316,35 @@ def test_adm_sigma_model_train_mode_and_gradients(R, name):
         assert (params[n].grad - p_ref.grad).norm() <= 1e-5 * p_ref.grad.norm() + 1e-7 * gmax, n
 
 
+def test_edm_sigma_model_train_mode_and_gradients(R):
+    """The oracle's train-mode EDM sigma-model forward and its autograd gradients against the reference's own module in train
+    mode (dropout 0): the target of NativeSigmaModel(family="edm") on the GPU.  (`norm1` of a PureUNetBlock is never applied,
+    src/edm_networks.py:940-944: its parameters get no gradient on either side.)"""
+    from oracle import edm_net
+    cfg, sg, sd, ssd, net, snet = _make_golden().edm_reference_modules("edm_tiny")
+    g = torch.Generator().manual_seed(6)
+    feat = torch.randn(5, sg["channels"], sg["dim"], sg["dim"], generator=g)
+    target = 1.0 + 0.3 * torch.randn(5, 1, 1, 1, generator=g)
+    snet.train()
+    for mod in snet.modules():
+        if hasattr(mod, "dropout") and isinstance(mod.dropout, float):
+            mod.dropout = 0.0
+    ref = torch.nn.functional.mse_loss(snet(feat.clone()) + 1, target)
+    ref.backward()
+    names = [k for k, _ in snet.named_parameters()]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    mine = dict(ssd)
+    mine.update(params)
+    loss = torch.nn.functional.mse_loss(edm_net.sigma_forward(mine, feat.clone(), training=True) + 1, target)
+    loss.backward()
+    assert torch.allclose(loss, ref, rtol=1e-6, atol=0)
+    used = [(n, p) for n, p in snet.named_parameters() if p.grad is not None]
+    assert {n for n, _ in snet.named_parameters() if n not in dict(used)} == {n for n in names if params[n].grad is None}
+    gmax = max(float(p.grad.norm()) for _, p in used)
+    for n, p_ref in used:
+        assert (params[n].grad - p_ref.grad).norm() <= 1e-5 * p_ref.grad.norm() + 1e-7 * gmax, n
+
+
 def test_adm256_layout(R):
     """Key names / shapes of the c4/c5 architecture (no forward: 553 M parameters)."""
     import importlib
