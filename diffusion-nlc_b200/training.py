@@ -609,3 +609,24 @@ def train_step_native(model, sigma, scheduler, batch_x, t, noise, extra, eta1, e
     loss, _ = sigma.loss_and_grad(torch.cat(feats), dist_real, nhwc=True)
     sigma.step(lr, weight_decay=weight_decay, **adam)
     return loss
+
+
+def train_step_native_edm(model, sigma_model, batch_x, sigma, noise, extra, eta1, eta2, lr, sigma_data=0.5, weight_decay=0.0,
+                          microbatch=None, **adam):
+    """One iteration of the EDM experiment's training loop (src/experiments.py:990-1017, unweighted loss) with nothing left to
+    autograd: `prepare_batch_edm` (noisy_img = x + sigma new_noise, dist_real), the frozen SongUNet's `encode` with the EDM
+    preconditioning of `encode_edm` (c_in = 1 / sqrt(sigma_data^2 + sigma^2), c_noise = log(sigma) / 4, :777-786) on the
+    tensor-core engine, `NativeSigmaModel(family="edm").loss_and_grad`, fused AdamW + EMA.  sigma: [B] (or [B,1,1,1]) noise
+    levels, drawn by the caller as the reference does (:990-993).  Returns the loss (device scalar)."""
+    noisy_x, dist_real = prepare_batch_edm(batch_x, sigma, noise, extra, eta1, eta2)
+    B = noisy_x.shape[0]
+    sg = sigma.to(noisy_x.device, torch.float32).reshape(B)
+    c_in = 1.0 / (sigma_data ** 2 + sg ** 2).sqrt()
+    c_noise = sg.log() / 4
+    mb = microbatch or B
+    feats = [model.encode_scaled(noisy_x[i:i + mb], c_noise[i:i + mb].contiguous(), c_in[i:i + mb].contiguous()).clone()
+             for i in range(0, B, mb)]
+    loss, _ = sigma_model.loss_and_grad(torch.cat(feats), dist_real, nhwc=True)
+    sigma_model.step(lr, weight_decay=weight_decay, **adam)
+    return loss
+

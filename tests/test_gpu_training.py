@@ -291,6 +291,60 @@ def test_native_edm_sigma_model_gradients_against_autograd(name, B, loss):
         assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
 
 
+def test_native_edm_training_iteration_end_to_end():
+    """train_step_native_edm: batch preparation, SongUNet encode with the EDM preconditioning on the engine (fp32 mode), native
+    sigma-model forward / backward and the fused AdamW, against the same iteration written with the oracle under autograd
+    (encode through the oracle on the CPU): loss within 1e-4, gradients within 1e-3 in norm, the AdamW update within 2e-5 wherever the gradient is above its noise."""
+    from nlc_b200 import training as T
+    from nlc_b200.edm_networks import SongUNet
+    from oracle import edm_net
+    cfg = dict(weights.EDM_CONFIGS["edm_tiny"])
+    sg = cfg.pop("sigma")
+    sd, ssd = weights.edm_unet_state_dict(**cfg, seed=3), weights.edm_sigma_state_dict(**sg, seed=4)
+    B, R = 6, cfg["img_resolution"]
+    g = torch.Generator().manual_seed(8)
+    x0 = torch.rand(B, 3, R, R, generator=g) * 2 - 1
+    noise, extra = torch.randn(B, 3, R, R, generator=g), torch.randn(B, 3, R, R, generator=g)
+    eta1, eta2 = 0.1 * torch.rand(B, generator=g), 0.5 * torch.rand(B, generator=g)
+    sigma = (torch.randn(B, generator=g) * 1.2 - 1.2).exp()
+    # the reference iteration through the oracle (src/experiments.py:996-1013)
+    new_noise = noise + eta1.view(B, 1, 1, 1) * (noise + eta2.view(B, 1, 1, 1) * extra)
+    dist_real = new_noise.flatten(1).norm(dim=1) / (3 * R * R) ** 0.5
+    noisy = x0 + sigma.view(B, 1, 1, 1) * new_noise
+    c_in = 1 / (0.5 ** 2 + sigma ** 2).sqrt()
+    with torch.no_grad():
+        feat = edm_net.unet_encode(sd, c_in.view(B, 1, 1, 1) * noisy, sigma.log() / 4, cfg)
+    names = [k for k in ssd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    osd = dict(ssd)
+    osd.update(params)
+    ref_loss = torch.nn.functional.mse_loss(edm_net.sigma_forward(osd, feat, training=True).reshape(-1) + 1, dist_real)
+    ref_loss.backward()
+    used = [n for n in names if params[n].grad is not None]
+    opt = torch.optim.AdamW([params[n] for n in used], lr=1e-3, weight_decay=0.0)
+    opt.step()
+    model = SongUNet(**{k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}, precision="fp32",
+                     device=dev).load_state_dict(sd)
+    sm = T.NativeSigmaModel(**sg, dropout=0.0, loss="l2", device=dev, family="edm").load_state_dict(ssd)
+    loss = T.train_step_native_edm(model, sm, x0.to(dev), sigma.to(dev), noise.to(dev), extra.to(dev), eta1.to(dev),
+                                   eta2.to(dev), lr=1e-3)
+    assert abs(loss.item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item())
+    gmax = max(float(params[n].grad.norm()) for n in used)
+    out = sm.state_dict()
+    for n in used:
+        a, b = sm.grads[n].cpu().double(), params[n].grad.double()
+        assert (a - b).norm() <= 1e-3 * b.norm() + 1e-6 * gmax, (n, float((a - b).norm()), float(b.norm()))
+        # The first AdamW step moves every element by ~lr * sign(g).  The biases of the last block and of fc_layer.1 only add a
+        # batch-independent constant in front of the train-mode BatchNorm1d, which removes it: their gradient is rounding
+        # noise on both sides and the step amplifies it to +-lr, as it does in the reference.  The update is therefore checked
+        # where the gradient is above its noise (the optimizer kernel itself is pinned by test_adamw_ema_kernel_follows_torch)
+        if b.norm() < 1e-4 * gmax:
+            continue
+        dn, dr = out[n].cpu().double() - ssd[n].double(), params[n].detach().double() - ssd[n].double()
+        big = b.abs() > 1e-2 * b.abs().max()
+        assert big.any() and (dn - dr)[big].abs().max() <= 2e-5, (n, float((dn - dr)[big].abs().max()))
+
+
 def test_native_sigma_model_graph_replay_and_dropout():
     """The captured pass (second and later calls at a batch size) equals the eager one; with dropout the pass runs, the masks
     of forward and backward agree (the loss decreases along -grad), and load_state_dict drops the captured graphs."""
