@@ -100,6 +100,7 @@ _SIGNATURES = {
     "nlc_bn1d_gelu_train": (_I, [_P, _P, _P, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nlc_bn1d_act_train": (_I, [_P, _P, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nlc_head_loss": (_I, [_P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    "nlc_head_loss_weighted": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     "nlc_fid_preprocess": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P]),
     "nlc_im2col_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I64, _P]),
     "nlc_pool2d": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),

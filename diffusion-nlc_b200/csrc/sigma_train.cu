@@ -303,25 +303,34 @@ __global__ void __launch_bounds__(128) bn1d_train_bwd_kernel(const float* __rest
 }
 
 // dist_hat = r + 1; kind 0: MSELoss(mean), 1: L1Loss(mean).  loss[0] = value, dr[b] = d loss / d r[b].  One block.
+// weight == NULL: mean reduction; else loss = sum_b w_b l_b / sum_b w_b (the EDM loop's `loss_weighted`, src/experiments.py:1019-1021)
 __global__ void __launch_bounds__(256) head_loss_kernel(const float* __restrict__ r, const float* __restrict__ target, int B,
-                                                        int kind, float* __restrict__ dist_hat, float* __restrict__ loss,
-                                                        float* __restrict__ dr) {
+                                                        int kind, const float* __restrict__ weight, float* __restrict__ dist_hat,
+                                                        float* __restrict__ loss, float* __restrict__ dr) {
     __shared__ float red[8];
+    float wsum = static_cast<float>(B);
+    if (weight) {
+        float a = 0.f;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) a += weight[b];
+        wsum = block_sum_256(a, red);
+        __syncthreads();
+    }
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float dh = r[b] + 1.0f;
         dist_hat[b] = dh;
         const float e = dh - target[b];
+        const float w = (weight ? weight[b] : 1.0f) / wsum;
         if (kind == 0) {
-            acc += e * e;
-            dr[b] = 2.0f * e / static_cast<float>(B);
+            acc += w * (e * e);
+            dr[b] = 2.0f * e * w;
         } else {
-            acc += fabsf(e);
-            dr[b] = (e > 0.f ? 1.0f : (e < 0.f ? -1.0f : 0.f)) / static_cast<float>(B);
+            acc += w * fabsf(e);
+            dr[b] = (e > 0.f ? 1.0f : (e < 0.f ? -1.0f : 0.f)) * w;
         }
     }
     acc = block_sum_256(acc, red);
-    if (threadIdx.x == 0) loss[0] = acc / static_cast<float>(B);
+    if (threadIdx.x == 0) loss[0] = acc;
 }
 
 static unsigned grid1d(long long n, int sm_count) {
@@ -453,7 +462,16 @@ extern "C" int nlc_head_loss(nlc_ctx* ctx, const float* r, const float* target, 
                              float* dr, void* stream_) {
     NLC_REQUIRE(ctx && r && target && dist_hat && loss && dr && B >= 1 && (kind == 0 || kind == 1),
                 "nlc_head_loss: kind 0 (MSE) or 1 (L1)");
-    head_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(r, target, B, kind, dist_hat, loss, dr);
+    head_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(r, target, B, kind, nullptr, dist_hat, loss, dr);
+    NLC_CHECK_LAUNCH();
+    return NLC_OK;
+}
+
+extern "C" int nlc_head_loss_weighted(nlc_ctx* ctx, const float* r, const float* target, const float* weight, int B, int kind,
+                                      float* dist_hat, float* loss, float* dr, void* stream_) {
+    NLC_REQUIRE(ctx && r && target && weight && dist_hat && loss && dr && B >= 1 && (kind == 0 || kind == 1),
+                "nlc_head_loss_weighted: kind 0 (MSE) or 1 (L1)");
+    head_loss_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream_)>>>(r, target, B, kind, weight, dist_hat, loss, dr);
     NLC_CHECK_LAUNCH();
     return NLC_OK;
 }

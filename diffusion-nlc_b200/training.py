@@ -366,36 +366,38 @@ class NativeSigmaModel:
                                        out.data_ptr(), out.numel(), _stream()))
 
     # ------------------------------------------------------------------ forward + backward
-    def loss_and_grad(self, feat, dist_real, nhwc=False):
+    def loss_and_grad(self, feat, dist_real, nhwc=False, weight=None):
         """feat: encoder feature [B, C, dim, dim] (the reference's layout) or NHWC [B, dim, dim, C] with nhwc=True;
         dist_real: [B] (or [B,1,1,1]) targets.  Training-mode forward, loss, backward: fills `grads`, updates the BatchNorm
         running statistics, returns (loss [1], dist_hat [B]) on the device (plan buffers: valid until the next call).
         The ~130 launches of the pass are captured in a CUDA graph after the first call at a batch size (NLC_GRAPH=0:
         always eager) - at 4x4 .. 8x8 pixels the pass is launch-bound otherwise."""
         B = feat.shape[0]
-        key = (B, bool(nhwc))
+        key = (B, bool(nhwc), weight is not None)
         st = self._static.get(key)
         if st is None:
             st = dict(feat=torch.empty(tuple(feat.shape), device=self.device), target=torch.empty(B, device=self.device),
-                      graph=None)
+                      weight=torch.empty(B, device=self.device) if weight is not None else None, graph=None)
             self._static[key] = st
         st["feat"].copy_(feat)
         st["target"].copy_(dist_real.reshape(B))
+        if weight is not None:  # per-sample loss weights (normalised by their sum inside the loss kernel)
+            st["weight"].copy_(weight.reshape(B))
         if st["graph"] is not None:
             st["graph"].replay()
         else:
-            out = self._loss_and_grad(st["feat"], st["target"], nhwc)
+            out = self._loss_and_grad(st["feat"], st["target"], nhwc, st["weight"])
             st["out"] = out
             if self.use_graph and self.device.type == "cuda":
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    st["out"] = self._loss_and_grad(st["feat"], st["target"], nhwc)
+                    st["out"] = self._loss_and_grad(st["feat"], st["target"], nhwc, st["weight"])
                 st["graph"] = g
         self.num_batches_tracked += 1
         return st["out"]
 
-    def _loss_and_grad(self, feat, target, nhwc):
+    def _loss_and_grad(self, feat, target, nhwc, weight=None):
         L, ctx, Cc = self._lib, self._ctx, self.C
         B, dim = feat.shape[0], self.dim
         self.grads.flat.zero_()
@@ -488,8 +490,12 @@ class NativeSigmaModel:
         r = self._buf("r", B, 1)
         self._linear(g, B, F1, self.params["final_mlp.weight"], self.params["final_mlp.bias"], r)
         dist_hat, loss, dr = self._buf("dist_hat", B), self._buf("loss", 1), self._buf("dr", B, 1)
-        _lib.check(L.nlc_head_loss(ctx, r.data_ptr(), target.data_ptr(), B, self.loss_kind, dist_hat.data_ptr(), loss.data_ptr(),
-                                   dr.data_ptr(), _stream()))
+        if weight is None:
+            _lib.check(L.nlc_head_loss(ctx, r.data_ptr(), target.data_ptr(), B, self.loss_kind, dist_hat.data_ptr(),
+                                       loss.data_ptr(), dr.data_ptr(), _stream()))
+        else:
+            _lib.check(L.nlc_head_loss_weighted(ctx, r.data_ptr(), target.data_ptr(), weight.data_ptr(), B, self.loss_kind,
+                                                dist_hat.data_ptr(), loss.data_ptr(), dr.data_ptr(), _stream()))
         # ---------------------------------------------------------------- backward
         dg = self._buf("dg", B, F1)
         self._linear_bwd(g, dr, B, F1, self.params["final_mlp.weight"], self.grads["final_mlp.weight"],
@@ -612,8 +618,9 @@ def train_step_native(model, sigma, scheduler, batch_x, t, noise, extra, eta1, e
 
 
 def train_step_native_edm(model, sigma_model, batch_x, sigma, noise, extra, eta1, eta2, lr, sigma_data=0.5, weight_decay=0.0,
-                          microbatch=None, **adam):
-    """One iteration of the EDM experiment's training loop (src/experiments.py:990-1017, unweighted loss) with nothing left to
+                          microbatch=None, loss_weighted=False, **adam):
+    """One iteration of the EDM experiment's training loop (src/experiments.py:990-1024; `loss_weighted` = its per-sample
+    weights (sigma^2 + sigma_data^2) / (sigma sigma_data)^2 normalised by their sum, :994,1019-1021) with nothing left to
     autograd: `prepare_batch_edm` (noisy_img = x + sigma new_noise, dist_real), the frozen SongUNet's `encode` with the EDM
     preconditioning of `encode_edm` (c_in = 1 / sqrt(sigma_data^2 + sigma^2), c_noise = log(sigma) / 4, :777-786) on the
     tensor-core engine, `NativeSigmaModel(family="edm").loss_and_grad`, fused AdamW + EMA.  sigma: [B] (or [B,1,1,1]) noise
@@ -626,7 +633,8 @@ def train_step_native_edm(model, sigma_model, batch_x, sigma, noise, extra, eta1
     mb = microbatch or B
     feats = [model.encode_scaled(noisy_x[i:i + mb], c_noise[i:i + mb].contiguous(), c_in[i:i + mb].contiguous()).clone()
              for i in range(0, B, mb)]
-    loss, _ = sigma_model.loss_and_grad(torch.cat(feats), dist_real, nhwc=True)
+    weight = (sg ** 2 + sigma_data ** 2) / (sg * sigma_data) ** 2 if loss_weighted else None
+    loss, _ = sigma_model.loss_and_grad(torch.cat(feats), dist_real, nhwc=True, weight=weight)
     sigma_model.step(lr, weight_decay=weight_decay, **adam)
     return loss
 

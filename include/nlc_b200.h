@@ -219,6 +219,9 @@ int nlc_bn1d_act_train(nlc_ctx* ctx, const float* x, const float* dy, int B, int
 /* dist_hat = r + 1 (src/experiments.py:689); loss = MSELoss (kind 0) | L1Loss (kind 1), mean reduction; dr = d loss / d r */
 int nlc_head_loss(nlc_ctx* ctx, const float* r, const float* target, int B, int kind, float* dist_hat, float* loss, float* dr,
                   void* stream);
+/* The same with per-sample weights [B]: loss = sum_b w_b l_b / sum_b w_b (`loss_weighted` of the EDM loop, src/experiments.py:1019-1021). */
+int nlc_head_loss_weighted(nlc_ctx* ctx, const float* r, const float* target, const float* weight, int B, int kind,
+                           float* dist_hat, float* loss, float* dr, void* stream);
 
 /* ---- FID statistics on the device.  The reference goes through the third-party pytorch_fid package
  * after writing every sample as a PNG (src/experiments.py:210-226 fid_helper -> compute_statistics_of_path /

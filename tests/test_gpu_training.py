@@ -291,6 +291,36 @@ def test_native_edm_sigma_model_gradients_against_autograd(name, B, loss):
         assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
 
 
+def test_native_sigma_model_weighted_loss():
+    """`loss_weighted` of the EDM loop (src/experiments.py:1019-1021): loss = sum_b w_b l_b / sum_b w_b with per-sample weights;
+    loss and gradients against autograd."""
+    from nlc_b200 import training as T
+    from oracle import edm_net
+    sg = dict(weights.EDM_CONFIGS["edm_tiny"])["sigma"]
+    ssd = weights.edm_sigma_state_dict(**sg, seed=9)
+    B = 6
+    g = torch.Generator().manual_seed(5)
+    feat = torch.randn(B, sg["channels"], sg["dim"], sg["dim"], generator=g)
+    target = 1.0 + 0.3 * torch.randn(B, generator=g)
+    w = 0.2 + 5 * torch.rand(B, generator=g)
+    names = [k for k in ssd if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    params = {n: torch.nn.Parameter(ssd[n].clone()) for n in names}
+    sd = dict(ssd)
+    sd.update(params)
+    dist_hat = edm_net.sigma_forward(sd, feat.clone(), training=True).reshape(-1) + 1
+    ref = ((w / w.sum()) * (dist_hat - target) ** 2).sum()
+    ref.backward()
+    m = T.NativeSigmaModel(**sg, dropout=0.0, loss="l2", device=dev, family="edm").load_state_dict(ssd)
+    got, _ = m.loss_and_grad(feat.permute(0, 2, 3, 1).contiguous().to(dev), target.to(dev), nhwc=True, weight=w.to(dev))
+    assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    gmax = max(float(params[n].grad.norm()) for n in names if params[n].grad is not None)
+    for n in names:
+        if params[n].grad is None:
+            continue
+        a, b = m.grads[n].cpu().double(), params[n].grad.double()
+        assert (a - b).norm() <= 3e-4 * b.norm() + 3e-7 * gmax, (n, float((a - b).norm()), float(b.norm()))
+
+
 def test_native_edm_training_iteration_end_to_end():
     """train_step_native_edm: batch preparation, SongUNet encode with the EDM preconditioning on the engine (fp32 mode), native
     sigma-model forward / backward and the fused AdamW, against the same iteration written with the oracle under autograd
