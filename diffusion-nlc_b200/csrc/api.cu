@@ -65,6 +65,9 @@ nlc_ctx* nlc_create(int device) {
     ctx->use_cta_pairs = !(e && e[0] == '0');
     e = getenv("NLC_SLAB");
     ctx->use_slab = e ? atoi(e) : 1;
+    e = getenv("NLC_SPLITK");
+    ctx->use_splitk = !(e && e[0] == '0');
+    ctx->splitk_ws = nullptr, ctx->splitk_bytes = 0;
     e = getenv("NLC_ATTN_ONEPASS");
     ctx->attn_onepass = !(e && e[0] == '0');
     e = getenv("NLC_TMA_EPI");
@@ -72,7 +75,10 @@ nlc_ctx* nlc_create(int device) {
     return ctx;
 }
 
-void nlc_destroy(nlc_ctx* ctx) { delete ctx; }
+void nlc_destroy(nlc_ctx* ctx) {
+    if (ctx && ctx->splitk_ws) cudaFree(ctx->splitk_ws);
+    delete ctx;
+}
 
 int nlc_sm_count(nlc_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
@@ -83,6 +89,8 @@ int nlc_ctx_set(nlc_ctx* ctx, const char* key, int value) {
     } else if (!strcmp(key, "slab")) {
         if (value < 0 || value > 2) return nlc::set_error(NLC_EINVAL, "nlc_ctx_set: slab must be 0, 1 or 2");
         ctx->use_slab = value;
+    } else if (!strcmp(key, "splitk")) {
+        ctx->use_splitk = value != 0;
     } else if (!strcmp(key, "attn_onepass")) {
         ctx->attn_onepass = value != 0;
     } else if (!strcmp(key, "tma_epi")) {

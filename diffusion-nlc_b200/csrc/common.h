@@ -88,5 +88,8 @@ struct nlc_ctx {
     int use_cta_pairs;  // tcgen05 cta_group::2 conv kernel for large layers (NLC_CTA_PAIRS=0 disables)
     int use_slab;       // halo-slab 3x3 kernel (conv_slab.cu): 0 off, 1 layers with 128 output channels, 2 every eligible layer
     int attn_onepass;   // fused attention with one pass over the keys (online softmax); NLC_ATTN_ONEPASS=0: the two-pass kernel
+    int use_splitk;     // split-K of the small-M convolution launches (NLC_SPLITK=0 disables)
+    void* splitk_ws;    // its workspace (grown outside graph capture; one stream at a time, like the engine's scratch buffers)
+    size_t splitk_bytes;
     int use_tma_epi;    // 16-bit conv epilogues through TMA (residual block by tensor load, output by tensor store); NLC_TMA_EPI=0 disables
 };

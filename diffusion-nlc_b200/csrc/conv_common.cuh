@@ -48,6 +48,11 @@ struct ConvKParams {
     int out_up;      // 0, or 1 + 2a + b: output pixel (n,ho,wo) is written at (n, 2ho+a, 2wo+b) of a [B,2Ho,2Wo,.] tensor
     int w_batched;
     int f16;         // 16-bit operands are fp16 (kind::f16 with the f16 format bits), not bf16
+    // split-K (small-M layers: a handful of tiles with a long serial K loop): unit u = (split = u / num_tiles, tile = u %
+    // num_tiles); split s accumulates K chunks [s * chunks_per_split, ...) and writes its raw fp32 accumulators to
+    // out_f32 + s * split_stride (a workspace); splitk_reduce_kernel sums the splits in a fixed order and applies the epilogue
+    int ksplit, chunks_per_split, num_units;
+    long long split_stride;
     int tma_epi;     // 16-bit epilogue through TMA (epi_tma_* below): output by tensor store, residual block by tensor load
     float* stats;    // GroupNorm partials of the fp32 output: [pixel/32][stats_nblk][2] = (mean, M2) over 32 px x 4 ch
     int stats_nblk;

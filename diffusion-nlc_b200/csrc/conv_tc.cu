@@ -116,7 +116,10 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+            for (int uu = unit0; uu < p.num_units; uu += unit_step) {
+                const int split = uu / p.num_tiles, unit = uu - split * p.num_tiles;  // (ksplit == 1: split 0, unit = uu)
+                const int k_lo = split * p.chunks_per_split;
+                const int k_hi = k_lo + p.chunks_per_split < p.total_chunks ? k_lo + p.chunks_per_split : p.total_chunks;
                 const int n_tile = unit / p.num_m_units;
                 const int m_tile = CTA2 ? 2 * (unit - n_tile * p.num_m_units) + static_cast<int>(rank)
                                         : unit - n_tile * p.num_m_units;
@@ -129,6 +132,10 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                 for (int s = 0; s < p.nseg; ++s) {
                     const ConvSegDev sg = p.seg[s];
                     for (int j = 0; j < sg.nchunk; ++j) {
+                        if (kchunk < k_lo || kchunk >= k_hi) {  // another split's K range
+                            ++kchunk;
+                            continue;
+                        }
                         mbar_wait(&empty[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
                         uint8_t* sb = sa + kAStageBytes;
@@ -203,11 +210,13 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     }
                 }
             } else {
-                for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+                for (int uu = unit0; uu < p.num_units; uu += unit_step) {
+                    const int k_lo = (uu / p.num_tiles) * p.chunks_per_split;
+                    const int k_hi = k_lo + p.chunks_per_split < p.total_chunks ? k_lo + p.chunks_per_split : p.total_chunks;
                     mbar_wait(&tempty[acc], acc_phase ^ 1);
                     tc_fence_after_sync();
                     const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                    for (int kc = 0; kc < p.total_chunks; ++kc) {
+                    for (int kc = k_lo; kc < k_hi; ++kc) {
                         mbar_wait(&full[stage], phase);
                         tc_fence_after_sync();
                         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -218,13 +227,13 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                             for (int k = 0; k < 4; ++k) {  // 4 x 32 B K-steps inside the 128 B swizzle row
                                 if (CTA2) {
                                     if (TF32)
-                                        umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                        umma_tf32_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kc - k_lo) | k) != 0);
                                     else
-                                        umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                        umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kc - k_lo) | k) != 0);
                                 } else if (TF32) {
-                                    umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                    umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kc - k_lo) | k) != 0);
                                 } else {
-                                    umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+                                    umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, ((kc - k_lo) | k) != 0);
                                 }
                             }
                             // smem slot reusable (in both CTAs of a pair) once these MMAs retire
@@ -254,14 +263,17 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+            for (int uu = unit0; uu < p.num_units; uu += unit_step) {
+                const int split = uu / p.num_tiles, unit = uu - split * p.num_tiles;
+                const int k_lo = split * p.chunks_per_split;
+                const int k_hi = k_lo + p.chunks_per_split < p.total_chunks ? k_lo + p.chunks_per_split : p.total_chunks;
                 const int n_tile = unit / p.num_m_units;
                 const int m_tile = CTA2 ? 2 * (unit - n_tile * p.num_m_units) + static_cast<int>(rank)
                                         : unit - n_tile * p.num_m_units;
                 const int tn = m_tile / tiles_per_img;
                 const int th = (m_tile - tn * tiles_per_img) / p.tiles_w;
                 const int n0 = tn * p.BN;
-                for (int kchunk = 0; kchunk < p.total_chunks; ++kchunk) {
+                for (int kchunk = k_lo; kchunk < k_hi; ++kchunk) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sb = smem + stage * Cfg::kStageBytes + kAStageBytes;
                     if (CTA2)
@@ -332,7 +344,9 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
         const int sub_r8 = lane >> 2, sub_c8 = lane & 3;  // bf16 pattern: 8 rows x 4 (8-channel) chunks
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int unit = unit0; unit < p.num_tiles; unit += unit_step) {
+        for (int uu = unit0; uu < p.num_units; uu += unit_step) {
+            const int split = uu / p.num_tiles, unit = uu - split * p.num_tiles;
+            float* const of32 = p.out_f32 + static_cast<size_t>(split) * p.split_stride;  // (split-K: this split's workspace slice)
             const int n_tile = unit / p.num_m_units;
             const int m_tile = CTA2 ? 2 * (unit - n_tile * p.num_m_units) + static_cast<int>(rank)
                                     : unit - n_tile * p.num_m_units;
@@ -413,7 +427,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
             };
             if (TEPI == 2 && p.resid) fetch_resid256(32 * half);
             // ... and the residual block of the NEXT tile of this CTA is pulled into L2 now, a whole tile ahead (conv_slab.cu)
-            if (p.resid != nullptr && p.resid_mode == 0 && !p.out_head_split && unit + unit_step < p.num_tiles) {
+            if (p.resid != nullptr && p.resid_mode == 0 && !p.out_head_split && unit + unit_step < p.num_tiles) {  // (never with split-K)
                 const int u2 = unit + unit_step;
                 const int nt2 = u2 / p.num_m_units;
                 const int mt2 = CTA2 ? 2 * (u2 - nt2 * p.num_m_units) + static_cast<int>(rank) : u2 - nt2 * p.num_m_units;
@@ -716,7 +730,7 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
                     for (int it = 0; it < 8; ++it) {
                         const int r = it * 4 + sub_r4;
                         if ((vmask >> r) & 1)
-                            reinterpret_cast<float4*>(p.out_f32 + opix(r) * p.ld_out_f32 + ocol0)[sub_c4] =
+                            reinterpret_cast<float4*>(of32 + opix(r) * p.ld_out_f32 + ocol0)[sub_c4] =
                                 *reinterpret_cast<const float4*>(stg + r * 32 + ((sub_c4 ^ (r & 7)) << 2));
                     }
                 }
@@ -772,6 +786,72 @@ __global__ void __launch_bounds__(MODE == 2 ? kThreadsX3 : kThreads, 1)
     if (warp == 2) {
         tc_fence_after_sync();
         if (CTA2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- split-K
+// Sum of the splits' raw accumulators (fixed order: deterministic) + the epilogue the main kernel would have applied, in the
+// same order: bias, per-sample row, residual (fp32 or 16-bit), scale, ReLU -> fp32 and / or operand-dtype outputs.
+struct SplitKReduce {
+    const float* ws;
+    long long stride;
+    int ksplit, Cout, HW;
+    long long npix;
+    const float* bias;
+    const float* rowvec;
+    int ld_rowvec;
+    const void* resid;
+    int ld_resid, resid16, f16;
+    float out_scale;
+    int act;
+    float* out_f32;
+    int ld_out_f32;
+    void* out_op;
+    int ld_out_op, op_is_f32;  // operand output: 16-bit (f16 / bf16), or fp32 rounded to tf32
+};
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitKReduce a) {
+    pdl_wait();
+    pdl_trigger();
+    const int c4n = a.Cout >> 2;
+    const long long total = a.npix * c4n;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long pix = i / c4n;
+        const int c = static_cast<int>(i - pix * c4n) << 2;
+        const float* w = a.ws + pix * a.Cout + c;
+        float4 f = *reinterpret_cast<const float4*>(w);
+        for (int s = 1; s < a.ksplit; ++s) {
+            const float4 t = *reinterpret_cast<const float4*>(w + s * a.stride);
+            f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
+        }
+        if (a.bias) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+            f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
+        }
+        if (a.rowvec) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(a.rowvec + (pix / a.HW) * a.ld_rowvec + c));
+            f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
+        }
+        if (a.resid) {
+            float4 t;
+            if (a.resid16)
+                t = unpack_op16x4(__ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(a.resid) +
+                                                                         pix * a.ld_resid + c)), a.f16);
+            else
+                t = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(a.resid) + pix * a.ld_resid + c));
+            f.x += t.x, f.y += t.y, f.z += t.z, f.w += t.w;
+        }
+        if (a.out_scale != 1.0f) f.x *= a.out_scale, f.y *= a.out_scale, f.z *= a.out_scale, f.w *= a.out_scale;
+        if (a.act) f.x = fmaxf(f.x, 0.f), f.y = fmaxf(f.y, 0.f), f.z = fmaxf(f.z, 0.f), f.w = fmaxf(f.w, 0.f);
+        if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + pix * a.ld_out_f32 + c) = f;
+        if (a.out_op) {
+            if (a.op_is_f32)
+                *reinterpret_cast<float4*>(static_cast<float*>(a.out_op) + pix * a.ld_out_op + c) =
+                    make_float4(round_tf32(f.x), round_tf32(f.y), round_tf32(f.z), round_tf32(f.w));
+            else
+                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(a.out_op) + pix * a.ld_out_op + c) =
+                    make_uint2(pack_op16x2(f.x, f.y, a.f16), pack_op16x2(f.z, f.w, a.f16));
+        }
     }
 }
 
@@ -951,6 +1031,7 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
         ktot += sg.nch;
     }
     p.total_chunks = ktot / chunk;
+    p.ksplit = 1, p.chunks_per_split = p.total_chunks, p.num_units = p.num_tiles, p.split_stride = 0;
 
     // (TMA only moves the 16-bit elements: the bf16 element type serves fp16 tensors as well)
     const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -1041,8 +1122,57 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
         const int rc = epi_tma_setup(ctx, d, p);
         if (rc != NLC_OK) return rc;
     }
+    // Split-K for the small-M layers (4x4 / 8x8 levels, small batches): when the tiles fill less than half of the SMs and the
+    // K loop is long, S splits share a tile's K range; their raw accumulators go to a workspace and splitk_reduce_kernel
+    // applies the epilogue.  Deterministic (fixed summation order); the plain epilogues only (no GroupNorm partials,
+    // sub-pixel placement, head merge or resampled residual - none of which occurs at these levels).
+    SplitKReduce red;
+    memset(&red, 0, sizeof(red));
+    {
+        const int slots = pair ? ctx->sm_count / 2 : ctx->sm_count;
+        const long long npix = static_cast<long long>(d->B) * d->Ho * d->Wo;
+        // (at least 8 K chunks per split, tiles on at most half of the SM slots: fewer chunks per split or fuller grids measured
+        //  slower at batch 32 - 4.72 against 4.65 ms per timestep - and no different at batch 256)
+        if (ctx->use_splitk && !x3 && !d->stats && !d->out_up && !d->out_head_split && d->resid_mode == 0 && !p.w_batched &&
+            p.num_tiles * 2 <= slots && p.total_chunks >= 16 && d->Cout % 4 == 0) {
+            int sp = slots / p.num_tiles;
+            if (sp > p.total_chunks / 8) sp = p.total_chunks / 8;
+            if (sp > 16) sp = 16;
+            if (sp >= 2) {
+                const int cps = (p.total_chunks + sp - 1) / sp;
+                sp = (p.total_chunks + cps - 1) / cps;
+                const size_t need = static_cast<size_t>(sp) * npix * d->Cout * sizeof(float);
+                bool ok = need <= ctx->splitk_bytes;
+                if (!ok) {  // grow the workspace - never while a CUDA graph is being captured (the plan's first pass is eager)
+                    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                    cudaStreamIsCapturing(stream, &cs);
+                    if (cs == cudaStreamCaptureStatusNone) {
+                        NLC_CHECK_CUDA(cudaStreamSynchronize(stream));
+                        if (ctx->splitk_ws) NLC_CHECK_CUDA(cudaFree(ctx->splitk_ws));
+                        ctx->splitk_ws = nullptr, ctx->splitk_bytes = 0;
+                        NLC_CHECK_CUDA(cudaMalloc(&ctx->splitk_ws, need));
+                        ctx->splitk_bytes = need;
+                        ok = true;
+                    }
+                }
+                if (ok && sp >= 2) {
+                    red.ws = static_cast<const float*>(ctx->splitk_ws), red.stride = npix * d->Cout, red.ksplit = sp;
+                    red.Cout = d->Cout, red.HW = d->Ho * d->Wo, red.npix = npix;
+                    red.bias = p.bias, red.rowvec = p.rowvec, red.ld_rowvec = p.ld_rowvec;
+                    red.resid = p.resid, red.ld_resid = p.ld_resid, red.resid16 = p.resid16, red.f16 = p.f16;
+                    red.out_scale = p.out_scale, red.act = p.act;
+                    red.out_f32 = p.out_f32, red.ld_out_f32 = p.ld_out_f32;
+                    red.out_op = p.out_op, red.ld_out_op = p.ld_out_op, red.op_is_f32 = tf32 ? 1 : 0;
+                    p.bias = nullptr, p.rowvec = nullptr, p.resid = nullptr, p.resid16 = 0, p.out_scale = 1.0f, p.act = 0;
+                    p.out_op = nullptr, p.out_f32 = static_cast<float*>(ctx->splitk_ws), p.ld_out_f32 = d->Cout, p.tma_epi = 0;
+                    p.ksplit = sp, p.chunks_per_split = cps, p.num_units = p.num_tiles * sp, p.split_stride = red.stride;
+                }
+            }
+        }
+    }
+    const int rc_main = [&]() -> int {
     if (pair) {
-        const int pairs = p.num_tiles < ctx->sm_count / 2 ? p.num_tiles : ctx->sm_count / 2;
+        const int pairs = p.num_units < ctx->sm_count / 2 ? p.num_units : ctx->sm_count / 2;
         if (tf32) {
             if (block_n == 256) return launch_conv<256, 1, true>(p, 2 * pairs, stream, ctx->device);
             return launch_conv<128, 1, true>(p, 2 * pairs, stream, ctx->device);
@@ -1050,7 +1180,7 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
         if (block_n == 256) return launch_conv<256, 0, true>(p, 2 * pairs, stream, ctx->device);
         return launch_conv<128, 0, true>(p, 2 * pairs, stream, ctx->device);
     }
-    const int grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+    const int grid = p.num_units < ctx->sm_count ? p.num_units : ctx->sm_count;
     if (x3) {
         if (block_n == 128) return launch_conv<128, 2, false>(p, grid, stream, ctx->device);
         return launch_conv<64, 2, false>(p, grid, stream, ctx->device);
@@ -1063,4 +1193,15 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
     if (block_n == 256) return launch_conv<256, 0, false>(p, grid, stream, ctx->device);
     if (block_n == 128) return launch_conv<128, 0, false>(p, grid, stream, ctx->device);
     return launch_conv<64, 0, false>(p, grid, stream, ctx->device);
+    }();
+    if (rc_main != NLC_OK || red.ksplit < 2) return rc_main;
+    {
+        const long long work = red.npix * (red.Cout >> 2);
+        long long blocks = (work + 255) / 256;
+        const long long cap = 8LL * ctx->sm_count;
+        if (blocks > cap) blocks = cap;
+        NLC_CHECK_CUDA(launch_pdl(splitk_reduce_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, red));
+        NLC_CHECK_LAUNCH();
+    }
+    return NLC_OK;
 }

@@ -47,12 +47,13 @@ nlc_ctx* nlc_create(int device);
 void nlc_destroy(nlc_ctx* ctx);
 int nlc_sm_count(nlc_ctx* ctx);
 /* Kernel-selection switches of a context (defaults from the environment: NLC_CTA_PAIRS, NLC_SLAB, NLC_TMA_EPI,
- * NLC_ATTN_ONEPASS):
+ * NLC_ATTN_ONEPASS, NLC_SPLITK):
  *   "cta_pairs" 0|1  tcgen05 cta_group::2 convolution kernels;
  *   "slab" 0|1|2     halo-slab 3x3 kernel: off / layers with 128 output channels / every eligible layer;
  *   "tma_epi" 0|1|2  16-bit convolution epilogues: staged through the load/store unit / through TMA (residual block by
  *                    tensor load, output by tensor store) / 256-bit global accesses from registers;
- *   "attn_onepass" 0|1  fused attention: two passes over the keys / one pass with an online softmax. */
+ *   "attn_onepass" 0|1  fused attention: two passes over the keys / one pass with an online softmax;
+ *   "splitk" 0|1     deterministic split-K (workspace + reducing epilogue kernel) of the small-M convolution launches. */
 int nlc_ctx_set(nlc_ctx* ctx, const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------

@@ -545,9 +545,10 @@ def test_conv_tc_resampled_residual(dev, mode, shape):
     from nlc_b200._lib import NLC_BF16
     B, H, W = shape
     C = 128
-    # (both launches on the tap-per-tile kernel: the halo-slab kernel, which takes the plain-residual one at these sizes, sums
-    #  the same products in another order)
+    # (both launches on the tap-per-tile kernel in one pass: the halo-slab kernel and the split-K path, which take the
+    #  plain-residual one at these sizes, sum the same products in another order)
     _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"slab", 0))
+    _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"splitk", 0))
     g = torch.Generator().manual_seed(31)
     x = _rnd(torch.randn(B, C, H, W, generator=g).to(dev), NLC_BF16)
     w = _rnd((torch.randn(C, C, 3, 3, generator=g) / (C * 9) ** 0.5).to(dev), NLC_BF16)
@@ -562,6 +563,7 @@ def test_conv_tc_resampled_residual(dev, mode, shape):
     ops.conv_tc([xa], ops.taps3x3(0, 0, C), wp, C, B, H, W, NLC_BF16, resid=ops.Act(resid), out_f32=b, resid_mode=mode)
     torch.cuda.synchronize()
     _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"slab", 1))
+    _lib.check(_lib.lib().nlc_ctx_set(_lib.ctx(0), b"splitk", 1))
     assert torch.equal(a.t, b.t)
     ref = F.conv2d(x, w, padding=1) + full.permute(0, 3, 1, 2)
     assert _rel(b.t.permute(0, 3, 1, 2), ref) < 5e-5
@@ -687,3 +689,65 @@ def test_conv_tma_epilogue_equals_lsu_epilogue(dev, prec, case):
         ref = ref + resid.float().permute(0, 3, 1, 2)
     got = buf[:B, ..., 32:32 + Cout] if sliced else buf[:B]
     assert _rel(got.permute(0, 3, 1, 2), ref * 0.5) < (8e-3 if prec == "bf16" else 1e-3)
+
+
+SPLITK_CASES = [
+    # B, H, W, Cin, Cout, k, stride, fp32 residual?, 16-bit residual?, fp32 out?, operand out?
+    (32, 4, 4, 512, 512, 3, 1, True, False, True, True),     # the c2 4x4 level: fp32 residual stream, both outputs
+    (5, 4, 4, 256, 512, 3, 1, False, False, True, False),    # ragged batch
+    (2, 2, 2, 512, 512, 3, 1, True, False, True, False),     # nine splits of eight chunks
+    (8, 8, 8, 256, 256, 3, 2, False, False, False, True),    # stride 2, operand output only
+    (4, 8, 8, 1024, 256, 1, 1, False, True, False, True),    # 1x1 with a 16-bit residual
+    (130, 1, 1, 1024, 128, 1, 1, False, False, True, True),  # 1x1 spatial
+]
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16", "tf32"])
+@pytest.mark.parametrize("case", SPLITK_CASES)
+def test_conv_split_k_equals_single_pass(dev, prec, case):
+    """Deterministic split-K of the small-M launches (workspace + splitk_reduce_kernel): against the single-pass launch (same
+    products, another fp32 summation order: 2e-5 of max|y|), against torch, and bit-reproducible over repeats."""
+    from nlc_b200 import _lib, ops
+    B, H, W, Cin, Cout, k, stride, r32, r16, o32_on, oop_on = case
+    dt = _dt(prec)
+    tdt = ops.OP_DTYPES[dt]
+    if r16 and prec == "tf32":
+        r16, r32 = False, True
+    g = torch.Generator().manual_seed(31)
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x = _rnd(torch.randn(B, H, W, Cin, generator=g).to(dev), dt)
+    w = _rnd((torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev), dt)
+    b = torch.randn(Cout, generator=g).to(dev)
+    rowvec = torch.randn(B, Cout, generator=g).to(dev)
+    resid = torch.randn(B, Ho, Wo, Cout, generator=g).to(dev)
+    resid = resid.to(tdt) if r16 else resid
+    segs = [(0, kh - pad, kw - pad, 0, Cin) for kh in range(k) for kw in range(k)]
+    wp = ops.pack_conv_weight(w, dt)
+    ctx = _lib.ctx(0)
+    outs = {}
+    try:
+        for mode in (1, 1, 0):
+            _lib.check(_lib.lib().nlc_ctx_set(ctx, b"splitk", mode))
+            o32 = ops.Act(torch.full((B, Ho, Wo, Cout), float("nan"), device=dev)) if o32_on else None
+            oop = ops.Act(torch.zeros(B, Ho, Wo, Cout, device=dev, dtype=tdt)) if oop_on else None
+            ops.conv_tc([ops.Act(x.to(tdt))], segs, wp, Cout, B, Ho, Wo, dt, stride=stride, bias=b, rowvec=rowvec,
+                        resid=ops.Act(resid) if (r32 or r16) else None, out_scale=0.5, out_f32=o32, out_op=oop, relu=True)
+            torch.cuda.synchronize()
+            cur = (o32.t.clone() if o32_on else None, oop.t.float().clone() if oop_on else None)
+            if mode == 1 and 1 in outs:  # second split-K run: bit-reproducible
+                for a, c in zip(outs[1], cur):
+                    assert a is None or torch.equal(a, c)
+            outs[mode] = cur
+    finally:
+        _lib.check(_lib.lib().nlc_ctx_set(ctx, b"splitk", 1))
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, stride=stride, padding=pad) + rowvec[:, :, None, None]
+    if r32 or r16:
+        ref = ref + resid.float().permute(0, 3, 1, 2)
+    ref = torch.relu(ref * 0.5)
+    if o32_on:
+        assert _rel(outs[1][0], outs[0][0]) < 2e-5
+        assert _rel(outs[1][0].permute(0, 3, 1, 2), ref) < 5e-5
+    if oop_on:
+        tol = 8e-3 if prec == "bf16" else 1e-3
+        assert _rel(outs[1][1], outs[0][1]) < tol and _rel(outs[1][1].permute(0, 3, 1, 2), ref) < tol
