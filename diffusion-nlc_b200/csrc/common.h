@@ -89,7 +89,7 @@ struct nlc_ctx {
     int use_slab;       // halo-slab 3x3 kernel (conv_slab.cu): 0 off, 1 layers with 128 output channels, 2 every eligible layer
     int attn_onepass;   // fused attention with one pass over the keys (online softmax); NLC_ATTN_ONEPASS=0: the two-pass kernel
     int use_splitk;     // split-K of the small-M convolution launches (NLC_SPLITK=0 disables)
-    void* splitk_ws;    // its workspace (grown outside graph capture; one stream at a time, like the engine's scratch buffers)
+    void* splitk_ws;    // its workspace: one fixed allocation (captured graphs hold the address); one stream at a time
     size_t splitk_bytes;
     int use_tma_epi;    // 16-bit conv epilogues through TMA (residual block by tensor load, output by tensor store); NLC_TMA_EPI=0 disables
 };

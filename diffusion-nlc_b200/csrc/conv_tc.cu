@@ -1138,23 +1138,24 @@ extern "C" int nlc_conv_tc(nlc_ctx* ctx, const nlc_conv_desc* d, void* stream_) 
             int sp = slots / p.num_tiles;
             if (sp > p.total_chunks / 8) sp = p.total_chunks / 8;
             if (sp > 16) sp = 16;
+            // The workspace is ONE fixed allocation per context, made at the first eligible launch outside graph capture and
+            // never moved or freed before nlc_destroy: captured graphs hold its address.  A launch whose splits do not fit
+            // takes fewer splits (or none).
+            constexpr size_t kSplitKBytes = 64u << 20;
+            if (!ctx->splitk_ws) {
+                cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+                cudaStreamIsCapturing(stream, &cs);
+                if (cs == cudaStreamCaptureStatusNone && cudaMalloc(&ctx->splitk_ws, kSplitKBytes) == cudaSuccess)
+                    ctx->splitk_bytes = kSplitKBytes;
+                else
+                    ctx->splitk_ws = nullptr, (void)cudaGetLastError();
+            }
+            const size_t per_split = static_cast<size_t>(npix) * d->Cout * sizeof(float);
+            if (static_cast<size_t>(sp) * per_split > ctx->splitk_bytes) sp = static_cast<int>(ctx->splitk_bytes / per_split);
             if (sp >= 2) {
                 const int cps = (p.total_chunks + sp - 1) / sp;
                 sp = (p.total_chunks + cps - 1) / cps;
-                const size_t need = static_cast<size_t>(sp) * npix * d->Cout * sizeof(float);
-                bool ok = need <= ctx->splitk_bytes;
-                if (!ok) {  // grow the workspace - never while a CUDA graph is being captured (the plan's first pass is eager)
-                    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-                    cudaStreamIsCapturing(stream, &cs);
-                    if (cs == cudaStreamCaptureStatusNone) {
-                        NLC_CHECK_CUDA(cudaStreamSynchronize(stream));
-                        if (ctx->splitk_ws) NLC_CHECK_CUDA(cudaFree(ctx->splitk_ws));
-                        ctx->splitk_ws = nullptr, ctx->splitk_bytes = 0;
-                        NLC_CHECK_CUDA(cudaMalloc(&ctx->splitk_ws, need));
-                        ctx->splitk_bytes = need;
-                        ok = true;
-                    }
-                }
+                const bool ok = ctx->splitk_ws != nullptr;
                 if (ok && sp >= 2) {
                     red.ws = static_cast<const float*>(ctx->splitk_ws), red.stride = npix * d->Cout, red.ksplit = sp;
                     red.Cout = d->Cout, red.HW = d->Ho * d->Wo, red.npix = npix;
