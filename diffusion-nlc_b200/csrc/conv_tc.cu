@@ -15,6 +15,11 @@
 // One persistent CTA per SM, 11 warps:  warp 0 = TMA producer of the A (activation) tiles, warp 1 = MMA issuer (one
 // elected thread), warps 2-9 = epilogue (TMEM -> registers -> bias/temb/residual/scale -> fp32 and/or operand-dtype
 // stores), warp 10 = TMA producer of the W (weight) tiles.
+// Epilogue variants (template TEPI): 0 = staged through a per-warp shared-memory block and the load/store unit (any output
+// combination, fp32 / resampled residuals, sub-pixel placement, head merge); 1 = 16-bit output only, through TMA (tensor
+// store of the output block, tensor load of the 16-bit residual block; conv_common.cuh); 2 = the same with 256-bit global
+// accesses from registers.  Small-M launches can split K over several CTAs per tile (ConvKParams.ksplit): the splits write
+// raw accumulators to a workspace and splitk_reduce_kernel (below) applies the epilogue.
 // smem ring of STAGES x (16 KB A + BLOCK_N*128 B W); two TMEM accumulators so the epilogue of tile i
 // overlaps the main loop of tile i+1.
 //
